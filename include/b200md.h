@@ -1,0 +1,217 @@
+/* b200md.h — C ABI of the B200-native Buckingham pair / PPPM / NVE hot path.
+ *
+ * This is the drop-in boundary for the /intel styles of HPAC/lammps-buck-intel: every entry point
+ * names the reference interface (file:line, relative to the reference tree) it replaces.  Plain C,
+ * plain pointers and sizes; no torch / CUDA types.  All functions return 0 on success; on failure they
+ * return a negative B200MD_E* code and b200md_last_error(ctx) holds the message — the same text the
+ * reference passes to error->all()/error->one() where one exists (SURVEY.md §8b "Errors").
+ *
+ * There is no CPU fallback: b200md_ctx_create fails when no sm_100 device is usable.
+ *
+ * Conventions
+ *   - atom types are 1-based; per-type-pair arrays are (ntypes+1)^2 row-major [itype*(ntypes+1)+jtype]
+ *   - host arrays: x,v,f are [n][3] doubles (LAMMPS atom->x[0] layout, fix_nve_intel.cpp:64-66)
+ *   - atoms live in HBM between calls, cell-sorted; "host order" always means the order of the last
+ *     b200md_atoms_upload (LAMMPS local index); downloads un-permute
+ *   - ev[8] = {evdwl, ecoul, v_xx, v_yy, v_zz, v_xy, v_xz, v_yz}  (ev_global, pair_buck_intel.cpp:337-349)
+ *   - eflag bit0 global energy, bit1 per-atom; vflag 1|2 global virial (newton is off on the device, so
+ *     both are evaluated as the per-pair tally, pair_buck_intel.cpp:93-96,312), 4 per-atom (not produced,
+ *     as in the reference: pair_buck_intel.cpp:362)
+ */
+#ifndef B200MD_H
+#define B200MD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200md_ctx b200md_ctx;
+
+enum {
+  B200MD_OK = 0,
+  B200MD_EINVAL = -1,    /* bad argument / call order */
+  B200MD_ECUDA = -2,     /* CUDA runtime error */
+  B200MD_ENODEV = -3,    /* no usable sm_100 device */
+  B200MD_ERANGE = -4,    /* "Out of range atoms - cannot compute PPPM" (pppm_intel.cpp:385) */
+  B200MD_EORDER = -5,    /* "PPPM order greater than supported by USER-INTEL" (pppm_intel.cpp:87-88) */
+  B200MD_ENOMEM = -6,
+  B200MD_EOVERFLOW = -7, /* neighbour storage / box too small for the ghost cutoff */
+  B200MD_ENONFINITE = -8,/* "Non-numeric box dimensions - simulation unstable" (pppm_intel.cpp:342) */
+  B200MD_ECOMM = -9      /* NCCL error */
+};
+
+/* FixIntel::PREC_MODE_* (pair_buck_intel.cpp:50-58).  SINGLE is not provided on the device. */
+enum { B200MD_PREC_DOUBLE = 0, B200MD_PREC_MIXED = 1 };
+
+/* pair styles: PairStyle(buck/intel,…) pair_buck_intel.h:20, buck/coul/cut/intel
+ * pair_buck_coul_cut_intel.h:21, buck/coul/long/intel pair_buck_coul_long_intel.h:20,
+ * buck/long/coul/long/intel pair_buck_long_coul_long_intel.h:20 */
+enum {
+  B200MD_PAIR_BUCK = 0,
+  B200MD_PAIR_BUCK_COUL_CUT = 1,
+  B200MD_PAIR_BUCK_COUL_LONG = 2,
+  B200MD_PAIR_BUCK_LONG_COUL_LONG = 3
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * context  — replaces FixIntel ("package intel … mode double|mixed") + IntelBuffers
+ * ownership (intel_buffers.h:272-312): the context owns every device array. */
+int b200md_ctx_create(int device, int precision, b200md_ctx **out);
+void b200md_ctx_destroy(b200md_ctx *ctx);
+const char *b200md_last_error(const b200md_ctx *ctx); /* ctx may be NULL: last create error */
+int b200md_version(void);
+
+/* units: force->qqrd2e, force->ftm2v (pair_buck_coul_long_intel.cpp:157, fix_nve_intel.cpp:131) */
+int b200md_set_units(b200md_ctx *ctx, double qqrd2e, double ftm2v);
+/* domain->boxlo/boxhi/periodicity (orthogonal boxes; pppm_intel.cpp:153 reads boxlo) */
+int b200md_set_box(b200md_ctx *ctx, const double boxlo[3], const double boxhi[3],
+                   const int periodic[3]);
+
+/* ------------------------------------------------------------------------------------------------
+ * atoms — replaces IntelBuffers::thr_pack (intel_buffers.h:185-203): one upload, then resident.
+ * q may be NULL (atom_style atomic), v may be NULL (zeros).  mass is per type [ntypes+1]. */
+int b200md_atoms_upload(b200md_ctx *ctx, int nlocal, int ntypes, const double *x, const double *v,
+                        const double *q, const int *type, const double *mass);
+/* refresh positions only, host order (the plug-in path: LAMMPS integrates on the host) */
+int b200md_atoms_set_x(b200md_ctx *ctx, const double *x);
+/* any of x,v,f may be NULL; f is [n][3]; eatom [n] (per-atom energy, f[].w of vec3_acc_t,
+ * intel_buffers.h:44) may be NULL */
+int b200md_atoms_download(b200md_ctx *ctx, double *x, double *v, double *f, double *eatom);
+int b200md_atoms_count(const b200md_ctx *ctx, int *nlocal, int *nghost);
+
+/* ------------------------------------------------------------------------------------------------
+ * pair styles — replaces Pair*Intel::init_style + pack_force_const (pair_buck_intel.cpp:367-443,
+ * pair_buck_coul_cut_intel.cpp:431-492, pair_buck_coul_long_intel.cpp:457-566,
+ * pair_buck_long_coul_long_intel.cpp:542-646).  The caller passes what init_one() produced. */
+typedef struct {
+  int style;               /* B200MD_PAIR_* */
+  int ntypes;
+  const double *cutsq;     /* (ntypes+1)^2 each */
+  const double *cut_ljsq;  /* cut_bucksq for long/coul/long */
+  const double *cut_coulsq;/* coul/cut: per pair; coul/long: global value replicated; buck: NULL */
+  const double *buck1, *buck2, *rhoinv, *a, *c, *offset;
+  double special_lj[4], special_coul[4]; /* force->special_* ; [0] forced to 1 as in the reference */
+  double g_ewald;          /* force->kspace->g_ewald (pair_buck_coul_long_intel.cpp:507) */
+  double g_ewald_6;        /* pair_buck_long_coul_long_intel.cpp:267 */
+  int ewald_order;         /* long/coul/long: bit1 = ORDER1, bit6 = ORDER6 (:111-112) */
+  /* Coulomb tables built by Pair::init_tables on the host (pair_buck_coul_long_intel.cpp:531-542);
+   * ncoultablebits = 0 selects the analytic erfc branch (:294-316) */
+  int ncoultablebits, ncoulmask, ncoulshiftbits;
+  double tabinnersq;
+  const double *rtable, *drtable, *ftable, *dftable, *etable, *detable, *ctable, *dctable;
+  /* dispersion tables (pair_buck_long_coul_long_intel.cpp:433-454); 0 bits = analytic (:414-431) */
+  int ndisptablebits, ndispmask, ndispshiftbits;
+  double tabinnerdispsq;
+  const double *rdisptable, *drdisptable, *fdisptable, *dfdisptable, *edisptable, *dedisptable;
+} b200md_pair_params;
+
+int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * neighbour list — replaces the "intel" NeighList request (pair_buck_intel.cpp:370) and
+ * buffers->get_cutneighsq() (:399-409): on-device cell binning, periodic ghost atoms, FULL list with
+ * newton off.  `neighbor skin bin`, `neigh_modify every/delay/check`. */
+int b200md_neigh_setup(b200md_ctx *ctx, double skin, int every, int delay, int check);
+/* wrap atoms (Domain::pbc), sort by cell, make ghosts, build the list (neighbor->build, ago = 0) */
+int b200md_neigh_build(b200md_ctx *ctx);
+/* Neighbor::decide at timestep `ntimestep`; *rebuilt = 1 if a build was done (else ghost positions are
+ * refreshed = Comm::forward_comm) */
+int b200md_neigh_decide(b200md_ctx *ctx, long ntimestep, int *rebuilt);
+/* parity-test access: sizes, then the list in HOST order.  numneigh[nlocal], offsets[nlocal+1],
+ * entries[total]: entry = j | special<<30 with j < nlocal an owned atom (host index) or
+ * j >= nlocal a ghost; ghost_src[nghost] host index of the atom each ghost images, ghost_shift
+ * [nghost][3] its periodic image. */
+int b200md_neigh_stats(b200md_ctx *ctx, long *total_entries, int *nghost, int *max_numneigh,
+                       long *nbuilds);
+int b200md_neigh_download(b200md_ctx *ctx, int *numneigh, long *offsets, int *entries,
+                          int *ghost_src, int *ghost_shift);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pair*Intel::compute(eflag,vflag) — pair_buck_intel.cpp:48-123 / eval<> :127-365,
+ * pair_buck_coul_cut_intel.cpp:134-402, pair_buck_coul_long_intel.cpp:55-453,
+ * pair_buck_long_coul_long_intel.cpp:57-539.  Overwrites the device force array (the step's first
+ * force contribution; force_clear is fused away).  ev may be NULL when eflag == vflag == 0. */
+int b200md_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double ev[8]);
+
+/* The reference eval<> signature itself, host buffers in and out (H2D/D2H inside the call): packed
+ * atoms x[nall][3], type[nall], q[nall] (IntelBuffers::get_x/get_q), CSR list numneigh/cnumneigh/
+ * firstneigh with special bits (intel_buffers.h:145-146), f[nlocal][4] out (vec3_acc_t).  newton off:
+ * the list must be FULL over owned atoms. */
+int b200md_pair_eval_host(b200md_ctx *ctx, int eflag, int vflag, int nlocal, int nall,
+                          const double *x, const int *type, const double *q, const int *numneigh,
+                          const long *cnumneigh, const int *firstneigh, double *f, double ev[8]);
+
+/* ------------------------------------------------------------------------------------------------
+ * PPPM — replaces PPPMIntel::init (pppm_intel.cpp:67-98) + PPPM::setup state and
+ * PPPMIntel::compute (:104-317): particle_map :326-392, make_rho :403-534, brick2fft :642-672,
+ * poisson_ik :811-977 / poisson_ad :986-1054, fieldforce_ik :541-640 / fieldforce_ad :679-804. */
+typedef struct {
+  int nx, ny, nz;        /* nx_pppm … (2^a 3^b 5^c) */
+  int order;             /* <= 7 */
+  double g_ewald;
+  int differentiation;   /* 0 = ik, 1 = ad (kspace_modify diff) */
+  double scale;          /* KSpace::scale, 1.0 */
+  int dispersion;        /* 0: Coulomb ('c', charges); 1: geometric dispersion ('g', weight B[type],
+                            pppm_disp_intel.cpp:245-313 with SURVEY §2.4-2 corrected) */
+  const double *B;       /* dispersion: [ntypes+1] geometric coefficients; else NULL */
+} b200md_pppm_params;
+
+int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p);
+/* forces are ACCUMULATED into the device force array (f +=, pppm_intel.cpp:628-630).
+ * energy / virial[6] may be NULL. */
+int b200md_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double virial[6]);
+/* host-buffer form of PPPMIntel::compute: x[n][3], q[n] in, f[n][3] += out */
+int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const double *x,
+                             const double *q, double *f, double *energy, double virial[6]);
+/* parity-test access (host order x-fastest nfft arrays; any may be NULL) */
+int b200md_pppm_download(b200md_ctx *ctx, double *density_fft, double *greensfn, double *field_x,
+                         double *field_y, double *field_z, double sf_coeff[6]);
+
+/* hand-written 3-D complex FFT used by PPPM, exposed for parity tests (replaces FFT3d::compute,
+ * pppm_intel.cpp:835,903): data = nz*ny*nx interleaved re/im doubles on the HOST, transformed in place;
+ * dir +1 forward exp(-ikx), -1 backward, unnormalised. */
+int b200md_fft3d_host(b200md_ctx *ctx, double *data, int nx, int ny, int nz, int dir);
+
+/* ------------------------------------------------------------------------------------------------
+ * fix nve/intel — FixNVEIntel::initial_integrate / final_integrate / reset_dt
+ * (fix_nve_intel.cpp:60-99, 103-127, 129-194), group all, per-type mass. */
+int b200md_nve_setup(b200md_ctx *ctx, double dt);
+int b200md_nve_initial_integrate(b200md_ctx *ctx);
+int b200md_nve_final_integrate(b200md_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Verlet::run on the device: nsteps of initial_integrate -> decide/build|forward ->
+ * pair -> kspace -> final_integrate with atoms resident.  Thermo-style energies are evaluated on the
+ * last step when thermo != NULL: thermo[0..7] = pair ev, [8] = kspace energy, [9..14] kspace virial,
+ * [15] = kinetic energy (sum 1/2 m v^2, mass units). */
+int b200md_run(b200md_ctx *ctx, long nsteps, double *thermo /*16 or NULL*/);
+/* forces only (setup phase of a run: build + pair + kspace), energies in thermo like b200md_run */
+int b200md_setup_forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo);
+
+/* per-phase device timers (the HPAC_TIMING / fix->start_watch hooks, pppm_intel.cpp:113-123,
+ * pair_buck_intel.cpp:80,356-359): accumulated CUDA-event ms since the last reset.
+ * names: see b200md_timer_name(i), i < b200md_timer_count(). */
+int b200md_timers_enable(b200md_ctx *ctx, int on);
+int b200md_timers_get(b200md_ctx *ctx, double *ms, long *calls, int n);
+int b200md_timers_reset(b200md_ctx *ctx);
+int b200md_timer_count(void);
+const char *b200md_timer_name(int i);
+/* number of kernels this library launched since ctx creation (bench.py's gpu_launches) */
+long b200md_launch_count(const b200md_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * multi-GPU: one process per GPU, z-slab spatial decomposition of atoms and of the PPPM
+ * grid.  Replaces Comm::borders/forward_comm (atom halo), GridComm, Remap and FFT3d transposes, and the
+ * two MPI_Allreduce calls of pppm_intel.cpp:260,273.  nccl_unique_id is the 128-byte ncclUniqueId
+ * produced by b200md_comm_unique_id on rank 0 and broadcast by the host (torch.distributed / MPI). */
+int b200md_comm_unique_id(void *id128);
+int b200md_comm_init(b200md_ctx *ctx, int rank, int nranks, const void *id128);
+int b200md_comm_finalize(b200md_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,437 @@
+"""b200md — Python (ctypes) binding of the C ABI in include/b200md.h.
+
+This is the harness-side mirror of the reference's plug-in surface: thin wrappers named after the reference
+classes (`PairBuck*Intel.compute`, `PPPMIntel.compute`, `FixNVEIntel`) over the C entry points.  It holds no
+compute: every number comes from libb200md.so (hand-written sm_100a kernels).  There is no CPU fallback —
+`load()` raises if the library is missing, and `Context()` raises if no B200 is visible.
+
+The directory name contains a hyphen, so import it through `__graft_entry__.load_package()` (or
+tests/conftest.py), which registers it as the module `lammps_buck_intel_b200`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIBPATH = os.path.join(HERE, "libb200md.so")
+CSRC = os.path.join(HERE, "csrc")
+HEADER = os.path.join(ROOT, "include", "b200md.h")
+
+PREC_DOUBLE, PREC_MIXED = 0, 1
+PAIR_BUCK, PAIR_BUCK_COUL_CUT, PAIR_BUCK_COUL_LONG, PAIR_BUCK_LONG_COUL_LONG = 0, 1, 2, 3
+SBBITS = 30
+NEIGHMASK = 0x3FFFFFFF
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+lp = C.POINTER(C.c_long)
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build(force=False, verbose=False):
+    """nvcc -> lammps-buck-intel_b200/libb200md.so (in-tree, so it travels to the GPU box)."""
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [HEADER]
+    stale = force or not os.path.exists(LIBPATH) or any(os.path.getmtime(d) > os.path.getmtime(LIBPATH) for d in deps)
+    if not stale:
+        return LIBPATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIBPATH] + sources() + extra_link_flags()
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIBPATH
+
+
+def extra_link_flags():
+    return []
+
+
+class PairParams(C.Structure):
+    _fields_ = [
+        ("style", C.c_int), ("ntypes", C.c_int),
+        ("cutsq", dp), ("cut_ljsq", dp), ("cut_coulsq", dp),
+        ("buck1", dp), ("buck2", dp), ("rhoinv", dp), ("a", dp), ("c", dp), ("offset", dp),
+        ("special_lj", C.c_double * 4), ("special_coul", C.c_double * 4),
+        ("g_ewald", C.c_double), ("g_ewald_6", C.c_double), ("ewald_order", C.c_int),
+        ("ncoultablebits", C.c_int), ("ncoulmask", C.c_int), ("ncoulshiftbits", C.c_int),
+        ("tabinnersq", C.c_double),
+        ("rtable", dp), ("drtable", dp), ("ftable", dp), ("dftable", dp),
+        ("etable", dp), ("detable", dp), ("ctable", dp), ("dctable", dp),
+        ("ndisptablebits", C.c_int), ("ndispmask", C.c_int), ("ndispshiftbits", C.c_int),
+        ("tabinnerdispsq", C.c_double),
+        ("rdisptable", dp), ("drdisptable", dp), ("fdisptable", dp), ("dfdisptable", dp),
+        ("edisptable", dp), ("dedisptable", dp),
+    ]
+
+
+class PppmParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("order", C.c_int),
+                ("g_ewald", C.c_double), ("differentiation", C.c_int), ("scale", C.c_double),
+                ("dispersion", C.c_int), ("B", dp)]
+
+
+_lib = None
+
+
+def load():
+    """Load libb200md.so; fail loudly if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise RuntimeError("libb200md.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(LIBPATH, mode=C.RTLD_GLOBAL)
+    lib.b200md_last_error.restype = C.c_char_p
+    lib.b200md_last_error.argtypes = [C.c_void_p]
+    lib.b200md_timer_name.restype = C.c_char_p
+    lib.b200md_launch_count.restype = C.c_long
+    lib.b200md_launch_count.argtypes = [C.c_void_p]
+    lib.b200md_ctx_destroy.argtypes = [C.c_void_p]
+    lib.b200md_ctx_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+class B200MDError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200md error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+def _d(a):
+    return a.ctypes.data_as(dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(ip) if a is not None else None
+
+
+def _l(a):
+    return a.ctypes.data_as(lp) if a is not None else None
+
+
+def f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side parameter logic of the stock base classes (PairBuck*::init_one, Pair::init_tables)
+
+def pair_coeffs(style, ntypes, A, rho, Cc, cut_lj, cut_coul=None, offset_flag=0):
+    """init_one for every type pair -> dict of (ntypes+1)^2 arrays the C ABI takes."""
+    tp1 = ntypes + 1
+
+    def full(v):
+        v = np.asarray(v, dtype=np.float64)
+        return np.full((tp1, tp1), float(v)) if v.ndim == 0 else v.reshape(tp1, tp1).copy()
+
+    A, rho, Cc, cut_lj = full(A), full(rho), full(Cc), full(cut_lj)
+    cut_coul = full(cut_coul) if cut_coul is not None else np.zeros((tp1, tp1))
+    rho = np.where(rho == 0.0, 1.0, rho)
+    out = dict(a=A, c=Cc, rhoinv=1.0 / rho, buck1=A / rho, buck2=6.0 * Cc)
+    cl = np.where(cut_lj > 0, cut_lj, 1.0)
+    out["offset"] = (A * np.exp(-cl / rho) - Cc / cl ** 6) if offset_flag else np.zeros((tp1, tp1))
+    out["cut_ljsq"] = cut_lj * cut_lj
+    out["cut_coulsq"] = cut_coul * cut_coul
+    cut = cut_lj if style == PAIR_BUCK else np.maximum(cut_lj, cut_coul)
+    out["cutsq"] = cut * cut
+    for k in out:
+        out[k][0, :] = 0.0
+        out[k][:, 0] = 0.0
+        out[k] = np.ascontiguousarray(out[k])
+    return out
+
+
+def init_coul_tables(cut_coul, g_ewald, qqrd2e, nbits=12, tabinner=np.sqrt(2.0)):
+    """Pair::init_bitmap + Pair::init_tables (no rRESPA, no MSM) -> (tables dict, mask, shift, tabinnersq)."""
+    from math import erfc as _erfc
+    EWALD_F = 1.12837917
+    inner, outer = float(tabinner), float(cut_coul)
+    nlowermin = 1
+    while not (2.0 ** nlowermin <= inner * inner < 2.0 ** (nlowermin + 1)):
+        nlowermin += 1 if 2.0 ** nlowermin <= inner * inner else -1
+    nexpbits = 0
+    required = outer * outer / 2.0 ** nlowermin
+    available = 2.0
+    while available < required:
+        nexpbits += 1
+        available = 2.0 ** (2.0 ** nexpbits)
+    nmantbits = nbits - nexpbits
+    nshiftbits = 24 - (nmantbits + 1)
+    nmask = (1 << (nbits + nshiftbits)) - 1
+    f2i = lambda f: int(np.float32(f).view(np.int32))
+    i2f = lambda i: float(np.int32(i).view(np.float32))
+    maskhi = f2i(outer * outer) & ~nmask
+    masklo = f2i(inner * inner) & ~nmask
+    ntable = 1 << nbits
+    tabinnersq = inner * inner
+    t = {k: np.zeros(ntable) for k in ("r", "dr", "f", "df", "e", "de", "c", "dc")}
+    minrsq = i2f(maskhi)
+    for i in range(ntable):
+        bits = (i << nshiftbits) | masklo
+        if i2f(bits) < tabinnersq:
+            bits = (i << nshiftbits) | maskhi
+        rsq = i2f(bits)
+        r = float(np.sqrt(np.float32(rsq)))
+        grij = g_ewald * r
+        expm2 = np.exp(-grij * grij)
+        derfc = _erfc(grij)
+        t["r"][i] = rsq
+        t["c"][i] = qqrd2e / r
+        t["f"][i] = qqrd2e / r * (derfc + EWALD_F * grij * expm2)
+        t["e"][i] = qqrd2e / r * derfc
+        minrsq = min(minrsq, rsq)
+    tabinnersq = minrsq
+    for a, b in (("dr", "r"), ("df", "f"), ("dc", "c"), ("de", "e")):
+        nxt = np.roll(t[b], -1)
+        t[a] = (1.0 / (nxt - t[b])) if a == "dr" else (nxt - t[b])
+    itablemin = (f2i(minrsq) & nmask) >> nshiftbits
+    itablemax = itablemin - 1 if itablemin != 0 else ntable - 1
+    top = i2f((itablemax << nshiftbits) | maskhi)
+    cut_coulsq = cut_coul * cut_coul
+    if top < cut_coulsq:
+        rsq = float(np.float32(cut_coulsq))
+        r = float(np.sqrt(np.float32(rsq)))
+        grij = g_ewald * r
+        expm2 = np.exp(-grij * grij)
+        derfc = _erfc(grij)
+        t["dr"][itablemax] = 1.0 / (rsq - t["r"][itablemax])
+        t["df"][itablemax] = qqrd2e / r * (derfc + EWALD_F * grij * expm2) - t["f"][itablemax]
+        t["dc"][itablemax] = qqrd2e / r - t["c"][itablemax]
+        t["de"][itablemax] = qqrd2e / r * derfc - t["e"][itablemax]
+    for k in t:
+        t[k] = np.ascontiguousarray(t[k])
+    return t, nmask, nshiftbits, tabinnersq
+
+
+class Context:
+    """One device context (= FixIntel + IntelBuffers + the resident atom state)."""
+
+    def __init__(self, device=0, precision=PREC_DOUBLE):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.b200md_ctx_create(C.c_int(device), C.c_int(precision), C.byref(h))
+        if rc != 0:
+            raise B200MDError(rc, self.lib.b200md_last_error(None).decode())
+        self.h = h
+        self.precision = precision
+        self.nlocal = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200md_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise B200MDError(rc, self.lib.b200md_last_error(self.h).decode())
+
+    # ---- setup ---------------------------------------------------------------------------------
+    def set_units(self, qqrd2e, ftm2v):
+        self._ck(self.lib.b200md_set_units(self.h, C.c_double(qqrd2e), C.c_double(ftm2v)))
+
+    def set_box(self, boxlo, boxhi, periodic=(1, 1, 1)):
+        self._ck(self.lib.b200md_set_box(self.h, _d(f64(boxlo)), _d(f64(boxhi)), _i(i32(periodic))))
+
+    def atoms_upload(self, x, type_, mass, v=None, q=None):
+        x = f64(x); v = f64(v); q = f64(q); type_ = i32(type_); mass = f64(mass)
+        self.nlocal = len(x)
+        self._ck(self.lib.b200md_atoms_upload(self.h, C.c_int(len(x)), C.c_int(len(mass) - 1), _d(x), _d(v), _d(q),
+                                              _i(type_), _d(mass)))
+
+    def atoms_set_x(self, x):
+        self._ck(self.lib.b200md_atoms_set_x(self.h, _d(f64(x))))
+
+    def atoms_download(self, want=("x", "v", "f")):
+        n = self.nlocal
+        out = {k: np.zeros((n, 3)) for k in want if k in ("x", "v", "f")}
+        if "eatom" in want:
+            out["eatom"] = np.zeros(n)
+        self._ck(self.lib.b200md_atoms_download(self.h, _d(out.get("x")), _d(out.get("v")), _d(out.get("f")),
+                                                _d(out.get("eatom"))))
+        return out
+
+    def pair_setup(self, style, ntypes, coeffs, special_lj=(1, 0, 0, 0), special_coul=(1, 0, 0, 0), g_ewald=0.0,
+                   g_ewald_6=0.0, ewald_order=0, coul_tables=None, disp_tables=None):
+        p = PairParams()
+        p.style, p.ntypes = style, ntypes
+        keep = {k: f64(v) for k, v in coeffs.items()}
+        for k in ("cutsq", "cut_ljsq", "cut_coulsq", "buck1", "buck2", "rhoinv", "a", "c", "offset"):
+            setattr(p, k, _d(keep[k]))
+        for i in range(4):
+            p.special_lj[i] = special_lj[i]
+            p.special_coul[i] = special_coul[i]
+        p.g_ewald, p.g_ewald_6, p.ewald_order = g_ewald, g_ewald_6, ewald_order
+        if coul_tables is not None:
+            t, mask, shift, inner = coul_tables
+            t = {k: f64(v) for k, v in t.items()}
+            keep["ct"] = t
+            p.ncoultablebits = int(np.log2(len(t["r"])))
+            p.ncoulmask, p.ncoulshiftbits, p.tabinnersq = mask, shift, inner
+            p.rtable, p.drtable, p.ftable, p.dftable = _d(t["r"]), _d(t["dr"]), _d(t["f"]), _d(t["df"])
+            p.etable, p.detable, p.ctable, p.dctable = _d(t["e"]), _d(t["de"]), _d(t["c"]), _d(t["dc"])
+        if disp_tables is not None:
+            t, mask, shift, inner = disp_tables
+            t = {k: f64(v) for k, v in t.items()}
+            keep["dt"] = t
+            p.ndisptablebits = int(np.log2(len(t["r"])))
+            p.ndispmask, p.ndispshiftbits, p.tabinnerdispsq = mask, shift, inner
+            p.rdisptable, p.drdisptable, p.fdisptable, p.dfdisptable = _d(t["r"]), _d(t["dr"]), _d(t["f"]), _d(t["df"])
+            p.edisptable, p.dedisptable = _d(t["e"]), _d(t["de"])
+        self._ck(self.lib.b200md_pair_setup(self.h, C.byref(p)))
+
+    def neigh_setup(self, skin, every=1, delay=0, check=1):
+        self._ck(self.lib.b200md_neigh_setup(self.h, C.c_double(skin), C.c_int(every), C.c_int(delay), C.c_int(check)))
+
+    def neigh_build(self):
+        self._ck(self.lib.b200md_neigh_build(self.h))
+
+    def neigh_decide(self, ntimestep=0):
+        r = C.c_int(0)
+        self._ck(self.lib.b200md_neigh_decide(self.h, C.c_long(ntimestep), C.byref(r)))
+        return r.value
+
+    def neigh_stats(self):
+        tot, ng, mx, nb = C.c_long(), C.c_int(), C.c_int(), C.c_long()
+        self._ck(self.lib.b200md_neigh_stats(self.h, C.byref(tot), C.byref(ng), C.byref(mx), C.byref(nb)))
+        return dict(total=tot.value, nghost=ng.value, max_numneigh=mx.value, nbuilds=nb.value)
+
+    def neigh_download(self):
+        st = self.neigh_stats()
+        n = self.nlocal
+        numneigh = np.zeros(n, np.int32)
+        offsets = np.zeros(n + 1, np.int64)
+        entries = np.zeros(max(st["total"], 1), np.int32)
+        gsrc = np.zeros(max(st["nghost"], 1), np.int32)
+        gshift = np.zeros((max(st["nghost"], 1), 3), np.int32)
+        self._ck(self.lib.b200md_neigh_download(self.h, _i(numneigh), _l(offsets), _i(entries), _i(gsrc), _i(gshift)))
+        return numneigh, offsets, entries[:st["total"]], gsrc[:st["nghost"]], gshift[:st["nghost"]]
+
+    # ---- Pair*Intel::compute --------------------------------------------------------------------
+    def pair_compute(self, eflag=0, vflag=0):
+        ev = np.zeros(8)
+        self._ck(self.lib.b200md_pair_compute(self.h, C.c_int(eflag), C.c_int(vflag), _d(ev)))
+        return ev
+
+    def pair_eval_host(self, eflag, vflag, nlocal, x, type_, q, numneigh, cnumneigh, firstneigh):
+        x = f64(x); type_ = i32(type_); q = f64(q)
+        f = np.zeros((nlocal, 4))
+        ev = np.zeros(8)
+        self._ck(self.lib.b200md_pair_eval_host(self.h, C.c_int(eflag), C.c_int(vflag), C.c_int(nlocal),
+                                                C.c_int(len(x)), _d(x), _i(type_), _d(q), _i(i32(numneigh)),
+                                                _l(np.ascontiguousarray(cnumneigh, np.int64)), _i(i32(firstneigh)),
+                                                _d(f), _d(ev)))
+        return f, ev
+
+    # ---- PPPMIntel --------------------------------------------------------------------------------
+    def pppm_setup(self, nx, ny, nz, order, g_ewald, differentiation=0, scale=1.0, dispersion=0, B=None):
+        p = PppmParams()
+        p.nx, p.ny, p.nz, p.order, p.g_ewald = nx, ny, nz, order, g_ewald
+        p.differentiation, p.scale, p.dispersion = differentiation, scale, dispersion
+        Bk = f64(B)
+        p.B = _d(Bk)
+        self._ck(self.lib.b200md_pppm_setup(self.h, C.byref(p)))
+        self.pppm_grid = (nx, ny, nz)
+
+    def pppm_compute(self, eflag=0, vflag=0):
+        e = C.c_double(0.0)
+        v = np.zeros(6)
+        self._ck(self.lib.b200md_pppm_compute(self.h, C.c_int(eflag), C.c_int(vflag), C.byref(e), _d(v)))
+        return e.value, v
+
+    def pppm_compute_host(self, x, q, eflag=0, vflag=0):
+        x = f64(x); q = f64(q)
+        f = np.zeros((len(x), 3))
+        e = C.c_double(0.0)
+        v = np.zeros(6)
+        self._ck(self.lib.b200md_pppm_compute_host(self.h, C.c_int(eflag), C.c_int(vflag), C.c_int(len(x)), _d(x),
+                                                   _d(q), _d(f), C.byref(e), _d(v)))
+        return f, e.value, v
+
+    def pppm_download(self):
+        nx, ny, nz = self.pppm_grid
+        n = nx * ny * nz
+        out = dict(density=np.zeros(n), greensfn=np.zeros(n), fx=np.zeros(n), fy=np.zeros(n), fz=np.zeros(n),
+                   sf_coeff=np.zeros(6))
+        self._ck(self.lib.b200md_pppm_download(self.h, _d(out["density"]), _d(out["greensfn"]), _d(out["fx"]),
+                                               _d(out["fy"]), _d(out["fz"]), _d(out["sf_coeff"])))
+        return out
+
+    def fft3d(self, a, direction):
+        a = np.ascontiguousarray(a, dtype=np.complex128).copy()
+        nz, ny, nx = a.shape
+        self._ck(self.lib.b200md_fft3d_host(self.h, a.ctypes.data_as(dp), C.c_int(nx), C.c_int(ny), C.c_int(nz),
+                                            C.c_int(direction)))
+        return a
+
+    # ---- FixNVEIntel / Verlet -----------------------------------------------------------------------
+    def nve_setup(self, dt):
+        self._ck(self.lib.b200md_nve_setup(self.h, C.c_double(dt)))
+
+    def nve_initial_integrate(self):
+        self._ck(self.lib.b200md_nve_initial_integrate(self.h))
+
+    def nve_final_integrate(self):
+        self._ck(self.lib.b200md_nve_final_integrate(self.h))
+
+    def setup_forces(self, eflag=1, vflag=1):
+        th = np.zeros(16)
+        self._ck(self.lib.b200md_setup_forces(self.h, C.c_int(eflag), C.c_int(vflag), _d(th)))
+        return th
+
+    def run(self, nsteps, thermo=False):
+        th = np.zeros(16) if thermo else None
+        self._ck(self.lib.b200md_run(self.h, C.c_long(nsteps), _d(th)))
+        return th
+
+    # ---- timers -------------------------------------------------------------------------------------
+    def timers_enable(self, on=True):
+        self._ck(self.lib.b200md_timers_enable(self.h, C.c_int(1 if on else 0)))
+
+    def timers_reset(self):
+        self._ck(self.lib.b200md_timers_reset(self.h))
+
+    def timers(self):
+        n = self.lib.b200md_timer_count()
+        ms = np.zeros(n)
+        calls = np.zeros(n, np.int64)
+        self._ck(self.lib.b200md_timers_get(self.h, _d(ms), _l(calls), C.c_int(n)))
+        return {self.lib.b200md_timer_name(C.c_int(i)).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
+
+    def launch_count(self):
+        return int(self.lib.b200md_launch_count(self.h))
+
+
+def make_context(system, precision=PREC_DOUBLE, device=0):
+    """Context with units, box and atoms of a workloads.* system dict."""
+    from . import workloads as W  # noqa: F401  (resolved through the registered package name)
+    u = W.UNITS[system["units"]]
+    ctx = Context(device, precision)
+    ctx.set_units(u["qqrd2e"], u["ftm2v"])
+    ctx.set_box(system["boxlo"], system["boxhi"])
+    ctx.atoms_upload(system["x"], system["type"], system["mass"], v=system.get("v"), q=system.get("q"))
+    return ctx

@@ -1,0 +1,224 @@
+// internal.h — device context shared by the kernels behind include/b200md.h.
+//
+// HBM layout (all arrays device-resident, capacity-grown, never shrunk):
+//   xq   double4[nall]   {x,y,z,q}      owned atoms [0,nlocal) sorted by neighbour bin, then ghosts
+//                                       [nlocal,nall) sorted by bin — one 32 B sector per gathered j
+//   xqf  float4[nall]    same, float    mixed mode only (IntelBuffers<float,double>::atom_t, q folded in)
+//   type int[nall]
+//   v    double4[nlocal] {vx,vy,vz,dtf/m}
+//   f    double4[nlocal] {fx,fy,fz,eatom}   (vec3_acc_t, intel_buffers.h:44)
+//   tag  int[nlocal]     host index of each sorted atom
+//   neighbour list: numneigh int[nlocal], offsets int64[nlocal+1], entries int[total] (CSR, rows in
+//   stencil order — the firstneigh/cnumneigh/numneigh triple of intel_buffers.h:145-146)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b200md.h"
+
+#define B2_SBBITS 30
+#define B2_NEIGHMASK 0x3FFFFFFF
+#define B2_MAXTYPES 8       // (ntypes+1) <= 9 rows staged in shared memory
+#define B2_MAXORDER 7
+
+enum TimerId {
+  T_NEIGH = 0, T_COMM, T_PAIR, T_MAKE_RHO, T_FFT, T_POISSON, T_FIELDFORCE, T_NVE, T_OTHER, T_COUNT
+};
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  int reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return 0;
+    size_t ncap = n + n / 8 + 64;
+    T *np = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np, ncap * sizeof(T));
+    if (e != cudaSuccess) return -1;
+    if (keep && p && cap) cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+    p = np;
+    cap = ncap;
+    return 0;
+  }
+  void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PairCoeff {  // one (itype,jtype) entry, flt_t-converted on the host at setup
+  double cutsq, cut_ljsq, cut_coulsq, buck1, buck2, rhoinv, a, c, offset;
+};
+
+struct PairState {
+  bool ready = false;
+  b200md_pair_params p{};     // scalars only; pointers are not kept
+  int tp1 = 0;
+  DevBuf<double> coeff_d;     // [tp1*tp1][9] doubles
+  DevBuf<float> coeff_f;      // same in float (mixed)
+  DevBuf<double> cutneighsq;  // [tp1*tp1] (flt_t-rounded values stored as double)
+  std::vector<double> h_cutsq;
+  double cutmax = 0.0;        // max cut over type pairs
+  // tables: 8 arrays of 2^bits (double and float copies)
+  DevBuf<double> ctab_d;      // [ntable][8] {r,dr,f,df,e,de,c,dc}
+  DevBuf<float> ctab_f;
+  DevBuf<double> dtab_d;      // dispersion [ntable][6] {r,dr,f,df,e,de}
+  DevBuf<float> dtab_f;
+};
+
+struct NeighState {
+  bool ready = false;
+  double skin = 0.3;
+  int every = 1, delay = 0, check = 1;
+  long last_build = -1, nbuilds = 0;
+  double cutneighmax = 0, cutghost = 0;
+  // bins
+  int nbin[3] = {0, 0, 0}, mshell[3] = {0, 0, 0}, mbin[3] = {0, 0, 0};
+  double bininv[3] = {0, 0, 0};
+  long nbins_tot = 0;
+  DevBuf<int> bin_of, bin_sorted;  // per atom: bin id before / after the sort
+  DevBuf<int> bin_count, bin_start, bin_end, bin_cursor;
+  DevBuf<int> perm;           // scratch permutation
+  DevBuf<int> ghost_src;      // [nghost] owned index (sorted order)
+  DevBuf<int> ghost_shift;    // [nghost] packed (sx+1) + 3*(sy+1) + 9*(sz+1)
+  DevBuf<int> ghost_cnt, goff, gsrc_tmp, gshift_tmp, gbin, gperm;  // scratch
+  int ago = 0;                // steps since the last build (Neighbor::ago)
+  DevBuf<int> numneigh;
+  DevBuf<long long> offsets;
+  DevBuf<int> entries;
+  long long total_entries = 0;
+  int max_numneigh = 0;
+  DevBuf<double4> xhold;      // positions at last build (owned)
+  DevBuf<int> flags;          // device flags: [0] displacement trigger, [1] errors
+  DevBuf<unsigned char> scan_ws;
+  // scratch for permuting
+  DevBuf<double4> tmp4a, tmp4b;
+  DevBuf<int> tmpi_a, tmpi_b;
+};
+
+struct PppmState;  // pppm.cu
+struct CommState;  // comm.cu
+
+struct b200md_ctx {
+  int device = 0;
+  int prec = B200MD_PREC_DOUBLE;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  double qqrd2e = 1.0, ftm2v = 1.0;
+  double boxlo[3] = {0, 0, 0}, boxhi[3] = {1, 1, 1}, prd[3] = {1, 1, 1};
+  int periodic[3] = {1, 1, 1};
+  bool box_set = false;
+
+  int nlocal = 0, nghost = 0, ntypes = 0;
+  bool has_q = false;
+  std::vector<double> mass;
+  DevBuf<double4> xq, v, f;
+  DevBuf<float4> xqf;
+  DevBuf<int> type, tag, inv_tag;
+  DevBuf<double> stage;       // staging for host transfers
+  double *h_pinned = nullptr; // small pinned scratch (ev partial results, flags)
+  size_t h_pinned_bytes = 0;
+
+  PairState pair;
+  NeighState neigh;
+  PppmState *pppm = nullptr;
+  CommState *comm = nullptr;
+
+  // nve
+  double dt = 0.0, dtv = 0.0, dtf = 0.0;
+  bool nve_ready = false;
+  long ntimestep = 0;
+
+  // ev reduction scratch
+  DevBuf<double> ev_partial;  // [nblocks][8]
+  DevBuf<double> ev_out;      // [32]
+
+  // timers
+  bool timers_on = false;
+  double t_ms[T_COUNT] = {0};
+  long t_calls[T_COUNT] = {0};
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  long launches = 0;
+};
+
+// ---- error helpers ---------------------------------------------------------------------------
+int b2_fail(b200md_ctx *ctx, int code, const char *fmt, ...);
+#define CUDA_OK(ctx, call)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return b2_fail(ctx, B200MD_ECUDA, "%s failed: %s (%s:%d)", #call,                     \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                          \
+  } while (0)
+#define KERNEL_OK(ctx, name)                                                                \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return b2_fail(ctx, B200MD_ECUDA, "launch of %s failed: %s", name,                    \
+                     cudaGetErrorString(e__));                                              \
+  } while (0)
+#define RESERVE(ctx, buf, n)                                                                \
+  do {                                                                                      \
+    if ((buf).reserve((size_t)(n), false, (ctx)->stream))                                   \
+      return b2_fail(ctx, B200MD_ENOMEM, "out of device memory reserving %s (%zu elements)", \
+                     #buf, (size_t)(n));                                                    \
+  } while (0)
+#define RESERVE_KEEP(ctx, buf, n)                                                           \
+  do {                                                                                      \
+    if ((buf).reserve((size_t)(n), true, (ctx)->stream))                                    \
+      return b2_fail(ctx, B200MD_ENOMEM, "out of device memory reserving %s (%zu elements)", \
+                     #buf, (size_t)(n));                                                    \
+  } while (0)
+#define TRY(expr)                    \
+  do {                               \
+    int rc__ = (expr);               \
+    if (rc__ != 0) return rc__;      \
+  } while (0)
+
+struct ScopedTimer {
+  b200md_ctx *c;
+  int id;
+  ScopedTimer(b200md_ctx *ctx, int id_) : c(ctx), id(id_) {
+    if (c->timers_on) cudaEventRecord(c->ev_a, c->stream);
+  }
+  ~ScopedTimer() {
+    if (c->timers_on) {
+      cudaEventRecord(c->ev_b, c->stream);
+      cudaEventSynchronize(c->ev_b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+      c->t_ms[id] += ms;
+      c->t_calls[id]++;
+    }
+  }
+};
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- cross-file internals ----------------------------------------------------------------------
+// scan.cu
+size_t b2_scan_ws_bytes(size_t n);
+int b2_exclusive_scan_i32(b200md_ctx *ctx, const int *in, int *out, size_t n, void *ws);            // out[n] = total
+int b2_exclusive_scan_i32_i64(b200md_ctx *ctx, const int *in, long long *out, size_t n, void *ws);  // out[n] = total
+// atoms.cu
+int b2_refresh_float_copy(b200md_ctx *ctx, int first, int count);
+// neigh.cu
+int b2_ghost_refresh(b200md_ctx *ctx);
+int b2_neigh_build(b200md_ctx *ctx);
+int b2_neigh_check_trigger(b200md_ctx *ctx, int *trigger);
+// pair.cu
+int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev);
+// pppm.cu
+int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial);
+void b2_pppm_free(b200md_ctx *ctx);
+// nve.cu
+int b2_nve_initial(b200md_ctx *ctx);
+int b2_nve_final(b200md_ctx *ctx);
+int b2_kinetic_energy(b200md_ctx *ctx, double *ke);
+// comm.cu
+void b2_comm_free(b200md_ctx *ctx);

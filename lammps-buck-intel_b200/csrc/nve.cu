@@ -1,0 +1,202 @@
+// nve.cu — fix nve/intel on the device, plus the resident Verlet loop.
+//
+// Replaces FixNVEIntel::initial_integrate / final_integrate / reset_dt (fix_nve_intel.cpp:60-99,
+// 103-127, 129-194; group all, per-type mass) and the stock Verlet::run order the reference plugs into
+// (SURVEY.md §3.1, App. A.6).  The arithmetic is un-fused (mul then add), like the reference's AVX build,
+// so x and v are bit-identical to the CPU oracle step for step given identical forces.
+// dtf/mass rides in v.w; the mixed-mode float copy of the positions (IntelBuffers::thr_pack,
+// intel_buffers.h:185-203) is written by the same kernel instead of a separate pack pass.
+#include "internal.h"
+
+namespace {
+
+__global__ void k_nve_set_dtfm(int n, const int *__restrict__ type, const double *__restrict__ mass, double dtf,
+                               double4 *__restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 vi = v[i];
+  vi.w = dtf / mass[type[i]];
+  v[i] = vi;
+}
+
+__global__ void k_nve_initial(int n, double dtv, double4 *__restrict__ xq, double4 *__restrict__ v,
+                              const double4 *__restrict__ f, float4 *__restrict__ xqf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 vi = v[i];
+  const double4 fi = f[i];
+  double4 xi = xq[i];
+  vi.x = __dadd_rn(vi.x, __dmul_rn(vi.w, fi.x));
+  vi.y = __dadd_rn(vi.y, __dmul_rn(vi.w, fi.y));
+  vi.z = __dadd_rn(vi.z, __dmul_rn(vi.w, fi.z));
+  xi.x = __dadd_rn(xi.x, __dmul_rn(dtv, vi.x));
+  xi.y = __dadd_rn(xi.y, __dmul_rn(dtv, vi.y));
+  xi.z = __dadd_rn(xi.z, __dmul_rn(dtv, vi.z));
+  v[i] = vi;
+  xq[i] = xi;
+  if (xqf) xqf[i] = make_float4((float)xi.x, (float)xi.y, (float)xi.z, (float)xi.w);
+}
+
+__global__ void k_nve_final(int n, double4 *__restrict__ v, const double4 *__restrict__ f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 vi = v[i];
+  const double4 fi = f[i];
+  vi.x = __dadd_rn(vi.x, __dmul_rn(vi.w, fi.x));
+  vi.y = __dadd_rn(vi.y, __dmul_rn(vi.w, fi.y));
+  vi.z = __dadd_rn(vi.z, __dmul_rn(vi.w, fi.z));
+  v[i] = vi;
+}
+
+// sum 1/2 m v^2: per-block partials in a fixed order, reduced by one block
+__global__ void __launch_bounds__(256) k_ke_partial(int n, const double4 *__restrict__ v, const int *__restrict__ type,
+                                                    const double *__restrict__ mass, double *__restrict__ partial) {
+  __shared__ double s[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = 0.0;
+  if (i < n) {
+    const double4 vi = v[i];
+    a = 0.5 * mass[type[i]] * (vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
+  }
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+__global__ void __launch_bounds__(256) k_sum1(int n, const double *__restrict__ partial, double *__restrict__ out) {
+  __shared__ double s[256];
+  double a = 0.0;
+  for (int r = threadIdx.x; r < n; r += 256) a += partial[r];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+}  // namespace
+
+static int upload_mass(b200md_ctx *ctx, double **dmass) {
+  // mass table sits behind ev_out (ev_out[16..32))
+  RESERVE(ctx, ctx->ev_out, 32);
+  if ((int)ctx->mass.size() > 16) return b2_fail(ctx, B200MD_EINVAL, "too many atom types");
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->ev_out.p + 16, ctx->mass.data(), ctx->mass.size() * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  *dmass = ctx->ev_out.p + 16;
+  return 0;
+}
+
+int b2_nve_initial(b200md_ctx *ctx) {
+  if (!ctx->nve_ready) return b2_fail(ctx, B200MD_EINVAL, "nve integrate before b200md_nve_setup");
+  ScopedTimer tm(ctx, T_NVE);
+  if (ctx->nlocal == 0) return 0;
+  k_nve_initial<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(
+      ctx->nlocal, ctx->dtv, ctx->xq.p, ctx->v.p, ctx->f.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr);
+  KERNEL_OK(ctx, "k_nve_initial");
+  return 0;
+}
+
+int b2_nve_final(b200md_ctx *ctx) {
+  if (!ctx->nve_ready) return b2_fail(ctx, B200MD_EINVAL, "nve integrate before b200md_nve_setup");
+  ScopedTimer tm(ctx, T_NVE);
+  if (ctx->nlocal == 0) return 0;
+  k_nve_final<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->f.p);
+  KERNEL_OK(ctx, "k_nve_final");
+  return 0;
+}
+
+int b2_kinetic_energy(b200md_ctx *ctx, double *ke) {
+  *ke = 0.0;
+  if (ctx->nlocal == 0) return 0;
+  double *dmass;
+  TRY(upload_mass(ctx, &dmass));
+  const int nb = cdiv(ctx->nlocal, 256);
+  RESERVE(ctx, ctx->ev_partial, (size_t)nb);
+  k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->type.p, dmass, ctx->ev_partial.p);
+  KERNEL_OK(ctx, "k_ke_partial");
+  k_sum1<<<1, 256, 0, ctx->stream>>>(nb, ctx->ev_partial.p, ctx->ev_out.p + 8);
+  KERNEL_OK(ctx, "k_sum1");
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->ev_out.p + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *ke = ctx->h_pinned[0];
+  return 0;
+}
+
+static int forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo) {
+  double ev[8] = {0};
+  TRY(b2_pair_compute(ctx, eflag, vflag, (eflag || vflag) ? ev : nullptr));
+  double ek = 0.0, vk[6] = {0};
+  if (ctx->pppm) TRY(b2_pppm_compute(ctx, eflag, vflag, &ek, vk));
+  if (thermo) {
+    for (int k = 0; k < 8; k++) thermo[k] = ev[k];
+    thermo[8] = ek;
+    for (int k = 0; k < 6; k++) thermo[9 + k] = vk[k];
+  }
+  return 0;
+}
+
+extern "C" {
+
+int b200md_nve_setup(b200md_ctx *ctx, double dt) {
+  if (!ctx || !(dt > 0)) return b2_fail(ctx, B200MD_EINVAL, "b200md_nve_setup: bad timestep");
+  cudaSetDevice(ctx->device);
+  ctx->dt = dt;
+  ctx->dtv = dt;                     // FixNVEIntel::reset_dt, fix_nve_intel.cpp:130-131
+  ctx->dtf = 0.5 * dt * ctx->ftm2v;
+  if (ctx->nlocal > 0) {
+    double *dmass;
+    TRY(upload_mass(ctx, &dmass));
+    k_nve_set_dtfm<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->type.p, dmass, ctx->dtf, ctx->v.p);
+    KERNEL_OK(ctx, "k_nve_set_dtfm");
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->nve_ready = true;
+  return 0;
+}
+
+int b200md_nve_initial_integrate(b200md_ctx *ctx) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  return b2_nve_initial(ctx);
+}
+
+int b200md_nve_final_integrate(b200md_ctx *ctx) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  return b2_nve_final(ctx);
+}
+
+int b200md_setup_forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  TRY(b2_neigh_build(ctx));
+  TRY(forces(ctx, eflag, vflag, thermo));
+  if (thermo) TRY(b2_kinetic_energy(ctx, &thermo[15]));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200md_run(b200md_ctx *ctx, long nsteps, double *thermo) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (!ctx->neigh.ready) return b2_fail(ctx, B200MD_EINVAL, "b200md_run before b200md_setup_forces");
+  for (long s = 0; s < nsteps; s++) {
+    const bool last = (s == nsteps - 1) && thermo;
+    ctx->ntimestep++;
+    TRY(b2_nve_initial(ctx));
+    int rebuilt = 0;
+    TRY(b200md_neigh_decide(ctx, ctx->ntimestep, &rebuilt));
+    TRY(forces(ctx, last ? 1 : 0, last ? 1 : 0, last ? thermo : nullptr));
+    TRY(b2_nve_final(ctx));
+    if (last) TRY(b2_kinetic_energy(ctx, &thermo[15]));
+  }
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"
