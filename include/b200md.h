@@ -172,7 +172,8 @@ int b200md_pppm_download(b200md_ctx *ctx, double *density_fft, double *greensfn,
 
 /* hand-written 3-D complex FFT used by PPPM, exposed for parity tests (replaces FFT3d::compute,
  * pppm_intel.cpp:835,903): data = nz*ny*nx interleaved re/im doubles on the HOST, transformed in place;
- * dir +1 forward exp(-ikx), -1 backward, unnormalised. */
+ * dir +1 is exp(+ikx) — what stock FFT3d does for flag=1 (pppm_intel.cpp:835) — and -1 is exp(-ikx);
+ * unnormalised. */
 int b200md_fft3d_host(b200md_ctx *ctx, double *data, int nx, int ny, int nz, int dir);
 
 /* ------------------------------------------------------------------------------------------------

@@ -38,18 +38,34 @@ def sources():
 
 
 def build(force=False, verbose=False):
-    """nvcc -> lammps-buck-intel_b200/libb200md.so (in-tree, so it travels to the GPU box)."""
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [HEADER]
-    stale = force or not os.path.exists(LIBPATH) or any(os.path.getmtime(d) > os.path.getmtime(LIBPATH) for d in deps)
-    if not stale:
-        return LIBPATH
+    """nvcc -> lammps-buck-intel_b200/libb200md.so (in-tree, so it travels to the GPU box).
+    Each .cu is compiled to build/<name>.o (in parallel, only when stale), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [HEADER]
+    hdr_m = max(os.path.getmtime(h) for h in hdrs)
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIBPATH] + sources() + extra_link_flags()
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
+            jobs.append([nvcc] + cflags + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(run, jobs))
+    if jobs or not os.path.exists(LIBPATH) or any(os.path.getmtime(o) > os.path.getmtime(LIBPATH) for o in objs):
+        run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIBPATH] + objs + extra_link_flags())
     return LIBPATH
 
 

@@ -1,12 +1,915 @@
-// placeholder translation unit replaced below
-#include "internal.h"
-struct PppmState { int dummy; };
-void b2_pppm_free(b200md_ctx *ctx) { delete ctx->pppm; ctx->pppm = nullptr; }
-int b2_pppm_compute(b200md_ctx *ctx, int, int, double *, double *) { return b2_fail(ctx, B200MD_EINVAL, "pppm not set up"); }
-extern "C" {
-int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *) { return b2_fail(ctx, B200MD_EINVAL, "todo"); }
-int b200md_pppm_compute(b200md_ctx *ctx, int, int, double *, double *) { return b2_fail(ctx, B200MD_EINVAL, "todo"); }
-int b200md_pppm_compute_host(b200md_ctx *ctx, int, int, int, const double *, const double *, double *, double *, double *) { return b2_fail(ctx, B200MD_EINVAL, "todo"); }
-int b200md_pppm_download(b200md_ctx *ctx, double *, double *, double *, double *, double *, double *) { return b2_fail(ctx, B200MD_EINVAL, "todo"); }
-int b200md_fft3d_host(b200md_ctx *ctx, double *, int, int, int, int) { return b2_fail(ctx, B200MD_EINVAL, "todo"); }
+// pppm.cu — PPPM long-range electrostatics on the device (single GPU part; comm.cu adds the slab split).
+//
+// Replaces PPPMIntel (pppm_intel.cpp):
+//   init :67-98, compute :104-317, particle_map<> :326-392, make_rho<> :403-534, brick2fft :642-672,
+//   poisson_ik<> :811-977, poisson_ad<> :986-1054, fieldforce_ik<> :541-640, fieldforce_ad<> :679-804
+// and the stock PPPM state those read: compute_gf_denom, compute_rho_coeffs,
+// compute_gf_ik / compute_gf_ad (+ compute_sf_precoeff), setup (fkx/fky/fkz, vg), qsum_qsq.
+//
+// Design (B200):
+//  * make_rho is a GATHER, not a scatter: atoms are counting-sorted by the grid cell of their lower-left
+//    stencil corner (integer atomics only), then one thread per grid point visits the order^3 cells whose
+//    atoms reach it, in a fixed order => no FP atomics, bitwise reproducible, no thread-private grids to
+//    reduce (pppm_intel.cpp:422-423,521-526 disappear).  The periodic ghost-cell fold (cg->reverse_comm,
+//    :185) and brick2fft (:642-672) are fused away: the gather wraps indices and writes the FFT layout.
+//  * FFT: hand-written shared-memory Stockham passes (fft.cuh).  The forward z pass, the Green's-function
+//    multiply with the energy/virial sums (:846-872), the -i k multiplies (:890-953) and the three inverse
+//    z passes are ONE kernel; the last inverse pass stores only the real part (the unpack loops :908-970).
+//  * fieldforce gathers with wrapped indices, so the ghost fill (cg->forward_comm, :219-220) is fused away.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "pppm_internal.h"
+
+namespace {
+
+// Stock FFT3d::compute(flag=+1) runs exp(+ikx) and flag=-1 runs exp(-ikx) (flag=1 selects the FFTW_BACKWARD /
+// KISS inverse plan); fft.cuh's `s` is +1 for exp(-i...) twiddles.  Pinned by the Ewald known-answer test.
+constexpr double S_FWD = -1.0;  // fft1->compute(work1,work1,1), pppm_intel.cpp:835
+constexpr double S_BWD = 1.0;   // fft2->compute(work2,work2,-1), :903,930,958
+
+// ---------------------------------------------------------------------------------------------
+// setup kernels
+
+__device__ __forceinline__ double d_square(double x) { return x * x; }
+__device__ __forceinline__ double d_powsinxx(double x, int n) {
+  if (x == 0.0) return 1.0;
+  double yy = sin(x) / x, ww = 1.0;
+  for (; n != 0; n >>= 1, yy *= yy)
+    if (n & 1) ww *= yy;
+  return ww;
 }
+__device__ __forceinline__ double d_gf_denom(const PppmConst &c, double x, double y, double z) {
+  double sx = 0, sy = 0, sz = 0;
+  for (int l = c.order - 1; l >= 0; l--) {
+    sx = c.gf_b[l] + sx * x;
+    sy = c.gf_b[l] + sy * y;
+    sz = c.gf_b[l] + sz * z;
+  }
+  const double s = sx * sy * sz;
+  return s * s;
+}
+
+// PPPM::compute_gf_ik
+__global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, double *__restrict__ greensfn) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (n >= nfft) return;
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
+  const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
+  const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
+  const double snx = d_square(sin(0.5 * unitkx * kper * xprd / c.nx));
+  const double sny = d_square(sin(0.5 * unitky * lper * yprd / c.ny));
+  const double snz = d_square(sin(0.5 * unitkz * mper * zprd / c.nz));
+  const double sqk = d_square(unitkx * kper) + d_square(unitky * lper) + d_square(unitkz * mper);
+  double g = 0.0;
+  if (sqk != 0.0) {
+    const double numerator = 12.5663706 / sqk;
+    const double denominator = d_gf_denom(c, snx, sny, snz);
+    const int twoorder = 2 * c.order;
+    double sum1 = 0.0;
+    for (int ax = -nbx; ax <= nbx; ax++) {
+      const double qx = unitkx * (kper + c.nx * ax);
+      const double sx = exp(-0.25 * d_square(qx / c.g_ewald));
+      const double wx = d_powsinxx(0.5 * qx * xprd / c.nx, twoorder);
+      for (int ay = -nby; ay <= nby; ay++) {
+        const double qy = unitky * (lper + c.ny * ay);
+        const double sy = exp(-0.25 * d_square(qy / c.g_ewald));
+        const double wy = d_powsinxx(0.5 * qy * yprd / c.ny, twoorder);
+        for (int az = -nbz; az <= nbz; az++) {
+          const double qz = unitkz * (mper + c.nz * az);
+          const double sz = exp(-0.25 * d_square(qz / c.g_ewald));
+          const double wz = d_powsinxx(0.5 * qz * zprd / c.nz, twoorder);
+          const double dot1 = unitkx * kper * qx + unitky * lper * qy + unitkz * mper * qz;
+          const double dot2 = qx * qx + qy * qy + qz * qz;
+          sum1 += (dot1 / dot2) * sx * sy * sz * wx * wy * wz;
+        }
+      }
+    }
+    g = numerator * sum1 / denominator;
+  }
+  greensfn[n] = g;
+}
+
+// PPPM::compute_sf_precoeff + the per-point part of compute_gf_ad
+__global__ void k_gf_ad(PppmConst c, double *__restrict__ greensfn, double *__restrict__ sfpre) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (n >= nfft) return;
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
+  const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
+  const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
+  const int twoorder = 2 * c.order;
+  const double qx = unitkx * kper, qy = unitky * lper, qz = unitkz * mper;
+  const double snx = d_square(sin(0.5 * qx * xprd / c.nx)), sny = d_square(sin(0.5 * qy * yprd / c.ny)),
+               snz = d_square(sin(0.5 * qz * zprd / c.nz));
+  const double sx = exp(-0.25 * d_square(qx / c.g_ewald)), sy = exp(-0.25 * d_square(qy / c.g_ewald)),
+               sz = exp(-0.25 * d_square(qz / c.g_ewald));
+  const double wx = d_powsinxx(0.5 * qx * xprd / c.nx, twoorder), wy = d_powsinxx(0.5 * qy * yprd / c.ny, twoorder),
+               wz = d_powsinxx(0.5 * qz * zprd / c.nz, twoorder);
+  const double sqk = qx * qx + qy * qy + qz * qz;
+  double g = 0.0;
+  if (sqk != 0.0) g = (k4PI / sqk) * sx * sy * sz * wx * wy * wz / d_gf_denom(c, snx, sny, snz);
+  greensfn[n] = g;
+  double wx0[5], wy0[5], wz0[5], wx1[5], wy1[5], wz1[5], wx2[5], wy2[5], wz2[5];
+  for (int i = 0; i < 5; i++) {
+    wx0[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 2))) / c.nx, c.order);
+    wx1[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 1))) / c.nx, c.order);
+    wx2[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i))) / c.nx, c.order);
+    wy0[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i - 2))) / c.ny, c.order);
+    wy1[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i - 1))) / c.ny, c.order);
+    wy2[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i))) / c.ny, c.order);
+    wz0[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i - 2))) / c.nz, c.order);
+    wz1[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i - 1))) / c.nz, c.order);
+    wz2[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i))) / c.nz, c.order);
+  }
+  double sum[6] = {0, 0, 0, 0, 0, 0};
+  for (int ax = 0; ax < 5; ax++)
+    for (int ay = 0; ay < 5; ay++)
+      for (int az = 0; az < 5; az++) {
+        const double u0 = wx0[ax] * wy0[ay] * wz0[az];
+        sum[0] += u0 * (wx1[ax] * wy0[ay] * wz0[az]);
+        sum[1] += u0 * (wx2[ax] * wy0[ay] * wz0[az]);
+        sum[2] += u0 * (wx0[ax] * wy1[ay] * wz0[az]);
+        sum[3] += u0 * (wx0[ax] * wy2[ay] * wz0[az]);
+        sum[4] += u0 * (wx0[ax] * wy0[ay] * wz1[az]);
+        sum[5] += u0 * (wx0[ax] * wy0[ay] * wz2[az]);
+      }
+  for (int t = 0; t < 6; t++) sfpre[(size_t)t * nfft + n] = sum[t] * g;
+}
+
+// fixed-order sum of `ncol` interleaved-by-column arrays: in[col*n + i] -> out[col]
+__global__ void __launch_bounds__(256) k_colsum_partial(long n, int ncol, const double *__restrict__ in, double *__restrict__ partial) {
+  __shared__ double s[256];
+  for (int col = 0; col < ncol; col++) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    s[threadIdx.x] = i < n ? in[(size_t)col * n + i] : 0.0;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+      if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)col * gridDim.x + blockIdx.x] = s[0];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_colsum_final(int nrows, int ncol, const double *__restrict__ partial, double *__restrict__ out) {
+  __shared__ double s[256];
+  for (int col = 0; col < ncol; col++) {
+    double a = 0.0;
+    for (int r = threadIdx.x; r < nrows; r += 256) a += partial[(size_t)col * nrows + r];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+      if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[col] = s[0];
+    __syncthreads();
+  }
+}
+
+// qsum_qsq: columns {q, q^2}
+__global__ void k_q_moments(int n, const double4 *__restrict__ xq, const int *__restrict__ type,
+                            const double *__restrict__ Btype, double *__restrict__ cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double q = Btype ? Btype[type[i]] : xq[i].w;
+  cols[i] = q;
+  cols[(size_t)n + i] = q * q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-step: particle_map + sort by cell
+
+template <class flt_t>
+__device__ __forceinline__ void map_atom(const PppmConst &c, flt_t x, flt_t y, flt_t z, int &nx, int &ny, int &nz) {
+  // particle_map<flt_t,acc_t>, pppm_intel.cpp:344-372 (index arithmetic in flt_t)
+  const flt_t fshift = (flt_t)c.shift;
+  nx = static_cast<int>((x - (flt_t)c.boxlo[0]) * (flt_t)c.delinv[0] + fshift) - PPPM_OFFSET;
+  ny = static_cast<int>((y - (flt_t)c.boxlo[1]) * (flt_t)c.delinv[1] + fshift) - PPPM_OFFSET;
+  nz = static_cast<int>((z - (flt_t)c.boxlo[2]) * (flt_t)c.delinv[2] + fshift) - PPPM_OFFSET;
+}
+
+template <class flt_t>
+__global__ void k_map_key(int n, const double4 *__restrict__ xq, const float4 *__restrict__ xqf, PppmConst c,
+                          int *__restrict__ key, int *__restrict__ cell_count, int *__restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int nx, ny, nz;
+  if (sizeof(flt_t) == 4) {
+    const float4 p = xqf[i];
+    map_atom<float>(c, p.x, p.y, p.z, nx, ny, nz);
+  } else {
+    const double4 p = xq[i];
+    map_atom<double>(c, p.x, p.y, p.z, nx, ny, nz);
+  }
+  if (nx + c.nlower < c.lo_out[0] || nx + c.nupper > c.hi_out[0] || ny + c.nlower < c.lo_out[1] ||
+      ny + c.nupper > c.hi_out[1] || nz + c.nlower < c.lo_out[2] || nz + c.nupper > c.hi_out[2])
+    flags[0] = 1;  // "Out of range atoms - cannot compute PPPM" (pppm_intel.cpp:379-385)
+  const int k = (wrapi(nz, c.nz) * c.ny + wrapi(ny, c.ny)) * c.nx + wrapi(nx, c.nx);
+  key[i] = k;
+  atomicAdd(&cell_count[k], 1);
+}
+
+__global__ void k_cell_scatter(int n, const int *__restrict__ key, int *__restrict__ cursor, int *__restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  perm[atomicAdd(&cursor[key[i]], 1)] = i;
+}
+
+__global__ void k_cell_order(long ncell, const int *__restrict__ start, int *__restrict__ perm) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ncell) return;
+  const int s = start[b], e = start[b + 1];
+  for (int a = s + 1; a < e; a++) {
+    const int kk = perm[a];
+    int k = a - 1;
+    while (k >= s && perm[k] > kk) {
+      perm[k + 1] = perm[k];
+      k--;
+    }
+    perm[k + 1] = kk;
+  }
+}
+
+template <class flt_t>
+__global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4 *__restrict__ xq,
+                              const float4 *__restrict__ xqf, const int *__restrict__ type,
+                              const double *__restrict__ Btype, PppmConst c, double4 *__restrict__ pa_x,
+                              int4 *__restrict__ pa_n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = perm[k];
+  int nx, ny, nz;
+  double dx, dy, dz, w;
+  if (sizeof(flt_t) == 4) {
+    const float4 p = xqf[i];
+    map_atom<float>(c, p.x, p.y, p.z, nx, ny, nz);
+    // FFT_SCALAR dx = nx + fshiftone - (x - lo)*xi with float operands (pppm_intel.cpp:469-471)
+    const float so = (float)c.shiftone;
+    dx = (double)(nx + so - (p.x - (float)c.boxlo[0]) * (float)c.delinv[0]);
+    dy = (double)(ny + so - (p.y - (float)c.boxlo[1]) * (float)c.delinv[1]);
+    dz = (double)(nz + so - (p.z - (float)c.boxlo[2]) * (float)c.delinv[2]);
+    const float qw = Btype ? (float)Btype[type[i]] : p.w;
+    w = (double)((float)c.delvolinv * qw);
+  } else {
+    const double4 p = xq[i];
+    map_atom<double>(c, p.x, p.y, p.z, nx, ny, nz);
+    dx = nx + c.shiftone - (p.x - c.boxlo[0]) * c.delinv[0];
+    dy = ny + c.shiftone - (p.y - c.boxlo[1]) * c.delinv[1];
+    dz = nz + c.shiftone - (p.z - c.boxlo[2]) * c.delinv[2];
+    w = c.delvolinv * (Btype ? Btype[type[i]] : p.w);
+  }
+  pa_x[k] = make_double4(dx, dy, dz, w);
+  pa_n[k] = make_int4(nx, ny, nz, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_rho as a gather: one thread per grid point
+
+template <class flt_t>
+__global__ void __launch_bounds__(256)
+k_make_rho(PppmConst c, const int *__restrict__ cell_start, const double4 *__restrict__ pa_x,
+           double *__restrict__ density) {
+  __shared__ double s_rc[B2_MAXORDER * B2_MAXORDER];
+  for (int k = threadIdx.x; k < c.order * c.order; k += blockDim.x) s_rc[k] = c.rho_coeff[k];
+  __syncthreads();
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (g >= nfft) return;
+  const int gx = (int)(g % c.nx), gy = (int)((g / c.nx) % c.ny), gz = (int)(g / ((long)c.nx * c.ny));
+  const int order = c.order;
+  double rho = 0.0;
+  // atom with lower-left cell (cx,cy,cz) reaches this point through stencil offsets (l,m,n) =
+  // (gx-cx, gy-cy, gz-cz) in [nlower,nupper]; fixed visiting order n, m, l ascending
+  for (int n = c.nlower; n <= c.nupper; n++) {
+    const int cz = wrapi(gz - n, c.nz);
+    for (int m = c.nlower; m <= c.nupper; m++) {
+      const int cy = wrapi(gy - m, c.ny);
+      const long row = ((long)cz * c.ny + cy) * c.nx;
+      for (int l = c.nlower; l <= c.nupper; l++) {
+        const int cx = wrapi(gx - l, c.nx);
+        const int s = cell_start[row + cx], e = cell_start[row + cx + 1];
+        for (int a = s; a < e; a++) {
+          const double4 p = pa_x[a];
+          double r1 = 0.0, r2 = 0.0, r3 = 0.0;
+          for (int t = order - 1; t >= 0; t--) {
+            r1 = s_rc[t * order + (l - c.nlower)] + r1 * p.x;
+            r2 = s_rc[t * order + (m - c.nlower)] + r2 * p.y;
+            r3 = s_rc[t * order + (n - c.nlower)] + r3 * p.z;
+          }
+          if (sizeof(flt_t) == 4) {  // flt_t rho[3][INTEL_P3M_MAXORDER] (pppm_intel.cpp:474)
+            r1 = (double)(float)r1; r2 = (double)(float)r2; r3 = (double)(float)r3;
+          }
+          rho += ((p.w * r3) * r2) * r1;  // z0*rho[2] -> y0*rho[1] -> x0*rho[0], :490-501
+        }
+      }
+    }
+  }
+  density[g] = rho;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FFT passes.  A line L has elements at base(L) + k*estride; base(L) = (L / inner)*outer + (L % inner).
+
+struct PassGeom {
+  long nlines;
+  int inner;
+  long outer;
+  long estride;
+};
+
+template <int LINE_CONTIG, int REAL_IN, int REAL_OUT>
+__global__ void __launch_bounds__(256)
+k_fft_pass(FftPlan1d pl, PassGeom pg, int TB, int LP, const double *in_real, const double2 *in, double2 *out,
+           double *out_real, double s) {  // in/out may alias (in-place passes): no __restrict__
+  extern __shared__ double2 smem[];
+  double2 *bufA = smem, *bufB = smem + (size_t)TB * LP;
+  const long L0 = (long)blockIdx.x * TB;
+  const int n = pl.n;
+  const int nl = (int)min((long)TB, pg.nlines - L0);
+  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+    int t, k;
+    if (LINE_CONTIG) { t = idx / n; k = idx - t * n; }
+    else { k = idx / nl; t = idx - k * nl; }
+    const long L = L0 + t;
+    const long g = (L / pg.inner) * pg.outer + (L % pg.inner) + (long)k * pg.estride;
+    bufA[t * LP + k] = REAL_IN ? make_double2(in_real[g], 0.0) : in[g];
+  }
+  __syncthreads();
+  double2 *res = block_fft(bufA, bufB, pl, LP, nl, s);
+  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+    int t, k;
+    if (LINE_CONTIG) { t = idx / n; k = idx - t * n; }
+    else { k = idx / nl; t = idx - k * nl; }
+    const long L = L0 + t;
+    const long g = (L / pg.inner) * pg.outer + (L % pg.inner) + (long)k * pg.estride;
+    const double2 v = res[t * LP + k];
+    if (REAL_OUT) out_real[g] = v.x;
+    else out[g] = v;
+  }
+}
+
+// forward z pass + Poisson (pppm_intel.cpp:843-872) + (-i k) multiplies (:890-953) + NCOMP inverse z passes.
+// lines are along z at (y,x) = L; TB consecutive L share y (mostly) and have consecutive x.
+// NCOMP = 3: ik (E-field components), NCOMP = 1: ad (potential only).  EV: energy/virial partial sums.
+template <int NCOMP, int EV>
+__global__ void __launch_bounds__(256)
+k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__restrict__ in,
+                double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
+                const double *__restrict__ fky, const double *__restrict__ fkz, double scaleinv, double g_ewald,
+                double *__restrict__ ev_partial) {
+  extern __shared__ double2 smem[];
+  double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *bufV = smem + 2 * (size_t)TB * LP;
+  __shared__ double s_red[8][8];
+  const long plane = (long)nx * ny;
+  const long nfft = plane * pl.n;
+  const long L0 = (long)blockIdx.x * TB;
+  const int n = pl.n;
+  const int nl = (int)min((long)TB, plane - L0);
+  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+    const int k = idx / nl, t = idx - k * nl;
+    bufA[t * LP + k] = in[(L0 + t) + (long)k * plane];
+  }
+  __syncthreads();
+  double2 *res = block_fft(bufA, bufB, pl, LP, nl, S_FWD);
+  double2 *other = (res == bufA) ? bufB : bufA;
+  // Green's function multiply; energy / virial tallies
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+    const int k = idx / nl, t = idx - k * nl;
+    const long L = L0 + t;
+    const long g = L + (long)k * plane;
+    const double2 w = res[t * LP + k];
+    const double gf = greensfn[g];
+    if (EV) {
+      const double eng = scaleinv * scaleinv * gf * (w.x * w.x + w.y * w.y);
+      const int ix = (int)(L % nx), iy = (int)(L / nx);
+      const double kx = fkx[ix], ky = fky[iy], kz = fkz[k];
+      const double sqk = kx * kx + ky * ky + kz * kz;
+      acc[0] += eng;
+      if (sqk != 0.0) {  // PPPM::setup vg[][] evaluated on the fly instead of stored (6 doubles / point)
+        const double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+        acc[1] += eng * (1.0 + vterm * kx * kx);
+        acc[2] += eng * (1.0 + vterm * ky * ky);
+        acc[3] += eng * (1.0 + vterm * kz * kz);
+        acc[4] += eng * (vterm * kx * ky);
+        acc[5] += eng * (vterm * kx * kz);
+        acc[6] += eng * (vterm * ky * kz);
+      }
+    }
+    const double sg = scaleinv * gf;
+    bufV[t * LP + k] = make_double2(w.x * sg, w.y * sg);
+  }
+  __syncthreads();
+  if (EV) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+      double v = acc[q];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) s_red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+      double sum = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) sum += s_red[w][threadIdx.x];
+      ev_partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sum;
+    }
+  }
+  for (int comp = 0; comp < NCOMP; comp++) {
+    double2 *a = res, *b = other;  // V lives in bufV; a/b are free ping-pong buffers
+    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+      const int k = idx / nl, t = idx - k * nl;
+      const double2 v = bufV[t * LP + k];
+      if (NCOMP == 1) a[t * LP + k] = v;
+      else {
+        const long L = L0 + t;
+        const double fk = comp == 0 ? fkx[(int)(L % nx)] : (comp == 1 ? fky[(int)(L / nx)] : fkz[k]);
+        a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);  // work2 = (fk*Im, -fk*Re), :894-895
+      }
+    }
+    __syncthreads();
+    double2 *r2 = block_fft(a, b, pl, LP, nl, S_BWD);
+    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+      const int k = idx / nl, t = idx - k * nl;
+      out[(size_t)comp * nfft + (L0 + t) + (long)k * plane] = r2[t * LP + k];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+
+int make_plan(b200md_ctx *ctx, FftPlan1d &pl, DevBuf<double2> &twbuf, int n) {
+  pl.n = n;
+  pl.nfac = 0;
+  int m = n;
+  while (m % 4 == 0) { pl.fac[pl.nfac++] = 4; m /= 4; }
+  while (m % 2 == 0) { pl.fac[pl.nfac++] = 2; m /= 2; }
+  while (m % 3 == 0) { pl.fac[pl.nfac++] = 3; m /= 3; }
+  while (m % 5 == 0) { pl.fac[pl.nfac++] = 5; m /= 5; }
+  if (m != 1) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", n);
+  std::vector<double2> tw(n);
+  for (int k = 0; k < n; k++) {
+    const long double ph = -2.0L * 3.14159265358979323846264338327950288L * k / n;
+    tw[k] = make_double2((double)cosl(ph), (double)sinl(ph));
+  }
+  RESERVE(ctx, twbuf, (size_t)n);
+  CUDA_OK(ctx, cudaMemcpy(twbuf.p, tw.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+  pl.tw = twbuf.p;
+  return 0;
+}
+
+int pick_tb(int n, int nbuf) {
+  // lines per block: as many as fit in ~110 KB of shared memory (2 blocks / SM), at most 16, at least 1
+  const int LP = n | 1;
+  int tb = 16;
+  while (tb > 1 && (size_t)nbuf * tb * LP * sizeof(double2) > 110 * 1024) tb >>= 1;
+  return tb;
+}
+
+template <int LC, int RI, int RO>
+int launch_pass(b200md_ctx *ctx, const FftPlan1d &pl, const PassGeom &pg, const double *in_real, const double2 *in,
+                double2 *out, double *out_real, double s) {
+  const int TB = pick_tb(pl.n, 2);
+  const int LP = pl.n | 1;
+  const size_t smem = 2 * (size_t)TB * LP * sizeof(double2);
+  if (smem > 200 * 1024) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d too long for one shared-memory line", pl.n);
+  auto kern = k_fft_pass<LC, RI, RO>;
+  CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblk = cdiv(pg.nlines, TB);
+  kern<<<nblk, 256, smem, ctx->stream>>>(pl, pg, TB, LP, in_real, in, out, out_real, s);
+  KERNEL_OK(ctx, "k_fft_pass");
+  return 0;
+}
+
+int reduce_cols(b200md_ctx *ctx, PppmState &ps, long n, int ncol, const double *cols, double *host_out) {
+  const int nb = cdiv(n, 256);
+  RESERVE(ctx, ps.partial, (size_t)nb * ncol);
+  RESERVE(ctx, ps.red, 16);
+  k_colsum_partial<<<nb, 256, 0, ctx->stream>>>(n, ncol, cols, ps.partial.p);
+  KERNEL_OK(ctx, "k_colsum_partial");
+  k_colsum_final<<<1, 256, 0, ctx->stream>>>(nb, ncol, ps.partial.p, ps.red.p);
+  KERNEL_OK(ctx, "k_colsum_final");
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, ncol * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < ncol; k++) host_out[k] = ctx->h_pinned[k];
+  return 0;
+}
+
+void compute_rho_coeffs(PppmConst &c) {
+  const int order = c.order;
+  const int w = 2 * order + 1;
+  std::vector<double> a((size_t)order * w, 0.0);
+  auto A = [&](int l, int k) -> double & { return a[(size_t)l * w + (k + order)]; };
+  A(0, 0) = 1.0;
+  for (int j = 1; j < order; j++)
+    for (int k = -j; k <= j; k += 2) {
+      double s = 0.0;
+      for (int l = 0; l < j; l++) {
+        A(l + 1, k) = (A(l, k + 1) - A(l, k - 1)) / (l + 1);
+        s += std::pow(0.5, (double)l + 1) * (A(l, k - 1) + std::pow(-1.0, (double)l) * A(l, k + 1)) / (l + 1);
+      }
+      A(0, k) = s;
+    }
+  for (int i = 0; i < B2_MAXORDER * B2_MAXORDER; i++) c.rho_coeff[i] = c.drho_coeff[i] = 0.0;
+  int m = (1 - order) / 2;
+  for (int k = -(order - 1); k < order; k += 2) {
+    for (int l = 0; l < order; l++) c.rho_coeff[l * order + (m - c.nlower)] = A(l, k);
+    for (int l = 1; l < order; l++) c.drho_coeff[(l - 1) * order + (m - c.nlower)] = l * A(l, k);
+    m++;
+  }
+}
+
+void compute_gf_denom(PppmConst &c) {
+  const int order = c.order;
+  for (int l = 1; l < order; l++) c.gf_b[l] = 0.0;
+  c.gf_b[0] = 1.0;
+  for (int m = 1; m < order; m++) {
+    int l;
+    for (l = m; l > 0; l--)
+      c.gf_b[l] = 4.0 * (c.gf_b[l] * (l - m) * (l - m - 0.5) - c.gf_b[l - 1] * (l - m - 1) * (l - m - 1));
+    c.gf_b[0] = 4.0 * (c.gf_b[0] * (l - m) * (l - m - 0.5));
+  }
+  long ifact = 1;
+  for (int k = 1; k < 2 * order; k++) ifact *= k;
+  const double gaminv = 1.0 / ifact;
+  for (int l = 0; l < order; l++) c.gf_b[l] *= gaminv;
+}
+
+int fft3d_forward_xy(b200md_ctx *ctx, PppmState &ps, const double *density, double2 *work) {
+  const PppmConst &c = ps.c;
+  PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1};
+  TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD)));
+  PassGeom gy{(long)c.nx * c.nz, c.nx, (long)c.nx * c.ny, (long)c.nx};
+  TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work, work, nullptr, S_FWD)));
+  return 0;
+}
+
+template <class flt_t>
+int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int eflag, int vflag, double *energy,
+                      double *virial) {
+  const PppmConst &c = ps.c;
+  const int n = v.n;
+  const long nfft = ps.nfft;
+  const int eflag_global = eflag & 1, vflag_global = vflag & 3;
+  const bool ad = ps.p.differentiation == 1;
+  const int ncomp = ad ? 1 : 3;
+  if (energy) *energy = 0.0;
+  if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
+
+  // qsum_qsq when the atom count changed (pppm_intel.cpp:142-145)
+  if (ps.q_natoms != n) {
+    RESERVE(ctx, ps.density, std::max((size_t)nfft, 2 * (size_t)n + 2));
+    if (n > 0) {
+      k_q_moments<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.type, ps.p.dispersion ? ps.Btype.p : nullptr,
+                                                          ps.density.p);
+      KERNEL_OK(ctx, "k_q_moments");
+      double m[2];
+      TRY(reduce_cols(ctx, ps, n, 2, ps.density.p, m));
+      ps.qsum = m[0];
+      ps.qsqsum = m[1];
+    } else ps.qsum = ps.qsqsum = 0.0;
+    ps.q_natoms = n;
+  }
+  if (ps.qsqsum == 0.0) return 0;  // "return if there are no charges" :149
+
+  // ---- particle_map + cell sort + make_rho ------------------------------------------------------
+  {
+    ScopedTimer tm(ctx, T_MAKE_RHO);
+    RESERVE(ctx, ps.key, (size_t)n + 1);
+    RESERVE(ctx, ps.perm, (size_t)n + 1);
+    RESERVE(ctx, ps.pa_x, (size_t)n + 1);
+    RESERVE(ctx, ps.pa_n, (size_t)n + 1);
+    RESERVE(ctx, ps.cell_count, (size_t)nfft + 1);
+    RESERVE(ctx, ps.cell_start, (size_t)nfft + 1);
+    RESERVE(ctx, ps.cursor, (size_t)nfft + 1);
+    RESERVE(ctx, ps.flags, 4);
+    RESERVE(ctx, ps.scan_ws, b2_scan_ws_bytes((size_t)nfft + 1));
+    CUDA_OK(ctx, cudaMemsetAsync(ps.cell_count.p, 0, ((size_t)nfft + 1) * sizeof(int), ctx->stream));
+    CUDA_OK(ctx, cudaMemsetAsync(ps.flags.p, 0, 4 * sizeof(int), ctx->stream));
+    if (n > 0) {
+      k_map_key<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.xqf, c, ps.key.p, ps.cell_count.p, ps.flags.p);
+      KERNEL_OK(ctx, "k_map_key");
+    }
+    TRY(b2_exclusive_scan_i32(ctx, ps.cell_count.p, ps.cell_start.p, (size_t)nfft, ps.scan_ws.p));
+    CUDA_OK(ctx, cudaMemcpyAsync(ps.cursor.p, ps.cell_start.p, (size_t)nfft * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n > 0) {
+      k_cell_scatter<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.key.p, ps.cursor.p, ps.perm.p);
+      KERNEL_OK(ctx, "k_cell_scatter");
+      k_cell_order<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(nfft, ps.cell_start.p, ps.perm.p);
+      KERNEL_OK(ctx, "k_cell_order");
+      k_fill_sorted<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.perm.p, v.xq, v.xqf, v.type,
+                                                                   ps.p.dispersion ? ps.Btype.p : nullptr, c, ps.pa_x.p,
+                                                                   ps.pa_n.p);
+      KERNEL_OK(ctx, "k_fill_sorted");
+    }
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    k_make_rho<flt_t><<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, ps.cell_start.p, ps.pa_x.p, ps.density.p);
+    KERNEL_OK(ctx, "k_make_rho");
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(int *)ctx->h_pinned) return b2_fail(ctx, B200MD_ERANGE, "Out of range atoms - cannot compute PPPM");
+  }
+
+  // ---- poisson: forward FFT, Green's function, gradients, inverse FFTs -------------------------------
+  const int ev = (eflag_global || vflag_global) ? 1 : 0;
+  int nblk_z = 0;
+  {
+    ScopedTimer tm(ctx, T_FFT);
+    TRY(fft3d_forward_xy(ctx, ps, ps.density.p, ps.work1.p));
+    const int TB = pick_tb(c.nz, 3);
+    const int LP = c.nz | 1;
+    const size_t smem = 3 * (size_t)TB * LP * sizeof(double2);
+    const long plane = (long)c.nx * c.ny;
+    nblk_z = cdiv(plane, TB);
+    const double scaleinv = 1.0 / ((double)c.nx * c.ny * c.nz);
+    if (ev) RESERVE(ctx, ps.partial, (size_t)nblk_z * 8);
+#define ZK(NC, E)                                                                                             \
+  do {                                                                                                        \
+    auto kern = k_fft_z_poisson<NC, E>;                                                                       \
+    CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    kern<<<nblk_z, 256, smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, TB, LP, ps.work1.p, ps.work2.p,          \
+                                             ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, scaleinv, c.g_ewald, \
+                                             ps.partial.p);                                                   \
+  } while (0)
+    if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
+    else { if (ev) ZK(3, 1); else ZK(3, 0); }
+#undef ZK
+    KERNEL_OK(ctx, "k_fft_z_poisson");
+    // inverse y over ncomp*nz planes, inverse x storing the real part
+    PassGeom gy{(long)c.nx * c.nz * ncomp, c.nx, (long)c.nx * c.ny, (long)c.nx};
+    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
+    PassGeom gx{(long)c.ny * c.nz * ncomp, 1, (long)c.nx, 1};
+    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
+  }
+  double evsum[8] = {0};
+  if (ev) {
+    ScopedTimer tm(ctx, T_POISSON);
+    RESERVE(ctx, ps.red, 16);
+    k_colsum_final<<<1, 256, 0, ctx->stream>>>(nblk_z, 7, ps.partial.p, ps.red.p);
+    KERNEL_OK(ctx, "k_colsum_final");
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 7; k++) evsum[k] = ctx->h_pinned[k];
+  }
+
+  // ---- fieldforce -----------------------------------------------------------------------------------
+  TRY(b2_fieldforce<flt_t>(ctx, ps, v));
+
+  // ---- energy / virial post-factors (pppm_intel.cpp:256-275) -----------------------------------------
+  const double qscale = ctx->qqrd2e * ps.p.scale;
+  if (eflag_global && energy) {
+    double e = evsum[0];
+    e *= 0.5 * ps.volume;
+    if (!ps.p.dispersion)
+      e -= c.g_ewald * ps.qsqsum / kPIS + kPI2 * ps.qsum * ps.qsum / (c.g_ewald * c.g_ewald * ps.volume);
+    e *= qscale;
+    *energy = e;
+  }
+  if (vflag_global && virial)
+    for (int k = 0; k < 6; k++) virial[k] = 0.5 * qscale * ps.volume * evsum[1 + k];
+  return 0;
+}
+
+}  // namespace
+
+void b2_pppm_free(b200md_ctx *ctx) {
+  PppmState *ps = ctx->pppm;
+  if (!ps) return;
+  for (int d = 0; d < 3; d++) ps->tw[d].free_();
+  ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
+  ps->work1.free_(); ps->work2.free_(); ps->sf_pre.free_(); ps->Btype.free_();
+  ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
+  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
+  delete ps;
+  ctx->pppm = nullptr;
+}
+
+int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial) {
+  if (!ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
+  PppmView v;
+  v.n = ctx->nlocal;
+  v.xq = ctx->xq.p;
+  v.xqf = ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr;
+  v.type = ctx->type.p;
+  v.f = ctx->f.p;
+  if (ctx->prec == B200MD_PREC_MIXED) return pppm_compute_view<float>(ctx, *ctx->pppm, v, eflag, vflag, energy, virial);
+  return pppm_compute_view<double>(ctx, *ctx->pppm, v, eflag, vflag, energy, virial);
+}
+
+extern "C" {
+
+int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
+  if (!ctx || !p) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_setup: NULL argument");
+  cudaSetDevice(ctx->device);
+  if (!ctx->box_set) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_setup before b200md_set_box");
+  if (p->order > B2_MAXORDER || p->order < 1)
+    return b2_fail(ctx, B200MD_EORDER, "PPPM order greater than supported by USER-INTEL");
+  if (p->nx < 2 || p->ny < 2 || p->nz < 2 || p->nx >= PPPM_OFFSET || p->ny >= PPPM_OFFSET || p->nz >= PPPM_OFFSET)
+    return b2_fail(ctx, B200MD_EINVAL, "PPPM grid is too large or too small");
+  if (!(p->g_ewald > 0)) return b2_fail(ctx, B200MD_EINVAL, "PPPM needs g_ewald > 0");
+  if (p->dispersion && !p->B) return b2_fail(ctx, B200MD_EINVAL, "dispersion PPPM needs B[type]");
+  for (int d = 0; d < 3; d++)
+    if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "PPPM needs a fully periodic box (no slab correction)");
+  b2_pppm_free(ctx);
+  PppmState *ps = new PppmState();
+  ctx->pppm = ps;
+  ps->p = *p;
+  ps->p.B = nullptr;
+  if (ps->p.scale == 0.0) ps->p.scale = 1.0;
+  PppmConst &c = ps->c;
+  c.nx = p->nx; c.ny = p->ny; c.nz = p->nz; c.order = p->order;
+  c.nlower = -(p->order - 1) / 2;
+  c.nupper = p->order / 2;
+  if (p->order % 2) { c.shift = PPPM_OFFSET + 0.5; c.shiftone = 0.0; }
+  else { c.shift = PPPM_OFFSET; c.shiftone = 0.5; }
+  c.g_ewald = p->g_ewald;
+  const int ng[3] = {p->nx, p->ny, p->nz};
+  const double dist = 0.5 * ctx->neigh.skin;  // cuthalf (no TIP4P qdist)
+  for (int d = 0; d < 3; d++) {
+    c.boxlo[d] = ctx->boxlo[d];
+    c.prd[d] = ctx->prd[d];
+    c.delinv[d] = ng[d] / ctx->prd[d];
+    // PPPM::set_grid_local extents, one rank: ghost cells reach dist beyond the box
+    const int nlo = static_cast<int>((0.0 - dist) * ng[d] / ctx->prd[d] + c.shift) - PPPM_OFFSET;
+    const int nhi = static_cast<int>((ctx->prd[d] + dist) * ng[d] / ctx->prd[d] + c.shift) - PPPM_OFFSET;
+    c.lo_out[d] = nlo + c.nlower;
+    c.hi_out[d] = nhi + c.nupper;
+  }
+  c.delvolinv = c.delinv[0] * c.delinv[1] * c.delinv[2];
+  ps->volume = ctx->prd[0] * ctx->prd[1] * ctx->prd[2];
+  ps->nfft = (long)p->nx * p->ny * p->nz;
+  if (ps->nfft > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");
+  compute_rho_coeffs(c);
+  compute_gf_denom(c);
+  for (int d = 0; d < 3; d++) TRY(make_plan(ctx, ps->plan[d], ps->tw[d], ng[d]));
+  const long nfft = ps->nfft;
+  const bool ad = p->differentiation == 1;
+  RESERVE(ctx, ps->greensfn, (size_t)nfft);
+  RESERVE(ctx, ps->density, (size_t)nfft);
+  RESERVE(ctx, ps->work1, (size_t)nfft);
+  RESERVE(ctx, ps->work2, (size_t)nfft * (ad ? 1 : 3));
+  RESERVE(ctx, ps->vd, (size_t)nfft * (ad ? 1 : 3));
+  RESERVE(ctx, ps->fkx, (size_t)p->nx);
+  RESERVE(ctx, ps->fky, (size_t)p->ny);
+  RESERVE(ctx, ps->fkz, (size_t)p->nz);
+  {
+    // PPPM::setup: fkx/fky/fkz
+    std::vector<double> fk;
+    DevBuf<double> *dst[3] = {&ps->fkx, &ps->fky, &ps->fkz};
+    for (int d = 0; d < 3; d++) {
+      const double unitk = k2PI / ctx->prd[d];
+      fk.assign(ng[d], 0.0);
+      for (int i = 0; i < ng[d]; i++) fk[i] = unitk * (i - ng[d] * (2 * i / ng[d]));
+      CUDA_OK(ctx, cudaMemcpy(dst[d]->p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  if (p->dispersion) {
+    RESERVE(ctx, ps->Btype, (size_t)ctx->ntypes + 1);
+    CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, p->B, ((size_t)ctx->ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (p->dispersion)
+    return b2_fail(ctx, B200MD_EINVAL, "dispersion Green's function is provided by b200md_pppm_disp (not built yet)");
+  if (!ad) {
+    const double fac = std::pow(-std::log(1.0e-7), 0.25);  // EPS_HOC, pppm_intel.cpp:39
+    const int nbx = static_cast<int>((c.g_ewald * c.prd[0] / (kPI * c.nx)) * fac);
+    const int nby = static_cast<int>((c.g_ewald * c.prd[1] / (kPI * c.ny)) * fac);
+    const int nbz = static_cast<int>((c.g_ewald * c.prd[2] / (kPI * c.nz)) * fac);
+    k_gf_ik<<<cdiv(nfft, 128), 128, 0, ctx->stream>>>(c, nbx, nby, nbz, ps->greensfn.p);
+    KERNEL_OK(ctx, "k_gf_ik");
+  } else {
+    RESERVE(ctx, ps->sf_pre, 6 * (size_t)nfft);
+    k_gf_ad<<<cdiv(nfft, 128), 128, 0, ctx->stream>>>(c, ps->greensfn.p, ps->sf_pre.p);
+    KERNEL_OK(ctx, "k_gf_ad");
+    double s[6];
+    TRY(reduce_cols(ctx, *ps, nfft, 6, ps->sf_pre.p, s));
+    // compute_gf_ad: self-force coefficients
+    double prex = kPI / ps->volume, prey = prex, prez = prex;
+    prex *= c.nx / c.prd[0];
+    prey *= c.ny / c.prd[1];
+    prez *= c.nz / c.prd[2];
+    ps->sf_coeff[0] = s[0] * prex; ps->sf_coeff[1] = s[1] * prex * 2;
+    ps->sf_coeff[2] = s[2] * prey; ps->sf_coeff[3] = s[3] * prey * 2;
+    ps->sf_coeff[4] = s[4] * prez; ps->sf_coeff[5] = s[5] * prez * 2;
+    ps->sf_pre.free_();
+  }
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  (void)k4PI;
+  return 0;
+}
+
+int b200md_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double virial[6]) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  TRY(b2_pppm_compute(ctx, eflag, vflag, energy, virial));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+namespace {
+__global__ void k_pack_xq(int n, const double *__restrict__ x, const double *__restrict__ q, double4 *__restrict__ xq,
+                          float4 *__restrict__ xqf, double4 *__restrict__ f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = make_double4(x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2], q[i]);
+  xq[i] = p;
+  if (xqf) xqf[i] = make_float4((float)p.x, (float)p.y, (float)p.z, (float)p.w);
+  f[i] = make_double4(0, 0, 0, 0);
+}
+}  // namespace
+
+int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const double *x, const double *q,
+                             double *f, double *energy, double virial[6]) {
+  if (!ctx || !x || !q || !f || n < 0) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_compute_host: bad arguments");
+  if (!ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
+  if (ctx->pppm->p.dispersion) return b2_fail(ctx, B200MD_EINVAL, "host form supports the Coulomb grid only");
+  cudaSetDevice(ctx->device);
+  DevBuf<double> dx, dq;
+  DevBuf<double4> dxq, df;
+  DevBuf<float4> dxqf;
+  const bool mixed = ctx->prec == B200MD_PREC_MIXED;
+  auto cleanup = [&]() { dx.free_(); dq.free_(); dxq.free_(); df.free_(); dxqf.free_(); };
+  if (dx.reserve(3 * (size_t)n + 1) || dq.reserve((size_t)n + 1) || dxq.reserve((size_t)n + 1) || df.reserve((size_t)n + 1) ||
+      (mixed && dxqf.reserve((size_t)n + 1))) {
+    cleanup();
+    return b2_fail(ctx, B200MD_ENOMEM, "out of device memory in b200md_pppm_compute_host");
+  }
+  cudaMemcpyAsync(dx.p, x, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dq.p, q, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (n) {
+    k_pack_xq<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, dx.p, dq.p, dxq.p, mixed ? dxqf.p : nullptr, df.p);
+    ctx->launches++;
+  }
+  PppmView v{n, dxq.p, mixed ? dxqf.p : nullptr, nullptr, df.p};
+  ctx->pppm->q_natoms = -1;  // a different atom set: recompute qsum/qsqsum
+  int rc = mixed ? pppm_compute_view<float>(ctx, *ctx->pppm, v, eflag, vflag, energy, virial)
+                 : pppm_compute_view<double>(ctx, *ctx->pppm, v, eflag, vflag, energy, virial);
+  ctx->pppm->q_natoms = -1;
+  if (!rc) {
+    std::vector<double> hf(4 * (size_t)n);
+    cudaMemcpyAsync(hf.data(), df.p, (size_t)n * sizeof(double4), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = b2_fail(ctx, B200MD_ECUDA, "pppm host compute failed: %s", cudaGetErrorString(e));
+    else
+      for (int i = 0; i < n; i++)
+        for (int d = 0; d < 3; d++) f[3 * (size_t)i + d] += hf[4 * (size_t)i + d];
+  }
+  cleanup();
+  return rc;
+}
+
+int b200md_pppm_download(b200md_ctx *ctx, double *density_fft, double *greensfn, double *field_x, double *field_y,
+                         double *field_z, double sf_coeff[6]) {
+  if (!ctx || !ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "pppm not set up");
+  cudaSetDevice(ctx->device);
+  PppmState &ps = *ctx->pppm;
+  const size_t nb = (size_t)ps.nfft * sizeof(double);
+  const bool ad = ps.p.differentiation == 1;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (density_fft) CUDA_OK(ctx, cudaMemcpy(density_fft, ps.density.p, nb, cudaMemcpyDeviceToHost));
+  if (greensfn) CUDA_OK(ctx, cudaMemcpy(greensfn, ps.greensfn.p, nb, cudaMemcpyDeviceToHost));
+  if (field_x) CUDA_OK(ctx, cudaMemcpy(field_x, ps.vd.p, nb, cudaMemcpyDeviceToHost));
+  if (field_y) CUDA_OK(ctx, cudaMemcpy(field_y, ps.vd.p + (ad ? 0 : ps.nfft), nb, cudaMemcpyDeviceToHost));
+  if (field_z) CUDA_OK(ctx, cudaMemcpy(field_z, ps.vd.p + (ad ? 0 : 2 * ps.nfft), nb, cudaMemcpyDeviceToHost));
+  if (sf_coeff) for (int k = 0; k < 6; k++) sf_coeff[k] = ps.sf_coeff[k];
+  return 0;
+}
+
+int b200md_fft3d_host(b200md_ctx *ctx, double *data, int nx, int ny, int nz, int dir) {
+  if (!ctx || !data || nx < 1 || ny < 1 || nz < 1) return b2_fail(ctx, B200MD_EINVAL, "b200md_fft3d_host: bad arguments");
+  cudaSetDevice(ctx->device);
+  FftPlan1d pl[3];
+  DevBuf<double2> tw[3], buf;
+  const int ng[3] = {nx, ny, nz};
+  const size_t nfft = (size_t)nx * ny * nz;
+  int rc = 0;
+  for (int d = 0; d < 3 && !rc; d++) rc = make_plan(ctx, pl[d], tw[d], ng[d]);
+  if (!rc && buf.reserve(nfft)) rc = b2_fail(ctx, B200MD_ENOMEM, "out of device memory in b200md_fft3d_host");
+  if (!rc) {
+    cudaMemcpyAsync(buf.p, data, nfft * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
+    const double s = dir > 0 ? S_FWD : S_BWD;
+    PassGeom gx{(long)ny * nz, 1, (long)nx, 1};
+    PassGeom gy{(long)nx * nz, nx, (long)nx * ny, (long)nx};
+    PassGeom gz{(long)nx * ny, nx * ny, 0, (long)nx * ny};
+    rc = launch_pass<1, 0, 0>(ctx, pl[0], gx, nullptr, buf.p, buf.p, nullptr, s);
+    if (!rc) rc = launch_pass<0, 0, 0>(ctx, pl[1], gy, nullptr, buf.p, buf.p, nullptr, s);
+    if (!rc) rc = launch_pass<0, 0, 0>(ctx, pl[2], gz, nullptr, buf.p, buf.p, nullptr, s);
+    if (!rc) {
+      cudaMemcpyAsync(data, buf.p, nfft * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaError_t e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) rc = b2_fail(ctx, B200MD_ECUDA, "fft3d failed: %s", cudaGetErrorString(e));
+    }
+  }
+  for (int d = 0; d < 3; d++) tw[d].free_();
+  buf.free_();
+  return rc;
+}
+
+}  // extern "C"

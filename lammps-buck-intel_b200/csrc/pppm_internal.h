@@ -1,0 +1,63 @@
+// pppm_internal.h — state shared by pppm.cu and fieldforce.cu
+#pragma once
+#include "fft.cuh"
+#include "internal.h"
+
+#define PPPM_OFFSET 16384
+static constexpr double kPI = 3.14159265358979323846;
+static constexpr double k2PI = 6.28318530717958647692;
+static constexpr double k4PI = 12.56637061435917295384;
+static constexpr double kPI2 = 1.57079632679489661923;
+static constexpr double kPIS = 1.77245385090551602729;
+
+struct PppmConst {  // everything the kernels need by value
+  int nx, ny, nz, order, nlower, nupper;
+  double shift, shiftone;
+  double boxlo[3], delinv[3], delvolinv;
+  double prd[3];
+  int lo_out[3], hi_out[3];  // brick extents of the reference (only for the "Out of range atoms" check)
+  double rho_coeff[B2_MAXORDER * B2_MAXORDER];   // [l][k-nlower]
+  double drho_coeff[B2_MAXORDER * B2_MAXORDER];
+  double gf_b[B2_MAXORDER];
+  double g_ewald;
+};
+
+struct PppmState {
+  b200md_pppm_params p{};
+  PppmConst c{};
+  long nfft = 0;
+  double volume = 0;
+  FftPlan1d plan[3];
+  DevBuf<double2> tw[3];
+  DevBuf<double> greensfn, fkx, fky, fkz, density, vd;  // vd: 3*nfft (ik) or nfft (ad: u)
+  DevBuf<double2> work1, work2;                         // work2: 3*nfft (ik) / nfft (ad)
+  DevBuf<double> sf_pre;                                // ad: 6*nfft
+  double sf_coeff[6] = {0, 0, 0, 0, 0, 0};
+  DevBuf<double> Btype;                                 // dispersion: per-type weight
+  // per-step atom -> cell sort
+  DevBuf<int> key, cell_count, cell_start, cursor, perm, flags;
+  DevBuf<double4> pa_x;  // sorted: {dx,dy,dz, weight*delvolinv}
+  DevBuf<int4> pa_n;     // sorted: {nx,ny,nz, atom index}
+  DevBuf<unsigned char> scan_ws;
+  DevBuf<double> partial, red;
+  double qsum = 0, qsqsum = 0;
+  long q_natoms = -1;
+};
+
+struct PppmView {
+  int n;
+  const double4 *xq;
+  const float4 *xqf;  // mixed mode positions (nullptr in double mode)
+  const int *type;
+  double4 *f;
+};
+
+
+__device__ __forceinline__ int wrapi(int a, int n) {
+  a %= n;
+  return a < 0 ? a + n : a;
+}
+
+// fieldforce.cu
+template <class flt_t>
+int b2_fieldforce(b200md_ctx *ctx, PppmState &ps, const PppmView &v);

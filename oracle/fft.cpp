@@ -90,7 +90,7 @@ extern "C" void orc_fft3d(double *data, int nx, int ny, int nz, int dir, int nth
   if (nthreads <= 0) nthreads = omp_get_max_threads();
   cpx *d = reinterpret_cast<cpx *>(data);
   const Plan px = make_plan(nx), py = make_plan(ny), pz = make_plan(nz);
-  const int sign = dir > 0 ? 1 : -1;
+  const int sign = dir > 0 ? -1 : 1;  // sign > 0 selects exp(-i...) twiddles
 #pragma omp parallel num_threads(nthreads)
   {
     std::vector<cpx> buf(std::max(nx, std::max(ny, nz)));

@@ -138,7 +138,7 @@ const double *orc_pppm_field(const orc_pppm *p, int dim);/* after compute: vdx/v
 const double *orc_pppm_sf_coeff(const orc_pppm *p);
 void orc_pppm_rho_coeff(const orc_pppm *p, double *rho_coeff /*order*order*/, double *drho_coeff);
 
-/* 3-D complex FFT used by the oracle (KISS-style mixed radix), dir=+1 forward e^{-ikx}, -1 backward,
+/* 3-D complex FFT used by the oracle (KISS-style mixed radix), dir=+1 is exp(+ikx) (LAMMPS flag=1), -1 is exp(-ikx),
  * unnormalised, interleaved re/im, x fastest. */
 void orc_fft3d(double *data, int nx, int ny, int nz, int dir, int nthreads);
 

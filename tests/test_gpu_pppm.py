@@ -1,0 +1,153 @@
+"""-m gpu parity: PPPM on the device vs the CPU oracle, same inputs, explicit (nx,ny,nz,order,g_ewald)
+("PPPM parity at explicit grid ... so both sides use the same grid")."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (8, 6, 5), (27, 25, 32), (40, 36, 36), (64, 60, 60), (108, 96, 96),
+                                   (135, 50, 45)])
+def test_fft3d_matches_numpy(pkg, shape):
+    rng = np.random.default_rng(11)
+    a = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    ctx = pkg.Context(0, 0)
+    fwd = ctx.fft3d(a, 1)      # LAMMPS flag=+1 == exp(+ikx)
+    ref = np.fft.ifftn(a) * a.size
+    assert np.abs(fwd - ref).max() <= 1e-12 * np.abs(ref).max()
+    bwd = ctx.fft3d(a, -1)
+    ref = np.fft.fftn(a)
+    assert np.abs(bwd - ref).max() <= 1e-12 * np.abs(ref).max()
+    back = ctx.fft3d(fwd, -1) / a.size
+    assert np.abs(back - a).max() <= 1e-12
+    with pytest.raises(pkg.B200MDError):
+        ctx.fft3d(np.zeros((7, 8, 8), complex), 1)   # 7 is not 2^a 3^b 5^c
+    ctx.close()
+
+
+def _case(W, name):
+    if name == "aC1":
+        return W.aC_system(1), (24, 24, 27), 0.28
+    if name == "aC2_1e-4":           # 9600 atoms, 36x36x40 @ 1e-4
+        return W.aC_system(2), (36, 36, 40), 0.2472
+    if name == "aC2_1e-5":
+        return W.aC_system(2), (60, 60, 64), 0.2776
+    if name == "water":              # S4 stand-in: 5184 atoms, neutral
+        return W.water_like_system(12), (40, 40, 40), 0.30
+    raise ValueError(name)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("name,order,ad", [("aC1", 5, 0), ("aC1", 3, 0), ("aC1", 4, 0), ("aC1", 7, 0), ("aC1", 2, 0),
+                                           ("aC2_1e-4", 5, 0), ("aC2_1e-5", 5, 0), ("water", 5, 0),
+                                           ("aC1", 5, 1), ("aC1", 4, 1), ("aC2_1e-4", 5, 1), ("aC1", 7, 1)])
+def test_pppm_matches_oracle(pkg, W, orc, name, order, ad, prec):
+    s, grid, g = _case(W, name)
+    u = W.UNITS[s["units"]]
+    ctx = pkg.make_context(s, precision=prec)
+    ctx.neigh_setup(2.0)
+    ctx.pppm_setup(*grid, order, g, differentiation=ad)
+    pp = orc.PPPM(*grid, order, g, s["boxlo"], s["boxhi"], u["qqrd2e"], diff_ad=ad, prec=prec)
+    fo, eo, vo = pp.compute(s["x"], s["q"])
+    # host-buffer form of PPPMIntel::compute
+    f, e, v = ctx.pppm_compute_host(s["x"], s["q"], 1, 1)
+    d = ctx.pppm_download()
+    tg = 1e-12
+    assert np.abs(d["greensfn"] - pp.greensfn()).max() <= tg * np.abs(pp.greensfn()).max()
+    tol_grid = 1e-11 if prec == 0 else 2e-5
+    rho = pp.density()
+    assert np.abs(d["density"] - rho).max() <= tol_grid * np.abs(rho).max()
+    for k, c in enumerate(("fx", "fy", "fz")):
+        ref = pp.field(k)
+        assert np.abs(d[c] - ref).max() <= tol_grid * np.abs(ref).max(), c
+        if ad:
+            break
+    tol_f = 1e-9 if prec == 0 else 1e-5
+    tol_e = 1e-10 if prec == 0 else 1e-5
+    assert util.rel_force_err(f, fo) <= tol_f
+    assert abs(e - eo) <= tol_e * abs(eo)
+    assert np.abs(v - vo).max() <= tol_e * np.abs(vo).max()
+    if ad:
+        assert np.abs(d["sf_coeff"] - pp.sf_coeff()).max() <= 1e-11 * np.abs(pp.sf_coeff()).max()
+    # resident form: accumulates onto whatever the force array holds (f +=), host order preserved
+    co = W.coeffs_aC(6.0, 6.0) if s["units"] == "metal" else None
+    if co is not None:
+        cf = pkg.pair_coeffs(pkg.PAIR_BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+        ctx.neigh_setup(0.3)
+        ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=g)
+        ctx.neigh_build()
+        ctx.pair_compute(0, 0)
+        fp = ctx.atoms_download(("f",))["f"]
+        e2, v2 = ctx.pppm_compute(1, 1)
+        ft = ctx.atoms_download(("f",))["f"]
+        assert util.rel_force_err(ft - fp, fo) <= tol_f
+        assert abs(e2 - eo) <= tol_e * abs(eo)
+    ctx.close()
+
+
+def test_pppm_deterministic_and_flags(pkg, W):
+    s, grid, g = _case(W, "aC1")
+    outs = []
+    for _ in range(2):
+        ctx = pkg.make_context(s)
+        ctx.pppm_setup(*grid, 5, g)
+        f, e, v = ctx.pppm_compute_host(s["x"], s["q"], 1, 1)
+        outs.append((f, e, v, ctx.pppm_download()["density"]))
+        f0, e0, v0 = ctx.pppm_compute_host(s["x"], s["q"], 0, 0)
+        assert e0 == 0.0 and not v0.any()
+        assert np.array_equal(f0, f)    # same kernels for forces with or without tallies
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+
+
+def test_pppm_errors(pkg, W):
+    s, grid, g = _case(W, "aC1")
+    ctx = pkg.make_context(s)
+    with pytest.raises(pkg.B200MDError) as ei:
+        ctx.pppm_setup(*grid, 8, g)
+    assert "PPPM order greater than supported" in str(ei.value)
+    ctx.neigh_setup(0.3)
+    ctx.pppm_setup(*grid, 5, g)
+    x = s["x"].copy()
+    x[17, 0] += 9.0 * (s["boxhi"][0] - s["boxlo"][0])
+    with pytest.raises(pkg.B200MDError) as ei:
+        ctx.pppm_compute_host(x, s["q"], 0, 0)
+    assert "Out of range atoms - cannot compute PPPM" in str(ei.value)
+    # uncharged system: returns without touching forces ("return if there are no charges", pppm_intel.cpp:149)
+    f, e, v = ctx.pppm_compute_host(s["x"], np.zeros(len(x)), 1, 1)
+    assert not f.any() and e == 0.0
+    ctx.close()
+
+
+def test_full_step_buck_coul_long_pppm(pkg, W, orc):
+    """the north-star step: buck/coul/long + PPPM forces and energies vs the oracle, then a short NVE run
+    conserves energy"""
+    s = W.aC_system(2)
+    u = W.UNITS["metal"]
+    g, grid = 0.2776, (60, 60, 64)
+    co = W.coeffs_aC(12.0, 12.0)
+    ctx = pkg.make_context(s)
+    cf = pkg.pair_coeffs(pkg.PAIR_BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+    ctx.neigh_setup(0.3)
+    ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=g)
+    ctx.pppm_setup(*grid, 5, g)
+    ctx.nve_setup(u["dt"])
+    th = ctx.setup_forces(1, 1)
+    f = ctx.atoms_download(("f",))["f"]
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=g)
+    fo, evo, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    pp = orc.PPPM(*grid, 5, g, s["boxlo"], s["boxhi"], u["qqrd2e"])
+    fk, ek, vk = pp.compute(s["x"], s["q"])
+    assert util.rel_force_err(f, fo[:, :3] + fk) <= 1e-9
+    assert abs(th[0] - evo[0]) <= 1e-10 * abs(evo[0]) and abs(th[1] - evo[1]) <= 1e-10 * abs(evo[1])
+    assert abs(th[8] - ek) <= 1e-10 * abs(ek)
+    assert np.abs(th[9:15] - vk).max() <= 1e-10 * np.abs(vk).max()
+    e0 = th[0] + th[1] + th[8] + u["mvv2e"] * th[15]
+    th1 = ctx.run(40, thermo=True)
+    e1 = th1[0] + th1[1] + th1[8] + u["mvv2e"] * th1[15]
+    assert abs(e1 - e0) <= 2e-5 * abs(e0), (e0, e1)
+    ctx.close()

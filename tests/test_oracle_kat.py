@@ -1,0 +1,221 @@
+"""Known-answer tests that pin the CPU oracle (the reference ships no tests or golden vectors, SURVEY.md §4,
+§8c: "parity unpinned").  Each KAT checks a restated formula against an independent closed form / library."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+
+def _dimer(orc, style, r, qq=(1.3, -0.7), **kw):
+    """two atoms at distance r along a skewed axis, no periodic images: returns (f on atom 0, ev)"""
+    d = np.array([0.36, -0.48, 0.8])
+    d /= np.linalg.norm(d)
+    x = np.array([[0.1, 0.2, 0.3], [0.1, 0.2, 0.3] + r * d])
+    t = np.array([1, 2], np.int32)
+    q = np.array(qq)
+    P = kw["P"]
+    nn = np.array([1, 0], np.int32)
+    off = np.array([0, 1, 1], np.int64)
+    ent = np.array([1], np.int32)
+    f, ev = orc.pair_eval(P, kw.get("prec", 0), 1, 1, 2, x, t, q, nn, off, ent, newton=1)
+    return f, ev, d
+
+
+def _params(orc, style, **kw):
+    A = np.zeros((3, 3)); rho = np.ones((3, 3)); C = np.zeros((3, 3))
+    A[1, 2] = A[2, 1] = 1800.0; rho[1, 2] = rho[2, 1] = 0.29; C[1, 2] = C[2, 1] = 130.0
+    A[1, 1] = A[2, 2] = 10.0; C[1, 1] = C[2, 2] = 1.0
+    return orc.Params(style, 2, A, rho, C, np.full((3, 3), 9.0), np.full((3, 3), 10.0), qqrd2e=14.399645, **kw)
+
+
+@pytest.mark.parametrize("r", [1.1, 2.5, 6.0, 8.9])
+def test_dimer_closed_form_all_styles(orc, r):
+    A, rho, C, qq, k = 1800.0, 0.29, 130.0, 1.3 * -0.7, 14.399645
+    e_b = A * math.exp(-r / rho) - C / r ** 6
+    f_b = A / rho * math.exp(-r / rho) - 6 * C / r ** 7          # -dE/dr
+    # buck
+    f, ev, d = _dimer(orc, orc.BUCK, r, P=_params(orc, orc.BUCK))
+    assert ev[0] == pytest.approx(e_b, rel=1e-13)
+    assert np.allclose(f[0, :3], -f_b * d, rtol=1e-12) and np.allclose(f[1, :3], f_b * d, rtol=1e-12)
+    # buck/coul/cut
+    f, ev, d = _dimer(orc, orc.BUCK_COUL_CUT, r, P=_params(orc, orc.BUCK_COUL_CUT))
+    assert ev[1] == pytest.approx(k * qq / r, rel=1e-13)
+    assert np.allclose(f[0, :3], -(f_b + k * qq / r ** 2) * d, rtol=1e-12)
+    # buck/coul/long analytic: erfc via the A&S 5-term polynomial (<= 1.5e-7 absolute)
+    g = 0.28
+    f, ev, d = _dimer(orc, orc.BUCK_COUL_LONG, r, P=_params(orc, orc.BUCK_COUL_LONG, g_ewald=g))
+    assert ev[1] == pytest.approx(k * qq * math.erfc(g * r) / r, abs=abs(k * qq / r) * 2e-7)
+    fc = k * qq * (math.erfc(g * r) / r ** 2 + 2 * g / math.sqrt(math.pi) * math.exp(-(g * r) ** 2) / r)
+    assert np.allclose(f[0, :3], -(f_b + fc) * d, rtol=0, atol=abs(k * qq / r ** 2) * 3e-7 + 1e-12)
+    # buck/long/coul/long, ORDER6 only: E = A e^{-r/rho} - C g6^6 e^{-x} (1 + x + x^2/2) / x^3, x = (g6 r)^2
+    g6 = 0.31
+    P = _params(orc, orc.BUCK_LONG_COUL_LONG, g_ewald_6=g6, order6=1)
+    f, ev, d = _dimer(orc, orc.BUCK_LONG_COUL_LONG, r, P=P)
+    xx = (g6 * r) ** 2
+    e6 = A * math.exp(-r / rho) - C * g6 ** 6 * math.exp(-xx) * (1 + xx + xx * xx / 2) / xx ** 3
+    assert ev[0] == pytest.approx(e6, rel=1e-12)
+
+
+@pytest.mark.parametrize("style,kw", [(0, {}), (1, {}), (2, dict(g_ewald=0.28)),
+                                       (3, dict(g_ewald=0.28, g_ewald_6=0.31, order1=1, order6=1)),
+                                       (3, dict(g_ewald_6=0.31, order6=1))])
+def test_force_is_minus_energy_gradient(orc, style, kw):
+    P = _params(orc, style, **kw)
+    for r in (1.3, 3.0, 7.7):
+        h = 1e-5
+        _, evp, _ = _dimer(orc, style, r + h, P=P)
+        _, evm, _ = _dimer(orc, style, r - h, P=P)
+        f, _, d = _dimer(orc, style, r, P=P)
+        dEdr = ((evp[0] + evp[1]) - (evm[0] + evm[1])) / (2 * h)
+        fr = float(f[1, :3] @ d)              # force on atom 1 along +d = -dE/dr
+        # the polynomial erfc has a 1e-7-level derivative inconsistency by construction
+        assert fr == pytest.approx(-dEdr, rel=2e-6, abs=1e-6)
+
+
+def test_as_erfc_polynomial(orc):
+    """pair_buck_coul_long_intel.cpp:296-307 constants reproduce erfc to 1.5e-7 absolute"""
+    A = (0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429)
+    p = 0.3275911
+    x = np.linspace(0.0, 6.0, 2001)
+    t = 1.0 / (1.0 + p * x)
+    poly = t * (A[0] + t * (A[1] + t * (A[2] + t * (A[3] + t * A[4])))) * np.exp(-x * x)
+    ref = np.array([math.erfc(v) for v in x])
+    assert np.abs(poly - ref).max() <= 1.5e-7
+
+
+def test_special_bonds_and_tables_dimer(orc, pkg):
+    g = 0.28
+    P = _params(orc, orc.BUCK_COUL_LONG, g_ewald=g, special_lj=(1, 0.0, 0.5, 0.25), special_coul=(1, 0.0, 0.3, 0.8))
+    r = 3.3
+    x = np.array([[0.0, 0, 0], [r, 0, 0]]); t = np.array([1, 2], np.int32); q = np.array([1.3, -0.7])
+    k, qq = 14.399645, -0.91
+    for sb in (1, 2, 3):
+        ent = np.array([1 | (sb << 30)], np.int64).astype(np.uint32).view(np.int32)
+        f, ev = orc.pair_eval(P, 0, 1, 0, 2, x, t, q, np.array([1, 0], np.int32), np.array([0, 1, 1]), ent)
+        fl, fc = P.p.special_lj[sb], P.p.special_coul[sb]
+        e_b = 1800.0 * math.exp(-r / 0.29) - 130.0 / r ** 6
+        assert ev[0] == pytest.approx(fl * e_b, rel=1e-12)
+        assert ev[1] == pytest.approx(k * qq / r * (math.erfc(g * r) - (1 - fc)), abs=abs(k * qq / r) * 2e-7)
+    # table branch: interpolation error of the 12-bit table is ~1e-6 relative to the analytic value
+    tabs = P.make_coul_tables(10.0)
+    f_t, ev_t = orc.pair_eval(P, 0, 1, 0, 2, x, t, q, np.array([1, 0], np.int32), np.array([0, 1, 1]), np.array([1], np.int32))
+    assert ev_t[1] == pytest.approx(k * qq * math.erfc(g * r) / r, rel=5e-6)
+    # the product's host-side table builder (Pair::init_tables in Python) matches the oracle's (to libm rounding)
+    t2, mask, shift, inner = pkg.init_coul_tables(10.0, g, 14.399645)
+    assert (mask, shift) == (P.p.ncoulmask, P.p.ncoulshiftbits) and inner == P.p.tabinnersq
+    for kk in tabs:
+        assert np.allclose(tabs[kk], t2[kk], rtol=1e-9, atol=1e-13 * np.abs(tabs[kk]).max()), kk
+
+
+def test_half_list_equals_brute_force_pair_set(orc, W):
+    for s, co, st, nt in ((W.fcc_system(6, 6, 6), W.coeffs_in_buck(2.5), orc.BUCK, 1),
+                          (W.aC_system(1), W.coeffs_aC(10.0, 10.0), orc.BUCK_COUL_CUT, 2)):
+        P = orc.Params(st, nt, co["A"], co["rho"], co["C"], co["cut_lj"], co.get("cut_coul"))
+        n = len(s["x"])
+        cm = P.cutmax() + 0.3
+        for prec in (0, 1):
+            xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cm)
+            cns = P.cutneighsq(0.3)
+            hn, hoff, hent = orc.neigh_half_bin(n, xa, ta, nt, cns, s["boxlo"], s["boxhi"], cm, prec)
+            fn, foff, fent = orc.neigh_full_brute(n, xa, ta, nt, cns, prec)
+            assert np.array_equal(util.pair_keys(n, hn, hent, src, shift, symmetrize=True),
+                                  util.pair_keys(n, fn, fent, src, shift))
+            # i in N(j) <=> j in N(i)
+            kf = util.pair_keys(n, fn, fent, src, shift)
+            assert 2 * hoff[-1] == foff[-1] == len(kf)
+
+
+def test_newton_sum_and_counts(orc, W):
+    s = W.fcc_system(8, 8, 8)
+    co = W.coeffs_in_buck(2.5)
+    P = orc.Params(orc.BUCK, 1, co["A"], co["rho"], co["C"], co["cut_lj"])
+    f, ev, aux = orc.pair_forces_periodic(P, 0, s["x"], s["type"], None, s["boxlo"], s["boxhi"], 0.3)
+    assert np.abs(f[:, :3].sum(0)).max() < 1e-10
+    # 38.8 half-list neighbours per atom at cut+skin for in.buck
+    assert aux["offsets"][-1] / len(s["x"]) == pytest.approx(38.8, abs=0.6)
+    # virial by pair tally equals f.r virial
+    _, ev2, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], None, s["boxlo"], s["boxhi"], 0.3, vflag=2)
+    assert np.allclose(ev[2:], ev2[2:], rtol=1e-9, atol=1e-9)
+
+
+def test_fft3d_matches_numpy(orc):
+    rng = np.random.default_rng(3)
+    for shape in ((8, 6, 5), (12, 10, 9), (27, 25, 16), (40, 36, 36)):
+        a = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+        fwd = orc.fft3d(a, 1)
+        # LAMMPS FFT3d: flag=+1 is exp(+ikx) = numpy's unnormalised inverse
+        assert np.abs(fwd - np.fft.ifftn(a) * a.size).max() <= 1e-11 * np.abs(fwd).max()
+        back = orc.fft3d(fwd, -1) / a.size
+        assert np.abs(back - a).max() <= 1e-12
+
+
+def test_pppm_plus_real_space_equals_ewald(orc, W):
+    """what in.buck_coul_long:12 really runs is kspace_style ewald: a tight PPPM + erfc real space must give
+    the same Coulomb forces/energy as a direct Ewald sum"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    g = 0.30
+    fe, ee, ve = orc.ewald_recip(s["x"], s["q"], s["boxlo"], s["boxhi"], g, 14, u["qqrd2e"])
+    pp = orc.PPPM(60, 60, 64, 7, g, s["boxlo"], s["boxhi"], u["qqrd2e"])
+    fp, ep, vp = pp.compute(s["x"], s["q"])
+    scale = np.abs(fe).max()
+    assert np.abs(fp - fe).max() / scale < 2e-5
+    assert ep == pytest.approx(ee, rel=1e-6)
+    assert np.allclose(vp, ve, rtol=1e-4, atol=1e-4 * np.abs(ve).max())
+    # ad differentiation converges to the same answer
+    pa = orc.PPPM(60, 60, 64, 7, g, s["boxlo"], s["boxhi"], u["qqrd2e"], diff_ad=1)
+    fa, ea, va = pa.compute(s["x"], s["q"])
+    assert np.abs(fa - fe).max() / scale < 2e-4
+    assert ea == pytest.approx(ee, rel=1e-6)
+
+
+def test_madelung_constant_rocksalt(orc, pkg):
+    """NaCl rock salt: E per ion pair = -M q^2 / r0 with M = 1.747565, from PPPM + real-space erfc"""
+    nc, a = 4, 5.64
+    r0 = a / 2
+    idx = np.stack(np.meshgrid(*[np.arange(2 * nc)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    x = idx * r0 + 0.25
+    q = np.where(idx.sum(1) % 2 == 0, 1.0, -1.0)
+    t = np.where(q > 0, 1, 2).astype(np.int32)
+    lo, hi = np.zeros(3), np.full(3, nc * a)
+    k = 14.399645
+    g = 0.40
+    A = np.zeros((3, 3)); rho = np.ones((3, 3)); C = np.zeros((3, 3))
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, A, rho, C, np.full((3, 3), 9.0), np.full((3, 3), 9.0), qqrd2e=k, g_ewald=g)
+    P.arr["cut_ljsq"][:] = 0.0  # Coulomb only
+    f, ev, _ = orc.pair_forces_periodic(P, 0, x, t, q, lo, hi, 0.3)
+    pp = orc.PPPM(48, 48, 48, 7, g, lo, hi, k)
+    fk, ek, _ = pp.compute(x, q)
+    npairs = len(x) / 2
+    M = -(ev[1] + ek) / npairs * r0 / k
+    assert M == pytest.approx(1.747565, abs=3e-5)
+    assert np.abs(f[:, :3] + fk).max() < 1e-3  # perfect lattice: forces vanish
+
+
+def test_pppm_sizing_heuristic(orc, W):
+    """PPPM::set_grid_global restated: grids are 2,3,5-smooth and land near the SURVEY §6.2 estimates"""
+    s = W.aC_system(1)
+    x, t, q, lo, hi = W.replicate(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 2, 2, 2)
+    qsq = float((q * q).sum())
+    for acc, expect in ((1e-4, (36, 36, 40)), (1e-5, (60, 60, 64))):
+        grid, g = orc.pppm_size(acc, 14.399645, qsq, len(x), 12.0, hi - lo, order=5)
+        for n in grid:
+            m = n
+            for p in (2, 3, 5):
+                while m % p == 0:
+                    m //= p
+            assert m == 1
+        assert all(abs(a - b) <= 0.25 * b for a, b in zip(grid, expect)), (grid, expect)
+        assert 0.2 < g < 0.4
+
+
+def test_nve_matches_closed_form(orc):
+    x = np.array([[0.0, 1.0, 2.0]]); v = np.array([[0.5, -0.25, 0.125]]); f = np.array([[2.0, 4.0, -8.0]])
+    dtfm = orc.nve_dtfm(np.array([1], np.int32), np.array([0.0, 4.0]), 0.01, 2.0)
+    assert np.allclose(dtfm, 0.5 * 0.01 * 2.0 / 4.0)
+    x1, v1 = orc.nve_initial(x, v, f, dtfm, 0.01)
+    assert np.allclose(v1, v + dtfm.reshape(1, 3) * f) and np.allclose(x1, x + 0.01 * v1)
+    assert np.allclose(orc.nve_final(v1, f, dtfm), v1 + dtfm.reshape(1, 3) * f)

@@ -1,0 +1,33 @@
+import os
+
+import numpy as np
+import pytest
+
+REF = "/root/reference/examples/data.aC"
+
+
+def test_fcc_counts(W):
+    s = W.fcc_system(20, 20, 20)
+    assert len(s["x"]) == 32000                       # examples/in.buck: 32 000 atoms
+    a = (4.0 / 0.8442) ** (1.0 / 3.0)
+    assert np.allclose(s["boxhi"], 20 * a)
+    assert ((s["x"] >= s["boxlo"]) & (s["x"] < s["boxhi"])).all()
+    assert np.abs((s["v"] * s["mass"][s["type"]][:, None]).sum(0)).max() < 1e-9
+
+
+def test_aC_counts_and_neutrality(W):
+    s = W.aC_system(2)
+    assert len(s["x"]) == 9600                        # examples/in.buck_coul_long: data.aC x 2^3
+    assert abs(s["q"].sum()) < 1e-9
+    assert (s["type"] == 1).sum() * 2 == (s["type"] == 2).sum()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present (GPU box)")
+def test_data_aC_regenerated_matches_shipped_file(W):
+    x, t, q, lo, hi = W.data_aC()
+    ref = np.loadtxt(REF, skiprows=16)
+    assert ref.shape == (1200, 6)
+    assert np.abs(ref[:, 3:6] - x).max() < 2e-5       # the file is rounded to 5 decimals
+    assert (ref[:, 1].astype(int) == t).all() and np.abs(ref[:, 2] - q).max() == 0.0
+    hdr = open(REF).read().split("\n")[5:8]
+    assert float(hdr[0].split()[1]) == hi[0] and float(hdr[2].split()[1]) == hi[2]
