@@ -28,6 +28,9 @@ NEIGHMASK = 0x3FFFFFFF
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
+# the float (mixed-mode) pair kernels replay the reference's un-fused IEEE arithmetic (csrc/pair_kernel.cuh)
+PER_FILE_FLAGS = {"pair_mixed.cu": ["-fmad=false"]}
+
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 lp = C.POINTER(C.c_long)
@@ -52,7 +55,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
-            jobs.append([nvcc] + cflags + ["-c", src, "-o", obj])
+            jobs.append([nvcc] + cflags + PER_FILE_FLAGS.get(os.path.basename(src), []) + ["-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:

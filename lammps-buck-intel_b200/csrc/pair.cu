@@ -16,335 +16,15 @@
 // reduction — no FP atomics.  Per-type-pair constants live in shared memory.
 // Cut-off test is rsq < cutsq.  Every list entry carries ev_pre = 1/2 (i is owned; the
 // mirrored entry supplies the other half), which reproduces the NEWTON_PAIR=0 tallies of :296-313.
-#include <algorithm>
-#include <cmath>
-#include <cstring>
+#include "pair_kernel.cuh"
 
-#include "internal.h"
+using namespace pairk;
+
+int b2_launch_pair_double(b200md_ctx *ctx, const PairView &v, long long total_entries, int evflag, double *ev_dev) {
+  return launch_pair<double>(ctx, v, total_entries, evflag, ev_dev);
+}
 
 namespace {
-
-enum { C_CUTSQ = 0, C_CUT_LJSQ, C_CUT_COULSQ, C_BUCK1, C_BUCK2, C_RHOINV, C_A, C_C, C_OFFSET, C_N };
-
-template <class flt_t>
-struct PairConsts {
-  int tp1;
-  flt_t qqrd2e, g_ewald, tabinnersq, tabinnerdispsq, g2, g6, g8;
-  flt_t special_lj[4], special_coul[4];
-  int ncoulmask, ncoulshiftbits, ndispmask, ndispshiftbits;
-  int order1, order6, coultable, disptable;
-};
-
-template <class flt_t> struct V4;
-template <> struct V4<double> { typedef double4 type; };
-template <> struct V4<float> { typedef float4 type; };
-
-__device__ __forceinline__ double m_exp(double x) { return exp(x); }
-__device__ __forceinline__ float m_exp(float x) { return expf(x); }
-__device__ __forceinline__ double m_rsqrt(double x) { return rsqrt(x); }
-__device__ __forceinline__ float m_rsqrt(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double m_rcp(double x) { return 1.0 / x; }
-__device__ __forceinline__ float m_rcp(float x) { return 1.0f / x; }
-
-struct PairView {  // device pointers of one evaluation
-  int nlocal;
-  const void *x;         // double4* or float4*
-  const int *type;
-  const int *numneigh;
-  const long long *offsets;
-  const int *entries;
-  double4 *f;
-};
-
-template <int STYLE, class flt_t, int EVFLAG, int TPA>
-__global__ void __launch_bounds__(256)
-k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const int *__restrict__ type,
-       const int *__restrict__ numneigh, const long long *__restrict__ offsets,
-       const int *__restrict__ entries, const PairConsts<flt_t> pc, const flt_t *__restrict__ coeff,
-       const flt_t *__restrict__ ctab, const flt_t *__restrict__ dtab, double4 *__restrict__ f,
-       double *__restrict__ ev_partial) {
-  typedef typename V4<flt_t>::type vec4;
-  __shared__ flt_t s_coeff[(B2_MAXTYPES + 1) * (B2_MAXTYPES + 1) * C_N];
-  __shared__ double s_ev[8][8];
-  for (int k = threadIdx.x; k < pc.tp1 * pc.tp1 * C_N; k += blockDim.x) s_coeff[k] = coeff[k];
-  __syncthreads();
-
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int sub = threadIdx.x & (TPA - 1);
-  const int i = gtid / TPA;
-  const bool active = i < nlocal;
-
-  double fx = 0.0, fy = 0.0, fz = 0.0;
-  double sevdwl = 0.0, secoul = 0.0, sv0 = 0.0, sv1 = 0.0, sv2 = 0.0, sv3 = 0.0, sv4 = 0.0, sv5 = 0.0;
-
-  if (active) {
-    const vec4 xi = x[i];
-    const flt_t qtmp = xi.w;
-    const flt_t *ci = s_coeff + type[i] * pc.tp1 * C_N;
-    const int jnum = numneigh[i];
-    const int *jlist = entries + offsets[i];
-
-    for (int jj = sub; jj < jnum; jj += TPA) {
-      const int e = jlist[jj];
-      const int sbindex = (e >> B2_SBBITS) & 3;
-      const int j = e & B2_NEIGHMASK;
-      const vec4 xj = x[j];
-      const flt_t *cij = ci + type[j] * C_N;
-      const flt_t delx = xi.x - xj.x;
-      const flt_t dely = xi.y - xj.y;
-      const flt_t delz = xi.z - xj.z;
-      const flt_t rsq = delx * delx + dely * dely + delz * delz;
-      if (rsq < cij[C_CUTSQ]) {
-        const flt_t rinv = m_rsqrt(rsq);
-        const flt_t r = rsq * rinv;
-        const flt_t r2inv = rinv * rinv;
-        flt_t forcecoul = (flt_t)0, forcebuck = (flt_t)0, evdwl = (flt_t)0, ecoul = (flt_t)0;
-
-        if (STYLE == B200MD_PAIR_BUCK_COUL_CUT) {
-          if (rsq < cij[C_CUT_COULSQ]) {
-            forcecoul = pc.qqrd2e * qtmp * xj.w * rinv;
-            if (sbindex) forcecoul *= pc.special_coul[sbindex];
-            if (EVFLAG) ecoul = forcecoul;
-          }
-        }
-        if (STYLE == B200MD_PAIR_BUCK_COUL_LONG || (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order1)) {
-          if (!pc.coultable || rsq <= pc.tabinnersq) {
-            const flt_t A1 = (flt_t)0.254829592, A2 = (flt_t)-0.284496736, A3 = (flt_t)1.421413741;
-            const flt_t A4 = (flt_t)-1.453152027, A5 = (flt_t)1.061405429;
-            const flt_t EWALD_F = (flt_t)1.12837917, EWALD_P = (flt_t)0.3275911;
-            const flt_t grij = pc.g_ewald * r;
-            const flt_t expm2 = m_exp(-grij * grij);
-            const flt_t t = m_rcp((flt_t)1.0 + EWALD_P * grij);
-            const flt_t erfc = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * expm2;
-            const flt_t prefactor = pc.qqrd2e * qtmp * xj.w * rinv;
-            forcecoul = prefactor * (erfc + EWALD_F * grij * expm2);
-            if (EVFLAG) ecoul = prefactor * erfc;
-            if (sbindex) {
-              const flt_t adjust = ((flt_t)1.0 - pc.special_coul[sbindex]) * prefactor;
-              forcecoul -= adjust;
-              if (EVFLAG) ecoul -= adjust;
-            }
-          } else {
-            const float rsq_lookup = (float)rsq;
-            const int itable = (__float_as_int(rsq_lookup) & pc.ncoulmask) >> pc.ncoulshiftbits;
-            const flt_t *tb = ctab + 8 * itable;  // {r,dr,f,df,e,de,c,dc}
-            const flt_t fraction = ((flt_t)rsq_lookup - tb[0]) * tb[1];
-            const flt_t qiqj = qtmp * xj.w;
-            forcecoul = qiqj * (tb[2] + fraction * tb[3]);
-            if (EVFLAG) ecoul = qiqj * (tb[4] + fraction * tb[5]);
-            if (sbindex) {
-              const flt_t prefactor = qiqj * (tb[6] + fraction * tb[7]);
-              const flt_t adjust = ((flt_t)1.0 - pc.special_coul[sbindex]) * prefactor;
-              forcecoul -= adjust;
-              if (EVFLAG) ecoul -= adjust;
-            }
-          }
-        }
-
-        if (rsq < cij[C_CUT_LJSQ]) {
-          const flt_t r6inv = r2inv * r2inv * r2inv;
-          const flt_t rexp = m_exp(-r * cij[C_RHOINV]);
-          if (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order6) {
-            if (!pc.disptable || rsq <= pc.tabinnerdispsq) {
-              const flt_t grij2 = pc.g2 * rsq;
-              const flt_t a2 = m_rcp(grij2);
-              const flt_t x2 = a2 * m_exp(-grij2) * cij[C_C];
-              forcebuck = r * rexp * cij[C_BUCK1] -
-                          pc.g8 * x2 * rsq * ((((flt_t)6.0 * a2 + (flt_t)6.0) * a2 + (flt_t)3.0) * a2 + (flt_t)1.0);
-              if (EVFLAG) evdwl = rexp * cij[C_A] - pc.g6 * x2 * ((a2 + (flt_t)1.0) * a2 + (flt_t)0.5);
-            } else {
-              const float rsq_lookup = (float)rsq;
-              const int itable = (__float_as_int(rsq_lookup) & pc.ndispmask) >> pc.ndispshiftbits;
-              const flt_t *tb = dtab + 6 * itable;  // {r,dr,f,df,e,de}
-              const flt_t fd = (rsq - tb[0]) * tb[1];
-              forcebuck = r * rexp * cij[C_BUCK1] - (tb[2] + fd * tb[3]) * cij[C_C];
-              if (EVFLAG) evdwl = rexp * cij[C_A] - (tb[4] + fd * tb[5]) * cij[C_C];
-            }
-            if (sbindex) {
-              const flt_t t = pc.special_lj[sbindex] - (flt_t)1.0;
-              forcebuck += t * r * rexp * cij[C_BUCK1] - t * r6inv * cij[C_BUCK2];
-              if (EVFLAG) evdwl += t * rexp * cij[C_A] - t * r6inv * cij[C_C];
-            }
-          } else {
-            forcebuck = r * rexp * cij[C_BUCK1] - r6inv * cij[C_BUCK2];
-            if (EVFLAG) evdwl = rexp * cij[C_A] - r6inv * cij[C_C] - cij[C_OFFSET];
-            if (sbindex) {
-              const flt_t factor_lj = pc.special_lj[sbindex];
-              forcebuck *= factor_lj;
-              if (EVFLAG) evdwl *= factor_lj;
-            }
-          }
-        }
-
-        const flt_t fpair = (forcecoul + forcebuck) * r2inv;
-        const double dfx = (double)(delx * fpair), dfy = (double)(dely * fpair), dfz = (double)(delz * fpair);
-        fx += dfx;
-        fy += dfy;
-        fz += dfz;
-        if (EVFLAG) {
-          sevdwl += 0.5 * (double)evdwl;
-          secoul += 0.5 * (double)ecoul;
-          const flt_t hf = (flt_t)0.5 * fpair;  // IP_PRE_ev_tally_nbor with ev_pre = 1/2
-          sv0 += (double)(hf * delx * delx);
-          sv1 += (double)(hf * dely * dely);
-          sv2 += (double)(hf * delz * delz);
-          sv3 += (double)(hf * delx * dely);
-          sv4 += (double)(hf * delx * delz);
-          sv5 += (double)(hf * dely * delz);
-        }
-      }
-    }
-  }
-
-  // fixed-shape xor tree over the TPA lanes of an atom
-#pragma unroll
-  for (int d = TPA >> 1; d > 0; d >>= 1) {
-    fx += __shfl_xor_sync(0xffffffffu, fx, d);
-    fy += __shfl_xor_sync(0xffffffffu, fy, d);
-    fz += __shfl_xor_sync(0xffffffffu, fz, d);
-    if (EVFLAG) {
-      sevdwl += __shfl_xor_sync(0xffffffffu, sevdwl, d);
-      secoul += __shfl_xor_sync(0xffffffffu, secoul, d);
-    }
-  }
-  if (active && sub == 0) f[i] = make_double4(fx, fy, fz, EVFLAG ? sevdwl + secoul : 0.0);
-
-  if (EVFLAG) {
-    // block tally: each atom's lane 0 carries its energies; virial terms are still per lane
-    double vals[8] = {(active && sub == 0) ? sevdwl : 0.0, (active && sub == 0) ? secoul : 0.0,
-                      sv0, sv1, sv2, sv3, sv4, sv5};
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], d);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0)
-#pragma unroll
-      for (int k = 0; k < 8; k++) s_ev[warp][k] = vals[k];
-    __syncthreads();
-    if (threadIdx.x < 8) {
-      double s = 0.0;
-      const int nw = blockDim.x >> 5;
-      for (int w = 0; w < nw; w++) s += s_ev[w][threadIdx.x];
-      ev_partial[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
-    }
-  }
-}
-
-// single block, fixed order: thread t sums partial rows t, t+256, ... then a shared-memory tree
-__global__ void __launch_bounds__(256) k_ev_reduce(int nrows, const double *__restrict__ partial, double *__restrict__ out) {
-  __shared__ double s[256];
-  for (int k = 0; k < 8; k++) {
-    double a = 0.0;
-    for (int r = threadIdx.x; r < nrows; r += 256) a += partial[(size_t)r * 8 + k];
-    s[threadIdx.x] = a;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-      if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[k] = s[0];
-    __syncthreads();
-  }
-}
-
-template <class flt_t>
-PairConsts<flt_t> make_consts(const PairState &ps) {
-  PairConsts<flt_t> pc;
-  const b200md_pair_params &p = ps.p;
-  pc.tp1 = ps.tp1;
-  pc.qqrd2e = (flt_t)0;  // filled by caller
-  pc.g_ewald = (flt_t)p.g_ewald;
-  pc.tabinnersq = (flt_t)p.tabinnersq;
-  pc.tabinnerdispsq = (flt_t)p.tabinnerdispsq;
-  const flt_t g2 = (flt_t)(p.g_ewald_6 * p.g_ewald_6);
-  pc.g2 = g2;
-  pc.g6 = g2 * g2 * g2;
-  pc.g8 = pc.g6 * g2;
-  for (int k = 0; k < 4; k++) {
-    pc.special_lj[k] = (flt_t)p.special_lj[k];
-    pc.special_coul[k] = (flt_t)p.special_coul[k];
-  }
-  pc.special_lj[0] = pc.special_coul[0] = (flt_t)1.0;  // pair_buck_intel.cpp:414-417
-  pc.ncoulmask = p.ncoulmask;
-  pc.ncoulshiftbits = p.ncoulshiftbits;
-  pc.ndispmask = p.ndispmask;
-  pc.ndispshiftbits = p.ndispshiftbits;
-  pc.order1 = (p.ewald_order >> 1) & 1;
-  pc.order6 = (p.ewald_order >> 6) & 1;
-  pc.coultable = p.ncoultablebits != 0;
-  pc.disptable = p.ndisptablebits != 0;
-  return pc;
-}
-
-int pick_tpa(const b200md_ctx *ctx, int nlocal, long long total_entries) {
-  // enough lanes per atom to coalesce the CSR row reads, fewer when the rows are short
-  const double avg = nlocal > 0 ? (double)total_entries / nlocal : 0.0;
-  if (avg >= 256.0) return 8;
-  if (avg >= 48.0) return 8;
-  if (avg >= 16.0) return 4;
-  (void)ctx;
-  return 4;
-}
-
-template <int STYLE, class flt_t, int EVFLAG>
-int launch_tpa(b200md_ctx *ctx, const PairView &v, int tpa, const PairConsts<flt_t> &pc, const flt_t *coeff,
-               const flt_t *ctab, const flt_t *dtab, double *ev_partial, int nblocks) {
-  typedef typename V4<flt_t>::type vec4;
-#define LAUNCH(T)                                                                                          \
-  k_pair<STYLE, flt_t, EVFLAG, T><<<nblocks, 256, 0, ctx->stream>>>(                                        \
-      v.nlocal, (const vec4 *)v.x, v.type, v.numneigh, v.offsets, v.entries, pc, coeff, ctab, dtab, v.f, \
-      ev_partial)
-  switch (tpa) {
-    case 4: LAUNCH(4); break;
-    case 8: LAUNCH(8); break;
-    case 16: LAUNCH(16); break;
-    default: LAUNCH(32); break;
-  }
-#undef LAUNCH
-  KERNEL_OK(ctx, "k_pair");
-  return 0;
-}
-
-template <class flt_t>
-int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int evflag, double *ev_dev) {
-  PairState &ps = ctx->pair;
-  PairConsts<flt_t> pc = make_consts<flt_t>(ps);
-  pc.qqrd2e = (flt_t)ctx->qqrd2e;
-  const flt_t *coeff, *ctab, *dtab;
-  if (sizeof(flt_t) == 8) {
-    coeff = (const flt_t *)ps.coeff_d.p; ctab = (const flt_t *)ps.ctab_d.p; dtab = (const flt_t *)ps.dtab_d.p;
-  } else {
-    coeff = (const flt_t *)ps.coeff_f.p; ctab = (const flt_t *)ps.ctab_f.p; dtab = (const flt_t *)ps.dtab_f.p;
-  }
-  const int tpa = pick_tpa(ctx, v.nlocal, total_entries);
-  const int nblocks = cdiv((long)v.nlocal * tpa, 256);
-  if (nblocks == 0) {
-    if (evflag) CUDA_OK(ctx, cudaMemsetAsync(ev_dev, 0, 8 * sizeof(double), ctx->stream));
-    return 0;
-  }
-  if (evflag) RESERVE(ctx, ctx->ev_partial, (size_t)nblocks * 8);
-  double *evp = ctx->ev_partial.p;
-#define STYLE_CASE(S)                                                                              \
-  case S:                                                                                          \
-    if (evflag) TRY((launch_tpa<S, flt_t, 1>(ctx, v, tpa, pc, coeff, ctab, dtab, evp, nblocks)));  \
-    else TRY((launch_tpa<S, flt_t, 0>(ctx, v, tpa, pc, coeff, ctab, dtab, evp, nblocks)));         \
-    break;
-  switch (ps.p.style) {
-    STYLE_CASE(B200MD_PAIR_BUCK)
-    STYLE_CASE(B200MD_PAIR_BUCK_COUL_CUT)
-    STYLE_CASE(B200MD_PAIR_BUCK_COUL_LONG)
-    STYLE_CASE(B200MD_PAIR_BUCK_LONG_COUL_LONG)
-    default: return b2_fail(ctx, B200MD_EINVAL, "unknown pair style %d", ps.p.style);
-  }
-#undef STYLE_CASE
-  if (evflag) {
-    k_ev_reduce<<<1, 256, 0, ctx->stream>>>(nblocks, evp, ev_dev);
-    KERNEL_OK(ctx, "k_ev_reduce");
-  }
-  return 0;
-}
 
 int finish_ev(b200md_ctx *ctx, int eflag, int vflag, double *ev) {
   // copy back ev_out[0..8) and mask by the flags actually requested (ev_setup semantics)
@@ -382,8 +62,8 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev) {
   v.offsets = ctx->neigh.offsets.p;
   v.entries = ctx->neigh.entries.p;
   v.f = ctx->f.p;
-  if (ctx->prec == B200MD_PREC_MIXED) TRY(launch_pair<float>(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p));
-  else TRY(launch_pair<double>(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p));
+  if (ctx->prec == B200MD_PREC_MIXED) TRY(b2_launch_pair_float(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p));
+  else TRY(b2_launch_pair_double(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p));
   if (evflag) TRY(finish_ev(ctx, eflag, vflag, ev));
   return 0;
 }
@@ -529,8 +209,8 @@ int b200md_pair_eval_host(b200md_ctx *ctx, int eflag, int vflag, int nlocal, int
   v.nlocal = nlocal;
   v.x = mixed ? (const void *)dxqf.p : (const void *)dxq.p;
   v.type = dtype.p; v.numneigh = dnum.p; v.offsets = doff.p; v.entries = dent.p; v.f = df.p;
-  rc = mixed ? launch_pair<float>(ctx, v, total, evflag, ctx->ev_out.p)
-             : launch_pair<double>(ctx, v, total, evflag, ctx->ev_out.p);
+  rc = mixed ? b2_launch_pair_float(ctx, v, total, evflag, ctx->ev_out.p)
+             : b2_launch_pair_double(ctx, v, total, evflag, ctx->ev_out.p);
   if (!rc) {
     cudaMemcpyAsync(f, df.p, (size_t)nlocal * sizeof(double4), cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);

@@ -185,13 +185,27 @@ __global__ void k_q_moments(int n, const double4 *__restrict__ xq, const int *__
 // ---------------------------------------------------------------------------------------------
 // per-step: particle_map + sort by cell
 
+// particle_map<flt_t,acc_t>, pppm_intel.cpp:344-372: index arithmetic in flt_t, un-fused (mul then add) like the
+// reference's AVX build so the integer cell of an atom is the same on both sides
+__device__ __forceinline__ int map1(double x, double lo, double xi, double fshift) {
+  return static_cast<int>(__dadd_rn(__dmul_rn(__dsub_rn(x, lo), xi), fshift)) - PPPM_OFFSET;
+}
+__device__ __forceinline__ int map1(float x, float lo, float xi, float fshift) {
+  return static_cast<int>(__fadd_rn(__fmul_rn(__fsub_rn(x, lo), xi), fshift)) - PPPM_OFFSET;
+}
 template <class flt_t>
 __device__ __forceinline__ void map_atom(const PppmConst &c, flt_t x, flt_t y, flt_t z, int &nx, int &ny, int &nz) {
-  // particle_map<flt_t,acc_t>, pppm_intel.cpp:344-372 (index arithmetic in flt_t)
   const flt_t fshift = (flt_t)c.shift;
-  nx = static_cast<int>((x - (flt_t)c.boxlo[0]) * (flt_t)c.delinv[0] + fshift) - PPPM_OFFSET;
-  ny = static_cast<int>((y - (flt_t)c.boxlo[1]) * (flt_t)c.delinv[1] + fshift) - PPPM_OFFSET;
-  nz = static_cast<int>((z - (flt_t)c.boxlo[2]) * (flt_t)c.delinv[2] + fshift) - PPPM_OFFSET;
+  nx = map1(x, (flt_t)c.boxlo[0], (flt_t)c.delinv[0], fshift);
+  ny = map1(y, (flt_t)c.boxlo[1], (flt_t)c.delinv[1], fshift);
+  nz = map1(z, (flt_t)c.boxlo[2], (flt_t)c.delinv[2], fshift);
+}
+// dx = nx + fshiftone - (x - lo)*xi (pppm_intel.cpp:469-471), operands in flt_t
+__device__ __forceinline__ double frac1(int n, double so, double x, double lo, double xi) {
+  return __dsub_rn(__dadd_rn((double)n, so), __dmul_rn(__dsub_rn(x, lo), xi));
+}
+__device__ __forceinline__ double frac1(int n, float so, float x, float lo, float xi) {
+  return (double)__fsub_rn(__fadd_rn((float)n, so), __fmul_rn(__fsub_rn(x, lo), xi));
 }
 
 template <class flt_t>
@@ -249,19 +263,18 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
   if (sizeof(flt_t) == 4) {
     const float4 p = xqf[i];
     map_atom<float>(c, p.x, p.y, p.z, nx, ny, nz);
-    // FFT_SCALAR dx = nx + fshiftone - (x - lo)*xi with float operands (pppm_intel.cpp:469-471)
     const float so = (float)c.shiftone;
-    dx = (double)(nx + so - (p.x - (float)c.boxlo[0]) * (float)c.delinv[0]);
-    dy = (double)(ny + so - (p.y - (float)c.boxlo[1]) * (float)c.delinv[1]);
-    dz = (double)(nz + so - (p.z - (float)c.boxlo[2]) * (float)c.delinv[2]);
+    dx = frac1(nx, so, p.x, (float)c.boxlo[0], (float)c.delinv[0]);
+    dy = frac1(ny, so, p.y, (float)c.boxlo[1], (float)c.delinv[1]);
+    dz = frac1(nz, so, p.z, (float)c.boxlo[2], (float)c.delinv[2]);
     const float qw = Btype ? (float)Btype[type[i]] : p.w;
-    w = (double)((float)c.delvolinv * qw);
+    w = (double)__fmul_rn((float)c.delvolinv, qw);
   } else {
     const double4 p = xq[i];
     map_atom<double>(c, p.x, p.y, p.z, nx, ny, nz);
-    dx = nx + c.shiftone - (p.x - c.boxlo[0]) * c.delinv[0];
-    dy = ny + c.shiftone - (p.y - c.boxlo[1]) * c.delinv[1];
-    dz = nz + c.shiftone - (p.z - c.boxlo[2]) * c.delinv[2];
+    dx = frac1(nx, c.shiftone, p.x, c.boxlo[0], c.delinv[0]);
+    dy = frac1(ny, c.shiftone, p.y, c.boxlo[1], c.delinv[1]);
+    dz = frac1(nz, c.shiftone, p.z, c.boxlo[2], c.delinv[2]);
     w = c.delvolinv * (Btype ? Btype[type[i]] : p.w);
   }
   pa_x[k] = make_double4(dx, dy, dz, w);

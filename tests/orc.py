@@ -260,6 +260,25 @@ def pair_forces_periodic(params, prec, x, type_, q, boxlo, boxhi, skin, eflag=1,
     return f[:n], ev, dict(x=xa, type=ta, q=qa, src=src, shift=shift, numneigh=nn, offsets=off, entries=ent)
 
 
+def pair_forces_periodic_newtoff(params, prec, x, type_, q, boxlo, boxhi, skin, eflag=1, vflag=1, nthreads=0, eatom=0):
+    """The reference's NEWTON_PAIR = 0 configuration (eval<EVFLAG,EFLAG,0>, pair_buck_intel.cpp:109-110): half list
+    with newton off = owned-owned pairs once (j > i), owned-ghost pairs from each side, f[j] only for owned j.
+    This is the configuration the device path mirrors (each side of a cross-boundary pair uses its own image)."""
+    n = len(x)
+    cutneighmax = params.cutmax() + skin
+    xa, ta, qa, src, shift = make_ghosts(x, type_, q, boxlo, boxhi, cutneighmax)
+    fn, foff, fent = neigh_full_brute(n, xa, ta, params.ntypes, params.cutneighsq(skin), prec)
+    i = np.repeat(np.arange(n), fn)
+    j = fent & NEIGHMASK
+    keep = (j >= n) | (j > i)
+    nn = np.bincount(i[keep], minlength=n).astype(np.int32)
+    off = np.zeros(n + 1, np.int64)
+    off[1:] = np.cumsum(nn)
+    ent = fent[keep]
+    f, ev = pair_eval(params, prec, eflag, vflag, n, xa, ta, qa, nn, off, ent, newton=0, eatom=eatom, nthreads=nthreads)
+    return f[:n], ev
+
+
 class PPPM:
     def __init__(self, nx, ny, nz, order, g_ewald, boxlo, boxhi, qqrd2e, diff_ad=0, prec=DOUBLE):
         self.h = lib().orc_pppm_create(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order),

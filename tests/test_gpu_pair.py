@@ -97,7 +97,23 @@ def test_pair_forces_energy_virial(pkg, W, orc, case, tables, prec):
     fo, evo, aux = orc.pair_forces_periodic(P, prec, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3,
                                             eflag=3, vflag=1, eatom=1)
     err = util.rel_force_err(d["f"], fo[:, :3])
-    assert err <= TOL_F[prec], "force error %g" % err
+    if prec == 0:
+        assert err <= TOL_F[0], "force error %g" % err
+    else:
+        # Mixed mode stores positions in float (thr_pack), so a pair that straddles the periodic boundary has a
+        # slightly different float distance seen from either side (float(x_k + L) - float(x_i) vs
+        # float(x_k) - float(x_i - L)); exp(-r/rho) amplifies that ulp ~50x.  The newton-on half list evaluates such
+        # a pair once, the device (newton off) from both sides — exactly like the reference's own NEWTON_PAIR=0
+        # path, which is therefore the 1e-5 comparison; against the newton-on arm the image noise remains.
+        fn_, evn = orc.pair_forces_periodic_newtoff(P, prec, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3,
+                                                    eflag=3, vflag=1, eatom=1)
+        errn = util.rel_force_err(d["f"], fn_[:, :3])
+        fd, _, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3, 0, 0)
+        print("mixed: gpu-vs-oracle(mixed,newton off) %.2e  gpu-vs-oracle(mixed,newton on) %.2e  "
+              "oracle(mixed)-vs-oracle(double) %.2e" % (errn, err, util.rel_force_err(fo[:, :3], fd[:, :3])))
+        assert errn <= TOL_F[1], "force error %g" % errn
+        assert err <= 5e-5
+        assert np.abs(evn[:2] - evo[:2]).max() <= 1e-6 * np.abs(evo[:2]).max()
     escale = max(abs(evo[0]), abs(evo[1]))
     assert abs(ev[0] - evo[0]) <= TOL_E[prec] * escale
     assert abs(ev[1] - evo[1]) <= TOL_E[prec] * escale
