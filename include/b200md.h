@@ -189,6 +189,12 @@ int b200md_nve_final_integrate(b200md_ctx *ctx);
  * last step when thermo != NULL: thermo[0..7] = pair ev, [8] = kspace energy, [9..14] kspace virial,
  * [15] = kinetic energy (sum 1/2 m v^2, mass units). */
 int b200md_run(b200md_ctx *ctx, long nsteps, double *thermo /*16 or NULL*/);
+/* same, bracketed by CUDA events on the library's stream: *elapsed_ms is device time of the nsteps */
+int b200md_run_timed(b200md_ctx *ctx, long nsteps, double *thermo, double *elapsed_ms);
+/* one timestep through HOST buffers (the plug-in deployment where LAMMPS keeps atom->x/f on the host):
+ * H2D of x_in[n][3] (NULL: keep device positions), one step, D2H of x_out and f_out ([n][3], may be NULL).
+ * Pass pinned memory for full PCIe speed. */
+int b200md_step_host(b200md_ctx *ctx, const double *x_in, double *x_out, double *f_out);
 /* forces only (setup phase of a run: build + pair + kspace), energies in thermo like b200md_run */
 int b200md_setup_forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo);
 
@@ -200,6 +206,9 @@ int b200md_timers_get(b200md_ctx *ctx, double *ms, long *calls, int n);
 int b200md_timers_reset(b200md_ctx *ctx);
 int b200md_timer_count(void);
 const char *b200md_timer_name(int i);
+/* roofline denominators measured on this device ("P_fp measured on the box by a microbenchmark"):
+ * kind 0 = FP64 FMA TFLOP/s, 1 = FP32 FMA TFLOP/s, 2 = HBM copy GB/s (read+write bytes).  Not a reference API. */
+int b200md_microbench(b200md_ctx *ctx, int kind, double *value);
 /* number of kernels this library launched since ctx creation (bench.py's gpu_launches) */
 long b200md_launch_count(const b200md_ctx *ctx);
 

@@ -240,6 +240,75 @@ def init_coul_tables(cut_coul, g_ewald, qqrd2e, nbits=12, tabinner=np.sqrt(2.0))
     return t, nmask, nshiftbits, tabinnersq
 
 
+_ACONS = {
+    1: [2.0 / 3.0],
+    2: [1.0 / 50.0, 5.0 / 294.0],
+    3: [1.0 / 588.0, 7.0 / 1440.0, 21.0 / 3872.0],
+    4: [1.0 / 4320.0, 3.0 / 1936.0, 7601.0 / 2271360.0, 143.0 / 28800.0],
+    5: [1.0 / 23232.0, 7601.0 / 13628160.0, 143.0 / 69120.0, 517231.0 / 106536960.0, 106640677.0 / 11737571328.0],
+    6: [691.0 / 68140800.0, 13.0 / 57600.0, 47021.0 / 35512320.0, 9694607.0 / 2095994880.0,
+        733191589.0 / 59609088000.0, 326190917.0 / 11700633600.0],
+    7: [1.0 / 345600.0, 3617.0 / 35512320.0, 745739.0 / 838397952.0, 56399353.0 / 12773376000.0,
+        25091609.0 / 1560084480.0, 1755948832039.0 / 36229939200000.0, 4887769399.0 / 37838389248.0],
+}
+
+
+def pppm_init(accuracy_relative, qqrd2e, q, natoms, cutoff, prd, order=5, mesh=None, gewald=None,
+              two_charge_force=None):
+    """PPPM::init -> set_grid_global -> adjust_gewald for ik differentiation (SURVEY App. A.5): returns
+    ((nx,ny,nz), g_ewald).  `q` is the charge array (qsqsum = sum q^2) or qsqsum itself.
+    mesh / gewald mimic `kspace_modify mesh` / `kspace_modify gewald`."""
+    from math import exp, log, sqrt, pi
+    qsqsum = float(np.sum(np.asarray(q, dtype=np.float64) ** 2)) if np.ndim(q) else float(q)
+    tcf = qqrd2e if two_charge_force is None else two_charge_force
+    accuracy = accuracy_relative * tcf
+    q2 = qsqsum * qqrd2e
+    xprd, yprd, zprd = (float(v) for v in prd)
+
+    def est(h, p, g):
+        hg = h * g
+        ssum = sum(a * hg ** (2.0 * m) for m, a in enumerate(_ACONS[order]))
+        return q2 * hg ** order * sqrt(g * p * sqrt(2.0 * pi) * ssum / natoms) / (p * p)
+
+    g = gewald
+    if g is None:
+        g = accuracy * sqrt(natoms * cutoff * xprd * yprd * zprd) / (2.0 * q2)
+        g = (1.35 - 0.15 * log(accuracy)) / cutoff if g >= 1.0 else sqrt(-log(g)) / cutoff
+    if mesh is None:
+        n = []
+        for p in (xprd, yprd, zprd):
+            h = 1.0 / g
+            k = int(p / h) + 1
+            err = est(h, p, g)
+            while err > accuracy:
+                err = est(h, p, g)
+                k += 1
+                h = p / k
+            n.append(k)
+    else:
+        n = list(mesh)
+
+    def factorable(k):
+        for f in (2, 3, 5):
+            while k % f == 0:
+                k //= f
+        return k == 1
+
+    n = [next(k for k in range(v, 100000) if factorable(k)) for v in n]
+    hs = [xprd / n[0], yprd / n[1], zprd / n[2]]
+    if gewald is None:
+        def nr_f(gg):
+            df_r = 2.0 * q2 * exp(-gg * gg * cutoff * cutoff) / sqrt(natoms * cutoff * xprd * yprd * zprd)
+            l = [est(hs[0], xprd, gg), est(hs[1], yprd, gg), est(hs[2], zprd, gg)]
+            return df_r - sqrt(l[0] ** 2 + l[1] ** 2 + l[2] ** 2) / sqrt(3.0)
+        for _ in range(10000):
+            f1, f2 = nr_f(g), nr_f(g + 1e-6)
+            g -= f1 / ((f2 - f1) / 1e-6)
+            if abs(nr_f(g)) < 1e-5:
+                break
+    return tuple(n), g
+
+
 class Context:
     """One device context (= FixIntel + IntelBuffers + the resident atom state)."""
 
@@ -427,6 +496,15 @@ class Context:
         self._ck(self.lib.b200md_run(self.h, C.c_long(nsteps), _d(th)))
         return th
 
+    def run_timed(self, nsteps):
+        ms = C.c_double(0.0)
+        self._ck(self.lib.b200md_run_timed(self.h, C.c_long(nsteps), None, C.byref(ms)))
+        return ms.value
+
+    def step_host(self, x_in, x_out, f_out):
+        """x_in/x_out/f_out: C-contiguous float64 [n,3] numpy arrays (pinned for speed) or None"""
+        self._ck(self.lib.b200md_step_host(self.h, _d(x_in), _d(x_out), _d(f_out)))
+
     # ---- timers -------------------------------------------------------------------------------------
     def timers_enable(self, on=True):
         self._ck(self.lib.b200md_timers_enable(self.h, C.c_int(1 if on else 0)))
@@ -440,6 +518,11 @@ class Context:
         calls = np.zeros(n, np.int64)
         self._ck(self.lib.b200md_timers_get(self.h, _d(ms), _l(calls), C.c_int(n)))
         return {self.lib.b200md_timer_name(C.c_int(i)).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
+
+    def microbench(self, kind):
+        v = C.c_double(0.0)
+        self._ck(self.lib.b200md_microbench(self.h, C.c_int(kind), C.byref(v)))
+        return v.value
 
     def launch_count(self):
         return int(self.lib.b200md_launch_count(self.h))

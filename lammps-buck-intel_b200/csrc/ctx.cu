@@ -7,6 +7,7 @@
 #include "internal.h"
 
 static std::string g_create_error;
+static void harvest_timers(b200md_ctx *ctx);
 
 int b2_fail(b200md_ctx *ctx, int code, const char *fmt, ...) {
   char buf[1024];
@@ -69,6 +70,23 @@ __global__ void to_float_copy(int first, int count, const double4 *__restrict__ 
   if (i >= count) return;
   const double4 p = xq[first + i];
   xqf[first + i] = make_float4((float)p.x, (float)p.y, (float)p.z, (float)p.w);
+}
+
+// measurement helpers (bench.py roofline denominators): register-resident FMA chains, and a plain copy
+template <class T>
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, T seed, T *__restrict__ out) {
+  T a0 = seed + threadIdx.x, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3, a4 = a0 + (T)4, a5 = a0 + (T)5,
+    a6 = a0 + (T)6, a7 = a0 + (T)7;
+  const T m = (T)0.999999, c = (T)1e-6;
+  for (int i = 0; i < iters; i++) {
+    a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+    a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+  }
+  const T s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == (T)-12345.678) out[0] = s;
+}
+__global__ void k_copy16(size_t n, const double2 *__restrict__ in, double2 *__restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
 }  // namespace
@@ -146,6 +164,8 @@ void b200md_ctx_destroy(b200md_ctx *ctx) {
   ns.perm.free_(); ns.ghost_src.free_(); ns.ghost_shift.free_(); ns.ghost_cnt.free_();
   ns.numneigh.free_(); ns.offsets.free_(); ns.entries.free_(); ns.xhold.free_(); ns.flags.free_();
   ns.scan_ws.free_(); ns.tmp4a.free_(); ns.tmp4b.free_(); ns.tmpi_a.free_(); ns.tmpi_b.free_();
+  harvest_timers(ctx);
+  for (cudaEvent_t e : ctx->t_pool) cudaEventDestroy(e);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -276,8 +296,25 @@ int b200md_timers_enable(b200md_ctx *ctx, int on) {
   ctx->timers_on = on != 0;
   return 0;
 }
+static void harvest_timers(b200md_ctx *ctx) {
+  if (ctx->t_pending.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &r : ctx->t_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ctx->t_ms[r.id] += ms;
+      ctx->t_calls[r.id]++;
+    }
+    ctx->t_pool.push_back(r.a);
+    ctx->t_pool.push_back(r.b);
+  }
+  ctx->t_pending.clear();
+}
+
 int b200md_timers_get(b200md_ctx *ctx, double *ms, long *calls, int n) {
   if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  harvest_timers(ctx);
   for (int i = 0; i < n && i < T_COUNT; i++) {
     if (ms) ms[i] = ctx->t_ms[i];
     if (calls) calls[i] = ctx->t_calls[i];
@@ -286,9 +323,48 @@ int b200md_timers_get(b200md_ctx *ctx, double *ms, long *calls, int n) {
 }
 int b200md_timers_reset(b200md_ctx *ctx) {
   if (!ctx) return B200MD_EINVAL;
+  harvest_timers(ctx);
   for (int i = 0; i < T_COUNT; i++) { ctx->t_ms[i] = 0; ctx->t_calls[i] = 0; }
   return 0;
 }
+// kind 0: FP64 FMA TFLOP/s, 1: FP32 FMA TFLOP/s, 2: HBM copy GB/s (read + write bytes).  Best of 5.
+int b200md_microbench(b200md_ctx *ctx, int kind, double *value) {
+  if (!ctx || !value) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0.0;
+  DevBuf<double2> buf;
+  const size_t ncopy = (size_t)1 << 26;  // 2 x 1 GiB
+  if (kind == 2 && buf.reserve(2 * ncopy)) return b2_fail(ctx, B200MD_ENOMEM, "microbench: out of memory");
+  RESERVE(ctx, ctx->ev_out, 32);
+  for (int rep = 0; rep < 6; rep++) {
+    const int iters = 1 << 14, blocks = ctx->sm_count * 8;
+    cudaEventRecord(a, ctx->stream);
+    if (kind == 0) k_fma_peak<double><<<blocks, 256, 0, ctx->stream>>>(iters, 1.0, ctx->ev_out.p);
+    else if (kind == 1) k_fma_peak<float><<<blocks, 256, 0, ctx->stream>>>(iters, 1.0f, (float *)ctx->ev_out.p);
+    else k_copy16<<<ctx->sm_count * 16, 512, 0, ctx->stream>>>(ncopy, buf.p, buf.p + ncopy);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    ctx->launches++;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep == 0) continue;  // warm-up
+    double v;
+    if (kind == 2) v = 2.0 * ncopy * sizeof(double2) / (ms * 1e-3) / 1e9;
+    else v = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+    best = v > best ? v : best;
+  }
+  buf.free_();
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return b2_fail(ctx, B200MD_ECUDA, "microbench failed: %s", cudaGetErrorString(e));
+  *value = best;
+  return 0;
+}
+
 int b200md_timer_count(void) { return T_COUNT; }
 const char *b200md_timer_name(int i) { return i >= 0 && i < T_COUNT ? kTimerNames[i] : ""; }
 long b200md_launch_count(const b200md_ctx *ctx) { return ctx ? ctx->launches : 0; }

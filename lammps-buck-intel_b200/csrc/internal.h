@@ -137,12 +137,22 @@ struct b200md_ctx {
   DevBuf<double> ev_partial;  // [nblocks][8]
   DevBuf<double> ev_out;      // [32]
 
-  // timers
+  // timers: event pairs are recorded on the launching stream without synchronising; elapsed times are
+  // harvested when the caller asks (b200md_timers_get), so a timed region is not perturbed
   bool timers_on = false;
   double t_ms[T_COUNT] = {0};
   long t_calls[T_COUNT] = {0};
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  struct TimerRec { int id; cudaEvent_t a, b; };
+  std::vector<TimerRec> t_pending;
+  std::vector<cudaEvent_t> t_pool;
   long launches = 0;
+  cudaEvent_t timer_event() {
+    if (!t_pool.empty()) { cudaEvent_t e = t_pool.back(); t_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
 };
 
 // ---- error helpers ---------------------------------------------------------------------------
@@ -183,17 +193,18 @@ int b2_fail(b200md_ctx *ctx, int code, const char *fmt, ...);
 struct ScopedTimer {
   b200md_ctx *c;
   int id;
+  cudaEvent_t a = nullptr;
   ScopedTimer(b200md_ctx *ctx, int id_) : c(ctx), id(id_) {
-    if (c->timers_on) cudaEventRecord(c->ev_a, c->stream);
+    if (c->timers_on) {
+      a = c->timer_event();
+      cudaEventRecord(a, c->stream);
+    }
   }
   ~ScopedTimer() {
-    if (c->timers_on) {
-      cudaEventRecord(c->ev_b, c->stream);
-      cudaEventSynchronize(c->ev_b);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-      c->t_ms[id] += ms;
-      c->t_calls[id]++;
+    if (a) {
+      cudaEvent_t b = c->timer_event();
+      cudaEventRecord(b, c->stream);
+      c->t_pending.push_back({id, a, b});
     }
   }
 };

@@ -181,6 +181,27 @@ int b200md_setup_forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo) {
   return 0;
 }
 
+int b200md_run_timed(b200md_ctx *ctx, long nsteps, double *thermo, double *elapsed_ms) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  TRY(b200md_run(ctx, nsteps, thermo));
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_b));
+  float ms = 0;
+  CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+int b200md_step_host(b200md_ctx *ctx, const double *x_in, double *x_out, double *f_out) {
+  if (!ctx) return B200MD_EINVAL;
+  if (x_in) TRY(b200md_atoms_set_x(ctx, x_in));
+  TRY(b200md_run(ctx, 1, nullptr));
+  return b200md_atoms_download(ctx, x_out, nullptr, f_out, nullptr);
+}
+
 int b200md_run(b200md_ctx *ctx, long nsteps, double *thermo) {
   if (!ctx) return B200MD_EINVAL;
   cudaSetDevice(ctx->device);

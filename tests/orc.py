@@ -372,3 +372,43 @@ def nve_final(v, f, dtfm):
     v = f64(v).copy()
     lib().orc_nve_final(C.c_int(len(v)), _d(v), _d(f64(f)), _d(f64(dtfm)))
     return v
+
+
+class MD:
+    """whole-timestep CPU loop (oracle/md.cpp) — CPU baseline and trajectory parity"""
+
+    def __init__(self, system, params, prec=DOUBLE, skin=0.3, every=1, delay=0, check=1, dt=0.001, ftm2v=1.0, pppm=None):
+        s = system
+        n = len(s["x"])
+        self.n = n
+        self.params, self.pppm = params, pppm
+        q = f64(s["q"]) if s.get("q") is not None else None
+        lib().orc_md_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().orc_md_create(
+            C.c_int(n), _d(f64(s["x"])), _d(f64(s["v"])) if s.get("v") is not None else None,
+            _d(q) if q is not None else None, _i(i32(s["type"])), C.c_int(s["ntypes"]), _d(f64(s["mass"])),
+            _d(f64(s["boxlo"])), _d(f64(s["boxhi"])), C.c_int(params.style), C.c_int(prec), C.byref(params.p),
+            C.c_double(skin), C.c_int(every), C.c_int(delay), C.c_int(check), C.c_double(dt), C.c_double(ftm2v),
+            pppm.h if pppm is not None else None))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_md_destroy(self.h)
+            self.h = None
+
+    def run(self, nsteps, nthreads=0):
+        timers = np.zeros(8)
+        nb = C.c_int(0)
+        lib().orc_md_run(self.h, C.c_int(nsteps), C.c_int(nthreads), _d(timers), C.byref(nb))
+        return dict(neigh=timers[0], pair=timers[1], kspace=timers[2], nve=timers[3], comm=timers[4], nbuilds=nb.value)
+
+    def get(self):
+        x = np.zeros((self.n, 3)); v = np.zeros((self.n, 3)); f = np.zeros((self.n, 3))
+        lib().orc_md_get(self.h, _d(x), _d(v), _d(f))
+        return x, v, f
+
+    def energy(self, nthreads=0):
+        ev = np.zeros(8)
+        ek = C.c_double(0.0); ke = C.c_double(0.0)
+        lib().orc_md_energy(self.h, C.c_int(nthreads), _d(ev), C.byref(ek), C.byref(ke))
+        return ev, ek.value, ke.value
