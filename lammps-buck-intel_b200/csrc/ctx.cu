@@ -7,7 +7,21 @@
 #include "internal.h"
 
 static std::string g_create_error;
-static void harvest_timers(b200md_ctx *ctx);
+static void harvest_timers(b200md_ctx *ctx) {
+  if (ctx->t_pending.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &r : ctx->t_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ctx->t_ms[r.id] += ms;
+      ctx->t_calls[r.id]++;
+    }
+    ctx->t_pool.push_back(r.a);
+    ctx->t_pool.push_back(r.b);
+  }
+  ctx->t_pending.clear();
+}
+
 
 int b2_fail(b200md_ctx *ctx, int code, const char *fmt, ...) {
   char buf[1024];
@@ -296,21 +310,6 @@ int b200md_timers_enable(b200md_ctx *ctx, int on) {
   ctx->timers_on = on != 0;
   return 0;
 }
-static void harvest_timers(b200md_ctx *ctx) {
-  if (ctx->t_pending.empty()) return;
-  cudaStreamSynchronize(ctx->stream);
-  for (auto &r : ctx->t_pending) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-      ctx->t_ms[r.id] += ms;
-      ctx->t_calls[r.id]++;
-    }
-    ctx->t_pool.push_back(r.a);
-    ctx->t_pool.push_back(r.b);
-  }
-  ctx->t_pending.clear();
-}
-
 int b200md_timers_get(b200md_ctx *ctx, double *ms, long *calls, int n) {
   if (!ctx) return B200MD_EINVAL;
   cudaSetDevice(ctx->device);
