@@ -111,7 +111,8 @@ class ClockSampler:
 
 def workload(W, rep, rank=0, nranks=1):
     """data.aC x rep^3 per GPU; ranks stack along z (weak scaling: per-GPU work fixed)."""
-    s = W.aC_system((rep, rep, rep * nranks))
+    # as the shipped script: the crystal of data.aC as read, `velocity all create 300.0` (no displacement)
+    s = W.aC_system((rep, rep, rep * nranks), jitter=0.0)
     return s
 
 
@@ -270,7 +271,7 @@ def cpu_setup(W, rep):
     orc = graft.load_oracle()
     pkg = graft.load_package()
     u = W.UNITS["metal"]
-    s = W.aC_system(rep)
+    s = W.aC_system(rep, jitter=0.0)
     natoms = len(s["x"])
     grid, g_ewald = pkg.pppm_init(ACC, u["qqrd2e"], s["q"], natoms, CUT, s["boxhi"] - s["boxlo"], order=ORDER)
     co = W.coeffs_aC(CUT, CUT)

@@ -193,57 +193,116 @@ struct Pos<float> {
   }
 };
 
-// one warp per owned atom; FILL = 0 counts, FILL = 1 writes the row at offsets[i]
+// One BLOCK per bin.  The block stages the positions/types of all candidate atoms of the bin's stencil (25 (y,z)
+// rows x {owned range, ghost range}, each one contiguous index range) in shared memory with coalesced loads, then
+// every warp takes owned atoms of the bin and scans the staged candidates 32 at a time: distance test, ballot,
+// ordered compaction, coalesced stores.  Candidates are read from HBM/L2 once per bin instead of once per atom.
+// FILL = 0 counts (numneigh), FILL = 1 writes the rows at offsets[i].  Candidate order = row order, owned then
+// ghost, ascending index => deterministic rows.
+#define NB_CHUNK 1536     // candidates staged at a time (static shared memory stays under 48 KB)
+#define NB_MAXI 64        // owned atoms of the bin handled per staging sweep
+#define NB_THREADS 512
+
 template <class flt_t, int FILL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NB_THREADS)
 k_build(int nlocal, const typename Pos<flt_t>::vec *__restrict__ x, const int *__restrict__ type,
-        const int *__restrict__ bin_sorted, const int *__restrict__ lstart, const int *__restrict__ gstart,
-        BinGeom g, int tp1, const double *__restrict__ cutneighsq, int *__restrict__ numneigh,
-        const long long *__restrict__ offsets, int *__restrict__ entries, int *__restrict__ maxn) {
+        const int *__restrict__ lstart, const int *__restrict__ gstart, BinGeom g, int tp1,
+        const double *__restrict__ cutneighsq, int *__restrict__ numneigh, const long long *__restrict__ offsets,
+        int *__restrict__ entries, int *__restrict__ maxn) {
   __shared__ flt_t s_cut[(B2_MAXTYPES + 1) * (B2_MAXTYPES + 1)];
-  for (int k = threadIdx.x; k < tp1 * tp1; k += blockDim.x) s_cut[k] = (flt_t)cutneighsq[k];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int i = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (i >= nlocal) return;
-  const typename Pos<flt_t>::vec xi = x[i];
-  const flt_t *cut_i = s_cut + type[i] * tp1;
-  const int b = bin_sorted[i];
-  const int ex = b % g.mbin[0], ey = (b / g.mbin[0]) % g.mbin[1], ez = b / (g.mbin[0] * g.mbin[1]);
-  const int x0 = max(ex - g.s[0], 0), x1 = min(ex + g.s[0], g.mbin[0] - 1);
-  int count = 0;
-  long long w = FILL ? offsets[i] : 0;
-  for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
-    const int rz = ez + dz;
-    if (rz < 0 || rz >= g.mbin[2]) continue;
-    for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
-      const int ry = ey + dy;
-      if (ry < 0 || ry >= g.mbin[1]) continue;
-      const int row = (rz * g.mbin[1] + ry) * g.mbin[0];
-#pragma unroll
-      for (int kind = 0; kind < 2; kind++) {
-        const int *st = kind ? gstart : lstart;
-        const int base = kind ? nlocal : 0;
-        const int j0 = st[row + x0] + base, j1 = st[row + x1 + 1] + base;
-        for (int jb = j0; jb < j1; jb += 32) {
-          const int j = jb + lane;
-          bool hit = false;
-          if (j < j1 && j != i) {
-            const flt_t rsq = Pos<flt_t>::rsq(xi, x[j]);
-            hit = rsq <= cut_i[type[j]];
+  __shared__ flt_t sx[NB_CHUNK], sy[NB_CHUNK], sz[NB_CHUNK];
+  __shared__ int sj[NB_CHUNK];
+  __shared__ unsigned char st[NB_CHUNK];
+  __shared__ int r_start[64], r_pref[65];   // candidate ranges (<= 2 * (2s+1)^2, s <= 2 -> 50) and their prefix sums
+  __shared__ int s_cnt[NB_MAXI];
+  __shared__ int s_nr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NB_THREADS / 32;
+  for (int k = tid; k < tp1 * tp1; k += NB_THREADS) s_cut[k] = (flt_t)cutneighsq[k];
+  // interior bin of this block
+  const int bx = blockIdx.x % g.nbin[0], by = (blockIdx.x / g.nbin[0]) % g.nbin[1], bz = blockIdx.x / (g.nbin[0] * g.nbin[1]);
+  const int ex = bx + g.m[0], ey = by + g.m[1], ez = bz + g.m[2];
+  const int binid = (ez * g.mbin[1] + ey) * g.mbin[0] + ex;
+  const int i0 = lstart[binid], i1 = lstart[binid + 1];
+  if (i0 == i1) return;
+  if (tid == 0) {
+    const int x0 = max(ex - g.s[0], 0), x1 = min(ex + g.s[0], g.mbin[0] - 1);
+    int nr = 0, tot = 0;
+    for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
+      const int rz = ez + dz;
+      if (rz < 0 || rz >= g.mbin[2]) continue;
+      for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
+        const int ry = ey + dy;
+        if (ry < 0 || ry >= g.mbin[1]) continue;
+        const int row = (rz * g.mbin[1] + ry) * g.mbin[0];
+        for (int kind = 0; kind < 2; kind++) {
+          const int *sp = kind ? gstart : lstart;
+          const int base = kind ? nlocal : 0;
+          const int j0 = sp[row + x0] + base, j1 = sp[row + x1 + 1] + base;
+          if (j1 > j0) {
+            r_start[nr] = j0;
+            r_pref[nr] = tot;
+            tot += j1 - j0;
+            nr++;
           }
-          const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (FILL && hit) entries[w + __popc(m & ((1u << lane) - 1))] = j;
-          const int c = __popc(m);
-          count += c;
-          w += c;
         }
       }
     }
+    r_pref[nr] = tot;
+    s_nr = nr;
   }
-  if (!FILL && lane == 0) {
-    numneigh[i] = count;
-    atomicMax(maxn, count);
+  __syncthreads();
+  const int nr = s_nr, ncand = r_pref[nr];
+  for (int ib = i0; ib < i1; ib += NB_MAXI) {
+    const int ni = min(NB_MAXI, i1 - ib);
+    for (int k = tid; k < ni; k += NB_THREADS) s_cnt[k] = 0;
+    for (int c0 = 0; c0 < ncand; c0 += NB_CHUNK) {
+      const int nc = min(NB_CHUNK, ncand - c0);
+      __syncthreads();  // previous chunk fully consumed (and s_cnt zeroed)
+      for (int k = tid; k < nc; k += NB_THREADS) {
+        const int c = c0 + k;
+        int lo = 0, hi = nr - 1;      // range r with r_pref[r] <= c < r_pref[r+1]
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (r_pref[mid] <= c) lo = mid; else hi = mid - 1;
+        }
+        const int j = r_start[lo] + (c - r_pref[lo]);
+        const typename Pos<flt_t>::vec p = x[j];
+        sx[k] = p.x; sy[k] = p.y; sz[k] = p.z;
+        sj[k] = j;
+        st[k] = (unsigned char)type[j];
+      }
+      __syncthreads();
+      for (int ii = warp; ii < ni; ii += nwarps) {
+        const int i = ib + ii;
+        const typename Pos<flt_t>::vec xi = x[i];
+        const flt_t *cut_i = s_cut + type[i] * tp1;
+        int count = s_cnt[ii];
+        const long long w0 = FILL ? offsets[i] : 0;
+        for (int k0 = 0; k0 < nc; k0 += 32) {
+          const int k = k0 + lane;
+          bool hit = false;
+          int j = -1;
+          if (k < nc) {
+            j = sj[k];
+            typename Pos<flt_t>::vec xj;
+            xj.x = sx[k]; xj.y = sy[k]; xj.z = sz[k];
+            const flt_t rsq = Pos<flt_t>::rsq(xi, xj);
+            hit = (j != i) && (rsq <= cut_i[st[k]]);
+          }
+          const unsigned mk = __ballot_sync(0xffffffffu, hit);
+          if (FILL && hit) entries[w0 + count + __popc(mk & ((1u << lane) - 1))] = j;
+          count += __popc(mk);
+        }
+        if (lane == 0) s_cnt[ii] = count;
+      }
+    }
+    __syncthreads();
+    if (!FILL)
+      for (int k = tid; k < ni; k += NB_THREADS) {
+        numneigh[ib + k] = s_cnt[k];
+        atomicMax(maxn, s_cnt[k]);
+      }
+    __syncthreads();
   }
 }
 
@@ -460,13 +519,13 @@ int b2_neigh_build(b200md_ctx *ctx) {
   long long total = 0;
   int maxn = 0;
   if (n > 0) {
-    const int nblk = cdiv((long)n * 32, 256);
+    const int nblk = g.nbin[0] * g.nbin[1] * g.nbin[2];  // one block per interior bin
     if (ctx->prec == B200MD_PREC_MIXED)
-      k_build<float, 0><<<nblk, 256, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, ns.bin_sorted.p, lstart, gstart, g,
+      k_build<float, 0><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, lstart, gstart, g,
                                                       ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p, nullptr,
                                                       nullptr, ns.flags.p + 2);
     else
-      k_build<double, 0><<<nblk, 256, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, ns.bin_sorted.p, lstart, gstart, g,
+      k_build<double, 0><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, lstart, gstart, g,
                                                        ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p, nullptr,
                                                        nullptr, ns.flags.p + 2);
     KERNEL_OK(ctx, "k_build<count>");
@@ -478,11 +537,11 @@ int b2_neigh_build(b200md_ctx *ctx) {
     maxn = *(int *)(ctx->h_pinned + 1);
     RESERVE(ctx, ns.entries, (size_t)total + 64);
     if (ctx->prec == B200MD_PREC_MIXED)
-      k_build<float, 1><<<nblk, 256, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, ns.bin_sorted.p, lstart, gstart, g,
+      k_build<float, 1><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, lstart, gstart, g,
                                                       ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p,
                                                       ns.offsets.p, ns.entries.p, ns.flags.p + 2);
     else
-      k_build<double, 1><<<nblk, 256, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, ns.bin_sorted.p, lstart, gstart, g,
+      k_build<double, 1><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, lstart, gstart, g,
                                                        ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p,
                                                        ns.offsets.p, ns.entries.p, ns.flags.p + 2);
     KERNEL_OK(ctx, "k_build<fill>");

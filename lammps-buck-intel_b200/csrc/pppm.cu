@@ -250,11 +250,17 @@ __global__ void k_cell_order(long ncell, const int *__restrict__ start, int *__r
   }
 }
 
+// per sorted atom: dx,dy,dz + weight (pa_x), lower-left cell + atom index (pa_n), and for the gather the
+// 3*order one-dimensional stencil weights (pa_w, Horner over rho_coeff exactly as pppm_intel.cpp:476-488; rounded
+// to flt_t like the reference's `flt_t rho[3][INTEL_P3M_MAXORDER]`, :474) and the wrapped x cell (pa_cx)
 template <class flt_t>
 __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4 *__restrict__ xq,
                               const float4 *__restrict__ xqf, const int *__restrict__ type,
                               const double *__restrict__ Btype, PppmConst c, double4 *__restrict__ pa_x,
-                              int4 *__restrict__ pa_n) {
+                              int4 *__restrict__ pa_n, double *__restrict__ pa_w, int *__restrict__ pa_cx) {
+  __shared__ double s_rc[B2_MAXORDER * B2_MAXORDER];
+  for (int k = threadIdx.x; k < c.order * c.order; k += blockDim.x) s_rc[k] = c.rho_coeff[k];
+  __syncthreads();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int i = perm[k];
@@ -279,50 +285,157 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
   }
   pa_x[k] = make_double4(dx, dy, dz, w);
   pa_n[k] = make_int4(nx, ny, nz, i);
+  pa_cx[k] = wrapi(nx, c.nx);
+  const int order = c.order;
+  double *wk = pa_w + (size_t)k * (3 * order);
+  for (int t = 0; t < order; t++) {
+    double r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    for (int l = order - 1; l >= 0; l--) {
+      r1 = s_rc[l * order + t] + r1 * dx;
+      r2 = s_rc[l * order + t] + r2 * dy;
+      r3 = s_rc[l * order + t] + r3 * dz;
+    }
+    if (sizeof(flt_t) == 4) { r1 = (double)(float)r1; r2 = (double)(float)r2; r3 = (double)(float)r3; }
+    wk[t] = r1;
+    wk[order + t] = r2;
+    wk[2 * order + t] = r3;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // make_rho as a gather: one thread per grid point
 
-template <class flt_t>
+// One thread per grid point, blocks are 8x8x4 tiles of points so that the threads of a block share atoms (L1).
+// The `order` cells of a (cy,cz) row that can reach the point are consecutive keys, i.e. ONE contiguous range of
+// the sorted atoms (two ranges when the row wraps around the periodic box): 2 loads per row instead of 2 per cell.
 __global__ void __launch_bounds__(256)
 k_make_rho(PppmConst c, const int *__restrict__ cell_start, const double4 *__restrict__ pa_x,
-           double *__restrict__ density) {
-  __shared__ double s_rc[B2_MAXORDER * B2_MAXORDER];
-  for (int k = threadIdx.x; k < c.order * c.order; k += blockDim.x) s_rc[k] = c.rho_coeff[k];
-  __syncthreads();
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
-  if (g >= nfft) return;
-  const int gx = (int)(g % c.nx), gy = (int)((g / c.nx) % c.ny), gz = (int)(g / ((long)c.nx * c.ny));
-  const int order = c.order;
+           const double *__restrict__ pa_w, const int *__restrict__ pa_cx, double *__restrict__ density) {
+  const int tx = threadIdx.x & 7, ty = (threadIdx.x >> 3) & 7, tz = threadIdx.x >> 6;
+  const int gx = blockIdx.x * 8 + tx, gy = blockIdx.y * 8 + ty, gz = blockIdx.z * 4 + tz;
+  if (gx >= c.nx || gy >= c.ny || gz >= c.nz) return;
+  const int order = c.order, w3 = 3 * order;
+  // x cells [gx-nupper, gx-nlower]; l - nlower = gx - cx - nlower (mod nx)
+  const int xlo = gx - c.nupper, xhi = gx - c.nlower;
   double rho = 0.0;
-  // atom with lower-left cell (cx,cy,cz) reaches this point through stencil offsets (l,m,n) =
-  // (gx-cx, gy-cy, gz-cz) in [nlower,nupper]; fixed visiting order n, m, l ascending
   for (int n = c.nlower; n <= c.nupper; n++) {
     const int cz = wrapi(gz - n, c.nz);
     for (int m = c.nlower; m <= c.nupper; m++) {
       const int cy = wrapi(gy - m, c.ny);
       const long row = ((long)cz * c.ny + cy) * c.nx;
-      for (int l = c.nlower; l <= c.nupper; l++) {
-        const int cx = wrapi(gx - l, c.nx);
-        const int s = cell_start[row + cx], e = cell_start[row + cx + 1];
+      // up to two pieces: [max(xlo,0), min(xhi,nx-1)] and the wrapped remainder
+      for (int piece = 0; piece < 2; piece++) {
+        int a0, a1;
+        if (piece == 0) { a0 = max(xlo, 0); a1 = min(xhi, c.nx - 1); }
+        else if (xlo < 0) { a0 = xlo + c.nx; a1 = c.nx - 1; }
+        else if (xhi >= c.nx) { a0 = 0; a1 = xhi - c.nx; }
+        else break;
+        const int s = cell_start[row + a0], e = cell_start[row + a1 + 1];
         for (int a = s; a < e; a++) {
-          const double4 p = pa_x[a];
-          double r1 = 0.0, r2 = 0.0, r3 = 0.0;
-          for (int t = order - 1; t >= 0; t--) {
-            r1 = s_rc[t * order + (l - c.nlower)] + r1 * p.x;
-            r2 = s_rc[t * order + (m - c.nlower)] + r2 * p.y;
-            r3 = s_rc[t * order + (n - c.nlower)] + r3 * p.z;
-          }
-          if (sizeof(flt_t) == 4) {  // flt_t rho[3][INTEL_P3M_MAXORDER] (pppm_intel.cpp:474)
-            r1 = (double)(float)r1; r2 = (double)(float)r2; r3 = (double)(float)r3;
-          }
-          rho += ((p.w * r3) * r2) * r1;  // z0*rho[2] -> y0*rho[1] -> x0*rho[0], :490-501
+          int l = gx - pa_cx[a];              // stencil offset along x, brought back into [nlower,nupper]
+          if (l > c.nupper) l -= c.nx;
+          else if (l < c.nlower) l += c.nx;
+          const double *wk = pa_w + (size_t)a * w3;
+          const double z0 = pa_x[a].w;
+          rho += ((z0 * wk[2 * order + (n - c.nlower)]) * wk[order + (m - c.nlower)]) * wk[l - c.nlower];
         }
       }
     }
   }
+  density[((long)gz * c.ny + gy) * c.nx + gx] = rho;
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_rho, tiled: the production path.  The grid is cut into 8x8x8-cell tiles.  ONE WARP owns one tile: it walks
+// the tile's atoms in sorted order (per (y,z) cell row one contiguous range of the cell-sorted arrays) and adds
+// each atom's order^3 stencil into a warp-private (8+order-1)^3 block of SHARED memory — the 32 lanes cover the
+// stencil points in ceil(order^3/32) rounds, distinct lanes hit distinct addresses, atoms are strictly sequential,
+// so there are no atomics and the summation order is fixed.  The stencil block (tile + halo) is then stored and a
+// second kernel gives every grid point the sum of the <= 8 tile blocks that cover it, in a fixed order (periodic
+// wrap included: this is the ghost-cell fold of cg->reverse_comm, pppm_intel.cpp:185, and brick2fft, :642-672).
+#define RHO_T 8
+
+struct TileGeom {
+  int ntx, nty, ntz, E;   // tiles per dimension, E = RHO_T + order - 1
+};
+
+__global__ void __launch_bounds__(128)
+k_rho_tiles(PppmConst c, TileGeom tg, const int *__restrict__ cell_start, const double4 *__restrict__ pa_x,
+            const double *__restrict__ pa_w, const int *__restrict__ pa_cx, double *__restrict__ tilebuf) {
+  extern __shared__ double s_tiles[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long tile = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
+  if (tile >= ntiles) return;
+  const int E = tg.E, E3 = E * E * E;
+  double *t = s_tiles + (size_t)warp * E3;
+  for (int k = lane; k < E3; k += 32) t[k] = 0.0;
+  __syncwarp();
+  const int tx = (int)(tile % tg.ntx), ty = (int)((tile / tg.ntx) % tg.nty), tz = (int)(tile / ((long)tg.ntx * tg.nty));
+  const int x0 = tx * RHO_T, y0 = ty * RHO_T, z0 = tz * RHO_T;
+  const int x1 = min(x0 + RHO_T, c.nx), y1 = min(y0 + RHO_T, c.ny), z1 = min(z0 + RHO_T, c.nz);
+  const int order = c.order, o2 = order * order, o3 = o2 * order;
+  for (int cz = z0; cz < z1; cz++)
+    for (int cy = y0; cy < y1; cy++) {
+      const long row = ((long)cz * c.ny + cy) * c.nx;
+      const int s = cell_start[row + x0], e = cell_start[row + x1];
+      for (int a = s; a < e; a++) {
+        const double *wk = pa_w + (size_t)a * (3 * order);
+        const double q0 = pa_x[a].w;
+        const int base = ((cz - z0) * E + (cy - y0)) * E + (pa_cx[a] - x0);
+        for (int p = lane; p < o3; p += 32) {
+          const int n = p / o2, r = p - n * o2, m = r / order, l = r - m * order;
+          // z0*rho[2][n] -> y0*rho[1][m] -> x0*rho[0][l]  (pppm_intel.cpp:490-501)
+          t[base + (n * E + m) * E + l] += ((q0 * wk[2 * order + n]) * wk[order + m]) * wk[l];
+        }
+        __syncwarp();
+      }
+    }
+  double *out = tilebuf + (size_t)tile * E3;
+  for (int k = lane; k < E3; k += 32) out[k] = t[k];
+}
+
+// covering tiles of a point along one dimension: every tile (own, and up to two on either side, periodic) whose
+// cells [ulo,uhi] reach the point, i.e. ulo + nlower <= g <= uhi + nupper in the point's unwrapped frame.  Returns
+// the count and, per hit, the tile index and the local coordinate inside that tile's stencil block.
+__device__ __forceinline__ int cover1(int g, int n, int nt, int nlower, int nupper, int *tile, int *loc) {
+  const int t = g / RHO_T;
+  int cnt = 0;
+#pragma unroll
+  for (int dt = -2; dt <= 2; dt++) {
+    int tt = t + dt, shift = 0;
+    if (tt < 0) { tt += nt; shift = -n; }
+    else if (tt >= nt) { tt -= nt; shift = n; }
+    if (tt < 0 || tt >= nt) continue;
+    const int ulo = tt * RHO_T + shift, uhi = min(tt * RHO_T + RHO_T, n) - 1 + shift;
+    if (g >= ulo + nlower && g <= uhi + nupper) {
+      tile[cnt] = tt;
+      loc[cnt] = g - ulo - nlower;
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(256)
+k_rho_fold(PppmConst c, TileGeom tg, const double *__restrict__ tilebuf, double *__restrict__ density) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (g >= nfft) return;
+  const int gx = (int)(g % c.nx), gy = (int)((g / c.nx) % c.ny), gz = (int)(g / ((long)c.nx * c.ny));
+  int txs[5], lxs[5], tys[5], lys[5], tzs[5], lzs[5];
+  const int nxc = cover1(gx, c.nx, tg.ntx, c.nlower, c.nupper, txs, lxs);
+  const int nyc = cover1(gy, c.ny, tg.nty, c.nlower, c.nupper, tys, lys);
+  const int nzc = cover1(gz, c.nz, tg.ntz, c.nlower, c.nupper, tzs, lzs);
+  const int E = tg.E;
+  const size_t E3 = (size_t)E * E * E;
+  double rho = 0.0;
+  for (int k = 0; k < nzc; k++)
+    for (int j = 0; j < nyc; j++)
+      for (int i = 0; i < nxc; i++) {
+        const size_t tile = ((size_t)tzs[k] * tg.nty + tys[j]) * tg.ntx + txs[i];
+        rho += tilebuf[tile * E3 + ((size_t)lzs[k] * E + lys[j]) * E + lxs[i]];
+      }
   density[g] = rho;
 }
 
@@ -601,6 +714,8 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     RESERVE(ctx, ps.perm, (size_t)n + 1);
     RESERVE(ctx, ps.pa_x, (size_t)n + 1);
     RESERVE(ctx, ps.pa_n, (size_t)n + 1);
+    RESERVE(ctx, ps.pa_w, ((size_t)n + 1) * 3 * c.order);
+    RESERVE(ctx, ps.pa_cx, (size_t)n + 1);
     RESERVE(ctx, ps.cell_count, (size_t)nfft + 1);
     RESERVE(ctx, ps.cell_start, (size_t)nfft + 1);
     RESERVE(ctx, ps.cursor, (size_t)nfft + 1);
@@ -621,12 +736,28 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
       KERNEL_OK(ctx, "k_cell_order");
       k_fill_sorted<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.perm.p, v.xq, v.xqf, v.type,
                                                                    ps.p.dispersion ? ps.Btype.p : nullptr, c, ps.pa_x.p,
-                                                                   ps.pa_n.p);
+                                                                   ps.pa_n.p, ps.pa_w.p, ps.pa_cx.p);
       KERNEL_OK(ctx, "k_fill_sorted");
     }
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    k_make_rho<flt_t><<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, ps.cell_start.p, ps.pa_x.p, ps.density.p);
-    KERNEL_OK(ctx, "k_make_rho");
+    if (c.nx >= 2 * RHO_T && c.ny >= 2 * RHO_T && c.nz >= 2 * RHO_T) {
+      TileGeom tg{cdiv(c.nx, RHO_T), cdiv(c.ny, RHO_T), cdiv(c.nz, RHO_T), RHO_T + c.order - 1};
+      const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
+      const size_t E3 = (size_t)tg.E * tg.E * tg.E;
+      RESERVE(ctx, ps.tilebuf, (size_t)ntiles * E3);
+      const int wpb = 4;
+      const size_t smem = wpb * E3 * sizeof(double);
+      CUDA_OK(ctx, cudaFuncSetAttribute(k_rho_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_rho_tiles<<<cdiv(ntiles, wpb), wpb * 32, smem, ctx->stream>>>(c, tg, ps.cell_start.p, ps.pa_x.p, ps.pa_w.p,
+                                                                      ps.pa_cx.p, ps.tilebuf.p);
+      KERNEL_OK(ctx, "k_rho_tiles");
+      k_rho_fold<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, tg, ps.tilebuf.p, ps.density.p);
+      KERNEL_OK(ctx, "k_rho_fold");
+    } else {  // grids smaller than two tiles per dimension: plain per-point gather
+      const dim3 grid(cdiv(c.nx, 8), cdiv(c.ny, 8), cdiv(c.nz, 4));
+      k_make_rho<<<grid, 256, 0, ctx->stream>>>(c, ps.cell_start.p, ps.pa_x.p, ps.pa_w.p, ps.pa_cx.p, ps.density.p);
+      KERNEL_OK(ctx, "k_make_rho");
+    }
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (*(int *)ctx->h_pinned) return b2_fail(ctx, B200MD_ERANGE, "Out of range atoms - cannot compute PPPM");
   }
@@ -700,7 +831,7 @@ void b2_pppm_free(b200md_ctx *ctx) {
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
   ps->work1.free_(); ps->work2.free_(); ps->sf_pre.free_(); ps->Btype.free_();
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
-  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
+  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
   delete ps;
   ctx->pppm = nullptr;
 }
@@ -727,6 +858,8 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     return b2_fail(ctx, B200MD_EORDER, "PPPM order greater than supported by USER-INTEL");
   if (p->nx < 2 || p->ny < 2 || p->nz < 2 || p->nx >= PPPM_OFFSET || p->ny >= PPPM_OFFSET || p->nz >= PPPM_OFFSET)
     return b2_fail(ctx, B200MD_EINVAL, "PPPM grid is too large or too small");
+  if (p->nx < 2 * p->order || p->ny < 2 * p->order || p->nz < 2 * p->order)
+    return b2_fail(ctx, B200MD_EINVAL, "PPPM grid must have at least 2*order points per dimension");
   if (!(p->g_ewald > 0)) return b2_fail(ctx, B200MD_EINVAL, "PPPM needs g_ewald > 0");
   if (p->dispersion && !p->B) return b2_fail(ctx, B200MD_EINVAL, "dispersion PPPM needs B[type]");
   for (int d = 0; d < 3; d++)

@@ -38,6 +38,9 @@ struct PppmState {
   DevBuf<int> key, cell_count, cell_start, cursor, perm, flags;
   DevBuf<double4> pa_x;  // sorted: {dx,dy,dz, weight*delvolinv}
   DevBuf<int4> pa_n;     // sorted: {nx,ny,nz, atom index}
+  DevBuf<double> pa_w;   // sorted: [3*order] one-dimensional stencil weights (x, y, z)
+  DevBuf<double> tilebuf;  // make_rho: per-tile stencil blocks (tile + halo)
+  DevBuf<int> pa_cx;     // sorted: wrapped x cell of the lower-left stencil corner
   DevBuf<unsigned char> scan_ws;
   DevBuf<double> partial, red;
   double qsum = 0, qsqsum = 0;
