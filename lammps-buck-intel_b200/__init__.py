@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + extra_compile_flags()
     jobs, objs = [], []
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
@@ -72,8 +72,24 @@ def build(force=False, verbose=False):
     return LIBPATH
 
 
+def nccl_paths():
+    """(include dir, lib dir) of NCCL: the torch-bundled copy when present (so one libnccl.so.2 serves both torch's
+    bootstrap and this library in the same process), else the system one."""
+    import sysconfig
+    sp = sysconfig.get_paths()["purelib"]
+    inc, lib = os.path.join(sp, "nvidia", "nccl", "include"), os.path.join(sp, "nvidia", "nccl", "lib")
+    if os.path.exists(os.path.join(inc, "nccl.h")) and os.path.exists(os.path.join(lib, "libnccl.so.2")):
+        return inc, lib
+    return "/usr/include", "/usr/lib/x86_64-linux-gnu"
+
+
+def extra_compile_flags():
+    return ["-I", nccl_paths()[0]]
+
+
 def extra_link_flags():
-    return []
+    lib = nccl_paths()[1]
+    return ["-L", lib, "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker", lib]
 
 
 class PairParams(C.Structure):

@@ -20,8 +20,10 @@
 namespace {
 
 struct BinGeom {
-  double lo[3], hi[3], prd[3], bininv[3];
+  double lo[3], hi[3], prd[3], bininv[3];   // the box this rank bins: whole box, or its z slab (multi-GPU)
+  double wlo[3], whi[3], wprd[3];           // the global periodic box (Domain::pbc and image shifts)
   int nbin[3], m[3], mbin[3], s[3], periodic[3];
+  int img[3];                               // 1: periodic images of this dimension are made locally
   double cutghost;
 };
 
@@ -30,24 +32,27 @@ __device__ __forceinline__ int bin_coord(double x, double lo, double bininv, int
   return min(max(b, 0), nbin - 1);
 }
 
-__global__ void k_wrap_bin(int n, double4 *__restrict__ xq, BinGeom g, int *__restrict__ bin_of,
+__global__ void k_wrap_bin(int n, double4 *__restrict__ xq, BinGeom g, int do_wrap, int *__restrict__ bin_of,
                            int *__restrict__ bin_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 p = xq[i];
   double c[3] = {p.x, p.y, p.z};
+  if (do_wrap) {
 #pragma unroll
-  for (int d = 0; d < 3; d++) {
-    if (g.periodic[d]) {  // Domain::pbc
-      if (c[d] < g.lo[d]) c[d] += g.prd[d];
-      if (c[d] >= g.hi[d]) {
-        c[d] -= g.prd[d];
-        c[d] = fmax(c[d], g.lo[d]);
+    for (int d = 0; d < 3; d++) {
+      if (g.periodic[d]) {  // Domain::pbc
+        if (c[d] < g.wlo[d]) c[d] += g.wprd[d];
+        if (c[d] >= g.whi[d]) {
+          c[d] -= g.wprd[d];
+          c[d] = fmax(c[d], g.wlo[d]);
+        }
       }
     }
+    p.x = c[0]; p.y = c[1]; p.z = c[2];
+    xq[i] = p;
   }
-  p.x = c[0]; p.y = c[1]; p.z = c[2];
-  xq[i] = p;
+  if (!bin_of) return;
   const int bx = bin_coord(c[0], g.lo[0], g.bininv[0], g.nbin[0]) + g.m[0];
   const int by = bin_coord(c[1], g.lo[1], g.bininv[1], g.nbin[1]) + g.m[1];
   const int bz = bin_coord(c[2], g.lo[2], g.bininv[2], g.nbin[2]) + g.m[2];
@@ -102,41 +107,59 @@ __device__ __forceinline__ void ghost_flags(const double4 p, const BinGeom &g, i
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     // Comm::borders slabs, inclusive on both ends: [lo, lo+cutghost] -> +prd, [hi-cutghost, hi] -> -prd
-    lo[d] = g.periodic[d] && c[d] <= g.lo[d] + g.cutghost;
-    hi[d] = g.periodic[d] && c[d] >= g.hi[d] - g.cutghost;
+    lo[d] = g.img[d] && c[d] <= g.lo[d] + g.cutghost;
+    hi[d] = g.img[d] && c[d] >= g.hi[d] - g.cutghost;
   }
 }
 
-__global__ void k_ghost_count(int n, const double4 *__restrict__ xq, BinGeom g, int *__restrict__ cnt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int lo[3], hi[3];
-  ghost_flags(xq[i], g, lo, hi);
-  cnt[i] = (1 + lo[0] + hi[0]) * (1 + lo[1] + hi[1]) * (1 + lo[2] + hi[2]) - 1;
+// base atom b: owned (b < nlocal, xq[b]) or z-halo atom received from a neighbour rank (rbuf[b - nlocal])
+__device__ __forceinline__ double4 base_pos(int b, int nlocal, const double4 *xq, const double4 *rbuf) {
+  return b < nlocal ? xq[b] : rbuf[b - nlocal];
 }
 
-__global__ void k_ghost_fill(int n, const double4 *__restrict__ xq, const int *__restrict__ bin_sorted, BinGeom g,
-                             const int *__restrict__ goff, int *__restrict__ gsrc, int *__restrict__ gshift,
-                             int *__restrict__ gbin, int *__restrict__ gbin_count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void k_ghost_count(int nlocal, int nbase, const double4 *__restrict__ xq, const double4 *__restrict__ rbuf,
+                              BinGeom g, int *__restrict__ cnt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbase) return;
   int lo[3], hi[3];
-  ghost_flags(xq[i], g, lo, hi);
-  int w = goff[i];
-  const int b = bin_sorted[i];
-  const int ex = b % g.mbin[0], ey = (b / g.mbin[0]) % g.mbin[1], ez = b / (g.mbin[0] * g.mbin[1]);
+  ghost_flags(base_pos(b, nlocal, xq, rbuf), g, lo, hi);
+  // a halo atom is itself a ghost (shift 0) in addition to its images
+  cnt[b] = (1 + lo[0] + hi[0]) * (1 + lo[1] + hi[1]) * (1 + lo[2] + hi[2]) - (b < nlocal ? 1 : 0);
+}
+
+__global__ void k_ghost_fill(int nlocal, int nbase, const double4 *__restrict__ xq, const double4 *__restrict__ rbuf,
+                             const int *__restrict__ bin_sorted, BinGeom g, const int *__restrict__ goff,
+                             int *__restrict__ gsrc, int *__restrict__ gshift, int *__restrict__ gbin,
+                             int *__restrict__ gbin_count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbase) return;
+  int lo[3], hi[3];
+  const double4 p = base_pos(b, nlocal, xq, rbuf);
+  ghost_flags(p, g, lo, hi);
+  int w = goff[b];
+  int ex, ey, ez;
+  if (b < nlocal) {
+    const int bb = bin_sorted[b];
+    ex = bb % g.mbin[0]; ey = (bb / g.mbin[0]) % g.mbin[1]; ez = bb / (g.mbin[0] * g.mbin[1]);
+  } else {  // halo atom: bin from its coordinates; it may sit in the z shell
+    ex = bin_coord(p.x, g.lo[0], g.bininv[0], g.nbin[0]) + g.m[0];
+    ey = bin_coord(p.y, g.lo[1], g.bininv[1], g.nbin[1]) + g.m[1];
+    const int bz = (int)floor((p.z - g.lo[2]) * g.bininv[2]);
+    ez = min(max(bz + g.m[2], 0), g.mbin[2] - 1);
+  }
+  const int src = b < nlocal ? b : -1 - (b - nlocal);
   for (int sz = -1; sz <= 1; sz++) {
     if ((sz == 1 && !lo[2]) || (sz == -1 && !hi[2])) continue;
     for (int sy = -1; sy <= 1; sy++) {
       if ((sy == 1 && !lo[1]) || (sy == -1 && !hi[1])) continue;
       for (int sx = -1; sx <= 1; sx++) {
         if ((sx == 1 && !lo[0]) || (sx == -1 && !hi[0])) continue;
-        if (!sx && !sy && !sz) continue;
+        if (!sx && !sy && !sz && b < nlocal) continue;
         const int gx = min(max(ex + sx * g.nbin[0], 0), g.mbin[0] - 1);
         const int gy = min(max(ey + sy * g.nbin[1], 0), g.mbin[1] - 1);
         const int gz = min(max(ez + sz * g.nbin[2], 0), g.mbin[2] - 1);
         const int gb = (gz * g.mbin[1] + gy) * g.mbin[0] + gx;
-        gsrc[w] = i;
+        gsrc[w] = src;
         gshift[w] = (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1);
         gbin[w] = gb;
         atomicAdd(&gbin_count[gb], 1);
@@ -156,22 +179,101 @@ __global__ void k_ghost_permute(int ng, const int *__restrict__ perm, const int 
   shift_out[k] = shift_in[i];
 }
 
-// Comm::forward_comm on one rank: ghost = owner + image shift.  set_type at build time only.
+// Comm::forward_comm: ghost = source + image shift; the source is an owned atom (src >= 0) or a z-halo atom just
+// received from a neighbour rank (src = -1 - k, position rbuf[k]).  set_type at build time only.
 __global__ void k_ghost_refresh(int nlocal, int ng, const int *__restrict__ src, const int *__restrict__ shift,
                                 double px, double py, double pz, double4 *__restrict__ xq, float4 *__restrict__ xqf,
-                                int *__restrict__ type, int set_type) {
+                                int *__restrict__ type, int set_type, const double4 *__restrict__ rbuf,
+                                const int *__restrict__ rtype) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ng) return;
   const int s = src[k];
   const int code = shift[k];
-  double4 p = xq[s];
+  double4 p = s >= 0 ? xq[s] : rbuf[-1 - s];
   const int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
   if (sx) p.x = p.x + sx * px;
   if (sy) p.y = p.y + sy * py;
   if (sz) p.z = p.z + sz * pz;
   xq[nlocal + k] = p;
   if (xqf) xqf[nlocal + k] = make_float4((float)p.x, (float)p.y, (float)p.z, (float)p.w);
-  if (set_type) type[nlocal + k] = type[s];
+  if (set_type) type[nlocal + k] = s >= 0 ? type[s] : rtype[-1 - s];
+}
+
+// ---- multi-GPU: migration (Comm::exchange) and z-halo (Comm::borders / forward_comm) ------------------------
+struct MigAtom {
+  double4 xq, v;
+  int type, tag, pad0, pad1;
+};
+
+// dest: 0 stay, 1 to the lower rank, 2 to the upper rank (positions are already wrapped into the global box)
+__global__ void k_mig_dest(int n, const double4 *__restrict__ xq, double zlo0, double slab_inv, int rank, int nranks,
+                           int *__restrict__ f_stay, int *__restrict__ f_lo, int *__restrict__ f_hi,
+                           int *__restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int sidx = (int)floor((xq[i].z - zlo0) * slab_inv);
+  sidx = min(max(sidx, 0), nranks - 1);
+  const int lower = (rank + nranks - 1) % nranks, upper = (rank + 1) % nranks;
+  int d = 0;
+  if (sidx != rank) {
+    if (sidx == lower) d = 1;
+    else if (sidx == upper) d = 2;
+    else { d = 0; *err = 1; }   // moved further than one slab between two rebuilds
+  }
+  f_stay[i] = d == 0;
+  f_lo[i] = d == 1;
+  f_hi[i] = d == 2;
+}
+
+__global__ void k_mig_pack(int n, const int *__restrict__ f_stay, const int *__restrict__ f_lo,
+                           const int *__restrict__ o_stay, const int *__restrict__ o_lo, const int *__restrict__ o_hi,
+                           const double4 *__restrict__ xq, const double4 *__restrict__ v, const int *__restrict__ type,
+                           const int *__restrict__ tag, double4 *__restrict__ xq_out, double4 *__restrict__ v_out,
+                           int *__restrict__ type_out, int *__restrict__ tag_out, MigAtom *__restrict__ m_lo,
+                           MigAtom *__restrict__ m_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (f_stay[i]) {
+    const int k = o_stay[i];
+    xq_out[k] = xq[i]; v_out[k] = v[i]; type_out[k] = type[i]; tag_out[k] = tag[i];
+  } else {
+    MigAtom a;
+    a.xq = xq[i]; a.v = v[i]; a.type = type[i]; a.tag = tag[i]; a.pad0 = a.pad1 = 0;
+    if (f_lo[i]) m_lo[o_lo[i]] = a;
+    else m_hi[o_hi[i]] = a;
+  }
+}
+
+__global__ void k_mig_unpack(int n, const MigAtom *__restrict__ m, int first, double4 *__restrict__ xq,
+                             double4 *__restrict__ v, int *__restrict__ type, int *__restrict__ tag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const MigAtom a = m[k];
+  xq[first + k] = a.xq; v[first + k] = a.v; type[first + k] = a.type; tag[first + k] = a.tag;
+}
+
+__global__ void k_halo_flag(int n, const double4 *__restrict__ xq, double zlo_cut, double zhi_cut,
+                            int *__restrict__ f_lo, int *__restrict__ f_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double z = xq[i].z;
+  f_lo[i] = z <= zlo_cut;   // inclusive slabs, like Comm::borders
+  f_hi[i] = z >= zhi_cut;
+}
+
+__global__ void k_compact_idx(int n, const int *__restrict__ flag, const int *__restrict__ off, int *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[off[i]] = i;
+}
+
+__global__ void k_halo_pack(int ns, const int *__restrict__ idx, const double4 *__restrict__ xq, double zshift,
+                            double4 *__restrict__ sbuf, const int *__restrict__ type, int *__restrict__ stype) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ns) return;
+  double4 p = xq[idx[k]];
+  p.z += zshift;
+  sbuf[k] = p;
+  if (stype) stype[k] = type[idx[k]];
 }
 
 template <class flt_t>
@@ -358,6 +460,10 @@ int make_geom(b200md_ctx *ctx, BinGeom &g) {
     g.hi[d] = ctx->boxhi[d];
     g.prd[d] = ctx->prd[d];
     g.periodic[d] = ctx->periodic[d];
+    g.wlo[d] = ctx->boxlo[d];
+    g.whi[d] = ctx->boxhi[d];
+    g.wprd[d] = ctx->prd[d];
+    g.img[d] = ctx->periodic[d];
     if (g.periodic[d] && g.prd[d] < ns.cutghost)
       return b2_fail(ctx, B200MD_EOVERFLOW,
                      "box length %g in dimension %d is shorter than the ghost cutoff %g (multiple periodic "
@@ -402,7 +508,7 @@ int b2_ghost_refresh(b200md_ctx *ctx) {
   if (ctx->nghost == 0) return 0;
   k_ghost_refresh<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
       ctx->nlocal, ctx->nghost, ns.ghost_src.p, ns.ghost_shift.p, ctx->prd[0], ctx->prd[1], ctx->prd[2],
-      ctx->xq.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 0);
+      ctx->xq.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 0, nullptr, nullptr);
   KERNEL_OK(ctx, "k_ghost_refresh");
   return 0;
 }
@@ -461,7 +567,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
 
   // 1. wrap + bin owned atoms, stable counting sort, permute the resident arrays
   if (n > 0) {
-    k_wrap_bin<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, g, ns.bin_of.p, lcount);
+    k_wrap_bin<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, g, 1, ns.bin_of.p, lcount);
     KERNEL_OK(ctx, "k_wrap_bin");
   }
   TRY(counting_sort(ctx, n, nb, ns.bin_of.p, lcount, lstart, ns.bin_cursor.p, ns.perm.p));
@@ -479,7 +585,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
   // 2. periodic ghost atoms: count / scan / fill, then sort the ghosts by bin too
   int ng = 0;
   if (n > 0) {
-    k_ghost_count<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, g, ns.ghost_cnt.p);
+    k_ghost_count<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, n, ctx->xq.p, nullptr, g, ns.ghost_cnt.p);
     KERNEL_OK(ctx, "k_ghost_count");
     TRY(b2_exclusive_scan_i32(ctx, ns.ghost_cnt.p, ns.goff.p, (size_t)n, ns.scan_ws.p));
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.goff.p + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -499,7 +605,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
     RESERVE(ctx, ns.gperm, (size_t)ng);
     RESERVE(ctx, ns.ghost_src, (size_t)ng);
     RESERVE(ctx, ns.ghost_shift, (size_t)ng);
-    k_ghost_fill<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, ns.bin_sorted.p, g, ns.goff.p,
+    k_ghost_fill<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, n, ctx->xq.p, nullptr, ns.bin_sorted.p, g, ns.goff.p,
                                                         ns.gsrc_tmp.p, ns.gshift_tmp.p, ns.gbin.p, gcount);
     KERNEL_OK(ctx, "k_ghost_fill");
   }
@@ -510,7 +616,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
     KERNEL_OK(ctx, "k_ghost_permute");
     k_ghost_refresh<<<cdiv(ng, 256), 256, 0, ctx->stream>>>(
         n, ng, ns.ghost_src.p, ns.ghost_shift.p, ctx->prd[0], ctx->prd[1], ctx->prd[2], ctx->xq.p,
-        ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 1);
+        ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 1, nullptr, nullptr);
     KERNEL_OK(ctx, "k_ghost_refresh");
   }
   TRY(b2_refresh_float_copy(ctx, 0, n));
