@@ -171,7 +171,7 @@ void b200md_ctx_destroy(b200md_ctx *ctx) {
   ctx->ev_partial.free_(); ctx->ev_out.free_();
   PairState &ps = ctx->pair;
   ps.coeff_d.free_(); ps.coeff_f.free_(); ps.cutneighsq.free_();
-  ps.ctab_d.free_(); ps.ctab_f.free_(); ps.dtab_d.free_(); ps.dtab_f.free_();
+  ps.ctab_d.free_(); ps.ctab_f.free_(); ps.dtab_d.free_(); ps.dtab_f.free_(); ps.exptab.free_();
   NeighState &ns = ctx->neigh;
   ns.bin_of.free_(); ns.bin_sorted.free_(); ns.goff.free_(); ns.gsrc_tmp.free_(); ns.gshift_tmp.free_();
   ns.gbin.free_(); ns.gperm.free_(); ns.bin_count.free_(); ns.bin_start.free_(); ns.bin_end.free_(); ns.bin_cursor.free_();

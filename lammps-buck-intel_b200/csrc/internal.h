@@ -66,6 +66,7 @@ struct PairState {
   DevBuf<float> ctab_f;
   DevBuf<double> dtab_d;      // dispersion [ntable][6] {r,dr,f,df,e,de}
   DevBuf<float> dtab_f;
+  DevBuf<double> exptab;      // 2^(k/64), k < 64: table of the double-precision exp kernel (pair_kernel.cuh)
 };
 
 struct NeighState {

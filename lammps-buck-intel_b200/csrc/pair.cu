@@ -113,6 +113,18 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p) {
   RESERVE(ctx, ps.coeff_f, hf.size());
   CUDA_OK(ctx, cudaMemcpy(ps.coeff_d.p, hd.data(), hd.size() * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_OK(ctx, cudaMemcpy(ps.coeff_f.p, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    // 2^(k/64), correctly rounded: fast_exp's table (pair_kernel.cuh)
+    double et[B2_EXP_TAB];
+    for (int k = 0; k < B2_EXP_TAB; k++) et[k] = (double)exp2l((long double)k / B2_EXP_TAB);
+    RESERVE(ctx, ps.exptab, B2_EXP_TAB);
+    CUDA_OK(ctx, cudaMemcpy(ps.exptab.p, et, sizeof(et), cudaMemcpyHostToDevice));
+    // fast_exp adds n>>6 to the exponent field without an underflow path: arguments stay above -700
+    for (int i = 1; i < tp1; i++)
+      for (int j = 1; j < tp1; j++)
+        if (std::sqrt(p->cut_ljsq[i * tp1 + j]) * p->rhoinv[i * tp1 + j] > 700.0)
+          return b2_fail(ctx, B200MD_EINVAL, "buck rho for types %d-%d is too small for its cutoff: exp(-r/rho) underflows", i, j);
+  }
   // tables
   if (p->ncoultablebits) {
     if (!p->rtable || !p->drtable || !p->ftable || !p->dftable || !p->etable || !p->detable || !p->ctable ||

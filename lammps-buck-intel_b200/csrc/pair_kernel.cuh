@@ -14,6 +14,9 @@ namespace pairk {
 
 enum { C_CUTSQ = 0, C_CUT_LJSQ, C_CUT_COULSQ, C_BUCK1, C_BUCK2, C_RHOINV, C_A, C_C, C_OFFSET, C_N };
 
+enum { MC_L = 0, MC_MAGIC, MC_LN2HI, MC_LN2LO, MC_E5, MC_E4, MC_E3, MC_HALF, MC_ONE, MC_R375, MC_EWP, MC_A1, MC_A2,
+       MC_A3, MC_A4, MC_A5, MC_EWF, MC_N };
+
 template <class flt_t>
 struct PairConsts {
   int tp1;
@@ -21,18 +24,72 @@ struct PairConsts {
   flt_t special_lj[4], special_coul[4];
   int ncoulmask, ncoulshiftbits, ndispmask, ndispshiftbits;
   int order1, order6, coultable, disptable;
+  flt_t mc[MC_N];   // numeric constants of the double-precision math kernels (see fill_math_consts)
 };
 
 template <class flt_t> struct V4;
 template <> struct V4<double> { typedef double4 type; };
 template <> struct V4<float> { typedef float4 type; };
 
-__device__ __forceinline__ double m_exp(double x) { return exp(x); }
-__device__ __forceinline__ float m_exp(float x) { return expf(x); }
-__device__ __forceinline__ double m_rsqrt(double x) { return rsqrt(x); }
-__device__ __forceinline__ float m_rsqrt(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double m_rcp(double x) { return 1.0 / x; }
-__device__ __forceinline__ float m_rcp(float x) { return 1.0f / x; }
+// ---- double-precision math of the hot loop ---------------------------------------------------------------------
+// The loop is bound by the FP64 pipe and by issue slots (ncu: profiles/r01_*), so the libdevice routines (generic
+// range checks, ~17 DFMA per exp, a correctly-rounded divide) are replaced by kernels sized for this loop's argument
+// ranges and error budget: every function below is accurate to <= 4e-16 relative (a few ulp), against a parity bar of
+// 1e-9 on forces.
+//   exp:   x = (n/64) ln2 + r, |r| <= ln2/128; exp(x) = 2^(n>>6) * T[n&63] * (1 + expm1(r)), T = 2^(k/64) in shared
+//          memory, expm1 by a degree-5 Taylor polynomial (remainder r^6/720 < 4e-17).  10 FP64 ops, no branches.
+//   rsqrt: MUFU.RSQ64H seed (~2^-20) + one third-order step (error e^3).  rcp likewise.
+#define B2_EXP_TAB 64
+// The numeric constants of these kernels travel in the kernel-parameter block (PairConsts::mc, constant bank 0), not
+// as literals: a double literal costs two UMOV/IMAD.MOV issue slots every time it is used (the compiler re-
+// materialises it inside the loop — 45 of the 223 instructions per pair in the first profile), a parameter is loaded
+// once into a (uniform) register ahead of the loop.
+
+static inline void fill_math_consts(double *mc) {
+  mc[MC_L] = 92.332482616893656877;        // 64 / ln 2
+  mc[MC_MAGIC] = 6755399441055744.0;       // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
+  mc[MC_LN2HI] = 1.0830424696223417e-02;   // ln2/64 rounded to 36 bits: n * HI is exact for |n| < 2^17
+  mc[MC_LN2LO] = 2.5728046223276688e-14;   // ln2/64 - HI
+  mc[MC_E5] = 1.0 / 120.0; mc[MC_E4] = 1.0 / 24.0; mc[MC_E3] = 1.0 / 6.0;
+  mc[MC_HALF] = 0.5; mc[MC_ONE] = 1.0; mc[MC_R375] = 0.375;
+  mc[MC_EWP] = 0.3275911;
+  mc[MC_A1] = 0.254829592; mc[MC_A2] = -0.284496736; mc[MC_A3] = 1.421413741; mc[MC_A4] = -1.453152027;
+  mc[MC_A5] = 1.061405429;
+  mc[MC_EWF] = 1.12837917;
+}
+static inline void fill_math_consts(float *) {}
+
+__device__ __forceinline__ double fast_exp(const double x, const double *__restrict__ s_tab, const double *mc) {
+  const double t = fma(x, mc[MC_L], mc[MC_MAGIC]);
+  const int n = __double2loint(t);
+  const double nf = t - mc[MC_MAGIC];
+  double r = fma(nf, -mc[MC_LN2HI], x);
+  r = fma(nf, -mc[MC_LN2LO], r);
+  double p = fma(r, mc[MC_E5], mc[MC_E4]);
+  p = fma(p, r, mc[MC_E3]);
+  p = fma(p, r, mc[MC_HALF]);
+  p = fma(p, r * r, r);
+  const double T = s_tab[n & (B2_EXP_TAB - 1)];
+  const double v = fma(T, p, T);
+  return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+__device__ __forceinline__ double fast_rsqrt(const double x, const double *mc) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(x, -(y * y), mc[MC_ONE]);
+  const double c = fma(e, mc[MC_R375], mc[MC_HALF]);
+  return fma(c, y * e, y);
+}
+__device__ __forceinline__ double fast_rcp(const double x, const double *mc) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, mc[MC_ONE]);
+  return fma(y, fma(e, e, e), y);
+}
+__device__ __forceinline__ double m_exp(double x, const double *s_tab, const double *mc) { return fast_exp(x, s_tab, mc); }
+__device__ __forceinline__ float m_exp(float x, const float *, const float *) { return expf(x); }
+__device__ __forceinline__ double m_rcp(double x, const double *mc) { return fast_rcp(x, mc); }
+__device__ __forceinline__ float m_rcp(float x, const float *) { return 1.0f / x; }
 // rsq with the reference's un-fused rounding ((dx*dx + dy*dy) + dz*dz, AVX build: no FMA) so that the
 // cut-off decisions and, in mixed mode, r itself are bit-identical to the CPU path
 __device__ __forceinline__ double m_rsq(double dx, double dy, double dz) {
@@ -46,13 +103,13 @@ __device__ __forceinline__ float m_rsq(float dx, float dy, float dz) {
 // r2inv = 1/rsq, r = 1/sqrt(r2inv) (pair_buck_coul_long_intel.cpp:287-288), the others r = sqrt(rsq)
 // (pair_buck_intel.cpp:254-255).
 template <int COUL_LONG>
-__device__ __forceinline__ void m_r(double rsq, double &r, double &rinv, double &r2inv) {
-  rinv = rsqrt(rsq);
+__device__ __forceinline__ void m_r(double rsq, double &r, double &rinv, double &r2inv, const double *mc) {
+  rinv = fast_rsqrt(rsq, mc);
   r = rsq * rinv;
   r2inv = rinv * rinv;
 }
 template <int COUL_LONG>
-__device__ __forceinline__ void m_r(float rsq, float &r, float &rinv, float &r2inv) {
+__device__ __forceinline__ void m_r(float rsq, float &r, float &rinv, float &r2inv, const float *) {
   r2inv = __fdiv_rn(1.0f, rsq);
   r = COUL_LONG ? __fdiv_rn(1.0f, __fsqrt_rn(r2inv)) : __fsqrt_rn(rsq);
   rinv = __fdiv_rn(1.0f, r);
@@ -64,23 +121,22 @@ __device__ __forceinline__ void m_r(float rsq, float &r, float &rinv, float &r2i
 // ~1.7e-5 from its double mode on data.aC); replaying the order keeps the two float paths together.
 template <class flt_t>
 __device__ __forceinline__ void ewald_real(flt_t g_ewald, flt_t qqrd2e, flt_t qi, flt_t qj, flt_t r, flt_t rinv,
-                                           flt_t &grij, flt_t &expm2, flt_t &erfc, flt_t &prefactor);
+                                           flt_t &grij, flt_t &expm2, flt_t &erfc, flt_t &prefactor,
+                                           const flt_t *s_tab, const flt_t *mc);
 template <>
 __device__ __forceinline__ void ewald_real<double>(double g_ewald, double qqrd2e, double qi, double qj, double r,
                                                    double rinv, double &grij, double &expm2, double &erfc,
-                                                   double &prefactor) {
-  const double A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741, A4 = -1.453152027, A5 = 1.061405429;
-  const double EWALD_P = 0.3275911;
+                                                   double &prefactor, const double *s_tab, const double *mc) {
   grij = g_ewald * r;
-  expm2 = exp(-grij * grij);
-  const double t = 1.0 / (1.0 + EWALD_P * grij);
-  erfc = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * expm2;
+  expm2 = fast_exp(-grij * grij, s_tab, mc);
+  const double t = fast_rcp(fma(mc[MC_EWP], grij, mc[MC_ONE]), mc);
+  erfc = t * (mc[MC_A1] + t * (mc[MC_A2] + t * (mc[MC_A3] + t * (mc[MC_A4] + t * mc[MC_A5])))) * expm2;
   prefactor = qqrd2e * qi * qj * rinv;
 }
 template <>
 __device__ __forceinline__ void ewald_real<float>(float g_ewald, float qqrd2e, float qi, float qj, float r,
                                                   float rinv, float &grij, float &expm2, float &erfc,
-                                                  float &prefactor) {
+                                                  float &prefactor, const float *, const float *) {
   const float A1 = 0.254829592f, A2 = -0.284496736f, A3 = 1.421413741f, A4 = -1.453152027f, A5 = 1.061405429f;
   const float INV_EWALD_P = (float)(1.0 / 0.3275911);
   (void)rinv;
@@ -93,6 +149,14 @@ __device__ __forceinline__ void ewald_real<float>(float g_ewald, float qqrd2e, f
   p = __fadd_rn(A1, __fmul_rn(t, p));
   erfc = __fmul_rn(__fmul_rn(t, p), expm2);
   prefactor = __fdiv_rn(__fmul_rn(__fmul_rn(qqrd2e, qi), qj), r);
+}
+
+// j = entry & NEIGHMASK, opaque to the optimiser: otherwise the mask is folded into the 64-bit address arithmetic of
+// x[j] (shift/mask/add-with-carry, 6 instructions) instead of one LOP3 + one IMAD.WIDE
+__device__ __forceinline__ int nbr_index(const int e) {
+  int j;
+  asm("and.b32 %0, %1, 0x3FFFFFFF;" : "=r"(j) : "r"(e));
+  return j;
 }
 
 struct PairView {  // device pointers of one evaluation
@@ -110,12 +174,14 @@ __global__ void __launch_bounds__(256)
 k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const int *__restrict__ type,
        const int *__restrict__ numneigh, const long long *__restrict__ offsets,
        const int *__restrict__ entries, const PairConsts<flt_t> pc, const flt_t *__restrict__ coeff,
-       const flt_t *__restrict__ ctab, const flt_t *__restrict__ dtab, double4 *__restrict__ f,
-       double *__restrict__ ev_partial) {
+       const flt_t *__restrict__ ctab, const flt_t *__restrict__ dtab, const flt_t *__restrict__ exptab,
+       double4 *__restrict__ f, double *__restrict__ ev_partial) {
   typedef typename V4<flt_t>::type vec4;
   __shared__ flt_t s_coeff[(B2_MAXTYPES + 1) * (B2_MAXTYPES + 1) * C_N];
+  __shared__ flt_t s_tab[B2_EXP_TAB];   // 2^(k/64) for fast_exp (double instantiation only)
   __shared__ double s_ev[8][8];
   for (int k = threadIdx.x; k < pc.tp1 * pc.tp1 * C_N; k += blockDim.x) s_coeff[k] = coeff[k];
+  if (sizeof(flt_t) == 8 && threadIdx.x < B2_EXP_TAB) s_tab[threadIdx.x] = exptab[threadIdx.x];
   __syncthreads();
 
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,19 +199,34 @@ k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const i
     const int jnum = numneigh[i];
     const int *jlist = entries + offsets[i];
 
+    // software pipeline over the two dependent loads of an iteration (list entry -> gathered atom): the entry is
+    // fetched two iterations ahead, the atom one ahead, so their latencies overlap the ~65 FP64 operations of a pair
+    int e_cur = 0, e_nxt = 0;
+    if (sub < jnum) e_cur = jlist[sub];
+    if (sub + TPA < jnum) e_nxt = jlist[sub + TPA];
+    int j_nxt = nbr_index(e_cur);
+    vec4 xj_nxt = x[j_nxt];
+    int tj_nxt = type[j_nxt];
+
+#pragma unroll 2
     for (int jj = sub; jj < jnum; jj += TPA) {
-      const int e = jlist[jj];
+      const int e = e_cur;
+      const vec4 xj = xj_nxt;
+      const int tj = tj_nxt;
+      e_cur = e_nxt;   // past the row's end this stays a valid (already used) entry: the loads below are harmless
+      if (jj + 2 * TPA < jnum) e_nxt = jlist[jj + 2 * TPA];
+      j_nxt = nbr_index(e_cur);
+      xj_nxt = x[j_nxt];
+      tj_nxt = type[j_nxt];
       const int sbindex = (e >> B2_SBBITS) & 3;
-      const int j = e & B2_NEIGHMASK;
-      const vec4 xj = x[j];
-      const flt_t *cij = ci + type[j] * C_N;
+      const flt_t *cij = ci + tj * C_N;
       const flt_t delx = xi.x - xj.x;
       const flt_t dely = xi.y - xj.y;
       const flt_t delz = xi.z - xj.z;
       const flt_t rsq = m_rsq(delx, dely, delz);
       if (rsq < cij[C_CUTSQ]) {
         flt_t r, rinv, r2inv;
-        m_r<STYLE == B200MD_PAIR_BUCK_COUL_LONG>(rsq, r, rinv, r2inv);
+        m_r<STYLE == B200MD_PAIR_BUCK_COUL_LONG>(rsq, r, rinv, r2inv, pc.mc);
         flt_t forcecoul = (flt_t)0, forcebuck = (flt_t)0, evdwl = (flt_t)0, ecoul = (flt_t)0;
 
         if (STYLE == B200MD_PAIR_BUCK_COUL_CUT) {
@@ -157,9 +238,9 @@ k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const i
         }
         if (STYLE == B200MD_PAIR_BUCK_COUL_LONG || (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order1)) {
           if (!pc.coultable || rsq <= pc.tabinnersq) {
-            const flt_t EWALD_F = (flt_t)1.12837917;
+            const flt_t EWALD_F = sizeof(flt_t) == 8 ? pc.mc[MC_EWF] : (flt_t)1.12837917;
             flt_t erfc, expm2, grij, prefactor;
-            ewald_real<flt_t>(pc.g_ewald, pc.qqrd2e, qtmp, xj.w, r, rinv, grij, expm2, erfc, prefactor);
+            ewald_real<flt_t>(pc.g_ewald, pc.qqrd2e, qtmp, xj.w, r, rinv, grij, expm2, erfc, prefactor, s_tab, pc.mc);
             forcecoul = prefactor * (erfc + EWALD_F * grij * expm2);
             if (EVFLAG) ecoul = prefactor * erfc;
             if (sbindex) {
@@ -186,12 +267,12 @@ k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const i
 
         if (rsq < cij[C_CUT_LJSQ]) {
           const flt_t r6inv = r2inv * r2inv * r2inv;
-          const flt_t rexp = m_exp(-r * cij[C_RHOINV]);
+          const flt_t rexp = m_exp(-r * cij[C_RHOINV], s_tab, pc.mc);
           if (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order6) {
             if (!pc.disptable || rsq <= pc.tabinnerdispsq) {
               const flt_t grij2 = pc.g2 * rsq;
-              const flt_t a2 = m_rcp(grij2);
-              const flt_t x2 = a2 * m_exp(-grij2) * cij[C_C];
+              const flt_t a2 = m_rcp(grij2, pc.mc);
+              const flt_t x2 = a2 * m_exp(-grij2, s_tab, pc.mc) * cij[C_C];
               forcebuck = r * rexp * cij[C_BUCK1] -
                           pc.g8 * x2 * rsq * ((((flt_t)6.0 * a2 + (flt_t)6.0) * a2 + (flt_t)3.0) * a2 + (flt_t)1.0);
               if (EVFLAG) evdwl = rexp * cij[C_A] - pc.g6 * x2 * ((a2 + (flt_t)1.0) * a2 + (flt_t)0.5);
@@ -318,6 +399,7 @@ PairConsts<flt_t> make_consts(const PairState &ps) {
   pc.order6 = (p.ewald_order >> 6) & 1;
   pc.coultable = p.ncoultablebits != 0;
   pc.disptable = p.ndisptablebits != 0;
+  fill_math_consts(pc.mc);
   return pc;
 }
 
@@ -333,12 +415,12 @@ static inline int pick_tpa(const b200md_ctx *ctx, int nlocal, long long total_en
 
 template <int STYLE, class flt_t, int EVFLAG>
 int launch_tpa(b200md_ctx *ctx, const PairView &v, int tpa, const PairConsts<flt_t> &pc, const flt_t *coeff,
-               const flt_t *ctab, const flt_t *dtab, double *ev_partial, int nblocks) {
+               const flt_t *ctab, const flt_t *dtab, const flt_t *exptab, double *ev_partial, int nblocks) {
   typedef typename V4<flt_t>::type vec4;
 #define LAUNCH(T)                                                                                          \
   k_pair<STYLE, flt_t, EVFLAG, T><<<nblocks, 256, 0, ctx->stream>>>(                                        \
-      v.nlocal, (const vec4 *)v.x, v.type, v.numneigh, v.offsets, v.entries, pc, coeff, ctab, dtab, v.f, \
-      ev_partial)
+      v.nlocal, (const vec4 *)v.x, v.type, v.numneigh, v.offsets, v.entries, pc, coeff, ctab, dtab, exptab,   \
+      v.f, ev_partial)
   switch (tpa) {
     case 4: LAUNCH(4); break;
     case 8: LAUNCH(8); break;
@@ -355,9 +437,10 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
   PairState &ps = ctx->pair;
   PairConsts<flt_t> pc = make_consts<flt_t>(ps);
   pc.qqrd2e = (flt_t)ctx->qqrd2e;
-  const flt_t *coeff, *ctab, *dtab;
+  const flt_t *coeff, *ctab, *dtab, *exptab = nullptr;
   if (sizeof(flt_t) == 8) {
     coeff = (const flt_t *)ps.coeff_d.p; ctab = (const flt_t *)ps.ctab_d.p; dtab = (const flt_t *)ps.dtab_d.p;
+    exptab = (const flt_t *)ps.exptab.p;
   } else {
     coeff = (const flt_t *)ps.coeff_f.p; ctab = (const flt_t *)ps.ctab_f.p; dtab = (const flt_t *)ps.dtab_f.p;
   }
@@ -371,8 +454,8 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
   double *evp = ctx->ev_partial.p;
 #define STYLE_CASE(S)                                                                              \
   case S:                                                                                          \
-    if (evflag) TRY((launch_tpa<S, flt_t, 1>(ctx, v, tpa, pc, coeff, ctab, dtab, evp, nblocks)));  \
-    else TRY((launch_tpa<S, flt_t, 0>(ctx, v, tpa, pc, coeff, ctab, dtab, evp, nblocks)));         \
+    if (evflag) TRY((launch_tpa<S, flt_t, 1>(ctx, v, tpa, pc, coeff, ctab, dtab, exptab, evp, nblocks)));  \
+    else TRY((launch_tpa<S, flt_t, 0>(ctx, v, tpa, pc, coeff, ctab, dtab, exptab, evp, nblocks)));         \
     break;
   switch (ps.p.style) {
     STYLE_CASE(B200MD_PAIR_BUCK)
