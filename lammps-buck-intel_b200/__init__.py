@@ -16,7 +16,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIBPATH = os.path.join(HERE, "libb200md.so")
+# B200MD_LIB selects an alternative build of the same library (kernel-tuning experiments: scratch/variants.py)
+LIBPATH = os.environ.get("B200MD_LIB") or os.path.join(HERE, "libb200md.so")
 CSRC = os.path.join(HERE, "csrc")
 HEADER = os.path.join(ROOT, "include", "b200md.h")
 

@@ -22,6 +22,10 @@
 
 #define B2_SBBITS 30
 #define B2_NEIGHMASK 0x3FFFFFFF
+// device-built lists with nall <= 2^26 carry the type of j in bits 26..29 of the entry (the pair kernel then needs no
+// type[j] gather); such lists never have special-bond bits.  Exports strip the type bits.
+#define B2_TYPESHIFT 26
+#define B2_IDXMASK26 0x03FFFFFF
 #define B2_MAXTYPES 8       // (ntypes+1) <= 9 rows staged in shared memory
 #define B2_MAXORDER 7
 
@@ -61,6 +65,7 @@ struct PairState {
   DevBuf<double> cutneighsq;  // [tp1*tp1] (flt_t-rounded values stored as double)
   std::vector<double> h_cutsq;
   double cutmax = 0.0;        // max cut over type pairs
+  bool same_cut = false;      // cut_ljsq == cutsq for all type pairs
   // tables: 8 arrays of 2^bits (double and float copies)
   DevBuf<double> ctab_d;      // [ntable][8] {r,dr,f,df,e,de,c,dc}
   DevBuf<float> ctab_f;
@@ -91,6 +96,7 @@ struct NeighState {
   DevBuf<int> entries;
   long long total_entries = 0;
   int max_numneigh = 0;
+  bool packed_type = false;   // entries carry type(j) << B2_TYPESHIFT
   DevBuf<double4> xhold;      // positions at last build (owned)
   DevBuf<int> flags;          // device flags: [0] displacement trigger, [1] errors
   DevBuf<unsigned char> scan_ws;

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NB_THREADS)
 k_build(int nlocal, const typename Pos<flt_t>::vec *__restrict__ x, const int *__restrict__ type,
         const int *__restrict__ lstart, const int *__restrict__ gstart, BinGeom g, int tp1,
         const double *__restrict__ cutneighsq, int *__restrict__ numneigh, const long long *__restrict__ offsets,
-        int *__restrict__ entries, int *__restrict__ maxn) {
+        int *__restrict__ entries, int *__restrict__ maxn, int pack_type) {
   __shared__ flt_t s_cut[(B2_MAXTYPES + 1) * (B2_MAXTYPES + 1)];
   __shared__ flt_t sx[NB_CHUNK], sy[NB_CHUNK], sz[NB_CHUNK];
   __shared__ int sj[NB_CHUNK];
@@ -392,7 +392,8 @@ k_build(int nlocal, const typename Pos<flt_t>::vec *__restrict__ x, const int *_
             hit = (j != i) && (rsq <= cut_i[st[k]]);
           }
           const unsigned mk = __ballot_sync(0xffffffffu, hit);
-          if (FILL && hit) entries[w0 + count + __popc(mk & ((1u << lane) - 1))] = j;
+          if (FILL && hit)
+            entries[w0 + count + __popc(mk & ((1u << lane) - 1))] = pack_type ? (j | ((int)st[k] << B2_TYPESHIFT)) : j;
           count += __popc(mk);
         }
         if (lane == 0) s_cnt[ii] = count;
@@ -425,7 +426,7 @@ __global__ void k_export_counts(int n, const int *__restrict__ tag, const int *_
 }
 __global__ void k_export_rows(int nlocal, const int *__restrict__ tag, const int *__restrict__ numneigh,
                               const long long *__restrict__ off_in, const int *__restrict__ entries,
-                              const long long *__restrict__ off_out, int *__restrict__ out) {
+                              const long long *__restrict__ off_out, int *__restrict__ out, int packed_type) {
   const int lane = threadIdx.x & 31;
   const int i = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (i >= nlocal) return;
@@ -433,9 +434,9 @@ __global__ void k_export_rows(int nlocal, const int *__restrict__ tag, const int
   const int n = numneigh[i];
   for (int k = lane; k < n; k += 32) {
     const int e = entries[src + k];
-    const int j = e & B2_NEIGHMASK;
+    const int j = e & (packed_type ? B2_IDXMASK26 : B2_NEIGHMASK);
     const int jj = j < nlocal ? tag[j] : j;  // ghosts keep their slot, owned atoms go to host index
-    out[dst + k] = jj | (e & ~B2_NEIGHMASK);
+    out[dst + k] = jj | (packed_type ? 0 : (e & ~B2_NEIGHMASK));
   }
 }
 __global__ void k_export_ghosts(int nlocal, int ng, const int *__restrict__ tag, const int *__restrict__ src,
@@ -624,16 +625,18 @@ int b2_neigh_build(b200md_ctx *ctx) {
   // 3. full list: count, scan to 64-bit CSR offsets, fill
   long long total = 0;
   int maxn = 0;
+  const int pack = (nall <= (size_t)B2_IDXMASK26 && ctx->ntypes < 16) ? 1 : 0;
+  ns.packed_type = pack != 0;
   if (n > 0) {
     const int nblk = g.nbin[0] * g.nbin[1] * g.nbin[2];  // one block per interior bin
     if (ctx->prec == B200MD_PREC_MIXED)
       k_build<float, 0><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, lstart, gstart, g,
                                                       ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p, nullptr,
-                                                      nullptr, ns.flags.p + 2);
+                                                      nullptr, ns.flags.p + 2, 0);
     else
       k_build<double, 0><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, lstart, gstart, g,
                                                        ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p, nullptr,
-                                                       nullptr, ns.flags.p + 2);
+                                                       nullptr, ns.flags.p + 2, 0);
     KERNEL_OK(ctx, "k_build<count>");
     TRY(b2_exclusive_scan_i32_i64(ctx, ns.numneigh.p, ns.offsets.p, (size_t)n, ns.scan_ws.p));
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -645,11 +648,11 @@ int b2_neigh_build(b200md_ctx *ctx) {
     if (ctx->prec == B200MD_PREC_MIXED)
       k_build<float, 1><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, lstart, gstart, g,
                                                       ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p,
-                                                      ns.offsets.p, ns.entries.p, ns.flags.p + 2);
+                                                      ns.offsets.p, ns.entries.p, ns.flags.p + 2, pack);
     else
       k_build<double, 1><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, lstart, gstart, g,
                                                        ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p,
-                                                       ns.offsets.p, ns.entries.p, ns.flags.p + 2);
+                                                       ns.offsets.p, ns.entries.p, ns.flags.p + 2, pack);
     KERNEL_OK(ctx, "k_build<fill>");
   }
   ns.total_entries = total;
@@ -747,7 +750,7 @@ int b200md_neigh_download(b200md_ctx *ctx, int *numneigh, long *offsets, int *en
     rc = b2_exclusive_scan_i32_i64(ctx, cnt.p, off.p, (size_t)n, ns.scan_ws.p);
     if (!rc) {
       k_export_rows<<<cdiv((long)n * 32, 256), 256, 0, ctx->stream>>>(n, ctx->tag.p, ns.numneigh.p, ns.offsets.p,
-                                                                    ns.entries.p, off.p, ent.p);
+                                                                    ns.entries.p, off.p, ent.p, ns.packed_type ? 1 : 0);
       ctx->launches++;
     }
   }

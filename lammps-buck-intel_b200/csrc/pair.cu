@@ -20,8 +20,9 @@
 
 using namespace pairk;
 
-int b2_launch_pair_double(b200md_ctx *ctx, const PairView &v, long long total_entries, int evflag, double *ev_dev) {
-  return launch_pair<double>(ctx, v, total_entries, evflag, ev_dev);
+int b2_launch_pair_double(b200md_ctx *ctx, const PairView &v, long long total_entries, int evflag, double *ev_dev,
+                          int has_special) {
+  return launch_pair<double>(ctx, v, total_entries, evflag, ev_dev, has_special);
 }
 
 namespace {
@@ -62,8 +63,10 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev) {
   v.offsets = ctx->neigh.offsets.p;
   v.entries = ctx->neigh.entries.p;
   v.f = ctx->f.p;
-  if (ctx->prec == B200MD_PREC_MIXED) TRY(b2_launch_pair_float(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p));
-  else TRY(b2_launch_pair_double(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p));
+  v.packed_type = ctx->neigh.packed_type ? 1 : 0;
+  // lists built on the device carry no special-bond bits (atomic systems)
+  if (ctx->prec == B200MD_PREC_MIXED) TRY(b2_launch_pair_float(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, 0));
+  else TRY(b2_launch_pair_double(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, 0));
   if (evflag) TRY(finish_ev(ctx, eflag, vflag, ev));
   return 0;
 }
@@ -91,6 +94,7 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p) {
   std::vector<float> hf((size_t)n * C_N, 0.0f);
   ps.h_cutsq.assign(n, 0.0);
   double cutmax = 0.0;
+  bool same_cut = true;
   for (int i = 1; i < tp1; i++)
     for (int j = 1; j < tp1; j++) {
       const int ij = i * tp1 + j;
@@ -106,9 +110,11 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p) {
       d[C_OFFSET] = p->offset[ij];
       for (int k = 0; k < C_N; k++) hf[(size_t)ij * C_N + k] = (float)d[k];
       ps.h_cutsq[ij] = p->cutsq[ij];
+      if (p->cut_ljsq[ij] != p->cutsq[ij]) same_cut = false;
       cutmax = std::max(cutmax, std::sqrt(p->cutsq[ij]));
     }
   ps.cutmax = cutmax;
+  ps.same_cut = same_cut;
   RESERVE(ctx, ps.coeff_d, hd.size());
   RESERVE(ctx, ps.coeff_f, hf.size());
   CUDA_OK(ctx, cudaMemcpy(ps.coeff_d.p, hd.data(), hd.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -188,7 +194,12 @@ int b200md_pair_eval_host(b200md_ctx *ctx, int eflag, int vflag, int nlocal, int
   const int evflag = ((eflag & 3) || (vflag & 3)) ? 1 : 0;
   if (evflag && !ev) return b2_fail(ctx, B200MD_EINVAL, "ev is NULL but energy/virial requested");
   long long total = 0;
-  for (int i = 0; i < nlocal; i++) total = std::max(total, (long long)cnumneigh[i] + numneigh[i]);
+  int has_special = 0;
+  for (int i = 0; i < nlocal; i++) {
+    total = std::max(total, (long long)cnumneigh[i] + numneigh[i]);
+    for (int k = 0; k < numneigh[i] && !has_special; k++)
+      if ((unsigned)firstneigh[cnumneigh[i] + k] >> B2_SBBITS) has_special = 1;
+  }
   DevBuf<double> dx, dq;
   DevBuf<double4> dxq, df;
   DevBuf<float4> dxqf;
@@ -220,9 +231,9 @@ int b200md_pair_eval_host(b200md_ctx *ctx, int eflag, int vflag, int nlocal, int
   PairView v;
   v.nlocal = nlocal;
   v.x = mixed ? (const void *)dxqf.p : (const void *)dxq.p;
-  v.type = dtype.p; v.numneigh = dnum.p; v.offsets = doff.p; v.entries = dent.p; v.f = df.p;
-  rc = mixed ? b2_launch_pair_float(ctx, v, total, evflag, ctx->ev_out.p)
-             : b2_launch_pair_double(ctx, v, total, evflag, ctx->ev_out.p);
+  v.type = dtype.p; v.numneigh = dnum.p; v.offsets = doff.p; v.entries = dent.p; v.f = df.p; v.packed_type = 0;
+  rc = mixed ? b2_launch_pair_float(ctx, v, total, evflag, ctx->ev_out.p, has_special)
+             : b2_launch_pair_double(ctx, v, total, evflag, ctx->ev_out.p, has_special);
   if (!rc) {
     cudaMemcpyAsync(f, df.p, (size_t)nlocal * sizeof(double4), cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);

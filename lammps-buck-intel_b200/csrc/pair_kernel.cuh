@@ -24,6 +24,7 @@ struct PairConsts {
   flt_t special_lj[4], special_coul[4];
   int ncoulmask, ncoulshiftbits, ndispmask, ndispshiftbits;
   int order1, order6, coultable, disptable;
+  int same_cut;     // cut_ljsq == cutsq for every type pair: the second cut-off test is skipped
   flt_t mc[MC_N];   // numeric constants of the double-precision math kernels (see fill_math_consts)
 };
 
@@ -153,11 +154,21 @@ __device__ __forceinline__ void ewald_real<float>(float g_ewald, float qqrd2e, f
 
 // j = entry & NEIGHMASK, opaque to the optimiser: otherwise the mask is folded into the 64-bit address arithmetic of
 // x[j] (shift/mask/add-with-carry, 6 instructions) instead of one LOP3 + one IMAD.WIDE
+template <int PACKT>
 __device__ __forceinline__ int nbr_index(const int e) {
   int j;
-  asm("and.b32 %0, %1, 0x3FFFFFFF;" : "=r"(j) : "r"(e));
+  if (PACKT) asm("and.b32 %0, %1, 0x03FFFFFF;" : "=r"(j) : "r"(e));
+  else asm("and.b32 %0, %1, 0x3FFFFFFF;" : "=r"(j) : "r"(e));
   return j;
 }
+// gather of one atom: a single 256-bit load in double mode (LDG.E.256, sm_100: half the L1 wavefronts of two
+// LDG.128 — the L1 data pipe, not HBM, is what the gathers of this kernel load), 128-bit in mixed mode
+__device__ __forceinline__ double4 ld_atom(const double4 *p) {
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_atom(const float4 *p) { return __ldg(p); }
 
 struct PairView {  // device pointers of one evaluation
   int nlocal;
@@ -167,10 +178,120 @@ struct PairView {  // device pointers of one evaluation
   const long long *offsets;
   const int *entries;
   double4 *f;
+  int packed_type;       // entries carry type(j) (NeighState::packed_type)
 };
 
-template <int STYLE, class flt_t, int EVFLAG, int TPA>
-__global__ void __launch_bounds__(256)
+#ifndef PAIR_MINB
+#define PAIR_MINB 4
+#endif
+
+// One pair evaluation: fpair (= F/r), evdwl, ecoul from rsq and the per-type-pair constants `cij`.
+// GENERAL = 1: everything — Coulomb / dispersion lookup tables (INTEL_ALLOW_TABLE), special-bond scaling — written
+//   with the reference's branch structure.
+// GENERAL = 0: the production flavour for lists built on the device (atomic systems: no special bits) with analytic
+//   kernels.  It has NO data-dependent branch: the three cut-off tests become selects, so that the two pairs of the
+//   2x-unrolled loop form one basic block and their FP64 dependency chains (exp -> polynomial -> ...) interleave.
+//   In-range lanes execute exactly the same operations in both flavours (results are bit-identical).
+template <int STYLE, class flt_t, int EVFLAG, int GENERAL>
+__device__ __forceinline__ void pair_eval(const PairConsts<flt_t> &pc, const flt_t *__restrict__ cij,
+                                          const flt_t *__restrict__ ctab, const flt_t *__restrict__ dtab,
+                                          const flt_t *__restrict__ s_tab, const flt_t rsq, const flt_t qtmp,
+                                          const flt_t qj, const int sbindex, flt_t &fpair, flt_t &evdwl, flt_t &ecoul) {
+  const bool in_cut = rsq < cij[C_CUTSQ];
+  fpair = (flt_t)0; evdwl = (flt_t)0; ecoul = (flt_t)0;
+  if (GENERAL && !in_cut) return;
+  flt_t r, rinv, r2inv;
+  m_r<STYLE == B200MD_PAIR_BUCK_COUL_LONG>(rsq, r, rinv, r2inv, pc.mc);
+  flt_t forcecoul = (flt_t)0, forcebuck = (flt_t)0;
+
+  if (STYLE == B200MD_PAIR_BUCK_COUL_CUT) {
+    const bool in_coul = rsq < cij[C_CUT_COULSQ];
+    if (!GENERAL || in_coul) {
+      forcecoul = pc.qqrd2e * qtmp * qj * rinv;
+      if (GENERAL && sbindex) forcecoul *= pc.special_coul[sbindex];
+      if (!GENERAL) forcecoul = in_coul ? forcecoul : (flt_t)0;
+      if (EVFLAG) ecoul = forcecoul;
+    }
+  }
+  if (STYLE == B200MD_PAIR_BUCK_COUL_LONG || (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order1)) {
+    if (!GENERAL || !pc.coultable || rsq <= pc.tabinnersq) {
+      const flt_t EWALD_F = sizeof(flt_t) == 8 ? pc.mc[MC_EWF] : (flt_t)1.12837917;
+      flt_t erfc, expm2, grij, prefactor;
+      ewald_real<flt_t>(pc.g_ewald, pc.qqrd2e, qtmp, qj, r, rinv, grij, expm2, erfc, prefactor, s_tab, pc.mc);
+      forcecoul = prefactor * (erfc + EWALD_F * grij * expm2);
+      if (EVFLAG) ecoul = prefactor * erfc;
+      if (GENERAL && sbindex) {
+        const flt_t adjust = ((flt_t)1.0 - pc.special_coul[sbindex]) * prefactor;
+        forcecoul -= adjust;
+        if (EVFLAG) ecoul -= adjust;
+      }
+    } else {
+      const float rsq_lookup = (float)rsq;
+      const int itable = (__float_as_int(rsq_lookup) & pc.ncoulmask) >> pc.ncoulshiftbits;
+      const flt_t *tb = ctab + 8 * itable;  // {r,dr,f,df,e,de,c,dc}
+      const flt_t fraction = ((flt_t)rsq_lookup - tb[0]) * tb[1];
+      const flt_t qiqj = qtmp * qj;
+      forcecoul = qiqj * (tb[2] + fraction * tb[3]);
+      if (EVFLAG) ecoul = qiqj * (tb[4] + fraction * tb[5]);
+      if (sbindex) {
+        const flt_t prefactor = qiqj * (tb[6] + fraction * tb[7]);
+        const flt_t adjust = ((flt_t)1.0 - pc.special_coul[sbindex]) * prefactor;
+        forcecoul -= adjust;
+        if (EVFLAG) ecoul -= adjust;
+      }
+    }
+  }
+
+  const bool in_lj = pc.same_cut ? true : rsq < cij[C_CUT_LJSQ];
+  if (!GENERAL || in_lj) {
+    const flt_t r6inv = r2inv * r2inv * r2inv;
+    const flt_t rexp = m_exp(-r * cij[C_RHOINV], s_tab, pc.mc);
+    if (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order6) {
+      if (!GENERAL || !pc.disptable || rsq <= pc.tabinnerdispsq) {
+        const flt_t grij2 = pc.g2 * rsq;
+        const flt_t a2 = m_rcp(grij2, pc.mc);
+        const flt_t x2 = a2 * m_exp(-grij2, s_tab, pc.mc) * cij[C_C];
+        forcebuck = r * rexp * cij[C_BUCK1] -
+                    pc.g8 * x2 * rsq * ((((flt_t)6.0 * a2 + (flt_t)6.0) * a2 + (flt_t)3.0) * a2 + (flt_t)1.0);
+        if (EVFLAG) evdwl = rexp * cij[C_A] - pc.g6 * x2 * ((a2 + (flt_t)1.0) * a2 + (flt_t)0.5);
+      } else {
+        const float rsq_lookup = (float)rsq;
+        const int itable = (__float_as_int(rsq_lookup) & pc.ndispmask) >> pc.ndispshiftbits;
+        const flt_t *tb = dtab + 6 * itable;  // {r,dr,f,df,e,de}
+        const flt_t fd = (rsq - tb[0]) * tb[1];
+        forcebuck = r * rexp * cij[C_BUCK1] - (tb[2] + fd * tb[3]) * cij[C_C];
+        if (EVFLAG) evdwl = rexp * cij[C_A] - (tb[4] + fd * tb[5]) * cij[C_C];
+      }
+      if (GENERAL && sbindex) {
+        const flt_t t = pc.special_lj[sbindex] - (flt_t)1.0;
+        forcebuck += t * r * rexp * cij[C_BUCK1] - t * r6inv * cij[C_BUCK2];
+        if (EVFLAG) evdwl += t * rexp * cij[C_A] - t * r6inv * cij[C_C];
+      }
+    } else {
+      forcebuck = r * rexp * cij[C_BUCK1] - r6inv * cij[C_BUCK2];
+      if (EVFLAG) evdwl = rexp * cij[C_A] - r6inv * cij[C_C] - cij[C_OFFSET];
+      if (GENERAL && sbindex) {
+        const flt_t factor_lj = pc.special_lj[sbindex];
+        forcebuck *= factor_lj;
+        if (EVFLAG) evdwl *= factor_lj;
+      }
+    }
+    if (!GENERAL) {
+      forcebuck = in_lj ? forcebuck : (flt_t)0;
+      if (EVFLAG) evdwl = in_lj ? evdwl : (flt_t)0;
+    }
+  }
+
+  fpair = (forcecoul + forcebuck) * r2inv;
+  if (!GENERAL) {
+    fpair = in_cut ? fpair : (flt_t)0;
+    if (EVFLAG) { evdwl = in_cut ? evdwl : (flt_t)0; ecoul = in_cut ? ecoul : (flt_t)0; }
+  }
+}
+
+// PACKT = 1: the entry carries type(j) in bits 26..29 (lists built on the device, internal.h) — no type[j] gather.
+template <int STYLE, class flt_t, int EVFLAG, int TPA, int GENERAL, int PACKT>
+__global__ void __launch_bounds__(256, PAIR_MINB)
 k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const int *__restrict__ type,
        const int *__restrict__ numneigh, const long long *__restrict__ offsets,
        const int *__restrict__ entries, const PairConsts<flt_t> pc, const flt_t *__restrict__ coeff,
@@ -204,118 +325,42 @@ k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const i
     int e_cur = 0, e_nxt = 0;
     if (sub < jnum) e_cur = jlist[sub];
     if (sub + TPA < jnum) e_nxt = jlist[sub + TPA];
-    int j_nxt = nbr_index(e_cur);
-    vec4 xj_nxt = x[j_nxt];
-    int tj_nxt = type[j_nxt];
+    int j_nxt = nbr_index<PACKT>(e_cur);
+    vec4 xj_nxt = ld_atom(x + j_nxt);
+    int tj_nxt = PACKT ? 0 : type[j_nxt];
 
 #pragma unroll 2
     for (int jj = sub; jj < jnum; jj += TPA) {
       const int e = e_cur;
       const vec4 xj = xj_nxt;
-      const int tj = tj_nxt;
+      const int tj = PACKT ? (e >> B2_TYPESHIFT) : tj_nxt;
       e_cur = e_nxt;   // past the row's end this stays a valid (already used) entry: the loads below are harmless
       if (jj + 2 * TPA < jnum) e_nxt = jlist[jj + 2 * TPA];
-      j_nxt = nbr_index(e_cur);
-      xj_nxt = x[j_nxt];
-      tj_nxt = type[j_nxt];
-      const int sbindex = (e >> B2_SBBITS) & 3;
+      j_nxt = nbr_index<PACKT>(e_cur);
+      xj_nxt = ld_atom(x + j_nxt);
+      if (!PACKT) tj_nxt = type[j_nxt];
+      const int sbindex = (GENERAL && !PACKT) ? (e >> B2_SBBITS) & 3 : 0;
       const flt_t *cij = ci + tj * C_N;
       const flt_t delx = xi.x - xj.x;
       const flt_t dely = xi.y - xj.y;
       const flt_t delz = xi.z - xj.z;
       const flt_t rsq = m_rsq(delx, dely, delz);
-      if (rsq < cij[C_CUTSQ]) {
-        flt_t r, rinv, r2inv;
-        m_r<STYLE == B200MD_PAIR_BUCK_COUL_LONG>(rsq, r, rinv, r2inv, pc.mc);
-        flt_t forcecoul = (flt_t)0, forcebuck = (flt_t)0, evdwl = (flt_t)0, ecoul = (flt_t)0;
-
-        if (STYLE == B200MD_PAIR_BUCK_COUL_CUT) {
-          if (rsq < cij[C_CUT_COULSQ]) {
-            forcecoul = pc.qqrd2e * qtmp * xj.w * rinv;
-            if (sbindex) forcecoul *= pc.special_coul[sbindex];
-            if (EVFLAG) ecoul = forcecoul;
-          }
-        }
-        if (STYLE == B200MD_PAIR_BUCK_COUL_LONG || (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order1)) {
-          if (!pc.coultable || rsq <= pc.tabinnersq) {
-            const flt_t EWALD_F = sizeof(flt_t) == 8 ? pc.mc[MC_EWF] : (flt_t)1.12837917;
-            flt_t erfc, expm2, grij, prefactor;
-            ewald_real<flt_t>(pc.g_ewald, pc.qqrd2e, qtmp, xj.w, r, rinv, grij, expm2, erfc, prefactor, s_tab, pc.mc);
-            forcecoul = prefactor * (erfc + EWALD_F * grij * expm2);
-            if (EVFLAG) ecoul = prefactor * erfc;
-            if (sbindex) {
-              const flt_t adjust = ((flt_t)1.0 - pc.special_coul[sbindex]) * prefactor;
-              forcecoul -= adjust;
-              if (EVFLAG) ecoul -= adjust;
-            }
-          } else {
-            const float rsq_lookup = (float)rsq;
-            const int itable = (__float_as_int(rsq_lookup) & pc.ncoulmask) >> pc.ncoulshiftbits;
-            const flt_t *tb = ctab + 8 * itable;  // {r,dr,f,df,e,de,c,dc}
-            const flt_t fraction = ((flt_t)rsq_lookup - tb[0]) * tb[1];
-            const flt_t qiqj = qtmp * xj.w;
-            forcecoul = qiqj * (tb[2] + fraction * tb[3]);
-            if (EVFLAG) ecoul = qiqj * (tb[4] + fraction * tb[5]);
-            if (sbindex) {
-              const flt_t prefactor = qiqj * (tb[6] + fraction * tb[7]);
-              const flt_t adjust = ((flt_t)1.0 - pc.special_coul[sbindex]) * prefactor;
-              forcecoul -= adjust;
-              if (EVFLAG) ecoul -= adjust;
-            }
-          }
-        }
-
-        if (rsq < cij[C_CUT_LJSQ]) {
-          const flt_t r6inv = r2inv * r2inv * r2inv;
-          const flt_t rexp = m_exp(-r * cij[C_RHOINV], s_tab, pc.mc);
-          if (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order6) {
-            if (!pc.disptable || rsq <= pc.tabinnerdispsq) {
-              const flt_t grij2 = pc.g2 * rsq;
-              const flt_t a2 = m_rcp(grij2, pc.mc);
-              const flt_t x2 = a2 * m_exp(-grij2, s_tab, pc.mc) * cij[C_C];
-              forcebuck = r * rexp * cij[C_BUCK1] -
-                          pc.g8 * x2 * rsq * ((((flt_t)6.0 * a2 + (flt_t)6.0) * a2 + (flt_t)3.0) * a2 + (flt_t)1.0);
-              if (EVFLAG) evdwl = rexp * cij[C_A] - pc.g6 * x2 * ((a2 + (flt_t)1.0) * a2 + (flt_t)0.5);
-            } else {
-              const float rsq_lookup = (float)rsq;
-              const int itable = (__float_as_int(rsq_lookup) & pc.ndispmask) >> pc.ndispshiftbits;
-              const flt_t *tb = dtab + 6 * itable;  // {r,dr,f,df,e,de}
-              const flt_t fd = (rsq - tb[0]) * tb[1];
-              forcebuck = r * rexp * cij[C_BUCK1] - (tb[2] + fd * tb[3]) * cij[C_C];
-              if (EVFLAG) evdwl = rexp * cij[C_A] - (tb[4] + fd * tb[5]) * cij[C_C];
-            }
-            if (sbindex) {
-              const flt_t t = pc.special_lj[sbindex] - (flt_t)1.0;
-              forcebuck += t * r * rexp * cij[C_BUCK1] - t * r6inv * cij[C_BUCK2];
-              if (EVFLAG) evdwl += t * rexp * cij[C_A] - t * r6inv * cij[C_C];
-            }
-          } else {
-            forcebuck = r * rexp * cij[C_BUCK1] - r6inv * cij[C_BUCK2];
-            if (EVFLAG) evdwl = rexp * cij[C_A] - r6inv * cij[C_C] - cij[C_OFFSET];
-            if (sbindex) {
-              const flt_t factor_lj = pc.special_lj[sbindex];
-              forcebuck *= factor_lj;
-              if (EVFLAG) evdwl *= factor_lj;
-            }
-          }
-        }
-
-        const flt_t fpair = (forcecoul + forcebuck) * r2inv;
-        const double dfx = (double)(delx * fpair), dfy = (double)(dely * fpair), dfz = (double)(delz * fpair);
-        fx += dfx;
-        fy += dfy;
-        fz += dfz;
-        if (EVFLAG) {
-          sevdwl += 0.5 * (double)evdwl;
-          secoul += 0.5 * (double)ecoul;
-          const flt_t hf = (flt_t)0.5 * fpair;  // IP_PRE_ev_tally_nbor with ev_pre = 1/2
-          sv0 += (double)(hf * delx * delx);
-          sv1 += (double)(hf * dely * dely);
-          sv2 += (double)(hf * delz * delz);
-          sv3 += (double)(hf * delx * dely);
-          sv4 += (double)(hf * delx * delz);
-          sv5 += (double)(hf * dely * delz);
-        }
+      flt_t fpair, evdwl, ecoul;
+      pair_eval<STYLE, flt_t, EVFLAG, GENERAL>(pc, cij, ctab, dtab, s_tab, rsq, qtmp, xj.w, sbindex, fpair, evdwl, ecoul);
+      const double dfx = (double)(delx * fpair), dfy = (double)(dely * fpair), dfz = (double)(delz * fpair);
+      fx += dfx;
+      fy += dfy;
+      fz += dfz;
+      if (EVFLAG) {
+        sevdwl += 0.5 * (double)evdwl;
+        secoul += 0.5 * (double)ecoul;
+        const flt_t hf = (flt_t)0.5 * fpair;  // IP_PRE_ev_tally_nbor with ev_pre = 1/2
+        sv0 += (double)(hf * delx * delx);
+        sv1 += (double)(hf * dely * dely);
+        sv2 += (double)(hf * delz * delz);
+        sv3 += (double)(hf * delx * dely);
+        sv4 += (double)(hf * delx * delz);
+        sv5 += (double)(hf * dely * delz);
       }
     }
   }
@@ -400,40 +445,44 @@ PairConsts<flt_t> make_consts(const PairState &ps) {
   pc.coultable = p.ncoultablebits != 0;
   pc.disptable = p.ndisptablebits != 0;
   fill_math_consts(pc.mc);
+  pc.same_cut = ps.same_cut ? 1 : 0;
   return pc;
 }
 
 static inline int pick_tpa(const b200md_ctx *ctx, int nlocal, long long total_entries) {
   // enough lanes per atom to coalesce the CSR row reads, fewer when the rows are short
   const double avg = nlocal > 0 ? (double)total_entries / nlocal : 0.0;
-  if (avg >= 256.0) return 8;
-  if (avg >= 48.0) return 8;
-  if (avg >= 16.0) return 4;
   (void)ctx;
-  return 4;
+  return avg >= 48.0 ? 8 : 4;
 }
 
 template <int STYLE, class flt_t, int EVFLAG>
-int launch_tpa(b200md_ctx *ctx, const PairView &v, int tpa, const PairConsts<flt_t> &pc, const flt_t *coeff,
-               const flt_t *ctab, const flt_t *dtab, const flt_t *exptab, double *ev_partial, int nblocks) {
+int launch_tpa(b200md_ctx *ctx, const PairView &v, int tpa, int variant, const PairConsts<flt_t> &pc,
+               const flt_t *coeff, const flt_t *ctab, const flt_t *dtab, const flt_t *exptab, double *ev_partial,
+               int nblocks) {
   typedef typename V4<flt_t>::type vec4;
-#define LAUNCH(T)                                                                                          \
-  k_pair<STYLE, flt_t, EVFLAG, T><<<nblocks, 256, 0, ctx->stream>>>(                                        \
-      v.nlocal, (const vec4 *)v.x, v.type, v.numneigh, v.offsets, v.entries, pc, coeff, ctab, dtab, exptab,   \
+#define LAUNCH(T, G, P)                                                                                    \
+  k_pair<STYLE, flt_t, EVFLAG, T, G, P><<<nblocks, 256, 0, ctx->stream>>>(                                  \
+      v.nlocal, (const vec4 *)v.x, v.type, v.numneigh, v.offsets, v.entries, pc, coeff, ctab, dtab, exptab, \
       v.f, ev_partial)
-  switch (tpa) {
-    case 4: LAUNCH(4); break;
-    case 8: LAUNCH(8); break;
-    case 16: LAUNCH(16); break;
-    default: LAUNCH(32); break;
-  }
+#define LAUNCH_T(T)                                \
+  do {                                             \
+    if (variant == 0) LAUNCH(T, 0, 1);             \
+    else if (variant == 1) LAUNCH(T, 1, 1);        \
+    else LAUNCH(T, 1, 0);                          \
+  } while (0)
+  if (tpa == 4) LAUNCH_T(4);
+  else LAUNCH_T(8);
+#undef LAUNCH_T
 #undef LAUNCH
   KERNEL_OK(ctx, "k_pair");
   return 0;
 }
 
+// has_special: the list may carry special-bond bits (host-supplied lists); lists built on the device never do
 template <class flt_t>
-int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int evflag, double *ev_dev) {
+int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int evflag, double *ev_dev,
+                int has_special) {
   PairState &ps = ctx->pair;
   PairConsts<flt_t> pc = make_consts<flt_t>(ps);
   pc.qqrd2e = (flt_t)ctx->qqrd2e;
@@ -444,6 +493,9 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
   } else {
     coeff = (const flt_t *)ps.coeff_f.p; ctab = (const flt_t *)ps.ctab_f.p; dtab = (const flt_t *)ps.dtab_f.p;
   }
+  // 0: branch-free analytic, packed type; 1: tables, packed type; 2: everything, type gathered (host lists)
+  const int variant = !v.packed_type ? 2 : ((pc.coultable || pc.disptable) ? 1 : 0);
+  if (has_special && v.packed_type) return b2_fail(ctx, B200MD_EINVAL, "packed-type list with special bits");
   const int tpa = pick_tpa(ctx, v.nlocal, total_entries);
   const int nblocks = cdiv((long)v.nlocal * tpa, 256);
   if (nblocks == 0) {
@@ -452,10 +504,10 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
   }
   if (evflag) RESERVE(ctx, ctx->ev_partial, (size_t)nblocks * 8);
   double *evp = ctx->ev_partial.p;
-#define STYLE_CASE(S)                                                                              \
-  case S:                                                                                          \
-    if (evflag) TRY((launch_tpa<S, flt_t, 1>(ctx, v, tpa, pc, coeff, ctab, dtab, exptab, evp, nblocks)));  \
-    else TRY((launch_tpa<S, flt_t, 0>(ctx, v, tpa, pc, coeff, ctab, dtab, exptab, evp, nblocks)));         \
+#define STYLE_CASE(S)                                                                                            \
+  case S:                                                                                                        \
+    if (evflag) TRY((launch_tpa<S, flt_t, 1>(ctx, v, tpa, variant, pc, coeff, ctab, dtab, exptab, evp, nblocks))); \
+    else TRY((launch_tpa<S, flt_t, 0>(ctx, v, tpa, variant, pc, coeff, ctab, dtab, exptab, evp, nblocks)));        \
     break;
   switch (ps.p.style) {
     STYLE_CASE(B200MD_PAIR_BUCK)
@@ -475,5 +527,7 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
 }  // namespace pairk
 
 // pair.cu / pair_mixed.cu
-int b2_launch_pair_double(b200md_ctx *ctx, const pairk::PairView &v, long long total_entries, int evflag, double *ev_dev);
-int b2_launch_pair_float(b200md_ctx *ctx, const pairk::PairView &v, long long total_entries, int evflag, double *ev_dev);
+int b2_launch_pair_double(b200md_ctx *ctx, const pairk::PairView &v, long long total_entries, int evflag, double *ev_dev,
+                          int has_special);
+int b2_launch_pair_float(b200md_ctx *ctx, const pairk::PairView &v, long long total_entries, int evflag, double *ev_dev,
+                         int has_special);
