@@ -94,6 +94,9 @@ struct NeighState {
   DevBuf<int> numneigh;
   DevBuf<long long> offsets;
   DevBuf<int> entries;
+  DevBuf<int> mask_words;         // build scratch: mask words per bin
+  DevBuf<long long> mask_off;     // their exclusive scan
+  DevBuf<unsigned> maskbuf;       // hit masks [bin][atom][candidate word]
   long long total_entries = 0;
   int max_numneigh = 0;
   bool packed_type = false;   // entries carry type(j) << B2_TYPESHIFT

@@ -295,117 +295,307 @@ struct Pos<float> {
   }
 };
 
-// One BLOCK per bin.  The block stages the positions/types of all candidate atoms of the bin's stencil (25 (y,z)
-// rows x {owned range, ghost range}, each one contiguous index range) in shared memory with coalesced loads, then
-// every warp takes owned atoms of the bin and scans the staged candidates 32 at a time: distance test, ballot,
-// ordered compaction, coalesced stores.  Candidates are read from HBM/L2 once per bin instead of once per atom.
-// FILL = 0 counts (numneigh), FILL = 1 writes the rows at offsets[i].  Candidate order = row order, owned then
-// ghost, ascending index => deterministic rows.
-#define NB_CHUNK 1536     // candidates staged at a time (static shared memory stays under 48 KB)
-#define NB_MAXI 64        // owned atoms of the bin handled per staging sweep
-#define NB_THREADS 512
+// ---- full list build: distances ONCE, as hit bit-masks; the fill pass is pure data movement ---------------------
+// One BLOCK per interior bin.  The candidates of the bin's stencil are 25 (y,z) rows x {owned range, ghost range},
+// each one contiguous index range, enumerated c = 0..ncand-1 in a fixed order (row order, owned then ghost, ascending
+// index => deterministic rows).
+//   k_nb_ranges  per bin: ncand, mask words per atom, atoms -> sizes for the mask buffer (scanned on the device)
+//   k_nb_mask    a warp takes 32 candidates (one per lane, held in registers) and loops over the bin's atoms, whose
+//                coordinates are broadcast from shared memory: one ballot per (atom, 32 candidates) is the hit mask,
+//                stored to HBM; per-atom counts are integer shared-memory atomics.
+//   k_nb_fill    a warp takes an atom, reads its mask words and writes the row (ordered compaction, coalesced).
+// Double mode: the test runs in FP32 on coordinates relative to the bin centre with a guard band; the (very rare)
+// candidates inside the band are decided by the exact un-fused FP64 expression, so the pair set stays bit-exact while
+// the FP64 pipe is idle.  Mixed mode: the criterion IS the reference's float expression on absolute float coordinates.
+#define NB_THREADS 256
+#define NB_MAXI 64          // owned atoms of a bin handled per sweep
+#define NB_MAXR 64          // candidate ranges per bin (<= 2 * (2s+1)^2 with s <= 2 -> 50)
+#define NB_FILLC 4096       // candidates staged at a time by the fill kernel
 
-template <class flt_t, int FILL>
+struct BinRanges {
+  int start[NB_MAXR];
+  int pref[NB_MAXR + 1];
+  int nr;
+};
+
+__device__ __forceinline__ void bin_ranges(const BinGeom &g, int nlocal, const int *__restrict__ lstart,
+                                           const int *__restrict__ gstart, int ex, int ey, int ez, BinRanges &R) {
+  const int x0 = max(ex - g.s[0], 0), x1 = min(ex + g.s[0], g.mbin[0] - 1);
+  int nr = 0, tot = 0;
+  for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
+    const int rz = ez + dz;
+    if (rz < 0 || rz >= g.mbin[2]) continue;
+    for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
+      const int ry = ey + dy;
+      if (ry < 0 || ry >= g.mbin[1]) continue;
+      const int row = (rz * g.mbin[1] + ry) * g.mbin[0];
+      for (int kind = 0; kind < 2; kind++) {
+        const int *sp = kind ? gstart : lstart;
+        const int base = kind ? nlocal : 0;
+        const int j0 = sp[row + x0] + base, j1 = sp[row + x1 + 1] + base;
+        if (j1 > j0 && nr < NB_MAXR) {
+          R.start[nr] = j0;
+          R.pref[nr] = tot;
+          tot += j1 - j0;
+          nr++;
+        }
+      }
+    }
+  }
+  R.pref[nr] = tot;
+  R.nr = nr;
+}
+
+__device__ __forceinline__ int cand_index(const BinRanges &R, int c) {
+  int lo = 0, hi = R.nr - 1;  // range r with pref[r] <= c < pref[r+1]
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (R.pref[mid] <= c) lo = mid; else hi = mid - 1;
+  }
+  return R.start[lo] + (c - R.pref[lo]);
+}
+
+__device__ __forceinline__ void bin_of_block(const BinGeom &g, int blk, int &ex, int &ey, int &ez) {
+  const int bx = blk % g.nbin[0], by = (blk / g.nbin[0]) % g.nbin[1], bz = blk / (g.nbin[0] * g.nbin[1]);
+  ex = bx + g.m[0]; ey = by + g.m[1]; ez = bz + g.m[2];
+}
+
+// words of mask storage per bin = atoms(bin) * ceil(ncand(bin)/32)
+__global__ void k_nb_ranges(int nblk, int nlocal, const int *__restrict__ lstart, const int *__restrict__ gstart,
+                            BinGeom g, int *__restrict__ words) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= nblk) return;
+  int ex, ey, ez;
+  bin_of_block(g, blk, ex, ey, ez);
+  const int binid = (ez * g.mbin[1] + ey) * g.mbin[0] + ex;
+  const int ni = lstart[binid + 1] - lstart[binid];
+  const int x0 = max(ex - g.s[0], 0), x1 = min(ex + g.s[0], g.mbin[0] - 1);
+  int tot = 0;
+  for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
+    const int rz = ez + dz;
+    if (rz < 0 || rz >= g.mbin[2]) continue;
+    for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
+      const int ry = ey + dy;
+      if (ry < 0 || ry >= g.mbin[1]) continue;
+      const int row = (rz * g.mbin[1] + ry) * g.mbin[0];
+      tot += lstart[row + x1 + 1] - lstart[row + x0] + gstart[row + x1 + 1] - gstart[row + x0];
+    }
+  }
+  words[blk] = ni * ((tot + 31) >> 5);
+}
+
+#define NB_MAXW 512         // mask words per atom with a precomputed word -> range table (else binary search)
+
+// candidate c -> atom index, starting the search at the range of the word's first candidate
+__device__ __forceinline__ int cand_index_from(const BinRanges &R, int r, int c) {
+  while (c >= R.pref[r + 1]) r++;
+  return R.start[r] + (c - R.pref[r]);
+}
+__device__ __forceinline__ int cand_range(const BinRanges &R, int c) {
+  int lo = 0, hi = R.nr - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (R.pref[mid] <= c) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// UCUT = 1: one cutneighsq for every type pair (the common case): thresholds live in registers.
+template <class flt_t, int UCUT>
 __global__ void __launch_bounds__(NB_THREADS)
-k_build(int nlocal, const typename Pos<flt_t>::vec *__restrict__ x, const int *__restrict__ type,
-        const int *__restrict__ lstart, const int *__restrict__ gstart, BinGeom g, int tp1,
-        const double *__restrict__ cutneighsq, int *__restrict__ numneigh, const long long *__restrict__ offsets,
-        int *__restrict__ entries, int *__restrict__ maxn, int pack_type) {
-  __shared__ flt_t s_cut[(B2_MAXTYPES + 1) * (B2_MAXTYPES + 1)];
-  __shared__ flt_t sx[NB_CHUNK], sy[NB_CHUNK], sz[NB_CHUNK];
-  __shared__ int sj[NB_CHUNK];
-  __shared__ unsigned char st[NB_CHUNK];
-  __shared__ int r_start[64], r_pref[65];   // candidate ranges (<= 2 * (2s+1)^2, s <= 2 -> 50) and their prefix sums
+k_nb_mask(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xqf, const int *__restrict__ type,
+          const int *__restrict__ lstart, const int *__restrict__ gstart, BinGeom g, int tp1,
+          const double *__restrict__ cutneighsq, const long long *__restrict__ maskoff,
+          unsigned *__restrict__ maskbuf, int *__restrict__ numneigh, int *__restrict__ maxn, int prefilter) {
+  constexpr int NT2 = (B2_MAXTYPES + 1) * (B2_MAXTYPES + 1);
+  __shared__ BinRanges R;
+  __shared__ float s_cut[NT2], s_band[NT2];
+  __shared__ float4 s_xi[NB_MAXI];         // double: bin-relative coordinates; float: absolute.  w = type * tp1
   __shared__ int s_cnt[NB_MAXI];
-  __shared__ int s_nr;
+  __shared__ unsigned char s_wr[NB_MAXW];  // range holding the first candidate of each mask word
+  __shared__ int s_self;                   // enumeration index of the bin's first own atom
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NB_THREADS / 32;
-  for (int k = tid; k < tp1 * tp1; k += NB_THREADS) s_cut[k] = (flt_t)cutneighsq[k];
-  // interior bin of this block
-  const int bx = blockIdx.x % g.nbin[0], by = (blockIdx.x / g.nbin[0]) % g.nbin[1], bz = blockIdx.x / (g.nbin[0] * g.nbin[1]);
-  const int ex = bx + g.m[0], ey = by + g.m[1], ez = bz + g.m[2];
+  int ex, ey, ez;
+  bin_of_block(g, blockIdx.x, ex, ey, ez);
   const int binid = (ez * g.mbin[1] + ey) * g.mbin[0] + ex;
   const int i0 = lstart[binid], i1 = lstart[binid + 1];
   if (i0 == i1) return;
   if (tid == 0) {
-    const int x0 = max(ex - g.s[0], 0), x1 = min(ex + g.s[0], g.mbin[0] - 1);
-    int nr = 0, tot = 0;
-    for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
-      const int rz = ez + dz;
-      if (rz < 0 || rz >= g.mbin[2]) continue;
-      for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
-        const int ry = ey + dy;
-        if (ry < 0 || ry >= g.mbin[1]) continue;
-        const int row = (rz * g.mbin[1] + ry) * g.mbin[0];
-        for (int kind = 0; kind < 2; kind++) {
-          const int *sp = kind ? gstart : lstart;
-          const int base = kind ? nlocal : 0;
-          const int j0 = sp[row + x0] + base, j1 = sp[row + x1 + 1] + base;
-          if (j1 > j0) {
-            r_start[nr] = j0;
-            r_pref[nr] = tot;
-            tot += j1 - j0;
-            nr++;
-          }
-        }
-      }
-    }
-    r_pref[nr] = tot;
-    s_nr = nr;
+    bin_ranges(g, nlocal, lstart, gstart, ex, ey, ez, R);
+    int cs = 0;
+    for (int r = 0; r < R.nr; r++)
+      if (R.start[r] <= i0 && i0 < R.start[r] + (R.pref[r + 1] - R.pref[r])) cs = R.pref[r] + (i0 - R.start[r]);
+    s_self = cs;
   }
+  // Double mode: the test runs in FP32 on bin-relative coordinates.  |rsq - cut| >= band decides in FP32 (the FP32
+  // error of rsq is < 1e-6 * cutneighsq, the band is 2e-5 * cutneighsq); a word with any candidate inside the band is
+  // redone with the exact un-fused FP64 expression (rare: ~4e-3 of the words).  prefilter = 0 (non-periodic boxes:
+  // atoms clamped into edge bins may sit far from the bin centre): band = inf, everything takes the exact test.
+  // Mixed mode: band = 0, the float expression on absolute float coordinates IS the criterion.
+  for (int k = tid; k < tp1 * tp1; k += NB_THREADS) {
+    const float cut = (float)cutneighsq[k];
+    s_cut[k] = cut;
+    s_band[k] = sizeof(flt_t) == 8 ? (prefilter ? cut * 2.0e-5f : __int_as_float(0x7f800000)) : 0.0f;
+  }
+  const double cx = g.lo[0] + ((ex - g.m[0]) + 0.5) / g.bininv[0];
+  const double cy = g.lo[1] + ((ey - g.m[1]) + 0.5) / g.bininv[1];
+  const double cz = g.lo[2] + ((ez - g.m[2]) + 0.5) / g.bininv[2];
   __syncthreads();
-  const int nr = s_nr, ncand = r_pref[nr];
+  const int ncand = R.pref[R.nr];
+  const int nwords = (ncand + 31) >> 5;
+  for (int w = tid; w < min(nwords, NB_MAXW); w += NB_THREADS) s_wr[w] = (unsigned char)cand_range(R, w * 32);
+  const int nit = i1 - i0;
+  const int cself0 = s_self;
+  const float ucut = s_cut[tp1 + 1], uband = s_band[tp1 + 1];
+  unsigned *mbase = maskbuf + maskoff[blockIdx.x];
   for (int ib = i0; ib < i1; ib += NB_MAXI) {
     const int ni = min(NB_MAXI, i1 - ib);
-    for (int k = tid; k < ni; k += NB_THREADS) s_cnt[k] = 0;
-    for (int c0 = 0; c0 < ncand; c0 += NB_CHUNK) {
-      const int nc = min(NB_CHUNK, ncand - c0);
-      __syncthreads();  // previous chunk fully consumed (and s_cnt zeroed)
-      for (int k = tid; k < nc; k += NB_THREADS) {
-        const int c = c0 + k;
-        int lo = 0, hi = nr - 1;      // range r with r_pref[r] <= c < r_pref[r+1]
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (r_pref[mid] <= c) lo = mid; else hi = mid - 1;
-        }
-        const int j = r_start[lo] + (c - r_pref[lo]);
-        const typename Pos<flt_t>::vec p = x[j];
-        sx[k] = p.x; sy[k] = p.y; sz[k] = p.z;
-        sj[k] = j;
-        st[k] = (unsigned char)type[j];
-      }
-      __syncthreads();
-      for (int ii = warp; ii < ni; ii += nwarps) {
-        const int i = ib + ii;
-        const typename Pos<flt_t>::vec xi = x[i];
-        const flt_t *cut_i = s_cut + type[i] * tp1;
-        int count = s_cnt[ii];
-        const long long w0 = FILL ? offsets[i] : 0;
-        for (int k0 = 0; k0 < nc; k0 += 32) {
-          const int k = k0 + lane;
-          bool hit = false;
-          int j = -1;
-          if (k < nc) {
-            j = sj[k];
-            typename Pos<flt_t>::vec xj;
-            xj.x = sx[k]; xj.y = sy[k]; xj.z = sz[k];
-            const flt_t rsq = Pos<flt_t>::rsq(xi, xj);
-            hit = (j != i) && (rsq <= cut_i[st[k]]);
-          }
-          const unsigned mk = __ballot_sync(0xffffffffu, hit);
-          if (FILL && hit)
-            entries[w0 + count + __popc(mk & ((1u << lane) - 1))] = pack_type ? (j | ((int)st[k] << B2_TYPESHIFT)) : j;
-          count += __popc(mk);
-        }
-        if (lane == 0) s_cnt[ii] = count;
+    __syncthreads();
+    for (int k = tid; k < ni; k += NB_THREADS) {
+      s_cnt[k] = 0;
+      const int tw = type[ib + k] * tp1;
+      if (sizeof(flt_t) == 8) {
+        const double4 p = xq[ib + k];
+        s_xi[k] = make_float4((float)(p.x - cx), (float)(p.y - cy), (float)(p.z - cz), __int_as_float(tw));
+      } else {
+        const float4 p = xqf[ib + k];
+        s_xi[k] = make_float4(p.x, p.y, p.z, __int_as_float(tw));
       }
     }
     __syncthreads();
-    if (!FILL)
-      for (int k = tid; k < ni; k += NB_THREADS) {
-        numneigh[ib + k] = s_cnt[k];
-        atomicMax(maxn, s_cnt[k]);
+    for (int w = warp; w < nwords; w += nwarps) {
+      const int c = w * 32 + lane;
+      const bool valid = c < ncand;
+      const int j = !valid ? 0 : (w < NB_MAXW ? cand_index_from(R, s_wr[w], c) : cand_index(R, c));
+      float xj, yj, zj;
+      const int tj = type[j];
+      if (sizeof(flt_t) == 8) {
+        const double4 p = xq[j];
+        xj = (float)(p.x - cx); yj = (float)(p.y - cy); zj = (float)(p.z - cz);
+      } else {
+        const float4 p = xqf[j];
+        xj = p.x; yj = p.y; zj = p.z;
       }
+      if (!valid) xj = 3.0e18f;   // never within any cut-off
+      // lane L keeps the mask of atom ii0 + L: one coalesced store per 32 atoms (layout [word][atom of the bin])
+      for (int ii0 = 0; ii0 < ni; ii0 += 32) {
+        const int nii = min(32, ni - ii0);
+        unsigned mymask = 0u;
+        bool amb = false;
+#pragma unroll 4
+        for (int k = 0; k < nii; k++) {
+          const float4 pi = s_xi[ii0 + k];
+          float rsq;
+          if (sizeof(flt_t) == 8) {
+            const float dx = pi.x - xj, dy = pi.y - yj, dz = pi.z - zj;
+            rsq = dx * dx + dy * dy + dz * dz;
+          } else {
+            rsq = Pos<float>::rsq(make_float4(pi.x, pi.y, pi.z, 0.f), make_float4(xj, yj, zj, 0.f));
+          }
+          float cut, band;
+          if (UCUT) { cut = ucut; band = uband; }
+          else { const int t2 = __float_as_int(pi.w) + tj; cut = s_cut[t2]; band = s_band[t2]; }
+          const unsigned mk = __ballot_sync(0xffffffffu, rsq <= cut);
+          if (sizeof(flt_t) == 8) amb = amb || (fabsf(rsq - cut) < band);
+          if (lane == k) mymask = mk;
+        }
+        if (sizeof(flt_t) == 8 && __any_sync(0xffffffffu, amb)) {
+          // exact redo of this word for the nii atoms
+          const double4 pj = xq[j];
+          for (int k = 0; k < nii; k++) {
+            const int ti = __float_as_int(s_xi[ii0 + k].w);
+            const bool hit = valid && Pos<double>::rsq(xq[ib + ii0 + k], pj) <= cutneighsq[ti + tj];
+            const unsigned mk = __ballot_sync(0xffffffffu, hit);
+            if (lane == k) mymask = mk;
+          }
+        }
+        if (lane < nii) {
+          // the atom itself is one of its candidates (rsq = 0): clear that bit
+          const int cs = cself0 + (ib - i0) + ii0 + lane;
+          if ((cs >> 5) == w) mymask &= ~(1u << (cs & 31));
+          mbase[(size_t)w * nit + (ib - i0 + ii0 + lane)] = mymask;
+          if (mymask) atomicAdd(&s_cnt[ii0 + lane], __popc(mymask));
+        }
+      }
+    }
     __syncthreads();
+    for (int k = tid; k < ni; k += NB_THREADS) {
+      numneigh[ib + k] = s_cnt[k];
+      atomicMax(maxn, s_cnt[k]);
+    }
+  }
+}
+
+// Fill: a warp takes an atom.  Per block of 32 mask words: lane L owns word L, a warp prefix sum of the popcounts
+// gives its run's offset, it expands its set bits into the warp's row buffer in shared memory, and the warp copies the
+// buffer to the CSR row with full-width coalesced stores.
+#undef NB_FILLC
+#define NB_FILLC 2048       // candidates staged at a time (64 mask words)
+__global__ void __launch_bounds__(NB_THREADS)
+k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lstart, const int *__restrict__ gstart,
+          BinGeom g, const long long *__restrict__ maskoff, const unsigned *__restrict__ maskbuf,
+          const long long *__restrict__ offsets, int *__restrict__ entries, int pack_type) {
+  __shared__ BinRanges R;
+  __shared__ int s_j[NB_FILLC];
+  __shared__ int s_buf[NB_THREADS / 32][1024];   // per warp: the hits of one 32-word block, in row order
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NB_THREADS / 32;
+  int ex, ey, ez;
+  bin_of_block(g, blockIdx.x, ex, ey, ez);
+  const int binid = (ez * g.mbin[1] + ey) * g.mbin[0] + ex;
+  const int i0 = lstart[binid], i1 = lstart[binid + 1];
+  if (i0 == i1) return;
+  if (tid == 0) bin_ranges(g, nlocal, lstart, gstart, ex, ey, ez, R);
+  __syncthreads();
+  const int ncand = R.pref[R.nr];
+  const int nwords = (ncand + 31) >> 5;
+  const int nit = i1 - i0;
+  const unsigned *mbase = maskbuf + maskoff[blockIdx.x];
+  int *buf = s_buf[warp];
+  for (int c0 = 0; c0 < ncand; c0 += NB_FILLC) {
+    const int nc = min(NB_FILLC, ncand - c0);
+    __syncthreads();
+    // one binary search per warp-load of 32 candidates, then a short forward walk (ranges hold ~40 candidates)
+    for (int k = tid; k < nc; k += NB_THREADS) {
+      const int r0 = cand_range(R, c0 + (k & ~31));
+      const int j = cand_index_from(R, r0, c0 + k);
+      s_j[k] = pack_type ? (j | (type[j] << B2_TYPESHIFT)) : j;
+    }
+    __syncthreads();
+    const int w0 = c0 >> 5, w1 = min(nwords, (c0 + NB_FILLC) >> 5);
+    for (int ii = warp; ii < nit; ii += nwarps) {
+      const unsigned *mcol = mbase + ii;   // word w of this atom: mcol[w * nit]
+      long long wpos = offsets[i0 + ii];
+      if (c0 > 0) {   // entries already written for this row by earlier candidate windows
+        int before = 0;
+        for (int w = lane; w < w0; w += 32) before += __popc(mcol[(size_t)w * nit]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+        wpos += before;
+      }
+      for (int wb = w0; wb < w1; wb += 32) {
+        const int wmine = wb + lane;
+        unsigned m = wmine < w1 ? mcol[(size_t)wmine * nit] : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int o = incl - cnt;
+        const int *sj = s_j + ((wmine << 5) - c0);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          buf[o++] = sj[b];
+        }
+        __syncwarp();
+        for (int k = lane; k < total; k += 32) entries[wpos + k] = buf[k];
+        __syncwarp();
+        wpos += total;
+      }
+    }
   }
 }
 
@@ -622,22 +812,41 @@ int b2_neigh_build(b200md_ctx *ctx) {
   }
   TRY(b2_refresh_float_copy(ctx, 0, n));
 
-  // 3. full list: count, scan to 64-bit CSR offsets, fill
+  // 3. full list: hit masks + counts, scan to 64-bit CSR offsets, fill from the masks
   long long total = 0;
   int maxn = 0;
   const int pack = (nall <= (size_t)B2_IDXMASK26 && ctx->ntypes < 16) ? 1 : 0;
   ns.packed_type = pack != 0;
   if (n > 0) {
     const int nblk = g.nbin[0] * g.nbin[1] * g.nbin[2];  // one block per interior bin
-    if (ctx->prec == B200MD_PREC_MIXED)
-      k_build<float, 0><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, lstart, gstart, g,
-                                                      ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p, nullptr,
-                                                      nullptr, ns.flags.p + 2, 0);
-    else
-      k_build<double, 0><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, lstart, gstart, g,
-                                                       ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p, nullptr,
-                                                       nullptr, ns.flags.p + 2, 0);
-    KERNEL_OK(ctx, "k_build<count>");
+    if (2 * (2 * g.s[1] + 1) * (2 * g.s[2] + 1) > NB_MAXR)
+      return b2_fail(ctx, B200MD_EOVERFLOW, "neighbour stencil too wide for the bin size");
+    RESERVE(ctx, ns.mask_words, (size_t)nblk + 1);
+    RESERVE(ctx, ns.mask_off, (size_t)nblk + 2);
+    RESERVE(ctx, ns.scan_ws, b2_scan_ws_bytes((size_t)nblk + 1));
+    k_nb_ranges<<<cdiv(nblk, 128), 128, 0, ctx->stream>>>(nblk, n, lstart, gstart, g, ns.mask_words.p);
+    KERNEL_OK(ctx, "k_nb_ranges");
+    TRY(b2_exclusive_scan_i32_i64(ctx, ns.mask_words.p, ns.mask_off.p, (size_t)nblk, ns.scan_ws.p));
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.mask_off.p + nblk, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    const long long mask_total = *(long long *)ctx->h_pinned;
+    RESERVE(ctx, ns.maskbuf, (size_t)mask_total + 64);
+    const int prefilter = (g.periodic[0] && g.periodic[1] && g.periodic[2]) ? 1 : 0;
+    bool ucut = true;   // one cutneighsq for all type pairs?
+    {
+      const int tp1 = ctx->pair.tp1;
+      for (int a = 1; a < tp1; a++)
+        for (int b = 1; b < tp1; b++)
+          if (ctx->pair.h_cutsq[a * tp1 + b] != ctx->pair.h_cutsq[tp1 + 1]) ucut = false;
+    }
+#define NB_MASK(F, U)                                                                                              \
+  k_nb_mask<F, U><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->xqf.p, ctx->type.p, lstart, gstart, g,   \
+                                                        ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.mask_off.p,      \
+                                                        ns.maskbuf.p, ns.numneigh.p, ns.flags.p + 2, prefilter)
+    if (ctx->prec == B200MD_PREC_MIXED) { if (ucut) NB_MASK(float, 1); else NB_MASK(float, 0); }
+    else { if (ucut) NB_MASK(double, 1); else NB_MASK(double, 0); }
+#undef NB_MASK
+    KERNEL_OK(ctx, "k_nb_mask");
     TRY(b2_exclusive_scan_i32_i64(ctx, ns.numneigh.p, ns.offsets.p, (size_t)n, ns.scan_ws.p));
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ns.flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -645,15 +854,9 @@ int b2_neigh_build(b200md_ctx *ctx) {
     total = *(long long *)ctx->h_pinned;
     maxn = *(int *)(ctx->h_pinned + 1);
     RESERVE(ctx, ns.entries, (size_t)total + 64);
-    if (ctx->prec == B200MD_PREC_MIXED)
-      k_build<float, 1><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xqf.p, ctx->type.p, lstart, gstart, g,
-                                                      ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p,
-                                                      ns.offsets.p, ns.entries.p, ns.flags.p + 2, pack);
-    else
-      k_build<double, 1><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->type.p, lstart, gstart, g,
-                                                       ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.numneigh.p,
-                                                       ns.offsets.p, ns.entries.p, ns.flags.p + 2, pack);
-    KERNEL_OK(ctx, "k_build<fill>");
+    k_nb_fill<<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->type.p, lstart, gstart, g, ns.mask_off.p, ns.maskbuf.p,
+                                                    ns.offsets.p, ns.entries.p, pack);
+    KERNEL_OK(ctx, "k_nb_fill");
   }
   ns.total_entries = total;
   ns.max_numneigh = maxn;
