@@ -73,6 +73,27 @@ def build(force=False, verbose=False):
     return LIBPATH
 
 
+HOST = os.path.join(HERE, "host")
+LMP = os.path.join(HERE, "lmp_b200")
+
+
+def build_host(force=False, verbose=False):
+    """g++ -> lammps-buck-intel_b200/lmp_b200: the C++ host classes (host/*.cpp, the reference's class surface) and the
+    input-script driver, linked against libb200md.so."""
+    srcs = sorted(os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".cpp"))
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [HEADER, LIBPATH]
+    if not force and os.path.exists(LMP) and os.path.getmtime(LMP) >= max(os.path.getmtime(d) for d in deps):
+        return LMP
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", LMP] + srcs + \
+          ["-L", HERE, "-l:libb200md.so", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n" + r.stdout + r.stderr)
+    return LMP
+
+
 def nccl_paths():
     """(include dir, lib dir) of NCCL: the torch-bundled copy when present (so one libnccl.so.2 serves both torch's
     bootstrap and this library in the same process), else the system one."""
@@ -255,6 +276,67 @@ def init_coul_tables(cut_coul, g_ewald, qqrd2e, nbits=12, tabinner=np.sqrt(2.0))
     for k in t:
         t[k] = np.ascontiguousarray(t[k])
     return t, nmask, nshiftbits, tabinnersq
+
+
+def _bitmap(inner, outer, nbits):
+    nlowermin = 1
+    while not (2.0 ** nlowermin <= inner * inner < 2.0 ** (nlowermin + 1)):
+        nlowermin += 1 if 2.0 ** nlowermin <= inner * inner else -1
+    nexpbits = 0
+    required = outer * outer / 2.0 ** nlowermin
+    available = 2.0
+    while available < required:
+        nexpbits += 1
+        available = 2.0 ** (2.0 ** nexpbits)
+    nshiftbits = 24 - (nbits - nexpbits + 1)
+    nmask = (1 << (nbits + nshiftbits)) - 1
+    f2i = lambda f: int(np.float32(f).view(np.int32))
+    return f2i(inner * inner) & ~nmask, f2i(outer * outer) & ~nmask, nmask, nshiftbits
+
+
+def init_disp_tables(cut_lj, g_ewald_6, nbits=12, tabinner=np.sqrt(2.0)):
+    """Pair::init_tables_disp (dispersion lookup of buck/long/coul/long, pair_buck_long_coul_long_intel.cpp:433-454)
+    -> (tables dict {r,dr,f,df,e,de}, mask, shift, tabinnerdispsq)"""
+    i2f = lambda i: float(np.int32(i).view(np.float32))
+    f2i = lambda f: int(np.float32(f).view(np.int32))
+    masklo, maskhi, nmask, nshiftbits = _bitmap(float(tabinner), float(cut_lj), nbits)
+    g2 = g_ewald_6 * g_ewald_6
+    g6 = g2 ** 3
+    g8 = g6 * g2
+    ntable = 1 << nbits
+    tabinnersq = float(tabinner) ** 2
+
+    def ev(rsq):
+        x2 = g2 * rsq
+        a2 = 1.0 / x2
+        x2 = a2 * np.exp(-x2)
+        return g8 * (((6.0 * a2 + 6.0) * a2 + 3.0) * a2 + 1.0) * x2 * rsq, g6 * ((a2 + 1.0) * a2 + 0.5) * x2
+
+    t = {k: np.zeros(ntable) for k in ("r", "dr", "f", "df", "e", "de")}
+    minrsq = i2f(maskhi)
+    for i in range(ntable):
+        bits = (i << nshiftbits) | masklo
+        if i2f(bits) < tabinnersq:
+            bits = (i << nshiftbits) | maskhi
+        rsq = i2f(bits)
+        t["r"][i] = rsq
+        t["f"][i], t["e"][i] = ev(rsq)
+        minrsq = min(minrsq, rsq)
+    for a, b in (("dr", "r"), ("df", "f"), ("de", "e")):
+        nxt = np.roll(t[b], -1)
+        t[a] = (1.0 / (nxt - t[b])) if a == "dr" else (nxt - t[b])
+    itablemin = (f2i(minrsq) & nmask) >> nshiftbits
+    itablemax = itablemin - 1 if itablemin != 0 else ntable - 1
+    top = i2f((itablemax << nshiftbits) | maskhi)
+    if top < cut_lj * cut_lj:
+        rsq = float(np.float32(cut_lj * cut_lj))
+        fo, eo = ev(rsq)
+        t["dr"][itablemax] = 1.0 / (rsq - t["r"][itablemax])
+        t["df"][itablemax] = fo - t["f"][itablemax]
+        t["de"][itablemax] = eo - t["e"][itablemax]
+    for k in t:
+        t[k] = np.ascontiguousarray(t[k])
+    return t, nmask, nshiftbits, minrsq
 
 
 _ACONS = {

@@ -126,7 +126,7 @@ int b2_fieldforce(b200md_ctx *ctx, PppmState &ps, const PppmView &v) {
   const PppmConst &c = ps.c;
   const int n = v.n;
   const bool ad = ps.p.differentiation == 1;
-  const double qs = ctx->qqrd2e * ps.p.scale;
+  const double qs = ps.p.dispersion ? 1.0 : ctx->qqrd2e * ps.p.scale;   // dispersion: f += B[type] * E
   const double *B = ps.p.dispersion ? ps.Btype.p : nullptr;
   const double *sf = ps.sf_coeff;
   if (n <= 0) return 0;

@@ -135,7 +135,8 @@ struct b200md_ctx {
 
   PairState pair;
   NeighState neigh;
-  PppmState *pppm = nullptr;
+  PppmState *pppm = nullptr;    // Coulomb grid (pppm/intel; function[0] of pppm/disp/intel)
+  PppmState *pppm6 = nullptr;   // geometric-mixing dispersion grid (function[1] of pppm/disp/intel)
   CommState *comm = nullptr;
 
   // nve

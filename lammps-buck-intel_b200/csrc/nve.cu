@@ -131,7 +131,7 @@ static int forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo) {
   double ev[8] = {0};
   TRY(b2_pair_compute(ctx, eflag, vflag, (eflag || vflag) ? ev : nullptr));
   double ek = 0.0, vk[6] = {0};
-  if (ctx->pppm) TRY(b2_pppm_compute(ctx, eflag, vflag, &ek, vk));
+  if (ctx->pppm || ctx->pppm6) TRY(b2_pppm_compute(ctx, eflag, vflag, &ek, vk));
   if (thermo) {
     for (int k = 0; k < 8; k++) thermo[k] = ev[k];
     thermo[8] = ek;

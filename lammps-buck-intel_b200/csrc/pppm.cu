@@ -141,6 +141,40 @@ __global__ void k_gf_ad(PppmConst c, double *__restrict__ greensfn, double *__re
   for (int t = 0; t < 6; t++) sfpre[(size_t)t * nfft + n] = sum[t] * g;
 }
 
+// PPPMDisp::compute_gf_6 [UPSTREAM]: influence function of the r^-6 reciprocal sum (c.g_ewald = g_ewald_6).  Used by
+// the geometric-mixing grid of PPPMDispIntel::compute (pppm_disp_intel.cpp:245-313).
+__global__ void k_gf_6(PppmConst c, double *__restrict__ greensfn) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (n >= nfft) return;
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
+  const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
+  const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
+  const double inv2ew = 1.0 / (2.0 * c.g_ewald);
+  const double rtpi = sqrt(kPI);
+  const double numerator = -kPI * rtpi * c.g_ewald * c.g_ewald * c.g_ewald / 3.0;
+  const double qx = unitkx * kper, qy = unitky * lper, qz = unitkz * mper;
+  const double snx2 = d_square(sin(0.5 * qx * xprd / c.nx)), sny2 = d_square(sin(0.5 * qy * yprd / c.ny)),
+               snz2 = d_square(sin(0.5 * qz * zprd / c.nz));
+  const double sx = exp(-qx * qx * inv2ew * inv2ew), sy = exp(-qy * qy * inv2ew * inv2ew),
+               sz = exp(-qz * qz * inv2ew * inv2ew);
+  const double argx = 0.5 * qx * xprd / c.nx, argy = 0.5 * qy * yprd / c.ny, argz = 0.5 * qz * zprd / c.nz;
+  double wx = argx != 0.0 ? pow(sin(argx) / argx, (double)c.order) : 1.0;
+  double wy = argy != 0.0 ? pow(sin(argy) / argy, (double)c.order) : 1.0;
+  double wz = argz != 0.0 ? pow(sin(argz) / argz, (double)c.order) : 1.0;
+  wx *= wx; wy *= wy; wz *= wz;
+  const double sqk = qx * qx + qy * qy + qz * qz;
+  double g = 0.0;
+  if (sqk != 0.0) {
+    const double rtsqk = sqrt(sqk);
+    const double term = (1.0 - 2.0 * sqk * inv2ew * inv2ew) * sx * sy * sz +
+                        2.0 * sqk * rtsqk * inv2ew * inv2ew * inv2ew * rtpi * erfc(rtsqk * inv2ew);
+    g = numerator * term * wx * wy * wz / d_gf_denom(c, snx2, sny2, snz2);
+  }
+  greensfn[n] = g;
+}
+
 // fixed-order sum of `ncol` interleaved-by-column arrays: in[col*n + i] -> out[col]
 __global__ void __launch_bounds__(256) k_colsum_partial(long n, int ncol, const double *__restrict__ in, double *__restrict__ partial) {
   __shared__ double s[256];
@@ -488,7 +522,7 @@ __global__ void __launch_bounds__(256)
 k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
                 const double *__restrict__ fky, const double *__restrict__ fkz, double scaleinv, double g_ewald,
-                double *__restrict__ ev_partial) {
+                double *__restrict__ ev_partial, int disp) {
   extern __shared__ double2 smem[];
   double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *bufV = smem + 2 * (size_t)TB * LP;
   __shared__ double s_red[8][8];
@@ -519,7 +553,13 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__r
       const double sqk = kx * kx + ky * ky + kz * kz;
       acc[0] += eng;
       if (sqk != 0.0) {  // PPPM::setup vg[][] evaluated on the fly instead of stored (6 doubles / point)
-        const double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+        double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+        if (disp) {   // vg_6 of PPPMDisp::setup
+          const double b = 0.5 * sqrt(sqk) / g_ewald, bs = b * b, bt = bs * b;
+          const double erft = 2.0 * bt * sqrt(kPI) * erfc(b), expt = exp(-bs);
+          const double nom = erft - 2.0 * bs * expt, denom = nom + expt;
+          vterm = denom == 0.0 ? 3.0 / sqk : 3.0 * nom / (sqk * denom);
+        }
         acc[1] += eng * (1.0 + vterm * kx * kx);
         acc[2] += eng * (1.0 + vterm * ky * ky);
         acc[3] += eng * (1.0 + vterm * kz * kz);
@@ -781,7 +821,7 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<nblk_z, 256, smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, TB, LP, ps.work1.p, ps.work2.p,          \
                                              ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, scaleinv, c.g_ewald, \
-                                             ps.partial.p);                                                   \
+                                             ps.partial.p, ps.p.dispersion);                                  \
   } while (0)
     if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
     else { if (ev) ZK(3, 1); else ZK(3, 0); }
@@ -808,12 +848,21 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   TRY(b2_fieldforce<flt_t>(ctx, ps, v));
 
   // ---- energy / virial post-factors (pppm_intel.cpp:256-275) -----------------------------------------
+  if (ps.p.dispersion) {
+    // pppm_disp_intel.cpp:486-510, geometric mixing: csum = sum B_i^2 (= qsqsum here), csumij = (sum B_i)^2
+    const double g3 = c.g_ewald * c.g_ewald * c.g_ewald;
+    const double csum = ps.qsqsum, csumij = ps.qsum * ps.qsum;
+    const double a = kPI * kPIS / (6.0 * ps.volume) * g3 * csumij;
+    if (eflag_global && energy) *energy = 0.5 * ps.volume * evsum[0] - a + g3 * g3 * csum / 12.0;
+    if (vflag_global && virial)
+      for (int k = 0; k < 6; k++) virial[k] = 0.5 * ps.volume * evsum[1 + k] - (k < 3 ? a : 0.0);
+    return 0;
+  }
   const double qscale = ctx->qqrd2e * ps.p.scale;
   if (eflag_global && energy) {
     double e = evsum[0];
     e *= 0.5 * ps.volume;
-    if (!ps.p.dispersion)
-      e -= c.g_ewald * ps.qsqsum / kPIS + kPI2 * ps.qsum * ps.qsum / (c.g_ewald * c.g_ewald * ps.volume);
+    e -= c.g_ewald * ps.qsqsum / kPIS + kPI2 * ps.qsum * ps.qsum / (c.g_ewald * c.g_ewald * ps.volume);
     e *= qscale;
     *energy = e;
   }
@@ -824,8 +873,8 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
 
 }  // namespace
 
-void b2_pppm_free(b200md_ctx *ctx) {
-  PppmState *ps = ctx->pppm;
+static void free_state(PppmState *&slot) {
+  PppmState *ps = slot;
   if (!ps) return;
   for (int d = 0; d < 3; d++) ps->tw[d].free_();
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
@@ -833,19 +882,41 @@ void b2_pppm_free(b200md_ctx *ctx) {
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
   ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
   delete ps;
-  ctx->pppm = nullptr;
+  slot = nullptr;
+}
+
+void b2_pppm_free(b200md_ctx *ctx) {
+  free_state(ctx->pppm);
+  free_state(ctx->pppm6);
+}
+
+template <class flt_t>
+static int compute_all(b200md_ctx *ctx, const PppmView &v, int eflag, int vflag, double *energy, double *virial) {
+  // PPPMDispIntel::compute: function[0] (Coulomb grid) then function[1] (geometric dispersion grid); energy and
+  // virial are the sums (pppm_disp_intel.cpp:183-313, 540-541)
+  if (energy) *energy = 0.0;
+  if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
+  PppmState *slots[2] = {ctx->pppm, ctx->pppm6};
+  for (PppmState *ps : slots) {
+    if (!ps) continue;
+    double e = 0.0, vv[6] = {0, 0, 0, 0, 0, 0};
+    TRY(pppm_compute_view<flt_t>(ctx, *ps, v, eflag, vflag, &e, vv));
+    if (energy) *energy += e;
+    if (virial) for (int k = 0; k < 6; k++) virial[k] += vv[k];
+  }
+  return 0;
 }
 
 int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial) {
-  if (!ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
+  if (!ctx->pppm && !ctx->pppm6) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
   PppmView v;
   v.n = ctx->nlocal;
   v.xq = ctx->xq.p;
   v.xqf = ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr;
   v.type = ctx->type.p;
   v.f = ctx->f.p;
-  if (ctx->prec == B200MD_PREC_MIXED) return pppm_compute_view<float>(ctx, *ctx->pppm, v, eflag, vflag, energy, virial);
-  return pppm_compute_view<double>(ctx, *ctx->pppm, v, eflag, vflag, energy, virial);
+  if (ctx->prec == B200MD_PREC_MIXED) return compute_all<float>(ctx, v, eflag, vflag, energy, virial);
+  return compute_all<double>(ctx, v, eflag, vflag, energy, virial);
 }
 
 extern "C" {
@@ -864,9 +935,12 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   if (p->dispersion && !p->B) return b2_fail(ctx, B200MD_EINVAL, "dispersion PPPM needs B[type]");
   for (int d = 0; d < 3; d++)
     if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "PPPM needs a fully periodic box (no slab correction)");
-  b2_pppm_free(ctx);
+  if (p->dispersion && p->differentiation == 1)
+    return b2_fail(ctx, B200MD_EINVAL, "kspace_modify diff ad is not provided for the dispersion grid");
+  PppmState *&slot = p->dispersion ? ctx->pppm6 : ctx->pppm;
+  free_state(slot);
   PppmState *ps = new PppmState();
-  ctx->pppm = ps;
+  slot = ps;
   ps->p = *p;
   ps->p.B = nullptr;
   if (ps->p.scale == 0.0) ps->p.scale = 1.0;
@@ -921,9 +995,10 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     RESERVE(ctx, ps->Btype, (size_t)ctx->ntypes + 1);
     CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, p->B, ((size_t)ctx->ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
   }
-  if (p->dispersion)
-    return b2_fail(ctx, B200MD_EINVAL, "dispersion Green's function is provided by b200md_pppm_disp (not built yet)");
-  if (!ad) {
+  if (p->dispersion) {
+    k_gf_6<<<cdiv(nfft, 128), 128, 0, ctx->stream>>>(c, ps->greensfn.p);
+    KERNEL_OK(ctx, "k_gf_6");
+  } else if (!ad) {
     const double fac = std::pow(-std::log(1.0e-7), 0.25);  // EPS_HOC, pppm_intel.cpp:39
     const int nbx = static_cast<int>((c.g_ewald * c.prd[0] / (kPI * c.nx)) * fac);
     const int nby = static_cast<int>((c.g_ewald * c.prd[1] / (kPI * c.ny)) * fac);

@@ -1,0 +1,636 @@
+// lmp_b200.cpp — minimal input-script driver for the commands of examples/in.buck, in.buck_big, in.buck_coul_cut and
+// in.buck_coul_long, so that the shipped scripts run unchanged on the B200 styles:
+//
+//     lmp_b200 -in in.buck_coul_long -sf intel -pk intel 0 mode double [-var x 2] [-kspace pppm]
+//
+// It plays the role of the upstream LAMMPS executable around the reference's plug-in classes: Input (command parsing),
+// Lattice/CreateAtoms/ReadData/Replicate, Velocity (RanPark stream), Verlet::setup/run in the stock order
+// (initial_integrate -> neighbor decide -> pair -> kspace -> final_integrate) and Thermo one-style output.
+// All forces, neighbour lists and integration run through the classes of this directory, i.e. through the C ABI.
+//   -dry-run     parse + host-side init only (no device): prints a JSON summary of what would run
+//   -host-step   plug-in deployment: positions/forces cross PCIe every step (FixIntel::resident = 0)
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+
+#include "fix_nve_intel.h"
+#include "pair_buck_coul_intel.h"
+#include "pppm_disp_intel.h"
+#include "pppm_intel.h"
+
+using namespace LAMMPS_NS;
+
+namespace {
+
+// ---- RanPark (Park-Miller minimal standard), as used by `velocity ... create` --------------------------------
+class RanPark {
+ public:
+  explicit RanPark(int s) : seed(s) {}
+  double uniform() {
+    const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836;
+    const int k = seed / IQ;
+    seed = IA * (seed - k * IQ) - IR * k;
+    if (seed < 0) seed += IM;
+    return (1.0 / IM) * seed;
+  }
+  // `loop geom`: seed hashed from the atom's coordinates
+  void reset(int ibase, const double *coord) {
+    unsigned int hash = 0;
+    const char *str = (const char *)&ibase;
+    for (size_t i = 0; i < sizeof(int); i++) { hash += str[i]; hash += (hash << 10); hash ^= (hash >> 6); }
+    str = (const char *)coord;
+    for (size_t i = 0; i < 3 * sizeof(double); i++) { hash += str[i]; hash += (hash << 10); hash ^= (hash >> 6); }
+    hash += (hash << 3);
+    hash ^= (hash >> 11);
+    hash += (hash << 15);
+    seed = hash & 0x7ffffff;
+    if (!seed) seed = 1;
+    for (int i = 0; i < 5; i++) uniform();
+  }
+
+ private:
+  int seed;
+};
+
+struct Script {
+  LAMMPS lmp;
+  std::map<std::string, std::string> vars;
+  std::unique_ptr<Pair> pair;
+  std::unique_ptr<KSpace> kspace;
+  std::unique_ptr<FixNVEIntel> nve;
+  std::string pair_style_name, kspace_style_name, kspace_override;
+  std::vector<std::string> kspace_args;
+  int thermo_every = 0;
+  bool suffix_intel = false, dry_run = false, host_step = false, echo = false;
+  int device = 0, prec_mode = FixIntel::PREC_MODE_DOUBLE;
+  double nktv2p = 1.0;
+  std::string dir;   // directory of the input script (read_data paths are relative to it)
+  // lattice
+  double lattice_a = 1.0;
+  std::vector<std::array<double, 3>> basis;
+  double reg_lo[3] = {0, 0, 0}, reg_hi[3] = {0, 0, 0};
+  bool dt_set = false;
+  double last_thermo[6] = {0, 0, 0, 0, 0, 0};
+  long nbuilds_reported = 0;
+
+  [[noreturn]] void fail(const std::string &m) { lmp.error->all(FLERR, m); }
+
+  // ---- variables: `variable x index 1`, `variable xx equal 20*$x`; $x and ${xx} substitution -------------------
+  double eval_expr(const std::string &e) {   // products / quotients / sums of numbers (enough for the scripts)
+    double acc = 0.0, term = 1.0;
+    char op = '*', sign = '+';
+    size_t i = 0;
+    bool have = false;
+    auto flush_term = [&]() { acc += sign == '+' ? term : -term; term = 1.0; op = '*'; have = false; };
+    while (i < e.size()) {
+      if (std::isspace((unsigned char)e[i])) { i++; continue; }
+      if ((e[i] == '+' || e[i] == '-') && have) { flush_term(); sign = e[i]; i++; continue; }
+      if (e[i] == '*' || e[i] == '/') { op = e[i]; i++; continue; }
+      char *end;
+      const double v = std::strtod(e.c_str() + i, &end);
+      if (end == e.c_str() + i) fail("Invalid syntax in variable formula: " + e);
+      term = op == '*' ? term * v : term / v;
+      have = true;
+      i = end - e.c_str();
+    }
+    if (have) flush_term();
+    return acc;
+  }
+  std::string substitute(const std::string &line) {
+    std::string out;
+    for (size_t i = 0; i < line.size(); i++) {
+      if (line[i] != '$') { out += line[i]; continue; }
+      std::string name;
+      if (i + 1 < line.size() && line[i + 1] == '{') {
+        const size_t c = line.find('}', i);
+        if (c == std::string::npos) fail("Invalid variable name");
+        name = line.substr(i + 2, c - i - 2);
+        i = c;
+      } else if (i + 1 < line.size()) { name = line.substr(i + 1, 1); i++; }
+      auto it = vars.find(name);
+      if (it == vars.end()) fail("Substitution for illegal variable " + name);
+      out += it->second;
+    }
+    return out;
+  }
+
+  void set_units(const std::string &u) {
+    Force *f = lmp.force;
+    lmp.update->unit_style = u;
+    if (u == "lj") {
+      f->boltz = 1.0; f->mvv2e = 1.0; f->ftm2v = 1.0; f->qqrd2e = f->qqr2e = 1.0; nktv2p = 1.0;
+      f->qelectron = 1.0; f->angstrom = 1.0;
+      if (!dt_set) lmp.update->dt = 0.005;
+      lmp.neighbor->skin = 0.3;
+    } else if (u == "metal") {
+      f->boltz = 8.617343e-5; f->mvv2e = 1.0364269e-4; f->ftm2v = 1.0 / 1.0364269e-4;
+      f->qqrd2e = f->qqr2e = 14.399645; nktv2p = 1.6021765e6;
+      f->qelectron = 1.0; f->angstrom = 1.0;
+      if (!dt_set) lmp.update->dt = 0.001;
+      lmp.neighbor->skin = 2.0;
+    } else if (u == "real") {
+      f->boltz = 0.0019872067; f->mvv2e = 48.88821291 * 48.88821291; f->ftm2v = 1.0 / 48.88821291 / 48.88821291;
+      f->qqrd2e = f->qqr2e = 332.06371; nktv2p = 68568.415;
+      f->qelectron = 1.0; f->angstrom = 1.0;
+      if (!dt_set) lmp.update->dt = 1.0;
+      lmp.neighbor->skin = 2.0;
+    } else fail("Illegal units command");
+  }
+
+  void create_atoms(int type) {
+    Atom *a = lmp.atom;
+    Domain *d = lmp.domain;
+    // lattice cells overlapping the box; k (z) outer, j, i inner, basis inner-most (CreateAtoms::add_lattice)
+    int lo[3], hi[3];
+    for (int q = 0; q < 3; q++) {
+      lo[q] = (int)std::floor(d->boxlo[q] / lattice_a) - 1;
+      hi[q] = (int)std::ceil(d->boxhi[q] / lattice_a) + 1;
+    }
+    for (int k = lo[2]; k <= hi[2]; k++)
+      for (int j = lo[1]; j <= hi[1]; j++)
+        for (int i = lo[0]; i <= hi[0]; i++)
+          for (const auto &b : basis) {
+            const double x[3] = {(i + b[0]) * lattice_a, (j + b[1]) * lattice_a, (k + b[2]) * lattice_a};
+            bool in = true;
+            for (int q = 0; q < 3; q++)
+              if (x[q] < d->boxlo[q] || x[q] >= d->boxhi[q]) in = false;
+            if (!in) continue;
+            a->x.insert(a->x.end(), x, x + 3);
+            a->type.push_back(type);
+          }
+    a->nlocal = (int)a->type.size();
+    a->natoms = a->nlocal;
+    a->v.assign((size_t)3 * a->nlocal, 0.0);
+    a->f.assign((size_t)3 * a->nlocal, 0.0);
+    if (a->q_flag) a->q.assign(a->nlocal, 0.0);
+  }
+
+  void read_data(const std::string &file) {
+    std::string path = file;
+    std::ifstream in(path);
+    if (!in && !dir.empty()) { path = dir + "/" + file; in.open(path); }
+    if (!in) fail("Cannot open file " + file);
+    Atom *a = lmp.atom;
+    std::string line;
+    std::getline(in, line);   // title
+    long natoms = 0;
+    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+    std::string section;
+    std::vector<std::pair<long, std::array<double, 5>>> rows;
+    while (std::getline(in, line)) {
+      const size_t hash = line.find('#');
+      if (hash != std::string::npos) line = line.substr(0, hash);
+      std::istringstream ss(line);
+      std::vector<std::string> w;
+      std::string t;
+      while (ss >> t) w.push_back(t);
+      if (w.empty()) continue;
+      if (w.size() >= 2 && w[1] == "atoms") { natoms = std::atol(w[0].c_str()); continue; }
+      if (w.size() >= 3 && w[1] == "atom" && w[2] == "types") {
+        a->ntypes = std::atoi(w[0].c_str());
+        a->mass.assign(a->ntypes + 1, 0.0);
+        a->mass_setflag.assign(a->ntypes + 1, 0);
+        continue;
+      }
+      if (w.size() >= 4 && w[2] == "xlo") { lo[0] = std::atof(w[0].c_str()); hi[0] = std::atof(w[1].c_str()); continue; }
+      if (w.size() >= 4 && w[2] == "ylo") { lo[1] = std::atof(w[0].c_str()); hi[1] = std::atof(w[1].c_str()); continue; }
+      if (w.size() >= 4 && w[2] == "zlo") { lo[2] = std::atof(w[0].c_str()); hi[2] = std::atof(w[1].c_str()); continue; }
+      if (w[0] == "Masses" || w[0] == "Atoms" || w[0] == "Velocities") { section = w[0]; continue; }
+      if (section == "Masses" && w.size() >= 2) {
+        const int t2 = std::atoi(w[0].c_str());
+        if (t2 < 1 || t2 > a->ntypes) fail("Invalid type for mass set");
+        a->mass[t2] = std::atof(w[1].c_str());
+        a->mass_setflag[t2] = 1;
+      } else if (section == "Atoms") {
+        // atom_style charge: id type q x y z ; atomic: id type x y z
+        const size_t need = a->q_flag ? 6 : 5;
+        if (w.size() < need) fail("Incorrect atom format in data file");
+        std::array<double, 5> r;
+        r[0] = std::atof(w[1].c_str());
+        size_t c = 2;
+        r[1] = a->q_flag ? std::atof(w[c++].c_str()) : 0.0;
+        r[2] = std::atof(w[c].c_str()); r[3] = std::atof(w[c + 1].c_str()); r[4] = std::atof(w[c + 2].c_str());
+        rows.push_back({std::atol(w[0].c_str()), r});
+      }
+    }
+    if ((long)rows.size() != natoms) fail("Did not assign all atoms correctly");
+    std::sort(rows.begin(), rows.end(), [](const auto &p, const auto &q) { return p.first < q.first; });
+    lmp.domain->set_box(lo, hi);
+    for (const auto &r : rows) {
+      double x[3] = {r.second[2], r.second[3], r.second[4]};
+      for (int d = 0; d < 3; d++) {   // Domain::remap into the periodic box
+        const double prd = hi[d] - lo[d];
+        while (x[d] < lo[d]) x[d] += prd;
+        while (x[d] >= hi[d]) x[d] -= prd;
+        x[d] = std::max(x[d], lo[d]);
+      }
+      a->x.insert(a->x.end(), x, x + 3);
+      a->type.push_back((int)r.second[0]);
+      if (a->q_flag) a->q.push_back(r.second[1]);
+    }
+    a->nlocal = (int)a->type.size();
+    a->natoms = a->nlocal;
+    a->v.assign((size_t)3 * a->nlocal, 0.0);
+    a->f.assign((size_t)3 * a->nlocal, 0.0);
+  }
+
+  void replicate(int nx, int ny, int nz) {
+    Atom *a = lmp.atom;
+    Domain *d = lmp.domain;
+    const int n = a->nlocal;
+    std::vector<double> x, q;
+    std::vector<int> type;
+    // new tags run z outer, y, x inner, old atoms inner-most (atom_offset = (iz*ny*nx + iy*nx + ix)*maxtag)
+    for (int iz = 0; iz < nz; iz++)
+      for (int iy = 0; iy < ny; iy++)
+        for (int ix = 0; ix < nx; ix++)
+          for (int i = 0; i < n; i++) {
+            x.push_back(a->x[3 * i] + ix * d->prd[0]);
+            x.push_back(a->x[3 * i + 1] + iy * d->prd[1]);
+            x.push_back(a->x[3 * i + 2] + iz * d->prd[2]);
+            type.push_back(a->type[i]);
+            if (a->q_flag) q.push_back(a->q[i]);
+          }
+    double hi[3] = {d->boxlo[0] + nx * d->prd[0], d->boxlo[1] + ny * d->prd[1], d->boxlo[2] + nz * d->prd[2]};
+    double lo[3] = {d->boxlo[0], d->boxlo[1], d->boxlo[2]};
+    d->set_box(lo, hi);
+    a->x.swap(x); a->q.swap(q); a->type.swap(type);
+    a->nlocal = (int)a->type.size();
+    a->natoms = a->nlocal;
+    a->v.assign((size_t)3 * a->nlocal, 0.0);
+    a->f.assign((size_t)3 * a->nlocal, 0.0);
+  }
+
+  double kinetic_energy() const {   // sum 1/2 m v^2 in energy units
+    const Atom *a = lmp.atom;
+    double ke = 0.0;
+    for (int i = 0; i < a->nlocal; i++) {
+      const double *v = &a->v[3 * (size_t)i];
+      ke += a->mass[a->type[i]] * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    }
+    return 0.5 * lmp.force->mvv2e * ke;
+  }
+  double dof() const { return 3.0 * lmp.atom->natoms - 3.0; }   // compute temp: fix_dof = dimension for a periodic box
+  double temperature() const { return 2.0 * kinetic_energy() / (dof() * lmp.force->boltz); }
+
+  // velocity all create T seed [loop all|local|geom] [dist uniform] [mom yes] [rot no]
+  void velocity_create(double t_desired, int seed, const std::string &loop) {
+    Atom *a = lmp.atom;
+    if (seed <= 0) fail("Illegal velocity create command");
+    for (int t = 1; t <= a->ntypes; t++)
+      if (!a->mass_setflag[t]) fail("Cannot use velocity create loop all unless atoms have IDs / masses are set");
+    RanPark random(seed);
+    for (int i = 0; i < a->nlocal; i++) {
+      if (loop == "geom" || loop == "local") random.reset(seed, &a->x[3 * (size_t)i]);
+      const double vx = random.uniform(), vy = random.uniform(), vz = random.uniform();
+      const double factor = 1.0 / std::sqrt(a->mass[a->type[i]]);
+      a->v[3 * (size_t)i] = vx * factor;
+      a->v[3 * (size_t)i + 1] = vy * factor;
+      a->v[3 * (size_t)i + 2] = vz * factor;
+    }
+    // zero linear momentum, then scale to the requested temperature
+    double p[3] = {0, 0, 0}, mtot = 0.0;
+    for (int i = 0; i < a->nlocal; i++) {
+      const double m = a->mass[a->type[i]];
+      for (int d = 0; d < 3; d++) p[d] += m * a->v[3 * (size_t)i + d];
+      mtot += m;
+    }
+    for (int i = 0; i < a->nlocal; i++)
+      for (int d = 0; d < 3; d++) a->v[3 * (size_t)i + d] -= p[d] / mtot;
+    const double t = temperature();
+    if (t == 0.0) fail("Attempting to rescale a 0.0 temperature");
+    const double fac = std::sqrt(t_desired / t);
+    for (double &v : a->v) v *= fac;
+  }
+
+  template <class Plain, class Intel>
+  Pair *make_pair() {
+    // `-sf intel` appends the suffix when the style exists; only the /intel classes compute on the device
+    if (!suffix_intel) fail("Pair style " + pair_style_name + " without -sf intel: only the /intel styles are provided");
+    return new Intel(&lmp);
+  }
+
+  void pair_style(const std::vector<std::string> &w) {
+    std::string s = w[1];
+    if (s.size() > 6 && s.substr(s.size() - 6) == "/intel") { s = s.substr(0, s.size() - 6); suffix_intel = true; }
+    pair_style_name = s;
+    if (s == "buck") pair.reset(make_pair<PairBuck, PairBuckIntel>());
+    else if (s == "buck/coul/cut") pair.reset(make_pair<PairBuckCoulCut, PairBuckCoulCutIntel>());
+    else if (s == "buck/coul/long") pair.reset(make_pair<PairBuckCoulLong, PairBuckCoulLongIntel>());
+    else if (s == "buck/long/coul/long") pair.reset(make_pair<PairBuckLongCoulLong, PairBuckLongCoulLongIntel>());
+    else fail("Unknown pair style " + s);
+    lmp.force->pair = pair.get();
+    std::vector<char *> args;
+    for (size_t i = 2; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
+    pair->settings((int)args.size(), args.data());
+  }
+
+  void kspace_style(const std::vector<std::string> &w) {
+    std::string s = kspace_override.empty() ? w[1] : kspace_override;
+    if (s.size() > 6 && s.substr(s.size() - 6) == "/intel") s = s.substr(0, s.size() - 6);
+    std::vector<char *> args;
+    for (size_t i = 2; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
+    if (s == "ewald") {
+      // in.buck_coul_long asks for `ewald 1e-6`; the reference has no ewald/intel, so `-sf intel` leaves stock Ewald in
+      // place.  This build has no CPU path: the mesh solver is used at the same accuracy, and says so.
+      std::fprintf(stderr, "WARNING: kspace_style ewald is not provided on the device; using pppm at the same accuracy\n");
+      s = "pppm";
+    }
+    kspace_style_name = s;
+    if (s == "pppm") kspace.reset(new PPPMIntel(&lmp, (int)args.size(), args.data()));
+    else if (s == "pppm/disp") kspace.reset(new PPPMDispIntel(&lmp, (int)args.size(), args.data()));
+    else fail("Unknown kspace style " + s);
+    lmp.force->kspace = kspace.get();
+  }
+
+  // ---- Verlet ---------------------------------------------------------------------------------------------------
+  void init_styles() {
+    Atom *a = lmp.atom;
+    if (!pair) fail("No pair style defined");   // all scripts of the reference define one
+    for (int t = 1; t <= a->ntypes; t++)
+      if (!a->mass_setflag[t]) fail("All masses are not set");
+    if (!lmp.fix_intel && !dry_run) lmp.fix_intel = new FixIntel(&lmp, device, prec_mode);
+    if (lmp.fix_intel) lmp.fix_intel->resident = host_step ? 0 : 1;
+  }
+
+  void print_thermo(long step, const double th[16], double ke) {
+    const double T = 2.0 * ke / (dof() * lmp.force->boltz);
+    const double epair = th[0] + th[1] + th[8];
+    const double vol = lmp.domain->prd[0] * lmp.domain->prd[1] * lmp.domain->prd[2];
+    const double vsum = th[2] + th[3] + th[4] + th[9] + th[10] + th[11];
+    const double press = (dof() * lmp.force->boltz * T + vsum) / 3.0 / vol * nktv2p;
+    std::printf("%8ld %14.8g %18.12g %14.8g %18.12g %14.8g\n", step, T, epair, 0.0, epair + ke, press);
+    last_thermo[0] = T; last_thermo[1] = epair; last_thermo[2] = epair + ke; last_thermo[3] = press;
+    last_thermo[4] = th[0] + th[1]; last_thermo[5] = th[8];
+    std::fflush(stdout);
+  }
+
+  void forces(int eflag, int vflag, double th[16]) {
+    for (int k = 0; k < 16; k++) th[k] = 0.0;
+    pair->compute(eflag, vflag);
+    th[0] = pair->eng_vdwl; th[1] = pair->eng_coul;
+    for (int k = 0; k < 6; k++) th[2 + k] = pair->virial[k];
+    if (kspace) {
+      kspace->compute(eflag, vflag);
+      th[8] = kspace->energy;
+      for (int k = 0; k < 6; k++) th[9 + k] = kspace->virial[k];
+    }
+  }
+
+  double device_ke() {   // kinetic energy from the device-resident velocities
+    lmp.fix_intel->sync_host(false, true, false);
+    return kinetic_energy();
+  }
+
+  void dry_summary() {
+    Atom *a = lmp.atom;
+    std::printf("{\"dry_run\": true, \"natoms\": %ld, \"ntypes\": %d, \"units\": \"%s\", \"box\": [%.10g, %.10g, %.10g], "
+                "\"pair_style\": \"%s\", \"cutforce\": %.10g, \"skin\": %g, \"every\": %d, \"delay\": %d, \"check\": %d, "
+                "\"dt\": %g, \"temperature\": %.10g",
+                a->natoms, a->ntypes, lmp.update->unit_style.c_str(), lmp.domain->prd[0], lmp.domain->prd[1],
+                lmp.domain->prd[2], pair_style_name.c_str(), pair->cutforce, lmp.neighbor->skin, lmp.neighbor->every,
+                lmp.neighbor->delay, lmp.neighbor->dist_check, lmp.update->dt, temperature());
+    if (kspace)
+      std::printf(", \"kspace_style\": \"%s\", \"g_ewald\": %.10g, \"grid\": [%d, %d, %d], \"order\": %d, "
+                  "\"g_ewald_6\": %.10g, \"grid_6\": [%d, %d, %d]",
+                  kspace_style_name.c_str(), kspace->g_ewald, kspace->nx_pppm, kspace->ny_pppm, kspace->nz_pppm,
+                  kspace->order, kspace->g_ewald_6, kspace->nx_pppm_6, kspace->ny_pppm_6, kspace->nz_pppm_6);
+    std::printf("}\n");
+  }
+
+  void run(long nsteps) {
+    init_styles();
+    if (dry_run) {
+      // host-side initialisation only: KSpace sizing first (the pair style reads g_ewald), then init_one
+      lmp.dry_run = true;
+      if (kspace) kspace->init();
+      pair->init();
+      dry_summary();
+      return;
+    }
+    FixIntel *fx = lmp.fix_intel;
+    fx->upload_atoms();
+    fx->setup_neighbor();
+    // LAMMPS::init order: force->init() runs kspace->init() before pair->init() (pair reads g_ewald)
+    if (kspace) kspace->init();
+    pair->init();
+    if (kspace) kspace->setup();
+    if (!nve) fail("No fix nve defined: nothing to integrate");
+    nve->init();
+    nve->setup(1);
+    // Verlet::setup
+    double th[16];
+    fx->ensure_neighbor(true);
+    {   // the setup build is not counted in "Neighbor list builds" (stock LAMMPS resets the counter at the run start)
+      long tot0 = 0, nb0 = 0;
+      int ng0 = 0, mx0 = 0;
+      b200md_neigh_stats(fx->ctx(), &tot0, &ng0, &mx0, &nb0);
+      nbuilds_reported = nb0;
+    }
+    forces(1, 1, th);
+    std::printf("Setting up Verlet run ...\n  Unit style    : %s\n  Current step  : %ld\n  Time step     : %g\n",
+                lmp.update->unit_style.c_str(), lmp.update->ntimestep, lmp.update->dt);
+    std::printf("%8s %14s %18s %14s %18s %14s\n", "Step", "Temp", "E_pair", "E_mol", "TotEng", "Press");
+    print_thermo(lmp.update->ntimestep, th, device_ke());
+    const long first = lmp.update->ntimestep;
+    for (long s = 1; s <= nsteps; s++) {
+      lmp.update->ntimestep++;
+      const bool out = (thermo_every && (lmp.update->ntimestep - first) % thermo_every == 0) || s == nsteps;
+      nve->initial_integrate(0);
+      if (fx->resident) fx->ensure_neighbor(false);
+      else fx->sync_host(true, false, false);   // host owns x in the plug-in deployment
+      forces(out ? 1 : 0, out ? 1 : 0, th);
+      nve->final_integrate();
+      if (out) print_thermo(lmp.update->ntimestep, th, device_ke());
+    }
+    long tot = 0, nb = 0;
+    int ng = 0, mx = 0;
+    b200md_neigh_stats(fx->ctx(), &tot, &ng, &mx, &nb);
+    std::printf("Loop of %ld steps with %ld atoms\nNeighbor list builds = %ld\nTotal # of neighbors = %ld\n"
+                "Ave neighs/atom = %.6g\n", nsteps, lmp.atom->natoms, nb - nbuilds_reported, tot,
+                lmp.atom->natoms ? (double)tot / lmp.atom->natoms : 0.0);
+    nbuilds_reported = nb;
+    fx->sync_host(true, true, true);
+  }
+
+  void command(const std::string &raw) {
+    std::string line = raw;
+    const size_t hash = line.find('#');
+    if (hash != std::string::npos) line = line.substr(0, hash);
+    line = substitute(line);
+    std::istringstream ss(line);
+    std::vector<std::string> w;
+    std::string t;
+    while (ss >> t) w.push_back(t);
+    if (w.empty()) return;
+    if (echo) std::printf("%s\n", line.c_str());
+    const std::string &c = w[0];
+    auto need = [&](size_t n) { if (w.size() < n) fail("Illegal " + c + " command"); };
+    Atom *a = lmp.atom;
+    if (c == "variable") {
+      need(4);
+      if (w[2] == "index") { if (!vars.count(w[1])) vars[w[1]] = w[3]; }   // -var on the command line wins
+      else if (w[2] == "equal") {
+        std::string e;
+        for (size_t i = 3; i < w.size(); i++) e += w[i];
+        char buf[64];
+        std::snprintf(buf, sizeof(buf), "%.15g", eval_expr(e));
+        vars[w[1]] = buf;
+      } else fail("Illegal variable command");
+    } else if (c == "units") { need(2); set_units(w[1]); }
+    else if (c == "atom_style") {
+      need(2);
+      if (w[1] == "atomic") a->q_flag = 0;
+      else if (w[1] == "charge") a->q_flag = 1;
+      else fail("Unknown atom style " + w[1]);
+    } else if (c == "lattice") {
+      need(3);
+      if (w[1] != "fcc") fail("Illegal lattice command (only fcc is provided)");
+      const double scale = std::atof(w[2].c_str());
+      // lj units: the value is a reduced density; other units: a lattice constant
+      lattice_a = lmp.update->unit_style == "lj" ? std::pow(4.0 / scale, 1.0 / 3.0) : scale;
+      basis = {{{0, 0, 0}}, {{0.5, 0.5, 0}}, {{0.5, 0, 0.5}}, {{0, 0.5, 0.5}}};
+      std::printf("Lattice spacing in x,y,z = %.6g %.6g %.6g\n", lattice_a, lattice_a, lattice_a);
+    } else if (c == "region") {
+      need(9);
+      if (w[2] != "block") fail("Illegal region command (only block is provided)");
+      for (int d = 0; d < 3; d++) {
+        reg_lo[d] = std::atof(w[3 + 2 * d].c_str()) * lattice_a;
+        reg_hi[d] = std::atof(w[4 + 2 * d].c_str()) * lattice_a;
+      }
+    } else if (c == "create_box") {
+      need(3);
+      a->ntypes = std::atoi(w[1].c_str());
+      a->mass.assign(a->ntypes + 1, 0.0);
+      a->mass_setflag.assign(a->ntypes + 1, 0);
+      lmp.domain->set_box(reg_lo, reg_hi);
+      std::printf("Created orthogonal box = (%g %g %g) to (%.6g %.6g %.6g)\n", reg_lo[0], reg_lo[1], reg_lo[2], reg_hi[0],
+                  reg_hi[1], reg_hi[2]);
+    } else if (c == "create_atoms") {
+      need(3);
+      create_atoms(std::atoi(w[1].c_str()));
+      std::printf("Created %d atoms\n", a->nlocal);
+    } else if (c == "read_data") {
+      need(2);
+      read_data(w[1]);
+      std::printf("  %d atoms\n", a->nlocal);
+    } else if (c == "replicate") {
+      need(4);
+      replicate(std::atoi(w[1].c_str()), std::atoi(w[2].c_str()), std::atoi(w[3].c_str()));
+      std::printf("  %d atoms\n", a->nlocal);
+    } else if (c == "mass") {
+      need(3);
+      int lo, hi;
+      if (w[1] == "*") { lo = 1; hi = a->ntypes; } else lo = hi = std::atoi(w[1].c_str());
+      if (lo < 1 || hi > a->ntypes) fail("Invalid type for mass set");
+      for (int t2 = lo; t2 <= hi; t2++) { a->mass[t2] = std::atof(w[2].c_str()); a->mass_setflag[t2] = 1; }
+    } else if (c == "velocity") {
+      need(5);
+      if (w[1] != "all" || w[2] != "create") fail("Illegal velocity command (only `all create` is provided)");
+      std::string loop = "all";
+      for (size_t i = 5; i + 1 < w.size(); i += 2)
+        if (w[i] == "loop") loop = w[i + 1];
+      velocity_create(std::atof(w[3].c_str()), std::atoi(w[4].c_str()), loop);
+    } else if (c == "pair_style") { need(2); pair_style(w); }
+    else if (c == "pair_coeff") {
+      if (!pair) fail("Pair_coeff command before pair_style is defined");
+      std::vector<char *> args;
+      for (size_t i = 1; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
+      pair->coeff((int)args.size(), args.data());
+    } else if (c == "pair_modify") {
+      if (!pair) fail("Pair_modify command before pair_style is defined");
+      for (size_t i = 1; i + 1 < w.size(); i += 2) {
+        if (w[i] == "table") pair->ncoultablebits = std::atoi(w[i + 1].c_str());
+        else if (w[i] == "table/disp") pair->ndisptablebits = std::atoi(w[i + 1].c_str());
+        else if (w[i] == "shift") pair->offset_flag = w[i + 1] == "yes";
+        else fail("Illegal pair_modify command");
+      }
+    } else if (c == "kspace_style") { need(3); kspace_style(w); }
+    else if (c == "kspace_modify") {
+      if (!kspace) fail("KSpace style has not yet been set");
+      std::vector<char *> args;
+      for (size_t i = 1; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
+      kspace->modify_params((int)args.size(), args.data());
+    } else if (c == "neighbor") {
+      need(3);
+      lmp.neighbor->skin = std::atof(w[1].c_str());
+      if (w[2] != "bin") fail("Illegal neighbor command (only bin is provided)");
+    } else if (c == "neigh_modify") {
+      for (size_t i = 1; i + 1 < w.size(); i += 2) {
+        if (w[i] == "every") lmp.neighbor->every = std::atoi(w[i + 1].c_str());
+        else if (w[i] == "delay") lmp.neighbor->delay = std::atoi(w[i + 1].c_str());
+        else if (w[i] == "check") lmp.neighbor->dist_check = w[i + 1] == "yes";
+        else fail("Illegal neigh_modify command");
+      }
+    } else if (c == "fix") {
+      need(4);
+      std::string s = w[3];
+      if (s.size() > 6 && s.substr(s.size() - 6) == "/intel") s = s.substr(0, s.size() - 6);
+      if (w[2] != "all" || s != "nve") fail("Unknown fix style " + w[3] + " (only `all nve` is provided)");
+      nve.reset(new FixNVEIntel(&lmp));
+    } else if (c == "package") {
+      need(2);
+      if (w[1] != "intel") fail("Illegal package command");
+      for (size_t i = 3; i + 1 < w.size(); i += 2)
+        if (w[i] == "mode") {
+          if (w[i + 1] == "double") prec_mode = FixIntel::PREC_MODE_DOUBLE;
+          else if (w[i + 1] == "mixed") prec_mode = FixIntel::PREC_MODE_MIXED;
+          else if (w[i + 1] == "single") prec_mode = FixIntel::PREC_MODE_SINGLE;
+          else fail("Illegal package intel mode");
+        }
+    } else if (c == "suffix") { need(2); suffix_intel = w[1] == "intel"; }
+    else if (c == "thermo") { need(2); thermo_every = std::atoi(w[1].c_str()); }
+    else if (c == "timestep") { need(2); lmp.update->dt = std::atof(w[1].c_str()); dt_set = true; }
+    else if (c == "run") { need(2); run(std::atol(w[1].c_str())); }
+    else if (c == "thermo_style" || c == "thermo_modify" || c == "processors" || c == "newton" || c == "echo" ||
+             c == "log" || c == "dimension" || c == "boundary") {
+      if (c == "boundary")
+        for (size_t i = 1; i < w.size() && i < 4; i++) lmp.domain->periodicity[i - 1] = w[i] == "p";
+    } else fail("Unknown command: " + c);
+  }
+};
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Script s;
+  std::string infile;
+  try {
+    for (int i = 1; i < argc; i++) {
+      const std::string a = argv[i];
+      if ((a == "-in" || a == "-i") && i + 1 < argc) infile = argv[++i];
+      else if ((a == "-sf" || a == "-suffix") && i + 1 < argc) s.suffix_intel = std::string(argv[++i]) == "intel";
+      else if ((a == "-var" || a == "-v") && i + 2 < argc) { s.vars[argv[i + 1]] = argv[i + 2]; i += 2; }
+      else if (a == "-pk" || a == "-package") {
+        // -pk intel Nphi [mode double|mixed]
+        std::string line = "package";
+        while (i + 1 < argc && argv[i + 1][0] != '-') line += std::string(" ") + argv[++i];
+        s.command(line);
+      } else if (a == "-dry-run") s.dry_run = true;
+      else if (a == "-host-step") s.host_step = true;
+      else if (a == "-echo") s.echo = true;
+      else if (a == "-device" && i + 1 < argc) s.device = std::atoi(argv[++i]);
+      else if (a == "-kspace" && i + 1 < argc) s.kspace_override = argv[++i];
+      else { std::fprintf(stderr, "lmp_b200: unknown option %s\n", a.c_str()); return 2; }
+    }
+    if (infile.empty()) { std::fprintf(stderr, "usage: lmp_b200 -in script [-sf intel] [-pk intel 0 mode double]\n"); return 2; }
+    const size_t slash = infile.rfind('/');
+    if (slash != std::string::npos) s.dir = infile.substr(0, slash);
+    std::ifstream in(infile);
+    if (!in) { std::fprintf(stderr, "ERROR: Cannot open input script %s\n", infile.c_str()); return 1; }
+    std::string line;
+    while (std::getline(in, line)) s.command(line);
+  } catch (const LAMMPSException &e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    std::printf("%s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

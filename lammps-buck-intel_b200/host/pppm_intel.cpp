@@ -1,0 +1,189 @@
+// pppm_intel.cpp — host side of pppm/intel.
+//   PPPMIntel::init     pppm_intel.cpp:67-98   (base init, "package intel" fix, order <= INTEL_P3M_MAXORDER check)
+//   PPPMIntel::compute  pppm_intel.cpp:104-317 (particle_map, make_rho, brick2fft, poisson, fieldforce, energy/virial
+//                                               post-factors)                                  -> b200md_pppm_compute
+// PPPM::init / set_grid_global / adjust_gewald restate the stock base class.
+#include "pppm_intel.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "pair_buck_intel.h"
+
+using namespace LAMMPS_NS;
+
+static const double MY_PI = 3.14159265358979323846;
+#define INTEL_P3M_MAXORDER 7   // pppm_intel.h of the reference
+
+void KSpace::modify_params(int narg, char **arg) {
+  int i = 0;
+  while (i < narg) {
+    if (!std::strcmp(arg[i], "mesh") && i + 3 < narg) {
+      nx_pppm = std::atoi(arg[i + 1]); ny_pppm = std::atoi(arg[i + 2]); nz_pppm = std::atoi(arg[i + 3]);
+      gridflag = (nx_pppm || ny_pppm || nz_pppm) ? 1 : 0;
+      i += 4;
+    } else if (!std::strcmp(arg[i], "mesh/disp") && i + 3 < narg) {
+      nx_pppm_6 = std::atoi(arg[i + 1]); ny_pppm_6 = std::atoi(arg[i + 2]); nz_pppm_6 = std::atoi(arg[i + 3]);
+      gridflag_6 = (nx_pppm_6 || ny_pppm_6 || nz_pppm_6) ? 1 : 0;
+      i += 4;
+    } else if (!std::strcmp(arg[i], "order") && i + 1 < narg) { order = std::atoi(arg[i + 1]); i += 2; }
+    else if (!std::strcmp(arg[i], "order/disp") && i + 1 < narg) { order_6 = std::atoi(arg[i + 1]); i += 2; }
+    else if (!std::strcmp(arg[i], "gewald") && i + 1 < narg) {
+      g_ewald = std::atof(arg[i + 1]);
+      gewaldflag = g_ewald != 0.0;
+      i += 2;
+    } else if (!std::strcmp(arg[i], "gewald/disp") && i + 1 < narg) {
+      g_ewald_6 = std::atof(arg[i + 1]);
+      gewaldflag_6 = g_ewald_6 != 0.0;
+      i += 2;
+    } else if (!std::strcmp(arg[i], "diff") && i + 1 < narg) {
+      if (!std::strcmp(arg[i + 1], "ad")) differentiation_flag = 1;
+      else if (!std::strcmp(arg[i + 1], "ik")) differentiation_flag = 0;
+      else error->all(FLERR, "Illegal kspace_modify command");
+      i += 2;
+    } else error->all(FLERR, "Illegal kspace_modify command");
+  }
+}
+
+PPPM::PPPM(LAMMPS *l, int narg, char **arg) : KSpace(l) {
+  if (narg < 1) error->all(FLERR, "Illegal kspace_style pppm command");
+  accuracy_relative = std::fabs(std::atof(arg[0]));
+}
+
+bool PPPM::factorable(int n) {
+  for (int f : {2, 3, 5})
+    while (n % f == 0) n /= f;
+  return n == 1;
+}
+
+void PPPM::init() {
+  if (domain->triclinic) error->all(FLERR, "Cannot (yet) use PPPM with triclinic box and this build");
+  for (int d = 0; d < 3; d++)
+    if (!domain->periodicity[d]) error->all(FLERR, "Cannot use nonperiodic boundaries with PPPM");
+  if (!atom->q_flag) error->all(FLERR, "KSpace style requires atom attribute q");
+  if (order < 2 || order > 7) error->all(FLERR, "PPPM order cannot be < 2 or > than 7");
+  if (!force->pair) error->all(FLERR, "KSpace style is incompatible with Pair style");
+  int itmp;
+  double *p_cutoff = (double *)force->pair->extract("cut_coul", itmp);
+  if (!p_cutoff) error->all(FLERR, "KSpace style is incompatible with Pair style");
+  cutoff = *p_cutoff;
+  // qsum_qsq
+  qsum = qsqsum = 0.0;
+  for (int i = 0; i < atom->nlocal; i++) { qsum += atom->q[i]; qsqsum += atom->q[i] * atom->q[i]; }
+  if (qsqsum == 0.0) error->all(FLERR, "Cannot use kspace solver on system with no charge");
+  q2 = qsqsum * force->qqrd2e;
+  two_charge_force = force->qqr2e * (force->qelectron * force->qelectron) / (force->angstrom * force->angstrom);
+  accuracy = accuracy_absolute >= 0.0 ? accuracy_absolute : accuracy_relative * two_charge_force;
+  set_grid_global();
+}
+
+// analytic rms force error of ik differentiation for grid spacing h along a box edge prd
+double PPPM::estimate_ik_error(double h, double prd, long natoms) const {
+  static const double acons[8][7] = {
+      {0, 0, 0, 0, 0, 0, 0},
+      {2.0 / 3.0, 0, 0, 0, 0, 0, 0},
+      {1.0 / 50.0, 5.0 / 294.0, 0, 0, 0, 0, 0},
+      {1.0 / 588.0, 7.0 / 1440.0, 21.0 / 3872.0, 0, 0, 0, 0},
+      {1.0 / 4320.0, 3.0 / 1936.0, 7601.0 / 2271360.0, 143.0 / 28800.0, 0, 0, 0},
+      {1.0 / 23232.0, 7601.0 / 13628160.0, 143.0 / 69120.0, 517231.0 / 106536960.0, 106640677.0 / 11737571328.0, 0, 0},
+      {691.0 / 68140800.0, 13.0 / 57600.0, 47021.0 / 35512320.0, 9694607.0 / 2095994880.0,
+       733191589.0 / 59609088000.0, 326190917.0 / 11700633600.0, 0},
+      {1.0 / 345600.0, 3617.0 / 35512320.0, 745739.0 / 838397952.0, 56399353.0 / 12773376000.0,
+       25091609.0 / 1560084480.0, 1755948832039.0 / 36229939200000.0, 4887769399.0 / 37838389248.0}};
+  double sum = 0.0;
+  for (int m = 0; m < order; m++) sum += acons[order][m] * std::pow(h * g_ewald, 2.0 * m);
+  return q2 * std::pow(h * g_ewald, (double)order) * std::sqrt(g_ewald * prd * std::sqrt(2.0 * MY_PI) * sum / natoms) /
+         (prd * prd);
+}
+
+double PPPM::newton_raphson_f() const {
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2];
+  const long natoms = atom->natoms;
+  const double df_rspace = 2.0 * q2 * std::exp(-g_ewald * g_ewald * cutoff * cutoff) /
+                           std::sqrt(natoms * cutoff * xprd * yprd * zprd);
+  const double lx = estimate_ik_error(xprd / nx_pppm, xprd, natoms);
+  const double ly = estimate_ik_error(yprd / ny_pppm, yprd, natoms);
+  const double lz = estimate_ik_error(zprd / nz_pppm, zprd, natoms);
+  return df_rspace - std::sqrt(lx * lx + ly * ly + lz * lz) / std::sqrt(3.0);
+}
+
+void PPPM::set_grid_global() {
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2];
+  const long natoms = atom->natoms;
+  if (!gewaldflag) {
+    if (accuracy <= 0.0) error->all(FLERR, "KSpace accuracy must be > 0");
+    g_ewald = accuracy * std::sqrt(natoms * cutoff * xprd * yprd * zprd) / (2.0 * q2);
+    if (g_ewald >= 1.0) g_ewald = (1.35 - 0.15 * std::log(accuracy)) / cutoff;
+    else g_ewald = std::sqrt(-std::log(g_ewald)) / cutoff;
+  }
+  if (!gridflag) {
+    if (differentiation_flag == 1) error->all(FLERR, "kspace_modify diff ad needs an explicit mesh in this build");
+    int *n[3] = {&nx_pppm, &ny_pppm, &nz_pppm};
+    const double prd[3] = {xprd, yprd, zprd};
+    for (int d = 0; d < 3; d++) {
+      double h = 1.0 / g_ewald;
+      int k = static_cast<int>(prd[d] / h) + 1;
+      double err = estimate_ik_error(h, prd[d], natoms);
+      while (err > accuracy) {
+        err = estimate_ik_error(h, prd[d], natoms);
+        k++;
+        h = prd[d] / k;
+      }
+      *n[d] = k;
+    }
+  }
+  while (!factorable(nx_pppm)) nx_pppm++;
+  while (!factorable(ny_pppm)) ny_pppm++;
+  while (!factorable(nz_pppm)) nz_pppm++;
+  if (nx_pppm >= 16384 || ny_pppm >= 16384 || nz_pppm >= 16384) error->all(FLERR, "PPPM grid is too large");
+  if (!gewaldflag && differentiation_flag == 0) {   // adjust_gewald: Newton-Raphson on the error balance
+    for (int i = 0; i < 10000; i++) {
+      const double f0 = newton_raphson_f();
+      g_ewald += 1.0e-6;
+      const double f1 = newton_raphson_f();
+      g_ewald -= 1.0e-6;
+      g_ewald -= f0 / ((f1 - f0) / 1.0e-6);
+      if (std::fabs(newton_raphson_f()) < 1.0e-5) return;
+    }
+    error->all(FLERR, "Could not compute g_ewald");
+  }
+}
+
+// ---- PPPMIntel -----------------------------------------------------------------------------------------------
+void PPPMIntel::init() {
+  PPPM::init();
+  if (!lmp->fix_intel && lmp->dry_run) return;
+  if (!lmp->fix_intel) error->all(FLERR, "The 'package intel' command is required for /intel styles");   // :73-74
+  fix = lmp->fix_intel;
+  if (order > INTEL_P3M_MAXORDER) error->all(FLERR, "PPPM order greater than supported by USER-INTEL");  // :87-88
+}
+
+void PPPMIntel::setup() {
+  if (!fix) return;   // dry run
+  b200md_pppm_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = nx_pppm; p.ny = ny_pppm; p.nz = nz_pppm;
+  p.order = order;
+  p.g_ewald = g_ewald;
+  p.differentiation = differentiation_flag;
+  p.scale = scale;
+  fix->check(b200md_pppm_setup(fix->ctx(), &p));
+}
+
+void PPPMIntel::compute(int eflag, int vflag) {
+  if (!fix) error->all(FLERR, "KSpace style pppm/intel used before init()");
+  if (!fix->resident) {
+    // plug-in deployment: positions were refreshed by the pair style of this step; forces are accumulated on the
+    // device and downloaded once, after the last force contribution
+  }
+  double e = 0.0;
+  energy = 0.0;
+  for (double &v : virial) v = 0.0;
+  fix->check(b200md_pppm_compute(fix->ctx(), eflag, vflag, &e, virial));
+  if (eflag & 1) energy = e;
+  if (!fix->resident) {
+    atom->f.assign((size_t)3 * atom->nlocal, 0.0);
+    fix->check(b200md_atoms_download(fix->ctx(), nullptr, nullptr, atom->f.data(), nullptr));
+  }
+}

@@ -125,6 +125,10 @@ void orc_pppm_size(double accuracy_relative, double two_charge_force, double qqr
 
 orc_pppm *orc_pppm_create(int nx, int ny, int nz, int order, double g_ewald, int diff_ad,
                           const double *boxlo, const double *boxhi, double qqrd2e, int prec);
+/* PPPMDispIntel 'g' (geometric mixing) grid: q array = B[type], g_ewald = g_ewald_6 (pppm_disp_intel.cpp:245-313,
+ * 486-510 + upstream PPPMDisp::compute_gf_6 / vg_6) */
+orc_pppm *orc_pppm_create_disp(int nx, int ny, int nz, int order, double g_ewald_6, const double *boxlo,
+                               const double *boxhi, int prec);
 void orc_pppm_destroy(orc_pppm *p);
 /* PPPMIntel::compute (single rank, periodic).  f[nlocal][3] is accumulated into (+=).
  * energy / virial[6] written when eflag / vflag. */

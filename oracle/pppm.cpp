@@ -77,6 +77,7 @@ double estimate_ik_error(double h, double prd, long natoms, int order, double g_
 
 struct orc_pppm {
   int nx_pppm, ny_pppm, nz_pppm, order, diff_ad, prec;
+  int dispersion = 0;   // 1: geometric-mixing dispersion grid (PPPMDispIntel 'g', pppm_disp_intel.cpp:245-313)
   double g_ewald, qqrd2e, scale;
   double boxlo[3], prd[3], volume;
   double cuthalf;
@@ -105,7 +106,8 @@ struct orc_pppm {
   }
 
   void init(int nx, int ny, int nz, int order_, double g, int ad, const double *lo, const double *hi,
-            double qq, int prec_) {
+            double qq, int prec_, int disp = 0) {
+    dispersion = disp;
     nx_pppm = nx; ny_pppm = ny; nz_pppm = nz; order = order_; g_ewald = g; diff_ad = ad;
     qqrd2e = qq; scale = 1.0; prec = prec_;
     for (int d = 0; d < 3; d++) { boxlo[d] = lo[d]; prd[d] = hi[d] - lo[d]; }
@@ -275,7 +277,14 @@ struct orc_pppm {
           if (sqk == 0.0) {
             for (int t = 0; t < 6; t++) v[t] = 0.0;
           } else {
-            const double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+            double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+            if (dispersion) {   // PPPMDisp::setup, vg_6: derivative of the r^-6 reciprocal kernel
+              const double rtpi = std::sqrt(MY_PI);
+              const double b = 0.5 * std::sqrt(sqk) / g_ewald, bs = b * b, bt = bs * b;
+              const double erft = 2.0 * bt * rtpi * std::erfc(b), expt = std::exp(-bs);
+              const double nom = erft - 2.0 * bs * expt, denom = nom + expt;
+              vterm = denom == 0.0 ? 3.0 / sqk : 3.0 * nom / (sqk * denom);
+            }
             v[0] = 1.0 + vterm * fkx[i] * fkx[i];
             v[1] = 1.0 + vterm * fky[j] * fky[j];
             v[2] = 1.0 + vterm * fkz[k] * fkz[k];
@@ -284,8 +293,56 @@ struct orc_pppm {
             v[5] = vterm * fky[j] * fkz[k];
           }
         }
-    if (diff_ad) compute_gf_ad();
+    if (dispersion) compute_gf_6();
+    else if (diff_ad) compute_gf_ad();
     else compute_gf_ik();
+  }
+
+  // PPPMDisp::compute_gf_6 [UPSTREAM, restated]: optimal influence function of the r^-6 reciprocal sum,
+  // g_ewald here is g_ewald_6.  Pinned by the dispersion-Ewald known-answer tests (tests/test_oracle_kat.py).
+  void compute_gf_6() {
+    const double xprd = prd[0], yprd = prd[1], zprd_slab = prd[2];
+    const double unitkx = MY_2PI / xprd, unitky = MY_2PI / yprd, unitkz = MY_2PI / zprd_slab;
+    const double inv2ew = 1.0 / (2.0 * g_ewald);
+    const double rtpi = std::sqrt(MY_PI);
+    const double numerator = -MY_PI * rtpi * g_ewald * g_ewald * g_ewald / 3.0;
+#pragma omp parallel for schedule(static)
+    for (int m = 0; m < nz_pppm; m++) {
+      const int mper = m - nz_pppm * (2 * m / nz_pppm);
+      const double qz = unitkz * mper;
+      const double snz2 = square(std::sin(0.5 * unitkz * mper * zprd_slab / nz_pppm));
+      const double sz = std::exp(-qz * qz * inv2ew * inv2ew);
+      const double argz = 0.5 * qz * zprd_slab / nz_pppm;
+      double wz = argz != 0.0 ? std::pow(std::sin(argz) / argz, order) : 1.0;
+      wz *= wz;
+      for (int l = 0; l < ny_pppm; l++) {
+        const int lper = l - ny_pppm * (2 * l / ny_pppm);
+        const double qy = unitky * lper;
+        const double sny2 = square(std::sin(0.5 * unitky * lper * yprd / ny_pppm));
+        const double sy = std::exp(-qy * qy * inv2ew * inv2ew);
+        const double argy = 0.5 * qy * yprd / ny_pppm;
+        double wy = argy != 0.0 ? std::pow(std::sin(argy) / argy, order) : 1.0;
+        wy *= wy;
+        for (int k = 0; k < nx_pppm; k++) {
+          const int kper = k - nx_pppm * (2 * k / nx_pppm);
+          const double qx = unitkx * kper;
+          const double snx2 = square(std::sin(0.5 * unitkx * kper * xprd / nx_pppm));
+          const double sx = std::exp(-qx * qx * inv2ew * inv2ew);
+          const double argx = 0.5 * qx * xprd / nx_pppm;
+          double wx = argx != 0.0 ? std::pow(std::sin(argx) / argx, order) : 1.0;
+          wx *= wx;
+          const double sqk = qx * qx + qy * qy + qz * qz;
+          const long n = ((long)m * ny_pppm + l) * nx_pppm + k;
+          if (sqk != 0.0) {
+            const double denominator = gf_denom(snx2, sny2, snz2);
+            const double rtsqk = std::sqrt(sqk);
+            const double term = (1.0 - 2.0 * sqk * inv2ew * inv2ew) * sx * sy * sz +
+                                2.0 * sqk * rtsqk * inv2ew * inv2ew * inv2ew * rtpi * std::erfc(rtsqk * inv2ew);
+            greensfn[n] = numerator * term * wx * wy * wz / denominator;
+          } else greensfn[n] = 0.0;
+        }
+      }
+    }
   }
 
   void compute_gf_ik() {
@@ -733,6 +790,21 @@ struct orc_pppm {
     if (diff_ad) fieldforce_ad<flt_t>(nlocal, x, q, f);
     else fieldforce_ik<flt_t>(nlocal, x, q, f, nthr);
     const double qscale = qqrd2e * scale;
+    if (dispersion) {
+      // pppm_disp_intel.cpp:486-510 with the 'q' array carrying B[type]: csum = sum B_i^2, csumij = (sum B_i)^2
+      const double csum = qsqsum, csumij = qsum * qsum, g3 = g_ewald * g_ewald * g_ewald;
+      if (eflag_global) {
+        energy *= 0.5 * volume;
+        energy += -MY_PI * MY_PIS / (6.0 * volume) * g3 * csumij + 1.0 / 12.0 * g3 * g3 * csum;
+        if (energy_out) *energy_out = energy;
+      }
+      if (vflag_global) {
+        const double a = MY_PI * MY_PIS / (6.0 * volume) * g3 * csumij;
+        for (int i = 0; i < 6; i++) virial[i] = 0.5 * volume * virial[i];
+        for (int i = 0; i < 3; i++) virial[i] -= a;
+        if (virial_out) for (int i = 0; i < 6; i++) virial_out[i] = virial[i];
+      }
+    } else {
     if (eflag_global) {
       energy *= 0.5 * volume;
       energy -= g_ewald * qsqsum / MY_PIS + MY_PI2 * qsum * qsum / (g_ewald * g_ewald * volume);
@@ -742,6 +814,7 @@ struct orc_pppm {
     if (vflag_global) {
       for (int i = 0; i < 6; i++) virial[i] = 0.5 * qscale * volume * virial[i];
       if (virial_out) for (int i = 0; i < 6; i++) virial_out[i] = virial[i];
+    }
     }
     // expose owned-cell fields for parity checks
     for (int d = 0; d < 3; d++) {
@@ -823,6 +896,15 @@ orc_pppm *orc_pppm_create(int nx, int ny, int nz, int order, double g_ewald, int
   if (order < 1 || order > MAXORDER) return nullptr;
   orc_pppm *p = new orc_pppm();
   p->init(nx, ny, nz, order, g_ewald, diff_ad, boxlo, boxhi, qqrd2e, prec);
+  return p;
+}
+/* dispersion grid, geometric mixing: pass w[i] = B[type[i]] as the `q` array of orc_pppm_compute; forces are
+ * f += w * E (no qqrd2e), energy/virial carry the dispersion self terms */
+orc_pppm *orc_pppm_create_disp(int nx, int ny, int nz, int order, double g_ewald_6, const double *boxlo,
+                               const double *boxhi, int prec) {
+  if (order < 1 || order > MAXORDER) return nullptr;
+  orc_pppm *p = new orc_pppm();
+  p->init(nx, ny, nz, order, g_ewald_6, 0, boxlo, boxhi, 1.0, prec, 1);
   return p;
 }
 void orc_pppm_destroy(orc_pppm *p) { delete p; }

@@ -178,6 +178,14 @@ class Params:
         self.p.etable, self.p.detable, self.p.ctable, self.p.dctable = _d(t["e"]), _d(t["de"]), _d(t["c"]), _d(t["dc"])
 
 
+    def set_disp_tables(self, t, nbits, mask, shift, tabinnerdispsq):
+        self.dtables = t
+        self.p.ndisptablebits, self.p.ndispmask, self.p.ndispshiftbits = nbits, mask, shift
+        self.p.tabinnerdispsq = tabinnerdispsq
+        self.p.rdisptable, self.p.drdisptable, self.p.fdisptable = _d(t["r"]), _d(t["dr"]), _d(t["f"])
+        self.p.dfdisptable, self.p.edisptable, self.p.dedisptable = _d(t["df"]), _d(t["e"]), _d(t["de"])
+
+
 def make_ghosts(x, type_, q, boxlo, boxhi, cutghost, periodic=(1, 1, 1)):
     """Returns (x_all, type_all, q_all, src, shift) with ghosts appended."""
     n = len(x)
@@ -290,6 +298,21 @@ class PPPM:
         self.grid = (nx, ny, nz)
         self.order = order
         self.nfft = nx * ny * nz
+
+    @classmethod
+    def dispersion(cls, nx, ny, nz, order, g_ewald_6, boxlo, boxhi, prec=DOUBLE):
+        """PPPMDispIntel 'g' grid (geometric mixing): compute(x, w) takes w[i] = B[type[i]]"""
+        self = cls.__new__(cls)
+        lib().orc_pppm_create_disp.restype = C.c_void_p
+        h = lib().orc_pppm_create_disp(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order), C.c_double(g_ewald_6),
+                                       _d(f64(boxlo)), _d(f64(boxhi)), C.c_int(prec))
+        if not h:
+            raise ValueError("PPPM order not supported")
+        self.h = C.c_void_p(h)
+        self.grid = (nx, ny, nz)
+        self.order = order
+        self.nfft = nx * ny * nz
+        return self
 
     def __del__(self):
         if getattr(self, "h", None):

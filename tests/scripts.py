@@ -1,0 +1,103 @@
+"""Input scripts with the semantics of the reference's examples (in.buck, in.buck_big, in.buck_coul_cut,
+in.buck_coul_long — SURVEY §6.2), written out for the lmp_b200 driver; data.aC is regenerated from its 12-atom basis
+(workloads.data_aC), so nothing under /root/reference is needed at run time."""
+import os
+
+IN_BUCK = """# Buckingham melt (examples/in.buck semantics)
+variable x index 1
+variable y index 1
+variable z index 1
+variable xx equal {n}*$x
+variable yy equal {n}*$y
+variable zz equal {n}*$z
+units lj
+atom_style atomic
+lattice fcc 0.8442
+region box block 0 ${{xx}} 0 ${{yy}} 0 ${{zz}}
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+velocity all create 1.44 87287 loop geom
+pair_style buck 2.5
+pair_coeff 1 1 1.0 0.2 -0.8
+neighbor 0.3 bin
+neigh_modify delay 0 every 20 check no
+fix 1 all nve
+thermo {thermo}
+run {steps}
+"""
+
+IN_BUCK_COUL_CUT = """units metal
+atom_style charge
+read_data data.aC
+replicate {r} {r} {r}
+pair_style buck/coul/cut 10.0
+pair_coeff 2 2 1388.77 .3623188 175.0
+pair_coeff 1 2 18003 .2052124 133.5381
+pair_coeff 1 1 0 .1 0
+neighbor 0.3 bin
+neigh_modify delay 0 every 1 check yes
+velocity all create 300.0 1281937
+fix 1 all nve
+thermo {thermo}
+run {steps}
+"""
+
+IN_BUCK_COUL_LONG = """units metal
+atom_style charge
+read_data data.aC
+replicate {r} {r} {r}
+pair_style buck/coul/long 12.0
+pair_coeff 2 2 1388.77 .3623188 175.0
+pair_coeff 1 2 18003 .2052124 133.5381
+pair_coeff 1 1 0 .1 0
+{pair_modify}
+kspace_style {kspace}
+neighbor 0.3 bin
+neigh_modify delay 0 every 1 check yes
+velocity all create 300.0 1281937
+fix 1 all nve
+thermo {thermo}
+run {steps}
+"""
+
+IN_BUCK_DISP = """# in.buck_big variant of BASELINE config 5: long-range dispersion + pppm/disp
+units lj
+atom_style atomic
+lattice fcc 0.8442
+region box block 0 {n} 0 {n} 0 {n}
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+velocity all create 1.44 87287 loop geom
+pair_style buck/long/coul/long long off 5.0
+pair_coeff 1 1 {A} 0.2 0.8
+pair_modify table/disp 0
+kspace_style pppm/disp 1e-4
+kspace_modify gewald/disp {g6} mesh/disp {m} {m} {m} order/disp 5
+neighbor 0.3 bin
+neigh_modify delay 5 every 1
+fix 1 all nve
+thermo {thermo}
+run {steps}
+"""
+
+
+def write_data_aC(W, path):
+    x, t, q, lo, hi = W.data_aC()
+    with open(path, "w") as fh:
+        fh.write(" regenerated alpha-cristobalite cell\n\n %d atoms\n 2 atom types\n\n" % len(x))
+        for d, nm in enumerate("xyz"):
+            fh.write(" %.16g %.16g %slo %shi\n" % (lo[d], hi[d], nm, nm))
+        fh.write("\n Masses\n\n 1 28.0855\n 2 15.9999\n\n Atoms\n\n")
+        for i in range(len(x)):
+            fh.write(" %d %d %.16g %.16g %.16g %.16g\n" % (i + 1, t[i], q[i], x[i, 0], x[i, 1], x[i, 2]))
+
+
+def write(tmpdir, name, text, W=None):
+    p = os.path.join(str(tmpdir), name)
+    with open(p, "w") as fh:
+        fh.write(text)
+    if W is not None:
+        write_data_aC(W, os.path.join(str(tmpdir), "data.aC"))
+    return p

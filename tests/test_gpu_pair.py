@@ -40,20 +40,41 @@ def _setup(pkg, W, orc, case, prec, tables=False):
         s = W.aC_system(2)
         co = W.coeffs_aC(12.0, 12.0)
         style, ostyle, nt, ge = pkg.PAIR_BUCK_COUL_LONG, orc.BUCK_COUL_LONG, 2, 0.3051
+    elif case == "lcl_disp":        # BASELINE config 5 variant: in.buck_big with `buck/long/coul/long long off 5.0`
+        s = W.fcc_system(7, 7, 8)
+        co = W.coeffs_in_buck(5.0)
+        co["C"] = -co["C"]          # attractive dispersion, as a long-range r^-6 term needs
+        style, ostyle, nt, ge, g6, o1, o6 = pkg.PAIR_BUCK_LONG_COUL_LONG, orc.BUCK_LONG_COUL_LONG, 1, 0.0, 0.85, 0, 1
+    elif case == "lcl_both":        # long Coulomb + long dispersion on the charged aC cell
+        s = W.aC_system(1)
+        co = W.coeffs_aC(10.0, 10.0)
+        style, ostyle, nt, ge, g6, o1, o6 = pkg.PAIR_BUCK_LONG_COUL_LONG, orc.BUCK_LONG_COUL_LONG, 2, 0.29, 0.33, 1, 1
+    elif case == "lcl_coul":        # long Coulomb, cut dispersion (ORDER1 only)
+        s = W.aC_system(1)
+        co = W.coeffs_aC(10.0, 10.0)
+        style, ostyle, nt, ge, g6, o1, o6 = pkg.PAIR_BUCK_LONG_COUL_LONG, orc.BUCK_LONG_COUL_LONG, 2, 0.29, 0.0, 1, 0
     else:
         raise ValueError(case)
     u = W.UNITS[s["units"]]
-    P = orc.Params(ostyle, nt, co["A"], co["rho"], co["C"], co["cut_lj"], co.get("cut_coul"), qqrd2e=u["qqrd2e"],
-                   g_ewald=ge)
-    cf = pkg.pair_coeffs(style, nt, co["A"], co["rho"], co["C"], co["cut_lj"], co.get("cut_coul"))
-    ct = None
-    if tables:
-        cc = float(co["cut_coul"][1, 1])
+    lcl = style == pkg.PAIR_BUCK_LONG_COUL_LONG
+    if not lcl:
+        g6, o1, o6 = 0.0, 0, 0
+    cutc = co.get("cut_coul", co["cut_lj"] if lcl else None)
+    P = orc.Params(ostyle, nt, co["A"], co["rho"], co["C"], co["cut_lj"], cutc, qqrd2e=u["qqrd2e"],
+                   g_ewald=ge, g_ewald_6=g6, order1=o1, order6=o6)
+    cf = pkg.pair_coeffs(style, nt, co["A"], co["rho"], co["C"], co["cut_lj"], cutc)
+    ct = dt = None
+    if tables and (not lcl or o1):
+        cc = float(cutc[1, 1])
         ct = pkg.init_coul_tables(cc, ge, u["qqrd2e"])
         P.set_coul_tables(ct[0], 12, ct[1], ct[2], ct[3])
+    if tables and lcl and o6:
+        dt = pkg.init_disp_tables(float(co["cut_lj"][1, 1]), g6)
+        P.set_disp_tables(dt[0], 12, dt[1], dt[2], dt[3])
     ctx = pkg.make_context(s, precision=prec)
     ctx.neigh_setup(0.3)
-    ctx.pair_setup(style, nt, cf, g_ewald=ge, coul_tables=ct)
+    ctx.pair_setup(style, nt, cf, g_ewald=ge, g_ewald_6=g6, ewald_order=(o1 << 1) | (o6 << 6), coul_tables=ct,
+                   disp_tables=dt)
     return s, P, ctx
 
 
@@ -87,7 +108,8 @@ def test_pair_set_bit_exact(pkg, W, orc, case, prec):
 @pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("case,tables", [("buck", False), ("buck_big", False), ("coul_cut", False),
                                          ("coul_cut_split", False), ("coul_long", False), ("coul_long", True),
-                                         ("coul_long_r2", False)])
+                                         ("coul_long_r2", False), ("lcl_disp", False), ("lcl_disp", True),
+                                         ("lcl_both", False), ("lcl_both", True), ("lcl_coul", False)])
 def test_pair_forces_energy_virial(pkg, W, orc, case, tables, prec):
     s, P, ctx = _setup(pkg, W, orc, case, prec, tables)
     n = len(s["x"])

@@ -155,3 +155,41 @@ def test_full_step_buck_coul_long_pppm(pkg, W, orc):
     # velocity Verlet at dt = 1 fs: the total energy wobbles by O((w dt)^2) of the kinetic energy, no drift
     assert abs(e1 - e0) <= 0.03 * u["mvv2e"] * th1[15], (e0, e1, u["mvv2e"] * th1[15])
     ctx.close()
+
+
+def _resident(ctx, s):
+    """PPPM alone on device-resident atoms: a fresh upload zeroes the force array, compute accumulates onto it"""
+    ctx.atoms_upload(s["x"], s["type"], s["mass"], v=s.get("v"), q=s.get("q"))
+    e, v = ctx.pppm_compute(1, 1)
+    return ctx.atoms_download(("f",))["f"], e, v
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("order", [5, 3, 7])
+def test_pppm_disp_geometric_matches_oracle(pkg, W, orc, order, prec):
+    """PPPMDispIntel 'g' grid (pppm_disp_intel.cpp:245-313 with the per-atom weight B[type]):
+    forces, energy (incl. the self terms :486-492) and virial (:498-510) against the oracle"""
+    s = W.aC_system(1)
+    B = np.array([0.0, 9.0, 13.2])
+    g6 = 0.31
+    grid = (30, 30, 32)
+    ctx = pkg.make_context(s, precision=prec)
+    ctx.neigh_setup(0.3)
+    ctx.pppm_setup(*grid, order, g6, dispersion=1, B=B)
+    f, e, v = _resident(ctx, s)
+    pp = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], prec=prec)
+    fo, eo, vo = pp.compute(s["x"], B[s["type"]])
+    tol_f, tol_e = (1e-9, 1e-10) if prec == 0 else (1e-5, 1e-5)
+    assert np.abs(f - fo).max() <= tol_f * np.abs(fo).max()
+    assert abs(e - eo) <= tol_e * abs(eo)
+    assert np.abs(v - vo).max() <= tol_e * np.abs(vo).max()
+    # Coulomb and dispersion grids together (pppm/disp with function[0] and function[1]): sums of the two
+    u = W.UNITS["metal"]
+    ctx.pppm_setup(24, 24, 27, 5, 0.28)
+    f2, e2, v2 = _resident(ctx, s)
+    pc = orc.PPPM(24, 24, 27, 5, 0.28, s["boxlo"], s["boxhi"], u["qqrd2e"], prec=prec)
+    fc, ec, vc = pc.compute(s["x"], s["q"])
+    assert np.abs(f2 - (fo + fc)).max() <= tol_f * np.abs(fo + fc).max() * 2
+    assert abs(e2 - (eo + ec)) <= tol_e * abs(eo + ec) * 2
+    assert np.abs(v2 - (vo + vc)).max() <= tol_e * np.abs(vo + vc).max() * 2
+    ctx.close()

@@ -1,0 +1,165 @@
+"""Host layer (lammps-buck-intel_b200/host): the reference's class surface + the input-script driver.
+CPU part: parsing, lattice / read_data / replicate, velocity, init_one products and PPPM sizing via `lmp_b200
+-dry-run` (no device).  GPU part (-m gpu): the scripts run end to end through the classes and the C ABI and are
+compared with the CPU oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import scripts
+
+
+def _run(pkg, args, cwd=None):
+    lmp = pkg.build_host()
+    r = subprocess.run([lmp] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+    return r
+
+
+def _summary(out):
+    line = [l for l in out.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+def _thermo(out):
+    rows, on = [], False
+    for l in out.splitlines():
+        w = l.split()
+        if w[:2] == ["Step", "Temp"]:
+            on = True
+            continue
+        if on:
+            try:
+                rows.append([float(v) for v in w])
+            except ValueError:
+                on = False
+    return np.array(rows)
+
+
+def test_dry_run_in_buck(pkg, W, tmp_path):
+    p = scripts.write(tmp_path, "in.buck", scripts.IN_BUCK.format(n=20, steps=100, thermo=0))
+    r = _run(pkg, ["-in", p, "-sf", "intel", "-dry-run"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    s = _summary(r.stdout)
+    assert s["natoms"] == 32000 and s["pair_style"] == "buck" and s["cutforce"] == 2.5
+    assert (s["every"], s["delay"], s["check"]) == (20, 0, 0)
+    assert s["temperature"] == pytest.approx(1.44, rel=1e-12)
+    assert np.allclose(s["box"], 20 * (4 / 0.8442) ** (1 / 3))
+    # -var overrides the index variable (the script's own scaling mechanism)
+    r = _run(pkg, ["-in", p, "-sf", "intel", "-dry-run", "-var", "x", "2"])
+    assert _summary(r.stdout)["natoms"] == 64000
+
+
+def test_dry_run_coul_long_sizing_matches_python(pkg, W, tmp_path):
+    """PPPM::set_grid_global / adjust_gewald in C++ (host/pppm_intel.cpp) == the Python restatement used by bench.py"""
+    for acc, r in ((1e-4, 2), (1e-6, 2), (1e-4, 3)):
+        txt = scripts.IN_BUCK_COUL_LONG.format(r=r, kspace="pppm %g" % acc, pair_modify="", steps=1, thermo=0)
+        p = scripts.write(tmp_path, "in.bcl", txt, W)
+        out = _run(pkg, ["-in", p, "-sf", "intel", "-dry-run"])
+        assert out.returncode == 0, out.stdout + out.stderr
+        s = _summary(out.stdout)
+        sysd = W.aC_system(r, jitter=0.0)
+        u = W.UNITS["metal"]
+        grid, g = pkg.pppm_init(acc, u["qqrd2e"], sysd["q"], len(sysd["x"]), 12.0, sysd["boxhi"] - sysd["boxlo"])
+        assert tuple(s["grid"]) == tuple(grid)
+        assert s["g_ewald"] == pytest.approx(g, rel=1e-9)
+        assert s["natoms"] == 1200 * r ** 3
+    # the shipped script says `kspace_style ewald 1e-6`: served by the mesh solver, with a warning
+    txt = scripts.IN_BUCK_COUL_LONG.format(r=2, kspace="ewald 1e-6", pair_modify="", steps=1, thermo=0)
+    out = _run(pkg, ["-in", scripts.write(tmp_path, "in.bcl", txt, W), "-sf", "intel", "-dry-run"])
+    assert "ewald is not provided" in out.stderr and tuple(_summary(out.stdout)["grid"]) == (96, 96, 108)
+
+
+def test_driver_errors(pkg, W, tmp_path):
+    bad = scripts.IN_BUCK.format(n=4, steps=1, thermo=0).replace("pair_coeff 1 1 1.0 0.2 -0.8", "")
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bad", bad), "-sf", "intel", "-dry-run"])
+    assert r.returncode == 1 and "All pair coeffs are not set" in r.stdout
+    nosf = scripts.IN_BUCK.format(n=4, steps=1, thermo=0)
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.nosf", nosf), "-dry-run"])
+    assert r.returncode == 1 and "only the /intel styles are provided" in r.stdout
+    cutc = scripts.IN_BUCK_DISP.format(n=4, g6=0.9, m=16, steps=1, thermo=0, A=3000.0).replace("long off", "long cut")
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.cut", cutc), "-sf", "intel", "-dry-run"])
+    assert r.returncode == 1 and "Coulomb cut not supported" in r.stdout
+
+
+@pytest.mark.gpu
+def test_in_buck_runs_like_the_oracle(pkg, W, orc, tmp_path):
+    """in.buck at 8^3 cells: step-0 E_pair / pressure equal the oracle on the same lattice; 100 NVE steps with the
+    script's `every 20 check no` cadence conserve energy and do exactly 5 rebuilds"""
+    p = scripts.write(tmp_path, "in.buck", scripts.IN_BUCK.format(n=8, steps=100, thermo=20))
+    r = _run(pkg, ["-in", p, "-sf", "intel", "-pk", "intel", "0", "mode", "double"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    assert th.shape[0] == 6 and th[0, 0] == 0 and th[-1, 0] == 100
+    s = W.fcc_system(8, 8, 8, jitter=0.0)
+    co = W.coeffs_in_buck(2.5)
+    P = orc.Params(orc.BUCK, 1, co["A"], co["rho"], co["C"], co["cut_lj"])
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], None, s["boxlo"], s["boxhi"], 0.3)
+    n = len(s["x"])
+    assert th[0, 1] == pytest.approx(1.44, rel=1e-9)
+    assert th[0, 2] == pytest.approx(ev[0], rel=1e-10)
+    vol = np.prod(s["boxhi"] - s["boxlo"])
+    press = ((3 * n - 3) * 1.44 + ev[2] + ev[3] + ev[4]) / 3.0 / vol
+    assert th[0, 5] == pytest.approx(press, rel=1e-8)
+    drift = np.abs(th[:, 4] - th[0, 4]).max() / n
+    assert drift < 3e-3, "total energy per atom drifts by %g" % drift   # un-shifted cut-off at 2.5 sigma, T* = 1.44
+    assert "Neighbor list builds = 5" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("table", [0, 12])
+def test_in_buck_coul_long_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
+    """in.buck_coul_long (data.aC x 2^3) with pppm 1e-4, analytic erfc and the stock Coulomb tables: step-0 energies
+    against the oracle (pair + PPPM) on the same inputs; resident and host-step deployments agree"""
+    txt = scripts.IN_BUCK_COUL_LONG.format(r=2, kspace="pppm 1e-4", pair_modify="pair_modify table %d" % table,
+                                           steps=10, thermo=5)
+    p = scripts.write(tmp_path, "in.bcl", txt, W)
+    r = _run(pkg, ["-in", p, "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    s = W.aC_system(2, jitter=0.0)
+    u = W.UNITS["metal"]
+    grid, g = pkg.pppm_init(1e-4, u["qqrd2e"], s["q"], len(s["x"]), 12.0, s["boxhi"] - s["boxlo"])
+    co = W.coeffs_aC(12.0, 12.0)
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=g)
+    if table:
+        ct = pkg.init_coul_tables(12.0, g, u["qqrd2e"])
+        P.set_coul_tables(ct[0], 12, ct[1], ct[2], ct[3])
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    pp = orc.PPPM(*grid, 5, g, s["boxlo"], s["boxhi"], u["qqrd2e"])
+    fk, ek, vk = pp.compute(s["x"], s["q"])
+    assert th[0, 2] == pytest.approx(ev[0] + ev[1] + ek, rel=1e-9)
+    assert th[0, 1] == pytest.approx(300.0, rel=1e-9)
+    n = len(s["x"])
+    # Verlet fluctuation of the stiff Si-O modes at dt = 1 fs is ~(w dt)^2/8 of the kinetic energy (0.04 eV/atom)
+    assert np.abs(th[:, 4] - th[0, 4]).max() / n < 1e-3
+    # plug-in deployment (host owns x and f, PCIe every step) walks the same trajectory
+    r2 = _run(pkg, ["-in", p, "-sf", "intel", "-host-step"])
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    th2 = _thermo(r2.stdout)
+    assert np.allclose(th2[:, 2], th[:, 2], rtol=1e-9, atol=0)
+
+
+@pytest.mark.gpu
+def test_buck_long_coul_long_with_pppm_disp(pkg, W, orc, tmp_path):
+    """BASELINE config 5 variant: buck/long/coul/long long off + pppm/disp (geometric grid) through the driver:
+    step-0 E_pair against the oracle's pair + dispersion-PPPM, energy conservation over 20 steps"""
+    n, g6, m = 6, 0.9, 30
+    txt = scripts.IN_BUCK_DISP.format(n=n, g6=g6, m=m, steps=20, thermo=10, A=3000.0)   # a real repulsive wall
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.disp", txt), "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    s = W.fcc_system(n, n, n, jitter=0.0)
+    A = np.zeros((2, 2)); rho = np.ones((2, 2)); C = np.zeros((2, 2))
+    A[1, 1], rho[1, 1], C[1, 1] = 3000.0, 0.2, 0.8
+    P = orc.Params(orc.BUCK_LONG_COUL_LONG, 1, A, rho, C, np.full((2, 2), 5.0), np.full((2, 2), 5.0), g_ewald_6=g6,
+                   order6=1)
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], None, s["boxlo"], s["boxhi"], 0.3)
+    pp = orc.PPPM.dispersion(m, m, m, 5, g6, s["boxlo"], s["boxhi"])
+    B = np.array([0.0, np.sqrt(0.8)])
+    fk, ek, vk = pp.compute(s["x"], B[s["type"]])
+    assert th[0, 2] == pytest.approx(ev[0] + ek, rel=1e-9)
+    assert np.abs(th[:, 4] - th[0, 4]).max() < 5e-4 * abs(th[0, 4])   # stiff, strongly compressed system

@@ -219,3 +219,61 @@ def test_nve_matches_closed_form(orc):
     x1, v1 = orc.nve_initial(x, v, f, dtfm, 0.01)
     assert np.allclose(v1, v + dtfm.reshape(1, 3) * f) and np.allclose(x1, x + 0.01 * v1)
     assert np.allclose(orc.nve_final(v1, f, dtfm), v1 + dtfm.reshape(1, 3) * f)
+
+
+def _disp_system(W):
+    s = W.aC_system(1)
+    B = np.array([0.0, 9.0, 13.2])                 # geometric mixing: C_ij = B_i B_j
+    C = np.outer(B, B)
+    A = np.zeros((3, 3)); rho = np.ones((3, 3))    # pure dispersion (no repulsive wall: only -C/r^6 is checked)
+    return s, B, C, A, rho
+
+
+def _disp_total(orc, s, B, C, A, rho, g6, rc=11.0, grid=(54, 54, 60), order=7):
+    P = orc.Params(orc.BUCK_LONG_COUL_LONG, 2, A, rho, C, np.full((3, 3), rc), np.full((3, 3), rc), qqrd2e=14.399645,
+                   g_ewald_6=g6, order6=1)
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    pp = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"])
+    fk, ek, vk = pp.compute(s["x"], B[s["type"]])
+    return f[:, :3] + fk, ev[0] + ek, ev[2:] + vk
+
+
+def test_dispersion_ewald_is_independent_of_g_ewald_6(orc, W):
+    """pppm/disp 'g' path + buck/long/coul/long ORDER6 real space: the split parameter must drop out of the total
+    energy, forces and virial (pins compute_gf_6, the self terms of pppm_disp_intel.cpp:486-510 and vg_6), and the
+    virial trace of an r^-6 potential is 6 E."""
+    s, B, C, A, rho = _disp_system(W)
+    f1, e1, v1 = _disp_total(orc, s, B, C, A, rho, 0.28)
+    f2, e2, v2 = _disp_total(orc, s, B, C, A, rho, 0.36)
+    assert e1 == pytest.approx(e2, rel=2e-6)
+    assert np.abs(f1 - f2).max() <= 2e-5 * np.abs(f1).max()
+    assert np.allclose(v1, v2, rtol=0, atol=2e-5 * np.abs(v1).max())
+    assert v1[0] + v1[1] + v1[2] == pytest.approx(6.0 * e1, rel=2e-5)
+
+
+def test_dispersion_ewald_equals_direct_lattice_sum(orc, W):
+    """... and equals the direct sum of -B_i B_j / r^6 over periodic images (R = 38 A + continuum tail)"""
+    s, B, C, A, rho = _disp_system(W)
+    ft, et, _ = _disp_total(orc, s, B, C, A, rho, 0.30)
+    x, w = s["x"], B[s["type"]]
+    prd = s["boxhi"] - s["boxlo"]
+    R = 38.0
+    nimg = [int(np.ceil(R / p)) for p in prd]
+    shifts = np.array([[i, j, k] for i in range(-nimg[0], nimg[0] + 1) for j in range(-nimg[1], nimg[1] + 1)
+                       for k in range(-nimg[2], nimg[2] + 1)], float) * prd
+    e = 0.0
+    f = np.zeros_like(x)
+    for sh in shifts:
+        d = x[:, None, :] - (x[None, :, :] + sh)          # r_i - r_j'
+        r2 = (d * d).sum(-1)
+        m = (r2 < R * R) & (r2 > 1e-12)
+        ww = w[:, None] * w[None, :]
+        r2m = np.where(m, r2, 1.0)
+        inv6 = np.where(m, 1.0 / r2m ** 3, 0.0)
+        e += -0.5 * (ww * inv6).sum()
+        # F_i = -dU/dr_i, U = -ww/r^6  ->  F_i = -6 ww d / r^8
+        f += (-6.0 * ww * inv6 / r2m)[:, :, None].__mul__(d).sum(1)
+    vol = prd.prod()
+    e += -0.5 * w.sum() ** 2 / vol * 4.0 * np.pi / (3.0 * R ** 3)
+    assert et == pytest.approx(e, rel=2e-5)
+    assert np.abs(ft - f).max() <= 1e-4 * np.abs(f).max()
