@@ -81,6 +81,11 @@ int b200md_atoms_set_x(b200md_ctx *ctx, const double *x);
  * intel_buffers.h:44) may be NULL */
 int b200md_atoms_download(b200md_ctx *ctx, double *x, double *v, double *f, double *eatom);
 int b200md_atoms_count(const b200md_ctx *ctx, int *nlocal, int *nghost);
+/* multi-GPU: the atoms this rank owns NOW (atoms migrate between the z slabs), device order, with their global ids
+ * (id = index in the concatenation of all ranks' uploads, rank 0 first); arrays sized `capacity` atoms; any of
+ * ids/x/v/f may be NULL.  Replaces the gather a host code would do over atom->tag. */
+int b200md_atoms_download_ids(b200md_ctx *ctx, int capacity, int *n_out, int *ids, double *x, double *v,
+                              double *f);
 
 /* ------------------------------------------------------------------------------------------------
  * pair styles — replaces Pair*Intel::init_style + pack_force_const (pair_buck_intel.cpp:367-443,

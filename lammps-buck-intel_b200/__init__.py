@@ -604,6 +604,41 @@ class Context:
         """x_in/x_out/f_out: C-contiguous float64 [n,3] numpy arrays (pinned for speed) or None"""
         self._ck(self.lib.b200md_step_host(self.h, _d(x_in), _d(x_out), _d(f_out)))
 
+    # ---- multi-GPU ----------------------------------------------------------------------------------
+    def comm_init(self, rank, nranks, unique_id=None):
+        """unique_id: the 128 bytes from comm_unique_id() on rank 0, broadcast by the caller.  Call before
+        atoms_upload / pppm_setup (global atom ids and the grid decomposition depend on it)."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._ck(self.lib.b200md_comm_init(self.h, C.c_int(rank), C.c_int(nranks), buf))
+        self.rank, self.nranks = rank, nranks
+
+    def comm_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        rc = self.lib.b200md_comm_unique_id(buf)
+        if rc != 0:
+            raise B200MDError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init_torch(self, dist, rank, nranks):
+        """bootstrap through torch.distributed: rank 0 creates the ncclUniqueId, everyone gets it by broadcast"""
+        obj = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        self.comm_init(rank, nranks, obj[0])
+
+    def atoms_download_ids(self, want=("x", "v", "f")):
+        """owned atoms of this rank in device order + their global ids (multi-GPU: atoms migrate between ranks)"""
+        nl, ng = C.c_int(), C.c_int()
+        self._ck(self.lib.b200md_atoms_count(self.h, C.byref(nl), C.byref(ng)))
+        cap = nl.value + 16
+        ids = np.zeros(cap, np.int32)
+        out = {k: np.zeros((cap, 3)) for k in want}
+        n = C.c_int()
+        self._ck(self.lib.b200md_atoms_download_ids(self.h, C.c_int(cap), C.byref(n), _i(ids), _d(out.get("x")),
+                                                    _d(out.get("v")), _d(out.get("f"))))
+        res = {k: v[:n.value] for k, v in out.items()}
+        res["ids"] = ids[:n.value]
+        return res
+
     # ---- timers -------------------------------------------------------------------------------------
     def timers_enable(self, on=True):
         self._ck(self.lib.b200md_timers_enable(self.h, C.c_int(1 if on else 0)))

@@ -78,6 +78,19 @@ int b2_comm_allreduce_max_int(b200md_ctx *ctx, int *dev, int n) {
   return 0;
 }
 
+int b2_comm_allgather_int(b200md_ctx *ctx, int value, int *host_out) {
+  CommState *cs = ctx->comm;
+  if (!cs) { host_out[0] = value; return 0; }
+  DevBuf<int> buf;
+  if (buf.reserve((size_t)cs->nranks + 1)) return b2_fail(ctx, B200MD_ENOMEM, "allgather: out of memory");
+  CUDA_OK(ctx, cudaMemcpyAsync(buf.p + cs->nranks, &value, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_OK(ctx, ncclAllGather(buf.p + cs->nranks, buf.p, 1, ncclInt, cs->comm, ctx->stream));
+  CUDA_OK(ctx, cudaMemcpyAsync(host_out, buf.p, cs->nranks * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  buf.free_();
+  return 0;
+}
+
 // all-to-all with per-peer element counts (bytes) and displacements: the FFT transposes
 int b2_comm_alltoallv(b200md_ctx *ctx, const void *sbuf, const size_t *scount, const size_t *sdisp, void *rbuf,
                       const size_t *rcount, const size_t *rdisp) {
@@ -87,6 +100,29 @@ int b2_comm_alltoallv(b200md_ctx *ctx, const void *sbuf, const size_t *scount, c
     if (scount[p]) NCCL_OK(ctx, ncclSend((const char *)sbuf + sdisp[p], scount[p], ncclChar, p, cs->comm, ctx->stream));
     if (rcount[p]) NCCL_OK(ctx, ncclRecv((char *)rbuf + rdisp[p], rcount[p], ncclChar, p, cs->comm, ctx->stream));
   }
+  NCCL_OK(ctx, ncclGroupEnd());
+  return 0;
+}
+
+CommGroup::CommGroup(b200md_ctx *c) : ctx(c) {
+  if (ctx->comm && ncclGroupStart() == ncclSuccess) open = true;
+}
+CommGroup::~CommGroup() {
+  if (open) ncclGroupEnd();
+}
+int CommGroup::send(const void *buf, size_t bytes, int peer) {
+  if (!open) return b2_fail(ctx, B200MD_ECOMM, "NCCL group is not open");
+  if (bytes) NCCL_OK(ctx, ncclSend(buf, bytes, ncclChar, peer, ctx->comm->comm, ctx->stream));
+  return 0;
+}
+int CommGroup::recv(void *buf, size_t bytes, int peer) {
+  if (!open) return b2_fail(ctx, B200MD_ECOMM, "NCCL group is not open");
+  if (bytes) NCCL_OK(ctx, ncclRecv(buf, bytes, ncclChar, peer, ctx->comm->comm, ctx->stream));
+  return 0;
+}
+int CommGroup::end() {
+  if (!open) return 0;
+  open = false;
   NCCL_OK(ctx, ncclGroupEnd());
   return 0;
 }
@@ -104,6 +140,7 @@ int b200md_comm_unique_id(void *id128) {
 
 int b200md_comm_init(b200md_ctx *ctx, int rank, int nranks, const void *id128) {
   if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return b2_fail(ctx, B200MD_EINVAL, "b200md_comm_init: bad rank");
+  if (nranks > 8) return b2_fail(ctx, B200MD_EINVAL, "b200md_comm_init: at most 8 ranks (one NVSwitch node)");
   cudaSetDevice(ctx->device);
   b2_comm_free(ctx);
   if (nranks == 1) return 0;

@@ -42,13 +42,13 @@ namespace {
 __global__ void pack_atoms(int n, const double *__restrict__ x, const double *__restrict__ v,
                            const double *__restrict__ q, const int *__restrict__ type,
                            double4 *__restrict__ xq, double4 *__restrict__ vv, int *__restrict__ tag,
-                           int *__restrict__ type_out) {
+                           int *__restrict__ type_out, int first_id) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   xq[i] = make_double4(x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2], q ? q[i] : 0.0);
   vv[i] = v ? make_double4(v[3 * (size_t)i], v[3 * (size_t)i + 1], v[3 * (size_t)i + 2], 0.0)
             : make_double4(0.0, 0.0, 0.0, 0.0);
-  tag[i] = i;
+  tag[i] = first_id + i;
   type_out[i] = type[i];
 }
 
@@ -240,9 +240,15 @@ int b200md_atoms_upload(b200md_ctx *ctx, int nlocal, int ntypes, const double *x
   if (v) CUDA_OK(ctx, cudaMemcpyAsync(sv, v, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (q) CUDA_OK(ctx, cudaMemcpyAsync(sq, q, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(ctx, cudaMemcpyAsync(st, type, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->first_id = 0;
+  if (b2_comm_nranks(ctx) > 1) {   // global ids: rank r's atoms follow those of ranks < r
+    std::vector<int> counts(b2_comm_nranks(ctx));
+    TRY(b2_comm_allgather_int(ctx, nlocal, counts.data()));
+    for (int r = 0; r < b2_comm_rank(ctx); r++) ctx->first_id += counts[r];
+  }
   if (nlocal) {
     pack_atoms<<<cdiv(nlocal, 256), 256, 0, ctx->stream>>>(nlocal, sx, v ? sv : nullptr, q ? sq : nullptr, st,
-                                                           ctx->xq.p, ctx->v.p, ctx->tag.p, ctx->type.p);
+                                                           ctx->xq.p, ctx->v.p, ctx->tag.p, ctx->type.p, ctx->first_id);
     KERNEL_OK(ctx, "pack_atoms");
     CUDA_OK(ctx, cudaMemsetAsync(ctx->f.p, 0, n * sizeof(double4), ctx->stream));
   }
@@ -256,6 +262,8 @@ int b200md_atoms_upload(b200md_ctx *ctx, int nlocal, int ntypes, const double *x
 
 int b200md_atoms_set_x(b200md_ctx *ctx, const double *x) {
   if (!ctx || !x) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_x: bad arguments");
+  if (b2_comm_nranks(ctx) > 1)
+    return b2_fail(ctx, B200MD_EINVAL, "host-order access is single-GPU only (atoms migrate between ranks)");
   cudaSetDevice(ctx->device);
   const size_t n = (size_t)ctx->nlocal;
   if (!n) return 0;
@@ -267,9 +275,32 @@ int b200md_atoms_set_x(b200md_ctx *ctx, const double *x) {
   return 0;
 }
 
+int b200md_atoms_download_ids(b200md_ctx *ctx, int capacity, int *n_out, int *ids, double *x, double *v, double *f) {
+  if (!ctx || !n_out) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  const int n = ctx->nlocal;
+  *n_out = n;
+  if (n > capacity) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_download_ids: capacity %d < %d owned atoms", capacity, n);
+  if (!n) return 0;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<double4> h((size_t)n);
+  auto fetch = [&](const double4 *src, double *dst) -> int {
+    CUDA_OK(ctx, cudaMemcpy(h.data(), src, (size_t)n * sizeof(double4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) { dst[3 * (size_t)i] = h[i].x; dst[3 * (size_t)i + 1] = h[i].y; dst[3 * (size_t)i + 2] = h[i].z; }
+    return 0;
+  };
+  if (ids) CUDA_OK(ctx, cudaMemcpy(ids, ctx->tag.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (x) TRY(fetch(ctx->xq.p, x));
+  if (v) TRY(fetch(ctx->v.p, v));
+  if (f) TRY(fetch(ctx->f.p, f));
+  return 0;
+}
+
 int b200md_atoms_download(b200md_ctx *ctx, double *x, double *v, double *f, double *eatom) {
   if (!ctx) return B200MD_EINVAL;
   cudaSetDevice(ctx->device);
+  if (b2_comm_nranks(ctx) > 1)
+    return b2_fail(ctx, B200MD_EINVAL, "host-order download is single-GPU only: use b200md_atoms_download_ids");
   const size_t n = (size_t)ctx->nlocal;
   if (!n) return 0;
   RESERVE(ctx, ctx->stage, 8 * n + 16);

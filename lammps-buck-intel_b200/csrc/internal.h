@@ -94,6 +94,14 @@ struct NeighState {
   DevBuf<int> numneigh;
   DevBuf<long long> offsets;
   DevBuf<int> entries;
+  // multi-GPU (z slabs): halo = owned atoms within cutghost of a slab face, sent to the neighbour rank every step
+  DevBuf<int> halo_idx;           // [ns_lo | ns_hi] owned indices sent to the lower / upper neighbour
+  int ns_lo = 0, ns_hi = 0, nr_lo = 0, nr_hi = 0;   // sent to lower/upper, received from lower/upper
+  DevBuf<double4> halo_sbuf, halo_rbuf;             // rbuf = [from lower | from upper]
+  DevBuf<int> halo_stype, halo_rtype;
+  DevBuf<int> mig_flag, mig_off;                    // migration scratch: 3 flag / 3 offset arrays
+  DevBuf<unsigned char> mig_send, mig_recv;
+  double slab_lo = 0, slab_hi = 0;                  // this rank's z slab
   DevBuf<int> mask_words;         // build scratch: mask words per bin
   DevBuf<long long> mask_off;     // their exclusive scan
   DevBuf<unsigned> maskbuf;       // hit masks [bin][atom][candidate word]
@@ -128,7 +136,8 @@ struct b200md_ctx {
   std::vector<double> mass;
   DevBuf<double4> xq, v, f;
   DevBuf<float4> xqf;
-  DevBuf<int> type, tag, inv_tag;
+  DevBuf<int> type, tag, inv_tag;   // tag: host index of each atom (multi-GPU: global id = first_id + host index)
+  int first_id = 0;                 // multi-GPU: global id of this rank's first uploaded atom
   DevBuf<double> stage;       // staging for host transfers
   double *h_pinned = nullptr; // small pinned scratch (ev partial results, flags)
   size_t h_pinned_bytes = 0;
@@ -244,3 +253,23 @@ int b2_nve_final(b200md_ctx *ctx);
 int b2_kinetic_energy(b200md_ctx *ctx, double *ke);
 // comm.cu
 void b2_comm_free(b200md_ctx *ctx);
+int b2_comm_nranks(const b200md_ctx *ctx);
+int b2_comm_rank(const b200md_ctx *ctx);
+int b2_comm_exchange(b200md_ctx *ctx, const void *s_lo, size_t n_lo, const void *s_hi, size_t n_hi, void *r_from_hi,
+                     size_t n_from_hi, void *r_from_lo, size_t n_from_lo);
+int b2_comm_exchange_counts(b200md_ctx *ctx, int n_lo, int n_hi, int *n_from_hi, int *n_from_lo);
+int b2_comm_allreduce_sum(b200md_ctx *ctx, double *dev, int n);
+int b2_comm_allreduce_max_int(b200md_ctx *ctx, int *dev, int n);
+int b2_comm_allgather_int(b200md_ctx *ctx, int value, int *host_out /*[nranks]*/);
+// grouped point-to-point calls (one NCCL group): several messages per peer are matched in issue order
+struct CommGroup {
+  b200md_ctx *ctx;
+  bool open = false;
+  explicit CommGroup(b200md_ctx *c);
+  ~CommGroup();
+  int send(const void *buf, size_t bytes, int peer);
+  int recv(void *buf, size_t bytes, int peer);
+  int end();
+};
+int b2_comm_alltoallv(b200md_ctx *ctx, const void *sbuf, const size_t *scount, const size_t *sdisp, void *rbuf,
+                      const size_t *rcount, const size_t *rdisp);

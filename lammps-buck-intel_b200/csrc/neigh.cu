@@ -633,7 +633,7 @@ __global__ void k_export_ghosts(int nlocal, int ng, const int *__restrict__ tag,
                                 const int *__restrict__ shift, int *__restrict__ out_src, int *__restrict__ out_shift) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ng) return;
-  out_src[k] = tag[src[k]];
+  out_src[k] = src[k] >= 0 ? tag[src[k]] : -1;   // -1: image of a halo atom owned by a neighbour rank
   const int code = shift[k];
   out_shift[3 * k] = code % 3 - 1;
   out_shift[3 * k + 1] = (code / 3) % 3 - 1;
@@ -646,6 +646,7 @@ int make_geom(b200md_ctx *ctx, BinGeom &g) {
   ns.cutghost = ns.cutneighmax;
   g.cutghost = ns.cutghost;
   const double binsize_optimal = 0.5 * ns.cutneighmax;
+  const int nranks = b2_comm_nranks(ctx), rank = b2_comm_rank(ctx);
   for (int d = 0; d < 3; d++) {
     g.lo[d] = ctx->boxlo[d];
     g.hi[d] = ctx->boxhi[d];
@@ -655,6 +656,18 @@ int make_geom(b200md_ctx *ctx, BinGeom &g) {
     g.whi[d] = ctx->boxhi[d];
     g.wprd[d] = ctx->prd[d];
     g.img[d] = ctx->periodic[d];
+    if (d == 2 && nranks > 1) {
+      // this rank bins its z slab; the shell bins on either side hold the halo atoms of the neighbour ranks (the
+      // z images across the global periodic boundary arrive already shifted)
+      if (!ctx->periodic[2]) return b2_fail(ctx, B200MD_EINVAL, "the z-slab decomposition needs a box periodic in z");
+      const double slab = ctx->prd[2] / nranks;
+      g.lo[2] = ctx->boxlo[2] + rank * slab;
+      g.hi[2] = rank == nranks - 1 ? ctx->boxhi[2] : ctx->boxlo[2] + (rank + 1) * slab;
+      g.prd[2] = g.hi[2] - g.lo[2];
+      g.img[2] = 0;
+      ns.slab_lo = g.lo[2];
+      ns.slab_hi = g.hi[2];
+    }
     if (g.periodic[d] && g.prd[d] < ns.cutghost)
       return b2_fail(ctx, B200MD_EOVERFLOW,
                      "box length %g in dimension %d is shorter than the ghost cutoff %g (multiple periodic "
@@ -692,14 +705,148 @@ int counting_sort(b200md_ctx *ctx, int n, long nbins, const int *keys, int *coun
   return 0;
 }
 
+
+// ---- multi-GPU host logic -------------------------------------------------------------------------------------
+// Comm::exchange: atoms that left this rank's z slab go to the lower / upper neighbour (never further: the rebuild
+// trigger fires long before an atom crosses a whole slab).
+int migrate(b200md_ctx *ctx) {
+  NeighState &ns = ctx->neigh;
+  const int nranks = b2_comm_nranks(ctx), rank = b2_comm_rank(ctx);
+  const int n = ctx->nlocal;
+  const double slab = ctx->prd[2] / nranks;
+  const size_t nn = (size_t)n + 64;
+  RESERVE(ctx, ns.mig_flag, 3 * nn);
+  RESERVE(ctx, ns.mig_off, 3 * (nn + 1));
+  RESERVE(ctx, ns.flags, 16);
+  RESERVE(ctx, ns.scan_ws, b2_scan_ws_bytes(nn + 1));
+  int *f_stay = ns.mig_flag.p, *f_lo = f_stay + nn, *f_hi = f_lo + nn;
+  int *o_stay = ns.mig_off.p, *o_lo = o_stay + nn + 1, *o_hi = o_lo + nn + 1;
+  CUDA_OK(ctx, cudaMemsetAsync(ns.flags.p + 4, 0, sizeof(int), ctx->stream));
+  int cnt[3] = {0, 0, 0};
+  if (n > 0) {
+    k_mig_dest<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, ctx->boxlo[2], 1.0 / slab, rank, nranks, f_stay, f_lo,
+                                                      f_hi, ns.flags.p + 4);
+    KERNEL_OK(ctx, "k_mig_dest");
+    TRY(b2_exclusive_scan_i32(ctx, f_stay, o_stay, (size_t)n, ns.scan_ws.p));
+    TRY(b2_exclusive_scan_i32(ctx, f_lo, o_lo, (size_t)n, ns.scan_ws.p));
+    TRY(b2_exclusive_scan_i32(ctx, f_hi, o_hi, (size_t)n, ns.scan_ws.p));
+    int *hp = (int *)ctx->h_pinned;
+    CUDA_OK(ctx, cudaMemcpyAsync(hp, o_stay + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(hp + 1, o_lo + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(hp + 2, o_hi + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(hp + 3, ns.flags.p + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    cnt[0] = hp[0]; cnt[1] = hp[1]; cnt[2] = hp[2];
+    if (hp[3]) return b2_fail(ctx, B200MD_EOVERFLOW, "an atom moved further than one z slab between two rebuilds");
+  }
+  int from_hi = 0, from_lo = 0;
+  TRY(b2_comm_exchange_counts(ctx, cnt[1], cnt[2], &from_hi, &from_lo));
+  const int nnew = cnt[0] + from_lo + from_hi;
+  const size_t cap = (size_t)nnew + 64;
+  RESERVE(ctx, ns.tmp4a, cap);
+  RESERVE(ctx, ns.tmp4b, cap);
+  RESERVE(ctx, ns.tmpi_a, cap);
+  RESERVE(ctx, ns.tmpi_b, cap);
+  RESERVE(ctx, ns.mig_send, (size_t)(cnt[1] + cnt[2] + 2) * sizeof(MigAtom));
+  RESERVE(ctx, ns.mig_recv, (size_t)(from_lo + from_hi + 2) * sizeof(MigAtom));
+  MigAtom *s_lo = (MigAtom *)ns.mig_send.p, *s_hi = s_lo + cnt[1];
+  MigAtom *r_lo = (MigAtom *)ns.mig_recv.p, *r_hi = r_lo + from_lo;
+  if (n > 0) {
+    k_mig_pack<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, f_stay, f_lo, o_stay, o_lo, o_hi, ctx->xq.p, ctx->v.p, ctx->type.p,
+                                                      ctx->tag.p, ns.tmp4a.p, ns.tmp4b.p, ns.tmpi_a.p, ns.tmpi_b.p, s_lo,
+                                                      s_hi);
+    KERNEL_OK(ctx, "k_mig_pack");
+  }
+  TRY(b2_comm_exchange(ctx, s_lo, (size_t)cnt[1] * sizeof(MigAtom), s_hi, (size_t)cnt[2] * sizeof(MigAtom), r_hi,
+                       (size_t)from_hi * sizeof(MigAtom), r_lo, (size_t)from_lo * sizeof(MigAtom)));
+  if (from_lo + from_hi > 0) {
+    k_mig_unpack<<<cdiv(from_lo + from_hi, 256), 256, 0, ctx->stream>>>(from_lo + from_hi, r_lo, cnt[0], ns.tmp4a.p,
+                                                                        ns.tmp4b.p, ns.tmpi_a.p, ns.tmpi_b.p);
+    KERNEL_OK(ctx, "k_mig_unpack");
+  }
+  std::swap(ctx->xq, ns.tmp4a);
+  std::swap(ctx->v, ns.tmp4b);
+  std::swap(ctx->type, ns.tmpi_a);
+  std::swap(ctx->tag, ns.tmpi_b);
+  ctx->nlocal = nnew;
+  return 0;
+}
+
+// Comm::borders along z: owned atoms within cutghost of a slab face go to that neighbour; index lists are kept for
+// the per-step forward communication.  rbuf = [from lower | from upper].
+int halo_setup(b200md_ctx *ctx, const BinGeom &g) {
+  NeighState &ns = ctx->neigh;
+  const int n = ctx->nlocal;
+  const size_t nn = (size_t)n + 64;
+  RESERVE(ctx, ns.mig_flag, 3 * nn);
+  RESERVE(ctx, ns.mig_off, 3 * (nn + 1));
+  int *f_lo = ns.mig_flag.p, *f_hi = f_lo + nn;
+  int *o_lo = ns.mig_off.p, *o_hi = o_lo + nn + 1;
+  ns.ns_lo = ns.ns_hi = 0;
+  if (n > 0) {
+    k_halo_flag<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, g.lo[2] + g.cutghost, g.hi[2] - g.cutghost, f_lo, f_hi);
+    KERNEL_OK(ctx, "k_halo_flag");
+    TRY(b2_exclusive_scan_i32(ctx, f_lo, o_lo, (size_t)n, ns.scan_ws.p));
+    TRY(b2_exclusive_scan_i32(ctx, f_hi, o_hi, (size_t)n, ns.scan_ws.p));
+    int *hp = (int *)ctx->h_pinned;
+    CUDA_OK(ctx, cudaMemcpyAsync(hp, o_lo + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(hp + 1, o_hi + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    ns.ns_lo = hp[0];
+    ns.ns_hi = hp[1];
+    RESERVE(ctx, ns.halo_idx, (size_t)ns.ns_lo + ns.ns_hi + 64);
+    k_compact_idx<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, f_lo, o_lo, ns.halo_idx.p);
+    KERNEL_OK(ctx, "k_compact_idx");
+    k_compact_idx<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, f_hi, o_hi, ns.halo_idx.p + ns.ns_lo);
+    KERNEL_OK(ctx, "k_compact_idx");
+  }
+  TRY(b2_comm_exchange_counts(ctx, ns.ns_lo, ns.ns_hi, &ns.nr_hi, &ns.nr_lo));
+  RESERVE(ctx, ns.halo_sbuf, (size_t)ns.ns_lo + ns.ns_hi + 64);
+  RESERVE(ctx, ns.halo_stype, (size_t)ns.ns_lo + ns.ns_hi + 64);
+  RESERVE(ctx, ns.halo_rbuf, (size_t)ns.nr_lo + ns.nr_hi + 64);
+  RESERVE(ctx, ns.halo_rtype, (size_t)ns.nr_lo + ns.nr_hi + 64);
+  return 0;
+}
+
+// Comm::forward_comm along z: positions (and, at build time, types) of the halo atoms; atoms sent across the global
+// periodic boundary are shifted by one box length so that they arrive as the right image
+int halo_exchange(b200md_ctx *ctx, int with_type) {
+  NeighState &ns = ctx->neigh;
+  const int nranks = b2_comm_nranks(ctx), rank = b2_comm_rank(ctx);
+  const double shift_lo = rank == 0 ? ctx->prd[2] : 0.0;             // to the lower neighbour (wraps for rank 0)
+  const double shift_hi = rank == nranks - 1 ? -ctx->prd[2] : 0.0;   // to the upper neighbour
+  if (ns.ns_lo > 0) {
+    k_halo_pack<<<cdiv(ns.ns_lo, 256), 256, 0, ctx->stream>>>(ns.ns_lo, ns.halo_idx.p, ctx->xq.p, shift_lo, ns.halo_sbuf.p,
+                                                              ctx->type.p, with_type ? ns.halo_stype.p : nullptr);
+    KERNEL_OK(ctx, "k_halo_pack");
+  }
+  if (ns.ns_hi > 0) {
+    k_halo_pack<<<cdiv(ns.ns_hi, 256), 256, 0, ctx->stream>>>(ns.ns_hi, ns.halo_idx.p + ns.ns_lo, ctx->xq.p, shift_hi,
+                                                              ns.halo_sbuf.p + ns.ns_lo, ctx->type.p,
+                                                              with_type ? ns.halo_stype.p + ns.ns_lo : nullptr);
+    KERNEL_OK(ctx, "k_halo_pack");
+  }
+  TRY(b2_comm_exchange(ctx, ns.halo_sbuf.p, (size_t)ns.ns_lo * sizeof(double4), ns.halo_sbuf.p + ns.ns_lo,
+                       (size_t)ns.ns_hi * sizeof(double4), ns.halo_rbuf.p + ns.nr_lo, (size_t)ns.nr_hi * sizeof(double4),
+                       ns.halo_rbuf.p, (size_t)ns.nr_lo * sizeof(double4)));
+  if (with_type)
+    TRY(b2_comm_exchange(ctx, ns.halo_stype.p, (size_t)ns.ns_lo * sizeof(int), ns.halo_stype.p + ns.ns_lo,
+                         (size_t)ns.ns_hi * sizeof(int), ns.halo_rtype.p + ns.nr_lo, (size_t)ns.nr_hi * sizeof(int),
+                         ns.halo_rtype.p, (size_t)ns.nr_lo * sizeof(int)));
+  return 0;
+}
+
 }  // namespace
 
 int b2_ghost_refresh(b200md_ctx *ctx) {
   NeighState &ns = ctx->neigh;
+  const bool multi = b2_comm_nranks(ctx) > 1;
+  if (multi) TRY(halo_exchange(ctx, 0));   // every rank takes part, with or without ghosts of its own
   if (ctx->nghost == 0) return 0;
   k_ghost_refresh<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
       ctx->nlocal, ctx->nghost, ns.ghost_src.p, ns.ghost_shift.p, ctx->prd[0], ctx->prd[1], ctx->prd[2],
-      ctx->xq.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 0, nullptr, nullptr);
+      ctx->xq.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 0,
+      multi ? ns.halo_rbuf.p : nullptr, multi ? ns.halo_rtype.p : nullptr);
   KERNEL_OK(ctx, "k_ghost_refresh");
   return 0;
 }
@@ -711,6 +858,15 @@ int b2_neigh_build(b200md_ctx *ctx) {
   ScopedTimer tm(ctx, T_NEIGH);
   BinGeom g;
   TRY(make_geom(ctx, g));
+  const bool multi = b2_comm_nranks(ctx) > 1;
+  if (multi) {
+    // Domain::pbc in the global box, then Comm::exchange between the z slabs
+    if (ctx->nlocal > 0) {
+      k_wrap_bin<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->xq.p, g, 1, nullptr, nullptr);
+      KERNEL_OK(ctx, "k_wrap_bin");
+    }
+    TRY(migrate(ctx));
+  }
   const int n = ctx->nlocal;
   const long nb = ns.nbins_tot;
   const size_t nmax = (size_t)n + 64;
@@ -758,7 +914,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
 
   // 1. wrap + bin owned atoms, stable counting sort, permute the resident arrays
   if (n > 0) {
-    k_wrap_bin<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, g, 1, ns.bin_of.p, lcount);
+    k_wrap_bin<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->xq.p, g, multi ? 0 : 1, ns.bin_of.p, lcount);
     KERNEL_OK(ctx, "k_wrap_bin");
   }
   TRY(counting_sort(ctx, n, nb, ns.bin_of.p, lcount, lstart, ns.bin_cursor.p, ns.perm.p));
@@ -773,13 +929,27 @@ int b2_neigh_build(b200md_ctx *ctx) {
     std::swap(ctx->tag, ns.tmpi_b);
   }
 
-  // 2. periodic ghost atoms: count / scan / fill, then sort the ghosts by bin too
+  // 2. ghost atoms: (multi-GPU) z halo from the neighbour ranks, then periodic images of owned + halo atoms;
+  //    count / scan / fill, then sort the ghosts by bin too
+  int nbase = n;
+  const double4 *rbuf = nullptr;
+  const int *rtype = nullptr;
+  if (multi) {
+    TRY(halo_setup(ctx, g));
+    TRY(halo_exchange(ctx, 1));
+    nbase = n + ns.nr_lo + ns.nr_hi;
+    rbuf = ns.halo_rbuf.p;
+    rtype = ns.halo_rtype.p;
+    RESERVE(ctx, ns.ghost_cnt, (size_t)nbase + 64);
+    RESERVE(ctx, ns.goff, (size_t)nbase + 64);
+    RESERVE(ctx, ns.scan_ws, b2_scan_ws_bytes((size_t)nbase + 64));
+  }
   int ng = 0;
-  if (n > 0) {
-    k_ghost_count<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, n, ctx->xq.p, nullptr, g, ns.ghost_cnt.p);
+  if (nbase > 0) {
+    k_ghost_count<<<cdiv(nbase, 256), 256, 0, ctx->stream>>>(n, nbase, ctx->xq.p, rbuf, g, ns.ghost_cnt.p);
     KERNEL_OK(ctx, "k_ghost_count");
-    TRY(b2_exclusive_scan_i32(ctx, ns.ghost_cnt.p, ns.goff.p, (size_t)n, ns.scan_ws.p));
-    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.goff.p + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(b2_exclusive_scan_i32(ctx, ns.ghost_cnt.p, ns.goff.p, (size_t)nbase, ns.scan_ws.p));
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.goff.p + nbase, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     ng = *(int *)ctx->h_pinned;
   }
@@ -796,8 +966,8 @@ int b2_neigh_build(b200md_ctx *ctx) {
     RESERVE(ctx, ns.gperm, (size_t)ng);
     RESERVE(ctx, ns.ghost_src, (size_t)ng);
     RESERVE(ctx, ns.ghost_shift, (size_t)ng);
-    k_ghost_fill<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, n, ctx->xq.p, nullptr, ns.bin_sorted.p, g, ns.goff.p,
-                                                        ns.gsrc_tmp.p, ns.gshift_tmp.p, ns.gbin.p, gcount);
+    k_ghost_fill<<<cdiv(nbase, 256), 256, 0, ctx->stream>>>(n, nbase, ctx->xq.p, rbuf, ns.bin_sorted.p, g, ns.goff.p,
+                                                            ns.gsrc_tmp.p, ns.gshift_tmp.p, ns.gbin.p, gcount);
     KERNEL_OK(ctx, "k_ghost_fill");
   }
   TRY(counting_sort(ctx, ng, nb, ns.gbin.p, gcount, gstart, ns.bin_cursor.p, ns.gperm.p));
@@ -807,7 +977,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
     KERNEL_OK(ctx, "k_ghost_permute");
     k_ghost_refresh<<<cdiv(ng, 256), 256, 0, ctx->stream>>>(
         n, ng, ns.ghost_src.p, ns.ghost_shift.p, ctx->prd[0], ctx->prd[1], ctx->prd[2], ctx->xq.p,
-        ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 1, nullptr, nullptr);
+        ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr, ctx->type.p, 1, rbuf, rtype);
     KERNEL_OK(ctx, "k_ghost_refresh");
   }
   TRY(b2_refresh_float_copy(ctx, 0, n));
@@ -869,11 +1039,15 @@ int b2_neigh_build(b200md_ctx *ctx) {
 int b2_neigh_check_trigger(b200md_ctx *ctx, int *trigger) {
   NeighState &ns = ctx->neigh;
   *trigger = 0;
-  if (ctx->nlocal == 0) return 0;
+  if (ctx->nlocal == 0 && b2_comm_nranks(ctx) == 1) return 0;
+  RESERVE(ctx, ns.flags, 16);
   CUDA_OK(ctx, cudaMemsetAsync(ns.flags.p, 0, sizeof(int), ctx->stream));
-  k_check_disp<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->xq.p, ns.xhold.p,
-                                                                0.25 * ns.skin * ns.skin, ns.flags.p);
-  KERNEL_OK(ctx, "k_check_disp");
+  if (ctx->nlocal > 0) {
+    k_check_disp<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->xq.p, ns.xhold.p,
+                                                                  0.25 * ns.skin * ns.skin, ns.flags.p);
+    KERNEL_OK(ctx, "k_check_disp");
+  }
+  TRY(b2_comm_allreduce_max_int(ctx, ns.flags.p, 1));   // every rank rebuilds when any rank must
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *trigger = *(int *)ctx->h_pinned;

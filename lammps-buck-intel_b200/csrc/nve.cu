@@ -112,15 +112,18 @@ int b2_nve_final(b200md_ctx *ctx) {
 
 int b2_kinetic_energy(b200md_ctx *ctx, double *ke) {
   *ke = 0.0;
-  if (ctx->nlocal == 0) return 0;
+  if (ctx->nlocal == 0 && b2_comm_nranks(ctx) == 1) return 0;
   double *dmass;
   TRY(upload_mass(ctx, &dmass));
   const int nb = cdiv(ctx->nlocal, 256);
-  RESERVE(ctx, ctx->ev_partial, (size_t)nb);
-  k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->type.p, dmass, ctx->ev_partial.p);
-  KERNEL_OK(ctx, "k_ke_partial");
+  RESERVE(ctx, ctx->ev_partial, (size_t)nb + 1);
+  if (nb > 0) {
+    k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->type.p, dmass, ctx->ev_partial.p);
+    KERNEL_OK(ctx, "k_ke_partial");
+  }
   k_sum1<<<1, 256, 0, ctx->stream>>>(nb, ctx->ev_partial.p, ctx->ev_out.p + 8);
   KERNEL_OK(ctx, "k_sum1");
+  TRY(b2_comm_allreduce_sum(ctx, ctx->ev_out.p + 8, 1));
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->ev_out.p + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *ke = ctx->h_pinned[0];

@@ -67,7 +67,10 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev) {
   // lists built on the device carry no special-bond bits (atomic systems)
   if (ctx->prec == B200MD_PREC_MIXED) TRY(b2_launch_pair_float(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, 0));
   else TRY(b2_launch_pair_double(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, 0));
-  if (evflag) TRY(finish_ev(ctx, eflag, vflag, ev));
+  if (evflag) {
+    TRY(b2_comm_allreduce_sum(ctx, ctx->ev_out.p, 8));   // global tallies over the ranks (no-op on one GPU)
+    TRY(finish_ev(ctx, eflag, vflag, ev));
+  }
   return 0;
 }
 

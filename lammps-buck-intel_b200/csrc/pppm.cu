@@ -52,11 +52,12 @@ __device__ __forceinline__ double d_gf_denom(const PppmConst &c, double x, doubl
 }
 
 // PPPM::compute_gf_ik
-__global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, double *__restrict__ greensfn) {
+// (yoff, nyl): the y rows this rank holds in the z-pencil layout [z][y local][x]; (0, ny) on one GPU
+__global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, int yoff, int nyl, double *__restrict__ greensfn) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
+  const long nfft = (long)c.nx * nyl * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % nyl) + yoff, m = (int)(n / ((long)c.nx * nyl));
   const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
   const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
@@ -143,11 +144,11 @@ __global__ void k_gf_ad(PppmConst c, double *__restrict__ greensfn, double *__re
 
 // PPPMDisp::compute_gf_6 [UPSTREAM]: influence function of the r^-6 reciprocal sum (c.g_ewald = g_ewald_6).  Used by
 // the geometric-mixing grid of PPPMDispIntel::compute (pppm_disp_intel.cpp:245-313).
-__global__ void k_gf_6(PppmConst c, double *__restrict__ greensfn) {
+__global__ void k_gf_6(PppmConst c, int yoff, int nyl, double *__restrict__ greensfn) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
+  const long nfft = (long)c.nx * nyl * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % nyl) + yoff, m = (int)(n / ((long)c.nx * nyl));
   const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
   const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
@@ -232,7 +233,7 @@ __device__ __forceinline__ void map_atom(const PppmConst &c, flt_t x, flt_t y, f
   const flt_t fshift = (flt_t)c.shift;
   nx = map1(x, (flt_t)c.boxlo[0], (flt_t)c.delinv[0], fshift);
   ny = map1(y, (flt_t)c.boxlo[1], (flt_t)c.delinv[1], fshift);
-  nz = map1(z, (flt_t)c.boxlo[2], (flt_t)c.delinv[2], fshift);
+  nz = map1(z, (flt_t)c.boxlo[2], (flt_t)c.delinv[2], fshift) - c.zoff;   // local plane index (zoff = 0 on one GPU)
 }
 // dx = nx + fshiftone - (x - lo)*xi (pppm_intel.cpp:469-471), operands in flt_t
 __device__ __forceinline__ double frac1(int n, double so, double x, double lo, double xi) {
@@ -306,7 +307,7 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
     const float so = (float)c.shiftone;
     dx = frac1(nx, so, p.x, (float)c.boxlo[0], (float)c.delinv[0]);
     dy = frac1(ny, so, p.y, (float)c.boxlo[1], (float)c.delinv[1]);
-    dz = frac1(nz, so, p.z, (float)c.boxlo[2], (float)c.delinv[2]);
+    dz = frac1(nz + c.zoff, so, p.z, (float)c.boxlo[2], (float)c.delinv[2]);
     const float qw = Btype ? (float)Btype[type[i]] : p.w;
     w = (double)__fmul_rn((float)c.delvolinv, qw);
   } else {
@@ -314,7 +315,7 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
     map_atom<double>(c, p.x, p.y, p.z, nx, ny, nz);
     dx = frac1(nx, c.shiftone, p.x, c.boxlo[0], c.delinv[0]);
     dy = frac1(ny, c.shiftone, p.y, c.boxlo[1], c.delinv[1]);
-    dz = frac1(nz, c.shiftone, p.z, c.boxlo[2], c.delinv[2]);
+    dz = frac1(nz + c.zoff, c.shiftone, p.z, c.boxlo[2], c.delinv[2]);
     w = c.delvolinv * (Btype ? Btype[type[i]] : p.w);
   }
   pa_x[k] = make_double4(dx, dy, dz, w);
@@ -610,6 +611,49 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU helpers: plane copies for the halos and pack/unpack for the two transposes
+
+// dst[(p0 + p) * plane + i] (+)= src[(s0 + p) * plane + i] for p < np
+template <int ADD>
+__global__ void k_planes(long plane, int np, const double *__restrict__ src, int s0, double *__restrict__ dst, int d0) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= plane * np) return;
+  const long p = t / plane, i = t - p * plane;
+  const double v = src[(s0 + p) * plane + i];
+  if (ADD) dst[(d0 + p) * plane + i] += v;
+  else dst[(d0 + p) * plane + i] = v;
+}
+
+// z-slab [nzo][ny][nx] -> per-destination blocks [q][nzo][nyl_q][nx] (block q starts at boff[q] elements)
+struct RankRows { int ylo[8], yhi[8]; long boff[8]; int n; };
+__global__ void k_tr_pack(int nx, int ny, int nzo, RankRows rr, const double2 *__restrict__ in, double2 *__restrict__ out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long tot = (long)nx * ny * nzo;
+  if (t >= tot) return;
+  const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / ((long)nx * ny));
+  int q = 0;
+  while (y >= rr.yhi[q]) q++;
+  const int nyl = rr.yhi[q] - rr.ylo[q];
+  out[rr.boff[q] + ((long)z * nyl + (y - rr.ylo[q])) * nx + x] = in[t];
+}
+// received blocks [p][ncomp][nzo][nyl_p][nx] -> [ncomp][nzo][ny][nx]
+__global__ void k_tr_unpack(int nx, int ny, int nzo, int ncomp, RankRows rr, const double2 *__restrict__ in,
+                            double2 *__restrict__ out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long slab = (long)nx * ny * nzo;
+  if (t >= slab * ncomp) return;
+  const int comp = (int)(t / slab);
+  const long r = t - comp * slab;
+  const int x = (int)(r % nx), y = (int)((r / nx) % ny), z = (int)(r / ((long)nx * ny));
+  int p = 0;
+  while (y >= rr.yhi[p]) p++;
+  const int nyl = rr.yhi[p] - rr.ylo[p];
+  // rr.boff[p]: start of rank p's data (all components); one component of it is nzo*nyl*nx elements
+  out[t] = in[rr.boff[p] + (long)comp * nzo * nyl * nx + ((long)z * nyl + (y - rr.ylo[p])) * nx + x];
+}
+
 // ---------------------------------------------------------------------------------------------
 // host helpers
 
@@ -710,12 +754,171 @@ void compute_gf_denom(PppmConst &c) {
   for (int l = 0; l < order; l++) c.gf_b[l] *= gaminv;
 }
 
-int fft3d_forward_xy(b200md_ctx *ctx, PppmState &ps, const double *density, double2 *work) {
+int fft3d_forward_xy(b200md_ctx *ctx, PppmState &ps, const double *density, double2 *work, int nplanes) {
   const PppmConst &c = ps.c;
-  PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1};
+  PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1};
   TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD)));
-  PassGeom gy{(long)c.nx * c.nz, c.nx, (long)c.nx * c.ny, (long)c.nx};
+  PassGeom gy{(long)c.nx * nplanes, c.nx, (long)c.nx * c.ny, (long)c.nx};
   TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work, work, nullptr, S_FWD)));
+  return 0;
+}
+
+
+// Poisson solve on nranks GPUs.  In: ps.density = local brick [c.nz][ny][nx].  Out: ps.vd = [ncomp][c.nz][ny][nx]
+// (the local brick of every field component, halos filled), evsum[7] = global energy / virial sums when ev.
+int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
+  const PppmConst &c = ps.c;
+  const int P = ps.nranks, me = ps.rank, lower = (me + P - 1) % P, upper = (me + 1) % P;
+  const int nx = c.nx, ny = c.ny, gnz = ps.gnz;
+  const long plane = (long)nx * ny;
+  const int nzo = ps.pzhi[me] - ps.pzlo[me];
+  const int ncomp = 3;
+  // halo widths: planes of a rank's brick below / above its owned range
+  auto lo_w = [&](int r) { return ps.pzlo[r] - ps.zoffs[r]; };
+  auto hi_w = [&](int r) { return ps.zoffs[r] + ps.nbzs[r] - ps.pzhi[r]; };
+  const int my_lo = lo_w(me), my_hi = hi_w(me);
+  const int up_lo = lo_w(upper), low_hi = hi_w(lower);   // what I receive: upper's low halo, lower's high halo
+  int nblk_z = 0;
+  {
+    ScopedTimer tm(ctx, T_COMM);
+    // ---- density halo sum (reverse comm): send my halo planes, add the neighbours' into my owned planes ---------
+    RESERVE(ctx, ps.dens_own, (size_t)plane * nzo);
+    RESERVE(ctx, ps.halo_r, (size_t)plane * std::max(up_lo + low_hi, my_lo + my_hi) * ncomp + 16);
+    const int nb = 256;
+    k_planes<0><<<cdiv(plane * nzo, nb), nb, 0, ctx->stream>>>(plane, nzo, ps.density.p, my_lo, ps.dens_own.p, 0);
+    KERNEL_OK(ctx, "k_planes");
+    // to lower: my planes [0, my_lo); to upper: my planes [my_lo + nzo, c.nz) — both contiguous in the brick
+    TRY(b2_comm_exchange(ctx, ps.density.p, (size_t)plane * my_lo * sizeof(double),
+                         ps.density.p + plane * (my_lo + nzo), (size_t)plane * my_hi * sizeof(double),
+                         ps.halo_r.p + plane * low_hi, (size_t)plane * up_lo * sizeof(double), ps.halo_r.p,
+                         (size_t)plane * low_hi * sizeof(double)));
+    if (low_hi > 0) {   // the lower rank's high halo covers my first low_hi owned planes
+      k_planes<1><<<cdiv(plane * low_hi, nb), nb, 0, ctx->stream>>>(plane, low_hi, ps.halo_r.p, 0, ps.dens_own.p, 0);
+      KERNEL_OK(ctx, "k_planes");
+    }
+    if (up_lo > 0) {    // the upper rank's low halo covers my last up_lo owned planes
+      k_planes<1><<<cdiv(plane * up_lo, nb), nb, 0, ctx->stream>>>(plane, up_lo, ps.halo_r.p, low_hi, ps.dens_own.p,
+                                                                  nzo - up_lo);
+      KERNEL_OK(ctx, "k_planes");
+    }
+  }
+  RankRows rr;
+  rr.n = P;
+  const int nyl = ps.yhis[me] - ps.ylos[me];
+  const long nT = (long)nx * nyl * gnz;   // points of my z-pencil block
+  {
+    ScopedTimer tm(ctx, T_FFT);
+    // ---- forward x, y on the owned planes -------------------------------------------------------------------------
+    RESERVE(ctx, ps.work1, (size_t)plane * nzo);
+    TRY(fft3d_forward_xy(ctx, ps, ps.dens_own.p, ps.work1.p, nzo));
+    // ---- transpose to z pencils: block for rank q = my planes x q's rows; lands at q in [z][row][x] order ---------
+    RESERVE(ctx, ps.tsend, (size_t)plane * nzo);
+    RESERVE(ctx, ps.workT, (size_t)nT);
+    RESERVE(ctx, ps.workT2, (size_t)nT * ncomp);
+    size_t scount[8], sdisp[8], rcount[8], rdisp[8];
+    long off = 0;
+    for (int q = 0; q < P; q++) {
+      rr.ylo[q] = ps.ylos[q]; rr.yhi[q] = ps.yhis[q]; rr.boff[q] = off;
+      const long cnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * nx;
+      scount[q] = cnt * sizeof(double2); sdisp[q] = off * sizeof(double2);
+      off += cnt;
+      rcount[q] = (size_t)(ps.pzhi[q] - ps.pzlo[q]) * nyl * nx * sizeof(double2);
+      rdisp[q] = (size_t)ps.pzlo[q] * nyl * nx * sizeof(double2);
+    }
+    k_tr_pack<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, rr, ps.work1.p, ps.tsend.p);
+    KERNEL_OK(ctx, "k_tr_pack");
+    TRY(b2_comm_alltoallv(ctx, ps.tsend.p, scount, sdisp, ps.workT.p, rcount, rdisp));
+    // ---- z pass + Green's function + gradients + inverse z on my pencils ------------------------------------------
+    const int TB = pick_tb(gnz, 3);
+    const int LP = gnz | 1;
+    const size_t smem = 3 * (size_t)TB * LP * sizeof(double2);
+    nblk_z = cdiv((long)nx * nyl, TB);
+    const double scaleinv = 1.0 / ((double)nx * ny * gnz);
+    if (ev) RESERVE(ctx, ps.partial, (size_t)std::max(nblk_z, 1) * 8);
+    if (nblk_z > 0) {
+#define ZK(E)                                                                                                   \
+  do {                                                                                                          \
+    auto kern = k_fft_z_poisson<3, E>;                                                                          \
+    CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    kern<<<nblk_z, 256, smem, ctx->stream>>>(ps.plan[2], nx, nyl, TB, LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
+                                             ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, scaleinv, c.g_ewald,   \
+                                             ps.partial.p, ps.p.dispersion);                                    \
+  } while (0)
+      if (ev) ZK(1); else ZK(0);
+#undef ZK
+      KERNEL_OK(ctx, "k_fft_z_poisson");
+    }
+    // ---- transpose back, all components in one exchange: to rank q its planes (contiguous in [z][row][x]) ---------
+    RESERVE(ctx, ps.trecv, (size_t)plane * nzo * ncomp);
+    {
+      CommGroup grp(ctx);
+      long roff = 0;
+      for (int q = 0; q < P; q++) {
+        const long scnt = (long)(ps.pzhi[q] - ps.pzlo[q]) * nyl * nx;
+        const long rcnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * nx;
+        rr.boff[q] = roff;
+        for (int comp = 0; comp < ncomp; comp++) {
+          TRY(grp.send(ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * nx, scnt * sizeof(double2), q));
+          TRY(grp.recv(ps.trecv.p + roff + (size_t)comp * rcnt, rcnt * sizeof(double2), q));
+        }
+        roff += rcnt * ncomp;
+      }
+      TRY(grp.end());
+    }
+    RESERVE(ctx, ps.work2, (size_t)plane * nzo * ncomp);
+    k_tr_unpack<<<cdiv(plane * nzo * ncomp, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, ncomp, rr, ps.trecv.p, ps.work2.p);
+    KERNEL_OK(ctx, "k_tr_unpack");
+    // ---- inverse y, x on the owned planes; the x pass keeps the real part -----------------------------------------
+    RESERVE(ctx, ps.vd_own, (size_t)plane * nzo * ncomp);
+    PassGeom gy{(long)nx * nzo * ncomp, nx, plane, (long)nx};
+    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
+    PassGeom gx{(long)ny * nzo * ncomp, 1, (long)nx, 1};
+    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+  }
+  {
+    ScopedTimer tm(ctx, T_COMM);
+    // ---- field halo fill (forward comm): my boundary owned planes go out, the brick is assembled ------------------
+    // lower needs its high halo = my first low_hi owned planes; upper needs its low halo = my last up_lo planes
+    const long bplane = plane * c.nz;   // one component of the local brick
+    RESERVE(ctx, ps.vd, (size_t)bplane * ncomp);
+    RESERVE(ctx, ps.halo_s, (size_t)plane * (low_hi + up_lo) * ncomp + 16);
+    const int nb = 256;
+    for (int comp = 0; comp < ncomp; comp++) {
+      const double *own = ps.vd_own.p + (size_t)comp * plane * nzo;
+      if (low_hi > 0) k_planes<0><<<cdiv(plane * low_hi, nb), nb, 0, ctx->stream>>>(plane, low_hi, own, 0, ps.halo_s.p, comp * low_hi);
+      if (up_lo > 0)
+        k_planes<0><<<cdiv(plane * up_lo, nb), nb, 0, ctx->stream>>>(plane, up_lo, own, nzo - up_lo,
+                                                                    ps.halo_s.p + plane * low_hi * ncomp, comp * up_lo);
+      k_planes<0><<<cdiv(plane * nzo, nb), nb, 0, ctx->stream>>>(plane, nzo, own, 0, ps.vd.p + (size_t)comp * bplane, my_lo);
+      ctx->launches += 3;
+    }
+    // receive: from upper -> my high halo (my_hi planes per component), from lower -> my low halo (my_lo planes)
+    TRY(b2_comm_exchange(ctx, ps.halo_s.p, (size_t)plane * low_hi * ncomp * sizeof(double),
+                         ps.halo_s.p + plane * low_hi * ncomp, (size_t)plane * up_lo * ncomp * sizeof(double),
+                         ps.halo_r.p + plane * my_lo * ncomp, (size_t)plane * my_hi * ncomp * sizeof(double), ps.halo_r.p,
+                         (size_t)plane * my_lo * ncomp * sizeof(double)));
+    for (int comp = 0; comp < ncomp; comp++) {
+      double *brick = ps.vd.p + (size_t)comp * bplane;
+      if (my_lo > 0) k_planes<0><<<cdiv(plane * my_lo, nb), nb, 0, ctx->stream>>>(plane, my_lo, ps.halo_r.p, comp * my_lo, brick, 0);
+      if (my_hi > 0)
+        k_planes<0><<<cdiv(plane * my_hi, nb), nb, 0, ctx->stream>>>(plane, my_hi, ps.halo_r.p + plane * my_lo * ncomp,
+                                                                    comp * my_hi, brick, my_lo + nzo);
+      ctx->launches += 2;
+    }
+    CUDA_OK(ctx, cudaGetLastError());
+  }
+  if (ev) {
+    ScopedTimer tm(ctx, T_POISSON);
+    RESERVE(ctx, ps.red, 16);
+    if (nblk_z > 0) {
+      k_colsum_final<<<1, 256, 0, ctx->stream>>>(nblk_z, 7, ps.partial.p, ps.red.p);
+      KERNEL_OK(ctx, "k_colsum_final");
+    } else CUDA_OK(ctx, cudaMemsetAsync(ps.red.p, 0, 8 * sizeof(double), ctx->stream));
+    TRY(b2_comm_allreduce_sum(ctx, ps.red.p, 7));   // MPI_Allreduce of energy and virial, pppm_intel.cpp:260,273
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 7; k++) evsum[k] = ctx->h_pinned[k];
+  }
   return 0;
 }
 
@@ -731,8 +934,9 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   if (energy) *energy = 0.0;
   if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
 
-  // qsum_qsq when the atom count changed (pppm_intel.cpp:142-145)
-  if (ps.q_natoms != n) {
+  // qsum_qsq when the atom count changed (pppm_intel.cpp:142-145).  Multi-GPU: the local count changes with every
+  // migration but the global sums do not, and the reduction is collective: done once per setup.
+  if (ps.nranks > 1 ? ps.q_natoms < 0 : ps.q_natoms != n) {
     RESERVE(ctx, ps.density, std::max((size_t)nfft, 2 * (size_t)n + 2));
     if (n > 0) {
       k_q_moments<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.type, ps.p.dispersion ? ps.Btype.p : nullptr,
@@ -743,6 +947,16 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
       ps.qsum = m[0];
       ps.qsqsum = m[1];
     } else ps.qsum = ps.qsqsum = 0.0;
+    if (ps.nranks > 1) {
+      RESERVE(ctx, ps.red, 16);
+      const double m2[2] = {ps.qsum, ps.qsqsum};
+      CUDA_OK(ctx, cudaMemcpyAsync(ps.red.p, m2, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      TRY(b2_comm_allreduce_sum(ctx, ps.red.p, 2));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+      ps.qsum = ctx->h_pinned[0];
+      ps.qsqsum = ctx->h_pinned[1];
+    }
     ps.q_natoms = n;
   }
   if (ps.qsqsum == 0.0) return 0;  // "return if there are no charges" :149
@@ -805,9 +1019,13 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   // ---- poisson: forward FFT, Green's function, gradients, inverse FFTs -------------------------------
   const int ev = (eflag_global || vflag_global) ? 1 : 0;
   int nblk_z = 0;
+  double evsum[8] = {0};
+  if (ps.nranks > 1) {
+    TRY(poisson_multi(ctx, ps, ev, evsum));
+  } else {
   {
     ScopedTimer tm(ctx, T_FFT);
-    TRY(fft3d_forward_xy(ctx, ps, ps.density.p, ps.work1.p));
+    TRY(fft3d_forward_xy(ctx, ps, ps.density.p, ps.work1.p, c.nz));
     const int TB = pick_tb(c.nz, 3);
     const int LP = c.nz | 1;
     const size_t smem = 3 * (size_t)TB * LP * sizeof(double2);
@@ -833,7 +1051,6 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     PassGeom gx{(long)c.ny * c.nz * ncomp, 1, (long)c.nx, 1};
     TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
   }
-  double evsum[8] = {0};
   if (ev) {
     ScopedTimer tm(ctx, T_POISSON);
     RESERVE(ctx, ps.red, 16);
@@ -842,6 +1059,7 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < 7; k++) evsum[k] = ctx->h_pinned[k];
+  }
   }
 
   // ---- fieldforce -----------------------------------------------------------------------------------
@@ -880,6 +1098,8 @@ static void free_state(PppmState *&slot) {
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
   ps->work1.free_(); ps->work2.free_(); ps->sf_pre.free_(); ps->Btype.free_();
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
+  ps->dens_own.free_(); ps->halo_s.free_(); ps->halo_r.free_(); ps->vd_own.free_(); ps->tsend.free_(); ps->trecv.free_();
+  ps->workT.free_(); ps->workT2.free_();
   ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
   delete ps;
   slot = nullptr;
@@ -964,15 +1184,56 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     c.hi_out[d] = nhi + c.nupper;
   }
   c.delvolinv = c.delinv[0] * c.delinv[1] * c.delinv[2];
+  c.zoff = 0;
   ps->volume = ctx->prd[0] * ctx->prd[1] * ctx->prd[2];
-  ps->nfft = (long)p->nx * p->ny * p->nz;
-  if (ps->nfft > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");
+  ps->gnz = p->nz;
+  ps->nranks = b2_comm_nranks(ctx);
+  ps->rank = b2_comm_rank(ctx);
+  int gf_yoff = 0, gf_nyl = p->ny;
+  if (ps->nranks > 1) {
+    // z-slab decomposition: owned planes, local brick (owned + stencil/skin halo) and z-pencil rows of every rank
+    const int P = ps->nranks, me = ps->rank;
+    if (p->differentiation == 1)
+      return b2_fail(ctx, B200MD_EINVAL, "kspace_modify diff ad is single-GPU only in this build");
+    const double Lz = ctx->prd[2];
+    ps->pzlo.resize(P); ps->pzhi.resize(P); ps->zoffs.resize(P); ps->nbzs.resize(P); ps->ylos.resize(P); ps->yhis.resize(P);
+    for (int r = 0; r < P; r++) {
+      const double zlo = r * (Lz / P), zhi = r == P - 1 ? Lz : (r + 1) * (Lz / P);
+      const int nlo = static_cast<int>((zlo - dist) * p->nz / Lz + c.shift) - PPPM_OFFSET;
+      const int nhi = static_cast<int>((zhi + dist) * p->nz / Lz + c.shift) - PPPM_OFFSET;
+      ps->pzlo[r] = (int)((long)r * p->nz / P);
+      ps->pzhi[r] = (int)((long)(r + 1) * p->nz / P);
+      const int blo = std::min(nlo + c.nlower, ps->pzlo[r]), bhi = std::max(nhi + c.nupper, ps->pzhi[r] - 1);
+      ps->zoffs[r] = blo;
+      ps->nbzs[r] = bhi - blo + 1;
+      ps->ylos[r] = (int)((long)r * p->ny / P);
+      ps->yhis[r] = (int)((long)(r + 1) * p->ny / P);
+    }
+    for (int r = 0; r < P; r++) {
+      const int lo_w = ps->pzlo[r] - ps->zoffs[r], hi_w = ps->zoffs[r] + ps->nbzs[r] - ps->pzhi[r];
+      const int lower = (r + P - 1) % P, upper = (r + 1) % P;
+      if (lo_w > ps->pzhi[lower] - ps->pzlo[lower] || hi_w > ps->pzhi[upper] - ps->pzlo[upper])
+        return b2_fail(ctx, B200MD_EINVAL, "PPPM grid: %d planes over %d GPUs leaves slabs thinner than the stencil halo",
+                       p->nz, P);
+    }
+    c.zoff = ps->zoffs[me];
+    c.nz = ps->nbzs[me];
+    c.lo_out[2] = 0;            // local frame: the brick IS the allowed range of stencil planes
+    c.hi_out[2] = c.nz - 1;
+    gf_yoff = ps->ylos[me];
+    gf_nyl = ps->yhis[me] - ps->ylos[me];
+  }
+  ps->nfft = (long)p->nx * p->ny * c.nz;   // points of the local brick (= the whole grid on one GPU)
+  if ((long)p->nx * p->ny * p->nz > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");
   compute_rho_coeffs(c);
   compute_gf_denom(c);
   for (int d = 0; d < 3; d++) TRY(make_plan(ctx, ps->plan[d], ps->tw[d], ng[d]));
   const long nfft = ps->nfft;
   const bool ad = p->differentiation == 1;
-  RESERVE(ctx, ps->greensfn, (size_t)nfft);
+  PppmConst cg = c;             // global-grid view for the Green's function kernels
+  cg.nz = p->nz;
+  const long ngf = (long)p->nx * gf_nyl * p->nz;   // Green's function points held here ([z][y rows of this rank][x])
+  RESERVE(ctx, ps->greensfn, (size_t)std::max(ngf, 1L));
   RESERVE(ctx, ps->density, (size_t)nfft);
   RESERVE(ctx, ps->work1, (size_t)nfft);
   RESERVE(ctx, ps->work2, (size_t)nfft * (ad ? 1 : 3));
@@ -995,15 +1256,16 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     RESERVE(ctx, ps->Btype, (size_t)ctx->ntypes + 1);
     CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, p->B, ((size_t)ctx->ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
   }
-  if (p->dispersion) {
-    k_gf_6<<<cdiv(nfft, 128), 128, 0, ctx->stream>>>(c, ps->greensfn.p);
+  if (ngf == 0) {
+  } else if (p->dispersion) {
+    k_gf_6<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p);
     KERNEL_OK(ctx, "k_gf_6");
   } else if (!ad) {
     const double fac = std::pow(-std::log(1.0e-7), 0.25);  // EPS_HOC, pppm_intel.cpp:39
-    const int nbx = static_cast<int>((c.g_ewald * c.prd[0] / (kPI * c.nx)) * fac);
-    const int nby = static_cast<int>((c.g_ewald * c.prd[1] / (kPI * c.ny)) * fac);
-    const int nbz = static_cast<int>((c.g_ewald * c.prd[2] / (kPI * c.nz)) * fac);
-    k_gf_ik<<<cdiv(nfft, 128), 128, 0, ctx->stream>>>(c, nbx, nby, nbz, ps->greensfn.p);
+    const int nbx = static_cast<int>((cg.g_ewald * cg.prd[0] / (kPI * cg.nx)) * fac);
+    const int nby = static_cast<int>((cg.g_ewald * cg.prd[1] / (kPI * cg.ny)) * fac);
+    const int nbz = static_cast<int>((cg.g_ewald * cg.prd[2] / (kPI * cg.nz)) * fac);
+    k_gf_ik<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, nbx, nby, nbz, gf_yoff, gf_nyl, ps->greensfn.p);
     KERNEL_OK(ctx, "k_gf_ik");
   } else {
     RESERVE(ctx, ps->sf_pre, 6 * (size_t)nfft);
@@ -1050,6 +1312,7 @@ int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const
                              double *f, double *energy, double virial[6]) {
   if (!ctx || !x || !q || !f || n < 0) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_compute_host: bad arguments");
   if (!ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
+  if (ctx->pppm->nranks > 1) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_compute_host is single-GPU only");
   if (ctx->pppm->p.dispersion) return b2_fail(ctx, B200MD_EINVAL, "host form supports the Coulomb grid only");
   cudaSetDevice(ctx->device);
   DevBuf<double> dx, dq;

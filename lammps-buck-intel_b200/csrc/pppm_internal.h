@@ -11,7 +11,8 @@ static constexpr double kPI2 = 1.57079632679489661923;
 static constexpr double kPIS = 1.77245385090551602729;
 
 struct PppmConst {  // everything the kernels need by value
-  int nx, ny, nz, order, nlower, nupper;
+  int nx, ny, nz, order, nlower, nupper;   // nz: planes of the LOCAL brick (= global nz on one GPU)
+  int zoff;                                // global index of local plane 0 (multi-GPU slab; 0 on one GPU)
   double shift, shiftone;
   double boxlo[3], delinv[3], delvolinv;
   double prd[3];
@@ -45,6 +46,18 @@ struct PppmState {
   DevBuf<double> partial, red;
   double qsum = 0, qsqsum = 0;
   long q_natoms = -1;
+  // ---- multi-GPU: z-slab decomposition of the grid -------------------------------------------------
+  // Every rank spreads its atoms onto a local brick of c.nz planes starting at global plane c.zoff (owned planes +
+  // stencil/skin halo, like nzlo_out..nzhi_out of PPPM::set_grid_local); halo planes are summed into their owners
+  // (cg->reverse_comm, pppm_intel.cpp:185), the FFT is slab-decomposed with one all-to-all per transpose
+  // (remap->perform / FFT3d, :664,:835,:903-958), and owned field planes are copied back out to the neighbours'
+  // halos (cg->forward_comm, :219-220).
+  int nranks = 1, rank = 0;
+  int gnz = 0;                                   // global nz
+  std::vector<int> pzlo, pzhi, zoffs, nbzs;      // per rank: owned planes [pzlo,pzhi), brick origin and height
+  std::vector<int> ylos, yhis;                   // per rank: y rows owned in the transposed (z-pencil) layout
+  DevBuf<double> dens_own, halo_s, halo_r, vd_own;
+  DevBuf<double2> tsend, trecv, workT, workT2;
 };
 
 struct PppmView {
