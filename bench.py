@@ -110,9 +110,14 @@ class ClockSampler:
 
 
 def workload(W, rep, rank=0, nranks=1):
-    """data.aC x rep^3 per GPU; ranks stack along z (weak scaling: per-GPU work fixed)."""
+    """data.aC x rep^3 per GPU; ranks stack along z (weak scaling: per-GPU work fixed).  Every rank generates only
+    its own block (its z slab of the rep x rep x rep*nranks system) and the global box."""
     # as the shipped script: the crystal of data.aC as read, `velocity all create 300.0` (no displacement)
-    s = W.aC_system((rep, rep, rep * nranks), jitter=0.0)
+    s = W.aC_system((rep, rep, rep), jitter=0.0, seed=1281937 + rank)
+    lz = s["boxhi"][2] - s["boxlo"][2]
+    s["x"][:, 2] += rank * lz
+    s["boxhi"] = s["boxhi"].copy()
+    s["boxhi"][2] = s["boxlo"][2] + nranks * lz
     return s
 
 
@@ -131,6 +136,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus:
@@ -142,9 +148,10 @@ def run_b200(args):
     prec = pkg.PREC_DOUBLE if args.prec == "double" else pkg.PREC_MIXED
     # each rank builds the whole (deterministic) system; the library keeps its slab
     s = workload(W, args.rep, rank, world)
-    natoms = len(s["x"])
+    nlocal0 = len(s["x"])
+    natoms = nlocal0 * world            # identical blocks: global count and charge sums follow from one block
     prd = s["boxhi"] - s["boxlo"]
-    grid, g_ewald = pkg.pppm_init(ACC, u["qqrd2e"], s["q"], natoms, CUT, prd, order=ORDER)
+    grid, g_ewald = pkg.pppm_init(ACC, u["qqrd2e"], float(np.sum(s["q"] ** 2)) * world, natoms, CUT, prd, order=ORDER)
     co, cf, ct = pair_setup_args(pkg, W, s, g_ewald, args.table)
     ctx = pkg.Context(local_rank, prec)
     ctx.set_units(u["qqrd2e"], u["ftm2v"])
@@ -192,12 +199,16 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (pair, FP64-bound: SURVEY §8d) ---------------------------------
     pair_ms, pair_calls = timers["pair"]
-    entries = st1["total"] * (world if world > 1 else 1)
+    entries = st1["total"]
+    if world > 1:
+        t = torch.tensor([float(entries)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        entries = int(t.item())
     fp64_peak = ctx.microbench(0) if prec == pkg.PREC_DOUBLE else ctx.microbench(1)
     hbm_peak, hbm_src = peaks()
     pair_avg_ms = pair_ms / max(pair_calls, 1)
     local_entries = st1["total"]
-    local_atoms = natoms // world
+    local_atoms = nlocal0
     achieved_tf = PAIR_FLOPS * local_entries / (pair_avg_ms * 1e-3) / 1e12 if pair_avg_ms > 0 else 0.0
     bytes_per_atom = (4.0 * local_entries / max(local_atoms, 1) + 8 + 32 + 32) if prec == pkg.PREC_DOUBLE else \
         (4.0 * local_entries / max(local_atoms, 1) + 8 + 16 + 32)

@@ -222,6 +222,12 @@ long b200md_launch_count(const b200md_ctx *ctx);
  * grid.  Replaces Comm::borders/forward_comm (atom halo), GridComm, Remap and FFT3d transposes, and the
  * two MPI_Allreduce calls of pppm_intel.cpp:260,273.  nccl_unique_id is the 128-byte ncclUniqueId
  * produced by b200md_comm_unique_id on rank 0 and broadcast by the host (torch.distributed / MPI). */
+/* The grid plan of the slab decomposition, pure host arithmetic (usable without a device): for every rank r the
+ * owned FFT planes [pzlo,pzhi), the local brick (origin zoff, nbz planes: owned planes + stencil + skin/2 halo =
+ * nzlo_out..nzhi_out of PPPM::set_grid_local for that rank's atom slab) and the y rows [ylo,yhi) it holds after the
+ * transpose to z pencils.  Arrays are [nranks].  Non-zero return: a halo would reach beyond the neighbouring rank. */
+int b200md_pppm_decomp(int nranks, int nz, int ny, int order, double skin, double prd_z, int *pzlo, int *pzhi,
+                       int *zoff, int *nbz, int *ylo, int *yhi);
 int b200md_comm_unique_id(void *id128);
 int b200md_comm_init(b200md_ctx *ctx, int rank, int nranks, const void *id128);
 int b200md_comm_finalize(b200md_ctx *ctx);

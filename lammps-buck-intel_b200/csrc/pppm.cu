@@ -1141,6 +1141,38 @@ int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, doubl
 
 extern "C" {
 
+// Pure host arithmetic (no device needed; exercised by the CPU tests): the z-slab plan of the grid for every rank.
+//   owned planes [pzlo,pzhi) (FFT slab), local brick origin zoff / height nbz (owned planes + stencil and skin/2 halo,
+//   PPPM::set_grid_local's nzlo_out..nzhi_out for the rank's atom slab), and the y rows [ylo,yhi) held after the
+//   transpose to z pencils.  Returns non-zero when a halo would reach beyond the neighbouring rank.
+int b200md_pppm_decomp(int nranks, int nz, int ny, int order, double skin, double prd_z, int *pzlo, int *pzhi, int *zoff,
+                       int *nbz, int *ylo, int *yhi) {
+  if (nranks < 1 || nz < 1 || ny < 1 || order < 1 || !(prd_z > 0)) return B200MD_EINVAL;
+  const int P = nranks;
+  const int nlower = -(order - 1) / 2, nupper = order / 2;
+  const double shift = (order % 2) ? PPPM_OFFSET + 0.5 : PPPM_OFFSET;
+  const double dist = 0.5 * skin;
+  for (int r = 0; r < P; r++) {
+    const double zlo = r * (prd_z / P), zhi = r == P - 1 ? prd_z : (r + 1) * (prd_z / P);
+    const int nlo = static_cast<int>((zlo - dist) * nz / prd_z + shift) - PPPM_OFFSET;
+    const int nhi = static_cast<int>((zhi + dist) * nz / prd_z + shift) - PPPM_OFFSET;
+    pzlo[r] = (int)((long)r * nz / P);
+    pzhi[r] = (int)((long)(r + 1) * nz / P);
+    const int blo = std::min(nlo + nlower, pzlo[r]), bhi = std::max(nhi + nupper, pzhi[r] - 1);
+    zoff[r] = blo;
+    nbz[r] = bhi - blo + 1;
+    ylo[r] = (int)((long)r * ny / P);
+    yhi[r] = (int)((long)(r + 1) * ny / P);
+  }
+  if (P > 1)
+    for (int r = 0; r < P; r++) {
+      const int lo_w = pzlo[r] - zoff[r], hi_w = zoff[r] + nbz[r] - pzhi[r];
+      const int lower = (r + P - 1) % P, upper = (r + 1) % P;
+      if (lo_w > pzhi[lower] - pzlo[lower] || hi_w > pzhi[upper] - pzlo[upper]) return B200MD_EINVAL;
+    }
+  return 0;
+}
+
 int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   if (!ctx || !p) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_setup: NULL argument");
   cudaSetDevice(ctx->device);
@@ -1195,27 +1227,11 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     const int P = ps->nranks, me = ps->rank;
     if (p->differentiation == 1)
       return b2_fail(ctx, B200MD_EINVAL, "kspace_modify diff ad is single-GPU only in this build");
-    const double Lz = ctx->prd[2];
     ps->pzlo.resize(P); ps->pzhi.resize(P); ps->zoffs.resize(P); ps->nbzs.resize(P); ps->ylos.resize(P); ps->yhis.resize(P);
-    for (int r = 0; r < P; r++) {
-      const double zlo = r * (Lz / P), zhi = r == P - 1 ? Lz : (r + 1) * (Lz / P);
-      const int nlo = static_cast<int>((zlo - dist) * p->nz / Lz + c.shift) - PPPM_OFFSET;
-      const int nhi = static_cast<int>((zhi + dist) * p->nz / Lz + c.shift) - PPPM_OFFSET;
-      ps->pzlo[r] = (int)((long)r * p->nz / P);
-      ps->pzhi[r] = (int)((long)(r + 1) * p->nz / P);
-      const int blo = std::min(nlo + c.nlower, ps->pzlo[r]), bhi = std::max(nhi + c.nupper, ps->pzhi[r] - 1);
-      ps->zoffs[r] = blo;
-      ps->nbzs[r] = bhi - blo + 1;
-      ps->ylos[r] = (int)((long)r * p->ny / P);
-      ps->yhis[r] = (int)((long)(r + 1) * p->ny / P);
-    }
-    for (int r = 0; r < P; r++) {
-      const int lo_w = ps->pzlo[r] - ps->zoffs[r], hi_w = ps->zoffs[r] + ps->nbzs[r] - ps->pzhi[r];
-      const int lower = (r + P - 1) % P, upper = (r + 1) % P;
-      if (lo_w > ps->pzhi[lower] - ps->pzlo[lower] || hi_w > ps->pzhi[upper] - ps->pzlo[upper])
-        return b2_fail(ctx, B200MD_EINVAL, "PPPM grid: %d planes over %d GPUs leaves slabs thinner than the stencil halo",
-                       p->nz, P);
-    }
+    if (b200md_pppm_decomp(P, p->nz, p->ny, p->order, ctx->neigh.skin, ctx->prd[2], ps->pzlo.data(), ps->pzhi.data(),
+                           ps->zoffs.data(), ps->nbzs.data(), ps->ylos.data(), ps->yhis.data()))
+      return b2_fail(ctx, B200MD_EINVAL, "PPPM grid: %d planes over %d GPUs leaves slabs thinner than the stencil halo",
+                     p->nz, P);
     c.zoff = ps->zoffs[me];
     c.nz = ps->nbzs[me];
     c.lo_out[2] = 0;            // local frame: the brick IS the allowed range of stencil planes

@@ -1,0 +1,150 @@
+"""N > 1 host logic on CPU (world_size 2 and 3, gloo): the z-slab plan of b200md_pppm_decomp is replayed with numpy
+arrays standing in for device buffers — density halo sum, slab FFT with the two all-to-all transposes and the field
+halo fill, exchanged over torch.distributed exactly as csrc/pppm.cu exchanges them over NCCL — and must reproduce
+the single-process result.  Also: the per-rank bench blocks tile the global box."""
+import ctypes as C
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import ctypes as C, os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, %(root)r)
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    lib = pkg.load()
+    rank, P = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    nx, ny, nz, order, skin, Lz = 12, 10, %(nz)d, 5, 0.6, 40.0
+    ia = lambda: (C.c_int * P)()
+    pzlo, pzhi, zoff, nbz, ylo, yhi = ia(), ia(), ia(), ia(), ia(), ia()
+    rc = lib.b200md_pppm_decomp(C.c_int(P), C.c_int(nz), C.c_int(ny), C.c_int(order), C.c_double(skin), C.c_double(Lz),
+                                pzlo, pzhi, zoff, nbz, ylo, yhi)
+    assert rc == 0
+    me, lower, upper = rank, (rank - 1) %% P, (rank + 1) %% P
+    # plan invariants
+    assert pzlo[0] == 0 and pzhi[P - 1] == nz and all(pzhi[r] == pzlo[r + 1] for r in range(P - 1))
+    assert ylo[0] == 0 and yhi[P - 1] == ny and all(yhi[r] == ylo[r + 1] for r in range(P - 1))
+    assert all(zoff[r] <= pzlo[r] and zoff[r] + nbz[r] >= pzhi[r] for r in range(P))
+    lo_w = lambda r: pzlo[r] - zoff[r]
+    hi_w = lambda r: zoff[r] + nbz[r] - pzhi[r]
+    # a global "density" whose brick-local contributions are known: every rank deposits g(z) * w_r on the planes of its
+    # brick (periodic), the owners must end up with the sum over the ranks whose bricks cover the plane
+    rng = np.random.default_rng(7)
+    base = rng.normal(size=(nz, ny, nx))
+    brick_planes = (np.arange(nbz[me]) + zoff[me]) %% nz
+    local = base[brick_planes] * (1.0 + me)                     # this rank's brick [nbz][ny][nx]
+    nzo = pzhi[me] - pzlo[me]
+    own = local[lo_w(me):lo_w(me) + nzo].copy()
+
+    def exchange(s_lo, s_hi, n_from_hi, n_from_lo):
+        """b2_comm_exchange: send to lower / upper, receive from upper / lower (message order as in comm.cu)"""
+        r_hi = torch.zeros(n_from_hi, dtype=torch.float64)
+        r_lo = torch.zeros(n_from_lo, dtype=torch.float64)
+        ops = []
+        if s_lo.numel(): ops.append(dist.P2POp(dist.isend, s_lo, lower))
+        if s_hi.numel(): ops.append(dist.P2POp(dist.isend, s_hi, upper))
+        if n_from_hi: ops.append(dist.P2POp(dist.irecv, r_hi, upper))
+        if n_from_lo: ops.append(dist.P2POp(dist.irecv, r_lo, lower))
+        for w in dist.batch_isend_irecv(ops): w.wait()
+        return r_hi.numpy(), r_lo.numpy()
+
+    plane = ny * nx
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).ravel().copy())
+    # ---- density halo sum ----
+    r_hi, r_lo = exchange(t(local[:lo_w(me)]), t(local[lo_w(me) + nzo:]), lo_w(upper) * plane, hi_w(lower) * plane)
+    if hi_w(lower): own[:hi_w(lower)] += r_lo.reshape(-1, ny, nx)
+    if lo_w(upper): own[nzo - lo_w(upper):] += r_hi.reshape(-1, ny, nx)
+    expect = np.zeros((nz, ny, nx))
+    for r in range(P):
+        for l in range(nbz[r]):
+            expect[(zoff[r] + l) %% nz] += base[(zoff[r] + l) %% nz] * (1.0 + r)
+    assert np.allclose(own, expect[pzlo[me]:pzhi[me]], rtol=0, atol=1e-12), "density halo sum"
+    # ---- slab FFT: x, y local; transpose; z; compare with the global transform ----
+    w1 = np.fft.fft(np.fft.fft(own.astype(complex), axis=2), axis=1)            # [nzo][ny][nx]
+    send = [torch.from_numpy(np.ascontiguousarray(w1[:, ylo[q]:yhi[q], :]).view(np.float64).ravel().copy()) for q in range(P)]
+    recv = [torch.zeros((pzhi[q] - pzlo[q]) * (yhi[me] - ylo[me]) * nx * 2, dtype=torch.float64) for q in range(P)]
+    dist.all_to_all(recv, send) if dist.get_backend() != "gloo" else [
+        w.wait() for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, send[q], q) for q in range(P) if q != me] +
+                                                 [dist.P2POp(dist.irecv, recv[q], q) for q in range(P) if q != me])]
+    recv[me] = send[me]
+    nyl = yhi[me] - ylo[me]
+    wT = np.concatenate([r.numpy().view(complex).reshape(pzhi[q] - pzlo[q], nyl, nx) for q, r in enumerate(recv)], axis=0)
+    wT = np.fft.fft(wT, axis=0)                                                  # [nz][nyl][nx]
+    ref = np.fft.fftn(expect)
+    assert np.allclose(wT, ref[:, ylo[me]:yhi[me], :], rtol=1e-12, atol=1e-9), "forward slab FFT"
+    # ---- back: inverse z, transpose (contiguous z chunks out, row blocks in), inverse y, x ----
+    wT = np.fft.ifft(wT, axis=0)
+    send = [torch.from_numpy(np.ascontiguousarray(wT[pzlo[q]:pzhi[q]]).view(np.float64).ravel().copy()) for q in range(P)]
+    recv = [torch.zeros(nzo * (yhi[q] - ylo[q]) * nx * 2, dtype=torch.float64) for q in range(P)]
+    [w.wait() for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, send[q], q) for q in range(P) if q != me] +
+                                              [dist.P2POp(dist.irecv, recv[q], q) for q in range(P) if q != me])]
+    recv[me] = send[me]
+    w2 = np.concatenate([r.numpy().view(complex).reshape(nzo, yhi[q] - ylo[q], nx) for q, r in enumerate(recv)], axis=1)
+    back = np.fft.ifft(np.fft.ifft(w2, axis=1), axis=2).real
+    assert np.allclose(back, expect[pzlo[me]:pzhi[me]], rtol=0, atol=1e-10), "inverse slab FFT"
+    # ---- field halo fill: the brick is owned planes + the neighbours' boundary planes ----
+    r_hi, r_lo = exchange(t(back[:hi_w(lower)]), t(back[nzo - lo_w(upper):] if lo_w(upper) else back[:0]),
+                          hi_w(me) * plane, lo_w(me) * plane)
+    brick = np.concatenate([r_lo.reshape(-1, ny, nx), back, r_hi.reshape(-1, ny, nx)], axis=0)
+    assert brick.shape[0] == nbz[me]
+    assert np.allclose(brick, expect[brick_planes], rtol=0, atol=1e-10), "field halo fill"
+    dist.barrier()
+    if rank == 0: print("DECOMP OK", P)
+''')
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,nz", [(2, 24), (3, 36), (2, 27)])
+def test_slab_plan_replayed_over_gloo(tmp_path, world, nz):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT, nz=nz))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "DECOMP OK %d" % world in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_decomp_rejects_thin_slabs(pkg):
+    lib = pkg.load()
+    P = 8
+    arr = [(C.c_int * P)() for _ in range(6)]
+    # 16 planes over 8 ranks: 2 owned planes per rank cannot hold an order-5 stencil halo
+    assert lib.b200md_pppm_decomp(C.c_int(P), C.c_int(16), C.c_int(16), C.c_int(5), C.c_double(0.3), C.c_double(30.0), *arr) != 0
+    assert lib.b200md_pppm_decomp(C.c_int(P), C.c_int(270 * 8), C.c_int(250), C.c_int(5), C.c_double(0.3), C.c_double(3362.0), *arr) == 0
+    assert arr[0][0] == 0 and arr[1][P - 1] == 270 * 8
+
+
+def test_bench_rank_blocks_tile_the_global_system(W):
+    """bench.py at N > 1: every rank generates its own z block; together they are the replicated crystal"""
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    P, rep = 3, 2
+    blocks = [bench.workload(W, rep, r, P) for r in range(P)]
+    whole = W.aC_system((rep, rep, rep * P), jitter=0.0)
+    x = np.concatenate([b["x"] for b in blocks])
+    assert np.allclose(blocks[0]["boxhi"], whole["boxhi"]) and len(x) == len(whole["x"])
+    key = lambda a: np.lexsort(np.round(a, 6).T[::-1])
+    assert np.allclose(x[key(x)], whole["x"][key(whole["x"])], atol=1e-9)
+    lz = (whole["boxhi"][2] - whole["boxlo"][2]) / P
+    for r, b in enumerate(blocks):
+        assert (b["x"][:, 2] >= r * lz - 1e-9).all() and (b["x"][:, 2] < (r + 1) * lz + 1e-9).all()
