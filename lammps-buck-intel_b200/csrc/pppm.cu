@@ -18,6 +18,7 @@
 //  * fieldforce gathers with wrapped indices, so the ghost fill (cg->forward_comm, :219-220) is fused away.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "pppm_internal.h"
@@ -321,6 +322,7 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
   pa_x[k] = make_double4(dx, dy, dz, w);
   pa_n[k] = make_int4(nx, ny, nz, i);
   pa_cx[k] = wrapi(nx, c.nx);
+  if (!pa_w) return;   // the tiled make_rho evaluates the weights itself
   const int order = c.order;
   double *wk = pa_w + (size_t)k * (3 * order);
   for (int t = 0; t < order; t++) {
@@ -394,38 +396,90 @@ struct TileGeom {
   int ntx, nty, ntz, E;   // tiles per dimension, E = RHO_T + order - 1
 };
 
+// ORDER is a template parameter: the stencil point(s) of a lane — p = lane + 32 r -> (n,m,l) — are fixed for the whole
+// kernel, so their shared-memory offsets are computed once.  Per atom, lanes 0..3*ORDER-1 evaluate the 3*ORDER
+// one-dimensional weights by Horner (pppm_intel.cpp:476-488, same operation order) and the stencil lanes fetch their
+// three factors by shuffle; the next atom's {dx,dy,dz,q} is prefetched while the current one is accumulated.
+// ROUNDF: mixed mode rounds the weights to float like the reference's `flt_t rho[3][INTEL_P3M_MAXORDER]` (:474).
+template <int ORDER, int ROUNDF>
 __global__ void __launch_bounds__(128)
 k_rho_tiles(PppmConst c, TileGeom tg, const int *__restrict__ cell_start, const double4 *__restrict__ pa_x,
-            const double *__restrict__ pa_w, const int *__restrict__ pa_cx, double *__restrict__ tilebuf) {
+            const int *__restrict__ pa_cx, double *__restrict__ tilebuf) {
   extern __shared__ double s_tiles[];
+  __shared__ double s_rc[ORDER * ORDER];
+  for (int k = threadIdx.x; k < ORDER * ORDER; k += blockDim.x) s_rc[k] = c.rho_coeff[k];
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long tile = (long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
   if (tile >= ntiles) return;
-  const int E = tg.E, E3 = E * E * E;
+  constexpr int E = RHO_T + ORDER - 1, E3 = E * E * E, O2 = ORDER * ORDER, O3 = O2 * ORDER, NR = (O3 + 31) / 32;
   double *t = s_tiles + (size_t)warp * E3;
   for (int k = lane; k < E3; k += 32) t[k] = 0.0;
+  int off[NR], src_z[NR], src_y[NR], src_x[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    const int p = min(lane + 32 * r, O3 - 1);
+    const int n = p / O2, rem = p - n * O2, m = rem / ORDER, l = rem - m * ORDER;
+    off[r] = (n * E + m) * E + l;
+    src_z[r] = 2 * ORDER + n; src_y[r] = ORDER + m; src_x[r] = l;
+  }
+  // this lane's weight: dimension wd (0 x, 1 y, 2 z), stencil index wk
+  const int wl = min(lane, 3 * ORDER - 1), wd = wl / ORDER, wk = wl - wd * ORDER;
   __syncwarp();
   const int tx = (int)(tile % tg.ntx), ty = (int)((tile / tg.ntx) % tg.nty), tz = (int)(tile / ((long)tg.ntx * tg.nty));
   const int x0 = tx * RHO_T, y0 = ty * RHO_T, z0 = tz * RHO_T;
   const int x1 = min(x0 + RHO_T, c.nx), y1 = min(y0 + RHO_T, c.ny), z1 = min(z0 + RHO_T, c.nz);
-  const int order = c.order, o2 = order * order, o3 = o2 * order;
-  for (int cz = z0; cz < z1; cz++)
-    for (int cy = y0; cy < y1; cy++) {
-      const long row = ((long)cz * c.ny + cy) * c.nx;
-      const int s = cell_start[row + x0], e = cell_start[row + x1];
-      for (int a = s; a < e; a++) {
-        const double *wk = pa_w + (size_t)a * (3 * order);
-        const double q0 = pa_x[a].w;
-        const int base = ((cz - z0) * E + (cy - y0)) * E + (pa_cx[a] - x0);
-        for (int p = lane; p < o3; p += 32) {
-          const int n = p / o2, r = p - n * o2, m = r / order, l = r - m * order;
-          // z0*rho[2][n] -> y0*rho[1][m] -> x0*rho[0][l]  (pppm_intel.cpp:490-501)
-          t[base + (n * E + m) * E + l] += ((q0 * wk[2 * order + n]) * wk[order + m]) * wk[l];
-        }
-        __syncwarp();
-      }
+  // the tile's (y,z) cell rows, each one contiguous range of the cell-sorted atoms: all ranges are fetched up front
+  // (lane r holds rows r and r + 32), so walking the tile's atoms never waits on a dependent index load
+  const int nyt = y1 - y0, nrows = nyt * (z1 - z0);
+  int rs[2], re[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int r = lane + 32 * k;
+    rs[k] = re[k] = 0;
+    if (r < nrows) {
+      const long row = ((long)(z0 + r / nyt) * c.ny + (y0 + r % nyt)) * c.nx;
+      rs[k] = cell_start[row + x0];
+      re[k] = cell_start[row + x1];
     }
+  }
+  int r = -1, a = 0, e = 0;
+  auto advance = [&]() {   // next atom of the tile; warp-uniform
+    a++;
+    while (a >= e && ++r < nrows) {
+      a = __shfl_sync(0xffffffffu, r < 32 ? rs[0] : rs[1], r & 31);
+      e = __shfl_sync(0xffffffffu, r < 32 ? re[0] : re[1], r & 31);
+    }
+  };
+  advance();
+  if (r < nrows) {
+    double4 nxt = pa_x[a];
+    int cx_nxt = pa_cx[a], row_nxt = r;
+    while (true) {
+      const double4 cur = nxt;
+      const int cx = cx_nxt, rowc = row_nxt;
+      advance();
+      const bool more = r < nrows;
+      if (more) { nxt = pa_x[a]; cx_nxt = pa_cx[a]; row_nxt = r; }
+      const double d = wd == 0 ? cur.x : (wd == 1 ? cur.y : cur.z);
+      double w = 0.0;
+#pragma unroll
+      for (int l = ORDER - 1; l >= 0; l--) w = s_rc[l * ORDER + wk] + w * d;
+      if (ROUNDF) w = (double)(float)w;
+      const int base = ((rowc / nyt) * E + (rowc % nyt)) * E - x0 + cx;
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        const double wz = __shfl_sync(0xffffffffu, w, src_z[q]);
+        const double wy = __shfl_sync(0xffffffffu, w, src_y[q]);
+        const double wx = __shfl_sync(0xffffffffu, w, src_x[q]);
+        // z0*rho[2][n] -> y0*rho[1][m] -> x0*rho[0][l]  (pppm_intel.cpp:490-501)
+        if (lane + 32 * q < O3) t[base + off[q]] += ((cur.w * wz) * wy) * wx;
+      }
+      __syncwarp();
+      if (!more) break;
+    }
+  }
   double *out = tilebuf + (size_t)tile * E3;
   for (int k = lane; k < E3; k += 32) out[k] = t[k];
 }
@@ -485,7 +539,7 @@ struct PassGeom {
 };
 
 template <int LINE_CONTIG, int REAL_IN, int REAL_OUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_fft_pass(FftPlan1d pl, PassGeom pg, int TB, int LP, const double *in_real, const double2 *in, double2 *out,
            double *out_real, double s) {  // in/out may alias (in-place passes): no __restrict__
   extern __shared__ double2 smem[];
@@ -519,14 +573,14 @@ k_fft_pass(FftPlan1d pl, PassGeom pg, int TB, int LP, const double *in_real, con
 // lines are along z at (y,x) = L; TB consecutive L share y (mostly) and have consecutive x.
 // NCOMP = 3: ik (E-field components), NCOMP = 1: ad (potential only).  EV: energy/virial partial sums.
 template <int NCOMP, int EV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
                 const double *__restrict__ fky, const double *__restrict__ fkz, double scaleinv, double g_ewald,
                 double *__restrict__ ev_partial, int disp) {
   extern __shared__ double2 smem[];
   double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *bufV = smem + 2 * (size_t)TB * LP;
-  __shared__ double s_red[8][8];
+  __shared__ double s_red[16][8];
   const long plane = (long)nx * ny;
   const long nfft = plane * pl.n;
   const long L0 = (long)blockIdx.x * TB;
@@ -677,11 +731,18 @@ int make_plan(b200md_ctx *ctx, FftPlan1d &pl, DevBuf<double2> &twbuf, int n) {
   return 0;
 }
 
+// tuning knobs of the FFT passes (environment overrides are for the kernel-tuning sweeps only)
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static int fft_threads() { static int t = env_int("B200MD_FFT_THREADS", 256); return t; }
 int pick_tb(int n, int nbuf) {
-  // lines per block: as many as fit in ~110 KB of shared memory (2 blocks / SM), at most 16, at least 1
+  // lines per block: as many as fit in the shared-memory budget, at most TBMAX, at least 1
+  static const int tbmax = env_int("B200MD_FFT_TBMAX", 4), kb = env_int("B200MD_FFT_SMEM_KB", 110);
   const int LP = n | 1;
-  int tb = 16;
-  while (tb > 1 && (size_t)nbuf * tb * LP * sizeof(double2) > 110 * 1024) tb >>= 1;
+  int tb = tbmax;
+  while (tb > 1 && (size_t)nbuf * tb * LP * sizeof(double2) > (size_t)kb * 1024) tb >>= 1;
   return tb;
 }
 
@@ -695,7 +756,7 @@ int launch_pass(b200md_ctx *ctx, const FftPlan1d &pl, const PassGeom &pg, const 
   auto kern = k_fft_pass<LC, RI, RO>;
   CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = cdiv(pg.nlines, TB);
-  kern<<<nblk, 256, smem, ctx->stream>>>(pl, pg, TB, LP, in_real, in, out, out_real, s);
+  kern<<<nblk, fft_threads(), smem, ctx->stream>>>(pl, pg, TB, LP, in_real, in, out, out_real, s);
   KERNEL_OK(ctx, "k_fft_pass");
   return 0;
 }
@@ -840,7 +901,7 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   do {                                                                                                          \
     auto kern = k_fft_z_poisson<3, E>;                                                                          \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<nblk_z, 256, smem, ctx->stream>>>(ps.plan[2], nx, nyl, TB, LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
+    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, TB, LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
                                              ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, scaleinv, c.g_ewald,   \
                                              ps.partial.p, ps.p.dispersion);                                    \
   } while (0)
@@ -968,7 +1029,8 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     RESERVE(ctx, ps.perm, (size_t)n + 1);
     RESERVE(ctx, ps.pa_x, (size_t)n + 1);
     RESERVE(ctx, ps.pa_n, (size_t)n + 1);
-    RESERVE(ctx, ps.pa_w, ((size_t)n + 1) * 3 * c.order);
+    const bool tiled = c.nx >= 2 * RHO_T && c.ny >= 2 * RHO_T && c.nz >= 2 * RHO_T;
+    if (!tiled) RESERVE(ctx, ps.pa_w, ((size_t)n + 1) * 3 * c.order);
     RESERVE(ctx, ps.pa_cx, (size_t)n + 1);
     RESERVE(ctx, ps.cell_count, (size_t)nfft + 1);
     RESERVE(ctx, ps.cell_start, (size_t)nfft + 1);
@@ -990,20 +1052,34 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
       KERNEL_OK(ctx, "k_cell_order");
       k_fill_sorted<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.perm.p, v.xq, v.xqf, v.type,
                                                                    ps.p.dispersion ? ps.Btype.p : nullptr, c, ps.pa_x.p,
-                                                                   ps.pa_n.p, ps.pa_w.p, ps.pa_cx.p);
+                                                                   ps.pa_n.p, tiled ? nullptr : ps.pa_w.p, ps.pa_cx.p);
       KERNEL_OK(ctx, "k_fill_sorted");
     }
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (c.nx >= 2 * RHO_T && c.ny >= 2 * RHO_T && c.nz >= 2 * RHO_T) {
+    if (tiled) {
       TileGeom tg{cdiv(c.nx, RHO_T), cdiv(c.ny, RHO_T), cdiv(c.nz, RHO_T), RHO_T + c.order - 1};
       const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
       const size_t E3 = (size_t)tg.E * tg.E * tg.E;
       RESERVE(ctx, ps.tilebuf, (size_t)ntiles * E3);
       const int wpb = 4;
       const size_t smem = wpb * E3 * sizeof(double);
-      CUDA_OK(ctx, cudaFuncSetAttribute(k_rho_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_rho_tiles<<<cdiv(ntiles, wpb), wpb * 32, smem, ctx->stream>>>(c, tg, ps.cell_start.p, ps.pa_x.p, ps.pa_w.p,
-                                                                      ps.pa_cx.p, ps.tilebuf.p);
+#define RHO_TILES(O)                                                                                              \
+  case O: {                                                                                                       \
+    if (sizeof(flt_t) == 4) {                                                                                     \
+      CUDA_OK(ctx, cudaFuncSetAttribute(k_rho_tiles<O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_rho_tiles<O, 1><<<cdiv(ntiles, wpb), wpb * 32, smem, ctx->stream>>>(c, tg, ps.cell_start.p, ps.pa_x.p,     \
+                                                                           ps.pa_cx.p, ps.tilebuf.p);             \
+    } else {                                                                                                      \
+      CUDA_OK(ctx, cudaFuncSetAttribute(k_rho_tiles<O, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_rho_tiles<O, 0><<<cdiv(ntiles, wpb), wpb * 32, smem, ctx->stream>>>(c, tg, ps.cell_start.p, ps.pa_x.p,     \
+                                                                           ps.pa_cx.p, ps.tilebuf.p);             \
+    }                                                                                                             \
+  } break;
+      switch (c.order) {
+        RHO_TILES(1) RHO_TILES(2) RHO_TILES(3) RHO_TILES(4) RHO_TILES(5) RHO_TILES(6) RHO_TILES(7)
+        default: return b2_fail(ctx, B200MD_EORDER, "PPPM order greater than supported by USER-INTEL");
+      }
+#undef RHO_TILES
       KERNEL_OK(ctx, "k_rho_tiles");
       k_rho_fold<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, tg, ps.tilebuf.p, ps.density.p);
       KERNEL_OK(ctx, "k_rho_fold");
@@ -1037,7 +1113,7 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   do {                                                                                                        \
     auto kern = k_fft_z_poisson<NC, E>;                                                                       \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    kern<<<nblk_z, 256, smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, TB, LP, ps.work1.p, ps.work2.p,          \
+    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, TB, LP, ps.work1.p, ps.work2.p,          \
                                              ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, scaleinv, c.g_ewald, \
                                              ps.partial.p, ps.p.dispersion);                                  \
   } while (0)
