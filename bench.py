@@ -213,14 +213,21 @@ def run_b200(args):
     bytes_per_atom = (4.0 * local_entries / max(local_atoms, 1) + 8 + 32 + 32) if prec == pkg.PREC_DOUBLE else \
         (4.0 * local_entries / max(local_atoms, 1) + 8 + 16 + 32)
     pair_gbs = bytes_per_atom * local_atoms / (pair_avg_ms * 1e-3) / 1e9 if pair_avg_ms > 0 else 0.0
-    roofline = {"kernel": "k_pair<buck/coul/long,%s>" % args.prec, "bound": "fp64" if prec == pkg.PREC_DOUBLE else "fp32",
+    kname = "k_pair<buck/coul/long,%s>" % args.prec
+    traffic = None   # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/traffic.json)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(kname, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roofline = {"kernel": kname, "bound": "fp64" if prec == pkg.PREC_DOUBLE else "fp32",
                 "achieved": round(achieved_tf, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
-                "frac": round(achieved_tf / fp64_peak, 4) if fp64_peak else None, "traffic": None,
+                "frac": round(achieved_tf / fp64_peak, 4) if fp64_peak else None, "traffic": traffic,
                 "peak_source": "FMA microbenchmark in this run (b200md_microbench); MEASURED_PEAKS.json holds no FP64 figure",
                 "work_model": "125 flop per neighbour-list entry (SURVEY 8d) x %d entries per launch" % local_entries,
                 "avg_launch_ms": round(pair_avg_ms, 4), "share_of_step": round(pair_avg_ms / ms_per_step, 4)}
     roofline_hbm = {"kernel": roofline["kernel"], "bound": "hbm", "achieved": round(pair_gbs, 1), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(pair_gbs / hbm_peak, 4), "traffic": None,
+                    "unit": "GB/s", "frac": round(pair_gbs / hbm_peak, 4), "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json (%s)" % hbm_src,
                     "work_model": "(4*nbar + 8 + 32 + 32) B per atom-step, nbar = %.1f" % (local_entries / max(local_atoms, 1))}
 

@@ -14,7 +14,7 @@ namespace pairk {
 
 enum { C_CUTSQ = 0, C_CUT_LJSQ, C_CUT_COULSQ, C_BUCK1, C_BUCK2, C_RHOINV, C_A, C_C, C_OFFSET, C_N };
 
-enum { MC_L = 0, MC_MAGIC, MC_LN2HI, MC_LN2LO, MC_E5, MC_E4, MC_E3, MC_HALF, MC_ONE, MC_R375, MC_EWP, MC_A1, MC_A2,
+enum { MC_L = 0, MC_MAGIC, MC_LN2HI, MC_LN2LO, MC_E7, MC_E6, MC_E5, MC_E4, MC_E3, MC_HALF, MC_ONE, MC_R375, MC_EWP, MC_A1, MC_A2,
        MC_A3, MC_A4, MC_A5, MC_EWF, MC_N };
 
 template <class flt_t>
@@ -40,17 +40,37 @@ template <> struct V4<float> { typedef float4 type; };
 //   exp:   x = (n/64) ln2 + r, |r| <= ln2/128; exp(x) = 2^(n>>6) * T[n&63] * (1 + expm1(r)), T = 2^(k/64) in shared
 //          memory, expm1 by a degree-5 Taylor polynomial (remainder r^6/720 < 4e-17).  10 FP64 ops, no branches.
 //   rsqrt: MUFU.RSQ64H seed (~2^-20) + one third-order step (error e^3).  rcp likewise.
+#ifndef B2_EXP_TAB
 #define B2_EXP_TAB 64
+#endif
+#if B2_EXP_TAB == 64
+#define B2_EXP_SHIFT 6
+#elif B2_EXP_TAB == 32
+#define B2_EXP_SHIFT 5
+#else
+#define B2_EXP_SHIFT 4
+#endif
 // The numeric constants of these kernels travel in the kernel-parameter block (PairConsts::mc, constant bank 0), not
 // as literals: a double literal costs two UMOV/IMAD.MOV issue slots every time it is used (the compiler re-
 // materialises it inside the loop — 45 of the 223 instructions per pair in the first profile), a parameter is loaded
 // once into a (uniform) register ahead of the loop.
 
 static inline void fill_math_consts(double *mc) {
+#if B2_EXP_TAB == 64
   mc[MC_L] = 92.332482616893656877;        // 64 / ln 2
-  mc[MC_MAGIC] = 6755399441055744.0;       // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
   mc[MC_LN2HI] = 1.0830424696223417e-02;   // ln2/64 rounded to 36 bits: n * HI is exact for |n| < 2^17
   mc[MC_LN2LO] = 2.5728046223276688e-14;   // ln2/64 - HI
+#elif B2_EXP_TAB == 32
+  mc[MC_L] = 46.16624130844683;
+  mc[MC_LN2HI] = 0.021660849392446835;
+  mc[MC_LN2LO] = 5.145609244655338e-14;
+#else
+  mc[MC_L] = 23.083120654223414;
+  mc[MC_LN2HI] = 0.04332169878489367;
+  mc[MC_LN2LO] = 1.0291218489310676e-13;
+#endif
+  mc[MC_MAGIC] = 6755399441055744.0;       // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
+  mc[MC_E7] = 1.0 / 5040.0; mc[MC_E6] = 1.0 / 720.0;
   mc[MC_E5] = 1.0 / 120.0; mc[MC_E4] = 1.0 / 24.0; mc[MC_E3] = 1.0 / 6.0;
   mc[MC_HALF] = 0.5; mc[MC_ONE] = 1.0; mc[MC_R375] = 0.375;
   mc[MC_EWP] = 0.3275911;
@@ -66,13 +86,22 @@ __device__ __forceinline__ double fast_exp(const double x, const double *__restr
   const double nf = t - mc[MC_MAGIC];
   double r = fma(nf, -mc[MC_LN2HI], x);
   r = fma(nf, -mc[MC_LN2LO], r);
+#if B2_EXP_TAB == 64
   double p = fma(r, mc[MC_E5], mc[MC_E4]);
+#elif B2_EXP_TAB == 32
+  double p = fma(r, mc[MC_E6], mc[MC_E5]);
+  p = fma(p, r, mc[MC_E4]);
+#else
+  double p = fma(r, mc[MC_E7], mc[MC_E6]);
+  p = fma(p, r, mc[MC_E5]);
+  p = fma(p, r, mc[MC_E4]);
+#endif
   p = fma(p, r, mc[MC_E3]);
   p = fma(p, r, mc[MC_HALF]);
   p = fma(p, r * r, r);
   const double T = s_tab[n & (B2_EXP_TAB - 1)];
   const double v = fma(T, p, T);
-  return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+  return __hiloint2double(__double2hiint(v) + ((n >> B2_EXP_SHIFT) << 20), __double2loint(v));
 }
 __device__ __forceinline__ double fast_rsqrt(const double x, const double *mc) {
   double y;
