@@ -112,6 +112,14 @@ int b2_refresh_float_copy(b200md_ctx *ctx, int first, int count) {
   return 0;
 }
 
+// sorted -> host order into a staging area of 3*nlocal doubles (on the main stream)
+int b2_unpack_to_stage(b200md_ctx *ctx, const double4 *src, double *stage3) {
+  if (ctx->nlocal == 0) return 0;
+  unpack_by_tag<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, src, ctx->tag.p, stage3, nullptr);
+  KERNEL_OK(ctx, "unpack_by_tag");
+  return 0;
+}
+
 extern "C" {
 
 int b200md_version(void) { return 100; }
@@ -149,6 +157,8 @@ int b200md_ctx_create(int device, int precision, b200md_ctx **out) {
     delete ctx;
     return b2_fail(nullptr, B200MD_ECUDA, "cudaStreamCreate failed");
   }
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev_a);
   cudaEventCreate(&ctx->ev_b);
   ctx->h_pinned_bytes = 1 << 16;
@@ -183,6 +193,8 @@ void b200md_ctx_destroy(b200md_ctx *ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

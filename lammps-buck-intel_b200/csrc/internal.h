@@ -123,6 +123,8 @@ struct b200md_ctx {
   int device = 0;
   int prec = B200MD_PREC_DOUBLE;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // device->host copies that overlap the force kernels (b200md_step_host)
+  cudaEvent_t ev_copy = nullptr;
   std::string err;
   int sm_count = 148;
 
@@ -247,6 +249,8 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev);
 // pppm.cu
 int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial);
 void b2_pppm_free(b200md_ctx *ctx);
+// ctx.cu
+int b2_unpack_to_stage(b200md_ctx *ctx, const double4 *src, double *stage3);
 // nve.cu
 int b2_nve_initial(b200md_ctx *ctx);
 int b2_nve_final(b200md_ctx *ctx);

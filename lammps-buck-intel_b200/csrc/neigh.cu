@@ -13,6 +13,8 @@
 // fixed order => deterministic list.  All counters are integers (no FP atomics anywhere).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <ctime>
 #include <vector>
 
 #include "internal.h"
@@ -851,8 +853,27 @@ int b2_ghost_refresh(b200md_ctx *ctx) {
   return 0;
 }
 
+// B200MD_DEBUG_NEIGH=1: wall-clock breakdown of every build on stderr (synchronises; for diagnosis only)
+namespace {
+struct BuildClock {
+  b200md_ctx *ctx;
+  bool on;
+  double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit BuildClock(b200md_ctx *c) : ctx(c) { static const bool e = getenv("B200MD_DEBUG_NEIGH") != nullptr; on = e; t0 = on ? now() : 0; }
+  void mark(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = now();
+    fprintf(stderr, "[neigh] %-10s %8.3f ms\n", what, t - t0);
+    t0 = t;
+  }
+};
+}  // namespace
+
 int b2_neigh_build(b200md_ctx *ctx) {
   NeighState &ns = ctx->neigh;
+  BuildClock clk(ctx);
   if (!ctx->box_set) return b2_fail(ctx, B200MD_EINVAL, "neighbour build before b200md_set_box");
   if (!ctx->pair.ready) return b2_fail(ctx, B200MD_EINVAL, "neighbour build before b200md_pair_setup");
   ScopedTimer tm(ctx, T_NEIGH);
@@ -929,6 +950,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
     std::swap(ctx->tag, ns.tmpi_b);
   }
 
+  clk.mark("sort");
   // 2. ghost atoms: (multi-GPU) z halo from the neighbour ranks, then periodic images of owned + halo atoms;
   //    count / scan / fill, then sort the ghosts by bin too
   int nbase = n;
@@ -958,6 +980,10 @@ int b2_neigh_build(b200md_ctx *ctx) {
   if (nall >= (size_t)B2_NEIGHMASK) return b2_fail(ctx, B200MD_EOVERFLOW, "too many atoms for 30-bit neighbour indices");
   RESERVE_KEEP(ctx, ctx->xq, nall + 64);
   RESERVE_KEEP(ctx, ctx->type, nall + 64);
+  // the resident arrays and their sort scratch swap roles at every build: size both alike now, so that the second
+  // build does not reallocate (a cudaFree of these buffers costs hundreds of ms with a multi-GB list resident)
+  RESERVE(ctx, ns.tmp4a, nall + 64);
+  RESERVE(ctx, ns.tmpi_a, nall + 64);
   if (ctx->prec == B200MD_PREC_MIXED) RESERVE(ctx, ctx->xqf, nall + 64);
   if (ng > 0) {
     RESERVE(ctx, ns.gsrc_tmp, (size_t)ng);
@@ -982,6 +1008,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
   }
   TRY(b2_refresh_float_copy(ctx, 0, n));
 
+  clk.mark("ghosts");
   // 3. full list: hit masks + counts, scan to 64-bit CSR offsets, fill from the masks
   long long total = 0;
   int maxn = 0;
@@ -1001,6 +1028,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     const long long mask_total = *(long long *)ctx->h_pinned;
     RESERVE(ctx, ns.maskbuf, (size_t)mask_total + 64);
+    clk.mark("ranges");
     const int prefilter = (g.periodic[0] && g.periodic[1] && g.periodic[2]) ? 1 : 0;
     bool ucut = true;   // one cutneighsq for all type pairs?
     {
@@ -1017,6 +1045,7 @@ int b2_neigh_build(b200md_ctx *ctx) {
     else { if (ucut) NB_MASK(double, 1); else NB_MASK(double, 0); }
 #undef NB_MASK
     KERNEL_OK(ctx, "k_nb_mask");
+    clk.mark("mask");
     TRY(b2_exclusive_scan_i32_i64(ctx, ns.numneigh.p, ns.offsets.p, (size_t)n, ns.scan_ws.p));
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ns.offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ns.flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1024,9 +1053,11 @@ int b2_neigh_build(b200md_ctx *ctx) {
     total = *(long long *)ctx->h_pinned;
     maxn = *(int *)(ctx->h_pinned + 1);
     RESERVE(ctx, ns.entries, (size_t)total + 64);
+    clk.mark("scan+alloc");
     k_nb_fill<<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->type.p, lstart, gstart, g, ns.mask_off.p, ns.maskbuf.p,
                                                     ns.offsets.p, ns.entries.p, pack);
     KERNEL_OK(ctx, "k_nb_fill");
+    clk.mark("fill");
   }
   ns.total_entries = total;
   ns.max_numneigh = maxn;

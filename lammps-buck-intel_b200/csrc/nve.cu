@@ -200,9 +200,33 @@ int b200md_run_timed(b200md_ctx *ctx, long nsteps, double *thermo, double *elaps
 
 int b200md_step_host(b200md_ctx *ctx, const double *x_in, double *x_out, double *f_out) {
   if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (b2_comm_nranks(ctx) > 1)
+    return b2_fail(ctx, B200MD_EINVAL, "b200md_step_host is single-GPU only (atoms migrate between ranks)");
+  if (!ctx->neigh.ready) return b2_fail(ctx, B200MD_EINVAL, "b200md_step_host before b200md_setup_forces");
   if (x_in) TRY(b200md_atoms_set_x(ctx, x_in));
-  TRY(b200md_run(ctx, 1, nullptr));
-  return b200md_atoms_download(ctx, x_out, nullptr, f_out, nullptr);
+  const size_t n = (size_t)ctx->nlocal;
+  RESERVE(ctx, ctx->stage, 8 * n + 16);
+  ctx->ntimestep++;
+  TRY(b2_nve_initial(ctx));
+  int rebuilt = 0;
+  TRY(b200md_neigh_decide(ctx, ctx->ntimestep, &rebuilt));
+  // positions are final for this step: their download runs on the copy stream underneath the force kernels
+  if (x_out && n) {
+    TRY(b2_unpack_to_stage(ctx, ctx->xq.p, ctx->stage.p));
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    CUDA_OK(ctx, cudaMemcpyAsync(x_out, ctx->stage.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  TRY(forces(ctx, 0, 0, nullptr));
+  TRY(b2_nve_final(ctx));
+  if (f_out && n) {
+    TRY(b2_unpack_to_stage(ctx, ctx->f.p, ctx->stage.p + 3 * n));
+    CUDA_OK(ctx, cudaMemcpyAsync(f_out, ctx->stage.p + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return 0;
 }
 
 int b200md_run(b200md_ctx *ctx, long nsteps, double *thermo) {

@@ -307,3 +307,37 @@ def test_error_paths(pkg, W):
     ctx.close()
     with pytest.raises(pkg.B200MDError):
         pkg.Context(0, 7)               # PREC_MODE_SINGLE etc. are not provided
+
+
+def test_step_host_matches_resident_run(pkg, W, orc):
+    """b200md_step_host (host buffers in and out every step, the plug-in deployment / bench.py's e2e leg) walks the
+    same trajectory, bit for bit, as the resident b200md_run"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    co = W.coeffs_aC(8.0, 8.0)
+    cf = pkg.pair_coeffs(pkg.PAIR_BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+
+    def make():
+        c = pkg.make_context(s)
+        c.neigh_setup(0.3)
+        c.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=0.3)
+        c.pppm_setup(24, 24, 27, 5, 0.3)
+        c.nve_setup(u["dt"])
+        c.setup_forces(0, 0)
+        return c
+
+    a, b = make(), make()
+    a.run(4)
+    da = a.atoms_download(("x", "f"))
+    n = len(s["x"])
+    xin = np.ascontiguousarray(b.atoms_download(("x",))["x"])
+    xout, fout = np.zeros((n, 3)), np.zeros((n, 3))
+    for _ in range(4):
+        b.step_host(xin, xout, fout)
+        xin, xout = xout, xin
+    assert np.array_equal(xin, da["x"]) and np.array_equal(fout, da["f"])
+    # x_in = NULL keeps the device positions; outputs may be NULL
+    b.step_host(None, None, fout)
+    a.run(1)
+    assert np.array_equal(fout, a.atoms_download(("f",))["f"])
+    a.close(); b.close()
