@@ -2,6 +2,7 @@
 // intel_buffers.h:272-312, and IntelBuffers::thr_pack, intel_buffers.h:185-203).
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -158,6 +159,17 @@ int b200md_ctx_create(int device, int precision, b200md_ctx **out) {
     return b2_fail(nullptr, B200MD_ECUDA, "cudaStreamCreate failed");
   }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = greatest priority (numerically lowest)
+    cudaStreamCreateWithPriority(&ctx->kstream, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_k, cudaEventDisableTiming);
+    ctx->main_stream = ctx->stream;
+    // measured on one B200 (profiles/r01_overlap.txt): hiding PPPM under the pair kernel slows that kernel by more
+    // than PPPM costs (10.96 -> 17.4 ms: they contend for L1/shared memory), so the overlap is opt-in
+    ctx->overlap = getenv("B200MD_OVERLAP") != nullptr;
+  }
   cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev_a);
   cudaEventCreate(&ctx->ev_b);
@@ -193,6 +205,9 @@ void b200md_ctx_destroy(b200md_ctx *ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
+  if (ctx->ev_k) cudaEventDestroy(ctx->ev_k);
+  if (ctx->kstream) cudaStreamDestroy(ctx->kstream);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -232,6 +247,7 @@ int b200md_atoms_upload(b200md_ctx *ctx, int nlocal, int ntypes, const double *x
     if (type[i] < 1 || type[i] > ntypes)
       return b2_fail(ctx, B200MD_EINVAL, "atom %d has type %d outside 1..%d", i, type[i], ntypes);
   cudaSetDevice(ctx->device);
+  ctx->ev_pre_valid = false;
   ctx->nlocal = nlocal;
   ctx->nghost = 0;
   ctx->ntypes = ntypes;
@@ -276,6 +292,7 @@ int b200md_atoms_set_x(b200md_ctx *ctx, const double *x) {
   if (!ctx || !x) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_x: bad arguments");
   if (b2_comm_nranks(ctx) > 1)
     return b2_fail(ctx, B200MD_EINVAL, "host-order access is single-GPU only (atoms migrate between ranks)");
+  ctx->ev_pre_valid = false;
   cudaSetDevice(ctx->device);
   const size_t n = (size_t)ctx->nlocal;
   if (!n) return 0;

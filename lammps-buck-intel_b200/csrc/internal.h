@@ -125,6 +125,12 @@ struct b200md_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // device->host copies that overlap the force kernels (b200md_step_host)
   cudaEvent_t ev_copy = nullptr;
+  // k-space overlap: particle_map .. poisson of PPPM run on `kstream` (higher priority) underneath the FP64-bound pair
+  // kernel; `ev_pre` (recorded on `stream` just before the pair launch) orders them after the position update,
+  // `ev_k` hands the fields back to `stream` for fieldforce (which must follow the pair kernel: it accumulates into f)
+  cudaStream_t kstream = nullptr, main_stream = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_k = nullptr;
+  bool overlap = false, ev_pre_valid = false;   // opt-in (B200MD_OVERLAP=1): see ctx.cu
   std::string err;
   int sm_count = 148;
 

@@ -842,6 +842,7 @@ int halo_exchange(b200md_ctx *ctx, int with_type) {
 
 int b2_ghost_refresh(b200md_ctx *ctx) {
   NeighState &ns = ctx->neigh;
+  ctx->ev_pre_valid = false;
   const bool multi = b2_comm_nranks(ctx) > 1;
   if (multi) TRY(halo_exchange(ctx, 0));   // every rank takes part, with or without ghosts of its own
   if (ctx->nghost == 0) return 0;
@@ -874,6 +875,7 @@ struct BuildClock {
 int b2_neigh_build(b200md_ctx *ctx) {
   NeighState &ns = ctx->neigh;
   BuildClock clk(ctx);
+  ctx->ev_pre_valid = false;
   if (!ctx->box_set) return b2_fail(ctx, B200MD_EINVAL, "neighbour build before b200md_set_box");
   if (!ctx->pair.ready) return b2_fail(ctx, B200MD_EINVAL, "neighbour build before b200md_pair_setup");
   ScopedTimer tm(ctx, T_NEIGH);

@@ -92,6 +92,7 @@ static int upload_mass(b200md_ctx *ctx, double **dmass) {
 }
 
 int b2_nve_initial(b200md_ctx *ctx) {
+  ctx->ev_pre_valid = false;   // positions change: a pending k-space overlap marker is stale
   if (!ctx->nve_ready) return b2_fail(ctx, B200MD_EINVAL, "nve integrate before b200md_nve_setup");
   ScopedTimer tm(ctx, T_NVE);
   if (ctx->nlocal == 0) return 0;

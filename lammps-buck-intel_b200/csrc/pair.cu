@@ -53,6 +53,13 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev) {
   if (!ctx->neigh.ready) return b2_fail(ctx, B200MD_EINVAL, "pair compute before a neighbour build");
   const int evflag = ((eflag & 3) || (vflag & 3)) ? 1 : 0;
   if (evflag && !ev) return b2_fail(ctx, B200MD_EINVAL, "ev is NULL but energy/virial requested");
+  // everything the k-space solver reads (positions, types) is final here: mark it, so that PPPM may start on its own
+  // stream underneath this kernel
+  ctx->ev_pre_valid = false;
+  if (ctx->overlap && (ctx->pppm || ctx->pppm6)) {
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_pre, ctx->stream));
+    ctx->ev_pre_valid = true;
+  }
   ScopedTimer tm(ctx, T_PAIR);
   RESERVE(ctx, ctx->ev_out, 32);
   PairView v;

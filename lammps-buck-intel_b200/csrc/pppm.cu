@@ -1139,7 +1139,16 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   }
 
   // ---- fieldforce -----------------------------------------------------------------------------------
-  TRY(b2_fieldforce<flt_t>(ctx, ps, v));
+  // accumulates into f, so it goes back to the main stream, behind the pair kernel (see b2_pppm_compute)
+  if (ctx->stream != ctx->main_stream) {
+    cudaStream_t ks = ctx->stream;
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_k, ks));
+    ctx->stream = ctx->main_stream;
+    CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_k, 0));
+    const int rc = b2_fieldforce<flt_t>(ctx, ps, v);
+    ctx->stream = ks;   // a second grid (pppm/disp) continues on the k-space stream
+    if (rc) return rc;
+  } else TRY(b2_fieldforce<flt_t>(ctx, ps, v));
 
   // ---- energy / virial post-factors (pppm_intel.cpp:256-275) -----------------------------------------
   if (ps.p.dispersion) {
@@ -1211,8 +1220,22 @@ int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, doubl
   v.xqf = ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr;
   v.type = ctx->type.p;
   v.f = ctx->f.p;
-  if (ctx->prec == B200MD_PREC_MIXED) return compute_all<float>(ctx, v, eflag, vflag, energy, virial);
-  return compute_all<double>(ctx, v, eflag, vflag, energy, virial);
+  // k-space overlap: when a pair kernel was just launched for these positions (ev_pre), run on the k-space stream
+  const bool overlap = ctx->overlap && ctx->ev_pre_valid && ctx->kstream;
+  ctx->ev_pre_valid = false;
+  if (overlap) {
+    CUDA_OK(ctx, cudaStreamWaitEvent(ctx->kstream, ctx->ev_pre, 0));
+    ctx->stream = ctx->kstream;
+  }
+  const int rc = ctx->prec == B200MD_PREC_MIXED ? compute_all<float>(ctx, v, eflag, vflag, energy, virial)
+                                                 : compute_all<double>(ctx, v, eflag, vflag, energy, virial);
+  if (overlap) {
+    // the main stream continues only after everything issued on the k-space stream (its buffers are reused next step)
+    cudaEventRecord(ctx->ev_k, ctx->kstream);
+    ctx->stream = ctx->main_stream;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_k, 0);
+  }
+  return rc;
 }
 
 extern "C" {
