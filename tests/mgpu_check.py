@@ -1,6 +1,6 @@
 """2..N-rank correctness check of the slab decomposition: every rank uploads its z slab of a small charged system,
 runs setup_forces + a few steps; forces / energies / positions are compared with a single-GPU run of the same system
-on rank 0 (a second context).  Launch: python -m torch.distributed.run --nproc-per-node N scratch/mgpu_check.py"""
+on rank 0 (a second context).  Launch: python -m torch.distributed.run --nproc-per-node N tests/mgpu_check.py (or pytest tests/test_gpu_multi.py)"""
 import importlib
 import os
 import sys
