@@ -15,6 +15,10 @@ struct FftPlan1d {
   int n = 0;
   int nfac = 0;
   int fac[24];
+  // per stage (host-filled): p = product of the previous radices, m = n / radix, tstep = n / (p * radix), and
+  // 1/p as a float for the division-free k = j mod p (exact for j < 2^12, see stockham_stage)
+  int sp[24], sm[24], ststep[24];
+  float sinvp[24];
   double2 *tw = nullptr;  // device: exp(-2 pi i m / n), m < n
 };
 
@@ -72,50 +76,59 @@ __device__ __forceinline__ void dft_small<5>(double2 *u, const double s) {
   u[3] = csub(p2, q2);
 }
 
-// one Stockham stage of radix R over TB lines: src -> dst (both [TB][LP])
+// one Stockham stage of radix R over TB lines: src -> dst (both [TB][LP]).  Threads are laid out as
+// (line t = tid >> lgtpl, butterfly lane j0 = tid & (tpl - 1)) with tpl = threads per line a power of two, so the
+// only index arithmetic per butterfly is k = j mod p, done with the precomputed float reciprocal of p.
 template <int R>
-__device__ __forceinline__ void stockham_stage(const double2 *__restrict__ src, double2 *__restrict__ dst, const int n,
-                                               const int LP, const int TB, const int p, const double2 *__restrict__ tw,
+__device__ __forceinline__ void stockham_stage(const double2 *__restrict__ src, double2 *__restrict__ dst, const int LP,
+                                               const int TB, const int lgtpl, const int p, const int m,
+                                               const int tstep, const float invp, const double2 *__restrict__ tw,
                                                const double s) {
-  const int m = n / R;        // butterflies per line
-  const int tstep = n / (p * R);  // twiddle index scale: angle = -2 pi t k / (p R) = -2 pi (t k tstep) / n
-  for (int idx = threadIdx.x; idx < TB * m; idx += blockDim.x) {
-    const int t = idx / m, j = idx - t * m;
-    const int k = j % p;
+  const int tpl = 1 << lgtpl;
+  const int j0 = threadIdx.x & (tpl - 1);
+  const int tstride = blockDim.x >> lgtpl;
+  for (int t = threadIdx.x >> lgtpl; t < TB; t += tstride) {
     const double2 *ls = src + t * LP;
-    double2 u[R];
+    double2 *ldb = dst + t * LP;
+    for (int j = j0; j < m; j += tpl) {
+      const int q = __float2int_rd(((float)j + 0.5f) * invp);
+      const int k = j - q * p;
+      double2 u[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) u[r] = ls[j + r * m];
-    if (k) {
+      for (int r = 0; r < R; r++) u[r] = ls[j + r * m];
+      if (k) {
 #pragma unroll
-      for (int r = 1; r < R; r++) {
-        double2 w = __ldg(&tw[r * k * tstep]);
-        w.y *= s;
-        u[r] = cmul(u[r], w);
+        for (int r = 1; r < R; r++) {
+          double2 w = tw[r * k * tstep];
+          w.y *= s;
+          u[r] = cmul(u[r], w);
+        }
       }
-    }
-    dft_small<R>(u, s);
-    double2 *ld = dst + t * LP + (j - k) * R + k;
+      dft_small<R>(u, s);
+      double2 *ld = ldb + (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; r++) ld[r * p] = u[r];
+      for (int r = 0; r < R; r++) ld[r * p] = u[r];
+    }
   }
 }
 
 // transforms the TB lines held in bufA in place-or-pong; returns the buffer holding the result
+// tw_s: the plan's twiddle table staged in shared memory by the caller (stage_twiddles)
+__device__ __forceinline__ void stage_twiddles(const FftPlan1d &pl, double2 *tw_s) {
+  for (int k = threadIdx.x; k < pl.n; k += blockDim.x) tw_s[k] = pl.tw[k];
+}
 __device__ __forceinline__ double2 *block_fft(double2 *bufA, double2 *bufB, const FftPlan1d &pl, const int LP,
-                                              const int TB, const double s) {
+                                              const int TB, const int lgtpl, const double s, const double2 *tw_s) {
   double2 *src = bufA, *dst = bufB;
-  int p = 1;
   for (int f = 0; f < pl.nfac; f++) {
     const int R = pl.fac[f];
     switch (R) {
-      case 2: stockham_stage<2>(src, dst, pl.n, LP, TB, p, pl.tw, s); break;
-      case 3: stockham_stage<3>(src, dst, pl.n, LP, TB, p, pl.tw, s); break;
-      case 4: stockham_stage<4>(src, dst, pl.n, LP, TB, p, pl.tw, s); break;
-      default: stockham_stage<5>(src, dst, pl.n, LP, TB, p, pl.tw, s); break;
+      case 2: stockham_stage<2>(src, dst, LP, TB, lgtpl, pl.sp[f], pl.sm[f], pl.ststep[f], pl.sinvp[f], tw_s, s); break;
+      case 3: stockham_stage<3>(src, dst, LP, TB, lgtpl, pl.sp[f], pl.sm[f], pl.ststep[f], pl.sinvp[f], tw_s, s); break;
+      case 4: stockham_stage<4>(src, dst, LP, TB, lgtpl, pl.sp[f], pl.sm[f], pl.ststep[f], pl.sinvp[f], tw_s, s); break;
+      default: stockham_stage<5>(src, dst, LP, TB, lgtpl, pl.sp[f], pl.sm[f], pl.ststep[f], pl.sinvp[f], tw_s, s); break;
     }
     __syncthreads();
-    p *= R;
     double2 *tmp = src; src = dst; dst = tmp;
   }
   return src;

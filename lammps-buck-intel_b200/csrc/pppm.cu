@@ -538,34 +538,47 @@ struct PassGeom {
   long estride;
 };
 
+// TB (lines per block) and blockDim.x are powers of two: lgTB = log2(TB), lgtpl = log2(blockDim.x / TB).  A thread
+// is (line t, lane within the line) for contiguous lines and (lane, line t) for strided ones, so that consecutive
+// threads touch consecutive addresses either way; the 64-bit base offset of a line is computed once per block.
 template <int LINE_CONTIG, int REAL_IN, int REAL_OUT>
 __global__ void __launch_bounds__(512)
-k_fft_pass(FftPlan1d pl, PassGeom pg, int TB, int LP, const double *in_real, const double2 *in, double2 *out,
+k_fft_pass(FftPlan1d pl, PassGeom pg, int lgTB, int LP, const double *in_real, const double2 *in, double2 *out,
            double *out_real, double s) {  // in/out may alias (in-place passes): no __restrict__
   extern __shared__ double2 smem[];
-  double2 *bufA = smem, *bufB = smem + (size_t)TB * LP;
+  __shared__ long s_base[32];
+  const int TB = 1 << lgTB;
+  const int lgtpl = 31 - __clz(blockDim.x) - lgTB, tpl = 1 << lgtpl;
+  double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *tw_s = smem + 2 * (size_t)TB * LP;
   const long L0 = (long)blockIdx.x * TB;
   const int n = pl.n;
   const int nl = (int)min((long)TB, pg.nlines - L0);
-  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-    int t, k;
-    if (LINE_CONTIG) { t = idx / n; k = idx - t * n; }
-    else { k = idx / nl; t = idx - k * nl; }
-    const long L = L0 + t;
-    const long g = (L / pg.inner) * pg.outer + (L % pg.inner) + (long)k * pg.estride;
-    bufA[t * LP + k] = REAL_IN ? make_double2(in_real[g], 0.0) : in[g];
+  stage_twiddles(pl, tw_s);
+  if (threadIdx.x < nl) {
+    const long L = L0 + threadIdx.x;
+    s_base[threadIdx.x] = (L / pg.inner) * pg.outer + (L % pg.inner);
   }
   __syncthreads();
-  double2 *res = block_fft(bufA, bufB, pl, LP, nl, s);
-  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-    int t, k;
-    if (LINE_CONTIG) { t = idx / n; k = idx - t * n; }
-    else { k = idx / nl; t = idx - k * nl; }
-    const long L = L0 + t;
-    const long g = (L / pg.inner) * pg.outer + (L % pg.inner) + (long)k * pg.estride;
-    const double2 v = res[t * LP + k];
-    if (REAL_OUT) out_real[g] = v.x;
-    else out[g] = v;
+  int t, k0, kstep;
+  if (LINE_CONTIG) { t = threadIdx.x >> lgtpl; k0 = threadIdx.x & (tpl - 1); kstep = tpl; }
+  else { t = threadIdx.x & (TB - 1); k0 = threadIdx.x >> lgTB; kstep = tpl; }
+  if (t < nl) {
+    const long base = s_base[t];
+    for (int k = k0; k < n; k += kstep) {
+      const long g = base + (long)k * pg.estride;
+      bufA[t * LP + k] = REAL_IN ? make_double2(in_real[g], 0.0) : in[g];
+    }
+  }
+  __syncthreads();
+  double2 *res = block_fft(bufA, bufB, pl, LP, nl, lgtpl, s, tw_s);
+  if (t < nl) {
+    const long base = s_base[t];
+    for (int k = k0; k < n; k += kstep) {
+      const long g = base + (long)k * pg.estride;
+      const double2 v = res[t * LP + k];
+      if (REAL_OUT) out_real[g] = v.x;
+      else out[g] = v;
+    }
   }
 }
 
@@ -574,57 +587,64 @@ k_fft_pass(FftPlan1d pl, PassGeom pg, int TB, int LP, const double *in_real, con
 // NCOMP = 3: ik (E-field components), NCOMP = 1: ad (potential only).  EV: energy/virial partial sums.
 template <int NCOMP, int EV>
 __global__ void __launch_bounds__(512)
-k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__restrict__ in,
+k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
                 const double *__restrict__ fky, const double *__restrict__ fkz, double scaleinv, double g_ewald,
                 double *__restrict__ ev_partial, int disp) {
   extern __shared__ double2 smem[];
+  const int TB = 1 << lgTB;
+  const int lgtpl = 31 - __clz(blockDim.x) - lgTB;
   double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *bufV = smem + 2 * (size_t)TB * LP;
+  double2 *tw_s = smem + 3 * (size_t)TB * LP;
   __shared__ double s_red[16][8];
+  stage_twiddles(pl, tw_s);
   const long plane = (long)nx * ny;
   const long nfft = plane * pl.n;
   const long L0 = (long)blockIdx.x * TB;
   const int n = pl.n;
   const int nl = (int)min((long)TB, plane - L0);
-  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-    const int k = idx / nl, t = idx - k * nl;
-    bufA[t * LP + k] = in[(L0 + t) + (long)k * plane];
-  }
+  // thread = (z lane k0, line t): consecutive threads touch consecutive lines = consecutive addresses
+  const int t = threadIdx.x & (TB - 1), k0 = threadIdx.x >> lgTB, kstep = blockDim.x >> lgTB;
+  const bool live = t < nl;
+  const long L = L0 + t;
+  const int ix = live ? (int)(L % nx) : 0, iy = live ? (int)(L / nx) : 0;
+  if (live)
+    for (int k = k0; k < n; k += kstep) bufA[t * LP + k] = in[L + (long)k * plane];
   __syncthreads();
-  double2 *res = block_fft(bufA, bufB, pl, LP, nl, S_FWD);
+  double2 *res = block_fft(bufA, bufB, pl, LP, nl, lgtpl, S_FWD, tw_s);
   double2 *other = (res == bufA) ? bufB : bufA;
   // Green's function multiply; energy / virial tallies
   double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-    const int k = idx / nl, t = idx - k * nl;
-    const long L = L0 + t;
-    const long g = L + (long)k * plane;
-    const double2 w = res[t * LP + k];
-    const double gf = greensfn[g];
-    if (EV) {
-      const double eng = scaleinv * scaleinv * gf * (w.x * w.x + w.y * w.y);
-      const int ix = (int)(L % nx), iy = (int)(L / nx);
-      const double kx = fkx[ix], ky = fky[iy], kz = fkz[k];
-      const double sqk = kx * kx + ky * ky + kz * kz;
-      acc[0] += eng;
-      if (sqk != 0.0) {  // PPPM::setup vg[][] evaluated on the fly instead of stored (6 doubles / point)
-        double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
-        if (disp) {   // vg_6 of PPPMDisp::setup
-          const double b = 0.5 * sqrt(sqk) / g_ewald, bs = b * b, bt = bs * b;
-          const double erft = 2.0 * bt * sqrt(kPI) * erfc(b), expt = exp(-bs);
-          const double nom = erft - 2.0 * bs * expt, denom = nom + expt;
-          vterm = denom == 0.0 ? 3.0 / sqk : 3.0 * nom / (sqk * denom);
+  if (live) {
+    const double kx = fkx[ix], ky = fky[iy];
+    for (int k = k0; k < n; k += kstep) {
+      const long g = L + (long)k * plane;
+      const double2 w = res[t * LP + k];
+      const double gf = greensfn[g];
+      if (EV) {
+        const double eng = scaleinv * scaleinv * gf * (w.x * w.x + w.y * w.y);
+        const double kz = fkz[k];
+        const double sqk = kx * kx + ky * ky + kz * kz;
+        acc[0] += eng;
+        if (sqk != 0.0) {  // PPPM::setup vg[][] evaluated on the fly instead of stored (6 doubles / point)
+          double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+          if (disp) {   // vg_6 of PPPMDisp::setup
+            const double b = 0.5 * sqrt(sqk) / g_ewald, bs = b * b, bt = bs * b;
+            const double erft = 2.0 * bt * sqrt(kPI) * erfc(b), expt = exp(-bs);
+            const double nom = erft - 2.0 * bs * expt, denom = nom + expt;
+            vterm = denom == 0.0 ? 3.0 / sqk : 3.0 * nom / (sqk * denom);
+          }
+          acc[1] += eng * (1.0 + vterm * kx * kx);
+          acc[2] += eng * (1.0 + vterm * ky * ky);
+          acc[3] += eng * (1.0 + vterm * kz * kz);
+          acc[4] += eng * (vterm * kx * ky);
+          acc[5] += eng * (vterm * kx * kz);
+          acc[6] += eng * (vterm * ky * kz);
         }
-        acc[1] += eng * (1.0 + vterm * kx * kx);
-        acc[2] += eng * (1.0 + vterm * ky * ky);
-        acc[3] += eng * (1.0 + vterm * kz * kz);
-        acc[4] += eng * (vterm * kx * ky);
-        acc[5] += eng * (vterm * kx * kz);
-        acc[6] += eng * (vterm * ky * kz);
       }
+      const double sg = scaleinv * gf;
+      bufV[t * LP + k] = make_double2(w.x * sg, w.y * sg);
     }
-    const double sg = scaleinv * gf;
-    bufV[t * LP + k] = make_double2(w.x * sg, w.y * sg);
   }
   __syncthreads();
   if (EV) {
@@ -645,22 +665,21 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int TB, int LP, const double2 *__r
   }
   for (int comp = 0; comp < NCOMP; comp++) {
     double2 *a = res, *b = other;  // V lives in bufV; a/b are free ping-pong buffers
-    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-      const int k = idx / nl, t = idx - k * nl;
-      const double2 v = bufV[t * LP + k];
-      if (NCOMP == 1) a[t * LP + k] = v;
-      else {
-        const long L = L0 + t;
-        const double fk = comp == 0 ? fkx[(int)(L % nx)] : (comp == 1 ? fky[(int)(L / nx)] : fkz[k]);
-        a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);  // work2 = (fk*Im, -fk*Re), :894-895
+    if (live) {
+      const double fkxy = comp == 0 ? fkx[ix] : fky[iy];
+      for (int k = k0; k < n; k += kstep) {
+        const double2 v = bufV[t * LP + k];
+        if (NCOMP == 1) a[t * LP + k] = v;
+        else {
+          const double fk = comp == 2 ? fkz[k] : fkxy;
+          a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);  // work2 = (fk*Im, -fk*Re), :894-895
+        }
       }
     }
     __syncthreads();
-    double2 *r2 = block_fft(a, b, pl, LP, nl, S_BWD);
-    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-      const int k = idx / nl, t = idx - k * nl;
-      out[(size_t)comp * nfft + (L0 + t) + (long)k * plane] = r2[t * LP + k];
-    }
+    double2 *r2 = block_fft(a, b, pl, LP, nl, lgtpl, S_BWD, tw_s);
+    if (live)
+      for (int k = k0; k < n; k += kstep) out[(size_t)comp * nfft + L + (long)k * plane] = r2[t * LP + k];
     __syncthreads();
   }
 }
@@ -720,6 +739,17 @@ int make_plan(b200md_ctx *ctx, FftPlan1d &pl, DevBuf<double2> &twbuf, int n) {
   while (m % 3 == 0) { pl.fac[pl.nfac++] = 3; m /= 3; }
   while (m % 5 == 0) { pl.fac[pl.nfac++] = 5; m /= 5; }
   if (m != 1) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", n);
+  if (n > 4096) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d is longer than one shared-memory line (4096)", n);
+  {
+    int pp = 1;
+    for (int f = 0; f < pl.nfac; f++) {
+      pl.sp[f] = pp;
+      pl.sm[f] = n / pl.fac[f];
+      pl.ststep[f] = n / (pp * pl.fac[f]);
+      pl.sinvp[f] = 1.0f / (float)pp;
+      pp *= pl.fac[f];
+    }
+  }
   std::vector<double2> tw(n);
   for (int k = 0; k < n; k++) {
     const long double ph = -2.0L * 3.14159265358979323846264338327950288L * k / n;
@@ -736,10 +766,11 @@ static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) l++; return l; }
 static int fft_threads() { static int t = env_int("B200MD_FFT_THREADS", 256); return t; }
 int pick_tb(int n, int nbuf) {
   // lines per block: as many as fit in the shared-memory budget, at most TBMAX, at least 1
-  static const int tbmax = env_int("B200MD_FFT_TBMAX", 4), kb = env_int("B200MD_FFT_SMEM_KB", 110);
+  static const int tbmax = env_int("B200MD_FFT_TBMAX", 8), kb = env_int("B200MD_FFT_SMEM_KB", 70);
   const int LP = n | 1;
   int tb = tbmax;
   while (tb > 1 && (size_t)nbuf * tb * LP * sizeof(double2) > (size_t)kb * 1024) tb >>= 1;
@@ -751,12 +782,12 @@ int launch_pass(b200md_ctx *ctx, const FftPlan1d &pl, const PassGeom &pg, const 
                 double2 *out, double *out_real, double s) {
   const int TB = pick_tb(pl.n, 2);
   const int LP = pl.n | 1;
-  const size_t smem = 2 * (size_t)TB * LP * sizeof(double2);
-  if (smem > 200 * 1024) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d too long for one shared-memory line", pl.n);
+  const size_t smem = (2 * (size_t)TB * LP + pl.n) * sizeof(double2);   // two line buffers + the twiddle table
+  if (smem > 220 * 1024) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d too long for one shared-memory line", pl.n);
   auto kern = k_fft_pass<LC, RI, RO>;
   CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = cdiv(pg.nlines, TB);
-  kern<<<nblk, fft_threads(), smem, ctx->stream>>>(pl, pg, TB, LP, in_real, in, out, out_real, s);
+  kern<<<nblk, fft_threads(), smem, ctx->stream>>>(pl, pg, ilog2(TB), LP, in_real, in, out, out_real, s);
   KERNEL_OK(ctx, "k_fft_pass");
   return 0;
 }
@@ -892,7 +923,7 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     // ---- z pass + Green's function + gradients + inverse z on my pencils ------------------------------------------
     const int TB = pick_tb(gnz, 3);
     const int LP = gnz | 1;
-    const size_t smem = 3 * (size_t)TB * LP * sizeof(double2);
+    const size_t smem = (3 * (size_t)TB * LP + gnz) * sizeof(double2);
     nblk_z = cdiv((long)nx * nyl, TB);
     const double scaleinv = 1.0 / ((double)nx * ny * gnz);
     if (ev) RESERVE(ctx, ps.partial, (size_t)std::max(nblk_z, 1) * 8);
@@ -901,7 +932,7 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   do {                                                                                                          \
     auto kern = k_fft_z_poisson<3, E>;                                                                          \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, TB, LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
+    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
                                              ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, scaleinv, c.g_ewald,   \
                                              ps.partial.p, ps.p.dispersion);                                    \
   } while (0)
@@ -1104,7 +1135,7 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     TRY(fft3d_forward_xy(ctx, ps, ps.density.p, ps.work1.p, c.nz));
     const int TB = pick_tb(c.nz, 3);
     const int LP = c.nz | 1;
-    const size_t smem = 3 * (size_t)TB * LP * sizeof(double2);
+    const size_t smem = (3 * (size_t)TB * LP + c.nz) * sizeof(double2);
     const long plane = (long)c.nx * c.ny;
     nblk_z = cdiv(plane, TB);
     const double scaleinv = 1.0 / ((double)c.nx * c.ny * c.nz);
@@ -1113,7 +1144,7 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   do {                                                                                                        \
     auto kern = k_fft_z_poisson<NC, E>;                                                                       \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, TB, LP, ps.work1.p, ps.work2.p,          \
+    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, ilog2(TB), LP, ps.work1.p, ps.work2.p,          \
                                              ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, scaleinv, c.g_ewald, \
                                              ps.partial.p, ps.p.dispersion);                                  \
   } while (0)
