@@ -309,7 +309,9 @@ struct Pos<float> {
 // Double mode: the test runs in FP32 on coordinates relative to the bin centre with a guard band; the (very rare)
 // candidates inside the band are decided by the exact un-fused FP64 expression, so the pair set stays bit-exact while
 // the FP64 pipe is idle.  Mixed mode: the criterion IS the reference's float expression on absolute float coordinates.
-#define NB_THREADS 256
+#ifndef NB_THREADS
+#define NB_THREADS 128   // 4 warps per bin-block: less waiting at the block barriers than 8 (profiles/r01_ncu_k_nb_mask.txt)
+#endif
 #define NB_MAXI 64          // owned atoms of a bin handled per sweep
 #define NB_MAXR 64          // candidate ranges per bin (<= 2 * (2s+1)^2 with s <= 2 -> 50)
 #define NB_FILLC 4096       // candidates staged at a time by the fill kernel
@@ -320,32 +322,44 @@ struct BinRanges {
   int nr;
 };
 
+// Cooperative: every thread of the block calls it (contains __syncthreads).  The <= 50 (row, kind) range loads are
+// issued by as many threads at once — done by one thread they are a serial chain of dependent global loads that the
+// whole block waits for (it was the top stall of both list kernels) — and thread 0 only compacts them from shared
+// memory, keeping the fixed row order.
 __device__ __forceinline__ void bin_ranges(const BinGeom &g, int nlocal, const int *__restrict__ lstart,
-                                           const int *__restrict__ gstart, int ex, int ey, int ez, BinRanges &R) {
+                                           const int *__restrict__ gstart, int ex, int ey, int ez, BinRanges &R,
+                                           int *s_raw /* shared, 2 * NB_MAXR ints */) {
+  const int nyr = 2 * g.s[1] + 1, nzr = 2 * g.s[2] + 1, nraw = 2 * nyr * nzr;
   const int x0 = max(ex - g.s[0], 0), x1 = min(ex + g.s[0], g.mbin[0] - 1);
-  int nr = 0, tot = 0;
-  for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
-    const int rz = ez + dz;
-    if (rz < 0 || rz >= g.mbin[2]) continue;
-    for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
-      const int ry = ey + dy;
-      if (ry < 0 || ry >= g.mbin[1]) continue;
+  for (int k = threadIdx.x; k < nraw; k += blockDim.x) {
+    const int kind = k & 1, rowi = k >> 1;
+    const int ry = ey + (rowi % nyr) - g.s[1], rz = ez + (rowi / nyr) - g.s[2];
+    int j0 = 0, len = 0;
+    if (ry >= 0 && ry < g.mbin[1] && rz >= 0 && rz < g.mbin[2]) {
       const int row = (rz * g.mbin[1] + ry) * g.mbin[0];
-      for (int kind = 0; kind < 2; kind++) {
-        const int *sp = kind ? gstart : lstart;
-        const int base = kind ? nlocal : 0;
-        const int j0 = sp[row + x0] + base, j1 = sp[row + x1 + 1] + base;
-        if (j1 > j0 && nr < NB_MAXR) {
-          R.start[nr] = j0;
-          R.pref[nr] = tot;
-          tot += j1 - j0;
-          nr++;
-        }
+      const int *sp = kind ? gstart : lstart;
+      j0 = sp[row + x0] + (kind ? nlocal : 0);
+      len = sp[row + x1 + 1] + (kind ? nlocal : 0) - j0;
+    }
+    s_raw[2 * k] = j0;
+    s_raw[2 * k + 1] = len;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nr = 0, tot = 0;
+    for (int k = 0; k < nraw; k++) {
+      const int len = s_raw[2 * k + 1];
+      if (len > 0) {
+        R.start[nr] = s_raw[2 * k];
+        R.pref[nr] = tot;
+        tot += len;
+        nr++;
       }
     }
+    R.pref[nr] = tot;
+    R.nr = nr;
   }
-  R.pref[nr] = tot;
-  R.nr = nr;
+  __syncthreads();
 }
 
 __device__ __forceinline__ int cand_index(const BinRanges &R, int c) {
@@ -422,8 +436,9 @@ k_nb_mask(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__
   const int binid = (ez * g.mbin[1] + ey) * g.mbin[0] + ex;
   const int i0 = lstart[binid], i1 = lstart[binid + 1];
   if (i0 == i1) return;
+  __shared__ int s_raw[2 * NB_MAXR];
+  bin_ranges(g, nlocal, lstart, gstart, ex, ey, ez, R, s_raw);
   if (tid == 0) {
-    bin_ranges(g, nlocal, lstart, gstart, ex, ey, ez, R);
     int cs = 0;
     for (int r = 0; r < R.nr; r++)
       if (R.start[r] <= i0 && i0 < R.start[r] + (R.pref[r + 1] - R.pref[r])) cs = R.pref[r] + (i0 - R.start[r]);
@@ -546,8 +561,8 @@ k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lsta
   const int binid = (ez * g.mbin[1] + ey) * g.mbin[0] + ex;
   const int i0 = lstart[binid], i1 = lstart[binid + 1];
   if (i0 == i1) return;
-  if (tid == 0) bin_ranges(g, nlocal, lstart, gstart, ex, ey, ez, R);
-  __syncthreads();
+  __shared__ int s_raw[2 * NB_MAXR];
+  bin_ranges(g, nlocal, lstart, gstart, ex, ey, ez, R, s_raw);
   const int ncand = R.pref[R.nr];
   const int nwords = (ncand + 31) >> 5;
   const int nit = i1 - i0;
