@@ -58,8 +58,8 @@ template <> struct V4<float> { typedef float4 type; };
 static inline void fill_math_consts(double *mc) {
 #if B2_EXP_TAB == 64
   mc[MC_L] = 92.332482616893656877;        // 64 / ln 2
-  mc[MC_LN2HI] = 1.0830424696223417e-02;   // ln2/64 rounded to 36 bits: n * HI is exact for |n| < 2^17
-  mc[MC_LN2LO] = 2.5728046223276688e-14;   // ln2/64 - HI
+  mc[MC_LN2HI] = 1.0830424696249145e-02;   // ln2/64 to full double precision (the reduction is a single FMA)
+  mc[MC_LN2LO] = 0.0;
 #elif B2_EXP_TAB == 32
   mc[MC_L] = 46.16624130844683;
   mc[MC_LN2HI] = 0.021660849392446835;
@@ -84,10 +84,11 @@ __device__ __forceinline__ double fast_exp(const double x, const double *__restr
   const double t = fma(x, mc[MC_L], mc[MC_MAGIC]);
   const int n = __double2loint(t);
   const double nf = t - mc[MC_MAGIC];
-  double r = fma(nf, -mc[MC_LN2HI], x);
-  r = fma(nf, -mc[MC_LN2LO], r);
+  // one FMA: nf * (ln2/64) is exact inside it, and |nf| * |fl(ln2/64) - ln2/64| < 4e-15 for |x| < 700
+  const double r = fma(nf, -mc[MC_LN2HI], x);
 #if B2_EXP_TAB == 64
-  double p = fma(r, mc[MC_E5], mc[MC_E4]);
+  // |r| <= ln2/128: the degree-4 remainder r^5/120 is < 4e-14 relative — four orders inside the 1e-9 parity bar
+  double p = mc[MC_E4];
 #elif B2_EXP_TAB == 32
   double p = fma(r, mc[MC_E6], mc[MC_E5]);
   p = fma(p, r, mc[MC_E4]);
@@ -128,6 +129,10 @@ __device__ __forceinline__ double m_rsq(double dx, double dy, double dz) {
 __device__ __forceinline__ float m_rsq(float dx, float dy, float dz) {
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
+// fused flavour for the production double kernel (mixed mode keeps the reference's float expression): the list criterion (neigh.cu) keeps the un-fused expression and
+// with it the bit-exact pair set; here a 1-ulp difference can only matter for a pair within 1 ulp of the force cut-off
+__device__ __forceinline__ double m_rsq_fused(double dx, double dy, double dz) { return fma(dz, dz, fma(dy, dy, dx * dx)); }
+__device__ __forceinline__ float m_rsq_fused(float dx, float dy, float dz) { return m_rsq(dx, dy, dz); }
 // r, 1/r, 1/r^2.  double: one rsqrt (error ~1 ulp, far inside 1e-9).  float: exp(-r/rho) amplifies an ulp of r
 // by r/rho ~ 50, so mixed mode replays the reference's own correctly-rounded sequence: COUL_LONG takes
 // r2inv = 1/rsq, r = 1/sqrt(r2inv) (pair_buck_coul_long_intel.cpp:287-288), the others r = sqrt(rsq)
@@ -373,7 +378,7 @@ k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const i
       const flt_t delx = xi.x - xj.x;
       const flt_t dely = xi.y - xj.y;
       const flt_t delz = xi.z - xj.z;
-      const flt_t rsq = m_rsq(delx, dely, delz);
+      const flt_t rsq = GENERAL ? m_rsq(delx, dely, delz) : m_rsq_fused(delx, dely, delz);
       flt_t fpair, evdwl, ecoul;
       pair_eval<STYLE, flt_t, EVFLAG, GENERAL>(pc, cij, ctab, dtab, s_tab, rsq, qtmp, xj.w, sbindex, fpair, evdwl, ecoul);
       const double dfx = (double)(delx * fpair), dfy = (double)(dely * fpair), dfz = (double)(delz * fpair);
