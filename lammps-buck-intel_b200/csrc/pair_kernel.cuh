@@ -263,9 +263,11 @@ __device__ __forceinline__ void pair_eval(const PairConsts<flt_t> &pc, const flt
       const float rsq_lookup = (float)rsq;
       const int itable = (__float_as_int(rsq_lookup) & pc.ncoulmask) >> pc.ncoulshiftbits;
       const flt_t *tb = ctab + 8 * itable;  // {r,dr,f,df,e,de,c,dc}
-      const flt_t fraction = ((flt_t)rsq_lookup - tb[0]) * tb[1];
+      // {r,dr,f,df} in one vector load (256-bit in double mode): the table gathers load the L1 data pipe
+      const typename V4<flt_t>::type t4 = ld_atom(reinterpret_cast<const typename V4<flt_t>::type *>(tb));
+      const flt_t fraction = ((flt_t)rsq_lookup - t4.x) * t4.y;
       const flt_t qiqj = qtmp * qj;
-      forcecoul = qiqj * (tb[2] + fraction * tb[3]);
+      forcecoul = qiqj * (t4.z + fraction * t4.w);
       if (EVFLAG) ecoul = qiqj * (tb[4] + fraction * tb[5]);
       if (sbindex) {
         const flt_t prefactor = qiqj * (tb[6] + fraction * tb[7]);
