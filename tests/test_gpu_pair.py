@@ -341,3 +341,68 @@ def test_step_host_matches_resident_run(pkg, W, orc):
     a.run(1)
     assert np.array_equal(fout, a.atoms_download(("f",))["f"])
     a.close(); b.close()
+
+
+def test_edge_cases_empty_ragged_nonperiodic(pkg, W, orc):
+    """empty system; atoms far outside the box (Domain::pbc wraps them); a very inhomogeneous system (empty bins, one
+    crowded bin, an isolated atom with no neighbours); a non-periodic box (no ghosts, FP64 test for every candidate)"""
+    co = W.coeffs_in_buck(2.5)
+    cf = pkg.pair_coeffs(pkg.PAIR_BUCK, 1, co["A"], co["rho"], co["C"], co["cut_lj"])
+    P = orc.Params(orc.BUCK, 1, co["A"], co["rho"], co["C"], co["cut_lj"])
+    lo, hi = np.zeros(3), np.array([14.0, 15.0, 16.0])
+    mass = np.array([0.0, 1.0])
+    # --- empty
+    ctx = pkg.Context()
+    ctx.set_units(1.0, 1.0); ctx.set_box(lo, hi)
+    ctx.atoms_upload(np.zeros((0, 3)), np.zeros(0, np.int32), mass)
+    ctx.neigh_setup(0.3); ctx.pair_setup(pkg.PAIR_BUCK, 1, cf); ctx.nve_setup(0.005)
+    th = ctx.setup_forces(1, 1)
+    assert not th.any() and ctx.neigh_stats()["total"] == 0
+    ctx.run(3)
+    ctx.close()
+    # --- ragged: a dense cluster, a sparse gas, one isolated atom; some coordinates several box lengths away
+    rng = np.random.default_rng(5)
+    cluster = np.array([7.0, 7.5, 8.0]) + rng.uniform(-1.4, 1.4, (300, 3))
+    gas = rng.uniform(0, 1, (60, 3)) * (hi - lo) * np.array([1.0, 1.0, 0.3])
+    x = np.concatenate([cluster, gas, [[0.7, 14.2, 15.1]]])
+    # keep every pair farther apart than 0.75 (the r^-6 term of in.buck's C = -0.8 is repulsive: no overflow, but keep
+    # forces in a sane range for the relative comparison)
+    keep = np.ones(len(x), bool)
+    for i in range(len(x)):
+        if keep[i]:
+            d = x[i + 1:] - x[i]
+            d -= np.round(d / (hi - lo)) * (hi - lo)
+            keep[i + 1:] &= (d * d).sum(1) > 0.75 ** 2
+    x = x[keep]
+    t = np.ones(len(x), np.int32)
+    xs = x.copy()
+    xs[::7] += np.array([3, -2, 1]) * (hi - lo)       # far outside: remapped by the first build only within one image,
+    xs[::7] -= np.array([2, -3, 1]) * (hi - lo)       # so bring them back to +-1 box length like a real trajectory
+    ctx = pkg.Context()
+    ctx.set_units(1.0, 1.0); ctx.set_box(lo, hi)
+    ctx.atoms_upload(xs, t, mass)
+    ctx.neigh_setup(0.3); ctx.pair_setup(pkg.PAIR_BUCK, 1, cf)
+    ctx.neigh_build()
+    ev = ctx.pair_compute(1, 1)
+    f = ctx.atoms_download(("f",))["f"]
+    xw = W.wrap(W.wrap(xs, lo, hi), lo, hi)
+    fo, evo, _ = orc.pair_forces_periodic(P, 0, xw, t, None, lo, hi, 0.3)
+    assert util.rel_force_err(f, fo[:, :3]) <= 1e-9
+    assert abs(ev[0] - evo[0]) <= 1e-10 * abs(evo[0])
+    nn = ctx.neigh_download()[0]
+    assert nn.min() == 0 and nn.max() > 20, "expected an isolated atom and a crowded bin"
+    ctx.close()
+    # --- non-periodic box: no ghosts at all, pair set = brute force over owned atoms
+    ctx = pkg.Context()
+    ctx.set_units(1.0, 1.0); ctx.set_box(lo, hi, periodic=(0, 0, 0))
+    ctx.atoms_upload(x, t, mass)
+    ctx.neigh_setup(0.3); ctx.pair_setup(pkg.PAIR_BUCK, 1, cf)
+    ctx.neigh_build()
+    st = ctx.neigh_stats()
+    assert st["nghost"] == 0
+    nn, off, ent, gsrc, gshift = ctx.neigh_download()
+    fn, foff, fent = orc.neigh_full_brute(len(x), x, t, 1, P.cutneighsq(0.3), 0)
+    assert np.array_equal(nn, fn)
+    for i in (0, len(x) // 2, len(x) - 1):
+        assert np.array_equal(np.sort(ent[off[i]:off[i + 1]] & pkg.NEIGHMASK), np.sort(fent[foff[i]:foff[i + 1]] & pkg.NEIGHMASK))
+    ctx.close()
