@@ -101,3 +101,21 @@ def write(tmpdir, name, text, W=None):
     if W is not None:
         write_data_aC(W, os.path.join(str(tmpdir), "data.aC"))
     return p
+
+IN_BUCK_BIG = """# examples/in.buck_big semantics (192 000 atoms as shipped; n scales the box for the tests)
+units lj
+atom_style atomic
+lattice fcc 0.8442
+region box block 0 {nx} 0 {ny} 0 {nz}
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+velocity all create 1.44 87287 loop geom
+pair_style buck 5.0
+pair_coeff 1 1 0.8 0.2 -0.8
+neighbor 0.3 bin
+neigh_modify delay 5 every 1
+fix 1 all nve
+thermo {thermo}
+run {steps}
+"""

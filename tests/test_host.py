@@ -163,3 +163,36 @@ def test_buck_long_coul_long_with_pppm_disp(pkg, W, orc, tmp_path):
     fk, ek, vk = pp.compute(s["x"], B[s["type"]])
     assert th[0, 2] == pytest.approx(ev[0] + ek, rel=1e-9)
     assert np.abs(th[:, 4] - th[0, 4]).max() < 5e-4 * abs(th[0, 4])   # stiff, strongly compressed system
+
+
+@pytest.mark.gpu
+def test_in_buck_coul_cut_and_in_buck_big_run_like_the_oracle(pkg, W, orc, tmp_path):
+    """the other two shipped scripts: in.buck_coul_cut (data.aC x 2^3 here, 4^3 as shipped) and in.buck_big
+    (12x12x12 cells here): step-0 energy and pressure against the oracle, `delay 5 every 1 check yes` cadence"""
+    txt = scripts.IN_BUCK_COUL_CUT.format(r=2, steps=10, thermo=5)
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bcc", txt, W), "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    s = W.aC_system(2, jitter=0.0)
+    u = W.UNITS["metal"]
+    co = W.coeffs_aC(10.0, 10.0)
+    P = orc.Params(orc.BUCK_COUL_CUT, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"])
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    assert th[0, 2] == pytest.approx(ev[0] + ev[1], rel=1e-10)
+    n = len(s["x"])
+    vol = np.prod(s["boxhi"] - s["boxlo"])
+    press = ((3 * n - 3) * u["boltz"] * 300.0 + ev[2] + ev[3] + ev[4]) / 3.0 / vol * 1.6021765e6
+    assert th[0, 5] == pytest.approx(press, rel=1e-8)
+    # in.buck_big: delay 5 => no rebuild during the first 5 steps whatever the atoms do
+    txt = scripts.IN_BUCK_BIG.format(nx=12, ny=12, nz=12, steps=5, thermo=5)
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.big", txt), "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    s = W.fcc_system(12, 12, 12, jitter=0.0)
+    co = W.coeffs_in_buck(5.0)
+    P = orc.Params(orc.BUCK, 1, co["A"], co["rho"], co["C"], co["cut_lj"])
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], None, s["boxlo"], s["boxhi"], 0.3)
+    assert th[0, 2] == pytest.approx(ev[0], rel=1e-10)
+    assert "Neighbor list builds = 0" in r.stdout
+    # continuum estimate 4/3 pi (5.3)^3 * 0.8442 = 526.5 (SURVEY 6.2); the perfect fcc lattice has 530 within 5.3
+    assert "Ave neighs/atom = 530" in r.stdout
