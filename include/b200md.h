@@ -166,7 +166,7 @@ typedef struct {
 
 int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p);
 /* forces are ACCUMULATED into the device force array (f +=, pppm_intel.cpp:628-630).
- * energy / virial[6] may be NULL. */
+ * energy / virial[6] may be NULL.  eflag bit1 / vflag bit2 (per-atom tallies, stock poisson_peratom) are refused. */
 int b200md_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double virial[6]);
 /* host-buffer form of PPPMIntel::compute: x[n][3], q[n] in, f[n][3] += out */
 int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const double *x,

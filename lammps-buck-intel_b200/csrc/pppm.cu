@@ -1245,6 +1245,10 @@ static int compute_all(b200md_ctx *ctx, const PppmView &v, int eflag, int vflag,
 
 int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial) {
   if (!ctx->pppm && !ctx->pppm6) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
+  // the reference hands per-atom tallies to stock poisson_peratom / fieldforce_peratom (pppm_intel.cpp:224-229,
+  // 281-301), which are not part of its hot path and not provided here: refuse rather than return zeros
+  if ((eflag & 2) || (vflag & 4))
+    return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial from PPPM is not provided (SURVEY 8f-2)");
   PppmView v;
   v.n = ctx->nlocal;
   v.xq = ctx->xq.p;
