@@ -536,6 +536,7 @@ struct PassGeom {
   int inner;
   long outer;
   long estride;
+  long split;   // REAL_OUT = 2: real part to out_real[g], imaginary part to out_real[g + split]
 };
 
 // TB (lines per block) and blockDim.x are powers of two: lgTB = log2(TB), lgtpl = log2(blockDim.x / TB).  A thread
@@ -576,7 +577,8 @@ k_fft_pass(FftPlan1d pl, PassGeom pg, int lgTB, int LP, const double *in_real, c
     for (int k = k0; k < n; k += kstep) {
       const long g = base + (long)k * pg.estride;
       const double2 v = res[t * LP + k];
-      if (REAL_OUT) out_real[g] = v.x;
+      if (REAL_OUT == 2) { out_real[g] = v.x; out_real[g + pg.split] = v.y; }
+      else if (REAL_OUT) out_real[g] = v.x;
       else out[g] = v;
     }
   }
@@ -589,8 +591,9 @@ template <int NCOMP, int EV>
 __global__ void __launch_bounds__(512)
 k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
-                const double *__restrict__ fky, const double *__restrict__ fkz, double scaleinv, double g_ewald,
-                double *__restrict__ ev_partial, int disp) {
+                const double *__restrict__ fky, const double *__restrict__ fkz, const double *__restrict__ fkxg,
+                const double *__restrict__ fkyg, double scaleinv, double g_ewald, double *__restrict__ ev_partial,
+                int disp) {
   extern __shared__ double2 smem[];
   const int TB = 1 << lgTB;
   const int lgtpl = 31 - __clz(blockDim.x) - lgTB;
@@ -663,16 +666,25 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
       ev_partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sum;
     }
   }
-  for (int comp = 0; comp < NCOMP; comp++) {
+  // ik: the three gradient fields are real, so two of them share one complex inverse transform:
+  // pack 0 = Wx + i Wy (real part -> Ex, imaginary part -> Ey), pack 1 = Wz, with W? = (fk?*Im V, -fk?*Re V)
+  // (pppm_intel.cpp:894-895, 921-922, 949-950).  Three inverse 3-D FFTs become two.
+  // The reference keeps Re(IFFT(W)); on an even grid W is not Hermitian at its own Nyquist plane (fk there is
+  // -n/2 * unitk, not 0) and that plane contributes exactly nothing to the real part — so dropping it (fkxg/fkyg
+  // have the Nyquist entry zeroed) leaves Re(IFFT(Wx)) unchanged and makes Wx, Wy exactly Hermitian, which is what
+  // the packing needs for the two fields not to leak into each other.
+  constexpr int NPACK = NCOMP == 3 ? 2 : 1;
+  for (int comp = 0; comp < NPACK; comp++) {
     double2 *a = res, *b = other;  // V lives in bufV; a/b are free ping-pong buffers
     if (live) {
-      const double fkxy = comp == 0 ? fkx[ix] : fky[iy];
+      const double kx = NCOMP == 3 ? fkxg[ix] : 0.0, ky = NCOMP == 3 ? fkyg[iy] : 0.0;
       for (int k = k0; k < n; k += kstep) {
         const double2 v = bufV[t * LP + k];
         if (NCOMP == 1) a[t * LP + k] = v;
+        else if (comp == 0) a[t * LP + k] = make_double2(kx * v.y + ky * v.x, ky * v.y - kx * v.x);
         else {
-          const double fk = comp == 2 ? fkz[k] : fkxy;
-          a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);  // work2 = (fk*Im, -fk*Re), :894-895
+          const double fk = fkz[k];
+          a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);
         }
       }
     }
@@ -848,9 +860,9 @@ void compute_gf_denom(PppmConst &c) {
 
 int fft3d_forward_xy(b200md_ctx *ctx, PppmState &ps, const double *density, double2 *work, int nplanes) {
   const PppmConst &c = ps.c;
-  PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1};
+  PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1, 0};
   TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD)));
-  PassGeom gy{(long)c.nx * nplanes, c.nx, (long)c.nx * c.ny, (long)c.nx};
+  PassGeom gy{(long)c.nx * nplanes, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
   TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work, work, nullptr, S_FWD)));
   return 0;
 }
@@ -933,15 +945,18 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     auto kern = k_fft_z_poisson<3, E>;                                                                          \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
     kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
-                                             ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, scaleinv, c.g_ewald,   \
-                                             ps.partial.p, ps.p.dispersion);                                    \
+                                             ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, ps.fkx_g.p,            \
+                                             ps.fky_g.p + ps.ylos[me], scaleinv, c.g_ewald, ps.partial.p,       \
+                                             ps.p.dispersion);                                                  \
   } while (0)
       if (ev) ZK(1); else ZK(0);
 #undef ZK
       KERNEL_OK(ctx, "k_fft_z_poisson");
     }
-    // ---- transpose back, all components in one exchange: to rank q its planes (contiguous in [z][row][x]) ---------
-    RESERVE(ctx, ps.trecv, (size_t)plane * nzo * ncomp);
+    // ---- transpose back, both packed transforms (Ex + i Ey, Ez) in one exchange: to rank q its planes (contiguous
+    //      in [z][row][x]) ----------------------------------------------------------------------------------------
+    const int npack = 2;
+    RESERVE(ctx, ps.trecv, (size_t)plane * nzo * npack);
     {
       CommGroup grp(ctx);
       long roff = 0;
@@ -949,23 +964,26 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
         const long scnt = (long)(ps.pzhi[q] - ps.pzlo[q]) * nyl * nx;
         const long rcnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * nx;
         rr.boff[q] = roff;
-        for (int comp = 0; comp < ncomp; comp++) {
+        for (int comp = 0; comp < npack; comp++) {
           TRY(grp.send(ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * nx, scnt * sizeof(double2), q));
           TRY(grp.recv(ps.trecv.p + roff + (size_t)comp * rcnt, rcnt * sizeof(double2), q));
         }
-        roff += rcnt * ncomp;
+        roff += rcnt * npack;
       }
       TRY(grp.end());
     }
-    RESERVE(ctx, ps.work2, (size_t)plane * nzo * ncomp);
-    k_tr_unpack<<<cdiv(plane * nzo * ncomp, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, ncomp, rr, ps.trecv.p, ps.work2.p);
+    RESERVE(ctx, ps.work2, (size_t)plane * nzo * npack);
+    k_tr_unpack<<<cdiv(plane * nzo * npack, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, npack, rr, ps.trecv.p, ps.work2.p);
     KERNEL_OK(ctx, "k_tr_unpack");
-    // ---- inverse y, x on the owned planes; the x pass keeps the real part -----------------------------------------
-    RESERVE(ctx, ps.vd_own, (size_t)plane * nzo * ncomp);
-    PassGeom gy{(long)nx * nzo * ncomp, nx, plane, (long)nx};
+    // ---- inverse y, x on the owned planes; the x pass stores Re (and Im of the first pack) as the three fields ------
+    const long nown = plane * nzo;
+    RESERVE(ctx, ps.vd_own, (size_t)nown * ncomp);
+    PassGeom gy{(long)nx * nzo * npack, nx, plane, (long)nx, 0};
     TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
-    PassGeom gx{(long)ny * nzo * ncomp, 1, (long)nx, 1};
-    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+    PassGeom gxy{(long)ny * nzo, 1, (long)nx, 1, nown};
+    TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+    PassGeom gz{(long)ny * nzo, 1, (long)nx, 1, 0};
+    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nown, nullptr, ps.vd_own.p + 2 * nown, S_BWD)));
   }
   {
     ScopedTimer tm(ctx, T_COMM);
@@ -1145,18 +1163,27 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     auto kern = k_fft_z_poisson<NC, E>;                                                                       \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, ilog2(TB), LP, ps.work1.p, ps.work2.p,          \
-                                             ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, scaleinv, c.g_ewald, \
-                                             ps.partial.p, ps.p.dispersion);                                  \
+                                             ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, ps.fkx_g.p, ps.fky_g.p,   \
+                                             scaleinv, c.g_ewald, ps.partial.p, ps.p.dispersion);            \
   } while (0)
     if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
     else { if (ev) ZK(3, 1); else ZK(3, 0); }
 #undef ZK
     KERNEL_OK(ctx, "k_fft_z_poisson");
-    // inverse y over ncomp*nz planes, inverse x storing the real part
-    PassGeom gy{(long)c.nx * c.nz * ncomp, c.nx, (long)c.nx * c.ny, (long)c.nx};
+    // inverse y over the packed transforms (2 for ik: Ex + i Ey and Ez; 1 for ad), inverse x storing the real part
+    // (and, for the first pack, the imaginary part as the second field)
+    const int npack = ad ? 1 : 2;
+    PassGeom gy{(long)c.nx * c.nz * npack, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
     TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
-    PassGeom gx{(long)c.ny * c.nz * ncomp, 1, (long)c.nx, 1};
-    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
+    if (ad) {
+      PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
+    } else {
+      PassGeom gxy{(long)c.ny * c.nz, 1, (long)c.nx, 1, nfft};
+      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
+      PassGeom gz{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nfft, nullptr, ps.vd.p + 2 * nfft, S_BWD)));
+    }
   }
   if (ev) {
     ScopedTimer tm(ctx, T_POISSON);
@@ -1211,6 +1238,7 @@ static void free_state(PppmState *&slot) {
   PppmState *ps = slot;
   if (!ps) return;
   for (int d = 0; d < 3; d++) ps->tw[d].free_();
+  ps->fkx_g.free_(); ps->fky_g.free_();
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
   ps->work1.free_(); ps->work2.free_(); ps->sf_pre.free_(); ps->Btype.free_();
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
@@ -1400,6 +1428,12 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
       fk.assign(ng[d], 0.0);
       for (int i = 0; i < ng[d]; i++) fk[i] = unitk * (i - ng[d] * (2 * i / ng[d]));
       CUDA_OK(ctx, cudaMemcpy(dst[d]->p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));
+      if (d < 2) {   // gradient copies with the Nyquist entry dropped (see k_fft_z_poisson)
+        DevBuf<double> &gdst = d == 0 ? ps->fkx_g : ps->fky_g;
+        RESERVE(ctx, gdst, (size_t)ng[d]);
+        if (ng[d] % 2 == 0) fk[ng[d] / 2] = 0.0;
+        CUDA_OK(ctx, cudaMemcpy(gdst.p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));
+      }
     }
   }
   if (p->dispersion) {
@@ -1529,9 +1563,9 @@ int b200md_fft3d_host(b200md_ctx *ctx, double *data, int nx, int ny, int nz, int
   if (!rc) {
     cudaMemcpyAsync(buf.p, data, nfft * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
     const double s = dir > 0 ? S_FWD : S_BWD;
-    PassGeom gx{(long)ny * nz, 1, (long)nx, 1};
-    PassGeom gy{(long)nx * nz, nx, (long)nx * ny, (long)nx};
-    PassGeom gz{(long)nx * ny, nx * ny, 0, (long)nx * ny};
+    PassGeom gx{(long)ny * nz, 1, (long)nx, 1, 0};
+    PassGeom gy{(long)nx * nz, nx, (long)nx * ny, (long)nx, 0};
+    PassGeom gz{(long)nx * ny, nx * ny, 0, (long)nx * ny, 0};
     rc = launch_pass<1, 0, 0>(ctx, pl[0], gx, nullptr, buf.p, buf.p, nullptr, s);
     if (!rc) rc = launch_pass<0, 0, 0>(ctx, pl[1], gy, nullptr, buf.p, buf.p, nullptr, s);
     if (!rc) rc = launch_pass<0, 0, 0>(ctx, pl[2], gz, nullptr, buf.p, buf.p, nullptr, s);

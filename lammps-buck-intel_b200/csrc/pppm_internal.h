@@ -30,6 +30,7 @@ struct PppmState {
   double volume = 0;
   FftPlan1d plan[3];
   DevBuf<double2> tw[3];
+  DevBuf<double> fkx_g, fky_g;   // gradient wave numbers: fkx/fky with the Nyquist entry zeroed (packed inverse FFT)
   DevBuf<double> greensfn, fkx, fky, fkz, density, vd;  // vd: 3*nfft (ik) or nfft (ad: u)
   DevBuf<double2> work1, work2;                         // work2: 3*nfft (ik) / nfft (ad)
   DevBuf<double> sf_pre;                                // ad: 6*nfft
