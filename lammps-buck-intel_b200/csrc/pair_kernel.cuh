@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -492,13 +493,18 @@ static inline int pick_tpa(const b200md_ctx *ctx, int nlocal, long long total_en
   return avg >= 48.0 ? 8 : 4;
 }
 
+static inline int pair_threads() {   // tuning knob (power of two, <= 256)
+  static const int t = getenv("B200MD_PAIR_THREADS") ? atoi(getenv("B200MD_PAIR_THREADS")) : 256;
+  return t;
+}
+
 template <int STYLE, class flt_t, int EVFLAG>
 int launch_tpa(b200md_ctx *ctx, const PairView &v, int tpa, int variant, const PairConsts<flt_t> &pc,
                const flt_t *coeff, const flt_t *ctab, const flt_t *dtab, const flt_t *exptab, double *ev_partial,
                int nblocks) {
   typedef typename V4<flt_t>::type vec4;
 #define LAUNCH(T, G, P)                                                                                    \
-  k_pair<STYLE, flt_t, EVFLAG, T, G, P><<<nblocks, 256, 0, ctx->stream>>>(                                  \
+  k_pair<STYLE, flt_t, EVFLAG, T, G, P><<<nblocks, pair_threads(), 0, ctx->stream>>>(                       \
       v.nlocal, (const vec4 *)v.x, v.type, v.numneigh, v.offsets, v.entries, pc, coeff, ctab, dtab, exptab, \
       v.f, ev_partial)
 #define LAUNCH_T(T)                                \
@@ -533,7 +539,7 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
   const int variant = !v.packed_type ? 2 : ((pc.coultable || pc.disptable) ? 1 : 0);
   if (has_special && v.packed_type) return b2_fail(ctx, B200MD_EINVAL, "packed-type list with special bits");
   const int tpa = pick_tpa(ctx, v.nlocal, total_entries);
-  const int nblocks = cdiv((long)v.nlocal * tpa, 256);
+  const int nblocks = cdiv((long)v.nlocal * tpa, pair_threads());
   if (nblocks == 0) {
     if (evflag) CUDA_OK(ctx, cudaMemsetAsync(ev_dev, 0, 8 * sizeof(double), ctx->stream));
     return 0;
