@@ -15,7 +15,7 @@ namespace pairk {
 
 enum { C_CUTSQ = 0, C_CUT_LJSQ, C_CUT_COULSQ, C_BUCK1, C_BUCK2, C_RHOINV, C_A, C_C, C_OFFSET, C_N };
 
-enum { MC_L = 0, MC_MAGIC, MC_LN2HI, MC_LN2LO, MC_E7, MC_E6, MC_E5, MC_E4, MC_E3, MC_HALF, MC_ONE, MC_R375, MC_EWP, MC_A1, MC_A2,
+enum { MC_L = 0, MC_MAGIC, MC_LN2, MC_E7, MC_E6, MC_E5, MC_E4, MC_E3, MC_HALF, MC_ONE, MC_R375, MC_EWP, MC_A1, MC_A2,
        MC_A3, MC_A4, MC_A5, MC_EWF, MC_N };
 
 template <class flt_t>
@@ -36,10 +36,11 @@ template <> struct V4<float> { typedef float4 type; };
 // ---- double-precision math of the hot loop ---------------------------------------------------------------------
 // The loop is bound by the FP64 pipe and by issue slots (ncu: profiles/r01_*), so the libdevice routines (generic
 // range checks, ~17 DFMA per exp, a correctly-rounded divide) are replaced by kernels sized for this loop's argument
-// ranges and error budget: every function below is accurate to <= 4e-16 relative (a few ulp), against a parity bar of
-// 1e-9 on forces.
-//   exp:   x = (n/64) ln2 + r, |r| <= ln2/128; exp(x) = 2^(n>>6) * T[n&63] * (1 + expm1(r)), T = 2^(k/64) in shared
-//          memory, expm1 by a degree-5 Taylor polynomial (remainder r^6/720 < 4e-17).  10 FP64 ops, no branches.
+// ranges and error budget: exp is accurate to 4e-14 relative, rsqrt / rcp to a few ulp, against a parity bar of 1e-9 on
+// forces (measured: max force error vs the oracle 6e-13, __graft_entry__.smoke).
+//   exp:   x = (n/64) ln2 + r, |r| <= ln2/128 (one FMA: n * fl(ln2/64) is exact inside it);
+//          exp(x) = 2^(n>>6) * T[n&63] * (1 + expm1(r)), T = 2^(k/64) in shared memory, expm1 by a degree-4 Taylor
+//          polynomial (remainder r^5/120 < 4e-14).  8 FP64 ops, no branches.
 //   rsqrt: MUFU.RSQ64H seed (~2^-20) + one third-order step (error e^3).  rcp likewise.
 #ifndef B2_EXP_TAB
 #define B2_EXP_TAB 64
@@ -59,16 +60,13 @@ template <> struct V4<float> { typedef float4 type; };
 static inline void fill_math_consts(double *mc) {
 #if B2_EXP_TAB == 64
   mc[MC_L] = 92.332482616893656877;        // 64 / ln 2
-  mc[MC_LN2HI] = 1.0830424696249145e-02;   // ln2/64 to full double precision (the reduction is a single FMA)
-  mc[MC_LN2LO] = 0.0;
+  mc[MC_LN2] = 1.0830424696249145e-02;     // ln2/64 to full double precision (the reduction is a single FMA)
 #elif B2_EXP_TAB == 32
   mc[MC_L] = 46.16624130844683;
-  mc[MC_LN2HI] = 0.021660849392446835;
-  mc[MC_LN2LO] = 5.145609244655338e-14;
+  mc[MC_LN2] = 0.02166084939249829;        // ln2/32
 #else
   mc[MC_L] = 23.083120654223414;
-  mc[MC_LN2HI] = 0.04332169878489367;
-  mc[MC_LN2LO] = 1.0291218489310676e-13;
+  mc[MC_LN2] = 0.04332169878499658;        // ln2/16
 #endif
   mc[MC_MAGIC] = 6755399441055744.0;       // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
   mc[MC_E7] = 1.0 / 5040.0; mc[MC_E6] = 1.0 / 720.0;
@@ -86,7 +84,7 @@ __device__ __forceinline__ double fast_exp(const double x, const double *__restr
   const int n = __double2loint(t);
   const double nf = t - mc[MC_MAGIC];
   // one FMA: nf * (ln2/64) is exact inside it, and |nf| * |fl(ln2/64) - ln2/64| < 4e-15 for |x| < 700
-  const double r = fma(nf, -mc[MC_LN2HI], x);
+  const double r = fma(nf, -mc[MC_LN2], x);
 #if B2_EXP_TAB == 64
   // |r| <= ln2/128: the degree-4 remainder r^5/120 is < 4e-14 relative — four orders inside the 1e-9 parity bar
   double p = mc[MC_E4];
