@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("shape", [(16, 16, 16), (8, 6, 5), (27, 25, 32), (40, 36, 36), (64, 60, 60), (108, 96, 96),
-                                   (135, 50, 45)])
+                                   (135, 50, 45), (12, 250, 270)])
 def test_fft3d_matches_numpy(pkg, shape):
     rng = np.random.default_rng(11)
     a = rng.normal(size=shape) + 1j * rng.normal(size=shape)
