@@ -394,38 +394,71 @@ k_make_rho(PppmConst c, const int *__restrict__ cell_start, const double4 *__res
 
 struct TileGeom {
   int ntx, nty, ntz, E;   // tiles per dimension, E = RHO_T + order - 1
+  signed char lane_pt[64];  // lane + 32 r -> (m,l) point m * order + l of the stencil's xy face, -1 = idle
 };
 
-// ORDER is a template parameter: the stencil point(s) of a lane — p = lane + 32 r -> (n,m,l) — are fixed for the whole
-// kernel, so their shared-memory offsets are computed once.  Per atom, lanes 0..3*ORDER-1 evaluate the 3*ORDER
-// one-dimensional weights by Horner (pppm_intel.cpp:476-488, same operation order) and the stencil lanes fetch their
-// three factors by shuffle; the next atom's {dx,dy,dz,q} is prefetched while the current one is accumulated.
+// x pitch of the shared-memory stencil block: the smallest >= E for which rho_lane_map finds conflict-free rounds
+__host__ __device__ constexpr int rho_pitch(int order) { return order == 5 ? 13 : RHO_T + order - 1; }
+
+// x pitch and lane -> (m,l) assignment: a round touches the addresses (m * pitch + l) of its active lanes; 64-bit
+// shared-memory accesses are served per half warp, 16 doubles per wavefront, so the 16 lanes of a half warp get points
+// with distinct (m * pitch + l) mod 16.  Order 5: pitch 13 puts the 25 points into lanes 0..24 of one round.
+static void rho_lane_map(int order, TileGeom &tg) {
+  const int O2 = order * order, NR2 = (O2 + 31) / 32, EP = rho_pitch(order);
+  std::vector<int> left(O2);
+  for (int p = 0; p < O2; p++) left[p] = p;
+  signed char *map = tg.lane_pt;
+  for (int k = 0; k < 64; k++) map[k] = -1;
+  for (int h = 0; h < 2 * NR2 && !left.empty(); h++) {   // half warps in order
+    bool used[16] = {};
+    int filled = 0;
+    for (size_t k = 0; k < left.size() && filled < 16;) {
+      const int p = left[k], res = ((p / order) * EP + p % order) % 16;
+      if (!used[res]) { used[res] = true; map[16 * h + filled++] = (signed char)p; left.erase(left.begin() + k); }
+      else k++;
+    }
+  }
+  // not reached for order <= 7 with rho_pitch: points that would conflict fill the idle lanes
+  for (int k = 0; k < 32 * NR2 && !left.empty(); k++)
+    if (map[k] < 0) { map[k] = (signed char)left.back(); left.pop_back(); }
+}
+
+// ORDER is a template parameter.  A lane owns the point (m,l) of the stencil's xy face (two for orders 6 and 7) for
+// the whole kernel: it keeps the Horner coefficients of rho[0][l] and rho[1][m] in registers and evaluates them per
+// atom itself (pppm_intel.cpp:476-488, same operation order); lanes 0..ORDER-1 also evaluate delvolinv*q*rho[2][n],
+// which every lane fetches by shuffle while it walks the ORDER planes of the stencil.  Per atom that is ORDER
+// shared-memory read-modify-writes and ORDER shuffles per lane; the next atom's {dx,dy,dz,q} is prefetched.
 // ROUNDF: mixed mode rounds the weights to float like the reference's `flt_t rho[3][INTEL_P3M_MAXORDER]` (:474).
 template <int ORDER, int ROUNDF>
 __global__ void __launch_bounds__(128)
 k_rho_tiles(PppmConst c, TileGeom tg, const int *__restrict__ cell_start, const double4 *__restrict__ pa_x,
             const int *__restrict__ pa_cx, double *__restrict__ tilebuf) {
   extern __shared__ double s_tiles[];
-  __shared__ double s_rc[ORDER * ORDER];
-  for (int k = threadIdx.x; k < ORDER * ORDER; k += blockDim.x) s_rc[k] = c.rho_coeff[k];
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long tile = (long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
   if (tile >= ntiles) return;
-  constexpr int E = RHO_T + ORDER - 1, E3 = E * E * E, O2 = ORDER * ORDER, O3 = O2 * ORDER, NR = (O3 + 31) / 32;
-  double *t = s_tiles + (size_t)warp * E3;
-  for (int k = lane; k < E3; k += 32) t[k] = 0.0;
-  int off[NR], src_z[NR], src_y[NR], src_x[NR];
+  constexpr int E = RHO_T + ORDER - 1, E3 = E * E * E, O2 = ORDER * ORDER, NR2 = (O2 + 31) / 32;
+  constexpr int EP = rho_pitch(ORDER), EEP = E * EP, E3S = E * EEP;
+  double *t = s_tiles + (size_t)warp * E3S;
+  for (int k = lane; k < E3S; k += 32) t[k] = 0.0;
+  unsigned off[NR2];
+  bool act[NR2];
+  double cxw[NR2][ORDER], cyw[NR2][ORDER], czw[ORDER];
 #pragma unroll
-  for (int r = 0; r < NR; r++) {
-    const int p = min(lane + 32 * r, O3 - 1);
-    const int n = p / O2, rem = p - n * O2, m = rem / ORDER, l = rem - m * ORDER;
-    off[r] = (n * E + m) * E + l;
-    src_z[r] = 2 * ORDER + n; src_y[r] = ORDER + m; src_x[r] = l;
+  for (int r = 0; r < NR2; r++) {
+    const int p = tg.lane_pt[lane + 32 * r];
+    act[r] = p >= 0;
+    const int m = max(p, 0) / ORDER, l = max(p, 0) - m * ORDER;
+    off[r] = (m * EP + l) * 8;   // bytes
+#pragma unroll
+    for (int k = 0; k < ORDER; k++) {
+      cxw[r][k] = c.rho_coeff[k * ORDER + l];
+      cyw[r][k] = c.rho_coeff[k * ORDER + m];
+    }
   }
-  // this lane's weight: dimension wd (0 x, 1 y, 2 z), stencil index wk
-  const int wl = min(lane, 3 * ORDER - 1), wd = wl / ORDER, wk = wl - wd * ORDER;
+#pragma unroll
+  for (int k = 0; k < ORDER; k++) czw[k] = c.rho_coeff[k * ORDER + min(lane, ORDER - 1)];
   __syncwarp();
   const int tx = (int)(tile % tg.ntx), ty = (int)((tile / tg.ntx) % tg.nty), tz = (int)(tile / ((long)tg.ntx * tg.nty));
   const int x0 = tx * RHO_T, y0 = ty * RHO_T, z0 = tz * RHO_T;
@@ -444,59 +477,75 @@ k_rho_tiles(PppmConst c, TileGeom tg, const int *__restrict__ cell_start, const 
       re[k] = cell_start[row + x1];
     }
   }
-  int r = -1, a = 0, e = 0;
+  // rb: shared-memory byte address of the stencil block's corner for the current cell row (ry, rz), minus x0
+  const unsigned t_sa = (unsigned)__cvta_generic_to_shared(t) - (unsigned)x0 * 8u;
+  int r = -1, a = 0, e = 0, ry = -1;
+  unsigned rb = t_sa - EP * 8u;
   auto advance = [&]() {   // next atom of the tile; warp-uniform
     a++;
     while (a >= e && ++r < nrows) {
       a = __shfl_sync(0xffffffffu, r < 32 ? rs[0] : rs[1], r & 31);
       e = __shfl_sync(0xffffffffu, r < 32 ? re[0] : re[1], r & 31);
+      rb += EP * 8u;
+      if (++ry == nyt) { ry = 0; rb += (E - nyt) * EP * 8u; }
     }
+  };
+  auto horner = [&](const double *cf, const double d) {
+    double w = 0.0;
+#pragma unroll
+    for (int l = ORDER - 1; l >= 0; l--) w = cf[l] + w * d;
+    if (ROUNDF) w = (double)(float)w;
+    return w;
   };
   advance();
   if (r < nrows) {
     double4 nxt = pa_x[a];
-    int cx_nxt = pa_cx[a], row_nxt = r;
+    unsigned sa_nxt = rb + (unsigned)pa_cx[a] * 8u;
     while (true) {
       const double4 cur = nxt;
-      const int cx = cx_nxt, rowc = row_nxt;
+      const unsigned sa = sa_nxt;
       advance();
       const bool more = r < nrows;
-      if (more) { nxt = pa_x[a]; cx_nxt = pa_cx[a]; row_nxt = r; }
-      const double d = wd == 0 ? cur.x : (wd == 1 ? cur.y : cur.z);
-      double w = 0.0;
+      if (more) { nxt = pa_x[a]; sa_nxt = rb + (unsigned)pa_cx[a] * 8u; }
+      // z0 = delvolinv*q*rho[2][n] on lane n, y0 = z0*rho[1][m], x0 = y0*rho[0][l]  (pppm_intel.cpp:490-501)
+      const double zl = cur.w * horner(czw, cur.z);
+      double wx[NR2], wy[NR2];
 #pragma unroll
-      for (int l = ORDER - 1; l >= 0; l--) w = s_rc[l * ORDER + wk] + w * d;
-      if (ROUNDF) w = (double)(float)w;
-      const int base = ((rowc / nyt) * E + (rowc % nyt)) * E - x0 + cx;
+      for (int q = 0; q < NR2; q++) { wx[q] = horner(cxw[q], cur.x); wy[q] = horner(cyw[q], cur.y); }
 #pragma unroll
-      for (int q = 0; q < NR; q++) {
-        const double wz = __shfl_sync(0xffffffffu, w, src_z[q]);
-        const double wy = __shfl_sync(0xffffffffu, w, src_y[q]);
-        const double wx = __shfl_sync(0xffffffffu, w, src_x[q]);
-        // z0*rho[2][n] -> y0*rho[1][m] -> x0*rho[0][l]  (pppm_intel.cpp:490-501)
-        if (lane + 32 * q < O3) t[base + off[q]] += ((cur.w * wz) * wy) * wx;
+      for (int n = 0; n < ORDER; n++) {
+        const double zw = __shfl_sync(0xffffffffu, zl, n);
+#pragma unroll
+        for (int q = 0; q < NR2; q++)
+          if (act[q]) {
+            double acc;
+            const unsigned ad = sa + off[q] + (unsigned)(n * EEP * 8);   // ptxas folds the constant into the access
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(acc) : "r"(ad) : "memory");
+            acc += (zw * wy[q]) * wx[q];
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(acc) : "memory");
+          }
       }
       __syncwarp();
       if (!more) break;
     }
   }
   double *out = tilebuf + (size_t)tile * E3;
-  for (int k = lane; k < E3; k += 32) out[k] = t[k];
+  for (int k = lane; k < E3; k += 32) out[k] = t[(k / E) * EP + k % E];
 }
 
 // covering tiles of a point along one dimension: every tile (own, and up to two on either side, periodic) whose
 // cells [ulo,uhi] reach the point, i.e. ulo + nlower <= g <= uhi + nupper in the point's unwrapped frame.  Returns
-// the count and, per hit, the tile index and the local coordinate inside that tile's stencil block.
-__device__ __forceinline__ int cover1(int g, int n, int nt, int nlower, int nupper, int *tile, int *loc) {
+// the count and, per hit, the tile index and the local coordinate inside that tile's stencil block.  Evaluated on
+// the host once per setup (cover_table): the fold kernel reads the result as one int4 per coordinate.
+static int cover1(int g, int n, int nt, int nlower, int nupper, int *tile, int *loc) {
   const int t = g / RHO_T;
   int cnt = 0;
-#pragma unroll
   for (int dt = -2; dt <= 2; dt++) {
     int tt = t + dt, shift = 0;
     if (tt < 0) { tt += nt; shift = -n; }
     else if (tt >= nt) { tt -= nt; shift = n; }
     if (tt < 0 || tt >= nt) continue;
-    const int ulo = tt * RHO_T + shift, uhi = min(tt * RHO_T + RHO_T, n) - 1 + shift;
+    const int ulo = tt * RHO_T + shift, uhi = std::min(tt * RHO_T + RHO_T, n) - 1 + shift;
     if (g >= ulo + nlower && g <= uhi + nupper) {
       tile[cnt] = tt;
       loc[cnt] = g - ulo - nlower;
@@ -506,26 +555,49 @@ __device__ __forceinline__ int cover1(int g, int n, int nt, int nlower, int nupp
   return cnt;
 }
 
+// entries of one coordinate: tile * 16 + local coordinate (E <= 14), -1 = unused, hits first
+static bool cover_table(int n, int nt, int nlower, int nupper, int4 *out) {
+  for (int g = 0; g < n; g++) {
+    int tile[5], loc[5];
+    const int cnt = cover1(g, n, nt, nlower, nupper, tile, loc);
+    if (cnt > 4) return false;
+    int e[4] = {-1, -1, -1, -1};
+    for (int k = 0; k < cnt; k++) e[k] = tile[k] * 16 + loc[k];
+    out[g] = make_int4(e[0], e[1], e[2], e[3]);
+  }
+  return true;
+}
+
+// block = 32 x-points by 8 y-rows of one z plane; the sum runs over the covering tiles in a fixed order (z outer,
+// x inner, tiles in ascending offset), so the density does not depend on the launch geometry
 __global__ void __launch_bounds__(256)
-k_rho_fold(PppmConst c, TileGeom tg, const double *__restrict__ tilebuf, double *__restrict__ density) {
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
-  if (g >= nfft) return;
-  const int gx = (int)(g % c.nx), gy = (int)((g / c.nx) % c.ny), gz = (int)(g / ((long)c.nx * c.ny));
-  int txs[5], lxs[5], tys[5], lys[5], tzs[5], lzs[5];
-  const int nxc = cover1(gx, c.nx, tg.ntx, c.nlower, c.nupper, txs, lxs);
-  const int nyc = cover1(gy, c.ny, tg.nty, c.nlower, c.nupper, tys, lys);
-  const int nzc = cover1(gz, c.nz, tg.ntz, c.nlower, c.nupper, tzs, lzs);
+k_rho_fold(PppmConst c, TileGeom tg, const int4 *__restrict__ cover, const double *__restrict__ tilebuf,
+           double *__restrict__ density) {
+  const int gx = blockIdx.x * 32 + threadIdx.x, gy = blockIdx.y * 8 + threadIdx.y, gz = blockIdx.z;
+  if (gx >= c.nx || gy >= c.ny) return;
+  const int4 cx = cover[gx], cy = cover[c.nx + gy], cz = cover[c.nx + c.ny + gz];
+  const int ex[4] = {cx.x, cx.y, cx.z, cx.w}, ey[4] = {cy.x, cy.y, cy.z, cy.w}, ez[4] = {cz.x, cz.y, cz.z, cz.w};
   const int E = tg.E;
   const size_t E3 = (size_t)E * E * E;
   double rho = 0.0;
-  for (int k = 0; k < nzc; k++)
-    for (int j = 0; j < nyc; j++)
-      for (int i = 0; i < nxc; i++) {
-        const size_t tile = ((size_t)tzs[k] * tg.nty + tys[j]) * tg.ntx + txs[i];
-        rho += tilebuf[tile * E3 + ((size_t)lzs[k] * E + lys[j]) * E + lxs[i]];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (ez[k] < 0) break;
+    const size_t tz = (size_t)(ez[k] >> 4) * tg.nty;
+    const int lz = (ez[k] & 15) * E;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (ey[j] < 0) break;
+      const size_t tzy = (tz + (ey[j] >> 4)) * tg.ntx;
+      const int lzy = (lz + (ey[j] & 15)) * E;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (ex[i] < 0) break;
+        rho += tilebuf[(tzy + (ex[i] >> 4)) * E3 + lzy + (ex[i] & 15)];
       }
-  density[g] = rho;
+    }
+  }
+  density[((size_t)gz * c.ny + gy) * c.nx + gx] = rho;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1107,11 +1179,12 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (tiled) {
       TileGeom tg{cdiv(c.nx, RHO_T), cdiv(c.ny, RHO_T), cdiv(c.nz, RHO_T), RHO_T + c.order - 1};
+      rho_lane_map(c.order, tg);
       const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
       const size_t E3 = (size_t)tg.E * tg.E * tg.E;
       RESERVE(ctx, ps.tilebuf, (size_t)ntiles * E3);
-      const int wpb = 4;
-      const size_t smem = wpb * E3 * sizeof(double);
+      static const int wpb = env_int("B200MD_RHO_WPB", 3);
+      const size_t smem = (size_t)wpb * tg.E * tg.E * rho_pitch(c.order) * sizeof(double);
 #define RHO_TILES(O)                                                                                              \
   case O: {                                                                                                       \
     if (sizeof(flt_t) == 4) {                                                                                     \
@@ -1130,7 +1203,8 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
       }
 #undef RHO_TILES
       KERNEL_OK(ctx, "k_rho_tiles");
-      k_rho_fold<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, tg, ps.tilebuf.p, ps.density.p);
+      k_rho_fold<<<dim3(cdiv(c.nx, 32), cdiv(c.ny, 8), c.nz), dim3(32, 8), 0, ctx->stream>>>(c, tg, ps.cover.p, ps.tilebuf.p,
+                                                                                           ps.density.p);
       KERNEL_OK(ctx, "k_rho_fold");
     } else {  // grids smaller than two tiles per dimension: plain per-point gather
       const dim3 grid(cdiv(c.nx, 8), cdiv(c.ny, 8), cdiv(c.nz, 4));
@@ -1244,7 +1318,7 @@ static void free_state(PppmState *&slot) {
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
   ps->dens_own.free_(); ps->halo_s.free_(); ps->halo_r.free_(); ps->vd_own.free_(); ps->tsend.free_(); ps->trecv.free_();
   ps->workT.free_(); ps->workT2.free_();
-  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
+  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->cover.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
   delete ps;
   slot = nullptr;
 }
@@ -1405,6 +1479,15 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   if ((long)p->nx * p->ny * p->nz > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");
   compute_rho_coeffs(c);
   compute_gf_denom(c);
+  {  // make_rho fold: covering tiles of every x, y and (local) z coordinate
+    std::vector<int4> cov((size_t)c.nx + c.ny + c.nz);
+    if (!cover_table(c.nx, cdiv(c.nx, RHO_T), c.nlower, c.nupper, cov.data()) ||
+        !cover_table(c.ny, cdiv(c.ny, RHO_T), c.nlower, c.nupper, cov.data() + c.nx) ||
+        !cover_table(c.nz, cdiv(c.nz, RHO_T), c.nlower, c.nupper, cov.data() + c.nx + c.ny))
+      return b2_fail(ctx, B200MD_EINVAL, "PPPM grid too small for the tiled charge assignment");
+    RESERVE(ctx, ps->cover, cov.size());
+    CUDA_OK(ctx, cudaMemcpy(ps->cover.p, cov.data(), cov.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  }
   for (int d = 0; d < 3; d++) TRY(make_plan(ctx, ps->plan[d], ps->tw[d], ng[d]));
   const long nfft = ps->nfft;
   const bool ad = p->differentiation == 1;

@@ -42,6 +42,7 @@ struct PppmState {
   DevBuf<int4> pa_n;     // sorted: {nx,ny,nz, atom index}
   DevBuf<double> pa_w;   // sorted: [3*order] one-dimensional stencil weights (x, y, z)
   DevBuf<double> tilebuf;  // make_rho: per-tile stencil blocks (tile + halo)
+  DevBuf<int4> cover;      // make_rho fold: covering tiles per x / y / z coordinate (cover_table)
   DevBuf<int> pa_cx;     // sorted: wrapped x cell of the lower-left stencil corner
   DevBuf<unsigned char> scan_ws;
   DevBuf<double> partial, red;
