@@ -543,18 +543,18 @@ k_nb_mask(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__
   }
 }
 
-// Fill: a warp takes an atom.  Per block of 32 mask words: lane L owns word L, a warp prefix sum of the popcounts
-// gives its run's offset, it expands its set bits into the warp's row buffer in shared memory, and the warp copies the
-// buffer to the CSR row with full-width coalesced stores.
+// Fill: a warp takes an atom.  Lane L holds the atom's mask words L, L + 32, ..; the warp then walks the non-empty
+// words in order: the word is broadcast by shuffle, lane b of it (bit b set) fetches candidate b's entry from the
+// block's staged table and stores it at pos + popc(bits below b) — consecutive words extend the row contiguously, so
+// the partial stores merge in L2 — and pos advances by the word's popcount.
 #undef NB_FILLC
-#define NB_FILLC 2048       // candidates staged at a time (64 mask words)
+#define NB_FILLC 4096       // candidates staged at a time (128 mask words: the usual stencil fits one window)
 __global__ void __launch_bounds__(NB_THREADS)
 k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lstart, const int *__restrict__ gstart,
           BinGeom g, const long long *__restrict__ maskoff, const unsigned *__restrict__ maskbuf,
           const long long *__restrict__ offsets, int *__restrict__ entries, int pack_type) {
   __shared__ BinRanges R;
   __shared__ int s_j[NB_FILLC];
-  __shared__ int s_buf[NB_THREADS / 32][1024];   // per warp: the hits of one 32-word block, in row order
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NB_THREADS / 32;
   int ex, ey, ez;
   bin_of_block(g, blockIdx.x, ex, ey, ez);
@@ -567,7 +567,8 @@ k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lsta
   const int nwords = (ncand + 31) >> 5;
   const int nit = i1 - i0;
   const unsigned *mbase = maskbuf + maskoff[blockIdx.x];
-  int *buf = s_buf[warp];
+  const unsigned ltmask = (1u << lane) - 1u;
+  const unsigned sj_lane = (unsigned)__cvta_generic_to_shared(s_j) + (unsigned)lane * 4u;
   for (int c0 = 0; c0 < ncand; c0 += NB_FILLC) {
     const int nc = min(NB_FILLC, ncand - c0);
     __syncthreads();
@@ -589,28 +590,29 @@ k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lsta
         for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
         wpos += before;
       }
-      for (int wb = w0; wb < w1; wb += 32) {
-        const int wmine = wb + lane;
-        unsigned m = wmine < w1 ? mcol[(size_t)wmine * nit] : 0u;
-        const int cnt = __popc(m);
-        int incl = cnt;
+      int *row = entries + wpos;
+      asm volatile("" : "+l"(row));   // keep the row pointer in registers (else it is rebuilt from wpos per store)
+      unsigned mw[NB_FILLC / 1024];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
+      for (int q = 0; q < NB_FILLC / 1024; q++) {
+        const int w = w0 + q * 32 + lane;
+        mw[q] = w < w1 ? mcol[(size_t)w * nit] : 0u;
+      }
+      int pos = 0;
+#pragma unroll
+      for (int q = 0; q < NB_FILLC / 1024; q++) {
+        unsigned nz = __ballot_sync(0xffffffffu, mw[q] != 0u);
+        const unsigned sq = sj_lane + (unsigned)q * 4096u;   // this lane's column of the group's 32 x 32 entries
+        while (nz) {
+          const int b = __ffs(nz) - 1;
+          nz &= nz - 1;
+          const unsigned m = __shfl_sync(0xffffffffu, mw[q], b);
+          int jw;   // every lane loads (the table is fully in bounds); only the hit lanes store
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(jw) : "r"(sq + ((unsigned)b << 7)));
+          const int at = pos + __popc(m & ltmask);
+          if ((m >> lane) & 1u) asm volatile("st.global.u32 [%0], %1;" ::"l"(row + at), "r"(jw) : "memory");
+          pos += __popc(m);
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int o = incl - cnt;
-        const int *sj = s_j + ((wmine << 5) - c0);
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          buf[o++] = sj[b];
-        }
-        __syncwarp();
-        for (int k = lane; k < total; k += 32) entries[wpos + k] = buf[k];
-        __syncwarp();
-        wpos += total;
       }
     }
   }
