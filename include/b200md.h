@@ -183,8 +183,14 @@ int b200md_fft3d_host(b200md_ctx *ctx, double *data, int nx, int ny, int nz, int
 
 /* ------------------------------------------------------------------------------------------------
  * fix nve/intel — FixNVEIntel::initial_integrate / final_integrate / reset_dt
- * (fix_nve_intel.cpp:60-99, 103-127, 129-194), group all, per-type mass. */
+ * (fix_nve_intel.cpp:60-99, 103-127, 129-194); group all and per-type mass unless b200md_nve_set_group says otherwise. */
 int b200md_nve_setup(b200md_ctx *ctx, double dt);
+/* fix nve/intel on a sub-group and / or with per-atom masses: the `mask[i] & groupbit` and `atom->rmass` branches of
+ * FixNVEIntel::reset_dt (fix_nve_intel.cpp:147-190: _dtfm = 0 outside the group) and the `_dtfm[i] != 0.0` branch of
+ * initial_integrate (:88-97: atoms outside the group keep x and v).  ingroup[n] (0 / non-zero) and rmass[n] are in
+ * upload order; either may be NULL (group all / per-type mass).  Call after b200md_atoms_upload and before
+ * b200md_nve_setup.  One GPU only (the arrays are indexed by upload position). */
+int b200md_nve_set_group(b200md_ctx *ctx, const int *ingroup, const double *rmass);
 int b200md_nve_initial_integrate(b200md_ctx *ctx);
 int b200md_nve_final_integrate(b200md_ctx *ctx);
 

@@ -579,6 +579,15 @@ class Context:
     def nve_setup(self, dt):
         self._ck(self.lib.b200md_nve_setup(self.h, C.c_double(dt)))
 
+    def nve_set_group(self, ingroup=None, rmass=None):
+        """fix nve on a sub-group (0/1 per atom) and / or with per-atom masses, upload order; before nve_setup"""
+        g = None if ingroup is None else np.ascontiguousarray(ingroup, dtype=np.int32)
+        m = None if rmass is None else np.ascontiguousarray(rmass, dtype=np.float64)
+        self._keep = (g, m)
+        self._ck(self.lib.b200md_nve_set_group(
+            self.h, None if g is None else g.ctypes.data_as(C.POINTER(C.c_int)),
+            None if m is None else m.ctypes.data_as(C.POINTER(C.c_double))))
+
     def nve_initial_integrate(self):
         self._ck(self.lib.b200md_nve_initial_integrate(self.h))
 

@@ -189,6 +189,7 @@ void b200md_ctx_destroy(b200md_ctx *ctx) {
   b2_pppm_free(ctx);
   b2_comm_free(ctx);
   ctx->xq.free_(); ctx->v.free_(); ctx->f.free_(); ctx->xqf.free_();
+  ctx->nve_group.free_(); ctx->nve_rmass.free_();
   ctx->type.free_(); ctx->tag.free_(); ctx->inv_tag.free_(); ctx->stage.free_();
   ctx->ev_partial.free_(); ctx->ev_out.free_();
   PairState &ps = ctx->pair;
@@ -287,6 +288,7 @@ int b200md_atoms_upload(b200md_ctx *ctx, int nlocal, int ntypes, const double *x
   ctx->neigh.ready = false;
   ctx->neigh.last_build = -1;
   ctx->nve_ready = false;
+  ctx->nve_grouped = ctx->nve_has_rmass = false;   // a new set of atoms: group / rmass have to be given again
   return 0;
 }
 

@@ -124,6 +124,9 @@ struct b200md_ctx {
   int device = 0;
   int prec = B200MD_PREC_DOUBLE;
   cudaStream_t stream = nullptr;
+  DevBuf<int> nve_group;       // fix nve on a sub-group: 0 / 1 per atom, upload order (b200md_nve_set_group)
+  DevBuf<double> nve_rmass;    // per-atom masses, upload order
+  bool nve_grouped = false, nve_has_rmass = false;
   cudaStream_t copy_stream = nullptr;   // device->host copies that overlap the force kernels (b200md_step_host)
   cudaEvent_t ev_copy = nullptr;
   // k-space overlap: particle_map .. poisson of PPPM run on `kstream` (higher priority) underneath the FP64-bound pair

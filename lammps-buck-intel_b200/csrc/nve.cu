@@ -6,24 +6,31 @@
 // so x and v are bit-identical to the CPU oracle step for step given identical forces.
 // dtf/mass rides in v.w; the mixed-mode float copy of the positions (IntelBuffers::thr_pack,
 // intel_buffers.h:185-203) is written by the same kernel instead of a separate pack pass.
+#include <vector>
+
 #include "internal.h"
 
 namespace {
 
+// _dtfm of FixNVEIntel::reset_dt (fix_nve_intel.cpp:147-190): dtf / mass[type] or dtf / rmass[i]; 0 outside the group
 __global__ void k_nve_set_dtfm(int n, const int *__restrict__ type, const double *__restrict__ mass, double dtf,
-                               double4 *__restrict__ v) {
+                               double4 *__restrict__ v, const int *__restrict__ tag, int first_id,
+                               const int *__restrict__ grp, const double *__restrict__ rmass) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 vi = v[i];
-  vi.w = dtf / mass[type[i]];
+  const int t = tag[i] - first_id;
+  const double m = rmass ? rmass[t] : mass[type[i]];
+  vi.w = (grp && !grp[t]) ? 0.0 : dtf / m;
   v[i] = vi;
 }
 
 __global__ void k_nve_initial(int n, double dtv, double4 *__restrict__ xq, double4 *__restrict__ v,
-                              const double4 *__restrict__ f, float4 *__restrict__ xqf) {
+                              const double4 *__restrict__ f, float4 *__restrict__ xqf, int grouped) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 vi = v[i];
+  if (grouped && vi.w == 0.0) return;   // `if (_dtfm[i] != 0.0)`, fix_nve_intel.cpp:92: neither v nor x moves
   const double4 fi = f[i];
   double4 xi = xq[i];
   vi.x = __dadd_rn(vi.x, __dmul_rn(vi.w, fi.x));
@@ -50,13 +57,16 @@ __global__ void k_nve_final(int n, double4 *__restrict__ v, const double4 *__res
 
 // sum 1/2 m v^2: per-block partials in a fixed order, reduced by one block
 __global__ void __launch_bounds__(256) k_ke_partial(int n, const double4 *__restrict__ v, const int *__restrict__ type,
-                                                    const double *__restrict__ mass, double *__restrict__ partial) {
+                                                    const double *__restrict__ mass, double *__restrict__ partial,
+                                                    const int *__restrict__ tag, int first_id,
+                                                    const double *__restrict__ rmass) {
   __shared__ double s[256];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double a = 0.0;
   if (i < n) {
     const double4 vi = v[i];
-    a = 0.5 * mass[type[i]] * (vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
+    const double m = rmass ? rmass[tag[i] - first_id] : mass[type[i]];
+    a = 0.5 * m * (vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
   }
   s[threadIdx.x] = a;
   __syncthreads();
@@ -97,7 +107,8 @@ int b2_nve_initial(b200md_ctx *ctx) {
   ScopedTimer tm(ctx, T_NVE);
   if (ctx->nlocal == 0) return 0;
   k_nve_initial<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(
-      ctx->nlocal, ctx->dtv, ctx->xq.p, ctx->v.p, ctx->f.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr);
+      ctx->nlocal, ctx->dtv, ctx->xq.p, ctx->v.p, ctx->f.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr,
+      ctx->nve_grouped ? 1 : 0);
   KERNEL_OK(ctx, "k_nve_initial");
   return 0;
 }
@@ -119,7 +130,8 @@ int b2_kinetic_energy(b200md_ctx *ctx, double *ke) {
   const int nb = cdiv(ctx->nlocal, 256);
   RESERVE(ctx, ctx->ev_partial, (size_t)nb + 1);
   if (nb > 0) {
-    k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->type.p, dmass, ctx->ev_partial.p);
+    k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->type.p, dmass, ctx->ev_partial.p, ctx->tag.p,
+                                              ctx->first_id, ctx->nve_has_rmass ? ctx->nve_rmass.p : nullptr);
     KERNEL_OK(ctx, "k_ke_partial");
   }
   k_sum1<<<1, 256, 0, ctx->stream>>>(nb, ctx->ev_partial.p, ctx->ev_out.p + 8);
@@ -155,11 +167,37 @@ int b200md_nve_setup(b200md_ctx *ctx, double dt) {
   if (ctx->nlocal > 0) {
     double *dmass;
     TRY(upload_mass(ctx, &dmass));
-    k_nve_set_dtfm<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->type.p, dmass, ctx->dtf, ctx->v.p);
+    k_nve_set_dtfm<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(
+        ctx->nlocal, ctx->type.p, dmass, ctx->dtf, ctx->v.p, ctx->tag.p, ctx->first_id,
+        ctx->nve_grouped ? ctx->nve_group.p : nullptr, ctx->nve_has_rmass ? ctx->nve_rmass.p : nullptr);
     KERNEL_OK(ctx, "k_nve_set_dtfm");
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->nve_ready = true;
+  return 0;
+}
+
+int b200md_nve_set_group(b200md_ctx *ctx, const int *ingroup, const double *rmass) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  if ((ingroup || rmass) && b2_comm_nranks(ctx) > 1)
+    return b2_fail(ctx, B200MD_EINVAL, "fix nve on a sub-group / with per-atom masses is single-GPU only in this build");
+  const size_t n = (size_t)ctx->nlocal;
+  ctx->nve_grouped = ingroup != nullptr && n > 0;
+  ctx->nve_has_rmass = rmass != nullptr && n > 0;
+  ctx->nve_ready = false;   // _dtfm has to be rebuilt (reset_dt)
+  if (ctx->nve_grouped) {
+    std::vector<int> g(n);
+    for (size_t i = 0; i < n; i++) g[i] = ingroup[i] ? 1 : 0;
+    RESERVE(ctx, ctx->nve_group, n);
+    CUDA_OK(ctx, cudaMemcpy(ctx->nve_group.p, g.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  if (ctx->nve_has_rmass) {
+    for (size_t i = 0; i < n; i++)
+      if (!(rmass[i] > 0.0)) return b2_fail(ctx, B200MD_EINVAL, "per-atom mass must be positive");
+    RESERVE(ctx, ctx->nve_rmass, n);
+    CUDA_OK(ctx, cudaMemcpy(ctx->nve_rmass.p, rmass, n * sizeof(double), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 

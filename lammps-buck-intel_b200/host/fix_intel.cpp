@@ -1,6 +1,8 @@
 // fix_intel.cpp — device-context owner (`package intel`), plus fix nve/intel.
 #include "fix_intel.h"
 
+#include <vector>
+
 #include "fix_nve_intel.h"
 
 using namespace LAMMPS_NS;
@@ -68,6 +70,14 @@ void FixNVEIntel::setup(int) { reset_dt(); }
 void FixNVEIntel::reset_dt() {
   dtv = update->dt;
   dtf = 0.5 * update->dt * force->ftm2v;
+  // mask[i] & groupbit and atom->rmass (fix_nve_intel.cpp:147-190): handed over before _dtfm is built
+  std::vector<int> in;
+  if (igroup != 0) {
+    in.resize(atom->nlocal);
+    for (int i = 0; i < atom->nlocal; i++) in[i] = (atom->mask[i] & groupbit) ? 1 : 0;
+  }
+  fix->check(b200md_nve_set_group(fix->ctx(), igroup != 0 ? in.data() : nullptr,
+                                  atom->rmass_flag ? atom->rmass.data() : nullptr));
   fix->check(b200md_nve_setup(fix->ctx(), update->dt));   // also precomputes dtf/mass per atom (_dtfm, :173-177)
 }
 

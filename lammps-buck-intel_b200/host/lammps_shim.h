@@ -54,6 +54,9 @@ class Atom {
   std::vector<double> q;
   std::vector<int> type;
   std::vector<double> mass;  // [ntypes+1]
+  std::vector<int> mask;     // group bits per atom (bit 0 = all); empty = every atom in `all` only
+  std::vector<double> rmass; // per-atom masses when rmass_flag (fix_nve_intel.cpp:148-156)
+  int rmass_flag = 0;
   std::vector<int> mass_setflag;
 };
 
@@ -191,6 +194,7 @@ class KSpace : protected Pointers {
 class Fix : protected Pointers {
  public:
   std::string id, style;
+  int igroup = 0, groupbit = 1;   // group all unless the fix command names another group
   explicit Fix(LAMMPS *l) : Pointers(l) {}
   virtual void init() {}
   virtual void setup(int) {}

@@ -65,6 +65,7 @@ struct Script {
   std::unique_ptr<Pair> pair;
   std::unique_ptr<KSpace> kspace;
   std::unique_ptr<FixNVEIntel> nve;
+  std::map<std::string, int> groups{{"all", 0}};   // group ID -> bit
   std::string pair_style_name, kspace_style_name, kspace_override;
   std::vector<std::string> kspace_args;
   int thermo_every = 0;
@@ -573,8 +574,39 @@ struct Script {
       need(4);
       std::string s = w[3];
       if (s.size() > 6 && s.substr(s.size() - 6) == "/intel") s = s.substr(0, s.size() - 6);
-      if (w[2] != "all" || s != "nve") fail("Unknown fix style " + w[3] + " (only `all nve` is provided)");
+      if (s != "nve") fail("Unknown fix style " + w[3] + " (only nve is provided)");
+      const auto gi = groups.find(w[2]);
+      if (gi == groups.end()) fail("Could not find fix group ID " + w[2]);
       nve.reset(new FixNVEIntel(&lmp));
+      nve->igroup = gi->second;
+      nve->groupbit = 1 << gi->second;
+    } else if (c == "group") {
+      // group ID type T1 T2 ... | group ID id N | N:M ...   (the two forms the /intel examples' variants use)
+      need(4);
+      if (!lmp.atom->nlocal) fail("Group command before simulation box is defined");
+      if (w[1] == "all") fail("Illegal group command");
+      if (!groups.count(w[1])) {
+        if (groups.size() >= 31) fail("Too many groups");
+        const int nb = (int)groups.size();
+        groups[w[1]] = nb;
+      }
+      const int bit = 1 << groups[w[1]];
+      Atom *a = lmp.atom;
+      if (a->mask.empty()) a->mask.assign(a->nlocal, 1);
+      if (w[2] == "type") {
+        for (size_t k = 3; k < w.size(); k++) {
+          const int t = std::atoi(w[k].c_str());
+          for (int i = 0; i < a->nlocal; i++)
+            if (a->type[i] == t) a->mask[i] |= bit;
+        }
+      } else if (w[2] == "id") {
+        for (size_t k = 3; k < w.size(); k++) {
+          long lo = std::atol(w[k].c_str()), hi = lo;
+          const size_t colon = w[k].find(':');
+          if (colon != std::string::npos) hi = std::atol(w[k].substr(colon + 1).c_str());
+          for (long id = std::max(lo, 1L); id <= hi && id <= a->nlocal; id++) a->mask[id - 1] |= bit;
+        }
+      } else fail("Illegal group command (type and id are provided)");
     } else if (c == "package") {
       need(2);
       if (w[1] != "intel") fail("Illegal package command");
@@ -589,6 +621,18 @@ struct Script {
     else if (c == "thermo") { need(2); thermo_every = std::atoi(w[1].c_str()); }
     else if (c == "timestep") { need(2); lmp.update->dt = std::atof(w[1].c_str()); dt_set = true; }
     else if (c == "run") { need(2); run(std::atol(w[1].c_str())); }
+    else if (c == "write_dump") {
+      // write_dump all xyz FILE: the host mirror of the positions (valid after a run: FixIntel::sync_host)
+      need(4);
+      if (w[1] != "all" || w[2] != "xyz") fail("Illegal write_dump command (only `all xyz` is provided)");
+      std::FILE *fp = std::fopen(w[3].c_str(), "w");
+      if (!fp) fail("Cannot open dump file " + w[3]);
+      const Atom *a = lmp.atom;
+      std::fprintf(fp, "%d\nAtoms. Timestep: %ld\n", a->nlocal, lmp.update->ntimestep);
+      for (int i = 0; i < a->nlocal; i++)
+        std::fprintf(fp, "%d %.17g %.17g %.17g\n", a->type[i], a->x[3 * i], a->x[3 * i + 1], a->x[3 * i + 2]);
+      std::fclose(fp);
+    }
     else if (c == "thermo_style" || c == "thermo_modify" || c == "processors" || c == "newton" || c == "echo" ||
              c == "log" || c == "dimension" || c == "boundary") {
       if (c == "boundary")

@@ -112,6 +112,10 @@ void orc_nve_dtfm(int nlocal, const int *type, const double *mass, double dt, do
 void orc_nve_initial(int nlocal, double *x, double *v, const double *f, const double *dtfm,
                      double dtv);
 void orc_nve_final(int nlocal, double *v, const double *f, const double *dtfm);
+/* sub-group / per-atom mass branches (fix_nve_intel.cpp:88-97, 147-190); rmass and ingroup may be NULL */
+void orc_nve_dtfm_group(int nlocal, const int *type, const double *mass, const double *rmass, const int *ingroup,
+                        double dt, double ftm2v, double *dtfm);
+void orc_nve_initial_group(int nlocal, double *x, double *v, const double *f, const double *dtfm, double dtv);
 
 /* ---- PPPM (pppm_intel.cpp + stock PPPM) */
 typedef struct orc_pppm orc_pppm;

@@ -517,6 +517,31 @@ void orc_nve_initial(int nlocal, double *x, double *v, const double *f, const do
   }
 }
 
+void orc_nve_dtfm_group(int nlocal, const int *type, const double *mass, const double *rmass, const int *ingroup,
+                        double dt, double ftm2v, double *dtfm) {
+  // FixNVEIntel::reset_dt (fix_nve_intel.cpp:147-190): rmass / per-type mass, 0 for atoms outside the group
+  const double dtf = 0.5 * dt * ftm2v;
+  int n = 0;
+  for (int i = 0; i < nlocal; i++) {
+    const double m = rmass ? rmass[i] : mass[type[i]];
+    const double d = (ingroup && !ingroup[i]) ? 0.0 : dtf / m;
+    dtfm[n++] = d;
+    dtfm[n++] = d;
+    dtfm[n++] = d;
+  }
+}
+
+void orc_nve_initial_group(int nlocal, double *x, double *v, const double *f, const double *dtfm, double dtv) {
+  // FixNVEIntel::initial_integrate, igroup != 0 branch (fix_nve_intel.cpp:88-97)
+  const long n3 = 3L * nlocal;
+  for (long i = 0; i < n3; i++) {
+    if (dtfm[i] != 0.0) {
+      v[i] += dtfm[i] * f[i];
+      x[i] += dtv * v[i];
+    }
+  }
+}
+
 void orc_nve_final(int nlocal, double *v, const double *f, const double *dtfm) {
   // FixNVEIntel::final_integrate (fix_nve_intel.cpp:103-127)
   const long n3 = 3L * nlocal;

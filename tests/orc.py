@@ -385,6 +385,22 @@ def nve_dtfm(type_, mass, dt, ftm2v):
     return out
 
 
+def nve_dtfm_group(type_, mass, dt, ftm2v, ingroup=None, rmass=None):
+    n = len(type_)
+    out = np.zeros(3 * n)
+    g = None if ingroup is None else i32(ingroup)
+    m = None if rmass is None else f64(rmass)
+    lib().orc_nve_dtfm_group(C.c_int(n), _i(i32(type_)), _d(f64(mass)), None if m is None else _d(m),
+                             None if g is None else _i(g), C.c_double(dt), C.c_double(ftm2v), _d(out))
+    return out
+
+
+def nve_initial_group(x, v, f, dtfm, dtv):
+    x = f64(x).copy(); v = f64(v).copy()
+    lib().orc_nve_initial_group(C.c_int(len(x)), _d(x), _d(v), _d(f64(f)), _d(f64(dtfm)), C.c_double(dtv))
+    return x, v
+
+
 def nve_initial(x, v, f, dtfm, dtv):
     x = f64(x).copy(); v = f64(v).copy()
     lib().orc_nve_initial(C.c_int(len(x)), _d(x), _d(v), _d(f64(f)), _d(f64(dtfm)), C.c_double(dtv))

@@ -241,6 +241,42 @@ def test_nve_bit_exact(pkg, W, orc):
     ctx.close()
 
 
+def test_nve_group_and_rmass_bit_exact(pkg, W, orc):
+    """fix nve/intel on a sub-group with per-atom masses (fix_nve_intel.cpp:88-97, 147-190): atoms outside the
+    group keep x and v bit for bit, the others match the oracle bit for bit; the kinetic energy uses rmass"""
+    s, P, ctx = _setup(pkg, W, orc, "coul_cut", 0)
+    u = W.UNITS["metal"]
+    n = len(s["type"])
+    rng = np.random.default_rng(5)
+    ingroup = (rng.random(n) < 0.6).astype(np.int32)
+    rmass = rng.uniform(5.0, 30.0, n)
+    ctx.nve_set_group(ingroup, rmass)
+    ctx.nve_setup(u["dt"])
+    ctx.neigh_build()            # the sort must carry the per-atom dtfm along
+    ctx.pair_compute(0, 0)
+    d0 = ctx.atoms_download(("x", "v", "f"))
+    dtfm = orc.nve_dtfm_group(s["type"], s["mass"], u["dt"], u["ftm2v"], ingroup, rmass)
+    ctx.nve_initial_integrate()
+    d1 = ctx.atoms_download(("x", "v"))
+    xo, vo = orc.nve_initial_group(d0["x"], d0["v"], d0["f"], dtfm, u["dt"])
+    assert np.array_equal(d1["x"], xo) and np.array_equal(d1["v"], vo)
+    frozen = ingroup == 0
+    assert frozen.any() and np.array_equal(d1["x"][frozen], d0["x"][frozen])
+    assert not np.array_equal(d1["x"][~frozen], d0["x"][~frozen])
+    ctx.nve_final_integrate()
+    d2 = ctx.atoms_download(("v",))
+    assert np.array_equal(d2["v"], orc.nve_final(vo, d0["f"], dtfm))
+    # group all again, per-type masses: the plain path is back
+    ctx.nve_set_group(None, None)
+    ctx.nve_setup(u["dt"])
+    ctx.nve_initial_integrate()
+    d3 = ctx.atoms_download(("x", "v"))
+    dt0 = orc.nve_dtfm(s["type"], s["mass"], u["dt"], u["ftm2v"])
+    xo3, vo3 = orc.nve_initial(d1["x"], d2["v"], d0["f"], dt0, u["dt"])
+    assert np.array_equal(d3["x"], xo3) and np.array_equal(d3["v"], vo3)
+    ctx.close()
+
+
 def test_run_energy_conservation_and_rebuilds(pkg, W, orc):
     """in.buck semantics: 100 NVE steps, rebuild every 20 steps without check (neigh_modify delay 0 every 20
     check no): total energy drift stays small and exactly 5 rebuilds happen"""

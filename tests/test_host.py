@@ -109,6 +109,26 @@ def test_in_buck_runs_like_the_oracle(pkg, W, orc, tmp_path):
 
 
 @pytest.mark.gpu
+def test_fix_nve_on_a_group_freezes_the_rest(pkg, W, tmp_path):
+    """`group mobile id 1:1000` + `fix 1 mobile nve`: FixNVEIntel's mask & groupbit branch (fix_nve_intel.cpp:88-97,
+    173-190) — atoms outside the group end the run exactly where create_atoms put them, the others have moved"""
+    dump0, dump1 = str(tmp_path / "x0.xyz"), str(tmp_path / "x1.xyz")
+    txt = scripts.IN_BUCK.format(n=8, steps=40, thermo=0)
+    txt = txt.replace("fix 1 all nve", "group mobile id 1:1000\nfix 1 mobile nve")
+    txt = txt.replace("run 40", "write_dump all xyz %s\nrun 40\nwrite_dump all xyz %s" % (dump0, dump1))
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.group", txt), "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    x0 = np.loadtxt(dump0, skiprows=2)[:, 1:]
+    x1 = np.loadtxt(dump1, skiprows=2)[:, 1:]
+    assert x0.shape == (2048, 3)
+    assert np.array_equal(x1[1000:], x0[1000:])
+    assert np.abs(x1[:1000] - x0[:1000]).max() > 1e-3
+    bad = txt.replace("fix 1 mobile nve", "fix 1 nobody nve")
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.nogroup", bad), "-sf", "intel", "-dry-run"])
+    assert r.returncode != 0 and "Could not find fix group ID" in r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("table", [0, 12])
 def test_in_buck_coul_long_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
     """in.buck_coul_long (data.aC x 2^3) with pppm 1e-4, analytic erfc and the stock Coulomb tables: step-0 energies

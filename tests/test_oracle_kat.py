@@ -277,3 +277,25 @@ def test_dispersion_ewald_equals_direct_lattice_sum(orc, W):
     e += -0.5 * w.sum() ** 2 / vol * 4.0 * np.pi / (3.0 * R ** 3)
     assert et == pytest.approx(e, rel=2e-5)
     assert np.abs(ft - f).max() <= 1e-4 * np.abs(f).max()
+
+
+def test_nve_group_branch_freezes_atoms_outside_the_group(orc):
+    """FixNVEIntel with igroup != all (fix_nve_intel.cpp:88-97, 173-190): dtfm is 0 outside the group and those
+    atoms keep x and v; inside, v += dtf/m f and x += dt v with rmass overriding the per-type mass"""
+    type_ = np.array([1, 2, 1, 2], dtype=np.int32)
+    mass = np.array([0.0, 2.0, 4.0])
+    rmass = np.array([1.0, 8.0, 16.0, 32.0])
+    ingroup = np.array([1, 0, 1, 1], dtype=np.int32)
+    dt, ftm2v = 0.5, 2.0            # dtf = 0.5
+    d = orc.nve_dtfm_group(type_, mass, dt, ftm2v, ingroup, rmass)
+    assert np.array_equal(d.reshape(4, 3)[:, 0], [0.5, 0.0, 0.5 / 16.0, 0.5 / 32.0])
+    d2 = orc.nve_dtfm_group(type_, mass, dt, ftm2v, ingroup, None)
+    assert np.array_equal(d2.reshape(4, 3)[:, 0], [0.25, 0.0, 0.25, 0.125])
+    assert np.array_equal(orc.nve_dtfm_group(type_, mass, dt, ftm2v), orc.nve_dtfm(type_, mass, dt, ftm2v))
+    x = np.arange(12.0).reshape(4, 3)
+    v = np.ones((4, 3))
+    f = np.full((4, 3), 4.0)
+    xo, vo = orc.nve_initial_group(x, v, f, d, dt)
+    assert np.array_equal(vo[1], v[1]) and np.array_equal(xo[1], x[1])          # frozen
+    assert np.array_equal(vo[0], [3.0, 3.0, 3.0]) and np.array_equal(xo[0], x[0] + 1.5)
+    assert np.array_equal(vo[2], 1.0 + 4.0 * 0.5 / 16.0 * np.ones(3))
