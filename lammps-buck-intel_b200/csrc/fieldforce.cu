@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(128)
 k_fieldforce(int n, PppmConst c, const double4 *__restrict__ pa_x, const int4 *__restrict__ pa_n,
              const double4 *__restrict__ xq, const float4 *__restrict__ xqf, const int *__restrict__ type,
              const double *__restrict__ Btype, const double *__restrict__ vd, double qqrd2e_scale,
-             double sf0, double sf1, double sf2, double sf3, double sf4, double sf5, double4 *__restrict__ f) {
+             double sf0, double sf1, double sf2, double sf3, double sf4, double sf5, int gnz,
+             double4 *__restrict__ f) {   // gnz: planes of the whole grid (c.nz is the local brick on several GPUs)
   __shared__ double s_rc[B2_MAXORDER * B2_MAXORDER], s_drc[B2_MAXORDER * B2_MAXORDER];
   for (int k = threadIdx.x; k < ORDER * ORDER; k += blockDim.x) {
     s_rc[k] = c.rho_coeff[k];
@@ -93,7 +94,7 @@ k_fieldforce(int n, PppmConst c, const double4 *__restrict__ pa_x, const int4 *_
   const flt_t qfactor = fq * qi;
   double4 fi = f[i];
   if (AD) {
-    const flt_t hx_inv = (flt_t)(c.nx / c.prd[0]), hy_inv = (flt_t)(c.ny / c.prd[1]), hz_inv = (flt_t)(c.nz / c.prd[2]);
+    const flt_t hx_inv = (flt_t)(c.nx / c.prd[0]), hy_inv = (flt_t)(c.ny / c.prd[1]), hz_inv = (flt_t)(gnz / c.prd[2]);
     ekx *= hx_inv; eky *= hy_inv; ekz *= hz_inv;
     const flt_t ftwo_pi = (flt_t)(kPI * 2.0), ffour_pi = (flt_t)(kPI * 4.0);
     const flt_t twoqsq = (flt_t)2.0 * qi * qi;
@@ -135,9 +136,9 @@ int b2_fieldforce(b200md_ctx *ctx, PppmState &ps, const PppmView &v) {
   case O:                                                                                                         \
     if (ad) k_fieldforce<flt_t, O, 1><<<nb, 128, 0, ctx->stream>>>(n, c, ps.pa_x.p, ps.pa_n.p, v.xq, v.xqf, v.type, B, \
                                                                    ps.vd.p, qs, sf[0], sf[1], sf[2], sf[3], sf[4],  \
-                                                                   sf[5], v.f);                                     \
+                                                                   sf[5], ps.gnz, v.f);                                     \
     else k_fieldforce<flt_t, O, 0><<<nb, 128, 0, ctx->stream>>>(n, c, ps.pa_x.p, ps.pa_n.p, v.xq, v.xqf, v.type, B,  \
-                                                                ps.vd.p, qs, 0, 0, 0, 0, 0, 0, v.f);                \
+                                                                ps.vd.p, qs, 0, 0, 0, 0, 0, 0, ps.gnz, v.f);                \
     break;
   switch (c.order) {
     FF(1) FF(2) FF(3) FF(4) FF(5) FF(6) FF(7)

@@ -96,11 +96,12 @@ __global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, int yoff, int ny
 }
 
 // PPPM::compute_sf_precoeff + the per-point part of compute_gf_ad
-__global__ void k_gf_ad(PppmConst c, double *__restrict__ greensfn, double *__restrict__ sfpre) {
+// (yoff, nyl: the y rows held by this rank, [z][row][x]; the whole grid on one GPU)
+__global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ greensfn, double *__restrict__ sfpre) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
+  const long nfft = (long)c.nx * nyl * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % nyl) + yoff, m = (int)(n / ((long)c.nx * nyl));
   const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
   const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
@@ -948,7 +949,8 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   const int nx = c.nx, ny = c.ny, gnz = ps.gnz;
   const long plane = (long)nx * ny;
   const int nzo = ps.pzhi[me] - ps.pzlo[me];
-  const int ncomp = 3;
+  const bool ad = ps.p.differentiation == 1;
+  const int ncomp = ad ? 1 : 3;   // field bricks: Ex, Ey, Ez (ik) or the potential u (ad)
   // halo widths: planes of a rank's brick below / above its owned range
   auto lo_w = [&](int r) { return ps.pzlo[r] - ps.zoffs[r]; };
   auto hi_w = [&](int r) { return ps.zoffs[r] + ps.nbzs[r] - ps.pzhi[r]; };
@@ -1012,22 +1014,23 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     const double scaleinv = 1.0 / ((double)nx * ny * gnz);
     if (ev) RESERVE(ctx, ps.partial, (size_t)std::max(nblk_z, 1) * 8);
     if (nblk_z > 0) {
-#define ZK(E)                                                                                                   \
+#define ZK(NC, E)                                                                                               \
   do {                                                                                                          \
-    auto kern = k_fft_z_poisson<3, E>;                                                                          \
+    auto kern = k_fft_z_poisson<NC, E>;                                                                         \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
     kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
                                              ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, ps.fkx_g.p,            \
                                              ps.fky_g.p + ps.ylos[me], scaleinv, c.g_ewald, ps.partial.p,       \
                                              ps.p.dispersion);                                                  \
   } while (0)
-      if (ev) ZK(1); else ZK(0);
+      if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
+      else { if (ev) ZK(3, 1); else ZK(3, 0); }
 #undef ZK
       KERNEL_OK(ctx, "k_fft_z_poisson");
     }
     // ---- transpose back, both packed transforms (Ex + i Ey, Ez) in one exchange: to rank q its planes (contiguous
     //      in [z][row][x]) ----------------------------------------------------------------------------------------
-    const int npack = 2;
+    const int npack = ad ? 1 : 2;
     RESERVE(ctx, ps.trecv, (size_t)plane * nzo * npack);
     {
       CommGroup grp(ctx);
@@ -1052,10 +1055,15 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     RESERVE(ctx, ps.vd_own, (size_t)nown * ncomp);
     PassGeom gy{(long)nx * nzo * npack, nx, plane, (long)nx, 0};
     TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
-    PassGeom gxy{(long)ny * nzo, 1, (long)nx, 1, nown};
-    TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
-    PassGeom gz{(long)ny * nzo, 1, (long)nx, 1, 0};
-    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nown, nullptr, ps.vd_own.p + 2 * nown, S_BWD)));
+    if (ad) {
+      PassGeom gu{(long)ny * nzo, 1, (long)nx, 1, 0};
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gu, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+    } else {
+      PassGeom gxy{(long)ny * nzo, 1, (long)nx, 1, nown};
+      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+      PassGeom gz{(long)ny * nzo, 1, (long)nx, 1, 0};
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nown, nullptr, ps.vd_own.p + 2 * nown, S_BWD)));
+    }
   }
   {
     ScopedTimer tm(ctx, T_COMM);
@@ -1461,8 +1469,6 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   if (ps->nranks > 1) {
     // z-slab decomposition: owned planes, local brick (owned + stencil/skin halo) and z-pencil rows of every rank
     const int P = ps->nranks, me = ps->rank;
-    if (p->differentiation == 1)
-      return b2_fail(ctx, B200MD_EINVAL, "kspace_modify diff ad is single-GPU only in this build");
     ps->pzlo.resize(P); ps->pzhi.resize(P); ps->zoffs.resize(P); ps->nbzs.resize(P); ps->ylos.resize(P); ps->yhis.resize(P);
     if (b200md_pppm_decomp(P, p->nz, p->ny, p->order, ctx->neigh.skin, ctx->prd[2], ps->pzlo.data(), ps->pzhi.data(),
                            ps->zoffs.data(), ps->nbzs.data(), ps->ylos.data(), ps->yhis.data()))
@@ -1535,16 +1541,24 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     k_gf_ik<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, nbx, nby, nbz, gf_yoff, gf_nyl, ps->greensfn.p);
     KERNEL_OK(ctx, "k_gf_ik");
   } else {
-    RESERVE(ctx, ps->sf_pre, 6 * (size_t)nfft);
-    k_gf_ad<<<cdiv(nfft, 128), 128, 0, ctx->stream>>>(c, ps->greensfn.p, ps->sf_pre.p);
+    RESERVE(ctx, ps->sf_pre, 6 * (size_t)ngf);
+    k_gf_ad<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p, ps->sf_pre.p);
     KERNEL_OK(ctx, "k_gf_ad");
     double s[6];
-    TRY(reduce_cols(ctx, *ps, nfft, 6, ps->sf_pre.p, s));
+    TRY(reduce_cols(ctx, *ps, ngf, 6, ps->sf_pre.p, s));
+    if (ps->nranks > 1) {   // the sums run over the whole grid (MPI_Allreduce in compute_sf_precoeff)
+      RESERVE(ctx, ps->red, 16);
+      CUDA_OK(ctx, cudaMemcpyAsync(ps->red.p, s, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      TRY(b2_comm_allreduce_sum(ctx, ps->red.p, 6));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps->red.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int k = 0; k < 6; k++) s[k] = ctx->h_pinned[k];
+    }
     // compute_gf_ad: self-force coefficients
     double prex = kPI / ps->volume, prey = prex, prez = prex;
-    prex *= c.nx / c.prd[0];
-    prey *= c.ny / c.prd[1];
-    prez *= c.nz / c.prd[2];
+    prex *= cg.nx / cg.prd[0];
+    prey *= cg.ny / cg.prd[1];
+    prez *= cg.nz / cg.prd[2];
     ps->sf_coeff[0] = s[0] * prex; ps->sf_coeff[1] = s[1] * prex * 2;
     ps->sf_coeff[2] = s[2] * prey; ps->sf_coeff[3] = s[3] * prey * 2;
     ps->sf_coeff[4] = s[4] * prez; ps->sf_coeff[5] = s[5] * prez * 2;

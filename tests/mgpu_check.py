@@ -19,6 +19,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 torch.cuda.set_device(lr)
 rep = (2, 2, int(os.environ.get("REPZ", "2")) * world)
 nsteps = int(os.environ.get("NSTEPS", "12"))
+DIFF = int(os.environ.get("DIFF", "0"))   # kspace_modify diff: 0 ik, 1 ad
 s = W.aC_system(rep, jitter=0.05)
 u = W.UNITS["metal"]
 n = len(s["x"])
@@ -34,7 +35,7 @@ def setup(ctx, sel):
     ctx.atoms_upload(s["x"][sel], s["type"][sel], s["mass"], v=s["v"][sel], q=s["q"][sel])
     ctx.neigh_setup(0.6)
     ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=g)
-    ctx.pppm_setup(*grid, 5, g)
+    ctx.pppm_setup(*grid, 5, g, differentiation=DIFF)
     ctx.nve_setup(u["dt"])
     return ctx.setup_forces(1, 1)
 
@@ -86,7 +87,7 @@ if rank == 0:
     dr = ref.atoms_download(("x", "f"))
     fs = np.abs(f0).max()
     e = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
-    print("ranks %d atoms %d grid %s builds/owned per rank %s" % (world, n, grid, nb))
+    print("ranks %d atoms %d grid %s diff %s builds/owned per rank %s" % (world, n, grid, "ad" if DIFF else "ik", nb))
     print("step 0: force err %.3e  epair err %.3e  ekspace err %.3e  virial err %.3e" %
           (np.abs(g0["f"] - f0).max() / fs, abs(th0[0] + th0[1] - r0[0] - r0[1]) / abs(r0[0] + r0[1]),
            abs(th0[8] - r0[8]) / abs(r0[8]), e(th0[2:8] + th0[9:15], r0[2:8] + r0[9:15])))

@@ -1,6 +1,6 @@
 """Multi-GPU parity (needs >= 2 visible GPUs, skipped otherwise): tests/mgpu_check.py runs the z-slab decomposition
 on N ranks over NCCL and compares forces, energies, virial and a 12-step trajectory (with migrations between the
-slabs) against a single-GPU context holding the same system."""
+slabs) against a single-GPU context holding the same system, for `kspace_modify diff ik` and `diff ad`."""
 import os
 import socket
 import subprocess
@@ -20,8 +20,8 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_slab_decomposition_matches_single_gpu(world):
+@pytest.mark.parametrize("world,diff", [(2, 0), (4, 0), (2, 1)])
+def test_slab_decomposition_matches_single_gpu(world, diff):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     s = socket.socket()
@@ -30,5 +30,5 @@ def test_slab_decomposition_matches_single_gpu(world):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, DIFF=str(diff)))
     assert r.returncode == 0 and "MGPU CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
