@@ -139,6 +139,9 @@ void orc_pppm_destroy(orc_pppm *p);
 void orc_pppm_compute(orc_pppm *p, int nlocal, const double *x, const double *q, int eflag,
                       int vflag, double *f, double *energy, double *virial, int nthreads);
 /* introspection for parity tests */
+/* per-atom tallies of the last compute with eflag & 2 / vflag & 4 (stock poisson_peratom / fieldforce_peratom):
+ * eatom[nlocal], vatom[nlocal][6] (xx,yy,zz,xy,xz,yz); Coulomb grid only */
+void orc_pppm_peratom(const orc_pppm *p, double *eatom, double *vatom);
 long orc_pppm_nfft(const orc_pppm *p);
 const double *orc_pppm_greensfn(const orc_pppm *p);
 const double *orc_pppm_density_fft(const orc_pppm *p);   /* after compute: folded density, nfft */

@@ -6,6 +6,7 @@
 //   brick2fft        :642-672                      poisson_ik     :811-977
 //   fieldforce_ik    :541-640                      poisson_ad     :986-1054
 //   fieldforce_ad    :679-804
+//   poisson_peratom / fieldforce_peratom: stock PPPM, called from :876, :1030 and :224-229 (eflag & 2, vflag & 4)
 // and of the stock PPPM state those functions read: set_grid_global,
 // adjust_gewald, compute_gf_denom, compute_rho_coeffs, compute_gf_ik / compute_gf_ad,
 // compute_sf_precoeff, setup (fkx, vg), GridComm reverse/forward on one rank (periodic fold / fill).
@@ -96,6 +97,8 @@ struct orc_pppm {
   std::vector<double> density_brick, vdx_brick, vdy_brick, vdz_brick, u_brick;
   std::vector<double> density_fft, work1, work2;
   std::vector<double> out_field[3];
+  std::vector<double> v_brick[6];         // per-atom virial bricks v0..v5 (stock PPPM::poisson_peratom)
+  std::vector<double> eatom, vatom;       // [nlocal], [nlocal][6] after a compute with eflag & 2 / vflag & 4
   std::vector<int> part2grid;
   double energy, virial[6];
 
@@ -645,6 +648,87 @@ struct orc_pppm {
         }
   }
 
+  // stock PPPM::poisson_peratom [UPSTREAM], called from poisson_ik / poisson_ad where the reference keeps the call
+  // (pppm_intel.cpp:876, :1030): work1 holds V(k) = rho(k) G(k) / N.  One inverse FFT for the potential (ik only: ad
+  // already has u_brick), six for V(k) vg[.][0..5].
+  void poisson_peratom(int eflag_atom, int vflag_atom, int nthr) {
+    auto to_brick = [&](std::vector<double> &brick) {
+      orc_fft3d(work2.data(), nx_pppm, ny_pppm, nz_pppm, -1, nthr);
+      long n = 0;
+      for (int k = 0; k < nz_pppm; k++)
+        for (int j = 0; j < ny_pppm; j++)
+          for (int i = 0; i < nx_pppm; i++) {
+            brick[bidx(k, j, i)] = work2[n];
+            n += 2;
+          }
+    };
+    if (eflag_atom && !diff_ad) {
+      for (long i = 0; i < 2 * nfft; i++) work2[i] = work1[i];
+      u_brick.resize(ngrid);
+      to_brick(u_brick);
+    }
+    if (!vflag_atom) return;
+    for (int c = 0; c < 6; c++) {
+      long n = 0;
+      for (long i = 0; i < nfft; i++) {
+        work2[n] = work1[n] * vg[6 * i + c];
+        n++;
+        work2[n] = work1[n] * vg[6 * i + c];
+        n++;
+      }
+      v_brick[c].resize(ngrid);
+      to_brick(v_brick[c]);
+    }
+  }
+
+  // stock PPPM::fieldforce_peratom [UPSTREAM] (called at pppm_intel.cpp:224-229 through the base class)
+  template <class flt_t>
+  void fieldforce_peratom(int nlocal, const std::vector<flt_t> &x, const std::vector<flt_t> &q, int eflag_atom,
+                          int vflag_atom) {
+    const flt_t lo0 = boxlo[0], lo1 = boxlo[1], lo2 = boxlo[2];
+    const flt_t xi = delxinv, yi = delyinv, zi = delzinv;
+    const flt_t fshiftone = shiftone;
+    for (int i = 0; i < nlocal; i++) {
+      const int nx = part2grid[3 * (size_t)i], ny = part2grid[3 * (size_t)i + 1],
+                nz = part2grid[3 * (size_t)i + 2];
+      const double dx = nx + fshiftone - (x[3 * (size_t)i] - lo0) * xi;
+      const double dy = ny + fshiftone - (x[3 * (size_t)i + 1] - lo1) * yi;
+      const double dz = nz + fshiftone - (x[3 * (size_t)i + 2] - lo2) * zi;
+      double rho[3][MAXORDER];
+      for (int k = nlower; k <= nupper; k++) {
+        double r1 = 0.0, r2 = 0.0, r3 = 0.0;   // stock compute_rho1d
+        for (int l = order - 1; l >= 0; l--) {
+          r1 = rc(l, k) + r1 * dx;
+          r2 = rc(l, k) + r2 * dy;
+          r3 = rc(l, k) + r3 * dz;
+        }
+        rho[0][k - nlower] = r1;
+        rho[1][k - nlower] = r2;
+        rho[2][k - nlower] = r3;
+      }
+      double u = 0.0, v[6] = {0, 0, 0, 0, 0, 0};
+      for (int n = nlower; n <= nupper; n++) {
+        const int mz = n + nz;
+        const double z0 = rho[2][n - nlower];
+        for (int m = nlower; m <= nupper; m++) {
+          const int my = m + ny;
+          const double y0 = z0 * rho[1][m - nlower];
+          for (int l = nlower; l <= nupper; l++) {
+            const int mx = l + nx;
+            const double x0 = y0 * rho[0][l - nlower];
+            const long b = bidx(mz, my, mx);
+            if (eflag_atom) u += x0 * u_brick[b];
+            if (vflag_atom)
+              for (int c = 0; c < 6; c++) v[c] += x0 * v_brick[c][b];
+          }
+        }
+      }
+      if (eflag_atom) eatom[i] += q[i] * u;
+      if (vflag_atom)
+        for (int c = 0; c < 6; c++) vatom[6 * (size_t)i + c] += q[i] * v[c];
+    }
+  }
+
   template <class flt_t>
   void fieldforce_ik(int nlocal, const std::vector<flt_t> &x, const std::vector<flt_t> &q, double *f,
                      int nthr) {
@@ -783,13 +867,32 @@ struct orc_pppm {
     make_rho<flt_t>(nlocal, x, q, nthr);
     reverse_comm_rho();
     brick2fft();
+    const int eflag_atom = (eflag & 2) && !dispersion, vflag_atom = (vflag & 4) && !dispersion;
     if (diff_ad) poisson_ad(eflag_global, vflag_global, nthr);
     else poisson_ik(eflag_global, vflag_global, nthr);
+    // work1 still holds V(k) (the gradient transforms use work2): the extra FFTs of poisson_peratom
+    if (eflag_atom || vflag_atom) poisson_peratom(eflag_atom, vflag_atom, nthr);
     if (diff_ad) forward_comm(u_brick);
     else { forward_comm(vdx_brick); forward_comm(vdy_brick); forward_comm(vdz_brick); }
+    if (eflag_atom && !diff_ad) forward_comm(u_brick);
+    if (vflag_atom) for (int c = 0; c < 6; c++) forward_comm(v_brick[c]);
     if (diff_ad) fieldforce_ad<flt_t>(nlocal, x, q, f);
     else fieldforce_ik<flt_t>(nlocal, x, q, f, nthr);
     const double qscale = qqrd2e * scale;
+    eatom.assign(eflag_atom ? nlocal : 0, 0.0);
+    vatom.assign(vflag_atom ? 6 * (size_t)nlocal : 0, 0.0);
+    if (eflag_atom || vflag_atom) {
+      fieldforce_peratom<flt_t>(nlocal, x, q, eflag_atom, vflag_atom);
+      // PPPM::compute, per-atom post-factors [UPSTREAM]: self-energy correction per atom, 1/2 for double counting
+      if (eflag_atom)
+        for (int i = 0; i < nlocal; i++) {
+          eatom[i] *= 0.5;
+          eatom[i] -= g_ewald * qd[i] * qd[i] / MY_PIS + MY_PI2 * qd[i] * qsum / (g_ewald * g_ewald * volume);
+          eatom[i] *= qscale;
+        }
+      if (vflag_atom)
+        for (size_t i = 0; i < 6 * (size_t)nlocal; i++) vatom[i] *= 0.5 * qscale;
+    }
     if (dispersion) {
       // pppm_disp_intel.cpp:486-510 with the 'q' array carrying B[type]: csum = sum B_i^2, csumij = (sum B_i)^2
       const double csum = qsqsum, csumij = qsum * qsum, g3 = g_ewald * g_ewald * g_ewald;
@@ -916,6 +1019,10 @@ void orc_pppm_compute(orc_pppm *p, int nlocal, const double *x, const double *q,
   if (p->prec == ORC_PREC_DOUBLE) rc = p->compute<double>(nlocal, x, q, eflag, vflag, f, energy, virial, nthreads);
   else rc = p->compute<float>(nlocal, x, q, eflag, vflag, f, energy, virial, nthreads);
   if (rc) std::fprintf(stderr, "oracle: Out of range atoms - cannot compute PPPM\n");
+}
+void orc_pppm_peratom(const orc_pppm *p, double *eatom, double *vatom) {
+  if (eatom) std::copy(p->eatom.begin(), p->eatom.end(), eatom);
+  if (vatom) std::copy(p->vatom.begin(), p->vatom.end(), vatom);
 }
 long orc_pppm_nfft(const orc_pppm *p) { return p->nfft; }
 const double *orc_pppm_greensfn(const orc_pppm *p) { return p->greensfn.data(); }

@@ -326,7 +326,15 @@ class PPPM:
         v = np.zeros(6)
         lib().orc_pppm_compute(self.h, C.c_int(n), _d(f64(x)), _d(f64(q)), C.c_int(eflag), C.c_int(vflag),
                                _d(f), C.byref(e), _d(v), C.c_int(nthreads))
+        self._n = n
         return f, e.value, v
+
+    def peratom(self, eatom=True, vatom=True):
+        """per-atom tallies of the last compute (eflag & 2 / vflag & 4)"""
+        e = np.zeros(self._n) if eatom else None
+        v = np.zeros((self._n, 6)) if vatom else None
+        lib().orc_pppm_peratom(self.h, None if e is None else _d(e), None if v is None else _d(v))
+        return e, v
 
     def _arr(self, ptr, n):
         return np.ctypeslib.as_array(ptr, shape=(n,)).copy()

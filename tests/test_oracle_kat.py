@@ -299,3 +299,43 @@ def test_nve_group_branch_freezes_atoms_outside_the_group(orc):
     assert np.array_equal(vo[1], v[1]) and np.array_equal(xo[1], x[1])          # frozen
     assert np.array_equal(vo[0], [3.0, 3.0, 3.0]) and np.array_equal(xo[0], x[0] + 1.5)
     assert np.array_equal(vo[2], 1.0 + 4.0 * 0.5 / 16.0 * np.ones(3))
+
+
+def test_pppm_peratom_sums_to_the_global_tallies(orc, W):
+    """stock poisson_peratom / fieldforce_peratom restated: interpolation uses the assignment function the density was
+    spread with, so by Parseval sum_i eatom_i = E and sum_i vatom_i = virial to round-off, for ik and ad"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    for ad in (0, 1):
+        pp = orc.PPPM(24, 24, 27, 5, 0.28, s["boxlo"], s["boxhi"], u["qqrd2e"], diff_ad=ad)
+        f, e, v = pp.compute(s["x"], s["q"], eflag=3, vflag=5)
+        ea, va = pp.peratom()
+        assert ea.sum() == pytest.approx(e, rel=1e-11)
+        assert np.allclose(va.sum(0), v, rtol=1e-10, atol=1e-10 * np.abs(v).max())
+        # the flags only add the tallies: forces, energy and virial are those of a plain compute
+        f0, e0, v0 = pp.compute(s["x"], s["q"])
+        assert np.array_equal(f, f0) and e == e0 and np.array_equal(v, v0)
+        assert not pp.peratom()[0].any()   # nothing tallied without the flags
+
+
+def test_peratom_energy_of_rocksalt_is_half_the_madelung_energy_per_ion(orc):
+    """every ion of NaCl carries -M k q^2 / (2 r0): pins the per-atom self-energy term and the factors 1/2 of
+    PPPM::compute's eatom post-processing together with the pair style's eatom"""
+    nc, a = 4, 5.64
+    r0 = a / 2
+    idx = np.stack(np.meshgrid(*[np.arange(2 * nc)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    x = idx * r0 + 0.25
+    q = np.where(idx.sum(1) % 2 == 0, 1.0, -1.0)
+    t = np.where(q > 0, 1, 2).astype(np.int32)
+    lo, hi = np.zeros(3), np.full(3, nc * a)
+    k, g = 14.399645, 0.40
+    A = np.zeros((3, 3)); rho = np.ones((3, 3)); C = np.zeros((3, 3))
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, A, rho, C, np.full((3, 3), 9.0), np.full((3, 3), 9.0), qqrd2e=k, g_ewald=g)
+    P.arr["cut_ljsq"][:] = 0.0
+    f, ev, _ = orc.pair_forces_periodic(P, 0, x, t, q, lo, hi, 0.3, eatom=1)
+    assert f[:, 3].sum() == pytest.approx(ev[0] + ev[1], rel=1e-12)
+    pp = orc.PPPM(48, 48, 48, 7, g, lo, hi, k)
+    pp.compute(x, q, eflag=3, vflag=0)
+    ek, _ = pp.peratom(vatom=False)
+    e_ion = f[:len(x), 3] + ek
+    assert np.allclose(e_ion, -1.747565 * k / (2 * r0), rtol=0, atol=2e-4)
