@@ -166,8 +166,13 @@ typedef struct {
 
 int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p);
 /* forces are ACCUMULATED into the device force array (f +=, pppm_intel.cpp:628-630).
- * energy / virial[6] may be NULL.  eflag bit1 / vflag bit2 (per-atom tallies, stock poisson_peratom) are refused. */
+ * energy / virial[6] may be NULL.  eflag bit1 / vflag bit2 ask for the per-atom tallies (b200md_pppm_peratom). */
 int b200md_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double virial[6]);
+/* Per-atom k-space energy and virial of the last b200md_pppm_compute called with eflag & 2 / vflag & 4: stock
+ * PPPM::poisson_peratom + fieldforce_peratom, which the reference reaches through its base class
+ * (pppm_intel.cpp:224-229, 876) and the eatom / vatom post-factors of PPPM::compute.  eatom[n], vatom[n][6]
+ * (xx,yy,zz,xy,xz,yz) in upload order; either may be NULL.  Coulomb grid, one GPU. */
+int b200md_pppm_peratom(b200md_ctx *ctx, double *eatom, double *vatom);
 /* host-buffer form of PPPMIntel::compute: x[n][3], q[n] in, f[n][3] += out */
 int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const double *x,
                              const double *q, double *f, double *energy, double virial[6]);

@@ -544,6 +544,14 @@ class Context:
         self._ck(self.lib.b200md_pppm_setup(self.h, C.byref(p)))
         self.pppm_grid = (nx, ny, nz)
 
+    def pppm_peratom(self, eatom=True, vatom=True):
+        """per-atom k-space energy [n] / virial [n,6] of the last pppm_compute(eflag & 2, vflag & 4), upload order"""
+        n = self.nlocal
+        e = np.zeros(n) if eatom else None
+        v = np.zeros((n, 6)) if vatom else None
+        self._ck(self.lib.b200md_pppm_peratom(self.h, None if e is None else _d(e), None if v is None else _d(v)))
+        return e, v
+
     def pppm_compute(self, eflag=0, vflag=0):
         e = C.c_double(0.0)
         v = np.zeros(6)

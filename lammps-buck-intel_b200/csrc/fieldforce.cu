@@ -149,5 +149,87 @@ int b2_fieldforce(b200md_ctx *ctx, PppmState &ps, const PppmView &v) {
   return 0;
 }
 
+// stock PPPM::fieldforce_peratom [UPSTREAM] (the reference calls it through the base class, pppm_intel.cpp:224-229) with
+// the per-atom post-factors of PPPM::compute folded in: one thread per atom interpolates the potential brick and the
+// six virial bricks (fields = [7][nfft]: u, v0..v5) with the stock double-precision weights.
+//   eatom = (1/2 q u - g q^2 / sqrt(pi) - pi/2 q qsum / (g^2 V)) qscale,   vatom_c = 1/2 qscale q v_c
+// out = [7][n] in the resident atom order.
+template <int ORDER>
+__global__ void __launch_bounds__(128)
+k_fieldforce_peratom(int n, PppmConst c, const double4 *__restrict__ pa_x, const int4 *__restrict__ pa_n,
+                     const double4 *__restrict__ xq, const double *__restrict__ fields, int do_e, int do_v,
+                     double qscale, double self_a, double self_b, double *__restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const double4 p = pa_x[a];
+  const int4 pn = pa_n[a];
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  double rho[3][ORDER];
+  int ix[ORDER], iy[ORDER], iz[ORDER];
+#pragma unroll
+  for (int k = 0; k < ORDER; k++) {
+    double r1 = 0.0, r2 = 0.0, r3 = 0.0;   // compute_rho1d
+#pragma unroll
+    for (int l = ORDER - 1; l >= 0; l--) {
+      r1 = c.rho_coeff[l * ORDER + k] + r1 * p.x;
+      r2 = c.rho_coeff[l * ORDER + k] + r2 * p.y;
+      r3 = c.rho_coeff[l * ORDER + k] + r3 * p.z;
+    }
+    rho[0][k] = r1; rho[1][k] = r2; rho[2][k] = r3;
+    ix[k] = wrapi(pn.x + c.nlower + k, c.nx);
+    iy[k] = wrapi(pn.y + c.nlower + k, c.ny);
+    iz[k] = wrapi(pn.z + c.nlower + k, c.nz);
+  }
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+  for (int nn = 0; nn < ORDER; nn++)
+#pragma unroll 1
+    for (int mm = 0; mm < ORDER; mm++) {
+      const long row = ((long)iz[nn] * c.ny + iy[mm]) * c.nx;
+      const double y0 = rho[2][nn] * rho[1][mm];
+#pragma unroll
+      for (int ll = 0; ll < ORDER; ll++) {
+        const double x0 = y0 * rho[0][ll];
+        const long g = row + ix[ll];
+        if (do_e) acc[0] += x0 * fields[g];
+        if (do_v) {
+#pragma unroll
+          for (int t = 1; t < 7; t++) acc[t] += x0 * fields[t * nfft + g];
+        }
+      }
+    }
+  const int i = pn.w;
+  const double q = xq[i].w;
+  if (do_e) out[i] = (0.5 * (q * acc[0]) - (self_a * q * q + self_b * q)) * qscale;
+  if (do_v)
+    for (int t = 1; t < 7; t++) out[(size_t)t * n + i] = 0.5 * qscale * (q * acc[t]);
+}
+
+int b2_fieldforce_peratom(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int do_e, int do_v) {
+  const PppmConst &c = ps.c;
+  const int n = v.n;
+  if (n <= 0) return 0;
+  RESERVE(ctx, ps.pa_out, 7 * (size_t)n);
+  const double qscale = ctx->qqrd2e * ps.p.scale;
+  const double self_a = c.g_ewald / kPIS;                                              // g q^2 / sqrt(pi)
+  const double self_b = kPI2 * ps.qsum / (c.g_ewald * c.g_ewald * ps.volume);          // pi/2 q qsum / (g^2 V)
+  const int nb = cdiv(n, 128);
+#define FP(O)                                                                                                   \
+  case O:                                                                                                       \
+    k_fieldforce_peratom<O><<<nb, 128, 0, ctx->stream>>>(n, c, ps.pa_x.p, ps.pa_n.p, v.xq, ps.pa_fields.p, do_e, do_v, \
+                                                          qscale, self_a, self_b, ps.pa_out.p);                  \
+    break;
+  switch (c.order) {
+    FP(1) FP(2) FP(3) FP(4) FP(5) FP(6) FP(7)
+    default: return b2_fail(ctx, B200MD_EORDER, "PPPM order greater than supported by USER-INTEL");
+  }
+#undef FP
+  KERNEL_OK(ctx, "k_fieldforce_peratom");
+  ps.pa_n_atoms = n;
+  ps.pa_have_e = do_e != 0;
+  ps.pa_have_v = do_v != 0;
+  return 0;
+}
+
 template int b2_fieldforce<double>(b200md_ctx *, PppmState &, const PppmView &);
 template int b2_fieldforce<float>(b200md_ctx *, PppmState &, const PppmView &);

@@ -812,6 +812,36 @@ __global__ void k_tr_unpack(int nx, int ny, int nzo, int ncomp, RankRows rr, con
   out[t] = in[rr.boff[p] + (long)comp * nzo * nyl * nx + ((long)z * nyl + (y - rr.ylo[p])) * nx + x];
 }
 
+// per-atom tallies: out = rho(k) * G(k) / N * (1 | vg_c(k)), c = comp - 1 (PPPM::poisson_peratom; vg as in PPPM::setup)
+__global__ void k_peratom_mul(PppmConst c, int comp, double scaleinv, const double2 *__restrict__ rhok,
+                              const double *__restrict__ greensfn, const double *__restrict__ fkx,
+                              const double *__restrict__ fky, const double *__restrict__ fkz, double2 *__restrict__ out) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (n >= nfft) return;
+  const int i = (int)(n % c.nx), j = (int)((n / c.nx) % c.ny), k = (int)(n / ((long)c.nx * c.ny));
+  double w = scaleinv * greensfn[n];
+  if (comp > 0) {
+    const double kx = fkx[i], ky = fky[j], kz = fkz[k];
+    const double sqk = kx * kx + ky * ky + kz * kz;
+    double vg = 0.0;
+    if (sqk != 0.0) {
+      const double vterm = -2.0 * (1.0 / sqk + 0.25 / (c.g_ewald * c.g_ewald));
+      switch (comp) {
+        case 1: vg = 1.0 + vterm * kx * kx; break;
+        case 2: vg = 1.0 + vterm * ky * ky; break;
+        case 3: vg = 1.0 + vterm * kz * kz; break;
+        case 4: vg = vterm * kx * ky; break;
+        case 5: vg = vterm * kx * kz; break;
+        default: vg = vterm * ky * kz; break;
+      }
+    }
+    w *= vg;
+  }
+  const double2 r = rhok[n];
+  out[n] = make_double2(r.x * w, r.y * w);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host helpers
 
@@ -1112,6 +1142,31 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   return 0;
 }
 
+// PPPM::poisson_peratom on one GPU.  ps.work1 holds the x- and y-transformed density (the fused z kernel of the normal
+// path does not write its z transform back): finish the forward transform, then per brick multiply by G / N (and
+// vg_c) and run one inverse 3-D FFT whose last pass stores the real part.  7 bricks: u, v0..v5.
+static int peratom_fields(b200md_ctx *ctx, PppmState &ps, int do_e, int do_v) {
+  const PppmConst &c = ps.c;
+  const long nfft = ps.nfft;
+  RESERVE(ctx, ps.pa_fields, 7 * (size_t)nfft);
+  RESERVE(ctx, ps.pa_work, (size_t)nfft);
+  PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
+  PassGeom gy{(long)c.nx * c.nz, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
+  PassGeom gz{(long)c.nx * c.ny, c.nx * c.ny, 0, (long)c.nx * c.ny, 0};
+  TRY((launch_pass<0, 0, 0>(ctx, ps.plan[2], gz, nullptr, ps.work1.p, ps.work1.p, nullptr, S_FWD)));
+  const double scaleinv = 1.0 / ((double)c.nx * c.ny * c.nz);
+  for (int comp = do_e ? 0 : 1; comp < (do_v ? 7 : 1); comp++) {
+    k_peratom_mul<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, comp, scaleinv, ps.work1.p, ps.greensfn.p, ps.fkx.p,
+                                                            ps.fky.p, ps.fkz.p, ps.pa_work.p);
+    KERNEL_OK(ctx, "k_peratom_mul");
+    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[2], gz, nullptr, ps.pa_work.p, ps.pa_work.p, nullptr, S_BWD)));
+    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.pa_work.p, ps.pa_work.p, nullptr, S_BWD)));
+    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.pa_work.p, nullptr, ps.pa_fields.p + (size_t)comp * nfft,
+                              S_BWD)));
+  }
+  return 0;
+}
+
 template <class flt_t>
 int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int eflag, int vflag, double *energy,
                       double *virial) {
@@ -1278,6 +1333,13 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   }
   }
 
+  // ---- per-atom energy / virial (eflag & 2, vflag & 4): extra inverse FFTs and their own gather ------------------
+  ps.pa_have_e = ps.pa_have_v = false;
+  if ((eflag & 2) || (vflag & 4)) {
+    TRY(peratom_fields(ctx, ps, eflag & 2, vflag & 4));
+    TRY(b2_fieldforce_peratom(ctx, ps, v, eflag & 2, vflag & 4));
+  }
+
   // ---- fieldforce -----------------------------------------------------------------------------------
   // accumulates into f, so it goes back to the main stream, behind the pair kernel (see b2_pppm_compute)
   if (ctx->stream != ctx->main_stream) {
@@ -1326,7 +1388,7 @@ static void free_state(PppmState *&slot) {
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
   ps->dens_own.free_(); ps->halo_s.free_(); ps->halo_r.free_(); ps->vd_own.free_(); ps->tsend.free_(); ps->trecv.free_();
   ps->workT.free_(); ps->workT2.free_();
-  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->cover.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
+  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->cover.free_(); ps->pa_fields.free_(); ps->pa_work.free_(); ps->pa_out.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
   delete ps;
   slot = nullptr;
 }
@@ -1356,9 +1418,14 @@ static int compute_all(b200md_ctx *ctx, const PppmView &v, int eflag, int vflag,
 int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial) {
   if (!ctx->pppm && !ctx->pppm6) return b2_fail(ctx, B200MD_EINVAL, "pppm compute before b200md_pppm_setup");
   // the reference hands per-atom tallies to stock poisson_peratom / fieldforce_peratom (pppm_intel.cpp:224-229,
-  // 281-301), which are not part of its hot path and not provided here: refuse rather than return zeros
-  if ((eflag & 2) || (vflag & 4))
-    return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial from PPPM is not provided (SURVEY 8f-2)");
+  // 281-301); provided here for the Coulomb grid on one GPU (b200md_pppm_peratom), refused elsewhere rather than
+  // returned as zeros
+  if ((eflag & 2) || (vflag & 4)) {
+    if (ctx->pppm6 || !ctx->pppm)
+      return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial is not provided for the dispersion grid");
+    if (b2_comm_nranks(ctx) > 1)
+      return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial from PPPM is single-GPU only in this build");
+  }
   PppmView v;
   v.n = ctx->nlocal;
   v.xq = ctx->xq.p;
@@ -1566,6 +1633,28 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   }
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   (void)k4PI;
+  return 0;
+}
+
+int b200md_pppm_peratom(b200md_ctx *ctx, double *eatom, double *vatom) {
+  if (!ctx || !ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_peratom before b200md_pppm_setup");
+  cudaSetDevice(ctx->device);
+  PppmState &ps = *ctx->pppm;
+  const int n = ctx->nlocal;
+  if ((eatom && !ps.pa_have_e) || (vatom && !ps.pa_have_v) || ps.pa_n_atoms != n)
+    return b2_fail(ctx, B200MD_EINVAL, "no per-atom tallies: the last b200md_pppm_compute did not ask for them");
+  if (n == 0) return 0;
+  std::vector<double> out(7 * (size_t)n);
+  std::vector<int> tag(n);
+  CUDA_OK(ctx, cudaMemcpyAsync(out.data(), ps.pa_out.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaMemcpyAsync(tag.data(), ctx->tag.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {   // resident order -> upload order
+    const size_t t = (size_t)(tag[i] - ctx->first_id);
+    if (eatom) eatom[t] = out[i];
+    if (vatom)
+      for (int k = 0; k < 6; k++) vatom[6 * t + k] = out[(size_t)(k + 1) * n + i];
+  }
   return 0;
 }
 

@@ -42,6 +42,12 @@ struct PppmState {
   DevBuf<int4> pa_n;     // sorted: {nx,ny,nz, atom index}
   DevBuf<double> pa_w;   // sorted: [3*order] one-dimensional stencil weights (x, y, z)
   DevBuf<double> tilebuf;  // make_rho: per-tile stencil blocks (tile + halo)
+  // per-atom energy / virial (stock poisson_peratom / fieldforce_peratom): potential + six virial bricks, results
+  DevBuf<double> pa_fields;   // [7][nfft]
+  DevBuf<double2> pa_work;    // [nfft]
+  DevBuf<double> pa_out;      // [7][n], resident atom order
+  int pa_n_atoms = 0;
+  bool pa_have_e = false, pa_have_v = false;
   DevBuf<int4> cover;      // make_rho fold: covering tiles per x / y / z coordinate (cover_table)
   DevBuf<int> pa_cx;     // sorted: wrapped x cell of the lower-left stencil corner
   DevBuf<unsigned char> scan_ws;
@@ -79,3 +85,4 @@ __device__ __forceinline__ int wrapi(int a, int n) {
 // fieldforce.cu
 template <class flt_t>
 int b2_fieldforce(b200md_ctx *ctx, PppmState &ps, const PppmView &v);
+int b2_fieldforce_peratom(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int do_e, int do_v);

@@ -174,6 +174,7 @@ class KSpace : protected Pointers {
  public:
   double energy = 0.0;
   double virial[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<double> eatom, vatom;   // [nlocal], [nlocal][6]: filled when compute() is asked for eflag & 2 / vflag & 4
   double g_ewald = 0.0, g_ewald_6 = 0.0;
   int order = 5, order_6 = 5;
   int nx_pppm = 0, ny_pppm = 0, nz_pppm = 0;

@@ -182,6 +182,12 @@ void PPPMIntel::compute(int eflag, int vflag) {
   for (double &v : virial) v = 0.0;
   fix->check(b200md_pppm_compute(fix->ctx(), eflag, vflag, &e, virial));
   if (eflag & 1) energy = e;
+  // eflag_atom / vflag_atom: stock poisson_peratom + fieldforce_peratom (reached at pppm_intel.cpp:224-229, :876)
+  if ((eflag & 2) || (vflag & 4)) {
+    if (eflag & 2) eatom.assign(atom->nlocal, 0.0);
+    if (vflag & 4) vatom.assign((size_t)6 * atom->nlocal, 0.0);
+    fix->check(b200md_pppm_peratom(fix->ctx(), (eflag & 2) ? eatom.data() : nullptr, (vflag & 4) ? vatom.data() : nullptr));
+  }
   if (!fix->resident) {
     atom->f.assign((size_t)3 * atom->nlocal, 0.0);
     fix->check(b200md_atoms_download(fix->ctx(), nullptr, nullptr, atom->f.data(), nullptr));

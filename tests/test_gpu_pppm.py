@@ -90,6 +90,42 @@ def test_pppm_matches_oracle(pkg, W, orc, name, order, ad, prec):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,order,ad,prec", [("aC1", 5, 0, 0), ("aC2_1e-4", 5, 1, 0), ("water", 7, 0, 0),
+                                                ("aC1", 4, 0, 1)])
+def test_pppm_peratom_matches_oracle(pkg, W, orc, name, order, ad, prec):
+    """eflag & 2 / vflag & 4: per-atom k-space energy and virial (stock poisson_peratom / fieldforce_peratom and the
+    eatom / vatom post-factors of PPPM::compute) against the oracle; they sum to the global tallies"""
+    s, grid, g = _case(W, name)
+    u = W.UNITS[s["units"]]
+    ctx = pkg.make_context(s, precision=prec)
+    ctx.neigh_setup(2.0)
+    ctx.pppm_setup(*grid, order, g, differentiation=ad)
+    pp = orc.PPPM(*grid, order, g, s["boxlo"], s["boxhi"], u["qqrd2e"], diff_ad=ad, prec=prec)
+    fo, eo, vo = pp.compute(s["x"], s["q"], eflag=3, vflag=5)
+    eao, vao = pp.peratom()
+    f0 = ctx.atoms_download(("f",))["f"]
+    e, v = ctx.pppm_compute(3, 5)
+    ea, va = ctx.pppm_peratom()
+    tol = 1e-10 if prec == 0 else 2e-5
+    assert np.abs(ea - eao).max() <= tol * np.abs(eao).max()
+    assert np.abs(va - vao).max() <= tol * np.abs(vao).max()
+    assert ea.sum() == pytest.approx(e, rel=1e-9 if prec == 0 else 1e-4)
+    assert np.allclose(va.sum(0), v, rtol=1e-8 if prec == 0 else 1e-4, atol=1e-8 * np.abs(v).max())
+    # the forces of the same call are the usual ones
+    f1 = ctx.atoms_download(("f",))["f"]
+    assert util.rel_force_err(f1 - f0, fo) <= (1e-9 if prec == 0 else 1e-5)
+    # energy only: the virial bricks are skipped and asking for them is an error; a plain compute clears the tallies
+    ctx.pppm_compute(3, 1)
+    ea2, _ = ctx.pppm_peratom(vatom=False)
+    assert np.array_equal(ea2, ea)
+    with pytest.raises(pkg.B200MDError):
+        ctx.pppm_peratom()
+    ctx.pppm_compute(1, 1)
+    with pytest.raises(pkg.B200MDError):
+        ctx.pppm_peratom(vatom=False)
+    ctx.close()
+
+
 def test_pppm_deterministic_and_flags(pkg, W):
     s, grid, g = _case(W, "aC1")
     outs = []
