@@ -162,6 +162,8 @@ typedef struct {
   int dispersion;        /* 0: Coulomb ('c', charges); 1: geometric dispersion ('g', weight B[type],
                             pppm_disp_intel.cpp:245-313 with SURVEY §2.4-2 corrected) */
   const double *B;       /* dispersion: [ntypes+1] geometric coefficients; else NULL */
+  double slab_volfactor; /* kspace_modify slab: > 1 = z is non-periodic, the mesh spans zprd * slab_volfactor and
+                            PPPM::slabcorr (pppm_intel.cpp:305) is applied; 0 or 1 = off.  Coulomb grid, one GPU */
 } b200md_pppm_params;
 
 int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p);

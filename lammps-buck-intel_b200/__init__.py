@@ -135,7 +135,7 @@ class PairParams(C.Structure):
 class PppmParams(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("order", C.c_int),
                 ("g_ewald", C.c_double), ("differentiation", C.c_int), ("scale", C.c_double),
-                ("dispersion", C.c_int), ("B", dp)]
+                ("dispersion", C.c_int), ("B", dp), ("slab_volfactor", C.c_double)]
 
 
 _lib = None
@@ -353,7 +353,7 @@ _ACONS = {
 
 
 def pppm_init(accuracy_relative, qqrd2e, q, natoms, cutoff, prd, order=5, mesh=None, gewald=None,
-              two_charge_force=None):
+              two_charge_force=None, slab=1.0):
     """PPPM::init -> set_grid_global -> adjust_gewald for ik differentiation (SURVEY App. A.5): returns
     ((nx,ny,nz), g_ewald).  `q` is the charge array (qsqsum = sum q^2) or qsqsum itself.
     mesh / gewald mimic `kspace_modify mesh` / `kspace_modify gewald`."""
@@ -375,7 +375,7 @@ def pppm_init(accuracy_relative, qqrd2e, q, natoms, cutoff, prd, order=5, mesh=N
         g = (1.35 - 0.15 * log(accuracy)) / cutoff if g >= 1.0 else sqrt(-log(g)) / cutoff
     if mesh is None:
         n = []
-        for p in (xprd, yprd, zprd):
+        for p in (xprd, yprd, zprd * slab):   # zprd_slab (kspace_modify slab)
             h = 1.0 / g
             k = int(p / h) + 1
             err = est(h, p, g)
@@ -394,11 +394,11 @@ def pppm_init(accuracy_relative, qqrd2e, q, natoms, cutoff, prd, order=5, mesh=N
         return k == 1
 
     n = [next(k for k in range(v, 100000) if factorable(k)) for v in n]
-    hs = [xprd / n[0], yprd / n[1], zprd / n[2]]
+    hs = [xprd / n[0], yprd / n[1], zprd * slab / n[2]]
     if gewald is None:
         def nr_f(gg):
             df_r = 2.0 * q2 * exp(-gg * gg * cutoff * cutoff) / sqrt(natoms * cutoff * xprd * yprd * zprd)
-            l = [est(hs[0], xprd, gg), est(hs[1], yprd, gg), est(hs[2], zprd, gg)]
+            l = [est(hs[0], xprd, gg), est(hs[1], yprd, gg), est(hs[2], zprd * slab, gg)]
             return df_r - sqrt(l[0] ** 2 + l[1] ** 2 + l[2] ** 2) / sqrt(3.0)
         for _ in range(10000):
             f1, f2 = nr_f(g), nr_f(g + 1e-6)
@@ -535,10 +535,11 @@ class Context:
         return f, ev
 
     # ---- PPPMIntel --------------------------------------------------------------------------------
-    def pppm_setup(self, nx, ny, nz, order, g_ewald, differentiation=0, scale=1.0, dispersion=0, B=None):
+    def pppm_setup(self, nx, ny, nz, order, g_ewald, differentiation=0, scale=1.0, dispersion=0, B=None, slab=0.0):
         p = PppmParams()
         p.nx, p.ny, p.nz, p.order, p.g_ewald = nx, ny, nz, order, g_ewald
         p.differentiation, p.scale, p.dispersion = differentiation, scale, dispersion
+        p.slab_volfactor = slab
         Bk = f64(B)
         p.B = _d(Bk)
         self._ck(self.lib.b200md_pppm_setup(self.h, C.byref(p)))
@@ -685,6 +686,9 @@ def make_context(system, precision=PREC_DOUBLE, device=0):
     u = W.UNITS[system["units"]]
     ctx = Context(device, precision)
     ctx.set_units(u["qqrd2e"], u["ftm2v"])
-    ctx.set_box(system["boxlo"], system["boxhi"])
+    if "periodic" in system:
+        ctx.set_box(system["boxlo"], system["boxhi"], system["periodic"])
+    else:
+        ctx.set_box(system["boxlo"], system["boxhi"])
     ctx.atoms_upload(system["x"], system["type"], system["mass"], v=system.get("v"), q=system.get("q"))
     return ctx

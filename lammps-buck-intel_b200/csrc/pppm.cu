@@ -219,6 +219,25 @@ __global__ void k_q_moments(int n, const double4 *__restrict__ xq, const int *__
   cols[(size_t)n + i] = q * q;
 }
 
+// PPPM::slabcorr [UPSTREAM], called at pppm_intel.cpp:305: dipole moments {q z, q z^2} ...
+__global__ void k_slab_moments(int n, const double4 *__restrict__ xq, double *__restrict__ cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  cols[i] = p.w * p.z;
+  cols[(size_t)n + i] = p.w * p.z * p.z;
+}
+// ... and the corrections: f_z += ffact q (dipole - qsum z); eatom += efact q (z dipole - (dipole_r2 + qsum z^2) / 2
+// - qsum zprd^2 / 12)
+__global__ void k_slabcorr(int n, const double4 *__restrict__ xq, double4 *__restrict__ f, double ffact, double dipole,
+                           double qsum, double *__restrict__ eatom, double efact, double dipole_r2, double zprd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  f[i].z += ffact * p.w * (dipole - qsum * p.z);
+  if (eatom) eatom[i] += efact * p.w * (p.z * dipole - 0.5 * (dipole_r2 + qsum * p.z * p.z) - qsum * zprd * zprd / 12.0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-step: particle_map + sort by cell
 
@@ -1373,6 +1392,22 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   }
   if (vflag_global && virial)
     for (int k = 0; k < 6; k++) virial[k] = 0.5 * qscale * ps.volume * evsum[1 + k];
+  // ---- slabcorr (pppm_intel.cpp:305): EW3DC dipole correction for `kspace_modify slab` ---------------------------
+  if (ps.p.slab_volfactor > 1.0 && n > 0) {
+    RESERVE(ctx, ps.slab_cols, 2 * (size_t)n);
+    k_slab_moments<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, ps.slab_cols.p);
+    KERNEL_OK(ctx, "k_slab_moments");
+    double m[2];
+    TRY(reduce_cols(ctx, ps, n, 2, ps.slab_cols.p, m));
+    const double dipole_all = m[0], dipole_r2 = m[1], zprd = ps.zprd;
+    const double e_slabcorr =
+        k2PI * (dipole_all * dipole_all - ps.qsum * dipole_r2 - ps.qsum * ps.qsum * zprd * zprd / 12.0) / ps.volume;
+    if (eflag_global && energy) *energy += qscale * e_slabcorr;
+    const double ffact = qscale * (-4.0 * kPI / ps.volume), efact = qscale * k2PI / ps.volume;
+    k_slabcorr<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.f, ffact, dipole_all, ps.qsum,
+                                                      ps.pa_have_e ? ps.pa_out.p : nullptr, efact, dipole_r2, zprd);
+    KERNEL_OK(ctx, "k_slabcorr");
+  }
   return 0;
 }
 
@@ -1388,7 +1423,7 @@ static void free_state(PppmState *&slot) {
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
   ps->dens_own.free_(); ps->halo_s.free_(); ps->halo_r.free_(); ps->vd_own.free_(); ps->tsend.free_(); ps->trecv.free_();
   ps->workT.free_(); ps->workT2.free_();
-  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->cover.free_(); ps->pa_fields.free_(); ps->pa_work.free_(); ps->pa_out.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
+  ps->flags.free_(); ps->pa_x.free_(); ps->pa_n.free_(); ps->pa_w.free_(); ps->pa_cx.free_(); ps->tilebuf.free_(); ps->cover.free_(); ps->slab_cols.free_(); ps->pa_fields.free_(); ps->pa_work.free_(); ps->pa_out.free_(); ps->scan_ws.free_(); ps->partial.free_(); ps->red.free_();
   delete ps;
   slot = nullptr;
 }
@@ -1496,8 +1531,18 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     return b2_fail(ctx, B200MD_EINVAL, "PPPM grid must have at least 2*order points per dimension");
   if (!(p->g_ewald > 0)) return b2_fail(ctx, B200MD_EINVAL, "PPPM needs g_ewald > 0");
   if (p->dispersion && !p->B) return b2_fail(ctx, B200MD_EINVAL, "dispersion PPPM needs B[type]");
-  for (int d = 0; d < 3; d++)
-    if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "PPPM needs a fully periodic box (no slab correction)");
+  // kspace_modify slab (PPPM::setup [UPSTREAM]): z is non-periodic, the mesh spans zprd * slab_volfactor and
+  // slabcorr() (pppm_intel.cpp:305) removes the inter-slab dipole interaction
+  const bool slab = p->slab_volfactor > 1.0;
+  if (slab) {
+    if (!ctx->periodic[0] || !ctx->periodic[1] || ctx->periodic[2])
+      return b2_fail(ctx, B200MD_EINVAL, "Incorrect boundaries with slab PPPM");
+    if (p->dispersion) return b2_fail(ctx, B200MD_EINVAL, "slab correction is not provided for the dispersion grid");
+    if (b2_comm_nranks(ctx) > 1) return b2_fail(ctx, B200MD_EINVAL, "slab PPPM is single-GPU only in this build");
+  } else {
+    for (int d = 0; d < 3; d++)
+      if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "Cannot use nonperiodic boundaries with PPPM");
+  }
   if (p->dispersion && p->differentiation == 1)
     return b2_fail(ctx, B200MD_EINVAL, "kspace_modify diff ad is not provided for the dispersion grid");
   PppmState *&slot = p->dispersion ? ctx->pppm6 : ctx->pppm;
@@ -1518,17 +1563,19 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   const double dist = 0.5 * ctx->neigh.skin;  // cuthalf (no TIP4P qdist)
   for (int d = 0; d < 3; d++) {
     c.boxlo[d] = ctx->boxlo[d];
-    c.prd[d] = ctx->prd[d];
-    c.delinv[d] = ng[d] / ctx->prd[d];
+    c.prd[d] = ctx->prd[d] * (d == 2 && slab ? p->slab_volfactor : 1.0);   // zprd_slab
+    c.delinv[d] = ng[d] / c.prd[d];
     // PPPM::set_grid_local extents, one rank: ghost cells reach dist beyond the box
-    const int nlo = static_cast<int>((0.0 - dist) * ng[d] / ctx->prd[d] + c.shift) - PPPM_OFFSET;
-    const int nhi = static_cast<int>((ctx->prd[d] + dist) * ng[d] / ctx->prd[d] + c.shift) - PPPM_OFFSET;
+    const int nlo = static_cast<int>((0.0 - dist) * ng[d] / c.prd[d] + c.shift) - PPPM_OFFSET;
+    int nhi = static_cast<int>((ctx->prd[d] + dist) * ng[d] / c.prd[d] + c.shift) - PPPM_OFFSET;
+    if (d == 2 && slab) nhi = std::max(nhi, ng[d] - 1);   // set_grid_local: the top rank owns the empty planes too
     c.lo_out[d] = nlo + c.nlower;
     c.hi_out[d] = nhi + c.nupper;
   }
   c.delvolinv = c.delinv[0] * c.delinv[1] * c.delinv[2];
   c.zoff = 0;
-  ps->volume = ctx->prd[0] * ctx->prd[1] * ctx->prd[2];
+  ps->volume = c.prd[0] * c.prd[1] * c.prd[2];   // xprd * yprd * zprd_slab
+  ps->zprd = ctx->prd[2];
   ps->gnz = p->nz;
   ps->nranks = b2_comm_nranks(ctx);
   ps->rank = b2_comm_rank(ctx);
@@ -1580,7 +1627,7 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     std::vector<double> fk;
     DevBuf<double> *dst[3] = {&ps->fkx, &ps->fky, &ps->fkz};
     for (int d = 0; d < 3; d++) {
-      const double unitk = k2PI / ctx->prd[d];
+      const double unitk = k2PI / c.prd[d];
       fk.assign(ng[d], 0.0);
       for (int i = 0; i < ng[d]; i++) fk[i] = unitk * (i - ng[d] * (2 * i / ng[d]));
       CUDA_OK(ctx, cudaMemcpy(dst[d]->p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));

@@ -48,6 +48,8 @@ struct PppmState {
   DevBuf<double> pa_out;      // [7][n], resident atom order
   int pa_n_atoms = 0;
   bool pa_have_e = false, pa_have_v = false;
+  DevBuf<double> slab_cols;   // slabcorr scratch: {q z, q z^2} per atom
+  double zprd = 0;            // the box's own z extent (volume and c.prd[2] carry zprd * slab_volfactor)
   DevBuf<int4> cover;      // make_rho fold: covering tiles per x / y / z coordinate (cover_table)
   DevBuf<int> pa_cx;     // sorted: wrapped x cell of the lower-left stencil corner
   DevBuf<unsigned char> scan_ws;

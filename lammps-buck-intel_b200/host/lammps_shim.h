@@ -184,6 +184,8 @@ class KSpace : protected Pointers {
   int gridflag_6 = 0, gewaldflag_6 = 0;
   double accuracy = 0.0, accuracy_relative = 0.0, accuracy_absolute = -1.0, two_charge_force = 0.0;
   double scale = 1.0;
+  int slabflag = 0;                 // kspace_modify slab
+  double slab_volfactor = 1.0;
   int suffix_flag = Suffix::NONE;
   explicit KSpace(LAMMPS *l) : Pointers(l) {}
   virtual void init() = 0;

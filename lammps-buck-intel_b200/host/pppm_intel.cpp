@@ -37,6 +37,14 @@ void KSpace::modify_params(int narg, char **arg) {
       g_ewald_6 = std::atof(arg[i + 1]);
       gewaldflag_6 = g_ewald_6 != 0.0;
       i += 2;
+    } else if (!std::strcmp(arg[i], "slab") && i + 1 < narg) {
+      // kspace_modify slab VOLFACTOR | nozforce (KSpace::modify_params [UPSTREAM])
+      if (!std::strcmp(arg[i + 1], "nozforce")) error->all(FLERR, "kspace_modify slab nozforce is not provided");
+      slab_volfactor = std::atof(arg[i + 1]);
+      if (slab_volfactor <= 1.0) error->all(FLERR, "Bad kspace_modify slab parameter");
+      if (slab_volfactor < 2.0) error->warning(FLERR, "Kspace_modify slab param < 2.0 may cause unphysical behavior");
+      slabflag = 1;
+      i += 2;
     } else if (!std::strcmp(arg[i], "diff") && i + 1 < narg) {
       if (!std::strcmp(arg[i + 1], "ad")) differentiation_flag = 1;
       else if (!std::strcmp(arg[i + 1], "ik")) differentiation_flag = 0;
@@ -59,8 +67,11 @@ bool PPPM::factorable(int n) {
 
 void PPPM::init() {
   if (domain->triclinic) error->all(FLERR, "Cannot (yet) use PPPM with triclinic box and this build");
-  for (int d = 0; d < 3; d++)
-    if (!domain->periodicity[d]) error->all(FLERR, "Cannot use nonperiodic boundaries with PPPM");
+  if (slabflag == 0)
+    for (int d = 0; d < 3; d++)
+      if (!domain->periodicity[d]) error->all(FLERR, "Cannot use nonperiodic boundaries with PPPM");
+  if (slabflag && (!domain->periodicity[0] || !domain->periodicity[1] || domain->periodicity[2]))
+    error->all(FLERR, "Incorrect boundaries with slab PPPM");
   if (!atom->q_flag) error->all(FLERR, "KSpace style requires atom attribute q");
   if (order < 2 || order > 7) error->all(FLERR, "PPPM order cannot be < 2 or > than 7");
   if (!force->pair) error->all(FLERR, "KSpace style is incompatible with Pair style");
@@ -104,7 +115,8 @@ double PPPM::newton_raphson_f() const {
                            std::sqrt(natoms * cutoff * xprd * yprd * zprd);
   const double lx = estimate_ik_error(xprd / nx_pppm, xprd, natoms);
   const double ly = estimate_ik_error(yprd / ny_pppm, yprd, natoms);
-  const double lz = estimate_ik_error(zprd / nz_pppm, zprd, natoms);
+  const double zprd_slab = zprd * slab_volfactor;
+  const double lz = estimate_ik_error(zprd_slab / nz_pppm, zprd_slab, natoms);
   return df_rspace - std::sqrt(lx * lx + ly * ly + lz * lz) / std::sqrt(3.0);
 }
 
@@ -120,7 +132,7 @@ void PPPM::set_grid_global() {
   if (!gridflag) {
     if (differentiation_flag == 1) error->all(FLERR, "kspace_modify diff ad needs an explicit mesh in this build");
     int *n[3] = {&nx_pppm, &ny_pppm, &nz_pppm};
-    const double prd[3] = {xprd, yprd, zprd};
+    const double prd[3] = {xprd, yprd, zprd * slab_volfactor};   // zprd_slab
     for (int d = 0; d < 3; d++) {
       double h = 1.0 / g_ewald;
       int k = static_cast<int>(prd[d] / h) + 1;
@@ -168,6 +180,7 @@ void PPPMIntel::setup() {
   p.g_ewald = g_ewald;
   p.differentiation = differentiation_flag;
   p.scale = scale;
+  p.slab_volfactor = slabflag ? slab_volfactor : 0.0;
   fix->check(b200md_pppm_setup(fix->ctx(), &p));
 }
 

@@ -80,7 +80,8 @@ struct orc_pppm {
   int nx_pppm, ny_pppm, nz_pppm, order, diff_ad, prec;
   int dispersion = 0;   // 1: geometric-mixing dispersion grid (PPPMDispIntel 'g', pppm_disp_intel.cpp:245-313)
   double g_ewald, qqrd2e, scale;
-  double boxlo[3], prd[3], volume;
+  double boxlo[3], prd[3], volume;   // prd[2] = zprd * slab_volfactor (zprd_slab of PPPM::setup)
+  double slab_volfactor = 1.0, zprd = 0.0;   // kspace_modify slab; zprd = the box's own z extent
   double cuthalf;
   int nlower, nupper;
   double shift, shiftone;
@@ -109,11 +110,14 @@ struct orc_pppm {
   }
 
   void init(int nx, int ny, int nz, int order_, double g, int ad, const double *lo, const double *hi,
-            double qq, int prec_, int disp = 0) {
+            double qq, int prec_, int disp = 0, double slab = 1.0) {
     dispersion = disp;
+    slab_volfactor = slab > 1.0 ? slab : 1.0;
     nx_pppm = nx; ny_pppm = ny; nz_pppm = nz; order = order_; g_ewald = g; diff_ad = ad;
     qqrd2e = qq; scale = 1.0; prec = prec_;
     for (int d = 0; d < 3; d++) { boxlo[d] = lo[d]; prd[d] = hi[d] - lo[d]; }
+    zprd = prd[2];
+    prd[2] *= slab_volfactor;
     volume = prd[0] * prd[1] * prd[2];
     cuthalf = 1.0;
     setup_grid();
@@ -919,6 +923,30 @@ struct orc_pppm {
       if (virial_out) for (int i = 0; i < 6; i++) virial_out[i] = virial[i];
     }
     }
+    // PPPM::slabcorr [UPSTREAM], called at pppm_intel.cpp:305
+    if (slab_volfactor > 1.0 && !dispersion) {
+      double dipole_all = 0.0, dipole_r2 = 0.0;
+      for (int i = 0; i < nlocal; i++) {
+        dipole_all += qd[i] * xd[3 * (size_t)i + 2];
+        dipole_r2 += qd[i] * xd[3 * (size_t)i + 2] * xd[3 * (size_t)i + 2];
+      }
+      const double e_slabcorr =
+          MY_2PI * (dipole_all * dipole_all - qsum * dipole_r2 - qsum * qsum * zprd * zprd / 12.0) / volume;
+      if (eflag_global) {
+        energy += qscale * e_slabcorr;
+        if (energy_out) *energy_out = energy;
+      }
+      if (!eatom.empty()) {
+        const double efact = qscale * MY_2PI / volume;
+        for (int i = 0; i < nlocal; i++) {
+          const double z = xd[3 * (size_t)i + 2];
+          eatom[i] += efact * qd[i] * (z * dipole_all - 0.5 * (dipole_r2 + qsum * z * z) - qsum * zprd * zprd / 12.0);
+        }
+      }
+      const double ffact = qscale * (-4.0 * MY_PI / volume);
+      for (int i = 0; i < nlocal; i++)
+        f[3 * (size_t)i + 2] += ffact * qd[i] * (dipole_all - qsum * xd[3 * (size_t)i + 2]);
+    }
     // expose owned-cell fields for parity checks
     for (int d = 0; d < 3; d++) {
       out_field[d].resize(nfft);
@@ -1008,6 +1036,13 @@ orc_pppm *orc_pppm_create_disp(int nx, int ny, int nz, int order, double g_ewald
   if (order < 1 || order > MAXORDER) return nullptr;
   orc_pppm *p = new orc_pppm();
   p->init(nx, ny, nz, order, g_ewald_6, 0, boxlo, boxhi, 1.0, prec, 1);
+  return p;
+}
+orc_pppm *orc_pppm_create_slab(int nx, int ny, int nz, int order, double g_ewald, int diff_ad, const double *boxlo,
+                               const double *boxhi, double qqrd2e, int prec, double slab_volfactor) {
+  if (order < 1 || order > MAXORDER) return nullptr;
+  orc_pppm *p = new orc_pppm();
+  p->init(nx, ny, nz, order, g_ewald, diff_ad, boxlo, boxhi, qqrd2e, prec, 0, slab_volfactor);
   return p;
 }
 void orc_pppm_destroy(orc_pppm *p) { delete p; }

@@ -288,10 +288,16 @@ def pair_forces_periodic_newtoff(params, prec, x, type_, q, boxlo, boxhi, skin, 
 
 
 class PPPM:
-    def __init__(self, nx, ny, nz, order, g_ewald, boxlo, boxhi, qqrd2e, diff_ad=0, prec=DOUBLE):
-        self.h = lib().orc_pppm_create(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order),
-                                       C.c_double(g_ewald), C.c_int(diff_ad), _d(f64(boxlo)),
-                                       _d(f64(boxhi)), C.c_double(qqrd2e), C.c_int(prec))
+    def __init__(self, nx, ny, nz, order, g_ewald, boxlo, boxhi, qqrd2e, diff_ad=0, prec=DOUBLE, slab=1.0):
+        if slab > 1.0:
+            lib().orc_pppm_create_slab.restype = C.c_void_p
+            self.h = lib().orc_pppm_create_slab(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order),
+                                                C.c_double(g_ewald), C.c_int(diff_ad), _d(f64(boxlo)),
+                                                _d(f64(boxhi)), C.c_double(qqrd2e), C.c_int(prec), C.c_double(slab))
+        else:
+            self.h = lib().orc_pppm_create(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order),
+                                           C.c_double(g_ewald), C.c_int(diff_ad), _d(f64(boxlo)),
+                                           _d(f64(boxhi)), C.c_double(qqrd2e), C.c_int(prec))
         if not self.h:
             raise ValueError("PPPM order not supported")
         self.h = C.c_void_p(self.h)

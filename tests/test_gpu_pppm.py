@@ -126,6 +126,47 @@ def test_pppm_peratom_matches_oracle(pkg, W, orc, name, order, ad, prec):
     ctx.close()
 
 
+@pytest.mark.parametrize("ad,prec", [(0, 0), (1, 0), (0, 1)])
+def test_slab_pppm_matches_oracle(pkg, W, orc, ad, prec):
+    """`boundary p p f` + `kspace_modify slab 3.0`: mesh over zprd * 3 and PPPM::slabcorr (pppm_intel.cpp:305) —
+    energy, virial, forces and per-atom energies against the oracle (itself pinned by four known answers)"""
+    rng = np.random.default_rng(3)
+    n, L = 400, 14.0
+    x = np.column_stack([rng.uniform(0, L, n), rng.uniform(0, L, n), rng.uniform(2.5, 10.5, n)])
+    q = np.where(np.arange(n) % 2 == 0, 1.0, -1.0)
+    q[x[:, 2] > 6.5] *= 1.5
+    q -= q.mean() - 0.01          # slightly non-neutral: the qsum terms of slabcorr are exercised too
+    s = dict(x=x, q=q, type=np.ones(n, np.int32), mass=np.array([0.0, 12.0]), boxlo=np.zeros(3), boxhi=np.full(3, L),
+             units="metal", periodic=(1, 1, 0))
+    u = W.UNITS["metal"]
+    grid, g = (30, 30, 90), 0.35
+    ctx = pkg.make_context(s, precision=prec)
+    ctx.neigh_setup(1.0)
+    ctx.pppm_setup(*grid, 5, g, differentiation=ad, slab=3.0)
+    pp = orc.PPPM(*grid, 5, g, s["boxlo"], s["boxhi"], u["qqrd2e"], diff_ad=ad, prec=prec, slab=3.0)
+    fo, eo, vo = pp.compute(x, q, eflag=3, vflag=1)
+    eao, _ = pp.peratom(vatom=False)
+    e, v = ctx.pppm_compute(3, 1)
+    f = ctx.atoms_download(("f",))["f"]
+    ea, _ = ctx.pppm_peratom(vatom=False)
+    tf, te = (1e-9, 1e-10) if prec == 0 else (1e-5, 1e-5)
+    assert util.rel_force_err(f, fo) <= tf
+    assert abs(e - eo) <= te * abs(eo) and np.abs(v - vo).max() <= te * np.abs(vo).max()
+    assert np.abs(ea - eao).max() <= (1e-10 if prec == 0 else 2e-5) * np.abs(eao).max()
+    ctx.close()
+    # a fully periodic box refuses the slab option, a p p f box refuses plain PPPM
+    ctx = pkg.make_context(dict(s, periodic=(1, 1, 1)), precision=prec)
+    with pytest.raises(pkg.B200MDError) as ei:
+        ctx.pppm_setup(*grid, 5, g, slab=3.0)
+    assert "Incorrect boundaries with slab PPPM" in str(ei.value)
+    ctx.close()
+    ctx = pkg.make_context(s, precision=prec)
+    with pytest.raises(pkg.B200MDError) as ei:
+        ctx.pppm_setup(*grid, 5, g)
+    assert "Cannot use nonperiodic boundaries with PPPM" in str(ei.value)
+    ctx.close()
+
+
 def test_pppm_deterministic_and_flags(pkg, W):
     s, grid, g = _case(W, "aC1")
     outs = []

@@ -72,6 +72,29 @@ def test_dry_run_coul_long_sizing_matches_python(pkg, W, tmp_path):
     assert "ewald is not provided" in out.stderr and tuple(_summary(out.stdout)["grid"]) == (96, 96, 108)
 
 
+def test_dry_run_slab_sizing_and_boundary_checks(pkg, W, tmp_path):
+    """`boundary p p f` + `kspace_modify slab 3.0`: the z mesh and the error balance use zprd * 3 (PPPM::set_grid_global
+    with zprd_slab), the same numbers as the Python restatement; wrong boundaries are the stock errors"""
+    base = scripts.IN_BUCK_COUL_LONG.format(r=2, kspace="pppm 1e-4\nkspace_modify slab 3.0", pair_modify="", steps=1,
+                                            thermo=0)
+    txt = "boundary p p f\n" + base
+    out = _run(pkg, ["-in", scripts.write(tmp_path, "in.slab", txt, W), "-sf", "intel", "-dry-run"])
+    assert out.returncode == 0, out.stdout + out.stderr
+    s = _summary(out.stdout)
+    sysd = W.aC_system(2, jitter=0.0)
+    u = W.UNITS["metal"]
+    prd = sysd["boxhi"] - sysd["boxlo"]
+    grid, g = pkg.pppm_init(1e-4, u["qqrd2e"], sysd["q"], len(sysd["x"]), 12.0, prd, slab=3.0)
+    grid0, _ = pkg.pppm_init(1e-4, u["qqrd2e"], sysd["q"], len(sysd["x"]), 12.0, prd)
+    assert tuple(s["grid"]) == tuple(grid) and grid[2] > 2 * grid0[2] and grid[:2] == grid0[:2]
+    assert s["g_ewald"] == pytest.approx(g, rel=1e-9)
+    out = _run(pkg, ["-in", scripts.write(tmp_path, "in.slab2", base, W), "-sf", "intel", "-dry-run"])
+    assert out.returncode != 0 and "Incorrect boundaries with slab PPPM" in out.stdout + out.stderr
+    noslab = txt.replace("kspace_modify slab 3.0\n", "")
+    out = _run(pkg, ["-in", scripts.write(tmp_path, "in.slab3", noslab, W), "-sf", "intel", "-dry-run"])
+    assert out.returncode != 0 and "Cannot use nonperiodic boundaries with PPPM" in out.stdout + out.stderr
+
+
 def test_driver_errors(pkg, W, tmp_path):
     bad = scripts.IN_BUCK.format(n=4, steps=1, thermo=0).replace("pair_coeff 1 1 1.0 0.2 -0.8", "")
     r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bad", bad), "-sf", "intel", "-dry-run"])

@@ -339,3 +339,52 @@ def test_peratom_energy_of_rocksalt_is_half_the_madelung_energy_per_ion(orc):
     ek, _ = pp.peratom(vatom=False)
     e_ion = f[:len(x), 3] + ek
     assert np.allclose(e_ion, -1.747565 * k / (2 * r0), rtol=0, atol=2e-4)
+
+
+def _slab_system(n=160, L=12.0, seed=3):
+    rng = np.random.default_rng(seed)
+    x = np.column_stack([rng.uniform(0, L, n), rng.uniform(0, L, n), rng.uniform(2.5, 8.5, n)])
+    q = np.where(np.arange(n) % 2 == 0, 1.0, -1.0)
+    q[x[:, 2] > 5.5] *= 1.5            # a net dipole along z ...
+    q -= q.mean()                      # ... in a neutral cell
+    return x, q, np.zeros(3), np.full(3, L)
+
+
+def test_slab_correction_known_answers(orc):
+    """kspace_modify slab (PPPM::setup with zprd_slab, PPPM::slabcorr at pppm_intel.cpp:305), four pins:
+    (1) against the plain periodic solver on the same extended cell the energy differs by exactly
+        qqrd2e 2 pi M_z^2 / V and the forces by -4 pi qqrd2e q M_z / V (neutral cell);
+    (2) the corrected energy no longer depends on the amount of vacuum (volfactor 3 vs 5), the uncorrected one does;
+    (3) it is invariant under a rigid shift along z inside the box;
+    (4) f_z = -dE/dz."""
+    x, q, lo, hi = _slab_system()
+    k, g, L = 14.399645, 0.55, hi[0]
+    f3, e3, _ = orc.PPPM(36, 36, 108, 7, g, lo, hi, k, slab=3.0).compute(x, q)
+    # (1) the same mesh as a fully periodic cell of height 3 L
+    hi3 = hi * np.array([1, 1, 3.0])
+    fp, ep, _ = orc.PPPM(36, 36, 108, 7, g, lo, hi3, k).compute(x, q)
+    M, V = (q * x[:, 2]).sum(), L * L * 3 * L
+    assert abs(M) > 2.0
+    assert e3 - ep == pytest.approx(k * 2 * math.pi * M * M / V, rel=1e-9)
+    df = f3 - fp
+    assert np.abs(df[:, :2]).max() == 0.0
+    assert np.allclose(df[:, 2], -4 * math.pi * k * q * M / V, rtol=1e-9, atol=1e-12)
+    # (2)
+    f5, e5, _ = orc.PPPM(36, 36, 180, 7, g, lo, hi, k, slab=5.0).compute(x, q)
+    hi5 = hi * np.array([1, 1, 5.0])
+    _, ep5, _ = orc.PPPM(36, 36, 180, 7, g, lo, hi5, k).compute(x, q)
+    assert abs(e5 - e3) < 2e-5 * abs(e3)
+    assert abs(ep5 - ep) > 50 * abs(e5 - e3)
+    assert np.abs(f5 - f3).max() < 1e-4 * np.abs(f3).max()
+    # (3)
+    xs = x + np.array([0.0, 0.0, 1.25])
+    fs, es, _ = orc.PPPM(36, 36, 108, 7, g, lo, hi, k, slab=3.0).compute(xs, q)
+    assert abs(es - e3) < 2e-5 * abs(e3) and np.abs(fs - f3).max() < 2e-4 * np.abs(f3).max()
+    # (4)
+    i, d = 7, 1e-4
+    pp = orc.PPPM(36, 36, 108, 7, g, lo, hi, k, slab=3.0)
+    xp, xm = x.copy(), x.copy()
+    xp[i, 2] += d
+    xm[i, 2] -= d
+    num = -(pp.compute(xp, q)[1] - pp.compute(xm, q)[1]) / (2 * d)
+    assert abs(num - f3[i, 2]) < 5e-4 * np.abs(f3).max()
