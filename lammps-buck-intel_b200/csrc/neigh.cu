@@ -8,9 +8,10 @@
 //
 // Design (B200): atoms are counting-sorted by bin (bin edge = cutneighmax/2, bins tile the box exactly so a
 // periodic shift is a whole number of bins); owned atoms come first, ghosts after, both in bin order, so
-// the five x-adjacent stencil bins of a (y,z) row are ONE contiguous index range.  One warp builds one
-// atom's row: 25 rows x {owned range, ghost range}, ballot-compacted, coalesced 128 B stores, rows in a
-// fixed order => deterministic list.  All counters are integers (no FP atomics anywhere).
+// the five x-adjacent stencil bins of a (y,z) row are ONE contiguous index range.  One block per bin: distances are
+// evaluated once into hit bit-masks (k_nb_mask), then one warp per atom expands its masks into the row (k_nb_fill):
+// 25 rows x {owned range, ghost range} in a fixed order => deterministic list; rows sit on a fixed pitch so each starts
+// on a 128 B line.  All counters are integers (no FP atomics anywhere).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -305,7 +306,8 @@ struct Pos<float> {
 //   k_nb_mask    a warp takes 32 candidates (one per lane, held in registers) and loops over the bin's atoms, whose
 //                coordinates are broadcast from shared memory: one ballot per (atom, 32 candidates) is the hit mask,
 //                stored to HBM; per-atom counts are integer shared-memory atomics.
-//   k_nb_fill    a warp takes an atom, reads its mask words and writes the row (ordered compaction, coalesced).
+//   k_nb_fill    a warp takes an atom, reads its mask words and writes the row (ordered compaction: one predicated
+//                store per non-empty word, rows on a fixed 128 B-aligned pitch).
 // Double mode: the test runs in FP32 on coordinates relative to the bin centre with a guard band; the (very rare)
 // candidates inside the band are decided by the exact un-fused FP64 expression, so the pair set stays bit-exact while
 // the FP64 pipe is idle.  Mixed mode: the criterion IS the reference's float expression on absolute float coordinates.
