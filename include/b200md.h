@@ -182,6 +182,11 @@ int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const
 int b200md_pppm_download(b200md_ctx *ctx, double *density_fft, double *greensfn, double *field_x,
                          double *field_y, double *field_z, double sf_coeff[6]);
 
+/* host-only plan of the tiled charge assignment, exposed for the CPU tests: shared-memory x pitch of a stencil block,
+ * lane -> stencil-face point map (-1 = idle lane) and, for a dimension of n grid points, the covering tiles of every
+ * coordinate as tile * 16 + local coordinate (-1 = unused), four entries per coordinate */
+int b200md_debug_rho_plan(int order, int n, int *pitch, int *lane_point, int *cover);
+
 /* hand-written 3-D complex FFT used by PPPM, exposed for parity tests (replaces FFT3d::compute,
  * pppm_intel.cpp:835,903): data = nz*ny*nx interleaved re/im doubles on the HOST, transformed in place;
  * dir +1 is exp(+ikx) — what stock FFT3d does for flag=1 (pppm_intel.cpp:835) — and -1 is exp(-ikx);

@@ -1683,6 +1683,21 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   return 0;
 }
 
+// host-only helpers of the tiled charge assignment, exposed for the CPU tests (no device needed)
+int b200md_debug_rho_plan(int order, int n, int *pitch, int *lane_point /*[64]*/, int *cover /*[n][4]*/) {
+  if (order < 1 || order > B2_MAXORDER || n < 1 || !pitch || !lane_point || !cover) return B200MD_EINVAL;
+  TileGeom tg{};
+  rho_lane_map(order, tg);
+  *pitch = rho_pitch(order);
+  for (int k = 0; k < 64; k++) lane_point[k] = tg.lane_pt[k];
+  std::vector<int4> cov(n);
+  if (!cover_table(n, cdiv(n, RHO_T), -(order - 1) / 2, order / 2, cov.data())) return B200MD_EINVAL;
+  for (int g = 0; g < n; g++) {
+    cover[4 * g] = cov[g].x; cover[4 * g + 1] = cov[g].y; cover[4 * g + 2] = cov[g].z; cover[4 * g + 3] = cov[g].w;
+  }
+  return 0;
+}
+
 int b200md_pppm_peratom(b200md_ctx *ctx, double *eatom, double *vatom) {
   if (!ctx || !ctx->pppm) return b2_fail(ctx, B200MD_EINVAL, "b200md_pppm_peratom before b200md_pppm_setup");
   cudaSetDevice(ctx->device);

@@ -95,6 +95,44 @@ def test_dry_run_slab_sizing_and_boundary_checks(pkg, W, tmp_path):
     assert out.returncode != 0 and "Cannot use nonperiodic boundaries with PPPM" in out.stdout + out.stderr
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5, 6, 7])
+def test_tiled_make_rho_plan(pkg, order):
+    """host-side plan of the tiled charge assignment (csrc/pppm.cu: rho_lane_map, cover_table): every stencil-face
+    point is owned by exactly one lane, the 16 lanes of a half warp hit 16 different 8-byte bank pairs, and the
+    cover table of a dimension lists, for every grid point, exactly the tile blocks that contain it"""
+    import ctypes as C
+    lib = pkg.load()
+    E = 8 + order - 1
+    nlower, nupper = -((order - 1) // 2), order // 2
+    for n in (2 * order + 2, 16, 17, 24, 27, 250, 270):
+        if n < 2 * order:
+            continue
+        pitch = C.c_int()
+        lanes = (C.c_int * 64)()
+        cover = (C.c_int * (4 * n))()
+        assert lib.b200md_debug_rho_plan(order, n, C.byref(pitch), lanes, cover) == 0
+        lanes = np.array(lanes[:])
+        pts = lanes[lanes >= 0]
+        assert sorted(pts) == list(range(order * order)) and pitch.value >= E
+        for h in range(4):
+            half = lanes[16 * h:16 * h + 16]
+            half = half[half >= 0]
+            res = ((half // order) * pitch.value + half % order) % 16
+            assert len(set(res)) == len(res), "bank conflict in half warp %d: %s" % (h, res)
+        cov = np.array(cover[:]).reshape(n, 4)
+        nt = (n + 7) // 8
+        for g in range(n):
+            got = sorted((e >> 4, e & 15) for e in cov[g] if e >= 0)
+            want = []
+            for t in range(nt):
+                lo, hi = 8 * t, min(8 * t + 8, n) - 1
+                for shift in (-n, 0, n):          # the tile and its periodic images
+                    if lo + shift + nlower <= g <= hi + shift + nupper:
+                        want.append((t, g - (lo + shift) - nlower))
+            assert got == sorted(want), (n, g, got, want)
+            assert all(0 <= loc < E for _, loc in got)
+
+
 def test_driver_errors(pkg, W, tmp_path):
     bad = scripts.IN_BUCK.format(n=4, steps=1, thermo=0).replace("pair_coeff 1 1 1.0 0.2 -0.8", "")
     r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bad", bad), "-sf", "intel", "-dry-run"])
