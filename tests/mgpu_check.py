@@ -20,6 +20,7 @@ torch.cuda.set_device(lr)
 rep = (2, 2, int(os.environ.get("REPZ", "2")) * world)
 nsteps = int(os.environ.get("NSTEPS", "12"))
 DIFF = int(os.environ.get("DIFF", "0"))   # kspace_modify diff: 0 ik, 1 ad
+DISP = int(os.environ.get("DISP", "0"))   # 1: add the geometric-mixing dispersion grid of pppm/disp (second PPPM state)
 s = W.aC_system(rep, jitter=0.05)
 u = W.UNITS["metal"]
 n = len(s["x"])
@@ -36,6 +37,8 @@ def setup(ctx, sel):
     ctx.neigh_setup(0.6)
     ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=g)
     ctx.pppm_setup(*grid, 5, g, differentiation=DIFF)
+    if DISP:
+        ctx.pppm_setup(60, 60, 32 * rep[2], 5, 0.31, dispersion=1, B=np.array([0.0, 9.0, 13.2]))
     ctx.nve_setup(u["dt"])
     return ctx.setup_forces(1, 1)
 
@@ -87,7 +90,7 @@ if rank == 0:
     dr = ref.atoms_download(("x", "f"))
     fs = np.abs(f0).max()
     e = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
-    print("ranks %d atoms %d grid %s diff %s builds/owned per rank %s" % (world, n, grid, "ad" if DIFF else "ik", nb))
+    print("ranks %d atoms %d grid %s diff %s builds/owned per rank %s" % (world, n, grid, ("ad" if DIFF else "ik") + (" + disp grid" if DISP else ""), nb))
     print("step 0: force err %.3e  epair err %.3e  ekspace err %.3e  virial err %.3e" %
           (np.abs(g0["f"] - f0).max() / fs, abs(th0[0] + th0[1] - r0[0] - r0[1]) / abs(r0[0] + r0[1]),
            abs(th0[8] - r0[8]) / abs(r0[8]), e(th0[2:8] + th0[9:15], r0[2:8] + r0[9:15])))

@@ -1,6 +1,6 @@
 """Multi-GPU parity (needs >= 2 visible GPUs, skipped otherwise): tests/mgpu_check.py runs the z-slab decomposition
 on N ranks over NCCL and compares forces, energies, virial and a 12-step trajectory (with migrations between the
-slabs) against a single-GPU context holding the same system, for `kspace_modify diff ik` and `diff ad`."""
+slabs) against a single-GPU context holding the same system, for `kspace_modify diff ik` and `diff ad`, and with the dispersion grid of pppm/disp as a second PPPM state."""
 import os
 import socket
 import subprocess
@@ -20,8 +20,8 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("world,diff", [(2, 0), (4, 0), (2, 1)])
-def test_slab_decomposition_matches_single_gpu(world, diff):
+@pytest.mark.parametrize("world,diff,disp", [(2, 0, 0), (4, 0, 0), (2, 1, 0), (2, 0, 1)])
+def test_slab_decomposition_matches_single_gpu(world, diff, disp):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     s = socket.socket()
@@ -30,5 +30,5 @@ def test_slab_decomposition_matches_single_gpu(world, diff):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, DIFF=str(diff)))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, DIFF=str(diff), DISP=str(disp)))
     assert r.returncode == 0 and "MGPU CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
