@@ -7,6 +7,7 @@
 // send/recv), small all-reduces.  The decomposition logic is in neigh.cu (atoms) and pppm.cu (grid).
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -155,6 +156,11 @@ int b200md_comm_init(b200md_ctx *ctx, int rank, int nranks, const void *id128) {
   std::memcpy(&id, id128, sizeof(id));
   NCCL_OK(ctx, ncclCommInitRank(&cs->comm, nranks, id, rank));
   ctx->neigh.ready = false;
+  // several GPUs: the k-space solve runs on its own stream underneath the pair kernel by default — part of its time
+  // is NCCL wait in the FFT transposes, which the pair kernel fills (4 GPUs: 20.3 -> 19.5 ms per step,
+  // profiles/r01_overlap.txt).  B200MD_OVERLAP=0 turns it off.
+  const char *ov = getenv("B200MD_OVERLAP");
+  ctx->overlap = !(ov && ov[0] == '0');
   return 0;
 }
 

@@ -167,8 +167,12 @@ int b200md_ctx_create(int device, int precision, b200md_ctx **out) {
     cudaEventCreateWithFlags(&ctx->ev_k, cudaEventDisableTiming);
     ctx->main_stream = ctx->stream;
     // measured on one B200 (profiles/r01_overlap.txt): hiding PPPM under the pair kernel slows that kernel by more
-    // than PPPM costs (10.96 -> 17.4 ms: they contend for L1/shared memory), so the overlap is opt-in
-    ctx->overlap = getenv("B200MD_OVERLAP") != nullptr;
+    // than PPPM costs (10.96 -> 17.4 ms: they contend for L1/shared memory), so on one GPU the overlap is opt-in
+    // (B200MD_OVERLAP=1); b200md_comm_init turns it on for several GPUs
+    {
+      const char *ov = getenv("B200MD_OVERLAP");
+      ctx->overlap = ov && ov[0] != '0';
+    }
   }
   cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev_a);
