@@ -316,7 +316,6 @@ struct Pos<float> {
 #endif
 #define NB_MAXI 64          // owned atoms of a bin handled per sweep
 #define NB_MAXR 64          // candidate ranges per bin (<= 2 * (2s+1)^2 with s <= 2 -> 50)
-#define NB_FILLC 4096       // candidates staged at a time by the fill kernel
 
 struct BinRanges {
   int start[NB_MAXR];
@@ -549,7 +548,6 @@ k_nb_mask(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__
 // words in order: the word is broadcast by shuffle, lane b of it (bit b set) fetches candidate b's entry from the
 // block's staged table and stores it at pos + popc(bits below b) — consecutive words extend the row contiguously, so
 // the partial stores merge in L2 — and pos advances by the word's popcount.
-#undef NB_FILLC
 #define NB_FILLC 4096       // candidates staged at a time (128 mask words: the usual stencil fits one window)
 __global__ void __launch_bounds__(NB_THREADS)
 k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lstart, const int *__restrict__ gstart,
