@@ -133,6 +133,23 @@ def test_tiled_make_rho_plan(pkg, order):
             assert all(0 <= loc < E for _, loc in got)
 
 
+REF_EXAMPLES = "/root/reference/examples"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("script,natoms,style,cut", [("in.buck", 32000, "buck", 2.5), ("in.buck_big", 192000, "buck", 5.0),
+                                                     ("in.buck_coul_cut", 76800, "buck/coul/cut", 10.0),
+                                                     ("in.buck_coul_long", 9600, "buck/coul/long", 12.0)])
+def test_shipped_example_scripts_parse_verbatim(pkg, script, natoms, style, cut):
+    """the reference's own examples/in.buck* are accepted as they are (CPU-only check, in the container that has the
+    reference mounted; the GPU tests run the same semantics from tests/scripts.py)"""
+    r = subprocess.run([os.path.join(pkg.HERE, "lmp_b200"), "-in", script, "-sf", "intel", "-dry-run"], cwd=REF_EXAMPLES,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    s = _summary(r.stdout)
+    assert (s["natoms"], s["pair_style"], s["cutforce"]) == (natoms, style, cut)
+
+
 def test_driver_errors(pkg, W, tmp_path):
     bad = scripts.IN_BUCK.format(n=4, steps=1, thermo=0).replace("pair_coeff 1 1 1.0 0.2 -0.8", "")
     r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bad", bad), "-sf", "intel", "-dry-run"])
