@@ -106,7 +106,7 @@ struct NeighState {
   DevBuf<long long> mask_off;     // their exclusive scan
   DevBuf<unsigned> maskbuf;       // hit masks [bin][atom][candidate word]
   long long total_entries = 0;
-  int pitch = 0;                  // entries per list row (multiple of 32: rows start on 128 B lines)
+  int pitch = 0;                  // entries per list row (multiple of 32: rows start on 128 B lines); 0 = packed CSR rows
   int max_numneigh = 0;
   bool packed_type = false;   // entries carry type(j) << B2_TYPESHIFT
   DevBuf<double4> xhold;      // positions at last build (owned)

@@ -1079,10 +1079,19 @@ int b2_neigh_build(b200md_ctx *ctx) {
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     total = *(long long *)ctx->h_pinned;
     maxn = *(int *)(ctx->h_pinned + 1);
-    ns.pitch = (maxn + 31) & ~31;
-    RESERVE(ctx, ns.entries, nmax * (size_t)ns.pitch + 64);
-    k_row_offsets<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ns.pitch, ns.offsets.p);
-    KERNEL_OK(ctx, "k_row_offsets");
+    // A very inhomogeneous system (one crowded spot sets the pitch for every row) would pay for the padding in memory:
+    // beyond 50 % overhead the rows stay packed at the scanned CSR offsets.  B200MD_LIST_CSR=1 forces that layout.
+    const int pitch = (maxn + 31) & ~31;
+    const char *csr_env = getenv("B200MD_LIST_CSR");
+    const bool padded = !(csr_env && csr_env[0] == '1') && (double)pitch * n <= 1.5 * (double)total + 4.0e6;
+    ns.pitch = padded ? pitch : 0;
+    if (padded) {
+      RESERVE(ctx, ns.entries, nmax * (size_t)pitch + 64);
+      k_row_offsets<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, pitch, ns.offsets.p);
+      KERNEL_OK(ctx, "k_row_offsets");
+    } else {
+      RESERVE(ctx, ns.entries, (size_t)total + 64);
+    }
     clk.mark("scan+alloc");
     k_nb_fill<<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->type.p, lstart, gstart, g, ns.mask_off.p, ns.maskbuf.p,
                                                     ns.offsets.p, ns.entries.p, pack);

@@ -220,6 +220,23 @@ def test_eval_host_with_special_bonds(pkg, W, orc, style, prec):
     ctx.close()
 
 
+def test_list_row_layouts_agree(pkg, W, orc, monkeypatch):
+    """the device list uses fixed-pitch, 128 B-aligned rows, or packed CSR rows when the padding would cost more than
+    half the list (forced here with B200MD_LIST_CSR=1): same rows, bit-identical forces and tallies"""
+    out = []
+    for csr in ("0", "1"):
+        monkeypatch.setenv("B200MD_LIST_CSR", csr)
+        s, P, ctx = _setup(pkg, W, orc, "coul_long", 0)
+        ctx.neigh_build()
+        ev = ctx.pair_compute(1, 1)
+        out.append((ctx.neigh_download(), ctx.atoms_download(("f",))["f"], ev))
+        ctx.close()
+    (l0, f0, e0), (l1, f1, e1) = out
+    for a, b in zip(l0, l1):     # numneigh, CSR offsets, entries, ghost sources and shifts of the exported list
+        assert np.array_equal(a, b)
+    assert l0[0].sum() > 0 and np.array_equal(f0, f1) and np.array_equal(np.asarray(e0), np.asarray(e1))
+
+
 def test_nve_bit_exact(pkg, W, orc):
     """fix nve/intel: x and v after initial/final integrate are bit-identical to the oracle given the same
     forces (un-fused mul+add, fix_nve_intel.cpp:74-77,116-117)"""
