@@ -290,7 +290,8 @@ struct Script {
     RanPark random(seed);
     for (int i = 0; i < a->nlocal; i++) {
       if (loop == "geom" || loop == "local") random.reset(seed, &a->x[3 * (size_t)i]);
-      const double vx = random.uniform(), vy = random.uniform(), vz = random.uniform();
+      // dist uniform: u - 1/2 per component, then 1/sqrt(m)
+      const double vx = random.uniform() - 0.5, vy = random.uniform() - 0.5, vz = random.uniform() - 0.5;
       const double factor = 1.0 / std::sqrt(a->mass[a->type[i]]);
       a->v[3 * (size_t)i] = vx * factor;
       a->v[3 * (size_t)i + 1] = vy * factor;
