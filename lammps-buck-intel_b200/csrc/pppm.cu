@@ -97,7 +97,9 @@ __global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, int yoff, int ny
 
 // PPPM::compute_sf_precoeff + the per-point part of compute_gf_ad
 // (yoff, nyl: the y rows held by this rank, [z][row][x]; the whole grid on one GPU)
-__global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ greensfn, double *__restrict__ sfpre) {
+// have_g: greensfn already holds the influence function (dispersion grid: k_gf_6) and only the sums are formed
+__global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ greensfn, double *__restrict__ sfpre,
+                        int have_g) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long nfft = (long)c.nx * nyl * c.nz;
   if (n >= nfft) return;
@@ -115,8 +117,11 @@ __global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ gre
                wz = d_powsinxx(0.5 * qz * zprd / c.nz, twoorder);
   const double sqk = qx * qx + qy * qy + qz * qz;
   double g = 0.0;
-  if (sqk != 0.0) g = (k4PI / sqk) * sx * sy * sz * wx * wy * wz / d_gf_denom(c, snx, sny, snz);
-  greensfn[n] = g;
+  if (have_g) g = greensfn[n];
+  else {
+    if (sqk != 0.0) g = (k4PI / sqk) * sx * sy * sz * wx * wy * wz / d_gf_denom(c, snx, sny, snz);
+    greensfn[n] = g;
+  }
   double wx0[5], wy0[5], wz0[5], wx1[5], wy1[5], wz1[5], wx2[5], wy2[5], wz2[5];
   for (int i = 0; i < 5; i++) {
     wx0[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 2))) / c.nx, c.order);
@@ -1543,8 +1548,6 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     for (int d = 0; d < 3; d++)
       if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "Cannot use nonperiodic boundaries with PPPM");
   }
-  if (p->dispersion && p->differentiation == 1)
-    return b2_fail(ctx, B200MD_EINVAL, "kspace_modify diff ad is not provided for the dispersion grid");
   PppmState *&slot = p->dispersion ? ctx->pppm6 : ctx->pppm;
   free_state(slot);
   PppmState *ps = new PppmState();
@@ -1644,7 +1647,7 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, p->B, ((size_t)ctx->ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (ngf == 0) {
-  } else if (p->dispersion) {
+  } else if (p->dispersion && !ad) {
     k_gf_6<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p);
     KERNEL_OK(ctx, "k_gf_6");
   } else if (!ad) {
@@ -1656,7 +1659,12 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     KERNEL_OK(ctx, "k_gf_ik");
   } else {
     RESERVE(ctx, ps->sf_pre, 6 * (size_t)ngf);
-    k_gf_ad<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p, ps->sf_pre.p);
+    if (p->dispersion) {   // PPPMDisp::compute_sf_coeff_6: the sums run over the r^-6 influence function
+      k_gf_6<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p);
+      KERNEL_OK(ctx, "k_gf_6");
+    }
+    k_gf_ad<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p, ps->sf_pre.p,
+                                                      p->dispersion ? 1 : 0);
     KERNEL_OK(ctx, "k_gf_ad");
     double s[6];
     TRY(reduce_cols(ctx, *ps, ngf, 6, ps->sf_pre.p, s));

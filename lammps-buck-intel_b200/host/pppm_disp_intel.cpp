@@ -89,6 +89,7 @@ void PPPMDispIntel::setup() {
   if (function[1]) {
     std::memset(&p, 0, sizeof(p));
     p.nx = nx_pppm_6; p.ny = ny_pppm_6; p.nz = nz_pppm_6; p.order = order_6; p.g_ewald = g_ewald_6;
+    p.differentiation = differentiation_flag;   // PPPMDisp uses one kspace_modify diff setting for both grids
     p.scale = 1.0; p.dispersion = 1; p.B = B.data();
     fix->check(b200md_pppm_setup(fix->ctx(), &p));
   }

@@ -133,6 +133,9 @@ orc_pppm *orc_pppm_create(int nx, int ny, int nz, int order, double g_ewald, int
  * 486-510 + upstream PPPMDisp::compute_gf_6 / vg_6) */
 orc_pppm *orc_pppm_create_disp(int nx, int ny, int nz, int order, double g_ewald_6, const double *boxlo,
                                const double *boxhi, int prec);
+/* the same grid with kspace_modify diff ad (fieldforce_g_ad, compute_sf_coeff_6 [UPSTREAM]) */
+orc_pppm *orc_pppm_create_disp_ad(int nx, int ny, int nz, int order, double g_ewald_6, int diff_ad,
+                                  const double *boxlo, const double *boxhi, int prec);
 /* kspace_modify slab: mesh over zprd * slab_volfactor, PPPM::slabcorr applied (pppm_intel.cpp:305); z non-periodic */
 orc_pppm *orc_pppm_create_slab(int nx, int ny, int nz, int order, double g_ewald, int diff_ad, const double *boxlo,
                                const double *boxhi, double qqrd2e, int prec, double slab_volfactor);

@@ -300,8 +300,16 @@ struct orc_pppm {
             v[5] = vterm * fky[j] * fkz[k];
           }
         }
-    if (dispersion) compute_gf_6();
-    else if (diff_ad) compute_gf_ad();
+    if (dispersion) {
+      compute_gf_6();
+      if (diff_ad) {   // PPPMDisp::compute_sf_coeff_6: the same sums over the r^-6 influence function
+        for (int t = 0; t < 6; t++) {
+          sf_coeff[t] = 0.0;
+          for (long n = 0; n < nfft; n++) sf_coeff[t] += sf_precoeff[t][n] * greensfn[n];
+        }
+        sf_prefactors();
+      }
+    } else if (diff_ad) compute_gf_ad();
     else compute_gf_ik();
   }
 
@@ -440,6 +448,12 @@ struct orc_pppm {
         }
       }
     }
+    sf_prefactors();
+  }
+
+  // the prefactors of compute_gf_ad / PPPMDisp::compute_sf_coeff_6 [UPSTREAM]
+  void sf_prefactors() {
+    const double xprd = prd[0], yprd = prd[1], zprd_slab = prd[2];
     double prex, prey, prez;
     prex = prey = prez = MY_PI / volume;
     prex *= nx_pppm / xprd;
@@ -1033,9 +1047,13 @@ orc_pppm *orc_pppm_create(int nx, int ny, int nz, int order, double g_ewald, int
  * f += w * E (no qqrd2e), energy/virial carry the dispersion self terms */
 orc_pppm *orc_pppm_create_disp(int nx, int ny, int nz, int order, double g_ewald_6, const double *boxlo,
                                const double *boxhi, int prec) {
+  return orc_pppm_create_disp_ad(nx, ny, nz, order, g_ewald_6, 0, boxlo, boxhi, prec);
+}
+orc_pppm *orc_pppm_create_disp_ad(int nx, int ny, int nz, int order, double g_ewald_6, int diff_ad, const double *boxlo,
+                                  const double *boxhi, int prec) {
   if (order < 1 || order > MAXORDER) return nullptr;
   orc_pppm *p = new orc_pppm();
-  p->init(nx, ny, nz, order, g_ewald_6, 0, boxlo, boxhi, 1.0, prec, 1);
+  p->init(nx, ny, nz, order, g_ewald_6, diff_ad, boxlo, boxhi, 1.0, prec, 1);
   return p;
 }
 orc_pppm *orc_pppm_create_slab(int nx, int ny, int nz, int order, double g_ewald, int diff_ad, const double *boxlo,

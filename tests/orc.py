@@ -306,12 +306,12 @@ class PPPM:
         self.nfft = nx * ny * nz
 
     @classmethod
-    def dispersion(cls, nx, ny, nz, order, g_ewald_6, boxlo, boxhi, prec=DOUBLE):
+    def dispersion(cls, nx, ny, nz, order, g_ewald_6, boxlo, boxhi, prec=DOUBLE, diff_ad=0):
         """PPPMDispIntel 'g' grid (geometric mixing): compute(x, w) takes w[i] = B[type[i]]"""
         self = cls.__new__(cls)
-        lib().orc_pppm_create_disp.restype = C.c_void_p
-        h = lib().orc_pppm_create_disp(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order), C.c_double(g_ewald_6),
-                                       _d(f64(boxlo)), _d(f64(boxhi)), C.c_int(prec))
+        lib().orc_pppm_create_disp_ad.restype = C.c_void_p
+        h = lib().orc_pppm_create_disp_ad(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order), C.c_double(g_ewald_6),
+                                          C.c_int(diff_ad), _d(f64(boxlo)), _d(f64(boxhi)), C.c_int(prec))
         if not h:
             raise ValueError("PPPM order not supported")
         self.h = C.c_void_p(h)

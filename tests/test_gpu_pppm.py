@@ -260,6 +260,15 @@ def test_pppm_disp_geometric_matches_oracle(pkg, W, orc, order, prec):
     assert np.abs(f - fo).max() <= tol_f * np.abs(fo).max()
     assert abs(e - eo) <= tol_e * abs(eo)
     assert np.abs(v - vo).max() <= tol_e * np.abs(vo).max()
+    # kspace_modify diff ad on the dispersion grid (fieldforce_g_ad, compute_sf_coeff_6)
+    ctx.pppm_setup(*grid, order, g6, dispersion=1, B=B, differentiation=1)
+    fa, ea, va = _resident(ctx, s)
+    pa = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], prec=prec, diff_ad=1)
+    fao, eao, vao = pa.compute(s["x"], B[s["type"]])
+    assert np.abs(fa - fao).max() <= tol_f * np.abs(fao).max()
+    assert abs(ea - eao) <= tol_e * abs(eao) and np.abs(va - vao).max() <= tol_e * np.abs(vao).max()
+    assert np.abs(fa - f).max() > 1e-6 * np.abs(f).max()      # not the ik path again
+    ctx.pppm_setup(*grid, order, g6, dispersion=1, B=B)
     # Coulomb and dispersion grids together (pppm/disp with function[0] and function[1]): sums of the two
     u = W.UNITS["metal"]
     ctx.pppm_setup(24, 24, 27, 5, 0.28)

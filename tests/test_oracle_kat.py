@@ -279,6 +279,27 @@ def test_dispersion_ewald_equals_direct_lattice_sum(orc, W):
     assert np.abs(ft - f).max() <= 1e-4 * np.abs(f).max()
 
 
+def test_dispersion_grid_ad_differentiation_converges_to_ik(orc, W):
+    """kspace_modify diff ad on the geometric dispersion grid (fieldforce_g_ad, compute_sf_coeff_6 [UPSTREAM]): the
+    energy and virial are those of ik (same poisson sums), the forces converge to the ik forces on a fine mesh, and
+    the self-force coefficients scale like the Coulomb ones (zero net force is restored to the mesh accuracy)"""
+    s, B, C, A, rho = _disp_system(W)
+    w = B[s["type"]]
+    g6, grid = 0.30, (54, 54, 60)
+    fi, ei, vi = orc.PPPM.dispersion(*grid, 7, g6, s["boxlo"], s["boxhi"]).compute(s["x"], w)
+    pa = orc.PPPM.dispersion(*grid, 7, g6, s["boxlo"], s["boxhi"], diff_ad=1)
+    fa, ea, va = pa.compute(s["x"], w)
+    assert ea == pytest.approx(ei, rel=1e-12) and np.allclose(va, vi, rtol=1e-12, atol=0)
+    scale = np.abs(fi).max()
+    assert np.abs(fa - fi).max() < 2e-4 * scale
+    assert np.abs(fa.sum(0)).max() < 1e-3 * scale
+    assert np.abs(pa.sf_coeff()).max() > 0.0
+    # a coarse mesh separates the two schemes: they are different discretisations, not the same code path
+    fc_i = orc.PPPM.dispersion(24, 24, 27, 5, g6, s["boxlo"], s["boxhi"]).compute(s["x"], w)[0]
+    fc_a = orc.PPPM.dispersion(24, 24, 27, 5, g6, s["boxlo"], s["boxhi"], diff_ad=1).compute(s["x"], w)[0]
+    assert np.abs(fc_a - fc_i).max() > 10 * np.abs(fa - fi).max()
+
+
 def test_nve_group_branch_freezes_atoms_outside_the_group(orc):
     """FixNVEIntel with igroup != all (fix_nve_intel.cpp:88-97, 173-190): dtfm is 0 outside the group and those
     atoms keep x and v; inside, v += dtf/m f and x += dt v with rmass overriding the per-type mass"""
