@@ -35,6 +35,29 @@ PPPM_CASES = {
     "pppm_disp_g5": ((30, 30, 32), 5, 0.31, 0, True),
 }
 B_DISP = np.array([0.0, 9.0, 13.2])
+# later additions, kept apart so that the first ten files stay byte-identical:
+#   name: (grid, order, g_ewald, diff_ad, dispersion, slab_volfactor, per-atom tallies)
+PPPM_CASES2 = {
+    "pppm_ik5_peratom": ((24, 24, 27), 5, 0.28, 0, False, 1.0, True),
+    "pppm_disp_g5_ad": ((30, 30, 32), 5, 0.31, 1, True, 1.0, False),
+    "pppm_slab3_ik5_peratom": ((24, 24, 80), 5, 0.28, 0, False, 3.0, True),
+}
+
+
+def pppm_case2(W, orc, name, prec=0):
+    """-> (system, f, e, v, eatom or None, vatom or None) from the oracle"""
+    grid, order, g, ad, disp, slab, peratom = PPPM_CASES2[name]
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    if disp:
+        pp = orc.PPPM.dispersion(*grid, order, g, s["boxlo"], s["boxhi"], diff_ad=ad, prec=prec)
+        w = B_DISP[s["type"]]
+    else:
+        pp = orc.PPPM(*grid, order, g, s["boxlo"], s["boxhi"], u["qqrd2e"], diff_ad=ad, slab=slab, prec=prec)
+        w = s["q"]
+    f, e, v = pp.compute(s["x"], w, eflag=3 if peratom else 1, vflag=5 if peratom else 1)
+    ea, va = pp.peratom() if peratom else (None, None)
+    return s, f, e, v, ea, va
 
 
 def system(W, name):
@@ -62,6 +85,13 @@ def main():
     pkg = graft.load_package()
     orc = graft.load_oracle()
     W = importlib.import_module("lammps_buck_intel_b200.workloads")
+    for name in PPPM_CASES2:
+        s, f, e, v, ea, va = pppm_case2(W, orc, name)
+        extra = {} if ea is None else dict(eatom=ea, vatom=va)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), f=f, e=e, v=v, **extra)
+        print(name, "e", e)
+    if "--new-only" in sys.argv:
+        return
     for name in CASES:
         s, u, co, P, ct, dt = pair_case(pkg, W, orc, name)
         f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3, eflag=3, vflag=1,

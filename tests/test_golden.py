@@ -45,6 +45,45 @@ def test_oracle_reproduces_golden_pppm(W, orc, name):
     assert np.allclose(v, g["v"], rtol=0, atol=1e-12 * np.abs(g["v"]).max())
 
 
+@pytest.mark.parametrize("name", sorted(mg.PPPM_CASES2))
+def test_oracle_reproduces_golden_pppm_variants(W, orc, name):
+    """per-atom tallies, the dispersion grid with ad differentiation, the slab correction"""
+    s, f, e, v, ea, va = mg.pppm_case2(W, orc, name)
+    g = _load(name)
+    assert util.rel_force_err(f, g["f"]) <= 1e-12
+    assert e == pytest.approx(float(g["e"]), rel=1e-12)
+    assert np.allclose(v, g["v"], rtol=0, atol=1e-12 * np.abs(g["v"]).max())
+    if ea is not None:
+        assert np.allclose(ea, g["eatom"], rtol=0, atol=1e-12 * np.abs(g["eatom"]).max())
+        assert np.allclose(va, g["vatom"], rtol=0, atol=1e-12 * np.abs(g["vatom"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(mg.PPPM_CASES2))
+def test_device_matches_golden_pppm_variants(pkg, W, name):
+    grid, order, gew, ad, disp, slab, peratom = mg.PPPM_CASES2[name]
+    s = W.aC_system(1)
+    if slab > 1.0:
+        s = dict(s, periodic=(1, 1, 0))
+    ctx = pkg.make_context(s)
+    ctx.neigh_setup(0.3)
+    if disp:
+        ctx.pppm_setup(*grid, order, gew, dispersion=1, B=mg.B_DISP, differentiation=ad)
+    else:
+        ctx.pppm_setup(*grid, order, gew, differentiation=ad, slab=slab if slab > 1.0 else 0.0)
+    e, v = ctx.pppm_compute(3 if peratom else 1, 5 if peratom else 1)
+    f = ctx.atoms_download(("f",))["f"]
+    g = _load(name)
+    assert util.rel_force_err(f, g["f"]) <= 1e-9
+    assert abs(e - float(g["e"])) <= 1e-10 * abs(float(g["e"]))
+    assert np.abs(v - g["v"]).max() <= 1e-10 * np.abs(g["v"]).max()
+    if peratom:
+        ea, va = ctx.pppm_peratom()
+        assert np.abs(ea - g["eatom"]).max() <= 1e-10 * np.abs(g["eatom"]).max()
+        assert np.abs(va - g["vatom"]).max() <= 1e-10 * np.abs(g["vatom"]).max()
+    ctx.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(mg.CASES))
 def test_device_matches_golden_pair(pkg, W, orc, name):
