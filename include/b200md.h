@@ -15,8 +15,8 @@
  *     b200md_atoms_upload (LAMMPS local index); downloads un-permute
  *   - ev[8] = {evdwl, ecoul, v_xx, v_yy, v_zz, v_xy, v_xz, v_yz}  (ev_global, pair_buck_intel.cpp:337-349)
  *   - eflag bit0 global energy, bit1 per-atom; vflag 1|2 global virial (newton is off on the device, so
- *     both are evaluated as the per-pair tally, pair_buck_intel.cpp:93-96,312), 4 per-atom (not produced,
- *     as in the reference: pair_buck_intel.cpp:362)
+ *     both are evaluated as the per-pair tally, pair_buck_intel.cpp:93-96,312), 4 per-atom (not produced by the
+ *     pair styles, as in the reference: pair_buck_intel.cpp:362; PPPM does produce it: b200md_pppm_peratom)
  */
 #ifndef B200MD_H
 #define B200MD_H
