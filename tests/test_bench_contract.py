@@ -51,3 +51,29 @@ def test_reference_arm_under_torchrun_prints_once():
     lines = _json_lines(r.stdout)
     assert len(lines) == 1, lines          # rank 0 alone runs and prints; the other rank exits 0 without work
     _check(lines[0], 2)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_own_arm_json_line_on_a_small_workload():
+    """bench.py on one GPU at a reduced size (--rep 4: 76 800 atoms): one JSON line carrying every key of the contract,
+    with the roofline, cpu_baseline, e2e and clocks objects filled in"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--rep", "4", "--steps", "6", "--warmup", "3",
+                        "--cpu-rep", "2", "--cpu-steps", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = _json_lines(r.stdout)
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in [k for k in KEYS if k != "impl"] + ["clocks", "gpu_launches", "roofline"]:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 6 and d["warmup"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
+    rf = d["roofline"]
+    assert rf["achieved"] > 0 and rf["peak"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 76800 * 24 and e["d2h_bytes_per_step"] == 76800 * 48
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
+    assert d["clocks"]["sm_max_mhz"] > 0
