@@ -592,13 +592,12 @@ struct Script {
         groups[w[1]] = nb;
       }
       const int bit = 1 << groups[w[1]];
-      Atom *a = lmp.atom;
       if (a->mask.empty()) a->mask.assign(a->nlocal, 1);
       if (w[2] == "type") {
         for (size_t k = 3; k < w.size(); k++) {
-          const int t = std::atoi(w[k].c_str());
+          const int gtype = std::atoi(w[k].c_str());
           for (int i = 0; i < a->nlocal; i++)
-            if (a->type[i] == t) a->mask[i] |= bit;
+            if (a->type[i] == gtype) a->mask[i] |= bit;
         }
       } else if (w[2] == "id") {
         for (size_t k = 3; k < w.size(); k++) {
@@ -628,7 +627,6 @@ struct Script {
       if (w[1] != "all" || w[2] != "xyz") fail("Illegal write_dump command (only `all xyz` is provided)");
       std::FILE *fp = std::fopen(w[3].c_str(), "w");
       if (!fp) fail("Cannot open dump file " + w[3]);
-      const Atom *a = lmp.atom;
       std::fprintf(fp, "%d\nAtoms. Timestep: %ld\n", a->nlocal, lmp.update->ntimestep);
       for (int i = 0; i < a->nlocal; i++)
         std::fprintf(fp, "%d %.17g %.17g %.17g\n", a->type[i], a->x[3 * i], a->x[3 * i + 1], a->x[3 * i + 2]);
