@@ -1199,7 +1199,6 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   const long nfft = ps.nfft;
   const int eflag_global = eflag & 1, vflag_global = vflag & 3;
   const bool ad = ps.p.differentiation == 1;
-  const int ncomp = ad ? 1 : 3;
   if (energy) *energy = 0.0;
   if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
 
@@ -1265,7 +1264,7 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     }
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (tiled) {
-      TileGeom tg{cdiv(c.nx, RHO_T), cdiv(c.ny, RHO_T), cdiv(c.nz, RHO_T), RHO_T + c.order - 1};
+      TileGeom tg{cdiv(c.nx, RHO_T), cdiv(c.ny, RHO_T), cdiv(c.nz, RHO_T), RHO_T + c.order - 1, {}};
       rho_lane_map(c.order, tg);
       const long ntiles = (long)tg.ntx * tg.nty * tg.ntz;
       const size_t E3 = (size_t)tg.E * tg.E * tg.E;
