@@ -104,9 +104,7 @@ def test_tiled_make_rho_plan(pkg, order):
     lib = pkg.load()
     E = 8 + order - 1
     nlower, nupper = -((order - 1) // 2), order // 2
-    for n in (2 * order + 2, 16, 17, 24, 27, 250, 270):
-        if n < 2 * order:
-            continue
+    for n in list(range(max(2 * order, 2), 100)) + [125, 128, 250, 270, 486]:
         pitch = C.c_int()
         lanes = (C.c_int * 64)()
         cover = (C.c_int * (4 * n))()
