@@ -1408,9 +1408,19 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
         k2PI * (dipole_all * dipole_all - ps.qsum * dipole_r2 - ps.qsum * ps.qsum * zprd * zprd / 12.0) / ps.volume;
     if (eflag_global && energy) *energy += qscale * e_slabcorr;
     const double ffact = qscale * (-4.0 * kPI / ps.volume), efact = qscale * k2PI / ps.volume;
+    // like fieldforce it adds to f: in overlap mode it goes to the main stream, behind the pair kernel
+    cudaStream_t ks = ctx->stream;
+    if (ks != ctx->main_stream) {
+      CUDA_OK(ctx, cudaEventRecord(ctx->ev_k, ks));
+      ctx->stream = ctx->main_stream;
+      CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_k, 0));
+    }
     k_slabcorr<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.f, ffact, dipole_all, ps.qsum,
                                                       ps.pa_have_e ? ps.pa_out.p : nullptr, efact, dipole_r2, zprd);
-    KERNEL_OK(ctx, "k_slabcorr");
+    const cudaError_t slab_err = cudaGetLastError();
+    ctx->stream = ks;
+    if (slab_err != cudaSuccess) return b2_fail(ctx, B200MD_ECUDA, "k_slabcorr: %s", cudaGetErrorString(slab_err));
+    ctx->launches++;
   }
   return 0;
 }
