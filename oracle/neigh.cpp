@@ -1,4 +1,5 @@
-// oracle/neigh.cpp — TEST INFRASTRUCTURE (see oracle.h).  PARITY UNPINNED.
+// oracle/neigh.cpp — TEST INFRASTRUCTURE (see oracle.h).  Upstream behaviour (the reference ships no neighbour code):
+// pinned by the O(N^2) known-answer pair set, not by oracle/_ref.
 //
 // CPU restatement of the stock-LAMMPS services the reference's pair loops consume but do not ship
 // (SURVEY.md Appendix A.3): periodic ghost atoms (Comm::borders, single rank) and the binned half

@@ -6,10 +6,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load it.  The product (lammps-buck-intel_b200/) never links or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, logs or golden vectors, and cannot
- * be compiled here (needs LAMMPS core + MPI + ICC).  The oracle is
- * pinned only by known-answer tests this repo authors (tests/test_oracle_kat.py):
- * closed-form dimers, -dE/dr, libm erfc, direct Ewald sums, the NaCl Madelung constant.
+ * PARITY PINNED against the reference's own code: oracle/Makefile.ref compiles pair_buck*_intel.cpp, pppm_intel.cpp
+ * and fix_nve_intel.cpp UNCHANGED from /root/reference (against the stand-in LAMMPS headers of oracle/ref_shim/) into
+ * oracle/_ref/libref.so, and tests/test_oracle_vs_ref.py asserts that this restatement and that library agree BIT FOR
+ * BIT (one thread) on forces, per-atom energies, energies, both virial forms, densities, fields, x and v, in double and
+ * mixed precision, analytic and table branches.  What the reference does not ship (the stock base classes: init_one,
+ * Pair::init_tables, PPPM::set_grid_global / compute_gf_ik / compute_rho_coeffs, the neighbour list, FFT3d) stays
+ * pinned only by the known-answer tests this repo authors (tests/test_oracle_kat.py): closed-form dimers, -dE/dr, libm
+ * erfc, direct Ewald sums, the NaCl Madelung constant.  pppm_disp_intel.cpp is not in oracle/_ref (needs the whole stock
+ * PPPMDisp and does not compile as shipped): the dispersion grid is KAT-pinned only.
  *
  * Conventions: atom types are 1-based (LAMMPS); per-type-pair arrays are
  * (ntypes+1)x(ntypes+1) row-major, index [itype*(ntypes+1)+jtype]; x is [n][3];
@@ -154,6 +159,19 @@ const double *orc_pppm_density_fft(const orc_pppm *p);   /* after compute: folde
 const double *orc_pppm_field(const orc_pppm *p, int dim);/* after compute: vdx/vdy/vdz (or u) nfft */
 const double *orc_pppm_sf_coeff(const orc_pppm *p);
 void orc_pppm_rho_coeff(const orc_pppm *p, double *rho_coeff /*order*order*/, double *drho_coeff);
+
+/* everything PPPMIntel reads from its base class, exported so that the reference's own compiled
+ * loops (oracle/_ref, ref_harness.cpp) can run on exactly the state the restatement uses */
+typedef struct {
+  int nx, ny, nz, order, diff_ad, nlower, nupper;
+  int lo_out[3], hi_out[3];
+  double shift, shiftone, g_ewald, qqrd2e, scale, volume;
+  double boxlo[3], prd[3], delinv[3], delvolinv;
+  const double *greensfn, *vg /*[nfft][6]*/, *fkx, *fky, *fkz;
+  const double *rho_coeff, *drho_coeff /*[order][order], k - nlower*/;
+  double sf_coeff[6];
+} orc_pppm_state;
+void orc_pppm_export(const orc_pppm *p, orc_pppm_state *st);
 
 /* 3-D complex FFT used by the oracle (KISS-style mixed radix), dir=+1 is exp(+ikx) (LAMMPS flag=1), -1 is exp(-ikx),
  * unnormalised, interleaved re/im, x fastest. */

@@ -1,4 +1,5 @@
-// oracle/pair.cpp — TEST INFRASTRUCTURE (see oracle.h).  PARITY UNPINNED.
+// oracle/pair.cpp — TEST INFRASTRUCTURE (see oracle.h).  Pinned bit for bit against the reference's own compiled loops
+// (oracle/_ref, tests/test_oracle_vs_ref.py).
 //
 // CPU restatement of the reference's four Buckingham eval<> loops, in the reference's own structure:
 // OpenMP static i-range split, thread-private force arrays reduced after the loop, flt_t arithmetic with
@@ -168,12 +169,14 @@ void eval(const int vflag, const int eatom, const int nlocal, const int nall, co
         }
         if (STYLE == ORC_BUCK_COUL_LONG || (STYLE == ORC_BUCK_LONG_COUL_LONG && ORDER1)) {
           // coul/long: whole Coulomb block gated by cutsq (:291); long/coul/long: same (:350)
-          if (!ncoultablebits || rsq <= tabinnersq) {
+          if (!ncoultablebits || (STYLE == ORC_BUCK_LONG_COUL_LONG ? rsq <= pp.tabinnersq : rsq <= tabinnersq)) {
             const flt_t A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741;
             const flt_t A4 = -1.453152027, A5 = 1.061405429;
             const flt_t EWALD_F = 1.12837917;
             const flt_t INV_EWALD_P = 1.0 / 0.3275911;
-            const flt_t grij = g_ewald * r;
+            // long/coul/long has no flt_t local for g_ewald: the product uses the base class's double member and only
+            // the assignment rounds (pair_buck_long_coul_long_intel.cpp:361); coul/long multiplies in flt_t (:167,304)
+            const flt_t grij = STYLE == ORC_BUCK_LONG_COUL_LONG ? (flt_t)(pp.g_ewald * r) : g_ewald * r;
             const flt_t expm2 = std::exp(-grij * grij);
             const flt_t t = INV_EWALD_P / (INV_EWALD_P + grij);
             const flt_t erfc = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * expm2;
@@ -206,13 +209,14 @@ void eval(const int vflag, const int eatom, const int nlocal, const int nall, co
           const flt_t r6inv = r2inv * r2inv * r2inv;
           const flt_t rexp = std::exp(-r * fc.rhoinv[ij]);
           if (STYLE == ORC_BUCK_LONG_COUL_LONG && ORDER6) {
-            if (!ndisptablebits || rsq <= tabinnerdispsq) {  // :414-431
+            if (!ndisptablebits || rsq <= pp.tabinnerdispsq) {  // :414-431 (double member, like :351)
               const flt_t grij2 = g2 * rsq;
               const flt_t a2 = (flt_t)1.0 / grij2;
               const flt_t x2 = a2 * std::exp(-grij2) * fc.c[ij];
-              forcebuck = r * rexp * fc.buck1[ij] -
-                          g8 * x2 * rsq * ((((flt_t)6.0 * a2 + (flt_t)6.0) * a2 + (flt_t)3.0) * a2 + (flt_t)1.0);
-              if (EFLAG) evdwl = rexp * fc.a[ij] - g6 * x2 * ((a2 + (flt_t)1.0) * a2 + (flt_t)0.5);
+              // the reference writes the polynomial with plain double literals (:418-422): in mixed mode it is evaluated in
+              // double and only the assignment rounds to flt_t (found by the bitwise check against oracle/_ref)
+              forcebuck = r * rexp * fc.buck1[ij] - g8 * x2 * rsq * (((6.0 * a2 + 6.0) * a2 + 3.0) * a2 + 1.0);
+              if (EFLAG) evdwl = rexp * fc.a[ij] - g6 * x2 * ((a2 + 1.0) * a2 + 0.5);
             } else {  // :433-444
               const float rsq_lookup = (float)rsq;
               const int itable = (float_bits(rsq_lookup) & ndispmask) >> ndispshiftbits;
@@ -224,7 +228,7 @@ void eval(const int vflag, const int eatom, const int nlocal, const int nall, co
             }
             if (sbindex) {  // :423-431, :445-453
               const flt_t f = fc.special_lj[sbindex];
-              const flt_t t = (f - (flt_t)1.0);
+              const flt_t t = (f - 1.0);
               forcebuck += t * r * rexp * fc.buck1[ij] - t * r6inv * fc.buck2[ij];
               if (EFLAG) evdwl += t * rexp * fc.a[ij] - t * r6inv * fc.c[ij];
             }

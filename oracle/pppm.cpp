@@ -1,4 +1,6 @@
-// oracle/pppm.cpp — TEST INFRASTRUCTURE (see oracle.h).  PARITY UNPINNED.
+// oracle/pppm.cpp — TEST INFRASTRUCTURE (see oracle.h).  The loops restated from pppm_intel.cpp are pinned bit for bit
+// against the reference's own compiled code (oracle/_ref, tests/test_oracle_vs_ref.py); the stock base-class parts
+// (grid sizing, Green's functions, pppm/disp) by known-answer tests only.
 //
 // CPU restatement of PPPMIntel (single rank, orthogonal periodic box, FFT_SCALAR = double):
 //   compute          pppm_intel.cpp:104-317        particle_map   :326-392
@@ -1082,6 +1084,21 @@ const double *orc_pppm_greensfn(const orc_pppm *p) { return p->greensfn.data(); 
 const double *orc_pppm_density_fft(const orc_pppm *p) { return p->density_fft.data(); }
 const double *orc_pppm_field(const orc_pppm *p, int dim) { return p->out_field[dim].data(); }
 const double *orc_pppm_sf_coeff(const orc_pppm *p) { return p->sf_coeff; }
+void orc_pppm_export(const orc_pppm *p, orc_pppm_state *st) {
+  st->nx = p->nx_pppm; st->ny = p->ny_pppm; st->nz = p->nz_pppm;
+  st->order = p->order; st->diff_ad = p->diff_ad; st->nlower = p->nlower; st->nupper = p->nupper;
+  st->lo_out[0] = p->nxlo_out; st->lo_out[1] = p->nylo_out; st->lo_out[2] = p->nzlo_out;
+  st->hi_out[0] = p->nxhi_out; st->hi_out[1] = p->nyhi_out; st->hi_out[2] = p->nzhi_out;
+  st->shift = p->shift; st->shiftone = p->shiftone; st->g_ewald = p->g_ewald; st->qqrd2e = p->qqrd2e;
+  st->scale = p->scale; st->volume = p->volume;
+  for (int d = 0; d < 3; d++) { st->boxlo[d] = p->boxlo[d]; st->prd[d] = p->prd[d]; }
+  st->delinv[0] = p->delxinv; st->delinv[1] = p->delyinv; st->delinv[2] = p->delzinv;
+  st->delvolinv = p->delvolinv;
+  st->greensfn = p->greensfn.data(); st->vg = p->vg.data();
+  st->fkx = p->fkx.data(); st->fky = p->fky.data(); st->fkz = p->fkz.data();
+  st->rho_coeff = p->rho_coeff.data(); st->drho_coeff = p->drho_coeff.data();
+  for (int k = 0; k < 6; k++) st->sf_coeff[k] = p->sf_coeff[k];
+}
 void orc_pppm_rho_coeff(const orc_pppm *p, double *rho_coeff, double *drho_coeff) {
   for (size_t i = 0; i < p->rho_coeff.size(); i++) {
     rho_coeff[i] = p->rho_coeff[i];

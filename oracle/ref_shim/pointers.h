@@ -1,0 +1,2 @@
+/* pointers.h — forwarder: the stand-in classes live in lammps_stub.h (TEST INFRASTRUCTURE, see that file) */
+#include "lammps_stub.h"
