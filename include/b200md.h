@@ -24,6 +24,16 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* Limits (stated, and reported as errors rather than silently exceeded):
+ *  - at most B200MD_MAX_TYPES = 8 atom types (the per-type-pair constants are staged in shared memory):
+ *    b200md_pair_setup fails with B200MD_EINVAL beyond that;
+ *  - lists built on the device carry the type of j in bits 26..29 of an entry while owned + ghost atoms of one GPU stay
+ *    <= 2^26 (67 M) and ntypes < 16; beyond that the entries are plain 30-bit indices and the pair kernel gathers
+ *    type[j] (slower, same results); 2^30 owned + ghost atoms per GPU is the hard limit of the entry format
+ *    (NEIGHMASK, like the reference's);
+ *  - a neighbour list may hold more than 2^31 entries (offsets are 64-bit). */
+#define B200MD_MAX_TYPES 8
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -182,10 +192,6 @@ int b200md_pppm_compute_host(b200md_ctx *ctx, int eflag, int vflag, int n, const
 int b200md_pppm_download(b200md_ctx *ctx, double *density_fft, double *greensfn, double *field_x,
                          double *field_y, double *field_z, double sf_coeff[6]);
 
-/* host-only plan of the tiled charge assignment, exposed for the CPU tests: shared-memory x pitch of a stencil block,
- * lane -> stencil-face point map (-1 = idle lane) and, for a dimension of n grid points, the covering tiles of every
- * coordinate as tile * 16 + local coordinate (-1 = unused), four entries per coordinate */
-int b200md_debug_rho_plan(int order, int n, int *pitch, int *lane_point, int *cover);
 
 /* hand-written 3-D complex FFT used by PPPM, exposed for parity tests (replaces FFT3d::compute,
  * pppm_intel.cpp:835,903): data = nz*ny*nx interleaved re/im doubles on the HOST, transformed in place;
@@ -218,6 +224,11 @@ int b200md_run_timed(b200md_ctx *ctx, long nsteps, double *thermo, double *elaps
  * H2D of x_in[n][3] (NULL: keep device positions), one step, D2H of x_out and f_out ([n][3], may be NULL).
  * Pass pinned memory for full PCIe speed. */
 int b200md_step_host(b200md_ctx *ctx, const double *x_in, double *x_out, double *f_out);
+/* the same on any number of GPUs: atoms migrate between the ranks, so results come back in DEVICE order with the atoms'
+ * global ids (first id of the rank's upload + upload index).  Positions stay resident (no upload); *n_out = atoms owned
+ * after this step's migration (<= capacity, else an error).  ids / x_out / f_out may be NULL. */
+int b200md_step_host_ids(b200md_ctx *ctx, int capacity, int *n_out, int *ids, double *x_out /*[cap][3]*/,
+                         double *f_out /*[cap][3]*/);
 /* forces only (setup phase of a run: build + pair + kspace), energies in thermo like b200md_run */
 int b200md_setup_forces(b200md_ctx *ctx, int eflag, int vflag, double *thermo);
 
@@ -229,9 +240,7 @@ int b200md_timers_get(b200md_ctx *ctx, double *ms, long *calls, int n);
 int b200md_timers_reset(b200md_ctx *ctx);
 int b200md_timer_count(void);
 const char *b200md_timer_name(int i);
-/* roofline denominators measured on this device ("P_fp measured on the box by a microbenchmark"):
- * kind 0 = FP64 FMA TFLOP/s, 1 = FP32 FMA TFLOP/s, 2 = HBM copy GB/s (read+write bytes).  Not a reference API. */
-int b200md_microbench(b200md_ctx *ctx, int kind, double *value);
+
 /* number of kernels this library launched since ctx creation (bench.py's gpu_launches) */
 long b200md_launch_count(const b200md_ctx *ctx);
 
@@ -246,6 +255,10 @@ long b200md_launch_count(const b200md_ctx *ctx);
  * transpose to z pencils.  Arrays are [nranks].  Non-zero return: a halo would reach beyond the neighbouring rank. */
 int b200md_pppm_decomp(int nranks, int nz, int ny, int order, double skin, double prd_z, int *pzlo, int *pzhi,
                        int *zoff, int *nbz, int *ylo, int *yhi);
+/* Call order: b200md_comm_init and b200md_neigh_setup come BEFORE b200md_pppm_setup.  b200md_comm_init drops any
+ * k-space state (it holds the rank count and the slab plan), b200md_neigh_setup drops it when the new skin is larger
+ * than the one its brick halo (skin/2) was sized for: a later b200md_pppm_compute then fails with "pppm compute before
+ * b200md_pppm_setup" instead of solving on a stale decomposition. */
 int b200md_comm_unique_id(void *id128);
 int b200md_comm_init(b200md_ctx *ctx, int rank, int nranks, const void *id128);
 int b200md_comm_finalize(b200md_ctx *ctx);

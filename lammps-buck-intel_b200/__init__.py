@@ -20,6 +20,7 @@ ROOT = os.path.dirname(HERE)
 LIBPATH = os.environ.get("B200MD_LIB") or os.path.join(HERE, "libb200md.so")
 CSRC = os.path.join(HERE, "csrc")
 HEADER = os.path.join(ROOT, "include", "b200md.h")
+HEADER_TESTING = os.path.join(ROOT, "include", "b200md_testing.h")
 
 PREC_DOUBLE, PREC_MIXED = 0, 1
 PAIR_BUCK, PAIR_BUCK_COUL_CUT, PAIR_BUCK_COUL_LONG, PAIR_BUCK_LONG_COUL_LONG = 0, 1, 2, 3
@@ -45,7 +46,7 @@ def build(force=False, verbose=False):
     """nvcc -> lammps-buck-intel_b200/libb200md.so (in-tree, so it travels to the GPU box).
     Each .cu is compiled to build/<name>.o (in parallel, only when stale), then linked."""
     from concurrent.futures import ThreadPoolExecutor
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [HEADER]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [HEADER, HEADER_TESTING]
     hdr_m = max(os.path.getmtime(h) for h in hdrs)
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
@@ -621,6 +622,13 @@ class Context:
     def step_host(self, x_in, x_out, f_out):
         """x_in/x_out/f_out: C-contiguous float64 [n,3] numpy arrays (pinned for speed) or None"""
         self._ck(self.lib.b200md_step_host(self.h, _d(x_in), _d(x_out), _d(f_out)))
+
+    def step_host_ids(self, ids, x_out, f_out):
+        """one step on any number of GPUs; ids int32 [cap], x_out / f_out float64 [cap,3] (pinned for speed) are filled
+        in device order for the atoms this rank owns after the step; returns that count"""
+        n = C.c_int(0)
+        self._ck(self.lib.b200md_step_host_ids(self.h, C.c_int(len(ids)), C.byref(n), _i(ids), _d(x_out), _d(f_out)))
+        return n.value
 
     # ---- multi-GPU ----------------------------------------------------------------------------------
     def comm_init(self, rank, nranks, unique_id=None):

@@ -9,6 +9,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "internal.h"
 
@@ -105,6 +106,90 @@ int b2_comm_alltoallv(b200md_ctx *ctx, const void *sbuf, const size_t *scount, c
   return 0;
 }
 
+int b2_comm_barrier(b200md_ctx *ctx) {
+  CommState *cs = ctx->comm;
+  if (!cs) return 0;
+  RESERVE(ctx, cs->cnt, 8);
+  // an all-reduce cannot complete on any rank before every rank has launched it, i.e. has finished the stream work
+  // ahead of it: stores into peer memory issued before the barrier are complete when kernels after it run
+  NCCL_OK(ctx, ncclAllReduce(cs->cnt.p + 4, cs->cnt.p + 5, 1, ncclInt, ncclSum, cs->comm, ctx->stream));
+  return 0;
+}
+
+int b2_comm_peer_alloc(b200md_ctx *ctx, PeerBuf &pb, size_t bytes, int *ok) {
+  CommState *cs = ctx->comm;
+  *ok = 0;
+  if (!cs || cs->nranks < 2) return 0;
+  const int P = cs->nranks, me = cs->rank;
+  b2_comm_peer_free(ctx, pb);
+  int good = 1;
+  void *loc = nullptr;
+  cudaIpcMemHandle_t h;
+  std::memset(&h, 0, sizeof(h));
+  if (cudaMalloc(&loc, bytes) != cudaSuccess) { good = 0; loc = nullptr; cudaGetLastError(); }
+  if (good && cudaIpcGetMemHandle(&h, loc) != cudaSuccess) { good = 0; cudaGetLastError(); }
+  // all-gather the handles (64 B each) and every rank's status
+  DevBuf<unsigned char> hb;
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + sizeof(int);
+  if (hb.reserve(rec * (size_t)(P + 1))) { if (loc) cudaFree(loc); return b2_fail(ctx, B200MD_ENOMEM, "peer alloc: out of memory"); }
+  std::vector<unsigned char> host(rec * (size_t)P);
+  std::memcpy(host.data(), &h, sizeof(h));
+  std::memcpy(host.data() + sizeof(h), &good, sizeof(int));
+  CUDA_OK(ctx, cudaMemcpyAsync(hb.p + rec * P, host.data(), rec, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_OK(ctx, ncclAllGather(hb.p + rec * P, hb.p, rec, ncclChar, cs->comm, ctx->stream));
+  CUDA_OK(ctx, cudaMemcpyAsync(host.data(), hb.p, rec * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int q = 0; q < P; q++) {
+    int g;
+    std::memcpy(&g, host.data() + rec * q + sizeof(h), sizeof(int));
+    if (!g) good = 0;
+  }
+  void *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (good) {
+    for (int q = 0; q < P; q++) {
+      if (q == me) { peer[q] = loc; continue; }
+      cudaIpcMemHandle_t hq;
+      std::memcpy(&hq, host.data() + rec * q, sizeof(hq));
+      if (cudaIpcOpenMemHandle(&peer[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        good = 0;
+        peer[q] = nullptr;
+        cudaGetLastError();
+      }
+    }
+  }
+  // the decision is collective: one rank without peer access sends everybody to the NCCL path
+  int *flag = (int *)hb.p;
+  CUDA_OK(ctx, cudaMemcpyAsync(flag, &good, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_OK(ctx, ncclAllReduce(flag, flag, 1, ncclInt, ncclMin, cs->comm, ctx->stream));
+  CUDA_OK(ctx, cudaMemcpyAsync(&good, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  hb.free_();
+  if (!good) {
+    for (int q = 0; q < P; q++)
+      if (q != me && peer[q]) cudaIpcCloseMemHandle(peer[q]);
+    if (loc) cudaFree(loc);
+    return 0;
+  }
+  pb.local = loc;
+  pb.bytes = bytes;
+  for (int q = 0; q < P; q++) pb.peer[q] = peer[q];
+  *ok = 1;
+  return 0;
+}
+
+void b2_comm_peer_free(b200md_ctx *ctx, PeerBuf &pb) {
+  if (!pb.local) return;
+  const int me = b2_comm_rank(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  for (int q = 0; q < 8; q++) {
+    if (pb.peer[q] && q != me && pb.peer[q] != pb.local) cudaIpcCloseMemHandle(pb.peer[q]);
+    pb.peer[q] = nullptr;
+  }
+  cudaFree(pb.local);
+  pb.local = nullptr;
+  pb.bytes = 0;
+}
+
 CommGroup::CommGroup(b200md_ctx *c) : ctx(c) {
   if (ctx->comm && ncclGroupStart() == ncclSuccess) open = true;
 }
@@ -144,6 +229,9 @@ int b200md_comm_init(b200md_ctx *ctx, int rank, int nranks, const void *id128) {
   if (nranks > 8) return b2_fail(ctx, B200MD_EINVAL, "b200md_comm_init: at most 8 ranks (one NVSwitch node)");
   cudaSetDevice(ctx->device);
   b2_comm_free(ctx);
+  // a k-space state keeps the rank count and the slab plan it was set up with: drop it, b200md_pppm_setup must follow
+  b2_pppm_free(ctx);
+  ctx->neigh.ready = false;
   if (nranks == 1) return 0;
   if (!id128) return b2_fail(ctx, B200MD_EINVAL, "b200md_comm_init: missing ncclUniqueId");
   CommState *cs = new CommState();

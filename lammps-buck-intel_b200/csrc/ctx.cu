@@ -35,8 +35,11 @@ int b2_fail(b200md_ctx *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
-static const char *kTimerNames[T_COUNT] = {"neigh",   "comm",       "pair", "make_rho", "fft",
-                                           "poisson", "fieldforce", "nve",  "other"};
+static const char *kTimerNames[T_COUNT] = {"neigh",       "comm",        "pair",         "make_rho",   "fft",
+                                           "poisson",     "fieldforce",  "nve",          "other",      "k_nb_mask",
+                                           "k_nb_fill",   "k_rho_tiles", "k_rho_fold",   "k_fft_x_fwd", "k_fft_y_fwd",
+                                           "k_fft_z_poisson", "k_fft_y_inv", "k_fft_x_inv", "k_nve_initial",
+                                           "k_nve_final"};
 
 namespace {
 

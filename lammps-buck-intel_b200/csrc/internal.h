@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/b200md.h"
+#include "../../include/b200md_testing.h"
 
 #define B2_SBBITS 30
 #define B2_NEIGHMASK 0x3FFFFFFF
@@ -29,9 +30,14 @@
 #define B2_MAXTYPES 8       // (ntypes+1) <= 9 rows staged in shared memory
 #define B2_MAXORDER 7
 
+// phase timers first (they partition the step); the K_* entries time single kernels INSIDE those phases (nested: do not
+// add them to the phase sum) so that bench.py can report a roofline per kernel from the same run
 enum TimerId {
-  T_NEIGH = 0, T_COMM, T_PAIR, T_MAKE_RHO, T_FFT, T_POISSON, T_FIELDFORCE, T_NVE, T_OTHER, T_COUNT
+  T_NEIGH = 0, T_COMM, T_PAIR, T_MAKE_RHO, T_FFT, T_POISSON, T_FIELDFORCE, T_NVE, T_OTHER,
+  K_NB_MASK, K_NB_FILL, K_RHO_TILES, K_RHO_FOLD, K_FFT_X_FWD, K_FFT_Y_FWD, K_FFT_Z_POISSON, K_FFT_Y_INV, K_FFT_X_INV,
+  K_NVE_INITIAL, K_NVE_FINAL, T_COUNT
 };
+#define T_PHASE_COUNT (T_OTHER + 1)
 
 template <class T>
 struct DevBuf {
@@ -226,8 +232,8 @@ struct ScopedTimer {
   b200md_ctx *c;
   int id;
   cudaEvent_t a = nullptr;
-  ScopedTimer(b200md_ctx *ctx, int id_) : c(ctx), id(id_) {
-    if (c->timers_on) {
+  ScopedTimer(b200md_ctx *ctx, int id_, bool enabled = true) : c(ctx), id(id_) {
+    if (c->timers_on && enabled) {
       a = c->timer_event();
       cudaEventRecord(a, c->stream);
     }
@@ -259,6 +265,7 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev);
 // pppm.cu
 int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, double *virial);
 void b2_pppm_free(b200md_ctx *ctx);
+void b2_pppm_skin_changed(b200md_ctx *ctx, double skin);
 // ctx.cu
 int b2_unpack_to_stage(b200md_ctx *ctx, const double4 *src, double *stage3);
 // nve.cu
@@ -287,3 +294,16 @@ struct CommGroup {
 };
 int b2_comm_alltoallv(b200md_ctx *ctx, const void *sbuf, const size_t *scount, const size_t *sdisp, void *rbuf,
                       const size_t *rcount, const size_t *rdisp);
+// peer memory over NVLink / NVSwitch: a buffer of the same size on every rank, mapped into every other rank's address
+// space (CUDA IPC), so that a kernel can store straight into its peers' copies — the FFT transposes of pppm.cu write
+// their blocks where the next pass reads them instead of packing, all-to-all-ing and unpacking.
+struct PeerBuf {
+  void *local = nullptr;
+  size_t bytes = 0;
+  void *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // peer[me] == local
+};
+// collective over all ranks; *ok = 0 when peer access is unavailable on any rank (nothing stays allocated then)
+int b2_comm_peer_alloc(b200md_ctx *ctx, PeerBuf &pb, size_t bytes, int *ok);
+void b2_comm_peer_free(b200md_ctx *ctx, PeerBuf &pb);
+// stream-ordered barrier over the ranks: returns (on the stream) once every rank has reached it
+int b2_comm_barrier(b200md_ctx *ctx);

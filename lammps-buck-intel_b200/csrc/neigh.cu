@@ -1065,8 +1065,11 @@ int b2_neigh_build(b200md_ctx *ctx) {
   k_nb_mask<F, U><<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->xq.p, ctx->xqf.p, ctx->type.p, lstart, gstart, g,   \
                                                         ctx->pair.tp1, ctx->pair.cutneighsq.p, ns.mask_off.p,      \
                                                         ns.maskbuf.p, ns.numneigh.p, ns.flags.p + 2, prefilter)
-    if (ctx->prec == B200MD_PREC_MIXED) { if (ucut) NB_MASK(float, 1); else NB_MASK(float, 0); }
-    else { if (ucut) NB_MASK(double, 1); else NB_MASK(double, 0); }
+    {
+      ScopedTimer tk(ctx, K_NB_MASK);
+      if (ctx->prec == B200MD_PREC_MIXED) { if (ucut) NB_MASK(float, 1); else NB_MASK(float, 0); }
+      else { if (ucut) NB_MASK(double, 1); else NB_MASK(double, 0); }
+    }
 #undef NB_MASK
     KERNEL_OK(ctx, "k_nb_mask");
     clk.mark("mask");
@@ -1093,8 +1096,11 @@ int b2_neigh_build(b200md_ctx *ctx) {
       RESERVE(ctx, ns.entries, (size_t)total + 64);
     }
     clk.mark("scan+alloc");
-    k_nb_fill<<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->type.p, lstart, gstart, g, ns.mask_off.p, ns.maskbuf.p,
-                                                    ns.offsets.p, ns.entries.p, pack);
+    {
+      ScopedTimer tk(ctx, K_NB_FILL);
+      k_nb_fill<<<nblk, NB_THREADS, 0, ctx->stream>>>(n, ctx->type.p, lstart, gstart, g, ns.mask_off.p, ns.maskbuf.p,
+                                                      ns.offsets.p, ns.entries.p, pack);
+    }
     KERNEL_OK(ctx, "k_nb_fill");
     clk.mark("fill");
   }
@@ -1134,6 +1140,8 @@ int b200md_neigh_setup(b200md_ctx *ctx, double skin, int every, int delay, int c
   ctx->neigh.delay = delay;
   ctx->neigh.check = check;
   ctx->neigh.ready = false;
+  // the PPPM brick halo is sized from skin/2 (PPPM::set_grid_local): a k-space state set up for a smaller skin is stale
+  b2_pppm_skin_changed(ctx, skin);
   return 0;
 }
 
@@ -1191,6 +1199,7 @@ int b200md_neigh_download(b200md_ctx *ctx, int *numneigh, long *offsets, int *en
     cleanup();
     return b2_fail(ctx, B200MD_ENOMEM, "out of device memory exporting the neighbour list");
   }
+  if (n == 0) cudaMemsetAsync(off.p, 0, sizeof(long long), ctx->stream);   // offsets[0] of an empty list
   if (n > 0) {
     k_export_counts<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ctx->tag.p, ns.numneigh.p, cnt.p);
     ctx->launches++;

@@ -12,6 +12,16 @@
 
 namespace {
 
+// {x,y,z,w}[n] -> [n][3] in the same (device) order
+__global__ void k_pack3(int n, const double4 *__restrict__ src, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 v = src[i];
+  out[3 * (size_t)i] = v.x;
+  out[3 * (size_t)i + 1] = v.y;
+  out[3 * (size_t)i + 2] = v.z;
+}
+
 // _dtfm of FixNVEIntel::reset_dt (fix_nve_intel.cpp:147-190): dtf / mass[type] or dtf / rmass[i]; 0 outside the group
 __global__ void k_nve_set_dtfm(int n, const int *__restrict__ type, const double *__restrict__ mass, double dtf,
                                double4 *__restrict__ v, const int *__restrict__ tag, int first_id,
@@ -106,6 +116,7 @@ int b2_nve_initial(b200md_ctx *ctx) {
   if (!ctx->nve_ready) return b2_fail(ctx, B200MD_EINVAL, "nve integrate before b200md_nve_setup");
   ScopedTimer tm(ctx, T_NVE);
   if (ctx->nlocal == 0) return 0;
+  ScopedTimer tk(ctx, K_NVE_INITIAL);
   k_nve_initial<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(
       ctx->nlocal, ctx->dtv, ctx->xq.p, ctx->v.p, ctx->f.p, ctx->prec == B200MD_PREC_MIXED ? ctx->xqf.p : nullptr,
       ctx->nve_grouped ? 1 : 0);
@@ -117,6 +128,7 @@ int b2_nve_final(b200md_ctx *ctx) {
   if (!ctx->nve_ready) return b2_fail(ctx, B200MD_EINVAL, "nve integrate before b200md_nve_setup");
   ScopedTimer tm(ctx, T_NVE);
   if (ctx->nlocal == 0) return 0;
+  ScopedTimer tk(ctx, K_NVE_FINAL);
   k_nve_final<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->f.p);
   KERNEL_OK(ctx, "k_nve_final");
   return 0;
@@ -261,6 +273,46 @@ int b200md_step_host(b200md_ctx *ctx, const double *x_in, double *x_out, double 
   TRY(b2_nve_final(ctx));
   if (f_out && n) {
     TRY(b2_unpack_to_stage(ctx, ctx->f.p, ctx->stage.p + 3 * n));
+    CUDA_OK(ctx, cudaMemcpyAsync(f_out, ctx->stage.p + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return 0;
+}
+
+// One timestep with the results handed to the host in DEVICE order together with the atoms' global ids — the form of
+// b200md_step_host that also works on several GPUs, where atoms migrate between the ranks at every rebuild and the
+// host therefore owns no fixed slice: positions stay resident (no upload), every step downloads this rank's ids, x and
+// f.  *n_out = atoms this rank owns after the step's migration; fails if capacity is smaller.
+int b200md_step_host_ids(b200md_ctx *ctx, int capacity, int *n_out, int *ids, double *x_out, double *f_out) {
+  if (!ctx || !n_out) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (!ctx->neigh.ready) return b2_fail(ctx, B200MD_EINVAL, "b200md_step_host_ids before b200md_setup_forces");
+  ctx->ntimestep++;
+  TRY(b2_nve_initial(ctx));
+  int rebuilt = 0;
+  TRY(b200md_neigh_decide(ctx, ctx->ntimestep, &rebuilt));
+  const size_t n = (size_t)ctx->nlocal;
+  *n_out = ctx->nlocal;
+  if (ctx->nlocal > capacity)
+    return b2_fail(ctx, B200MD_EINVAL, "b200md_step_host_ids: capacity %d < %d owned atoms", capacity, ctx->nlocal);
+  RESERVE(ctx, ctx->stage, 8 * n + 16);
+  const int nb = cdiv(ctx->nlocal, 256);
+  if (n) {   // positions and ids are final for this step: their download runs underneath the force kernels
+    if (x_out) {
+      k_pack3<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->xq.p, ctx->stage.p);
+      KERNEL_OK(ctx, "k_pack3");
+    }
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    if (x_out) CUDA_OK(ctx, cudaMemcpyAsync(x_out, ctx->stage.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (ids) CUDA_OK(ctx, cudaMemcpyAsync(ids, ctx->tag.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  TRY(forces(ctx, 0, 0, nullptr));
+  TRY(b2_nve_final(ctx));
+  if (f_out && n) {
+    k_pack3<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->f.p, ctx->stage.p + 3 * n);
+    KERNEL_OK(ctx, "k_pack3");
     CUDA_OK(ctx, cudaMemcpyAsync(f_out, ctx->stage.p + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

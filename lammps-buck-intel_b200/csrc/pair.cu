@@ -136,10 +136,22 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p) {
     RESERVE(ctx, ps.exptab, B2_EXP_TAB);
     CUDA_OK(ctx, cudaMemcpy(ps.exptab.p, et, sizeof(et), cudaMemcpyHostToDevice));
     // fast_exp adds n>>6 to the exponent field without an underflow path: arguments stay above -700
+    // (and never positive): every exponential of the loop is checked here — exp(-r/rho), exp(-(g_ewald r)^2) of the
+    // real-space Ewald term, exp(-g_ewald_6^2 r^2) of the buck/long dispersion term
     for (int i = 1; i < tp1; i++)
-      for (int j = 1; j < tp1; j++)
+      for (int j = 1; j < tp1; j++) {
+        if (!(p->rhoinv[i * tp1 + j] > 0.0))
+          return b2_fail(ctx, B200MD_EINVAL, "buck rho for types %d-%d must be positive", i, j);
         if (std::sqrt(p->cut_ljsq[i * tp1 + j]) * p->rhoinv[i * tp1 + j] > 700.0)
           return b2_fail(ctx, B200MD_EINVAL, "buck rho for types %d-%d is too small for its cutoff: exp(-r/rho) underflows", i, j);
+      }
+    const bool ewald1 = p->style == B200MD_PAIR_BUCK_COUL_LONG ||
+                        (p->style == B200MD_PAIR_BUCK_LONG_COUL_LONG && ((p->ewald_order >> 1) & 1));
+    const bool ewald6 = p->style == B200MD_PAIR_BUCK_LONG_COUL_LONG && ((p->ewald_order >> 6) & 1);
+    if (ewald1 && p->g_ewald * cutmax * p->g_ewald * cutmax > 700.0)
+      return b2_fail(ctx, B200MD_EINVAL, "g_ewald %g is too large for the cutoff %g: exp(-(g r)^2) underflows", p->g_ewald, cutmax);
+    if (ewald6 && p->g_ewald_6 * cutmax * p->g_ewald_6 * cutmax > 700.0)
+      return b2_fail(ctx, B200MD_EINVAL, "g_ewald_6 %g is too large for the cutoff %g: exp(-(g r)^2) underflows", p->g_ewald_6, cutmax);
   }
   // tables
   if (p->ncoultablebits) {
@@ -203,12 +215,25 @@ int b200md_pair_eval_host(b200md_ctx *ctx, int eflag, int vflag, int nlocal, int
   cudaSetDevice(ctx->device);
   const int evflag = ((eflag & 3) || (vflag & 3)) ? 1 : 0;
   if (evflag && !ev) return b2_fail(ctx, B200MD_EINVAL, "ev is NULL but energy/virial requested");
+  // the caller's arrays index device memory (per-type rows of the constant table, gathered atoms): check them here, this
+  // entry point is the boundary for host-built lists
+  const int ntypes = ctx->pair.tp1 - 1;
+  for (int i = 0; i < nall; i++)
+    if (type[i] < 1 || type[i] > ntypes)
+      return b2_fail(ctx, B200MD_EINVAL, "b200md_pair_eval_host: type[%d] = %d outside 1..%d", i, type[i], ntypes);
   long long total = 0;
   int has_special = 0;
   for (int i = 0; i < nlocal; i++) {
+    if (numneigh[i] < 0 || cnumneigh[i] < 0)
+      return b2_fail(ctx, B200MD_EINVAL, "b200md_pair_eval_host: negative count or offset for atom %d", i);
     total = std::max(total, (long long)cnumneigh[i] + numneigh[i]);
-    for (int k = 0; k < numneigh[i] && !has_special; k++)
-      if ((unsigned)firstneigh[cnumneigh[i] + k] >> B2_SBBITS) has_special = 1;
+    for (int k = 0; k < numneigh[i]; k++) {
+      const int e = firstneigh[cnumneigh[i] + k];
+      if ((e & B2_NEIGHMASK) >= nall)
+        return b2_fail(ctx, B200MD_EINVAL, "b200md_pair_eval_host: list entry %d of atom %d points past nall = %d",
+                       e & B2_NEIGHMASK, i, nall);
+      if ((unsigned)e >> B2_SBBITS) has_special = 1;
+    }
   }
   DevBuf<double> dx, dq;
   DevBuf<double4> dxq, df;

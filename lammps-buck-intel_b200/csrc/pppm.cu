@@ -836,6 +836,39 @@ __global__ void k_tr_unpack(int nx, int ny, int nzo, int ncomp, RankRows rr, con
   out[t] = in[rr.boff[p] + (long)comp * nzo * nyl * nx + ((long)z * nyl + (y - rr.ylo[p])) * nx + x];
 }
 
+// ---- peer-memory transposes: the producer stores every element where its consumer (another GPU) will read it -------
+struct PeerPtrs { double2 *p[8]; };
+struct RankPlanes { int zlo[8], zhi[8]; int n; };
+// forward: my x/y-transformed planes [nzo][ny][nx] -> rank q's z-pencil block [gnz][nyl_q][nx], plane zglob0 + z
+// (threads run along x: 16 B stores, nx of them contiguous in the peer's memory)
+__global__ void __launch_bounds__(256)
+k_tr_scatter_fwd(int nx, int ny, int nzo, int zglob0, RankRows rr, PeerPtrs dst, const double2 *__restrict__ in) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long tot = (long)nx * ny * nzo;
+  if (t >= tot) return;
+  const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / ((long)nx * ny));
+  int q = 0;
+  while (y >= rr.yhi[q]) q++;
+  const int nyl = rr.yhi[q] - rr.ylo[q];
+  dst.p[q][((long)(zglob0 + z) * nyl + (y - rr.ylo[q])) * nx + x] = in[t];
+}
+// backward: my pencils [npack][gnz][nyl][nx] -> rank q's [npack][nzo_q][ny][nx] (the layout the inverse y pass reads),
+// rows ylo_me .. ylo_me + nyl of its planes
+__global__ void __launch_bounds__(256)
+k_tr_scatter_bwd(int nx, int ny, int nyl, int gnz, int ylo_me, int npack, RankPlanes rp, PeerPtrs dst,
+                 const double2 *__restrict__ in) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long blk = (long)nx * nyl * gnz;
+  if (t >= blk * npack) return;
+  const int comp = (int)(t / blk);
+  const long r = t - comp * blk;
+  const int x = (int)(r % nx), row = (int)((r / nx) % nyl), z = (int)(r / ((long)nx * nyl));
+  int q = 0;
+  while (z >= rp.zhi[q]) q++;
+  const int nzq = rp.zhi[q] - rp.zlo[q];
+  dst.p[q][(((long)comp * nzq + (z - rp.zlo[q])) * ny + (ylo_me + row)) * nx + x] = in[t];
+}
+
 // per-atom tallies: out = rho(k) * G(k) / N * (1 | vg_c(k)), c = comp - 1 (PPPM::poisson_peratom; vg as in PPPM::setup)
 __global__ void k_peratom_mul(PppmConst c, int comp, double scaleinv, const double2 *__restrict__ rhok,
                               const double *__restrict__ greensfn, const double *__restrict__ fkx,
@@ -918,7 +951,7 @@ int pick_tb(int n, int nbuf) {
 
 template <int LC, int RI, int RO>
 int launch_pass(b200md_ctx *ctx, const FftPlan1d &pl, const PassGeom &pg, const double *in_real, const double2 *in,
-                double2 *out, double *out_real, double s) {
+                double2 *out, double *out_real, double s, int timer_id = -1) {
   const int TB = pick_tb(pl.n, 2);
   const int LP = pl.n | 1;
   const size_t smem = (2 * (size_t)TB * LP + pl.n) * sizeof(double2);   // two line buffers + the twiddle table
@@ -926,7 +959,10 @@ int launch_pass(b200md_ctx *ctx, const FftPlan1d &pl, const PassGeom &pg, const 
   auto kern = k_fft_pass<LC, RI, RO>;
   CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = cdiv(pg.nlines, TB);
-  kern<<<nblk, fft_threads(), smem, ctx->stream>>>(pl, pg, ilog2(TB), LP, in_real, in, out, out_real, s);
+  {
+    ScopedTimer tk(ctx, timer_id >= 0 ? timer_id : T_OTHER, timer_id >= 0);
+    kern<<<nblk, fft_threads(), smem, ctx->stream>>>(pl, pg, ilog2(TB), LP, in_real, in, out, out_real, s);
+  }
   KERNEL_OK(ctx, "k_fft_pass");
   return 0;
 }
@@ -988,9 +1024,9 @@ void compute_gf_denom(PppmConst &c) {
 int fft3d_forward_xy(b200md_ctx *ctx, PppmState &ps, const double *density, double2 *work, int nplanes) {
   const PppmConst &c = ps.c;
   PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1, 0};
-  TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD)));
+  TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD, K_FFT_X_FWD)));
   PassGeom gy{(long)c.nx * nplanes, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
-  TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work, work, nullptr, S_FWD)));
+  TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work, work, nullptr, S_FWD, K_FFT_Y_FWD)));
   return 0;
 }
 
@@ -1057,9 +1093,30 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
       rcount[q] = (size_t)(ps.pzhi[q] - ps.pzlo[q]) * nyl * nx * sizeof(double2);
       rdisp[q] = (size_t)ps.pzlo[q] * nyl * nx * sizeof(double2);
     }
-    k_tr_pack<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, rr, ps.work1.p, ps.tsend.p);
-    KERNEL_OK(ctx, "k_tr_pack");
-    TRY(b2_comm_alltoallv(ctx, ps.tsend.p, scount, sdisp, ps.workT.p, rcount, rdisp));
+    double2 *workT = ps.p2p ? (double2 *)ps.symT.local : ps.workT.p;
+    PeerPtrs peersT, peersW;
+    RankPlanes rp;
+    rp.n = P;
+    for (int q = 0; q < 8; q++) {
+      peersT.p[q] = (double2 *)ps.symT.peer[q];
+      peersW.p[q] = (double2 *)ps.symW.peer[q];
+      rp.zlo[q] = q < P ? ps.pzlo[q] : 0;
+      rp.zhi[q] = q < P ? ps.pzhi[q] : 0;
+    }
+    if (ps.p2p) {
+      // every rank stores its planes straight into the pencil blocks of their owners (NVLink stores from the kernel);
+      // the barrier orders those stores before the z pass of every rank.  Nobody still reads its pencil block: the
+      // second barrier of the previous step came after every rank's z pass.
+      if (plane * nzo > 0) {
+        k_tr_scatter_fwd<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, ps.pzlo[me], rr, peersT, ps.work1.p);
+        KERNEL_OK(ctx, "k_tr_scatter_fwd");
+      }
+      TRY(b2_comm_barrier(ctx));
+    } else {
+      k_tr_pack<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, rr, ps.work1.p, ps.tsend.p);
+      KERNEL_OK(ctx, "k_tr_pack");
+      TRY(b2_comm_alltoallv(ctx, ps.tsend.p, scount, sdisp, ps.workT.p, rcount, rdisp));
+    }
     // ---- z pass + Green's function + gradients + inverse z on my pencils ------------------------------------------
     const int TB = pick_tb(gnz, 3);
     const int LP = gnz | 1;
@@ -1072,19 +1129,34 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   do {                                                                                                          \
     auto kern = k_fft_z_poisson<NC, E>;                                                                         \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, ps.workT.p, ps.workT2.p, ps.greensfn.p, \
+    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, workT, ps.workT2.p, ps.greensfn.p, \
                                              ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, ps.fkx_g.p,            \
                                              ps.fky_g.p + ps.ylos[me], scaleinv, c.g_ewald, ps.partial.p,       \
                                              ps.p.dispersion);                                                  \
   } while (0)
-      if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
-      else { if (ev) ZK(3, 1); else ZK(3, 0); }
+      {
+        ScopedTimer tk(ctx, K_FFT_Z_POISSON);
+        if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
+        else { if (ev) ZK(3, 1); else ZK(3, 0); }
+      }
 #undef ZK
       KERNEL_OK(ctx, "k_fft_z_poisson");
     }
     // ---- transpose back, both packed transforms (Ex + i Ey, Ez) in one exchange: to rank q its planes (contiguous
     //      in [z][row][x]) ----------------------------------------------------------------------------------------
     const int npack = ad ? 1 : 2;
+    double2 *work2 = ps.p2p ? (double2 *)ps.symW.local : nullptr;
+    if (ps.p2p) {
+      // the same the other way: every rank stores its pencils into the plane blocks of their owners, already in the
+      // [pack][plane][y][x] layout of the inverse y pass (no unpack kernel); the first barrier of this step came after
+      // every rank's inverse passes of the previous step, so nobody still reads its plane block
+      if (nT > 0) {
+        k_tr_scatter_bwd<<<cdiv(nT * npack, 256), 256, 0, ctx->stream>>>(nx, ny, nyl, gnz, ps.ylos[me], npack, rp, peersW,
+                                                                        ps.workT2.p);
+        KERNEL_OK(ctx, "k_tr_scatter_bwd");
+      }
+      TRY(b2_comm_barrier(ctx));
+    } else {
     RESERVE(ctx, ps.trecv, (size_t)plane * nzo * npack);
     {
       CommGroup grp(ctx);
@@ -1104,19 +1176,22 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     RESERVE(ctx, ps.work2, (size_t)plane * nzo * npack);
     k_tr_unpack<<<cdiv(plane * nzo * npack, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, npack, rr, ps.trecv.p, ps.work2.p);
     KERNEL_OK(ctx, "k_tr_unpack");
+    work2 = ps.work2.p;
+    }
     // ---- inverse y, x on the owned planes; the x pass stores Re (and Im of the first pack) as the three fields ------
     const long nown = plane * nzo;
     RESERVE(ctx, ps.vd_own, (size_t)nown * ncomp);
     PassGeom gy{(long)nx * nzo * npack, nx, plane, (long)nx, 0};
-    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
+    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work2, work2, nullptr, S_BWD, K_FFT_Y_INV)));
     if (ad) {
       PassGeom gu{(long)ny * nzo, 1, (long)nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gu, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gu, nullptr, work2, nullptr, ps.vd_own.p, S_BWD, K_FFT_X_INV)));
     } else {
       PassGeom gxy{(long)ny * nzo, 1, (long)nx, 1, nown};
-      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd_own.p, S_BWD)));
+      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, work2, nullptr, ps.vd_own.p, S_BWD, K_FFT_X_INV)));
       PassGeom gz{(long)ny * nzo, 1, (long)nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nown, nullptr, ps.vd_own.p + 2 * nown, S_BWD)));
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, work2 + nown, nullptr, ps.vd_own.p + 2 * nown, S_BWD,
+                                K_FFT_X_INV)));
     }
   }
   {
@@ -1283,14 +1358,20 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
                                                                            ps.pa_cx.p, ps.tilebuf.p);             \
     }                                                                                                             \
   } break;
-      switch (c.order) {
-        RHO_TILES(1) RHO_TILES(2) RHO_TILES(3) RHO_TILES(4) RHO_TILES(5) RHO_TILES(6) RHO_TILES(7)
-        default: return b2_fail(ctx, B200MD_EORDER, "PPPM order greater than supported by USER-INTEL");
+      {
+        ScopedTimer tk(ctx, K_RHO_TILES);
+        switch (c.order) {
+          RHO_TILES(1) RHO_TILES(2) RHO_TILES(3) RHO_TILES(4) RHO_TILES(5) RHO_TILES(6) RHO_TILES(7)
+          default: return b2_fail(ctx, B200MD_EORDER, "PPPM order greater than supported by USER-INTEL");
+        }
       }
 #undef RHO_TILES
       KERNEL_OK(ctx, "k_rho_tiles");
-      k_rho_fold<<<dim3(cdiv(c.nx, 32), cdiv(c.ny, 8), c.nz), dim3(32, 8), 0, ctx->stream>>>(c, tg, ps.cover.p, ps.tilebuf.p,
-                                                                                           ps.density.p);
+      {
+        ScopedTimer tk(ctx, K_RHO_FOLD);
+        k_rho_fold<<<dim3(cdiv(c.nx, 32), cdiv(c.ny, 8), c.nz), dim3(32, 8), 0, ctx->stream>>>(c, tg, ps.cover.p,
+                                                                                             ps.tilebuf.p, ps.density.p);
+      }
       KERNEL_OK(ctx, "k_rho_fold");
     } else {  // grids smaller than two tiles per dimension: plain per-point gather
       const dim3 grid(cdiv(c.nx, 8), cdiv(c.ny, 8), cdiv(c.nz, 4));
@@ -1326,23 +1407,27 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
                                              ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, ps.fkx_g.p, ps.fky_g.p,   \
                                              scaleinv, c.g_ewald, ps.partial.p, ps.p.dispersion);            \
   } while (0)
-    if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
-    else { if (ev) ZK(3, 1); else ZK(3, 0); }
+    {
+      ScopedTimer tk(ctx, K_FFT_Z_POISSON);
+      if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
+      else { if (ev) ZK(3, 1); else ZK(3, 0); }
+    }
 #undef ZK
     KERNEL_OK(ctx, "k_fft_z_poisson");
     // inverse y over the packed transforms (2 for ik: Ex + i Ey and Ez; 1 for ad), inverse x storing the real part
     // (and, for the first pack, the imaginary part as the second field)
     const int npack = ad ? 1 : 2;
     PassGeom gy{(long)c.nx * c.nz * npack, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
-    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD)));
+    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD, K_FFT_Y_INV)));
     if (ad) {
       PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD, K_FFT_X_INV)));
     } else {
       PassGeom gxy{(long)c.ny * c.nz, 1, (long)c.nx, 1, nfft};
-      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD)));
+      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD, K_FFT_X_INV)));
       PassGeom gz{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nfft, nullptr, ps.vd.p + 2 * nfft, S_BWD)));
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nfft, nullptr, ps.vd.p + 2 * nfft, S_BWD,
+                                K_FFT_X_INV)));
     }
   }
   if (ev) {
@@ -1427,9 +1512,11 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
 
 }  // namespace
 
-static void free_state(PppmState *&slot) {
+static void free_state(b200md_ctx *ctx, PppmState *&slot) {
   PppmState *ps = slot;
   if (!ps) return;
+  b2_comm_peer_free(ctx, ps->symT);
+  b2_comm_peer_free(ctx, ps->symW);
   for (int d = 0; d < 3; d++) ps->tw[d].free_();
   ps->fkx_g.free_(); ps->fky_g.free_();
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
@@ -1443,8 +1530,16 @@ static void free_state(PppmState *&slot) {
 }
 
 void b2_pppm_free(b200md_ctx *ctx) {
-  free_state(ctx->pppm);
-  free_state(ctx->pppm6);
+  free_state(ctx, ctx->pppm);
+  free_state(ctx, ctx->pppm6);
+}
+
+// The brick halo (lo_out / hi_out, PPPM::set_grid_local) is sized from skin / 2 at setup: a state set up with a smaller
+// skin than the one now in force would raise spurious "Out of range atoms" errors (or, on several GPUs, miss halo
+// planes), so it is dropped; a smaller or equal skin keeps it.
+void b2_pppm_skin_changed(b200md_ctx *ctx, double skin) {
+  if (ctx->pppm && skin > ctx->pppm->skin_setup) free_state(ctx, ctx->pppm);
+  if (ctx->pppm6 && skin > ctx->pppm6->skin_setup) free_state(ctx, ctx->pppm6);
 }
 
 template <class flt_t>
@@ -1558,7 +1653,7 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
       if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "Cannot use nonperiodic boundaries with PPPM");
   }
   PppmState *&slot = p->dispersion ? ctx->pppm6 : ctx->pppm;
-  free_state(slot);
+  free_state(ctx, slot);
   PppmState *ps = new PppmState();
   slot = ps;
   ps->p = *p;
@@ -1591,6 +1686,7 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   ps->gnz = p->nz;
   ps->nranks = b2_comm_nranks(ctx);
   ps->rank = b2_comm_rank(ctx);
+  ps->skin_setup = ctx->neigh.skin;
   int gf_yoff = 0, gf_nyl = p->ny;
   if (ps->nranks > 1) {
     // z-slab decomposition: owned planes, local brick (owned + stencil/skin halo) and z-pencil rows of every rank
@@ -1606,6 +1702,28 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     c.hi_out[2] = c.nz - 1;
     gf_yoff = ps->ylos[me];
     gf_nyl = ps->yhis[me] - ps->ylos[me];
+    // peer-memory transposes: one z-pencil block and one plane block per rank, sized for the largest share and mapped
+    // into every rank (collective; falls back to the NCCL all-to-all when peer access is unavailable or B200MD_P2P=0)
+    const char *pe = getenv("B200MD_P2P");
+    if (!(pe && pe[0] == '0')) {
+      int maxrows = 0, maxplanes = 0;
+      for (int q = 0; q < P; q++) {
+        maxrows = std::max(maxrows, ps->yhis[q] - ps->ylos[q]);
+        maxplanes = std::max(maxplanes, ps->pzhi[q] - ps->pzlo[q]);
+      }
+      const int npack = p->differentiation == 1 ? 1 : 2;
+      const size_t bytesT = ((size_t)p->nx * maxrows * p->nz + 16) * sizeof(double2);
+      const size_t bytesW = ((size_t)p->nx * p->ny * maxplanes * npack + 16) * sizeof(double2);
+      int okT = 0, okW = 0;
+      TRY(b2_comm_peer_alloc(ctx, ps->symT, bytesT, &okT));
+      TRY(b2_comm_peer_alloc(ctx, ps->symW, bytesW, &okW));
+      ps->p2p = okT && okW;
+      if (!ps->p2p) {
+        b2_comm_peer_free(ctx, ps->symT);
+        b2_comm_peer_free(ctx, ps->symW);
+        if (me == 0) fprintf(stderr, "b200md: no peer access between the GPUs, FFT transposes use the NCCL all-to-all\n");
+      }
+    }
   }
   ps->nfft = (long)p->nx * p->ny * c.nz;   // points of the local brick (= the whole grid on one GPU)
   if ((long)p->nx * p->ny * p->nz > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");

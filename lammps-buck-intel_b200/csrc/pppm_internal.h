@@ -63,11 +63,17 @@ struct PppmState {
   // (remap->perform / FFT3d, :664,:835,:903-958), and owned field planes are copied back out to the neighbours'
   // halos (cg->forward_comm, :219-220).
   int nranks = 1, rank = 0;
+  double skin_setup = 0;                         // neighbour skin the brick halo was sized for
   int gnz = 0;                                   // global nz
   std::vector<int> pzlo, pzhi, zoffs, nbzs;      // per rank: owned planes [pzlo,pzhi), brick origin and height
   std::vector<int> ylos, yhis;                   // per rank: y rows owned in the transposed (z-pencil) layout
   DevBuf<double> dens_own, halo_s, halo_r, vd_own;
   DevBuf<double2> tsend, trecv, workT, workT2;
+  // peer-memory transposes (default on several GPUs; B200MD_P2P=0 or missing peer access selects the NCCL all-to-all):
+  // symT = every rank's z-pencil block, symW = every rank's [pack][owned planes][ny][nx] block; the transpose kernels of
+  // the other ranks store straight into them
+  PeerBuf symT, symW;
+  bool p2p = false;
 };
 
 struct PppmView {

@@ -49,6 +49,7 @@ class Atom {
   int nlocal = 0, ntypes = 0;
   long natoms = 0;
   int q_flag = 0;          // atom_style charge
+  int molecule_flag = 0;   // atom_style full: the data file carries a molecule id column
   // contiguous [nlocal][3] storage, as atom->x[0] (fix_nve_intel.cpp:64-66)
   std::vector<double> x, v, f;
   std::vector<double> q;

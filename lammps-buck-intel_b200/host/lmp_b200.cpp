@@ -203,19 +203,22 @@ struct Script {
       if (w.size() >= 4 && w[2] == "xlo") { lo[0] = std::atof(w[0].c_str()); hi[0] = std::atof(w[1].c_str()); continue; }
       if (w.size() >= 4 && w[2] == "ylo") { lo[1] = std::atof(w[0].c_str()); hi[1] = std::atof(w[1].c_str()); continue; }
       if (w.size() >= 4 && w[2] == "zlo") { lo[2] = std::atof(w[0].c_str()); hi[2] = std::atof(w[1].c_str()); continue; }
-      if (w[0] == "Masses" || w[0] == "Atoms" || w[0] == "Velocities") { section = w[0]; continue; }
+      // sections of atom_style full that the pair / k-space path does not read (examples/data.spce) are skipped
+      if (w[0] == "Masses" || w[0] == "Atoms" || w[0] == "Velocities" || w[0] == "Bonds" || w[0] == "Angles" ||
+          w[0] == "Dihedrals" || w[0] == "Impropers") { section = w[0]; continue; }
       if (section == "Masses" && w.size() >= 2) {
         const int t2 = std::atoi(w[0].c_str());
         if (t2 < 1 || t2 > a->ntypes) fail("Invalid type for mass set");
         a->mass[t2] = std::atof(w[1].c_str());
         a->mass_setflag[t2] = 1;
       } else if (section == "Atoms") {
-        // atom_style charge: id type q x y z ; atomic: id type x y z
-        const size_t need = a->q_flag ? 6 : 5;
+        // atom_style charge: id type q x y z ; atomic: id type x y z ; full: id mol type q x y z [ix iy iz]
+        const size_t mol = a->molecule_flag ? 1 : 0;
+        const size_t need = (a->q_flag ? 6 : 5) + mol;
         if (w.size() < need) fail("Incorrect atom format in data file");
         std::array<double, 5> r;
-        r[0] = std::atof(w[1].c_str());
-        size_t c = 2;
+        r[0] = std::atof(w[1 + mol].c_str());
+        size_t c = 2 + mol;
         r[1] = a->q_flag ? std::atof(w[c++].c_str()) : 0.0;
         r[2] = std::atof(w[c].c_str()); r[3] = std::atof(w[c + 1].c_str()); r[4] = std::atof(w[c + 2].c_str());
         rows.push_back({std::atol(w[0].c_str()), r});
@@ -491,6 +494,7 @@ struct Script {
       need(2);
       if (w[1] == "atomic") a->q_flag = 0;
       else if (w[1] == "charge") a->q_flag = 1;
+      else if (w[1] == "full") { a->q_flag = 1; a->molecule_flag = 1; }   // positions and charges only (examples/in.spce)
       else fail("Unknown atom style " + w[1]);
     } else if (c == "lattice") {
       need(3);

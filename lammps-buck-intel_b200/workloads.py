@@ -105,6 +105,22 @@ def fcc_system(nx, ny, nz, rho_star=0.8442, seed=87287, jitter=0.05, temperature
     return dict(x=x, v=v, type=t, q=None, boxlo=lo, boxhi=hi, mass=mass, ntypes=1, units="lj")
 
 
+def spce_system(rep, seed=432567, temperature=300.0):
+    """S4: examples/data.spce (4 500 atoms, SPC/E water; tests/golden/data_spce.npz, made by
+    tests/golden/make_data_spce.py from the reference's file) wrapped into the box and replicated — the PPPM input of
+    in.spce (`read_data data.spce`, `replicate 4 4 4`; positions and charges only: bonds/SHAKE are not on the path)."""
+    import os
+    r = (rep, rep, rep) if np.isscalar(rep) else tuple(rep)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "data_spce.npz")
+    d = np.load(path)
+    lo, hi = d["boxlo"].copy(), d["boxhi"].copy()
+    x = wrap(d["x"], lo, hi)
+    x, t, q, lo, hi = replicate(x, d["type"], d["q"], lo, hi, *r)
+    rng = np.random.default_rng(seed)
+    v = velocities(rng, t, d["mass"], temperature, UNITS["real"])
+    return dict(x=x, v=v, type=t, q=q, boxlo=lo, boxhi=hi, mass=d["mass"].copy(), ntypes=2, units="real")
+
+
 def water_like_system(nmol_side, seed=4711, box=35.5):
     """S4 stand-in for data.spce (positions+charges only, PPPM-only workload): rigid SPC/E-geometry
     molecules (O -0.8472, H +0.4236, r_OH = 1, angle 109.47) on a jittered simple-cubic lattice with random

@@ -11,9 +11,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "b200md.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200md_[a-z0-9_]+)\s*\(", src)))
+    """every function declared in include/*.h (the drop-in boundary b200md.h and the test-only b200md_testing.h)"""
+    syms = set()
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(os.listdir(inc)):
+        if not h.endswith(".h"):
+            continue
+        src = open(os.path.join(inc, h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms.update(re.findall(r"\b(b200md_[a-z0-9_]+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_header_symbols_exported(pkg):

@@ -66,7 +66,8 @@ def test_own_arm_json_line_on_a_small_workload():
     lines = _json_lines(r.stdout)
     assert len(lines) == 1
     d = json.loads(lines[0])
-    for k in [k for k in KEYS if k != "impl"] + ["clocks", "gpu_launches", "roofline"]:
+    for k in [k for k in KEYS if k != "impl"] + ["clocks", "gpu_launches", "roofline", "roofline_kernels",
+                                                 "step_roofline_frac", "parity"]:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 6 and d["warmup"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
@@ -77,3 +78,13 @@ def test_own_arm_json_line_on_a_small_workload():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
     assert d["clocks"]["sm_max_mhz"] > 0
+    # one roofline entry per kernel with >= 1 % of the step, measured in this run
+    names = [r["kernel"] for r in d["roofline_kernels"]]
+    assert "k_pair" in names and any(n.startswith("k_fft") for n in names)
+    for r in d["roofline_kernels"]:
+        assert r["avg_launch_ms"] > 0 and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 2e-3
+    assert 0.0 < d["step_roofline_frac"] <= 1.0
+    # parity of the same styles on the bounded sample (here data.aC x 2^3), GPU vs oracle, inside the bench line
+    p = d["parity"]
+    assert p["ok"] is True and p["pair_set_equal"] is True
+    assert p["max_rel_force_err"] <= 1e-9 and p["epair_rel"] <= 1e-10 and p["ekspace_rel"] <= 1e-9

@@ -134,17 +134,32 @@ def test_decomp_rejects_thin_slabs(pkg):
 
 
 def test_bench_rank_blocks_tile_the_global_system(W):
-    """bench.py at N > 1: every rank generates its own z block; together they are the replicated crystal"""
+    """bench.py at N > 1: every rank generates the z blocks overlapping its slab and keeps the atoms inside it; together
+    they are the replicated crystal — also when the blocks do not align with the slabs (cubic geometry: 5 cells over
+    3 ranks)"""
     import importlib
     sys.path.insert(0, ROOT)
     bench = importlib.import_module("bench")
-    P, rep = 3, 2
-    blocks = [bench.workload(W, rep, r, P) for r in range(P)]
-    whole = W.aC_system((rep, rep, rep * P), jitter=0.0)
-    x = np.concatenate([b["x"] for b in blocks])
-    assert np.allclose(blocks[0]["boxhi"], whole["boxhi"]) and len(x) == len(whole["x"])
-    key = lambda a: np.lexsort(np.round(a, 6).T[::-1])
-    assert np.allclose(x[key(x)], whole["x"][key(whole["x"])], atol=1e-9)
-    lz = (whole["boxhi"][2] - whole["boxlo"][2]) / P
-    for r, b in enumerate(blocks):
-        assert (b["x"][:, 2] >= r * lz - 1e-9).all() and (b["x"][:, 2] < (r + 1) * lz + 1e-9).all()
+    make = lambda r3: W.aC_system(r3, jitter=0.0)
+    for P, reps in ((3, (2, 2, 6)), (3, (2, 2, 5)), (2, (1, 1, 3))):
+        blocks = [bench.rank_system(make, reps, r, P) for r in range(P)]
+        whole = W.aC_system(reps, jitter=0.0)
+        x = np.concatenate([b["x"] for b in blocks])
+        assert np.allclose(blocks[0]["boxhi"], whole["boxhi"]) and len(x) == len(whole["x"])
+        key = lambda a: np.lexsort(np.round(a, 6).T[::-1])
+        assert np.allclose(x[key(x)], whole["x"][key(whole["x"])], atol=1e-9)
+        lz = (whole["boxhi"][2] - whole["boxlo"][2]) / P
+        for r, b in enumerate(blocks):
+            assert (b["x"][:, 2] >= r * lz - 1e-9).all() and (b["x"][:, 2] < (r + 1) * lz + 1e-9).all()
+            assert len(b["x"]) == len(b["type"]) == len(b["q"]) == len(b["v"])
+
+
+def test_bench_cube_geometry_keeps_the_per_gpu_atom_count():
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    for world, r in ((1, 15), (2, 19), (4, 24), (8, 30)):      # SURVEY S3: data.aC x 30^3 on 8 GPUs
+        assert bench.split_reps(15, world, "cube", "weak") == (r, r, r)
+        assert abs(r ** 3 / world / 15 ** 3 - 1.0) < 0.03
+    assert bench.split_reps(15, 8, "slab", "weak") == (15, 15, 120)
+    assert bench.split_reps(24, 4, "slab", "strong") == (24, 24, 24)

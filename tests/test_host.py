@@ -292,3 +292,22 @@ def test_in_buck_coul_cut_and_in_buck_big_run_like_the_oracle(pkg, W, orc, tmp_p
     assert "Neighbor list builds = 0" in r.stdout
     # continuum estimate 4/3 pi (5.3)^3 * 0.8442 = 526.5; the perfect fcc lattice has 530 within 5.3
     assert "Ave neighs/atom = 530" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="the reference tree is only mounted in the build container")
+def test_read_data_atom_style_full_data_spce(pkg, W, tmp_path):
+    """`atom_style full` + `read_data data.spce` (examples/in.spce:3-6): the molecule column is skipped, charges and
+    positions are read, Bonds / Angles sections are ignored; PPPM sizing of the replicated box equals the Python one"""
+    txt = ("units real\natom_style full\nread_data %s/data.spce\nreplicate 2 2 2\n"
+           "pair_style buck/coul/long 8.8\npair_coeff * * 0.0 1.0 0.0\nkspace_style pppm 1.0e-4\n"
+           "neighbor 2.0 bin\nneigh_modify every 1 delay 10 check yes\nfix 1 all nve\nrun 0\n" % REF_EXAMPLES)
+    p = scripts.write(tmp_path, "in.spce_pppm", txt)
+    r = _run(pkg, ["-in", p, "-sf", "intel", "-dry-run"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    s = _summary(r.stdout)
+    sysd = W.spce_system(2)
+    u = W.UNITS["real"]
+    assert s["natoms"] == 36000 == len(sysd["x"])
+    assert np.allclose(s["box"], sysd["boxhi"] - sysd["boxlo"], rtol=1e-12)
+    grid, g = pkg.pppm_init(1e-4, u["qqrd2e"], sysd["q"], 36000, 8.8, sysd["boxhi"] - sysd["boxlo"])
+    assert tuple(s["grid"]) == tuple(grid) and s["g_ewald"] == pytest.approx(g, rel=1e-9)

@@ -31,3 +31,25 @@ def test_data_aC_regenerated_matches_shipped_file(W):
     assert (ref[:, 1].astype(int) == t).all() and np.abs(ref[:, 2] - q).max() == 0.0
     hdr = open(REF).read().split("\n")[5:8]
     assert float(hdr[0].split()[1]) == hi[0] and float(hdr[2].split()[1]) == hi[2]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/examples/data.spce"), reason="reference tree not mounted")
+def test_data_spce_fixture_is_the_reference_file():
+    """tests/golden/data_spce.npz is examples/data.spce (positions, charges, types, box), re-parsed here"""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_data_spce", os.path.join(here, "golden", "make_data_spce.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    d = m.parse("/root/reference/examples/data.spce")
+    g = np.load(os.path.join(here, "golden", "data_spce.npz"))
+    for k in ("x", "q", "type", "mol", "boxlo", "boxhi", "mass"):
+        assert np.array_equal(d[k], g[k]), k
+    assert len(g["x"]) == 4500 and abs(g["q"].sum()) < 1e-9
+
+
+def test_spce_system_replicates_the_fixture(W):
+    s = W.spce_system(2)
+    assert len(s["x"]) == 36000 and s["units"] == "real"
+    assert np.all(s["x"] >= s["boxlo"]) and np.all(s["x"] < s["boxhi"])
+    assert abs(s["q"].sum()) < 1e-8
