@@ -537,19 +537,34 @@ k_rho_tiles(PppmConst c, TileGeom tg, const int *__restrict__ cell_start, const 
       double wx[NR2], wy[NR2];
 #pragma unroll
       for (int q = 0; q < NR2; q++) { wx[q] = horner(cxw[q], cur.x); wy[q] = horner(cyw[q], cur.y); }
+      // the ORDER planes of an atom are distinct addresses: all loads first, then the adds, then all stores, so that the
+      // shared-memory latencies overlap instead of forming ORDER load -> add -> store chains (order of the volatile
+      // accesses = program order; the previous atom's stores precede these loads)
+      double acc[ORDER][NR2];
+#pragma unroll
+      for (int n = 0; n < ORDER; n++)
+#pragma unroll
+        for (int q = 0; q < NR2; q++) {
+          acc[n][q] = 0.0;
+          if (act[q]) {
+            const unsigned ad = sa + off[q] + (unsigned)(n * EEP * 8);   // ptxas folds the constant into the access
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(acc[n][q]) : "r"(ad) : "memory");
+          }
+        }
 #pragma unroll
       for (int n = 0; n < ORDER; n++) {
         const double zw = __shfl_sync(0xffffffffu, zl, n);
 #pragma unroll
+        for (int q = 0; q < NR2; q++) acc[n][q] += (zw * wy[q]) * wx[q];
+      }
+#pragma unroll
+      for (int n = 0; n < ORDER; n++)
+#pragma unroll
         for (int q = 0; q < NR2; q++)
           if (act[q]) {
-            double acc;
-            const unsigned ad = sa + off[q] + (unsigned)(n * EEP * 8);   // ptxas folds the constant into the access
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(acc) : "r"(ad) : "memory");
-            acc += (zw * wy[q]) * wx[q];
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(acc) : "memory");
+            const unsigned ad = sa + off[q] + (unsigned)(n * EEP * 8);
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(acc[n][q]) : "memory");
           }
-      }
       __syncwarp();
       if (!more) break;
     }
