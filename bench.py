@@ -58,6 +58,8 @@ def parse():
                     choices=["buck_coul_long", "buck", "buck_big", "buck_coul_cut", "spce_pppm", "buck_big_disp"])
     ap.add_argument("--rep", type=int, default=0, help="replication per dimension per GPU (0: the config's default; "
                                                        "buck_coul_long 15 -> 4.05 M atoms)")
+    ap.add_argument("--rep3", type=int, nargs=3, default=None, help="explicit replication / cells per dimension (one GPU), "
+                                                                     "e.g. 30 40 40 = the in.buck_big box")
     ap.add_argument("--geometry", default="slab", choices=["slab", "cube"],
                     help="N > 1: 'slab' stacks the per-GPU blocks along z (rep x rep x rep*N), 'cube' replicates the "
                          "global system isotropically to the same atom count (SURVEY S3: data.aC x 30^3 on 8 GPUs)")
@@ -212,6 +214,8 @@ class Config:
         return W.spce_system(rep3)
 
     def global_reps(self):
+        if self.args.rep3 and self.world == 1:
+            return tuple(self.args.rep3)
         return split_reps(self.rep, self.world, self.args.geometry, self.args.scaling)
 
     def setup(self, ctx, s, natoms_global, qsq_global):
@@ -292,7 +296,8 @@ class Config:
 # ---------------------------------------------------------------------------------------------------------------------
 # per-kernel roofline (SURVEY §8d work models; launch times from CUDA events recorded on the launching stream)
 
-def kernel_rooflines(cfg, timers, steps, N, nall, entries, F, G_tiles, fp_peak, hbm_peak, prec, ncomp_packs=2):
+def kernel_rooflines(cfg, timers, steps, N, nall, entries, F, G_tiles, fp_peak, hbm_peak, prec, ncomp_packs=2,
+                     fp32_peak=None):
     """timers: name -> (ms, calls) accumulated over `steps` timed steps on this rank.  Returns (list, ideal ms/step)."""
     flt = 8 if prec == "double" else 4
     fl = PAIR_FLOPS.get(cfg["flops_key"]) if cfg.get("flops_key") else None
@@ -318,8 +323,19 @@ def kernel_rooflines(cfg, timers, steps, N, nall, entries, F, G_tiles, fp_peak, 
     if fl:
         add("k_pair", "pair", "fp64" if prec == "double" else "fp32", fl * entries,
             "%g flop per list entry (SURVEY 8d) x %d entries" % (fl, entries))
-    add("k_nb_mask", "k_nb_mask", "hbm", 32.0 * nall + entries / 8.0 * 3.8,
-        "reads 32 B x nall, writes the hit masks (~3.8 candidates per neighbour, 1 bit each); issue-bound in practice")
+    # the mask kernel is arithmetic: ~3.8 candidates per neighbour (5^3-bin stencil over the cut-off sphere), 9 flop per
+    # distance test (3 sub, 3 mul/fma, compare), FP32 on bin-relative coordinates with an exact FP64 redo in the guard band
+    ms_m, calls_m = timers.get("k_nb_mask", (0.0, 0))
+    if calls_m and fp32_peak:
+        work = 9.0 * 3.8 * entries
+        avg = ms_m / calls_m
+        ach = work / (avg * 1e-3) / 1e12
+        rows.append({"kernel": "k_nb_mask", "bound": "fp32", "avg_launch_ms": round(avg, 4), "launches": int(calls_m),
+                     "ms_per_step": round(ms_m / steps, 4), "work_per_launch": work,
+                     "work_model": "9 flop x 3.8 candidates per list entry (distance tests of the 5^3-bin stencil)",
+                     "achieved": round(ach, 2), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+                     "frac": round(ach / fp32_peak, 4),
+                     "ideal_ms_per_step": round(work / (fp32_peak * 1e12) * 1e3 * calls_m / steps, 4)})
     add("k_nb_fill", "k_nb_fill", "hbm", 4.0 * entries + 8.0 * N + entries / 8.0 * 3.8,
         "writes 4 B x entries + 8 B x N, reads the hit masks")
     add("k_rho_tiles", "k_rho_tiles", "hbm", 40.0 * N + 8.0 * G_tiles, "40 B x N + 8 B x tile-block points")
@@ -581,8 +597,9 @@ def run_b200(args):
     if grid:
         E = 8 + ORDER - 1
         G_tiles = int(np.prod([-(-g // 8) for g in (grid[0], grid[1], max(grid[2] // world, 8))])) * E ** 3
+    fp32_peak = ctx.microbench(1)
     rows, ideal_ms, nbar = kernel_rooflines(desc, timers, args.steps, nlocal0, nlocal0 + int(st1["nghost"]), entries_local,
-                                            F, G_tiles, fp_peak, hbm_peak, args.prec)
+                                            F, G_tiles, fp_peak, hbm_peak, args.prec, fp32_peak=fp32_peak)
     for r in rows:
         r["share_of_step"] = round(r["ms_per_step"] / ms_per_step, 4)
     rows = [r for r in rows if r["share_of_step"] >= 0.01 or r["kernel"] == "k_pair"]
