@@ -459,3 +459,41 @@ def test_edge_cases_empty_ragged_nonperiodic(pkg, W, orc):
     for i in (0, len(x) // 2, len(x) - 1):
         assert np.array_equal(np.sort(ent[off[i]:off[i + 1]] & pkg.NEIGHMASK), np.sort(fent[foff[i]:foff[i + 1]] & pkg.NEIGHMASK))
     ctx.close()
+
+
+def test_table_inner_cutoff_and_list_flavours_agree(pkg, W, orc):
+    """Coulomb tables on a device-built list with a pair inside the tables' inner cut-off (r < sqrt 2: the reference takes
+    the analytic branch there, pair_buck_coul_long_intel.cpp:294) against the oracle, and the packed-type flavour of the
+    kernel against the type-gathering flavour used for host-supplied lists (same pairs)"""
+    s = W.aC_system(1)
+    x = s["x"].copy()
+    # bring one oxygen to 1.25 A of another atom (inside tabinner = sqrt 2)
+    d = x[1] - x[0]
+    d -= np.round(d / (s["boxhi"] - s["boxlo"])) * (s["boxhi"] - s["boxlo"])
+    x[1] = x[0] + d / np.linalg.norm(d) * 1.25
+    s = dict(s, x=W.wrap(x, s["boxlo"], s["boxhi"]))
+    u = W.UNITS["metal"]
+    co = W.coeffs_aC(12.0, 12.0)
+    ge = 0.2776
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=ge)
+    ct = pkg.init_coul_tables(12.0, ge, u["qqrd2e"])
+    P.set_coul_tables(ct[0], 12, ct[1], ct[2], ct[3])
+    cf = pkg.pair_coeffs(pkg.PAIR_BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+    ctx = pkg.make_context(s)
+    ctx.neigh_setup(0.3)
+    ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=ge, coul_tables=ct)
+    ctx.neigh_build()
+    ev = ctx.pair_compute(1, 1)
+    f = ctx.atoms_download(("f",))["f"]
+    fo, evo, aux = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    assert util.rel_force_err(f, fo[:, :3]) <= 1e-9
+    assert abs(ev[1] - evo[1]) <= 1e-10 * abs(evo[1]) and abs(ev[0] - evo[0]) <= 1e-10 * max(abs(evo[0]), abs(evo[1]))
+    # the generic flavour (host-supplied list of the same pairs, type gathered, branches as the reference has them)
+    nn, off, ent, gsrc, gshift = ctx.neigh_download()
+    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], P.cutmax() + 0.3)
+    hn, hoff, hent = orc.neigh_full_brute(len(x), xa, ta, 2, P.cutneighsq(0.3), 0)
+    fg, evg = ctx.pair_eval_host(1, 1, len(x), xa, ta, qa, hn, hoff[:-1], hent)
+    assert util.rel_force_err(f, fg[:, :3]) <= 1e-12
+    assert abs(ev[1] - evg[1]) <= 1e-12 * abs(evg[1])
+    ctx.close()
