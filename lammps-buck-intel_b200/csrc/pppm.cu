@@ -1118,10 +1118,25 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
       rp.zlo[q] = q < P ? ps.pzlo[q] : 0;
       rp.zhi[q] = q < P ? ps.pzhi[q] : 0;
     }
-    if (ps.p2p) {
+    if (ps.p2p && ps.p2p_dma) {
+      // copy engines: one strided (2-D) device-to-peer copy per destination moves my planes' rows ylo_q..yhi_q
+      // straight into rank q's pencil block at plane pzlo_me — no pack kernel, no SM time (the pair kernel that runs
+      // underneath on the main stream keeps the SMs), NVLink at DMA speed.  The barrier orders the copies before the z
+      // pass of every rank; nobody still reads its pencil block (the second barrier of the previous step came after
+      // every rank's z pass).
+      for (int k = 0; k < P && nzo > 0; k++) {
+        const int q = (me + k) % P;   // start with myself, then round the ring: spreads the traffic over the peers
+        const int nylq = ps.yhis[q] - ps.ylos[q];
+        if (nylq == 0) continue;
+        CUDA_OK(ctx, cudaMemcpy2DAsync(peersT.p[q] + (size_t)ps.pzlo[me] * nylq * nx, (size_t)nylq * nx * sizeof(double2),
+                                       ps.work1.p + (size_t)ps.ylos[q] * nx, (size_t)plane * sizeof(double2),
+                                       (size_t)nylq * nx * sizeof(double2), (size_t)nzo, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+      }
+      TRY(b2_comm_barrier(ctx));
+    } else if (ps.p2p) {
       // every rank stores its planes straight into the pencil blocks of their owners (NVLink stores from the kernel);
-      // the barrier orders those stores before the z pass of every rank.  Nobody still reads its pencil block: the
-      // second barrier of the previous step came after every rank's z pass.
+      // the barrier orders those stores before the z pass of every rank.
       if (plane * nzo > 0) {
         k_tr_scatter_fwd<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, ps.pzlo[me], rr, peersT, ps.work1.p);
         KERNEL_OK(ctx, "k_tr_scatter_fwd");
@@ -1161,10 +1176,23 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     //      in [z][row][x]) ----------------------------------------------------------------------------------------
     const int npack = ad ? 1 : 2;
     double2 *work2 = ps.p2p ? (double2 *)ps.symW.local : nullptr;
-    if (ps.p2p) {
-      // the same the other way: every rank stores its pencils into the plane blocks of their owners, already in the
-      // [pack][plane][y][x] layout of the inverse y pass (no unpack kernel); the first barrier of this step came after
-      // every rank's inverse passes of the previous step, so nobody still reads its plane block
+    if (ps.p2p && ps.p2p_dma) {
+      // the same the other way: per destination and packed field one 2-D copy puts my rows of its planes where its
+      // inverse y pass reads them ([pack][plane][y][x]: no unpack kernel).  The first barrier of this step came after
+      // every rank's inverse passes of the previous step, so nobody still reads its plane block.
+      for (int k = 0; k < P && nyl > 0; k++) {
+        const int q = (me + k) % P;
+        const int nzq = ps.pzhi[q] - ps.pzlo[q];
+        if (nzq == 0) continue;
+        for (int comp = 0; comp < npack; comp++)
+          CUDA_OK(ctx, cudaMemcpy2DAsync(peersW.p[q] + ((size_t)comp * nzq * ny + ps.ylos[me]) * nx, (size_t)plane * sizeof(double2),
+                                         ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * nx,
+                                         (size_t)nyl * nx * sizeof(double2), (size_t)nyl * nx * sizeof(double2), (size_t)nzq,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      TRY(b2_comm_barrier(ctx));
+    } else if (ps.p2p) {
+      // kernel flavour of the same: every rank stores its pencils into the plane blocks of their owners
       if (nT > 0) {
         k_tr_scatter_bwd<<<cdiv(nT * npack, 256), 256, 0, ctx->stream>>>(nx, ny, nyl, gnz, ps.ylos[me], npack, rp, peersW,
                                                                         ps.workT2.p);
@@ -1719,7 +1747,10 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     gf_nyl = ps->yhis[me] - ps->ylos[me];
     // peer-memory transposes: one z-pencil block and one plane block per rank, sized for the largest share and mapped
     // into every rank (collective; falls back to the NCCL all-to-all when peer access is unavailable or B200MD_P2P=0)
+    // B200MD_P2P: 0 = NCCL all-to-all (pack kernel, grouped send/recv, unpack kernel), 1 = stores from a scatter
+    // kernel, 2 = strided copy-engine copies (default)
     const char *pe = getenv("B200MD_P2P");
+    ps->p2p_dma = !(pe && pe[0] == '1');
     if (!(pe && pe[0] == '0')) {
       int maxrows = 0, maxplanes = 0;
       for (int q = 0; q < P; q++) {

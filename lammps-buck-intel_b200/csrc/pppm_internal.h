@@ -73,7 +73,7 @@ struct PppmState {
   // symT = every rank's z-pencil block, symW = every rank's [pack][owned planes][ny][nx] block; the transpose kernels of
   // the other ranks store straight into them
   PeerBuf symT, symW;
-  bool p2p = false;
+  bool p2p = false, p2p_dma = true;
 };
 
 struct PppmView {

@@ -8,7 +8,7 @@ OUT=gpurun_out/r2_mgpu_check_${N}.txt
 : > $OUT
 port=29600
 tr() { port=$((port+1)); python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port "$@"; }
-for p2p in 1 0; do
+for p2p in ${P2PS:-2 0}; do
   for mode in "0 0" "1 0" "0 1"; do
     set -- $mode
     echo "== N=$N DIFF=$1 DISP=$2 B200MD_P2P=$p2p" >> $OUT
@@ -17,8 +17,8 @@ for p2p in 1 0; do
 done
 cat $OUT
 if [ "${BENCH:-1}" = "1" ]; then
-  for geo in slab cube; do
-    for p2p in 1 0; do
+  for geo in ${GEOS:-slab cube}; do
+    for p2p in ${P2PS:-2 0}; do
       f=gpurun_out/r2_bench_${N}gpu_${geo}_p2p${p2p}
       B200MD_P2P=$p2p tr bench.py --gpus $N --steps ${STEPS:-20} --warmup 5 --geometry $geo > $f.json 2> $f.err
       echo "bench $geo p2p=$p2p rc=$?"; tail -c 400 $f.err
