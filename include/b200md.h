@@ -63,7 +63,11 @@ enum {
   B200MD_PAIR_BUCK = 0,
   B200MD_PAIR_BUCK_COUL_CUT = 1,
   B200MD_PAIR_BUCK_COUL_LONG = 2,
-  B200MD_PAIR_BUCK_LONG_COUL_LONG = 3
+  B200MD_PAIR_BUCK_LONG_COUL_LONG = 3,
+  /* lj/long/coul/long/intel, pair_lj_long_coul_long_intel.h:20 (with `cut long` it is the
+   * lj/cut/coul/long of examples/in.spce:7).  In b200md_pair_params buck1, buck2, a, c carry lj1, lj2, lj3, lj4
+   * (pair_lj_long_coul_long_intel.cpp:831-834); rhoinv is not read. */
+  B200MD_PAIR_LJ_LONG_COUL_LONG = 4
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -124,6 +128,14 @@ typedef struct {
 } b200md_pair_params;
 
 int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p);
+
+/* special bonds for lists built on the device (molecular systems: the 1-2 / 1-3 / 1-4 partners that stock Neighbor
+ * flags in bits 30-31 of a list entry, consumed at pair_buck_coul_long_intel.cpp:283,312 via special_lj / special_coul).
+ * nspecial[n][3] holds LAMMPS's cumulative counts (partners [0,n0) are 1-2, [n0,n1) 1-3, [n1,n2) 1-4), special[n][maxspecial]
+ * the partners as 0-based upload indices; both in upload order.  Call after b200md_atoms_upload; NULL clears.  Flagged
+ * pairs stay in the list whatever their factor (stock drops factor-0 pairs when no k-space style is defined: forces are
+ * identical, the pair set is not).  One GPU only (the arrays are indexed by upload position); maxspecial <= 32. */
+int b200md_atoms_set_special(b200md_ctx *ctx, int maxspecial, const int *nspecial, const int *special);
 
 /* ------------------------------------------------------------------------------------------------
  * neighbour list — replaces the "intel" NeighList request (pair_buck_intel.cpp:370) and

@@ -24,6 +24,7 @@ HEADER_TESTING = os.path.join(ROOT, "include", "b200md_testing.h")
 
 PREC_DOUBLE, PREC_MIXED = 0, 1
 PAIR_BUCK, PAIR_BUCK_COUL_CUT, PAIR_BUCK_COUL_LONG, PAIR_BUCK_LONG_COUL_LONG = 0, 1, 2, 3
+PAIR_LJ_LONG_COUL_LONG = 4   # pair_coeffs: A = epsilon, rho = sigma
 SBBITS = 30
 NEIGHMASK = 0x3FFFFFFF
 
@@ -203,9 +204,18 @@ def pair_coeffs(style, ntypes, A, rho, Cc, cut_lj, cut_coul=None, offset_flag=0)
     A, rho, Cc, cut_lj = full(A), full(rho), full(Cc), full(cut_lj)
     cut_coul = full(cut_coul) if cut_coul is not None else np.zeros((tp1, tp1))
     rho = np.where(rho == 0.0, 1.0, rho)
-    out = dict(a=A, c=Cc, rhoinv=1.0 / rho, buck1=A / rho, buck2=6.0 * Cc)
     cl = np.where(cut_lj > 0, cut_lj, 1.0)
-    out["offset"] = (A * np.exp(-cl / rho) - Cc / cl ** 6) if offset_flag else np.zeros((tp1, tp1))
+    if style == PAIR_LJ_LONG_COUL_LONG:
+        # PairLJLongCoulLong::init_one [UPSTREAM]: A = epsilon, rho = sigma; buck1, buck2, a, c carry lj1, lj2, lj3, lj4
+        # (pair_lj_long_coul_long_intel.cpp:831-834)
+        out = dict(buck1=48.0 * A * rho ** 12.0, buck2=24.0 * A * rho ** 6.0, a=4.0 * A * rho ** 12.0,
+                   c=4.0 * A * rho ** 6.0, rhoinv=np.zeros((tp1, tp1)))
+        ratio = rho / cl
+        out["offset"] = np.where(cut_lj > 0, 4.0 * A * (ratio ** 12.0 - ratio ** 6.0), 0.0) if offset_flag else \
+            np.zeros((tp1, tp1))
+    else:
+        out = dict(a=A, c=Cc, rhoinv=1.0 / rho, buck1=A / rho, buck2=6.0 * Cc)
+        out["offset"] = (A * np.exp(-cl / rho) - Cc / cl ** 6) if offset_flag else np.zeros((tp1, tp1))
     out["cut_ljsq"] = cut_lj * cut_lj
     out["cut_coulsq"] = cut_coul * cut_coul
     cut = cut_lj if style == PAIR_BUCK else np.maximum(cut_lj, cut_coul)
@@ -450,6 +460,16 @@ class Context:
         self.nlocal = len(x)
         self._ck(self.lib.b200md_atoms_upload(self.h, C.c_int(len(x)), C.c_int(len(mass) - 1), _d(x), _d(v), _d(q),
                                               _i(type_), _d(mass)))
+
+    def atoms_set_special(self, nspecial=None, special=None):
+        """special bonds of a molecular system for device-built lists: nspecial [n,3] cumulative counts (1-2, 1-3, 1-4),
+        special [n,maxspecial] partner upload indices; None clears"""
+        if nspecial is None:
+            self._ck(self.lib.b200md_atoms_set_special(self.h, C.c_int(0), None, None))
+            return
+        ns = i32(nspecial)
+        sp = i32(special)
+        self._ck(self.lib.b200md_atoms_set_special(self.h, C.c_int(sp.shape[1]), _i(ns), _i(sp)))
 
     def atoms_set_x(self, x):
         self._ck(self.lib.b200md_atoms_set_x(self.h, _d(f64(x))))

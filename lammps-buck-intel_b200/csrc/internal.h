@@ -130,6 +130,8 @@ struct b200md_ctx {
   int device = 0;
   int prec = B200MD_PREC_DOUBLE;
   cudaStream_t stream = nullptr;
+  DevBuf<int> sp_count, sp_list;   // special bonds, upload order: [n][3] cumulative counts, [n][sp_max] partner ids
+  int sp_max = 0;                  // 0: atomic system, lists carry no special bits
   DevBuf<int> nve_group;       // fix nve on a sub-group: 0 / 1 per atom, upload order (b200md_nve_set_group)
   DevBuf<double> nve_rmass;    // per-atom masses, upload order
   bool nve_grouped = false, nve_has_rmass = false;

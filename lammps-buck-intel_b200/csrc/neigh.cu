@@ -618,6 +618,41 @@ k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lsta
   }
 }
 
+// Special bonds (molecular systems): a warp takes an atom that has special partners, keeps their ids one per lane and
+// scans its row; an entry whose partner's id matches gets the partner's class (1-2, 1-3, 1-4) in bits 30-31 — what stock
+// Neighbor writes from atom->special / nspecial (consumed at pair_buck_coul_long_intel.cpp:283).  Ids are upload
+// indices: tag[] of an owned atom, tag[ghost_src[]] of a periodic image.
+__global__ void __launch_bounds__(128)
+k_nb_mark_special(int nlocal, const int *__restrict__ tag, const int *__restrict__ ghost_src,
+                  const int *__restrict__ numneigh, const long long *__restrict__ offsets, int *__restrict__ entries,
+                  int idxmask, const int *__restrict__ sp_count, const int *__restrict__ sp_list, int sp_max) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= nlocal) return;
+  const int ti = tag[i];
+  const int n12 = sp_count[3 * ti], n13 = sp_count[3 * ti + 1], ns = sp_count[3 * ti + 2];
+  if (ns == 0) return;
+  const int mine = lane < ns ? sp_list[(size_t)ti * sp_max + lane] : -1;
+  int *row = entries + offsets[i];
+  const int n = numneigh[i];
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    int e = 0, tj = -2;
+    if (k < n) {
+      e = row[k];
+      const int j = e & idxmask;
+      const int o = j < nlocal ? j : ghost_src[j - nlocal];
+      tj = o >= 0 ? tag[o] : -2;
+    }
+    int which = 0;
+    for (int s = 0; s < ns; s++) {
+      const int id = __shfl_sync(0xffffffffu, mine, s);
+      if (tj == id) which = s < n12 ? 1 : (s < n13 ? 2 : 3);
+    }
+    if (which) row[k] = e | (which << B2_SBBITS);
+  }
+}
+
 __global__ void k_row_offsets(int n, int pitch, long long *__restrict__ offsets) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) offsets[i] = (long long)i * pitch;
@@ -650,7 +685,7 @@ __global__ void k_export_rows(int nlocal, const int *__restrict__ tag, const int
     const int e = entries[src + k];
     const int j = e & (packed_type ? B2_IDXMASK26 : B2_NEIGHMASK);
     const int jj = j < nlocal ? tag[j] : j;  // ghosts keep their slot, owned atoms go to host index
-    out[dst + k] = jj | (packed_type ? 0 : (e & ~B2_NEIGHMASK));
+    out[dst + k] = jj | (e & ~B2_NEIGHMASK);   // special-bond bits stay, the packed type bits do not
   }
 }
 __global__ void k_export_ghosts(int nlocal, int ng, const int *__restrict__ tag, const int *__restrict__ src,
@@ -1103,6 +1138,13 @@ int b2_neigh_build(b200md_ctx *ctx) {
     }
     KERNEL_OK(ctx, "k_nb_fill");
     clk.mark("fill");
+  }
+  if (ctx->sp_max > 0 && n > 0) {
+    if (b2_comm_nranks(ctx) > 1) return b2_fail(ctx, B200MD_EINVAL, "special bonds are single-GPU only in this build");
+    k_nb_mark_special<<<cdiv((long)n * 32, 128), 128, 0, ctx->stream>>>(
+        n, ctx->tag.p, ns.ghost_src.p, ns.numneigh.p, ns.offsets.p, ns.entries.p,
+        ns.packed_type ? B2_IDXMASK26 : B2_NEIGHMASK, ctx->sp_count.p, ctx->sp_list.p, ctx->sp_max);
+    KERNEL_OK(ctx, "k_nb_mark_special");
   }
   ns.total_entries = total;
   ns.max_numneigh = maxn;

@@ -213,6 +213,33 @@ int b200md_nve_set_group(b200md_ctx *ctx, const int *ingroup, const double *rmas
   return 0;
 }
 
+int b200md_atoms_set_special(b200md_ctx *ctx, int maxspecial, const int *nspecial, const int *special) {
+  if (!ctx) return B200MD_EINVAL;
+  cudaSetDevice(ctx->device);
+  ctx->neigh.ready = false;   // the next list carries (or drops) the bits
+  if (!nspecial || !special || maxspecial <= 0) {
+    ctx->sp_max = 0;
+    return 0;
+  }
+  if (b2_comm_nranks(ctx) > 1) return b2_fail(ctx, B200MD_EINVAL, "special bonds are single-GPU only in this build");
+  if (maxspecial > 32) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: maxspecial %d > 32", maxspecial);
+  const size_t n = (size_t)ctx->nlocal;
+  for (size_t i = 0; i < n; i++) {
+    const int a = nspecial[3 * i], b = nspecial[3 * i + 1], c = nspecial[3 * i + 2];
+    if (a < 0 || b < a || c < b || c > maxspecial)
+      return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: bad cumulative counts for atom %zu", i);
+    for (int k = 0; k < c; k++)
+      if (special[i * maxspecial + k] < 0 || (size_t)special[i * maxspecial + k] >= n)
+        return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: partner %d of atom %zu is not an atom", k, i);
+  }
+  RESERVE(ctx, ctx->sp_count, 3 * n + 1);
+  RESERVE(ctx, ctx->sp_list, n * (size_t)maxspecial + 1);
+  CUDA_OK(ctx, cudaMemcpy(ctx->sp_count.p, nspecial, 3 * n * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(ctx, cudaMemcpy(ctx->sp_list.p, special, n * (size_t)maxspecial * sizeof(int), cudaMemcpyHostToDevice));
+  ctx->sp_max = maxspecial;
+  return 0;
+}
+
 int b200md_nve_initial_integrate(b200md_ctx *ctx) {
   if (!ctx) return B200MD_EINVAL;
   cudaSetDevice(ctx->device);

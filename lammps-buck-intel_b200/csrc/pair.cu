@@ -71,9 +71,11 @@ int b2_pair_compute(b200md_ctx *ctx, int eflag, int vflag, double *ev) {
   v.entries = ctx->neigh.entries.p;
   v.f = ctx->f.p;
   v.packed_type = ctx->neigh.packed_type ? 1 : 0;
-  // lists built on the device carry no special-bond bits (atomic systems)
-  if (ctx->prec == B200MD_PREC_MIXED) TRY(b2_launch_pair_float(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, 0));
-  else TRY(b2_launch_pair_double(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, 0));
+  // lists built on the device carry special-bond bits only for molecular systems (b200md_atoms_set_special)
+  const int has_special = ctx->sp_max > 0 ? 1 : 0;
+  if (ctx->prec == B200MD_PREC_MIXED)
+    TRY(b2_launch_pair_float(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, has_special));
+  else TRY(b2_launch_pair_double(ctx, v, ctx->neigh.total_entries, evflag, ctx->ev_out.p, has_special));
   if (evflag) {
     TRY(b2_comm_allreduce_sum(ctx, ctx->ev_out.p, 8));   // global tallies over the ranks (no-op on one GPU)
     TRY(finish_ev(ctx, eflag, vflag, ev));
@@ -86,7 +88,7 @@ extern "C" {
 int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p) {
   if (!ctx || !p) return b2_fail(ctx, B200MD_EINVAL, "b200md_pair_setup: NULL argument");
   cudaSetDevice(ctx->device);
-  if (p->style < B200MD_PAIR_BUCK || p->style > B200MD_PAIR_BUCK_LONG_COUL_LONG)
+  if (p->style < B200MD_PAIR_BUCK || p->style > B200MD_PAIR_LJ_LONG_COUL_LONG)
     return b2_fail(ctx, B200MD_EINVAL, "unknown pair style %d", p->style);
   if (p->ntypes < 1 || p->ntypes > B2_MAXTYPES)
     return b2_fail(ctx, B200MD_EINVAL, "ntypes %d outside 1..%d", p->ntypes, B2_MAXTYPES);
@@ -140,14 +142,15 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p) {
     // real-space Ewald term, exp(-g_ewald_6^2 r^2) of the buck/long dispersion term
     for (int i = 1; i < tp1; i++)
       for (int j = 1; j < tp1; j++) {
+        if (p->style == B200MD_PAIR_LJ_LONG_COUL_LONG) continue;   // no exp(-r/rho) in the Lennard-Jones style
         if (!(p->rhoinv[i * tp1 + j] > 0.0))
           return b2_fail(ctx, B200MD_EINVAL, "buck rho for types %d-%d must be positive", i, j);
         if (std::sqrt(p->cut_ljsq[i * tp1 + j]) * p->rhoinv[i * tp1 + j] > 700.0)
           return b2_fail(ctx, B200MD_EINVAL, "buck rho for types %d-%d is too small for its cutoff: exp(-r/rho) underflows", i, j);
       }
-    const bool ewald1 = p->style == B200MD_PAIR_BUCK_COUL_LONG ||
-                        (p->style == B200MD_PAIR_BUCK_LONG_COUL_LONG && ((p->ewald_order >> 1) & 1));
-    const bool ewald6 = p->style == B200MD_PAIR_BUCK_LONG_COUL_LONG && ((p->ewald_order >> 6) & 1);
+    const bool lcl = p->style == B200MD_PAIR_BUCK_LONG_COUL_LONG || p->style == B200MD_PAIR_LJ_LONG_COUL_LONG;
+    const bool ewald1 = p->style == B200MD_PAIR_BUCK_COUL_LONG || (lcl && ((p->ewald_order >> 1) & 1));
+    const bool ewald6 = lcl && ((p->ewald_order >> 6) & 1);
     if (ewald1 && p->g_ewald * cutmax * p->g_ewald * cutmax > 700.0)
       return b2_fail(ctx, B200MD_EINVAL, "g_ewald %g is too large for the cutoff %g: exp(-(g r)^2) underflows", p->g_ewald, cutmax);
     if (ewald6 && p->g_ewald_6 * cutmax * p->g_ewald_6 * cutmax > 700.0)

@@ -246,7 +246,8 @@ __device__ __forceinline__ void pair_eval(const PairConsts<flt_t> &pc, const flt
       if (EVFLAG) ecoul = forcecoul;
     }
   }
-  if (STYLE == B200MD_PAIR_BUCK_COUL_LONG || (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order1)) {
+  constexpr bool LCL = STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG || STYLE == B200MD_PAIR_LJ_LONG_COUL_LONG;
+  if (STYLE == B200MD_PAIR_BUCK_COUL_LONG || (LCL && pc.order1)) {
     if (!GENERAL || !pc.coultable || rsq <= pc.tabinnersq) {
       const flt_t EWALD_F = sizeof(flt_t) == 8 ? pc.mc[MC_EWF] : (flt_t)1.12837917;
       flt_t erfc, expm2, grij, prefactor;
@@ -278,7 +279,47 @@ __device__ __forceinline__ void pair_eval(const PairConsts<flt_t> &pc, const flt
   }
 
   const bool in_lj = pc.same_cut ? true : rsq < cij[C_CUT_LJSQ];
-  if (!GENERAL || in_lj) {
+  if (STYLE == B200MD_PAIR_LJ_LONG_COUL_LONG) {
+    // pair_lj_long_coul_long_intel.cpp:620-688; C_BUCK1, C_BUCK2, C_A, C_C hold lj1, lj2, lj3, lj4
+    if (!GENERAL || in_lj) {
+      const flt_t r6inv = r2inv * r2inv * r2inv;
+      const flt_t lj1 = cij[C_BUCK1], lj2 = cij[C_BUCK2], lj3 = cij[C_A], lj4 = cij[C_C];
+      if (pc.order6) {
+        if (!GENERAL || !pc.disptable || rsq <= pc.tabinnerdispsq) {
+          const flt_t grij2 = pc.g2 * rsq;
+          const flt_t a2 = m_rcp(grij2, pc.mc);
+          const flt_t x2 = a2 * m_exp(-grij2, s_tab, pc.mc) * lj4;
+          forcebuck = r6inv * r6inv * lj1 -
+                      pc.g8 * x2 * rsq * ((((flt_t)6.0 * a2 + (flt_t)6.0) * a2 + (flt_t)3.0) * a2 + (flt_t)1.0);
+          if (EVFLAG) evdwl = r6inv * r6inv * lj3 - pc.g6 * x2 * ((a2 + (flt_t)1.0) * a2 + (flt_t)0.5);
+        } else {
+          const float rsq_lookup = (float)rsq;
+          const int itable = (__float_as_int(rsq_lookup) & pc.ndispmask) >> pc.ndispshiftbits;
+          const flt_t *tb = dtab + 6 * itable;  // {r,dr,f,df,e,de}
+          const flt_t fd = (rsq - tb[0]) * tb[1];
+          forcebuck = r6inv * r6inv * lj1 - (tb[2] + fd * tb[3]) * lj4;
+          if (EVFLAG) evdwl = r6inv * r6inv * lj3 - (tb[4] + fd * tb[5]) * lj4;
+        }
+        if (GENERAL && sbindex) {
+          const flt_t t = r6inv * ((flt_t)1.0 - pc.special_lj[sbindex]);
+          forcebuck += t * (lj2 - r6inv * lj1);
+          if (EVFLAG) evdwl += t * (lj4 - r6inv * lj3);
+        }
+      } else {
+        forcebuck = r6inv * (r6inv * lj1 - lj2);
+        if (EVFLAG) evdwl = r6inv * (r6inv * lj3 - lj4) - cij[C_OFFSET];
+        if (GENERAL && sbindex) {
+          const flt_t factor_lj = pc.special_lj[sbindex];
+          forcebuck *= factor_lj;
+          if (EVFLAG) evdwl *= factor_lj;
+        }
+      }
+      if (!GENERAL) {
+        forcebuck = in_lj ? forcebuck : (flt_t)0;
+        if (EVFLAG) evdwl = in_lj ? evdwl : (flt_t)0;
+      }
+    }
+  } else if (!GENERAL || in_lj) {
     const flt_t r6inv = r2inv * r2inv * r2inv;
     const flt_t rexp = m_exp(-r * cij[C_RHOINV], s_tab, pc.mc);
     if (STYLE == B200MD_PAIR_BUCK_LONG_COUL_LONG && pc.order6) {
@@ -368,13 +409,13 @@ k_pair(const int nlocal, const typename V4<flt_t>::type *__restrict__ x, const i
     for (int jj = sub; jj < jnum; jj += TPA) {
       const int e = e_cur;
       const vec4 xj = xj_nxt;
-      const int tj = PACKT ? (e >> B2_TYPESHIFT) : tj_nxt;
+      const int tj = PACKT ? ((e >> B2_TYPESHIFT) & 15) : tj_nxt;
       e_cur = e_nxt;   // past the row's end this stays a valid (already used) entry: the loads below are harmless
       if (jj + 2 * TPA < jnum) e_nxt = jlist[jj + 2 * TPA];
       j_nxt = nbr_index<PACKT>(e_cur);
       xj_nxt = ld_atom(x + j_nxt);
       if (!PACKT) tj_nxt = type[j_nxt];
-      const int sbindex = (GENERAL && !PACKT) ? (e >> B2_SBBITS) & 3 : 0;
+      const int sbindex = GENERAL ? (e >> B2_SBBITS) & 3 : 0;
       const flt_t *cij = ci + tj * C_N;
       const flt_t delx = xi.x - xj.x;
       const flt_t dely = xi.y - xj.y;
@@ -534,8 +575,8 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
     coeff = (const flt_t *)ps.coeff_f.p; ctab = (const flt_t *)ps.ctab_f.p; dtab = (const flt_t *)ps.dtab_f.p;
   }
   // 0: branch-free analytic, packed type; 1: tables, packed type; 2: everything, type gathered (host lists)
-  const int variant = !v.packed_type ? 2 : ((pc.coultable || pc.disptable) ? 1 : 0);
-  if (has_special && v.packed_type) return b2_fail(ctx, B200MD_EINVAL, "packed-type list with special bits");
+  // (special-bond bits ride in bits 30-31 beside the packed type: the generic flavour reads them)
+  const int variant = !v.packed_type ? 2 : ((pc.coultable || pc.disptable || has_special) ? 1 : 0);
   const int tpa = pick_tpa(ctx, v.nlocal, total_entries);
   const int nblocks = cdiv((long)v.nlocal * tpa, pair_threads());
   if (nblocks == 0) {
@@ -554,6 +595,7 @@ int launch_pair(b200md_ctx *ctx, const PairView &v, long long total_entries, int
     STYLE_CASE(B200MD_PAIR_BUCK_COUL_CUT)
     STYLE_CASE(B200MD_PAIR_BUCK_COUL_LONG)
     STYLE_CASE(B200MD_PAIR_BUCK_LONG_COUL_LONG)
+    STYLE_CASE(B200MD_PAIR_LJ_LONG_COUL_LONG)
     default: return b2_fail(ctx, B200MD_EINVAL, "unknown pair style %d", ps.p.style);
   }
 #undef STYLE_CASE

@@ -118,7 +118,17 @@ def spce_system(rep, seed=432567, temperature=300.0):
     x, t, q, lo, hi = replicate(x, d["type"], d["q"], lo, hi, *r)
     rng = np.random.default_rng(seed)
     v = velocities(rng, t, d["mass"], temperature, UNITS["real"])
-    return dict(x=x, v=v, type=t, q=q, boxlo=lo, boxhi=hi, mass=d["mass"].copy(), ntypes=2, units="real")
+    nrep = r[0] * r[1] * r[2]
+    mol = (np.tile(d["mol"], nrep) + np.repeat(np.arange(nrep), len(d["mol"])) * int(d["mol"].max())).astype(np.int32)
+    return dict(x=x, v=v, type=t, q=q, boxlo=lo, boxhi=hi, mass=d["mass"].copy(), ntypes=2, units="real", mol=mol)
+
+
+def coeffs_spce(cut_lj=6.8, cut_coul=8.8):
+    """examples/in.spce:7-11: lj/cut/coul/long 6.8 8.8, pair_coeff 1 1 0.15535 3.166, * 2 0 0 (epsilon as A, sigma as rho)"""
+    eps = np.zeros((3, 3)); sig = np.ones((3, 3))
+    eps[1, 1], sig[1, 1] = 0.15535, 3.166
+    sig[1, 2] = sig[2, 1] = sig[2, 2] = 1.0
+    return dict(A=eps, rho=sig, C=np.zeros((3, 3)), cut_lj=np.full((3, 3), float(cut_lj)), cut_coul=np.full((3, 3), float(cut_coul)))
 
 
 def water_like_system(nmol_side, seed=4711, box=35.5):

@@ -27,7 +27,10 @@
 extern "C" {
 #endif
 
-enum { ORC_BUCK = 0, ORC_BUCK_COUL_CUT = 1, ORC_BUCK_COUL_LONG = 2, ORC_BUCK_LONG_COUL_LONG = 3 };
+enum { ORC_BUCK = 0, ORC_BUCK_COUL_CUT = 1, ORC_BUCK_COUL_LONG = 2, ORC_BUCK_LONG_COUL_LONG = 3,
+       /* pair_lj_long_coul_long_intel.cpp (`lj/long/coul/long cut long` is the lj/cut/coul/long of in.spce):
+        * A = epsilon, rho = sigma on input; buck1, buck2, a, c carry lj1, lj2, lj3, lj4 */
+       ORC_LJ_LONG_COUL_LONG = 4 };
 enum { ORC_PREC_DOUBLE = 0, ORC_PREC_MIXED = 1 };
 
 /* packed per-type-pair constants, doubles; restates ForceConst<flt_t> of all four styles

@@ -107,7 +107,6 @@ void eval(const int vflag, const int eatom, const int nlocal, const int nall, co
   const flt_t qqrd2e = fc.qqrd2e;
   const flt_t g_ewald = fc.g_ewald;
   const flt_t tabinnersq = fc.tabinnersq;
-  const flt_t tabinnerdispsq = fc.tabinnerdispsq;
   const flt_t g2 = (flt_t)(pp.g_ewald_6 * pp.g_ewald_6), g6 = g2 * g2 * g2, g8 = g6 * g2;
 
   const int f_stride = nall;
@@ -167,16 +166,17 @@ void eval(const int vflag, const int eatom, const int nlocal, const int nall, co
             }
           }
         }
-        if (STYLE == ORC_BUCK_COUL_LONG || (STYLE == ORC_BUCK_LONG_COUL_LONG && ORDER1)) {
+        constexpr bool LCL = STYLE == ORC_BUCK_LONG_COUL_LONG || STYLE == ORC_LJ_LONG_COUL_LONG;
+        if (STYLE == ORC_BUCK_COUL_LONG || (LCL && ORDER1)) {
           // coul/long: whole Coulomb block gated by cutsq (:291); long/coul/long: same (:350)
-          if (!ncoultablebits || (STYLE == ORC_BUCK_LONG_COUL_LONG ? rsq <= pp.tabinnersq : rsq <= tabinnersq)) {
+          if (!ncoultablebits || (LCL ? rsq <= pp.tabinnersq : rsq <= tabinnersq)) {
             const flt_t A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741;
             const flt_t A4 = -1.453152027, A5 = 1.061405429;
             const flt_t EWALD_F = 1.12837917;
             const flt_t INV_EWALD_P = 1.0 / 0.3275911;
             // long/coul/long has no flt_t local for g_ewald: the product uses the base class's double member and only
             // the assignment rounds (pair_buck_long_coul_long_intel.cpp:361); coul/long multiplies in flt_t (:167,304)
-            const flt_t grij = STYLE == ORC_BUCK_LONG_COUL_LONG ? (flt_t)(pp.g_ewald * r) : g_ewald * r;
+            const flt_t grij = LCL ? (flt_t)(pp.g_ewald * r) : g_ewald * r;
             const flt_t expm2 = std::exp(-grij * grij);
             const flt_t t = INV_EWALD_P / (INV_EWALD_P + grij);
             const flt_t erfc = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * expm2;
@@ -205,7 +205,43 @@ void eval(const int vflag, const int eatom, const int nlocal, const int nall, co
           }
         }
 
-        if (rsq < fc.cut_ljsq[ij]) {
+        if (STYLE == ORC_LJ_LONG_COUL_LONG) {
+          // pair_lj_long_coul_long_intel.cpp:620-688: buck1, buck2, a, c hold lj1, lj2, lj3, lj4
+          if (rsq < fc.cut_ljsq[ij]) {
+            const flt_t lj1 = fc.buck1[ij], lj2 = fc.buck2[ij], lj3 = fc.a[ij], lj4 = fc.c[ij];
+            if (ORDER6) {
+              const flt_t r6inv = r2inv * r2inv * r2inv;
+              if (!ndisptablebits || rsq <= pp.tabinnerdispsq) {  // :622-638 (double literals: see the Buckingham twin)
+                const flt_t grij2 = g2 * rsq;
+                const flt_t a2 = (flt_t)1.0 / grij2;
+                const flt_t x2 = a2 * std::exp(-grij2) * lj4;
+                forcebuck = r6inv * r6inv * lj1 - g8 * x2 * rsq * (((6.0 * a2 + 6.0) * a2 + 3.0) * a2 + 1.0);
+                if (EFLAG) evdwl = r6inv * r6inv * lj3 - g6 * x2 * ((a2 + 1.0) * a2 + 0.5);
+              } else {  // :640-652
+                const float rsq_lookup = (float)rsq;
+                const int itable = (float_bits(rsq_lookup) & ndispmask) >> ndispshiftbits;
+                const flt_t fd = (rsq - fc.rdisp[itable]) * fc.drdisp[itable];
+                forcebuck = r6inv * r6inv * lj1 - (fc.fdisp[itable] + fd * fc.dfdisp[itable]) * lj4;
+                if (EFLAG) evdwl = r6inv * r6inv * lj3 - (fc.edisp[itable] + fd * fc.dedisp[itable]) * lj4;
+              }
+              if (sbindex) {  // :632-638, :653-661
+                const flt_t f = fc.special_lj[sbindex];
+                const flt_t t = r6inv * (1.0 - f);
+                forcebuck += t * (lj2 - r6inv * lj1);
+                if (EFLAG) evdwl += t * (lj4 - r6inv * lj3);
+              }
+            } else {  // :664-675
+              const flt_t r6inv = r2inv * r2inv * r2inv;
+              forcebuck = r6inv * (r6inv * lj1 - lj2);
+              if (EFLAG) evdwl = r6inv * (r6inv * lj3 - lj4) - fc.offset[ij];
+              if (sbindex) {
+                const flt_t factor_lj = fc.special_lj[sbindex];
+                forcebuck *= factor_lj;
+                if (EFLAG) evdwl *= factor_lj;
+              }
+            }
+          }
+        } else if (rsq < fc.cut_ljsq[ij]) {
           const flt_t r6inv = r2inv * r2inv * r2inv;
           const flt_t rexp = std::exp(-r * fc.rhoinv[ij]);
           if (STYLE == ORC_BUCK_LONG_COUL_LONG && ORDER6) {
@@ -365,6 +401,25 @@ void orc_pair_init(int style, int ntypes, const double *A, const double *rho, co
       const int ij = i * tp1 + j;
       const double cl = cut_lj[ij];
       const double cc = cut_coul ? cut_coul[ij] : 0.0;
+      if (style == ORC_LJ_LONG_COUL_LONG) {
+        // PairLJLongCoulLong::init_one [UPSTREAM]: A = epsilon, rho = sigma
+        const double eps = A[ij], sig = rho[ij];
+        p->buck1[ij] = 48.0 * eps * std::pow(sig, 12.0);   // lj1
+        p->buck2[ij] = 24.0 * eps * std::pow(sig, 6.0);    // lj2
+        p->a[ij] = 4.0 * eps * std::pow(sig, 12.0);        // lj3
+        p->c[ij] = 4.0 * eps * std::pow(sig, 6.0);         // lj4
+        p->rhoinv[ij] = 0.0;
+        if (offset_flag && cl > 0.0) {
+          const double ratio = sig / cl;
+          p->offset[ij] = 4.0 * eps * (std::pow(ratio, 12.0) - std::pow(ratio, 6.0));
+        } else
+          p->offset[ij] = 0.0;
+        p->cut_ljsq[ij] = cl * cl;
+        p->cut_coulsq[ij] = cc * cc;
+        const double cut = std::max(cl, cc);
+        p->cutsq[ij] = cut * cut;
+        continue;
+      }
       p->a[ij] = A[ij];
       p->c[ij] = C[ij];
       p->rhoinv[ij] = 1.0 / rho[ij];
@@ -494,6 +549,7 @@ void orc_pair_eval(int style, int prec, int eflag, int vflag, int eatom, int new
     STYLE_CASE(ORC_BUCK_COUL_CUT)
     STYLE_CASE(ORC_BUCK_COUL_LONG)
     STYLE_CASE(ORC_BUCK_LONG_COUL_LONG)
+    STYLE_CASE(ORC_LJ_LONG_COUL_LONG)
   }
 #undef STYLE_CASE
 }

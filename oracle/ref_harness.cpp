@@ -1,8 +1,8 @@
 // ref_harness.cpp — drives the reference's OWN translation units (compiled unchanged from /root/reference into
 // oracle/_ref/libref.so, recipe: oracle/Makefile.ref) on caller-supplied inputs.  TEST INFRASTRUCTURE ONLY.
 //
-// What runs from the reference: PairBuck{,CoulCut,CoulLong,LongCoulLong}Intel::init_style / pack_force_const / compute /
-// eval<> (pair_buck_intel.cpp:48-443 and the three siblings), IntelBuffers::thr_pack (intel_buffers.h:185-203),
+// What runs from the reference: PairBuck{,CoulCut,CoulLong,LongCoulLong}Intel and PairLJLongCoulLongIntel::init_style /
+// pack_force_const / compute / eval<> (pair_buck_intel.cpp:48-443 and the four siblings), IntelBuffers::thr_pack (intel_buffers.h:185-203),
 // PPPMIntel::compute / particle_map / make_rho / brick2fft / poisson_ik / poisson_ad / fieldforce_ik / fieldforce_ad
 // (pppm_intel.cpp:104-1054), FixNVEIntel::setup / reset_dt / initial_integrate / final_integrate (fix_nve_intel.cpp).
 // What is NOT in the reference and is supplied by ref_shim/ (stand-ins stating SURVEY.md App. A): the LAMMPS core
@@ -21,6 +21,7 @@
 #include "pair_buck_coul_long_intel.h"
 #include "pair_buck_intel.h"
 #include "pair_buck_long_coul_long_intel.h"
+#include "pair_lj_long_coul_long_intel.h"
 #include "pppm_intel.h"
 
 #include "oracle.h"
@@ -225,6 +226,15 @@ int ref_pair_eval(int style, int prec, int eflag, int vflag, int eatom, int newt
       fill2(pb->buck_a_read, A, tp1); fill2(pb->buck_rho_read, rho, tp1); fill2(pb->buck_c_read, C, tp1);
       fill2(pb->cut_buck_read, cut_lj, tp1);
       pb->cut_buck_global = cut_lj[tp1 + 1];
+      pb->cut_coul = cut_coul ? cut_coul[tp1 + 1] : 0.0;
+      pb->ewald_order = (p->order1 ? 1 << 1 : 0) | (p->order6 ? 1 << 6 : 0);
+      set_tables(pb);
+      pair = pb;
+    } else if (style == ORC_LJ_LONG_COUL_LONG) {   // A = epsilon, rho = sigma
+      auto *pb = new PairLJLongCoulLongIntel(&w.lmp);
+      pb->allocate();
+      fill2(pb->epsilon_read, A, tp1); fill2(pb->sigma_read, rho, tp1); fill2(pb->cut_lj_read, cut_lj, tp1);
+      pb->cut_lj_global = cut_lj[tp1 + 1];
       pb->cut_coul = cut_coul ? cut_coul[tp1 + 1] : 0.0;
       pb->ewald_order = (p->order1 ? 1 << 1 : 0) | (p->order6 ? 1 << 6 : 0);
       set_tables(pb);

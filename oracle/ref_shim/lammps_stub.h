@@ -523,6 +523,53 @@ class PairBuckLongCoulLong : public Pair {
   double **rhoinv = nullptr, **buck1 = nullptr, **buck2 = nullptr, **offset = nullptr;
 };
 
+/* pair_style lj/long/coul/long (A.2 names; the reference reads ewald_order, cut_ljsq, lj1..lj4, offset, g_ewald,
+ * g_ewald_6 and the tables: pair_lj_long_coul_long_intel.cpp:111-112,479,571,817-835) */
+class PairLJLongCoulLong : public Pair {
+ public:
+  explicit PairLJLongCoulLong(LAMMPS *lmp) : Pair(lmp) {}
+  void allocate() {
+    const int n = atom->ntypes + 1;
+    base_allocate(n);
+    alloc2(cut_lj, n); alloc2(cut_ljsq, n); alloc2(cut_lj_read, n);
+    alloc2(epsilon, n); alloc2(sigma, n); alloc2(epsilon_read, n); alloc2(sigma_read, n);
+    alloc2(lj1, n); alloc2(lj2, n); alloc2(lj3, n); alloc2(lj4, n); alloc2(offset, n);
+  }
+  virtual void compute(int, int) {}
+  virtual void init_style();
+  virtual double init_one(int i, int j) {
+    if (setflag[i][j] == 0) error->all(FLERR, "All pair coeffs are not set");
+    epsilon[i][j] = epsilon_read[i][j];
+    sigma[i][j] = sigma_read[i][j];
+    if (ewald_order & (1 << 6)) cut_lj[i][j] = cut_lj_global;
+    else cut_lj[i][j] = cut_lj_read[i][j];
+    const double cut = cut_lj[i][j] > cut_coul ? cut_lj[i][j] : cut_coul;
+    cutsq[i][j] = cut * cut;
+    cut_ljsq[i][j] = cut_lj[i][j] * cut_lj[i][j];
+    lj1[i][j] = 48.0 * epsilon[i][j] * pow(sigma[i][j], 12.0);
+    lj2[i][j] = 24.0 * epsilon[i][j] * pow(sigma[i][j], 6.0);
+    lj3[i][j] = 4.0 * epsilon[i][j] * pow(sigma[i][j], 12.0);
+    lj4[i][j] = 4.0 * epsilon[i][j] * pow(sigma[i][j], 6.0);
+    if (offset_flag && cut_lj[i][j] > 0.0) {
+      const double ratio = sigma[i][j] / cut_lj[i][j];
+      offset[i][j] = 4.0 * epsilon[i][j] * (pow(ratio, 12.0) - pow(ratio, 6.0));
+    } else offset[i][j] = 0.0;
+    cutsq[j][i] = cutsq[i][j];
+    cut_ljsq[j][i] = cut_ljsq[i][j];
+    lj1[j][i] = lj1[i][j];
+    lj2[j][i] = lj2[i][j];
+    lj3[j][i] = lj3[i][j];
+    lj4[j][i] = lj4[i][j];
+    offset[j][i] = offset[i][j];
+    return cut;
+  }
+  int ewald_order = 0, ewald_off = 0;
+  double cut_lj_global = 0, cut_coul = 0, cut_coulsq = 0, g_ewald = 0, g_ewald_6 = 0;
+  double **cut_lj = nullptr, **cut_ljsq = nullptr, **cut_lj_read = nullptr;
+  double **epsilon = nullptr, **sigma = nullptr, **epsilon_read = nullptr, **sigma_read = nullptr;
+  double **lj1 = nullptr, **lj2 = nullptr, **lj3 = nullptr, **lj4 = nullptr, **offset = nullptr;
+};
+
 /* ---- KSpace / PPPM base (A.5) ------------------------------------------------------------------------------------ */
 class KSpace : public Pointers {
  public:
@@ -559,6 +606,14 @@ class KSpace : public Pointers {
 inline void PairBuckCoulLong::init_style() {
   cut_coulsq = cut_coul * cut_coul;
   g_ewald = force->kspace->g_ewald;
+  neighbor->request(this);
+}
+inline void PairLJLongCoulLong::init_style() {
+  cut_coulsq = cut_coul * cut_coul;
+  if (force->kspace) {
+    g_ewald = force->kspace->g_ewald;
+    g_ewald_6 = force->kspace->g_ewald_6;
+  }
   neighbor->request(this);
 }
 inline void PairBuckLongCoulLong::init_style() {

@@ -17,6 +17,7 @@ LIB = os.path.join(ODIR, "_build", "liboracle.so")
 STAMP = os.path.join(ODIR, "_build", "host.txt")
 
 BUCK, BUCK_COUL_CUT, BUCK_COUL_LONG, BUCK_LONG_COUL_LONG = 0, 1, 2, 3
+LJ_LONG_COUL_LONG = 4   # A = epsilon, rho = sigma
 DOUBLE, MIXED = 0, 1
 SBBITS = 30
 NEIGHMASK = 0x3FFFFFFF

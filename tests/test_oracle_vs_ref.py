@@ -169,3 +169,39 @@ def test_nve_bitwise(W, orc):
     xo, vo = orc.nve_initial_group(x, v, f, dg, dt)
     assert np.array_equal(xo, xr) and np.array_equal(vo, vr)
     assert np.array_equal(xr[ingroup == 0], x[ingroup == 0])
+
+
+@pytest.mark.parametrize("prec", [0, 1], ids=["double", "mixed"])
+@pytest.mark.parametrize("variant", ["cut_long", "cut_long_table", "long_long", "long_long_table"])
+def test_lj_long_coul_long_bitwise(pkg, W, orc, variant, prec):
+    """pair_lj_long_coul_long_intel.cpp on the real data.spce water box: `lj/long/coul/long cut long 6.8 8.8`
+    (= the lj/cut/coul/long of examples/in.spce:7) and `long long`, analytic and tabulated, with the special-bond bits of
+    the water molecules (special_bonds lj/coul 0.0 0.0 0.5) in the list — forces, per-atom energies, energies, virial"""
+    s = W.spce_system(1)
+    u = W.UNITS["real"]
+    co = W.coeffs_spce()
+    o6 = 1 if variant.startswith("long_long") else 0
+    ge, g6 = 0.32, 0.30 if o6 else 0.0
+    P = orc.Params(orc.LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"],
+                   qqrd2e=u["qqrd2e"], g_ewald=ge, g_ewald_6=g6, order1=1, order6=o6, special_lj=(1, 0.0, 0.0, 0.5),
+                   special_coul=(1, 0.0, 0.0, 0.5))
+    if variant.endswith("table"):
+        ct = pkg.init_coul_tables(8.8, ge, u["qqrd2e"])
+        P.set_coul_tables(ct[0], 12, ct[1], ct[2], ct[3])
+        # the reference copies the dispersion tables whenever the Coulomb ones are on (:850-866)
+        dt = pkg.init_disp_tables(6.8, g6 if o6 else 0.3)
+        P.set_disp_tables(dt[0], 12 if o6 else 0, dt[1], dt[2], dt[3])
+    n = len(s["x"])
+    skin = 2.0
+    cutneighmax = P.cutmax() + skin
+    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cutneighmax)
+    nn, off, ent = orc.neigh_half_bin(n, xa, ta, 2, P.cutneighsq(skin), s["boxlo"], s["boxhi"], cutneighmax, prec)
+    ent = util.water_special_bits(n, nn, ent, src, s["mol"], s["type"])
+    assert ((ent.view(np.uint32) >> 30) != 0).sum() == 3 * (n // 3)      # two O-H and one H-H pair per molecule
+    for eflag, vflag, eatom in ((0, 0, 0), (1, 1, 1), (1, 2, 0)):
+        fo, evo = orc.pair_eval(P, prec, eflag, vflag, n, xa, ta, qa, nn, off, ent, newton=1, eatom=eatom, nthreads=1)
+        fr, evr = refc.pair_eval(P, prec, eflag, vflag, n, xa, ta, qa, nn, off, ent, newton=1, eatom=eatom, nthreads=1,
+                                 skin=skin)
+        assert np.array_equal(fo, fr), (variant, prec, eflag, vflag, np.abs(fo - fr).max())
+        assert np.array_equal(evo, evr), (variant, prec, evo, evr)
+    assert np.abs(fo[:n, :3]).max() > 1.0
