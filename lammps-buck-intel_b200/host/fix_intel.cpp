@@ -32,6 +32,10 @@ void FixIntel::upload_atoms() {
   check(b200md_set_box(_ctx, domain->boxlo, domain->boxhi, per));
   check(b200md_atoms_upload(_ctx, atom->nlocal, atom->ntypes, atom->x.data(), atom->v.empty() ? nullptr : atom->v.data(),
                             atom->q_flag ? atom->q.data() : nullptr, atom->type.data(), atom->mass.data()));
+  // molecular systems: the special-bond partners that become bits 30-31 of the device-built list entries
+  if (atom->maxspecial > 0)
+    check(b200md_atoms_set_special(_ctx, atom->maxspecial, atom->nspecial.data(), atom->special.data()));
+  else check(b200md_atoms_set_special(_ctx, 0, nullptr, nullptr));
   _uploaded = true;
   list_built = false;
 }

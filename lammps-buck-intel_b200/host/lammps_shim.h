@@ -59,6 +59,11 @@ class Atom {
   std::vector<double> rmass; // per-atom masses when rmass_flag (fix_nve_intel.cpp:148-156)
   int rmass_flag = 0;
   std::vector<int> mass_setflag;
+  // bond topology of a molecular data file (atom_style full; 0-based atom pairs): only the special-bond lists derived
+  // from it reach the hot path (bits 30-31 of the neighbour-list entries)
+  std::vector<int> bonds;            // [nbonds][2]
+  std::vector<int> nspecial, special; // [nlocal][3] cumulative 1-2 / 1-3 / 1-4 counts, [nlocal][maxspecial]
+  int maxspecial = 0;
 };
 
 class Pair;

@@ -22,6 +22,7 @@
 
 #include "fix_nve_intel.h"
 #include "pair_buck_coul_intel.h"
+#include "pair_lj_long_coul_long_intel.h"
 #include "pppm_disp_intel.h"
 #include "pppm_intel.h"
 
@@ -211,6 +212,9 @@ struct Script {
         if (t2 < 1 || t2 > a->ntypes) fail("Invalid type for mass set");
         a->mass[t2] = std::atof(w[1].c_str());
         a->mass_setflag[t2] = 1;
+      } else if (section == "Bonds" && w.size() >= 4) {   // id type atom1 atom2 (1-based ids)
+        a->bonds.push_back(std::atoi(w[2].c_str()) - 1);
+        a->bonds.push_back(std::atoi(w[3].c_str()) - 1);
       } else if (section == "Atoms") {
         // atom_style charge: id type q x y z ; atomic: id type x y z ; full: id mol type q x y z [ix iy iz]
         const size_t mol = a->molecule_flag ? 1 : 0;
@@ -266,10 +270,55 @@ struct Script {
     double lo[3] = {d->boxlo[0], d->boxlo[1], d->boxlo[2]};
     d->set_box(lo, hi);
     a->x.swap(x); a->q.swap(q); a->type.swap(type);
+    if (!a->bonds.empty()) {   // every image carries the molecule's bonds (the data file keeps molecules whole)
+      std::vector<int> b;
+      for (int r = 0; r < nx * ny * nz; r++)
+        for (int v : a->bonds) b.push_back(v + r * n);
+      a->bonds.swap(b);
+    }
     a->nlocal = (int)a->type.size();
     a->natoms = a->nlocal;
     a->v.assign((size_t)3 * a->nlocal, 0.0);
     a->f.assign((size_t)3 * a->nlocal, 0.0);
+  }
+
+  // Special::build [UPSTREAM]: 1-2 partners are the bonded atoms, 1-3 their partners, 1-4 one hop further; an atom is
+  // listed once, in its nearest class, never itself.  Stored as LAMMPS does: cumulative counts + one id list per atom.
+  void build_special() {
+    Atom *a = lmp.atom;
+    a->maxspecial = 0;
+    a->nspecial.clear();
+    a->special.clear();
+    if (a->bonds.empty()) return;
+    const int n = a->nlocal;
+    std::vector<std::vector<int>> one(n), all(n);
+    for (size_t b = 0; b + 1 < a->bonds.size(); b += 2) {
+      const int i = a->bonds[b], j = a->bonds[b + 1];
+      if (i < 0 || j < 0 || i >= n || j >= n) fail("Bond atoms missing");
+      one[i].push_back(j);
+      one[j].push_back(i);
+    }
+    a->nspecial.assign((size_t)3 * n, 0);
+    for (int i = 0; i < n; i++) {
+      std::vector<int> lvl = one[i], seen = one[i];
+      seen.push_back(i);
+      all[i] = one[i];
+      a->nspecial[3 * i] = (int)all[i].size();
+      for (int hop = 1; hop < 3; hop++) {
+        std::vector<int> next;
+        for (int p : lvl)
+          for (int q : one[p])
+            if (std::find(seen.begin(), seen.end(), q) == seen.end()) { seen.push_back(q); next.push_back(q); }
+        all[i].insert(all[i].end(), next.begin(), next.end());
+        a->nspecial[3 * i + hop] = (int)all[i].size();
+        lvl.swap(next);
+      }
+      a->maxspecial = std::max(a->maxspecial, (int)all[i].size());
+    }
+    if (a->maxspecial > 32) fail("More than 32 special neighbors per atom");
+    a->special.assign((size_t)n * std::max(a->maxspecial, 1), 0);
+    for (int i = 0; i < n; i++)
+      for (size_t s2 = 0; s2 < all[i].size(); s2++) a->special[(size_t)i * a->maxspecial + s2] = all[i][s2];
   }
 
   double kinetic_energy() const {   // sum 1/2 m v^2 in energy units
@@ -330,9 +379,14 @@ struct Script {
     else if (s == "buck/coul/cut") pair.reset(make_pair<PairBuckCoulCut, PairBuckCoulCutIntel>());
     else if (s == "buck/coul/long") pair.reset(make_pair<PairBuckCoulLong, PairBuckCoulLongIntel>());
     else if (s == "buck/long/coul/long") pair.reset(make_pair<PairBuckLongCoulLong, PairBuckLongCoulLongIntel>());
+    else if (s == "lj/long/coul/long" || s == "lj/cut/coul/long")
+      pair.reset(make_pair<PairLJLongCoulLong, PairLJLongCoulLongIntel>());
     else fail("Unknown pair style " + s);
     lmp.force->pair = pair.get();
     std::vector<char *> args;
+    // `lj/cut/coul/long cut_lj [cut_coul]` (examples/in.spce:7) is `lj/long/coul/long cut long cut_lj [cut_coul]`
+    static char a_cut[] = "cut", a_long[] = "long";
+    if (s == "lj/cut/coul/long") { args.push_back(a_cut); args.push_back(a_long); }
     for (size_t i = 2; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
     pair->settings((int)args.size(), args.data());
   }
@@ -421,6 +475,7 @@ struct Script {
       return;
     }
     FixIntel *fx = lmp.fix_intel;
+    build_special();
     fx->upload_atoms();
     fx->setup_neighbor();
     // LAMMPS::init order: force->init() runs kspace->init() before pair->init() (pair reads g_ewald)
@@ -544,6 +599,23 @@ struct Script {
       for (size_t i = 5; i + 1 < w.size(); i += 2)
         if (w[i] == "loop") loop = w[i + 1];
       velocity_create(std::atof(w[3].c_str()), std::atoi(w[4].c_str()), loop);
+    } else if (c == "special_bonds") {
+      // `special_bonds lj/coul a b c` | `lj a b c` | `coul a b c` (examples/in.spce:16)
+      for (size_t i = 1; i < w.size();) {
+        if ((w[i] == "lj/coul" || w[i] == "lj" || w[i] == "coul") && i + 3 < w.size() + 0) {
+          for (int t = 0; t < 3; t++) {
+            const double v = std::atof(w[i + 1 + t].c_str());
+            if (w[i] != "coul") lmp.force->special_lj[1 + t] = v;
+            if (w[i] != "lj") lmp.force->special_coul[1 + t] = v;
+          }
+          i += 4;
+        } else fail("Illegal special_bonds command");
+      }
+    } else if (c == "bond_style" || c == "angle_style" || c == "dihedral_style" || c == "improper_style" ||
+               c == "bond_coeff" || c == "angle_coeff" || c == "dihedral_coeff" || c == "improper_coeff") {
+      // bonded terms are not on the pair / k-space path: the topology only feeds the special-bond lists
+      if (c == "bond_style" && w.size() > 1 && w[1] != "none")
+        std::fprintf(stderr, "WARNING: bonded interactions are not computed by this driver (pair + kspace only)\n");
     } else if (c == "pair_style") { need(2); pair_style(w); }
     else if (c == "pair_coeff") {
       if (!pair) fail("Pair_coeff command before pair_style is defined");

@@ -119,3 +119,31 @@ fix 1 all nve
 thermo {thermo}
 run {steps}
 """
+
+# examples/in.spce with the parts that are on the pair / k-space path: the real data.spce (atom_style full, Bonds read
+# for the special lists), lj/cut/coul/long 6.8 8.8, pppm 1.0e-4, special_bonds lj/coul 0.0 0.0 0.5, the script's
+# neighbour settings and 2 fs step.  SHAKE, the bonded terms and NVT of the original are outside that path: fix nve.
+IN_SPCE_NVE = """units real
+atom_style full
+read_data {data}
+replicate {r} {r} {r}
+pair_style lj/cut/coul/long 6.8 8.8
+kspace_style pppm 1.0e-4
+pair_coeff 1 1 0.15535 3.166
+pair_coeff * 2 0.0000 0.0000
+bond_style harmonic
+angle_style harmonic
+dihedral_style none
+improper_style none
+bond_coeff 1 1000.00 1.000
+angle_coeff 1 100.0 109.47
+special_bonds lj/coul 0.0 0.0 0.5
+{pair_modify}
+neighbor 2.0 bin
+neigh_modify every 1 delay 10 check yes
+fix 1 all nve
+velocity all create 300 432567 dist uniform
+timestep 2.0
+thermo {thermo}
+run {steps}
+"""

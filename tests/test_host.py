@@ -311,3 +311,78 @@ def test_read_data_atom_style_full_data_spce(pkg, W, tmp_path):
     assert np.allclose(s["box"], sysd["boxhi"] - sysd["boxlo"], rtol=1e-12)
     grid, g = pkg.pppm_init(1e-4, u["qqrd2e"], sysd["q"], 36000, 8.8, sysd["boxhi"] - sysd["boxlo"])
     assert tuple(s["grid"]) == tuple(grid) and s["g_ewald"] == pytest.approx(g, rel=1e-9)
+
+
+def _write_data_spce(W, tmp_path):
+    """data.spce for the driver, regenerated from the committed fixture (atom_style full: id mol type q x y z) with the
+    O-H bonds of every molecule; the reference file itself is not available on the GPU box"""
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_spce.npz"))
+    n = len(d["x"])
+    path = os.path.join(str(tmp_path), "data.spce")
+    with open(path, "w") as fh:
+        fh.write("LAMMPS Atom File\n\n%d atoms\n%d bonds\n\n2 atom types\n1 bond types\n\n" % (n, 2 * (n // 3)))
+        for k, c in enumerate("xyz"):
+            fh.write("%.5f %.5f %slo %shi\n" % (d["boxlo"][k], d["boxhi"][k], c, c))
+        fh.write("\nMasses\n\n1 %.4f\n2 %.5f\n\nAtoms\n\n" % (d["mass"][1], d["mass"][2]))
+        for i in range(n):
+            fh.write("%d %d %d %.4f %.5f %.5f %.5f 0 0 0\n" % (i + 1, d["mol"][i], d["type"][i], d["q"][i], *d["x"][i]))
+        fh.write("\nBonds\n\n")
+        b = 1
+        for o in range(0, n, 3):
+            for h in (1, 2):
+                fh.write("%d 1 %d %d\n" % (b, o + 1, o + 1 + h))
+                b += 1
+    return path
+
+
+def test_dry_run_in_spce_nve(pkg, W, tmp_path):
+    """the in.spce commands on the pair / k-space path are accepted: atom_style full with Bonds, lj/cut/coul/long mapped
+    onto lj/long/coul/long cut long, special_bonds, the bonded-style commands (ignored), PPPM sizing"""
+    data = _write_data_spce(W, tmp_path)
+    p = scripts.write(tmp_path, "in.spce_nve", scripts.IN_SPCE_NVE.format(data=data, r=2, pair_modify="", thermo=0, steps=0))
+    r = _run(pkg, ["-in", p, "-sf", "intel", "-dry-run"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    s = _summary(r.stdout)
+    sysd = W.spce_system(2)
+    u = W.UNITS["real"]
+    grid, g = pkg.pppm_init(1e-4, u["qqrd2e"], sysd["q"], 36000, 8.8, sysd["boxhi"] - sysd["boxlo"])
+    assert s["natoms"] == 36000 and s["pair_style"] == "lj/cut/coul/long" and s["cutforce"] == 8.8
+    assert tuple(s["grid"]) == tuple(grid) and s["g_ewald"] == pytest.approx(g, rel=1e-9)
+    assert (s["every"], s["delay"], s["check"]) == (1, 10, 1) and s["dt"] == 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("table", [0, 12])
+def test_in_spce_nve_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
+    """in.spce's non-bonded + k-space force through the driver and the host classes (PairLJLongCoulLongIntel, PPPMIntel,
+    special bonds from the Bonds section): step-0 E_pair against the oracle on the same system"""
+    import util
+    data = _write_data_spce(W, tmp_path)
+    txt = scripts.IN_SPCE_NVE.format(data=data, r=1, pair_modify="pair_modify table %d" % table, thermo=1, steps=2)
+    p = scripts.write(tmp_path, "in.spce_nve", txt)
+    r = _run(pkg, ["-in", p, "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    s = W.spce_system(1)
+    # the data file is written with 5 decimals: read the same numbers
+    s["x"] = W.wrap(np.round(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_spce.npz"))["x"], 5),
+                    s["boxlo"], s["boxhi"])
+    n = len(s["x"])
+    u = W.UNITS["real"]
+    co = W.coeffs_spce()
+    grid, ge = pkg.pppm_init(1e-4, u["qqrd2e"], s["q"], n, 8.8, s["boxhi"] - s["boxlo"])
+    P = orc.Params(orc.LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=ge, order1=1, special_lj=(1, 0.0, 0.0, 0.5), special_coul=(1, 0.0, 0.0, 0.5))
+    if table:
+        ct = pkg.init_coul_tables(8.8, ge, u["qqrd2e"])
+        P.set_coul_tables(ct[0], 12, ct[1], ct[2], ct[3])
+        dt = pkg.init_disp_tables(6.8, 0.3)
+        P.set_disp_tables(dt[0], 0, dt[1], dt[2], dt[3])
+    cm = P.cutmax() + 2.0
+    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cm)
+    hn, hoff, hent = orc.neigh_half_bin(n, xa, ta, 2, P.cutneighsq(2.0), s["boxlo"], s["boxhi"], cm, 0)
+    hent = util.water_special_bits(n, hn, hent, src, s["mol"], s["type"])
+    fo, evo = orc.pair_eval(P, 0, 1, 0, n, xa, ta, qa, hn, hoff, hent, newton=1)
+    fk, ek, vk = orc.PPPM(*grid, 5, ge, s["boxlo"], s["boxhi"], u["qqrd2e"]).compute(s["x"], s["q"])
+    assert th[0, 2] == pytest.approx(evo[0] + evo[1] + ek, rel=1e-8)
+    assert th[0, 1] == pytest.approx(300.0, rel=1e-9)
