@@ -16,6 +16,8 @@ double precision (`package intel mode double`) — SURVEY.md §8d S3 / §6.2.
     buck_big                    examples/in.buck_big: pair buck 5.0, delay 5 every 1
     buck_coul_cut               examples/in.buck_coul_cut: data.aC x rep^3, buck/coul/cut 10.0, no kspace
     spce_pppm                   examples/in.spce electrostatics only: data.spce x rep^3, PPPMIntel::compute alone
+    spce                        examples/in.spce pair + k-space path: lj/cut/coul/long 6.8 8.8 with the molecules' special
+                                bonds in the device-built list + pppm, fix nve (SHAKE / bonds / NVT are off that path)
     buck_big_disp               BASELINE config 5: fcc melt, buck/long/coul/long long off 5.0 + pppm/disp (geometric)
 
 The JSON line carries, beside the contract's keys: `roofline` (the dominant kernel), `roofline_kernels` (one entry per
@@ -45,7 +47,10 @@ import __graft_entry__ as graft  # noqa: E402
 UNIT = "atom-timesteps/s"
 ORDER = 5
 # SURVEY §8d official work per pair evaluation (one neighbour-list entry)
-PAIR_FLOPS = {"buck": 58.0, "buck_coul_cut": 69.0, "buck_coul_long": 125.0, "buck_long_coul_long": 98.0}
+PAIR_FLOPS = {"buck": 58.0, "buck_coul_cut": 69.0, "buck_coul_long": 125.0, "buck_long_coul_long": 98.0,
+              # not in SURVEY 8d's list; counted the same way from pair_lj_long_coul_long_intel.cpp:540-690 (ORDER1, cut LJ):
+              # the buck/coul/long count without exp(-r/rho) and its two multiplies
+              "lj_long_coul_long": 103.0}
 
 
 def parse():
@@ -55,7 +60,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="buck_coul_long",
-                    choices=["buck_coul_long", "buck", "buck_big", "buck_coul_cut", "spce_pppm", "buck_big_disp"])
+                    choices=["buck_coul_long", "buck", "buck_big", "buck_coul_cut", "spce_pppm", "spce", "buck_big_disp"])
     ap.add_argument("--rep", type=int, default=0, help="replication per dimension per GPU (0: the config's default; "
                                                        "buck_coul_long 15 -> 4.05 M atoms)")
     ap.add_argument("--rep3", type=int, nargs=3, default=None, help="explicit replication / cells per dimension (one GPU), "
@@ -194,15 +199,16 @@ class Config:
         self.args, self.pkg, self.W, self.world = args, pkg, W, world
         c = args.config
         self.name = c
-        self.kspace = c in ("buck_coul_long", "spce_pppm", "buck_big_disp")
+        self.kspace = c in ("buck_coul_long", "spce_pppm", "spce", "buck_big_disp")
         self.pair = c != "spce_pppm"
-        dflt = {"buck_coul_long": 15, "buck_coul_cut": 15, "buck": 100, "buck_big": 100, "spce_pppm": 4,
+        dflt = {"buck_coul_long": 15, "buck_coul_cut": 15, "buck": 100, "buck_big": 100, "spce_pppm": 4, "spce": 8,
                 "buck_big_disp": 100}[c]
         self.rep = args.rep or dflt
         self.metric = {"buck_coul_long": "atom-timesteps/s buck/coul/long+PPPM", "buck": "atom-timesteps/s buck",
                        "buck_big": "atom-timesteps/s buck (in.buck_big)",
                        "buck_coul_cut": "atom-timesteps/s buck/coul/cut",
                        "spce_pppm": "atom-timesteps/s PPPM only (data.spce)",
+                       "spce": "atom-timesteps/s lj/cut/coul/long+PPPM (data.spce)",
                        "buck_big_disp": "atom-timesteps/s buck/long/coul/long+pppm/disp"}[c]
 
     def system(self, rep3):
@@ -211,7 +217,7 @@ class Config:
             return W.aC_system(rep3, jitter=0.0)   # the crystal as read, `velocity all create 300.0`
         if c in ("buck", "buck_big", "buck_big_disp"):
             return W.fcc_system(*rep3, jitter=0.0)
-        return W.spce_system(rep3)
+        return W.spce_system(rep3, temperature=30.0 if c == "spce" else 300.0)   # no bonded forces: keep the molecules together
 
     def global_reps(self):
         if self.args.rep3 and self.world == 1:
@@ -270,6 +276,29 @@ class Config:
             d = dict(style="buck/long/coul/long long off %.1f + pppm/disp (geometric) order %d" % (cut, ORDER),
                      grid=nmesh, g_ewald_6=g6, neigh="skin 0.3 delay 5 every 1 check yes",
                      flops_key="buck_long_coul_long")
+        elif c == "spce":
+            cl, cc, skin = 6.8, 8.8, 2.0
+            grid, g = pkg.pppm_init(a.acc, u["qqrd2e"], qsq_global, natoms_global, cc, prd, order=ORDER)
+            co = W.coeffs_spce(cl, cc)
+            cf = pkg.pair_coeffs(pkg.PAIR_LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+            ct = pkg.init_coul_tables(cc, g, u["qqrd2e"]) if a.table else None
+            sp = (1, 0.0, 0.0, 0.5)
+            ctx.neigh_setup(skin, every=1, delay=10, check=1)
+            ctx.pair_setup(pkg.PAIR_LJ_LONG_COUL_LONG, 2, cf, special_lj=sp, special_coul=sp, g_ewald=g,
+                           ewald_order=1 << 1, coul_tables=ct)
+            n = len(s["x"])
+            nsp = np.zeros((n, 3), np.int32)
+            spl = np.zeros((n, 2), np.int32)
+            o = np.arange(0, n, 3)            # O, H, H per molecule (examples/data.spce)
+            nsp[o] = (2, 2, 2)
+            spl[o, 0], spl[o, 1] = o + 1, o + 2
+            for h, other in ((o + 1, o + 2), (o + 2, o + 1)):
+                nsp[h] = (1, 2, 2)
+                spl[h, 0], spl[h, 1] = o, other
+            ctx.atoms_set_special(nsp, spl)
+            ctx.pppm_setup(*grid, ORDER, g)
+            d = dict(style="lj/cut/coul/long %.1f %.1f + special_bonds lj/coul 0 0 0.5 + pppm %g order %d" % (cl, cc, a.acc, ORDER),
+                     grid=list(grid), g_ewald=g, neigh="skin 2.0 delay 10 every 1 check yes", flops_key="lj_long_coul_long")
         elif c == "spce_pppm":
             cut = 8.8
             grid, g = pkg.pppm_init(a.acc, u["qqrd2e"], qsq_global, natoms_global, cut, prd, order=ORDER)
@@ -702,7 +731,7 @@ def run_b200(args):
             "dtype": "f64" if prec == pkg.PREC_DOUBLE else "f32 compute / f64 accumulate", "data": "synthetic",
             "config": {"workload": "%s x %dx%dx%d (%d atoms) %s, %s, nve dt %g" %
                                    ("data.aC" if "aC" in str(cfg.name) or cfg.name.startswith("buck_coul") else
-                                    ("data.spce" if cfg.name == "spce_pppm" else "fcc rho* 0.8442"),
+                                    ("data.spce" if cfg.name.startswith("spce") else "fcc rho* 0.8442"),
                                     rx, ry, blocks_z, natoms, desc["style"], desc["neigh"], u["dt"]),
                        "name": cfg.name, "precision": args.prec, "coulomb": "table" if args.table else "analytic erfc",
                        "grid": desc.get("grid"), "g_ewald": desc.get("g_ewald", desc.get("g_ewald_6")),
