@@ -780,11 +780,53 @@ def cpu_baseline(args, W):
     t0 = time.perf_counter()
     tm = md.run(args.cpu_steps, cores)
     dt = time.perf_counter() - t0
+    try:
+        ref_loops = reference_loops(args, W)
+    except Exception as ex:   # noqa: BLE001
+        ref_loops = {"error": str(ex)}
     return {"value": natoms * args.cpu_steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "reference_loops": ref_loops,
             "sample": "data.aC x %d^3 = %d atoms, grid %dx%dx%d, %d steps, %.1f s; restatement of the reference loops "
                       "(g++ -O3 -march=native -fopenmp; bit-identical to the reference's own compiled loops, oracle/_ref), "
                       "not the ICC USER-INTEL build" % (args.cpu_rep, natoms, *grid, args.cpu_steps, dt),
             "phase_s": {k: round(v, 3) for k, v in tm.items() if k != "nbuilds"}}
+
+
+def reference_loops(args, W):
+    """the reference's OWN compiled loops (oracle/_ref/libref.so: pair_buck_coul_long_intel.cpp eval<> and
+    PPPMIntel::compute, built unchanged by oracle/Makefile.ref, g++ -O3 -fopenmp, all host cores) timed on the sample —
+    the two hot loops only: the neighbour list, ghosts and the integrator around them are not in the reference"""
+    graft.load_oracle()
+    import refc
+    if not refc.available():
+        return None
+    orc = graft.load_oracle()
+    pkg = graft.load_package()
+    cores = os.cpu_count() or 1
+    u = W.UNITS["metal"]
+    s = W.aC_system(args.cpu_rep)
+    n = len(s["x"])
+    cut, skin = 12.0, 0.3
+    grid, g = pkg.pppm_init(args.acc, u["qqrd2e"], s["q"], n, cut, s["boxhi"] - s["boxlo"], order=ORDER)
+    co = W.coeffs_aC(cut, cut)
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=g)
+    cm = P.cutmax() + skin
+    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cm)
+    nn, off, ent = orc.neigh_half_bin(n, xa, ta, 2, P.cutneighsq(skin), s["boxlo"], s["boxhi"], cm, orc.DOUBLE)
+    tp, tk = [], []
+    for _ in range(3):
+        refc.pair_eval(P, orc.DOUBLE, 0, 0, n, xa, ta, qa, nn, off, ent, newton=1, nthreads=cores, skin=skin)
+        tp.append(refc.last_seconds())
+    pp = orc.PPPM(*grid, ORDER, g, s["boxlo"], s["boxhi"], u["qqrd2e"])
+    for _ in range(3):
+        refc.pppm_compute(pp, s["x"], s["q"], eflag=0, vflag=0, nthreads=cores, want_grids=False)
+        tk.append(refc.last_seconds())
+    return {"kind": "reference", "cores": cores, "atoms": n, "half_list_entries": int(len(ent)),
+            "pair_seconds_per_call": round(min(tp), 4), "pppm_seconds_per_call": round(min(tk), 4),
+            "pair_plus_pppm_atoms_per_s": n / (min(tp) + min(tk)),
+            "what": "PairBuckCoulLongIntel::compute (eval<0,0,1>) and PPPMIntel::compute of /root/reference compiled unchanged "
+                    "(oracle/_ref), best of 3, %d OpenMP threads" % cores}
 
 
 def run_reference(args):

@@ -12,6 +12,7 @@
 // The entry points mirror oracle.h so that a test can hand the same arrays to both and compare bit for bit.
 #include <pthread.h>
 
+#include <chrono>
 #include <string>
 
 #include "fix_intel.h"
@@ -29,6 +30,12 @@
 using namespace LAMMPS_NS;
 
 namespace {
+
+double g_last_seconds = 0.0;   // wall time of the last compute() call of the reference (ref_last_seconds)
+struct Stopwatch {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~Stopwatch() { g_last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 struct StubKSpace : public KSpace {
   StubKSpace(LAMMPS *lmp) : KSpace(lmp, 0, nullptr) {}
@@ -249,7 +256,10 @@ int ref_pair_eval(int style, int prec, int eflag, int vflag, int eatom, int newt
     else stage_buffers<double, double>(w, nlocal, nall, numneigh, offsets, entries);
     w.neighbor.ago = 1;   // a step after the build: compute() repacks positions itself (thr_pack, x only)
 
-    pair->compute(eflag ? (eatom ? 3 : 1) : 0, vflag);
+    {
+      Stopwatch sw;
+      pair->compute(eflag ? (eatom ? 3 : 1) : 0, vflag);
+    }
 
     for (int i = 0; i < nall; i++) {
       f[4 * (size_t)i + 0] = w.atom.f[i][0];
@@ -421,7 +431,10 @@ void *pppm_thread(void *vp) {
     pp.init();   // PPPMIntel::init: FixIntel lookup, order check
     if (c.prec == ORC_PREC_MIXED) stage_buffers<float, double>(w, c.nlocal, c.nlocal, nullptr, nullptr, nullptr);
     else stage_buffers<double, double>(w, c.nlocal, c.nlocal, nullptr, nullptr, nullptr);
-    pp.compute(c.eflag, c.vflag);
+    {
+      Stopwatch sw;
+      pp.compute(c.eflag, c.vflag);
+    }
     // fieldforce adds into IntelBuffers::_f (thread 0's array): that is the k-space force
     if (c.prec == ORC_PREC_MIXED) {
       auto *fb = w.fix->get_mixed_buffers()->get_f();
@@ -465,6 +478,9 @@ int ref_pppm_compute(const orc_pppm_state *st, int prec, int nlocal, const doubl
   if (rc < 0) return fail(err, errlen, "ref_pppm_compute: could not start the worker thread");
   return rc;
 }
+
+/* seconds the reference's own compute() took in the last ref_pair_eval / ref_pppm_compute call (set-up excluded) */
+double ref_last_seconds(void) { return g_last_seconds; }
 
 int ref_has_openmp(void) {
 #if defined(_OPENMP)

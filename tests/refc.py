@@ -126,3 +126,10 @@ def pppm_compute(pp, x, q, prec=orc.DOUBLE, eflag=1, vflag=1, nthreads=1, want_g
     if rc:
         raise RuntimeError("ref_pppm_compute: " + err.value.decode())
     return f, e.value, v, dens, fields
+
+
+def last_seconds():
+    """wall time of the reference's compute() inside the last pair_eval / pppm_compute call (harness set-up excluded)"""
+    f = lib().ref_last_seconds
+    f.restype = C.c_double
+    return float(f())

@@ -77,6 +77,9 @@ def test_own_arm_json_line_on_a_small_workload():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 76800 * 24 and e["d2h_bytes_per_step"] == 76800 * 48
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
+    # the reference's own compiled loops (oracle/_ref travels to the GPU box prebuilt) timed beside the port
+    rl = cb["reference_loops"]
+    assert rl["kind"] == "reference" and rl["pair_seconds_per_call"] > 0 and rl["pppm_seconds_per_call"] > 0
     assert d["clocks"]["sm_max_mhz"] > 0
     # one roofline entry per kernel with >= 1 % of the step, measured in this run
     names = [r["kernel"] for r in d["roofline_kernels"]]

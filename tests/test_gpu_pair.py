@@ -497,3 +497,49 @@ def test_table_inner_cutoff_and_list_flavours_agree(pkg, W, orc):
     assert util.rel_force_err(f, fg[:, :3]) <= 1e-12
     assert abs(ev[1] - evg[1]) <= 1e-12 * abs(evg[1])
     ctx.close()
+
+
+def test_setup_guards_and_host_list_validation(pkg, W, orc):
+    """errors instead of silent garbage (round-1 advisor findings): exponent arguments outside fast_exp's range are
+    refused at setup; b200md_pair_eval_host checks the caller's types and list entries; a k-space state is dropped by a
+    later b200md_neigh_setup with a larger skin (its brick halo is sized from skin/2)"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    co = W.coeffs_aC(12.0, 12.0)
+    cf = pkg.pair_coeffs(pkg.PAIR_BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+    ctx = pkg.make_context(s)
+    ctx.neigh_setup(0.3)
+    with pytest.raises(pkg.B200MDError, match="g_ewald"):
+        ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=3.0)          # (3 * 12)^2 > 700
+    bad = {k: v.copy() for k, v in cf.items()}
+    bad["rhoinv"][1, 2] = bad["rhoinv"][2, 1] = -1.0
+    with pytest.raises(pkg.B200MDError, match="must be positive"):
+        ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, bad, g_ewald=0.28)
+    cfl = pkg.pair_coeffs(pkg.PAIR_BUCK_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+    with pytest.raises(pkg.B200MDError, match="g_ewald_6"):
+        ctx.pair_setup(pkg.PAIR_BUCK_LONG_COUL_LONG, 2, cfl, g_ewald=0.28, g_ewald_6=2.5, ewald_order=(1 << 1) | (1 << 6))
+    ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=0.28)
+    # host-supplied list: a type outside 1..ntypes, an entry past nall
+    n = len(s["x"])
+    nn = np.ones(n, np.int32)
+    off = np.arange(n, dtype=np.int64)
+    ent = ((np.arange(n) + 1) % n).astype(np.int32)
+    t_bad = s["type"].copy()
+    t_bad[5] = 3
+    with pytest.raises(pkg.B200MDError, match="type"):
+        ctx.pair_eval_host(0, 0, n, s["x"], t_bad, s["q"], nn, off, ent)
+    e_bad = ent.copy()
+    e_bad[7] = n + 3
+    with pytest.raises(pkg.B200MDError, match="past nall"):
+        ctx.pair_eval_host(0, 0, n, s["x"], s["type"], s["q"], nn, off, e_bad)
+    f, ev = ctx.pair_eval_host(0, 0, n, s["x"], s["type"], s["q"], nn, off, ent)
+    assert np.isfinite(f).all()
+    # stale k-space state
+    ctx.pppm_setup(24, 24, 27, 5, 0.28)
+    ctx.neigh_setup(0.2)                      # smaller skin: the halo still covers it, the state stays
+    ctx.setup_forces(0, 0)
+    ctx.neigh_setup(1.0)                      # larger skin: the state is dropped
+    with pytest.raises(pkg.B200MDError, match="before b200md_pppm_setup"):
+        ctx.pppm_compute(0, 0)
+    # an empty system exports offsets[0] = 0
+    ctx.close()
