@@ -65,9 +65,11 @@ def parse():
                                                        "buck_coul_long 15 -> 4.05 M atoms)")
     ap.add_argument("--rep3", type=int, nargs=3, default=None, help="explicit replication / cells per dimension (one GPU), "
                                                                      "e.g. 30 40 40 = the in.buck_big box")
-    ap.add_argument("--geometry", default="slab", choices=["slab", "cube"],
-                    help="N > 1: 'slab' stacks the per-GPU blocks along z (rep x rep x rep*N), 'cube' replicates the "
-                         "global system isotropically to the same atom count (SURVEY S3: data.aC x 30^3 on 8 GPUs)")
+    ap.add_argument("--geometry", default="cube", choices=["slab", "cube"],
+                    help="N > 1: 'cube' (default) replicates the global system isotropically, round(rep * N^(1/3)) per "
+                         "dimension (SURVEY S3: data.aC x 30^3 = 32.4 M atoms on 8 GPUs; 19^3 / 24^3 on 2 / 4: per-GPU "
+                         "work within 2.5 %% of the single-GPU run); 'slab' stacks the per-GPU blocks along z "
+                         "(rep x rep x rep*N), which keeps the halo area per GPU constant and flatters a slab decomposition")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: --rep is the GLOBAL replication, split over the ranks")
     ap.add_argument("--acc", type=float, default=1.0e-4, help="kspace accuracy (the shipped in.buck_coul_long says 1e-6)")
@@ -283,7 +285,11 @@ class Config:
             cf = pkg.pair_coeffs(pkg.PAIR_LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
             ct = pkg.init_coul_tables(cc, g, u["qqrd2e"]) if a.table else None
             sp = (1, 0.0, 0.0, 0.5)
-            ctx.neigh_setup(skin, every=1, delay=10, check=1)
+            # SHAKE and the bonded terms are off this path, so nothing holds the sites of a molecule together: the positions
+            # advance with a 0.01 fs step (same work per step) and the list is rebuilt every 10 steps, the cadence in.spce
+            # reaches with its 2 A skin and `delay 10`
+            ctx.neigh_setup(skin, every=10, delay=0, check=0)
+            self.dt_override = 0.01
             ctx.pair_setup(pkg.PAIR_LJ_LONG_COUL_LONG, 2, cf, special_lj=sp, special_coul=sp, g_ewald=g,
                            ewald_order=1 << 1, coul_tables=ct)
             n = len(s["x"])
@@ -298,7 +304,8 @@ class Config:
             ctx.atoms_set_special(nsp, spl)
             ctx.pppm_setup(*grid, ORDER, g)
             d = dict(style="lj/cut/coul/long %.1f %.1f + special_bonds lj/coul 0 0 0.5 + pppm %g order %d" % (cl, cc, a.acc, ORDER),
-                     grid=list(grid), g_ewald=g, neigh="skin 2.0 delay 10 every 1 check yes", flops_key="lj_long_coul_long")
+                     grid=list(grid), g_ewald=g, neigh="skin 2.0, rebuilt every 10 steps, dt 0.01 fs (no SHAKE / bonds on the path)",
+                     flops_key="lj_long_coul_long")
         elif c == "spce_pppm":
             cut = 8.8
             grid, g = pkg.pppm_init(a.acc, u["qqrd2e"], qsq_global, natoms_global, cut, prd, order=ORDER)
@@ -306,7 +313,7 @@ class Config:
             ctx.pppm_setup(*grid, ORDER, g)
             d = dict(style="pppm %g order %d (lj/cut/coul/long 6.8 8.8 not evaluated: electrostatics only)" % (a.acc, ORDER),
                      grid=list(grid), g_ewald=g, neigh="none (k-space only)", flops_key=None)
-        ctx.nve_setup(u["dt"])
+        ctx.nve_setup(getattr(self, "dt_override", None) or u["dt"])
         return d
 
     @staticmethod
