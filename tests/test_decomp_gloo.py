@@ -163,3 +163,62 @@ def test_bench_cube_geometry_keeps_the_per_gpu_atom_count():
         assert abs(r ** 3 / world / 15 ** 3 - 1.0) < 0.03
     assert bench.split_reps(15, 8, "slab", "weak") == (15, 15, 120)
     assert bench.split_reps(24, 4, "slab", "strong") == (24, 24, 24)
+
+
+def _memcpy2d(dst, doff, dpitch, src, soff, spitch, width, height):
+    """cudaMemcpy2DAsync on flat arrays (element units): `height` rows of `width` elements"""
+    for r in range(height):
+        dst[doff + r * dpitch: doff + r * dpitch + width] = src[soff + r * spitch: soff + r * spitch + width]
+
+
+@pytest.mark.parametrize("P,nx,ny,nz,npack", [(2, 6, 10, 24, 2), (3, 5, 10, 37, 2), (4, 4, 9, 48, 1), (8, 3, 13, 96, 2)])
+def test_peer_copy_plan_tiles_the_transposes(pkg, P, nx, ny, nz, npack):
+    """the copy-engine transposes of csrc/pppm.cu (poisson_multi): the strided copies every rank issues into its peers'
+    pencil / plane blocks — destination offset and pitch, source offset and pitch, width, height exactly as in the
+    cudaMemcpy2DAsync calls — cover each destination block once and put every element where the next pass reads it
+    (uneven row / plane splits included)"""
+    lib = pkg.load()
+    arr = [(C.c_int * P)() for _ in range(6)]
+    assert lib.b200md_pppm_decomp(C.c_int(P), C.c_int(nz), C.c_int(ny), C.c_int(5), C.c_double(0.3), C.c_double(4.0 * nz),
+                                  *arr) == 0
+    pzlo, pzhi, _, _, ylo, yhi = [list(a) for a in arr]
+    plane = nx * ny
+    rng = np.random.default_rng(3)
+    G = rng.normal(size=(nz, ny, nx))                       # the global array after the x / y passes
+    maxrows = max(yhi[q] - ylo[q] for q in range(P))
+    maxplanes = max(pzhi[q] - pzlo[q] for q in range(P))
+    symT = [np.full(nx * maxrows * nz, np.nan) for _ in range(P)]
+    # forward: rank me holds its planes [nzo][ny][nx]; one copy per destination q
+    for me in range(P):
+        nzo = pzhi[me] - pzlo[me]
+        work1 = np.ascontiguousarray(G[pzlo[me]:pzhi[me]]).ravel()
+        for k in range(P):
+            q = (me + k) % P
+            nylq = yhi[q] - ylo[q]
+            if nylq == 0 or nzo == 0:
+                continue
+            _memcpy2d(symT[q], pzlo[me] * nylq * nx, nylq * nx, work1, ylo[q] * nx, plane, nylq * nx, nzo)
+    for q in range(P):
+        nyl = yhi[q] - ylo[q]
+        got = symT[q][:nz * nyl * nx].reshape(nz, nyl, nx)
+        assert np.array_equal(got, G[:, ylo[q]:yhi[q], :]), ("forward", q)
+    # backward: rank me holds its pencils [npack][nz][nyl][nx]; one copy per destination and packed field
+    H = [rng.normal(size=(nz, ny, nx)) for _ in range(npack)]
+    symW = [np.full(npack * plane * maxplanes, np.nan) for _ in range(P)]
+    for me in range(P):
+        nyl = yhi[me] - ylo[me]
+        nT = nx * nyl * nz
+        workT2 = np.concatenate([np.ascontiguousarray(H[c][:, ylo[me]:yhi[me], :]).ravel() for c in range(npack)])
+        for k in range(P):
+            q = (me + k) % P
+            nzq = pzhi[q] - pzlo[q]
+            if nzq == 0 or nyl == 0:
+                continue
+            for comp in range(npack):
+                _memcpy2d(symW[q], (comp * nzq * ny + ylo[me]) * nx, plane, workT2, comp * nT + pzlo[q] * nyl * nx,
+                          nyl * nx, nyl * nx, nzq)
+    for q in range(P):
+        nzq = pzhi[q] - pzlo[q]
+        got = symW[q][:npack * nzq * plane].reshape(npack, nzq, ny, nx)
+        for c in range(npack):
+            assert np.array_equal(got[c], H[c][pzlo[q]:pzhi[q]]), ("backward", q, c)
