@@ -181,9 +181,15 @@ typedef struct {
   double g_ewald;
   int differentiation;   /* 0 = ik, 1 = ad (kspace_modify diff) */
   double scale;          /* KSpace::scale, 1.0 */
-  int dispersion;        /* 0: Coulomb ('c', charges); 1: geometric dispersion ('g', weight B[type],
-                            pppm_disp_intel.cpp:245-313 with SURVEY §2.4-2 corrected) */
-  const double *B;       /* dispersion: [ntypes+1] geometric coefficients; else NULL */
+  int dispersion;        /* 0: Coulomb ('c', charges, function[0]); r^-6 grids of PPPMDispIntel::compute by mixing rule:
+                            1: geometric (function[1], 'g', pppm_disp_intel.cpp:245-313 with SURVEY §2.4-2 corrected),
+                            2: arithmetic (function[2], seven grids, :315-407), 3: none (function[3], :409-467) */
+  const double *B;       /* the array PPPMDisp::init_coeffs builds for that rule, type index 0 unused:
+                            1: B[ntypes+1], C_ij = B_i B_j;
+                            2: B[7 (ntypes+1)], B[7 i + k] = sqrt(eps_i) / 4 * sqrt(binom(6,k)) * sigma_i^k
+                               (C_ij = sum_k B_i[k] B_j[6-k] = 4 eps_ij sigma_ij^6, Lorentz-Berthelot);
+                            3: B[(ntypes+1)^2] = C_ij itself, symmetric (split into eigen-components inside);
+                            0: NULL */
   double slab_volfactor; /* kspace_modify slab: > 1 = z is non-periodic, the mesh spans zprd * slab_volfactor and
                             PPPM::slabcorr (pppm_intel.cpp:305) is applied; 0 or 1 = off.  Coulomb grid, one GPU */
 } b200md_pppm_params;

@@ -12,6 +12,11 @@ extern "C" {
  * coordinate as tile * 16 + local coordinate (-1 = unused), four entries per coordinate */
 int b200md_debug_rho_plan(int order, int n, int *pitch, int *lane_point, int *cover);
 
+/* host-only: the signed self-coupled components a dispersion grid is split into (b200md_pppm_params.dispersion = 1, 2, 3
+ * and its B array; see disp_components in csrc/pppm.cu).  W[ncomp][ntypes+1], sign[ncomp]; returns ncomp (<= 16) or a
+ * negative error.  sum_m sign[m] W[m][i] W[m][j] is the r^-6 coefficient of the type pair. */
+int b200md_debug_disp_components(int mix, int ntypes, const double *B, double *W, double *sign);
+
 /* roofline denominators measured on this device ("P_fp measured on the box by a microbenchmark"):
  * kind 0 = FP64 FMA TFLOP/s, 1 = FP32 FMA TFLOP/s, 2 = HBM copy GB/s (read+write bytes).  Not a reference API. */
 int b200md_microbench(b200md_ctx *ctx, int kind, double *value);

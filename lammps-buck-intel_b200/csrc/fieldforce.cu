@@ -127,8 +127,9 @@ int b2_fieldforce(b200md_ctx *ctx, PppmState &ps, const PppmView &v) {
   const PppmConst &c = ps.c;
   const int n = v.n;
   const bool ad = ps.p.differentiation == 1;
-  const double qs = ps.p.dispersion ? 1.0 : ctx->qqrd2e * ps.p.scale;   // dispersion: f += B[type] * E
-  const double *B = ps.p.dispersion ? ps.Btype.p : nullptr;
+  // dispersion: f += sign_m * W_m[type] * E_m for the component m of this pass
+  const double qs = ps.p.dispersion ? ps.comp_sign[ps.cur] : ctx->qqrd2e * ps.p.scale;
+  const double *B = ps.p.dispersion ? ps.Btype.p + (size_t)ps.cur * (ctx->ntypes + 1) : nullptr;
   const double *sf = ps.sf_coeff;
   if (n <= 0) return 0;
   const int nb = cdiv(n, 128);

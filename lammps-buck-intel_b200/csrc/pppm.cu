@@ -1322,30 +1322,42 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
 
   // qsum_qsq when the atom count changed (pppm_intel.cpp:142-145).  Multi-GPU: the local count changes with every
   // migration but the global sums do not, and the reduction is collective: done once per setup.
+  const int ncomp = ps.p.dispersion ? ps.ncomp : 1;
+  const int tp1 = ctx->ntypes + 1;
   if (ps.nranks > 1 ? ps.q_natoms < 0 : ps.q_natoms != n) {
     RESERVE(ctx, ps.density, std::max((size_t)nfft, 2 * (size_t)n + 2));
-    if (n > 0) {
-      k_q_moments<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.type, ps.p.dispersion ? ps.Btype.p : nullptr,
-                                                          ps.density.p);
-      KERNEL_OK(ctx, "k_q_moments");
-      double m[2];
-      TRY(reduce_cols(ctx, ps, n, 2, ps.density.p, m));
-      ps.qsum = m[0];
-      ps.qsqsum = m[1];
-    } else ps.qsum = ps.qsqsum = 0.0;
+    for (int m = 0; m < ncomp; m++) {
+      if (n > 0) {
+        k_q_moments<<<cdiv(n, 256), 256, 0, ctx->stream>>>(
+            n, v.xq, v.type, ps.p.dispersion ? ps.Btype.p + (size_t)m * tp1 : nullptr, ps.density.p);
+        KERNEL_OK(ctx, "k_q_moments");
+        double mm[2];
+        TRY(reduce_cols(ctx, ps, n, 2, ps.density.p, mm));
+        ps.comp_qsum[m] = mm[0];
+        ps.comp_qsqsum[m] = mm[1];
+      } else ps.comp_qsum[m] = ps.comp_qsqsum[m] = 0.0;
+    }
     if (ps.nranks > 1) {
-      RESERVE(ctx, ps.red, 16);
-      const double m2[2] = {ps.qsum, ps.qsqsum};
-      CUDA_OK(ctx, cudaMemcpyAsync(ps.red.p, m2, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      TRY(b2_comm_allreduce_sum(ctx, ps.red.p, 2));
-      CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      RESERVE(ctx, ps.red, 2 * PppmState::MAXCOMP);
+      double m2[2 * PppmState::MAXCOMP];
+      for (int m = 0; m < ncomp; m++) { m2[2 * m] = ps.comp_qsum[m]; m2[2 * m + 1] = ps.comp_qsqsum[m]; }
+      CUDA_OK(ctx, cudaMemcpyAsync(ps.red.p, m2, 2 * ncomp * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      TRY(b2_comm_allreduce_sum(ctx, ps.red.p, 2 * ncomp));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, ps.red.p, 2 * ncomp * sizeof(double), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
       CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-      ps.qsum = ctx->h_pinned[0];
-      ps.qsqsum = ctx->h_pinned[1];
+      for (int m = 0; m < ncomp; m++) { ps.comp_qsum[m] = ctx->h_pinned[2 * m]; ps.comp_qsqsum[m] = ctx->h_pinned[2 * m + 1]; }
     }
     ps.q_natoms = n;
   }
-  if (ps.qsqsum == 0.0) return 0;  // "return if there are no charges" :149
+  // "return if there are no charges" :149 - per component of a dispersion grid
+  bool sorted = false;
+  for (int comp = 0; comp < ncomp; comp++) {
+  ps.cur = comp;
+  ps.qsum = ps.comp_qsum[comp];
+  ps.qsqsum = ps.comp_qsqsum[comp];
+  if (ps.qsqsum == 0.0) continue;
+  const double *Bcomp = ps.p.dispersion ? ps.Btype.p + (size_t)comp * tp1 : nullptr;
 
   // ---- particle_map + cell sort + make_rho ------------------------------------------------------
   {
@@ -1362,21 +1374,25 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     RESERVE(ctx, ps.cursor, (size_t)nfft + 1);
     RESERVE(ctx, ps.flags, 4);
     RESERVE(ctx, ps.scan_ws, b2_scan_ws_bytes((size_t)nfft + 1));
-    CUDA_OK(ctx, cudaMemsetAsync(ps.cell_count.p, 0, ((size_t)nfft + 1) * sizeof(int), ctx->stream));
-    CUDA_OK(ctx, cudaMemsetAsync(ps.flags.p, 0, 4 * sizeof(int), ctx->stream));
-    if (n > 0) {
-      k_map_key<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.xqf, c, ps.key.p, ps.cell_count.p, ps.flags.p);
-      KERNEL_OK(ctx, "k_map_key");
+    if (!sorted) {   // the cell sort does not depend on the weights: once for all components
+      CUDA_OK(ctx, cudaMemsetAsync(ps.cell_count.p, 0, ((size_t)nfft + 1) * sizeof(int), ctx->stream));
+      CUDA_OK(ctx, cudaMemsetAsync(ps.flags.p, 0, 4 * sizeof(int), ctx->stream));
+      if (n > 0) {
+        k_map_key<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, v.xq, v.xqf, c, ps.key.p, ps.cell_count.p, ps.flags.p);
+        KERNEL_OK(ctx, "k_map_key");
+      }
+      TRY(b2_exclusive_scan_i32(ctx, ps.cell_count.p, ps.cell_start.p, (size_t)nfft, ps.scan_ws.p));
+      CUDA_OK(ctx, cudaMemcpyAsync(ps.cursor.p, ps.cell_start.p, (size_t)nfft * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+      if (n > 0) {
+        k_cell_scatter<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.key.p, ps.cursor.p, ps.perm.p);
+        KERNEL_OK(ctx, "k_cell_scatter");
+        k_cell_order<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(nfft, ps.cell_start.p, ps.perm.p);
+        KERNEL_OK(ctx, "k_cell_order");
+      }
+      sorted = true;
     }
-    TRY(b2_exclusive_scan_i32(ctx, ps.cell_count.p, ps.cell_start.p, (size_t)nfft, ps.scan_ws.p));
-    CUDA_OK(ctx, cudaMemcpyAsync(ps.cursor.p, ps.cell_start.p, (size_t)nfft * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     if (n > 0) {
-      k_cell_scatter<<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.key.p, ps.cursor.p, ps.perm.p);
-      KERNEL_OK(ctx, "k_cell_scatter");
-      k_cell_order<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(nfft, ps.cell_start.p, ps.perm.p);
-      KERNEL_OK(ctx, "k_cell_order");
-      k_fill_sorted<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.perm.p, v.xq, v.xqf, v.type,
-                                                                   ps.p.dispersion ? ps.Btype.p : nullptr, c, ps.pa_x.p,
+      k_fill_sorted<flt_t><<<cdiv(n, 256), 256, 0, ctx->stream>>>(n, ps.perm.p, v.xq, v.xqf, v.type, Bcomp, c, ps.pa_x.p,
                                                                    ps.pa_n.p, tiled ? nullptr : ps.pa_w.p, ps.pa_cx.p);
       KERNEL_OK(ctx, "k_fill_sorted");
     }
@@ -1505,14 +1521,15 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
 
   // ---- energy / virial post-factors (pppm_intel.cpp:256-275) -----------------------------------------
   if (ps.p.dispersion) {
-    // pppm_disp_intel.cpp:486-510, geometric mixing: csum = sum B_i^2 (= qsqsum here), csumij = (sum B_i)^2
-    const double g3 = c.g_ewald * c.g_ewald * c.g_ewald;
+    // pppm_disp_intel.cpp:486-510: csum = sum_i C_ii, csumij = sum_ij C_ij.  Per component C_ij = sign W_i W_j, so
+    // csum = sign * qsqsum and csumij = sign * qsum^2 (geometric mixing: one component, W = B)
+    const double g3 = c.g_ewald * c.g_ewald * c.g_ewald, sg = ps.comp_sign[comp];
     const double csum = ps.qsqsum, csumij = ps.qsum * ps.qsum;
     const double a = kPI * kPIS / (6.0 * ps.volume) * g3 * csumij;
-    if (eflag_global && energy) *energy = 0.5 * ps.volume * evsum[0] - a + g3 * g3 * csum / 12.0;
+    if (eflag_global && energy) *energy += sg * (0.5 * ps.volume * evsum[0] - a + g3 * g3 * csum / 12.0);
     if (vflag_global && virial)
-      for (int k = 0; k < 6; k++) virial[k] = 0.5 * ps.volume * evsum[1 + k] - (k < 3 ? a : 0.0);
-    return 0;
+      for (int k = 0; k < 6; k++) virial[k] += sg * (0.5 * ps.volume * evsum[1 + k] - (k < 3 ? a : 0.0));
+    continue;
   }
   const double qscale = ctx->qqrd2e * ps.p.scale;
   if (eflag_global && energy) {
@@ -1550,10 +1567,99 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     if (slab_err != cudaSuccess) return b2_fail(ctx, B200MD_ECUDA, "k_slabcorr: %s", cudaGetErrorString(slab_err));
     ctx->launches++;
   }
+  }   // components
   return 0;
 }
 
 }  // namespace
+
+// Signed self-coupled components of a dispersion grid (PppmState::ncomp): W[m][type], sign[m] with
+// C_ij = sum_m sign_m W_m[i] W_m[j] the r^-6 coefficient of the type pair.
+//   mix 1, geometric (pppm_disp_intel.cpp:245-313): B[T+1], C_ij = B_i B_j -> one component.
+//   mix 2, arithmetic (:315-407): B[7 (T+1)] in the layout of PPPMDisp::init_coeffs, B[7 i + k], C_ij = sum_k B_i[k]
+//     B_j[6-k].  The reference spreads seven densities a_k and couples a_k with a_{6-k} (poisson_2s_ik); here each
+//     coupled pair is rotated into two self-coupled densities, 2 <a_k, a_{6-k}> = <p, p> - <m, m> with
+//     p, m = (a_k +- a_{6-k}) / sqrt 2, so that the same seven grids run through the one-density kernels: signs
+//     + (a_3), + + + (p), - - - (m).  Energy, virial and forces are the same sums (tests/test_gpu_pppm.py).
+//   mix 3, no mixing rule (:409-467): B[(T+1)^2] = C_ij, symmetric; C = V diag(lambda) V^T by cyclic Jacobi sweeps
+//     (what PPPMDisp::init_coeffs does with its own eigen solver): W_m = sqrt|lambda_m| V[:, m], sign_m = sign lambda_m;
+//     eigenvalues below 1e-12 max|lambda| are dropped (nsplit).
+static int disp_components(int mix, int T, const double *B, std::vector<double> &W, std::vector<double> &sign) {
+  const int tp1 = T + 1;
+  W.clear(); sign.clear();
+  if (mix == 1) {
+    W.assign(B, B + tp1);
+    sign.push_back(1.0);
+    return 0;
+  }
+  if (mix == 2) {
+    const double r = std::sqrt(0.5);
+    W.assign((size_t)7 * tp1, 0.0);
+    for (int i = 0; i < tp1; i++) {
+      W[i] = B[7 * i + 3];
+      for (int k = 0; k < 3; k++) {
+        W[(size_t)(1 + k) * tp1 + i] = r * (B[7 * i + k] + B[7 * i + 6 - k]);
+        W[(size_t)(4 + k) * tp1 + i] = r * (B[7 * i + k] - B[7 * i + 6 - k]);
+      }
+    }
+    sign = {1, 1, 1, 1, -1, -1, -1};
+    return 0;
+  }
+  if (mix != 3 || T < 1 || T > PppmState::MAXCOMP) return 1;
+  // cyclic Jacobi on the T x T block of types 1..T
+  std::vector<double> A((size_t)T * T), V((size_t)T * T, 0.0);
+  double amax = 0.0;
+  for (int i = 0; i < T; i++)
+    for (int j = 0; j < T; j++) {
+      A[(size_t)i * T + j] = B[(size_t)(i + 1) * tp1 + j + 1];
+      amax = std::max(amax, std::fabs(A[(size_t)i * T + j]));
+    }
+  for (int i = 0; i < T; i++)
+    for (int j = 0; j < i; j++)
+      if (std::fabs(A[(size_t)i * T + j] - A[(size_t)j * T + i]) > 1e-12 * amax) return 1;
+  for (int i = 0; i < T; i++) V[(size_t)i * T + i] = 1.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = 0.0;
+    for (int i = 0; i < T; i++)
+      for (int j = i + 1; j < T; j++) off += A[(size_t)i * T + j] * A[(size_t)i * T + j];
+    if (off <= 1e-30 * amax * amax) break;
+    for (int pI = 0; pI < T; pI++)
+      for (int q = pI + 1; q < T; q++) {
+        const double apq = A[(size_t)pI * T + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * T + q] - A[(size_t)pI * T + pI]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < T; k++) {   // A <- A J
+          const double akp = A[(size_t)k * T + pI], akq = A[(size_t)k * T + q];
+          A[(size_t)k * T + pI] = cs * akp - sn * akq;
+          A[(size_t)k * T + q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < T; k++) {   // A <- J^T A
+          const double apk = A[(size_t)pI * T + k], aqk = A[(size_t)q * T + k];
+          A[(size_t)pI * T + k] = cs * apk - sn * aqk;
+          A[(size_t)q * T + k] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < T; k++) {   // V <- V J
+          const double vkp = V[(size_t)k * T + pI], vkq = V[(size_t)k * T + q];
+          V[(size_t)k * T + pI] = cs * vkp - sn * vkq;
+          V[(size_t)k * T + q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  double lmax = 0.0;
+  for (int m = 0; m < T; m++) lmax = std::max(lmax, std::fabs(A[(size_t)m * T + m]));
+  for (int m = 0; m < T; m++) {
+    const double lam = A[(size_t)m * T + m];
+    if (std::fabs(lam) <= 1e-12 * lmax) continue;
+    const size_t base = W.size();
+    W.resize(base + tp1, 0.0);
+    for (int i = 0; i < T; i++) W[base + i + 1] = std::sqrt(std::fabs(lam)) * V[(size_t)i * T + m];
+    sign.push_back(lam > 0 ? 1.0 : -1.0);
+  }
+  if (sign.empty()) { W.assign(tp1, 0.0); sign.push_back(1.0); }
+  return 0;
+}
 
 static void free_state(b200md_ctx *ctx, PppmState *&slot) {
   PppmState *ps = slot;
@@ -1816,8 +1922,14 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     }
   }
   if (p->dispersion) {
-    RESERVE(ctx, ps->Btype, (size_t)ctx->ntypes + 1);
-    CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, p->B, ((size_t)ctx->ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double> W, sg;
+    if (disp_components(p->dispersion, ctx->ntypes, p->B, W, sg))
+      return b2_fail(ctx, B200MD_EINVAL, "dispersion PPPM: mixing must be 1 (geometric), 2 (arithmetic) or 3 (none) "
+                                         "with a symmetric coefficient matrix");
+    ps->ncomp = (int)sg.size();
+    for (int m = 0; m < ps->ncomp; m++) ps->comp_sign[m] = sg[m];
+    RESERVE(ctx, ps->Btype, W.size());
+    CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (ngf == 0) {
   } else if (p->dispersion && !ad) {
@@ -1862,6 +1974,15 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   (void)k4PI;
   return 0;
+}
+
+int b200md_debug_disp_components(int mix, int ntypes, const double *B, double *W, double *sign) {
+  if (!B || !W || !sign || ntypes < 1) return B200MD_EINVAL;
+  std::vector<double> w, s;
+  if (disp_components(mix, ntypes, B, w, s)) return B200MD_EINVAL;
+  std::copy(w.begin(), w.end(), W);
+  std::copy(s.begin(), s.end(), sign);
+  return (int)s.size();
 }
 
 // host-only helpers of the tiled charge assignment, exposed for the CPU tests (no device needed)

@@ -35,7 +35,14 @@ struct PppmState {
   DevBuf<double2> work1, work2;                         // work2: 3*nfft (ik) / nfft (ad)
   DevBuf<double> sf_pre;                                // ad: 6*nfft
   double sf_coeff[6] = {0, 0, 0, 0, 0, 0};
-  DevBuf<double> Btype;                                 // dispersion: per-type weight
+  DevBuf<double> Btype;                                 // dispersion: per-type weights, [ncomp][ntypes + 1]
+  // Dispersion grids are sums of SIGNED self-coupled components: E = sum_m sign_m <rho_m, G rho_m>, rho_m spread with
+  // the per-type weight W_m[type].  geometric: one component (W = B, +).  arithmetic (7 coupled grids a0..a6 of
+  // pppm_disp_intel.cpp:315-407) and no mixing (:409-467): see disp_components() in pppm.cu.
+  static constexpr int MAXCOMP = 16;
+  int ncomp = 1, cur = 0;                               // cur: the component the kernels of this pass work on
+  double comp_sign[MAXCOMP] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+  double comp_qsum[MAXCOMP] = {0}, comp_qsqsum[MAXCOMP] = {0};
   // per-step atom -> cell sort
   DevBuf<int> key, cell_count, cell_start, cursor, perm, flags;
   DevBuf<double4> pa_x;  // sorted: {dx,dy,dz, weight*delvolinv}

@@ -154,6 +154,8 @@ class Pair : protected Pointers {
   std::vector<double> eatom;
   int suffix_flag = Suffix::NONE;
   int ewaldflag = 0, dispersionflag = 0, offset_flag = 0;
+  enum { GEOMETRIC = 0, ARITHMETIC = 1, SIXTHPOWER = 2 };   // pair.h [UPSTREAM]
+  int mix_flag = GEOMETRIC;       // pair_modify mix geometric|arithmetic
   int ncoultablebits = 12;        // pair_modify table 12 (stock default)
   int ndisptablebits = 12;
   double tabinner = 1.4142135623730951, tabinner_disp = 1.4142135623730951;
@@ -165,6 +167,8 @@ class Pair : protected Pointers {
   virtual void init_style() = 0;
   virtual double init_one(int i, int j) = 0;
   virtual void init();   // loops init_one over type pairs (Pair::init)
+  // the init_one loop alone: what PPPMDisp::init calls pair->init() for before it reads the mixed coefficients
+  virtual void init_all_pairs() {}
   virtual void *extract(const char *, int &dim) { dim = 0; return nullptr; }
 
  protected:
@@ -188,6 +192,7 @@ class KSpace : protected Pointers {
   int differentiation_flag = 0;   // kspace_modify diff ik|ad
   int gridflag = 0, gewaldflag = 0;   // kspace_modify mesh / gewald
   int gridflag_6 = 0, gewaldflag_6 = 0;
+  int mixflag = 0;                // kspace_modify mix/disp pair (0) | geom (1) | none (2)
   double accuracy = 0.0, accuracy_relative = 0.0, accuracy_absolute = -1.0, two_charge_force = 0.0;
   double scale = 1.0;
   int slabflag = 0;                 // kspace_modify slab

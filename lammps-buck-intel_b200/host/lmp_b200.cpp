@@ -628,6 +628,11 @@ struct Script {
         if (w[i] == "table") pair->ncoultablebits = std::atoi(w[i + 1].c_str());
         else if (w[i] == "table/disp") pair->ndisptablebits = std::atoi(w[i + 1].c_str());
         else if (w[i] == "shift") pair->offset_flag = w[i + 1] == "yes";
+        else if (w[i] == "mix") {
+          if (w[i + 1] == "geometric") pair->mix_flag = Pair::GEOMETRIC;
+          else if (w[i + 1] == "arithmetic") pair->mix_flag = Pair::ARITHMETIC;
+          else fail("Illegal pair_modify command (mix geometric|arithmetic are provided)");
+        }
         else fail("Illegal pair_modify command");
       }
     } else if (c == "kspace_style") { need(3); kspace_style(w); }

@@ -44,7 +44,7 @@ class PairBuck : public Pair {
                     const PairTables *ctab, const PairTables *dtab);
   void device_compute(FixIntel *fix, int eflag, int vflag);
   FixIntel *require_fix_intel();
-  void init_all_pairs();   // pack_force_const repeats init_one for every type pair (pair_buck_intel.cpp:399-409)
+  void init_all_pairs() override;   // pack_force_const repeats init_one for every type pair (pair_buck_intel.cpp:399-409)
   static void bounds(Error *error, const char *str, int nmax, int &nlo, int &nhi);
   static void init_bitmap(double inner, double outer, int ntablebits, int &masklo, int &maskhi, int &nmask,
                           int &nshiftbits);

@@ -55,11 +55,13 @@ void PairLJLongCoulLong::coeff(int narg, char **arg) {
 // lj1 = 48 eps sigma^12, lj2 = 24 eps sigma^6, lj3 = 4 eps sigma^12, lj4 = 4 eps sigma^6; offset = 4 eps ((s/rc)^12 - (s/rc)^6)
 double PairLJLongCoulLong::init_one(int i, int j) {
   const int n = tp1(), ij = i * n + j, ji = j * n + i;
-  // no explicit i-j coefficients: the stock default for this style is geometric mixing (mix_flag = GEOMETRIC)
+  // no explicit i-j coefficients: Pair::mix_energy / mix_distance [UPSTREAM] with `pair_modify mix` (stock default of
+  // this style: geometric)
   if (!setflag[ij]) {
     if (!setflag[i * n + i] || !setflag[j * n + j]) error->all(FLERR, "All pair coeffs are not set");
     epsilon[ij] = std::sqrt(epsilon[i * n + i] * epsilon[j * n + j]);
-    sigma[ij] = std::sqrt(sigma[i * n + i] * sigma[j * n + j]);
+    sigma[ij] = mix_flag == ARITHMETIC ? 0.5 * (sigma[i * n + i] + sigma[j * n + j])
+                                       : std::sqrt(sigma[i * n + i] * sigma[j * n + j]);
     k.cut_lj[ij] = std::max(k.cut_lj[i * n + i], k.cut_lj[j * n + j]);
     setflag[ij] = 1;
   }
@@ -102,6 +104,12 @@ void *PairLJLongCoulLong::extract(const char *str, int &dim) {
   dim = 0;
   if (std::strcmp(str, "cut_coul") == 0) return &cut_coul;
   if (std::strcmp(str, "ewald_order") == 0) return &ewald_order;
+  if (std::strcmp(str, "ewald_mix") == 0) return &mix_flag;
+  dim = 2;   // [(ntypes+1)^2] matrices read by PPPMDisp::init_coeffs
+  if (std::strcmp(str, "B") == 0) return k.c.data();          // lj4 = 4 eps sigma^6
+  if (std::strcmp(str, "epsilon") == 0) return epsilon.data();
+  if (std::strcmp(str, "sigma") == 0) return sigma.data();
+  dim = 0;
   return nullptr;
 }
 

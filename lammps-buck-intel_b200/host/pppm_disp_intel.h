@@ -1,7 +1,7 @@
 // pppm_disp_intel.h — KSpaceStyle(pppm/disp/intel,PPPMDispIntel) on the device (pppm_disp_intel.h:18-40 of the
-// reference).  Of the four "functions" of PPPMDisp the reference accelerates the Coulomb grid ('c') and the
-// geometric-mixing dispersion grid ('g') (pppm_disp_intel.cpp:183-313); those are the two provided here.  Arithmetic
-// mixing (7 grids) and no-mixing are out of scope, as in SURVEY §2.1-6.
+// reference).  All four "functions" of PPPMDisp::compute run on the device: the Coulomb grid ('c') and the
+// geometric-mixing dispersion grid ('g') the reference accelerates itself (pppm_disp_intel.cpp:183-313), and the
+// arithmetic-mixing (seven grids, :315-407) and no-mixing (:409-467) branches it leaves to the stock members.
 #pragma once
 #include "pppm_intel.h"
 
@@ -14,7 +14,10 @@ class PPPMDispIntel : public PPPM {
   void setup() override;
   void compute(int eflag, int vflag) override;
   int function[4] = {0, 0, 0, 0};   // Coulomb, geometric, arithmetic, none
-  std::vector<double> B;            // geometric mixing: B[type] = sqrt(|C_ii|)
+  int disp_rule() const { return function[1] ? 1 : (function[2] ? 2 : (function[3] ? 3 : 0)); }
+  // PPPMDisp::init_coeffs: geometric B[type] = sqrt(|C_ii|); arithmetic B[7 type + k]; none: the C_ij matrix itself
+  // (its eigen-split is done behind b200md_pppm_setup)
+  std::vector<double> B;
   double csum = 0.0, csumij = 0.0, cutoff_lj = 0.0;
   double lj_rspace_error(double g6) const;
 

@@ -23,6 +23,13 @@ void KSpace::modify_params(int narg, char **arg) {
       nx_pppm = std::atoi(arg[i + 1]); ny_pppm = std::atoi(arg[i + 2]); nz_pppm = std::atoi(arg[i + 3]);
       gridflag = (nx_pppm || ny_pppm || nz_pppm) ? 1 : 0;
       i += 4;
+    } else if (!std::strcmp(arg[i], "mix/disp") && i + 1 < narg) {
+      // KSpace::modify_params [UPSTREAM]: which of PPPMDisp's dispersion functions serves the pair style
+      if (!std::strcmp(arg[i + 1], "pair")) mixflag = 0;
+      else if (!std::strcmp(arg[i + 1], "geom")) mixflag = 1;
+      else if (!std::strcmp(arg[i + 1], "none")) mixflag = 2;
+      else error->all(FLERR, "Illegal kspace_modify command");
+      i += 2;
     } else if (!std::strcmp(arg[i], "mesh/disp") && i + 3 < narg) {
       nx_pppm_6 = std::atoi(arg[i + 1]); ny_pppm_6 = std::atoi(arg[i + 2]); nz_pppm_6 = std::atoi(arg[i + 3]);
       gridflag_6 = (nx_pppm_6 || ny_pppm_6 || nz_pppm_6) ? 1 : 0;

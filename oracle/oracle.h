@@ -144,6 +144,13 @@ orc_pppm *orc_pppm_create_disp(int nx, int ny, int nz, int order, double g_ewald
 /* the same grid with kspace_modify diff ad (fieldforce_g_ad, compute_sf_coeff_6 [UPSTREAM]) */
 orc_pppm *orc_pppm_create_disp_ad(int nx, int ny, int nz, int order, double g_ewald_6, int diff_ad,
                                   const double *boxlo, const double *boxhi, int prec);
+/* PPPMDispIntel::compute function[2] / function[3] (pppm_disp_intel.cpp:315-467 + stock PPPMDisp members): arithmetic
+ * mixing on seven coupled grids, w7[n][7] = B[7 type + k]; no mixing rule on nsplit eigen-grids,
+ * wn[n][nsplit] = B[nsplit type + k], lam[nsplit] the eigenvalues.  p from orc_pppm_create_disp[_ad]. */
+void orc_pppm_compute_arith(orc_pppm *p, int nlocal, const double *x, const double *w7, int eflag, int vflag, double *f,
+                            double *energy, double *virial, int nthreads);
+void orc_pppm_compute_none(orc_pppm *p, int nlocal, const double *x, int nsplit, const double *wn, const double *lam,
+                           int eflag, int vflag, double *f, double *energy, double *virial, int nthreads);
 /* kspace_modify slab: mesh over zprd * slab_volfactor, PPPM::slabcorr applied (pppm_intel.cpp:305); z non-periodic */
 orc_pppm *orc_pppm_create_slab(int nx, int ny, int nz, int order, double g_ewald, int diff_ad, const double *boxlo,
                                const double *boxhi, double qqrd2e, int prec, double slab_volfactor);

@@ -799,8 +799,10 @@ struct orc_pppm {
     }
   }
 
+  // selfc (mixed dispersion grids only): per-atom coefficient of the self-force term in place of 2 q^2
   template <class flt_t>
-  void fieldforce_ad(int nlocal, const std::vector<flt_t> &x, const std::vector<flt_t> &q, double *f) {
+  void fieldforce_ad(int nlocal, const std::vector<flt_t> &x, const std::vector<flt_t> &q, double *f,
+                     const double *selfc = nullptr) {
     const flt_t ftwo_pi = MY_PI * 2.0, ffour_pi = MY_PI * 4.0;
     const flt_t lo0 = boxlo[0], lo1 = boxlo[1], lo2 = boxlo[2];
     const flt_t xi = delxinv, yi = delyinv, zi = delzinv;
@@ -851,7 +853,7 @@ struct orc_pppm {
       eky *= hy_inv;
       ekz *= hz_inv;
       const flt_t qfactor = fqqrd2es * q[i];
-      const flt_t twoqsq = (flt_t)2.0 * q[i] * q[i];
+      const flt_t twoqsq = selfc ? (flt_t)selfc[i] : (flt_t)2.0 * q[i] * q[i];
       const flt_t s1 = x[3 * (size_t)i] * hx_inv;
       const flt_t s2 = x[3 * (size_t)i + 1] * hy_inv;
       const flt_t s3 = x[3 * (size_t)i + 2] * hz_inv;
@@ -974,6 +976,203 @@ struct orc_pppm {
     }
     return 0;
   }
+
+  // ---- PPPMDispIntel::compute, function[2] (arithmetic mixing, pppm_disp_intel.cpp:315-407) and function[3] (no mixing
+  // rule, :409-467).  The members it calls - make_rho_a / _none, brick2fft_a / _none, poisson_2s_ik / _ad,
+  // poisson_none_ik / _ad, fieldforce_a_ik / _ad, fieldforce_none_ik / _ad - are stock PPPMDisp [UPSTREAM, restated]:
+  // the reference calls them through its base class and does not ship them.  Pinned by known-answer tests
+  // (tests/test_oracle_kat.py: the split of the r^-6 lattice sum must not depend on g_ewald_6, equal-sigma arithmetic
+  // mixing equals geometric mixing, a rank-one coefficient matrix equals geometric mixing).
+
+  // stock PPPMDisp::poisson_2s_ik / poisson_2s_ad: two real densities ride in ONE complex transform (real and imaginary
+  // part) and come back as the real and imaginary part of the inverse transforms.  When energy or virial are wanted
+  // they are transformed separately first and the cross term 2 s2 G Re(D1 conj D2) is tallied.
+  void poisson_2s(const std::vector<double> &d1, const std::vector<double> &d2, int eflag_global, int vflag_global,
+                  int nthr, std::vector<double> *b1, std::vector<double> *b2) {
+    const double scaleinv = 1.0 / ((double)nx_pppm * ny_pppm * nz_pppm);
+    if (!(eflag_global || vflag_global)) {
+      for (long i = 0; i < nfft; i++) {
+        work1[2 * i] = d1[i];
+        work1[2 * i + 1] = d2[i];
+      }
+      orc_fft3d(work1.data(), nx_pppm, ny_pppm, nz_pppm, 1, nthr);
+    } else {
+      for (long i = 0; i < nfft; i++) {
+        work1[2 * i] = d1[i];
+        work1[2 * i + 1] = 0.0;
+        work2[2 * i] = 0.0;
+        work2[2 * i + 1] = d2[i];
+      }
+      orc_fft3d(work1.data(), nx_pppm, ny_pppm, nz_pppm, 1, nthr);
+      orc_fft3d(work2.data(), nx_pppm, ny_pppm, nz_pppm, 1, nthr);
+      const double s2 = scaleinv * scaleinv;
+      long n = 0;
+      for (long i = 0; i < nfft; i++) {
+        const double eng = 2.0 * s2 * greensfn[i] * (work1[n] * work2[n + 1] - work1[n + 1] * work2[n]);
+        if (vflag_global)
+          for (int j = 0; j < 6; j++) virial[j] += eng * vg[6 * i + j];
+        if (eflag_global) energy += eng;
+        n += 2;
+      }
+      for (long i = 0; i < 2 * nfft; i++) work1[i] += work2[i];
+    }
+    for (long i = 0; i < nfft; i++) {
+      work1[2 * i] *= scaleinv * greensfn[i];
+      work1[2 * i + 1] *= scaleinv * greensfn[i];
+    }
+    const int nb = diff_ad ? 1 : 3;
+    for (int d = 0; d < nb; d++) {
+      long n = 0;
+      for (int k = 0; k < nz_pppm; k++)
+        for (int j = 0; j < ny_pppm; j++)
+          for (int i = 0; i < nx_pppm; i++) {
+            if (diff_ad) {
+              work2[n] = work1[n];
+              work2[n + 1] = work1[n + 1];
+            } else {
+              const double fk = d == 0 ? fkx[i] : (d == 1 ? fky[j] : fkz[k]);
+              work2[n] = fk * work1[n + 1];
+              work2[n + 1] = -fk * work1[n];
+            }
+            n += 2;
+          }
+      orc_fft3d(work2.data(), nx_pppm, ny_pppm, nz_pppm, -1, nthr);
+      b1[d].assign(ngrid, 0.0);
+      b2[d].assign(ngrid, 0.0);
+      n = 0;
+      for (int k = 0; k < nz_pppm; k++)
+        for (int j = 0; j < ny_pppm; j++)
+          for (int i = 0; i < nx_pppm; i++) {
+            b1[d][bidx(k, j, i)] = work2[n];
+            b2[d][bidx(k, j, i)] = work2[n + 1];
+            n += 2;
+          }
+    }
+  }
+
+  void disp_post(double csum, double csumij, int eflag_global, int vflag_global, double *energy_out,
+                 double *virial_out) {
+    // pppm_disp_intel.cpp:486-510
+    const double g3 = g_ewald * g_ewald * g_ewald;
+    if (eflag_global) {
+      energy *= 0.5 * volume;
+      energy += -MY_PI * MY_PIS / (6.0 * volume) * g3 * csumij + 1.0 / 12.0 * g3 * g3 * csum;
+      if (energy_out) *energy_out = energy;
+    }
+    if (vflag_global) {
+      const double a = MY_PI * MY_PIS / (6.0 * volume) * g3 * csumij;
+      for (int i = 0; i < 6; i++) virial[i] = 0.5 * volume * virial[i];
+      for (int i = 0; i < 3; i++) virial[i] -= a;
+      if (virial_out) for (int i = 0; i < 6; i++) virial_out[i] = virial[i];
+    }
+  }
+
+  // w7[n][7] = B[7 * type + k] (PPPMDisp::init_coeffs, arithmetic): C_ij = sum_k B_i[k] B_j[6 - k]
+  template <class flt_t>
+  int compute_arith(int nlocal, const double *xd, const double *w7, int eflag, int vflag, double *f,
+                    double *energy_out, double *virial_out, int nthr) {
+    const int eflag_global = eflag & 1, vflag_global = vflag & 3;
+    energy = 0.0;
+    for (int i = 0; i < 6; i++) virial[i] = 0.0;
+    std::vector<flt_t> x(3 * (size_t)nlocal), q(nlocal);
+    for (size_t i = 0; i < 3 * (size_t)nlocal; i++) x[i] = (flt_t)xd[i];
+    if (particle_map<flt_t>(nlocal, x, nthr)) return 1;
+    // make_rho_a, reverse_comm(REVERSE_RHO_A), brick2fft_a: seven densities
+    std::vector<double> dfft[7];
+    for (int k = 0; k < 7; k++) {
+      for (int i = 0; i < nlocal; i++) q[i] = (flt_t)w7[7 * (size_t)i + k];
+      make_rho<flt_t>(nlocal, x, q, nthr);
+      reverse_comm_rho();
+      brick2fft();
+      dfft[k] = density_fft;
+    }
+    const int nb = diff_ad ? 1 : 3;
+    std::vector<double> br[7][3];
+    // a3 couples with itself: poisson_ik / poisson_ad
+    density_fft = dfft[3];
+    if (diff_ad) {
+      poisson_ad(eflag_global, vflag_global, nthr);
+      br[3][0] = u_brick;
+    } else {
+      poisson_ik(eflag_global, vflag_global, nthr);
+      br[3][0] = vdx_brick; br[3][1] = vdy_brick; br[3][2] = vdz_brick;
+    }
+    // (a0,a6), (a1,a5), (a2,a4): poisson_2s_ik / poisson_2s_ad
+    for (int k = 0; k < 3; k++) poisson_2s(dfft[k], dfft[6 - k], eflag_global, vflag_global, nthr, br[k], br[6 - k]);
+    for (int k = 0; k < 7; k++)
+      for (int d = 0; d < nb; d++) forward_comm(br[k][d]);
+    // fieldforce_a_ik / fieldforce_a_ad: lj_k = B[7 type + 6 - k] multiplies the field of grid k; the ad self force
+    // carries 4 lj0 lj6 + 4 lj1 lj5 + 4 lj2 lj4 + 2 lj3 lj3
+    std::vector<double> selfc(nlocal, 0.0), zero(nlocal, 0.0);
+    double csum = 0.0, colsum[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < nlocal; i++) {
+      double cii = 0.0;
+      for (int k = 0; k < 7; k++) {
+        cii += w7[7 * (size_t)i + k] * w7[7 * (size_t)i + 6 - k];
+        colsum[k] += w7[7 * (size_t)i + k];
+      }
+      selfc[i] = 2.0 * cii;
+      csum += cii;
+    }
+    for (int k = 0; k < 7; k++) {
+      for (int i = 0; i < nlocal; i++) q[i] = (flt_t)w7[7 * (size_t)i + 6 - k];
+      if (diff_ad) {
+        u_brick.swap(br[k][0]);
+        fieldforce_ad<flt_t>(nlocal, x, q, f, k == 0 ? selfc.data() : zero.data());
+        u_brick.swap(br[k][0]);
+      } else {
+        vdx_brick.swap(br[k][0]); vdy_brick.swap(br[k][1]); vdz_brick.swap(br[k][2]);
+        fieldforce_ik<flt_t>(nlocal, x, q, f, nthr);
+        vdx_brick.swap(br[k][0]); vdy_brick.swap(br[k][1]); vdz_brick.swap(br[k][2]);
+      }
+    }
+    double csumij = 0.0;
+    for (int k = 0; k < 7; k++) csumij += colsum[k] * colsum[6 - k];
+    disp_post(csum, csumij, eflag_global, vflag_global, energy_out, virial_out);
+    return 0;
+  }
+
+  // wn[n][nsplit] = B[nsplit * type + k], lam[nsplit] (the eigenvalues PPPMDisp::init_coeffs keeps in the row of type 0):
+  // C_ij = sum_k lam_k B_i[k] B_j[k]
+  template <class flt_t>
+  int compute_none(int nlocal, const double *xd, int nsplit, const double *wn, const double *lam, int eflag, int vflag,
+                   double *f, double *energy_out, double *virial_out, int nthr) {
+    const int eflag_global = eflag & 1, vflag_global = vflag & 3;
+    std::vector<flt_t> x(3 * (size_t)nlocal), q(nlocal);
+    for (size_t i = 0; i < 3 * (size_t)nlocal; i++) x[i] = (flt_t)xd[i];
+    if (particle_map<flt_t>(nlocal, x, nthr)) return 1;
+    double etot = 0.0, vtot[6] = {0, 0, 0, 0, 0, 0}, csum = 0.0, csumij = 0.0;
+    std::vector<double> selfc(nlocal, 0.0);
+    for (int k = 0; k < nsplit; k++) {
+      double colsum = 0.0;
+      for (int i = 0; i < nlocal; i++) {
+        const double w = wn[(size_t)nsplit * i + k];
+        q[i] = (flt_t)w;
+        colsum += w;
+        csum += lam[k] * w * w;
+        selfc[i] = 2.0 * lam[k] * w * w;
+      }
+      csumij += lam[k] * colsum * colsum;
+      make_rho<flt_t>(nlocal, x, q, nthr);   // make_rho_none, one grid at a time
+      reverse_comm_rho();
+      brick2fft();
+      energy = 0.0;
+      for (int i = 0; i < 6; i++) virial[i] = 0.0;
+      if (diff_ad) poisson_ad(eflag_global, vflag_global, nthr);   // poisson_none_ad / _ik: weight B[k] = lam_k
+      else poisson_ik(eflag_global, vflag_global, nthr);
+      etot += lam[k] * energy;
+      for (int i = 0; i < 6; i++) vtot[i] += lam[k] * virial[i];
+      if (diff_ad) forward_comm(u_brick);
+      else { forward_comm(vdx_brick); forward_comm(vdy_brick); forward_comm(vdz_brick); }
+      for (int i = 0; i < nlocal; i++) q[i] = (flt_t)(lam[k] * wn[(size_t)nsplit * i + k]);
+      if (diff_ad) fieldforce_ad<flt_t>(nlocal, x, q, f, selfc.data());   // fieldforce_none_ad / _ik
+      else fieldforce_ik<flt_t>(nlocal, x, q, f, nthr);
+    }
+    energy = etot;
+    for (int i = 0; i < 6; i++) virial[i] = vtot[i];
+    disp_post(csum, csumij, eflag_global, vflag_global, energy_out, virial_out);
+    return 0;
+  }
 };
 
 extern "C" {
@@ -1073,6 +1272,25 @@ void orc_pppm_compute(orc_pppm *p, int nlocal, const double *x, const double *q,
   int rc;
   if (p->prec == ORC_PREC_DOUBLE) rc = p->compute<double>(nlocal, x, q, eflag, vflag, f, energy, virial, nthreads);
   else rc = p->compute<float>(nlocal, x, q, eflag, vflag, f, energy, virial, nthreads);
+  if (rc) std::fprintf(stderr, "oracle: Out of range atoms - cannot compute PPPM\n");
+}
+/* dispersion grid with arithmetic mixing (seven coupled grids) / without a mixing rule (nsplit eigen-grids); p from
+ * orc_pppm_create_disp[_ad].  w7[n][7] = B[7 type + k]; wn[n][nsplit] = B[nsplit type + k], lam = eigenvalues. */
+void orc_pppm_compute_arith(orc_pppm *p, int nlocal, const double *x, const double *w7, int eflag, int vflag, double *f,
+                            double *energy, double *virial, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  int rc;
+  if (p->prec == ORC_PREC_DOUBLE) rc = p->compute_arith<double>(nlocal, x, w7, eflag, vflag, f, energy, virial, nthreads);
+  else rc = p->compute_arith<float>(nlocal, x, w7, eflag, vflag, f, energy, virial, nthreads);
+  if (rc) std::fprintf(stderr, "oracle: Out of range atoms - cannot compute PPPM\n");
+}
+void orc_pppm_compute_none(orc_pppm *p, int nlocal, const double *x, int nsplit, const double *wn, const double *lam,
+                           int eflag, int vflag, double *f, double *energy, double *virial, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  int rc;
+  if (p->prec == ORC_PREC_DOUBLE)
+    rc = p->compute_none<double>(nlocal, x, nsplit, wn, lam, eflag, vflag, f, energy, virial, nthreads);
+  else rc = p->compute_none<float>(nlocal, x, nsplit, wn, lam, eflag, vflag, f, energy, virial, nthreads);
   if (rc) std::fprintf(stderr, "oracle: Out of range atoms - cannot compute PPPM\n");
 }
 void orc_pppm_peratom(const orc_pppm *p, double *eatom, double *vatom) {

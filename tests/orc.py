@@ -336,6 +336,31 @@ class PPPM:
         self._n = n
         return f, e.value, v
 
+    def compute_arith(self, x, w7, eflag=1, vflag=1, nthreads=0):
+        """function[2], arithmetic mixing: w7[n,7] = B[7 type + k] (disp_B_arithmetic(...)[type])"""
+        n = len(x)
+        f = np.zeros((n, 3))
+        e = C.c_double(0.0)
+        v = np.zeros(6)
+        w7 = f64(w7)
+        assert w7.shape == (n, 7)
+        lib().orc_pppm_compute_arith(self.h, C.c_int(n), _d(f64(x)), _d(w7), C.c_int(eflag), C.c_int(vflag),
+                                     _d(f), C.byref(e), _d(v), C.c_int(nthreads))
+        return f, e.value, v
+
+    def compute_none(self, x, wn, lam, eflag=1, vflag=1, nthreads=0):
+        """function[3], no mixing rule: wn[n,nsplit] = B[nsplit type + k], lam[nsplit] eigenvalues"""
+        n = len(x)
+        f = np.zeros((n, 3))
+        e = C.c_double(0.0)
+        v = np.zeros(6)
+        wn = f64(wn)
+        lam = f64(lam)
+        assert wn.shape == (n, len(lam))
+        lib().orc_pppm_compute_none(self.h, C.c_int(n), _d(f64(x)), C.c_int(len(lam)), _d(wn), _d(lam), C.c_int(eflag),
+                                    C.c_int(vflag), _d(f), C.byref(e), _d(v), C.c_int(nthreads))
+        return f, e.value, v
+
     def peratom(self, eatom=True, vatom=True):
         """per-atom tallies of the last compute (eflag & 2 / vflag & 4)"""
         e = np.zeros(self._n) if eatom else None
@@ -362,6 +387,33 @@ class PPPM:
         a = np.zeros(self.order * self.order); b = np.zeros(self.order * self.order)
         lib().orc_pppm_rho_coeff(self.h, _d(a), _d(b))
         return a.reshape(self.order, self.order), b.reshape(self.order, self.order)
+
+
+def disp_B_arithmetic(epsilon, sigma):
+    """PPPMDisp::init_coeffs, function[2] [UPSTREAM, restated]: B[7 i + k] = sqrt(eps_i) / 4 * sqrt(binom(6,k)) *
+    sigma_i^k for type i = 0..ntypes (epsilon[0], sigma[0] unused), so that sum_k B_i[k] B_j[6-k] = 4 sqrt(eps_i eps_j)
+    ((sigma_i + sigma_j) / 2)^6 = lj4_ij of pair lj/long/coul/long with `pair_modify mix arithmetic`.  The prefactor is
+    fixed by that identity (the r^-6 lattice sum must not depend on g_ewald_6, tests/test_oracle_kat.py)."""
+    eps = f64(epsilon)
+    sig = f64(sigma)
+    c = np.sqrt([1.0, 6.0, 15.0, 20.0, 15.0, 6.0, 1.0])
+    B = np.zeros((len(eps), 7))
+    for i in range(len(eps)):
+        B[i] = np.sqrt(eps[i]) / 4.0 * c * sig[i] ** np.arange(7)
+    return B
+
+
+def disp_B_none(Cij):
+    """PPPMDisp::init_coeffs, function[3] [UPSTREAM, restated]: eigen-decomposition of the symmetric r^-6 coefficient
+    matrix of types 1..ntypes, C = V diag(lam) V^T; returns (B[ntypes+1, nsplit] with B[i, k] = V[i-1, k], lam[nsplit]);
+    eigenvalues below 1e-12 max|lam| are dropped."""
+    Cij = f64(Cij)
+    lam, V = np.linalg.eigh(Cij[1:, 1:])
+    keep = np.abs(lam) > 1e-12 * np.abs(lam).max()
+    lam, V = lam[keep], V[:, keep]
+    B = np.zeros((Cij.shape[0], len(lam)))
+    B[1:] = V
+    return B, lam
 
 
 def pppm_size(accuracy_relative, qqrd2e, qsqsum, natoms, cutoff, prd, order=5, grid=(0, 0, 0), g_ewald=0.0,

@@ -83,6 +83,26 @@ run {steps}
 """
 
 
+# lj/long/coul/long long long + pppm/disp with arithmetic mixing (PPPMDisp function[0] + function[2]) or, with
+# `kspace_modify mix/disp none`, the no-mixing-rule branch (function[3]) on data.aC's two atom types
+IN_LJ_DISP_MIX = """units metal
+atom_style charge
+read_data data.aC
+pair_style lj/long/coul/long long long 9.0
+pair_coeff 1 1 0.008 2.9
+pair_coeff 2 2 0.021 3.3
+pair_modify mix arithmetic table 0 table/disp 0
+kspace_style pppm/disp 1e-4
+kspace_modify mesh 24 24 27 gewald 0.28 mesh/disp 30 30 32 gewald/disp 0.31 order/disp 5 {mixdisp}
+neighbor 0.3 bin
+neigh_modify delay 0 every 1 check yes
+velocity all create 300.0 1281937
+fix 1 all nve
+thermo {thermo}
+run {steps}
+"""
+
+
 def write_data_aC(W, path):
     x, t, q, lo, hi = W.data_aC()
     with open(path, "w") as fh:

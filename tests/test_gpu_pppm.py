@@ -242,6 +242,53 @@ def _resident(ctx, s):
 
 
 @pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("ad", [0, 1])
+@pytest.mark.parametrize("rule", ["arithmetic", "none"])
+def test_pppm_disp_arithmetic_and_no_mixing_match_oracle(pkg, W, orc, rule, ad, prec):
+    """PPPMDispIntel::compute function[2] (arithmetic mixing, seven coupled grids, pppm_disp_intel.cpp:315-407) and
+    function[3] (no mixing rule, eigen-grids, :409-467): the device runs them as signed self-coupled components of the
+    one-density kernels; forces, energy and virial against the oracle's restatement of the coupled-grid algorithm
+    (make_rho_a / poisson_2s_ik|ad / fieldforce_a_ik|ad and the _none members), ik and ad, with and without the
+    energy / virial tallies"""
+    s = W.aC_system(1)
+    eps = np.array([0.0, 0.8, 2.1]); sig = np.array([0.0, 2.9, 3.6])
+    Cij = 4.0 * np.sqrt(np.outer(eps, eps)) * ((sig[:, None] + sig[None, :]) / 2.0) ** 6
+    g6, grid, order = 0.31, (30, 30, 32), 5
+    ctx = pkg.make_context(s, precision=prec)
+    ctx.neigh_setup(0.3)
+    pp = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], prec=prec, diff_ad=ad)
+    if rule == "arithmetic":
+        B7 = orc.disp_B_arithmetic(eps, sig)
+        ctx.pppm_setup(*grid, order, g6, dispersion=2, B=B7, differentiation=ad)
+        fo, eo, vo = pp.compute_arith(s["x"], B7[s["type"]])
+    else:
+        Cn = Cij.copy()
+        Cn[1, 2] = Cn[2, 1] = 0.7 * Cij[1, 2]          # not expressible by any mixing rule
+        Bn, lam = orc.disp_B_none(Cn)
+        ctx.pppm_setup(*grid, order, g6, dispersion=3, B=Cn, differentiation=ad)
+        fo, eo, vo = pp.compute_none(s["x"], Bn[s["type"]], lam)
+    f, e, v = _resident(ctx, s)
+    # seven grids whose contributions largely cancel: 1e-8 of the largest force in double mode
+    tol_f, tol_e = (1e-8, 1e-10) if prec == 0 else (2e-5, 1e-5)
+    assert np.abs(f - fo).max() <= tol_f * np.abs(fo).max()
+    assert abs(e - eo) <= tol_e * abs(eo)
+    assert np.abs(v - vo).max() <= tol_e * np.abs(vo).max()
+    # without the tallies the forces are the same bits
+    ctx.atoms_upload(s["x"], s["type"], s["mass"], v=s.get("v"), q=s.get("q"))
+    ctx.pppm_compute(0, 0)
+    assert np.array_equal(ctx.atoms_download(("f",))["f"], f)
+    # Coulomb grid + mixed dispersion grid in one compute (function[0] + function[2|3]): the sums
+    u = W.UNITS["metal"]
+    ctx.pppm_setup(24, 24, 27, 5, 0.28, differentiation=ad)
+    f2, e2, v2 = _resident(ctx, s)
+    fc, ec, vc = orc.PPPM(24, 24, 27, 5, 0.28, s["boxlo"], s["boxhi"], u["qqrd2e"], prec=prec, diff_ad=ad).compute(
+        s["x"], s["q"])
+    assert np.abs(f2 - (fo + fc)).max() <= 2 * tol_f * np.abs(fo + fc).max()
+    assert abs(e2 - (eo + ec)) <= 2 * tol_e * abs(eo + ec)
+    ctx.close()
+
+
+@pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("order", [5, 3, 7])
 def test_pppm_disp_geometric_matches_oracle(pkg, W, orc, order, prec):
     """PPPMDispIntel 'g' grid (pppm_disp_intel.cpp:245-313 with the per-atom weight B[type]):

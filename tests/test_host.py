@@ -95,6 +95,54 @@ def test_dry_run_slab_sizing_and_boundary_checks(pkg, W, tmp_path):
     assert out.returncode != 0 and "Cannot use nonperiodic boundaries with PPPM" in out.stdout + out.stderr
 
 
+def test_dispersion_grid_components(pkg, orc):
+    """csrc/pppm.cu disp_components (host side of b200md_pppm_setup): the signed self-coupled components a dispersion
+    grid is run as reproduce the r^-6 coefficient of every type pair, sum_m sign_m W_m[i] W_m[j] = C_ij -
+    geometric (one), arithmetic (seven: the coupled grids a_k, a_{6-k} rotated into p, m = (a_k +- a_{6-k}) / sqrt 2),
+    none (cyclic-Jacobi eigen-split, checked against numpy's eigh)"""
+    import ctypes as C
+    lib = pkg.load()
+    lib.b200md_debug_disp_components.restype = C.c_int
+    dp = C.POINTER(C.c_double)
+
+    def comps(mix, T, B):
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        W = np.zeros(16 * (T + 1)); sg = np.zeros(16)
+        n = lib.b200md_debug_disp_components(C.c_int(mix), C.c_int(T), B.ctypes.data_as(dp), W.ctypes.data_as(dp),
+                                             sg.ctypes.data_as(dp))
+        assert n > 0, n
+        return W[:n * (T + 1)].reshape(n, T + 1), sg[:n]
+
+    rng = np.random.default_rng(5)
+    for T in (1, 2, 3, 5, 8):
+        eps = np.concatenate([[0.0], rng.uniform(0.05, 2.0, T)])
+        sig = np.concatenate([[0.0], rng.uniform(1.5, 4.0, T)])
+        Bg = 2.0 * np.sqrt(eps) * sig ** 3
+        W, sg = comps(1, T, Bg)
+        assert W.shape == (1, T + 1) and np.array_equal(W[0], Bg) and sg[0] == 1.0
+        B7 = orc.disp_B_arithmetic(eps, sig)
+        W, sg = comps(2, T, B7)
+        assert len(sg) == 7 and list(sg) == [1, 1, 1, 1, -1, -1, -1]
+        Cl = 4.0 * np.sqrt(np.outer(eps, eps)) * ((sig[:, None] + sig[None, :]) / 2.0) ** 6
+        Cw = np.einsum("m,mi,mj->ij", sg, W, W)
+        assert np.allclose(Cw[1:, 1:], Cl[1:, 1:], rtol=1e-12, atol=1e-12 * Cl.max())
+        # no mixing rule: a random symmetric (indefinite) matrix
+        A = rng.normal(size=(T, T)); A = A + A.T
+        Cn = np.zeros((T + 1, T + 1)); Cn[1:, 1:] = A
+        W, sg = comps(3, T, Cn)
+        Cw = np.einsum("m,mi,mj->ij", sg, W, W)
+        assert np.allclose(Cw, Cn, rtol=0, atol=1e-12 * np.abs(A).max())
+        lam = np.linalg.eigvalsh(A)
+        assert sorted(np.round(sg * (W * W).sum(1), 9)) == sorted(np.round(lam, 9))   # |W_m|^2 sign_m = eigenvalue m
+    # rank-deficient: one eigen-grid; asymmetric input is refused
+    b = np.array([0.0, 9.0, 13.2])
+    W, sg = comps(3, 2, np.outer(b, b))
+    assert len(sg) == 1 and np.allclose(np.abs(W[0]), b, rtol=1e-12)
+    bad = np.outer(b, b); bad[1, 2] += 1.0
+    assert lib.b200md_debug_disp_components(C.c_int(3), C.c_int(2), bad.ctypes.data_as(dp), np.zeros(64).ctypes.data_as(dp),
+                                            np.zeros(16).ctypes.data_as(dp)) < 0
+
+
 @pytest.mark.parametrize("order", [1, 2, 3, 4, 5, 6, 7])
 def test_tiled_make_rho_plan(pkg, order):
     """host-side plan of the tiled charge assignment (csrc/pppm.cu: rho_lane_map, cover_table): every stencil-face
@@ -259,6 +307,32 @@ def test_buck_long_coul_long_with_pppm_disp(pkg, W, orc, tmp_path):
     fk, ek, vk = pp.compute(s["x"], B[s["type"]])
     assert th[0, 2] == pytest.approx(ev[0] + ek, rel=1e-9)
     assert np.abs(th[:, 4] - th[0, 4]).max() < 5e-4 * abs(th[0, 4])   # stiff, strongly compressed system
+
+
+@pytest.mark.gpu
+def test_lj_long_coul_long_with_pppm_disp_arithmetic_and_none(pkg, W, orc, tmp_path):
+    """lj/long/coul/long long long with `pair_modify mix arithmetic` + pppm/disp through the driver: PPPMDispIntel::init
+    picks function[2] (ewald_mix = ARITHMETIC), `kspace_modify mix/disp none` function[3]; step-0 E_pair against the
+    oracle's pair + Coulomb PPPM + seven-grid dispersion PPPM.  Both rules see the same C_ij, so their energies agree."""
+    e_pair = {}
+    for rule, mixdisp in (("arithmetic", ""), ("none", "mix/disp none")):
+        txt = scripts.IN_LJ_DISP_MIX.format(mixdisp=mixdisp, steps=4, thermo=2)
+        r = _run(pkg, ["-in", scripts.write(tmp_path, "in.ljmix", txt, W), "-sf", "intel"])
+        assert r.returncode == 0, r.stdout + r.stderr
+        e_pair[rule] = _thermo(r.stdout)[0, 2]
+    s = W.aC_system(1, jitter=0.0)
+    u = W.UNITS["metal"]
+    eps = np.array([0.0, 0.008, 0.021]); sig = np.array([0.0, 2.9, 3.3])
+    e_ij = np.sqrt(np.outer(eps, eps)); s_ij = (sig[:, None] + sig[None, :]) / 2.0
+    P = orc.Params(orc.LJ_LONG_COUL_LONG, 2, e_ij, s_ij, np.zeros((3, 3)), np.full((3, 3), 9.0), np.full((3, 3), 9.0),
+                   qqrd2e=u["qqrd2e"], g_ewald=0.28, g_ewald_6=0.31, order1=1, order6=1)   # A = epsilon, rho = sigma
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    fc, ec, vc = orc.PPPM(24, 24, 27, 5, 0.28, s["boxlo"], s["boxhi"], u["qqrd2e"]).compute(s["x"], s["q"])
+    B7 = orc.disp_B_arithmetic(eps, sig)
+    fd, ed, vd = orc.PPPM.dispersion(30, 30, 32, 5, 0.31, s["boxlo"], s["boxhi"]).compute_arith(s["x"], B7[s["type"]])
+    want = ev[0] + ev[1] + ec + ed
+    assert e_pair["arithmetic"] == pytest.approx(want, rel=1e-9)
+    assert e_pair["none"] == pytest.approx(want, rel=1e-9)
 
 
 @pytest.mark.gpu

@@ -300,6 +300,91 @@ def test_dispersion_grid_ad_differentiation_converges_to_ik(orc, W):
     assert np.abs(fc_a - fc_i).max() > 10 * np.abs(fa - fi).max()
 
 
+def _lb_matrix(eps, sig):
+    """lj4_ij = 4 eps_ij sigma_ij^6 with Lorentz-Berthelot mixing (pair lj/long/coul/long, mix arithmetic)"""
+    return 4.0 * np.sqrt(np.outer(eps, eps)) * ((sig[:, None] + sig[None, :]) / 2.0) ** 6
+
+
+def _mixed_total(orc, s, Cij, g6, kspace, rc=11.0, grid=(54, 54, 60), order=7):
+    """real space (buck/long/coul/long ORDER6 with A = 0: only -C_ij/r^6) + the k-space part given by kspace(pp)"""
+    A = np.zeros((3, 3)); rho = np.ones((3, 3))
+    P = orc.Params(orc.BUCK_LONG_COUL_LONG, 2, A, rho, Cij, np.full((3, 3), rc), np.full((3, 3), rc), qqrd2e=14.399645,
+                   g_ewald_6=g6, order6=1)
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 0.3)
+    pp = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"])
+    fk, ek, vk = kspace(pp)
+    return f[:, :3] + fk, ev[0] + ek, ev[2:] + vk
+
+
+def test_arithmetic_mixing_coefficients(orc):
+    """PPPMDisp::init_coeffs, function[2] restated: sum_k B_i[k] B_j[6-k] is lj4_ij of Lorentz-Berthelot mixing"""
+    eps = np.array([0.0, 0.8, 2.1, 0.05]); sig = np.array([0.0, 2.9, 3.6, 1.7])
+    B7 = orc.disp_B_arithmetic(eps, sig)
+    C = np.einsum("ik,jk->ij", B7, B7[:, ::-1])
+    assert np.allclose(C[1:, 1:], _lb_matrix(eps, sig)[1:, 1:], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("ad", [0, 1])
+def test_arithmetic_mixing_with_equal_sigma_is_geometric_mixing(orc, W, ad):
+    """function[2] (seven coupled grids, poisson_2s) against function[1] (one grid): with one sigma for every type
+    C_ij = B_i B_j, B_i = 2 sqrt(eps_i) sigma^3, and both paths must give the same energy, virial and forces"""
+    s = W.aC_system(1)
+    eps = np.array([0.0, 0.8, 2.1]); sig = np.array([0.0, 3.1, 3.1])
+    B7 = orc.disp_B_arithmetic(eps, sig)
+    Bg = 2.0 * np.sqrt(eps) * sig ** 3
+    grid, order, g6 = (24, 24, 27), 5, 0.30
+    fa, ea, va = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], diff_ad=ad).compute_arith(s["x"], B7[s["type"]])
+    fg, eg, vg = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], diff_ad=ad).compute(s["x"], Bg[s["type"]])
+    assert ea == pytest.approx(eg, rel=1e-11)
+    assert np.allclose(va, vg, rtol=0, atol=1e-11 * np.abs(vg).max())
+    assert np.abs(fa - fg).max() <= 2e-9 * np.abs(fg).max()   # seven grids whose contributions largely cancel
+    # without energy / virial poisson_2s packs two densities into one transform: same forces
+    fa0 = orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], diff_ad=ad).compute_arith(
+        s["x"], B7[s["type"]], eflag=0, vflag=0)[0]
+    assert np.abs(fa0 - fa).max() <= 2e-9 * np.abs(fa).max()
+
+
+@pytest.mark.parametrize("ad", [0, 1])
+def test_no_mixing_rule_on_the_arithmetic_matrix_equals_arithmetic_mixing(orc, W, ad):
+    """function[3] (eigen-grids of C_ij) fed with the Lorentz-Berthelot matrix against function[2] (seven grids): two
+    different decompositions of the same coefficients; and a rank-one matrix reduces to geometric mixing"""
+    s = W.aC_system(1)
+    eps = np.array([0.0, 0.8, 2.1]); sig = np.array([0.0, 2.9, 3.6])
+    B7 = orc.disp_B_arithmetic(eps, sig)
+    Bn, lam = orc.disp_B_none(_lb_matrix(eps, sig))
+    assert len(lam) == 2 and lam.min() < 0 < lam.max()      # indefinite: a negative eigen-grid is exercised
+    grid, order, g6 = (24, 24, 27), 5, 0.30
+    mk = lambda: orc.PPPM.dispersion(*grid, order, g6, s["boxlo"], s["boxhi"], diff_ad=ad)
+    fa, ea, va = mk().compute_arith(s["x"], B7[s["type"]])
+    fn, en, vn = mk().compute_none(s["x"], Bn[s["type"]], lam)
+    assert en == pytest.approx(ea, rel=1e-10)
+    assert np.allclose(vn, va, rtol=0, atol=1e-10 * np.abs(va).max())
+    assert np.abs(fn - fa).max() <= 2e-9 * np.abs(fa).max()
+    Bg = np.array([0.0, 9.0, 13.2])
+    B1, lam1 = orc.disp_B_none(np.outer(Bg, Bg))
+    assert len(lam1) == 1
+    f1, e1, v1 = mk().compute_none(s["x"], B1[s["type"]], lam1)
+    fg, eg, vg = mk().compute(s["x"], Bg[s["type"]])
+    assert e1 == pytest.approx(eg, rel=1e-11) and np.abs(f1 - fg).max() <= 1e-11 * np.abs(fg).max()
+    assert np.allclose(v1, vg, rtol=0, atol=1e-11 * np.abs(vg).max())
+
+
+def test_arithmetic_mixing_ewald_is_independent_of_g_ewald_6(orc, W):
+    """function[2] + the ORDER6 real space with lj4_ij of Lorentz-Berthelot mixing: the split parameter drops out of
+    energy, forces and virial - this fixes the absolute scale of B[7 i + k] (a wrong prefactor leaves a g-dependent
+    remainder) - and the virial trace of an r^-6 potential is 6 E"""
+    s = W.aC_system(1)
+    eps = np.array([0.0, 0.8, 2.1]); sig = np.array([0.0, 2.9, 3.6])
+    Cij = _lb_matrix(eps, sig)
+    w7 = orc.disp_B_arithmetic(eps, sig)[s["type"]]
+    f1, e1, v1 = _mixed_total(orc, s, Cij, 0.28, lambda pp: pp.compute_arith(s["x"], w7))
+    f2, e2, v2 = _mixed_total(orc, s, Cij, 0.36, lambda pp: pp.compute_arith(s["x"], w7))
+    assert e1 == pytest.approx(e2, rel=2e-6)
+    assert np.abs(f1 - f2).max() <= 2e-5 * np.abs(f1).max()
+    assert np.allclose(v1, v2, rtol=0, atol=2e-5 * np.abs(v1).max())
+    assert v1[0] + v1[1] + v1[2] == pytest.approx(6.0 * e1, rel=2e-5)
+
+
 def test_nve_group_branch_freezes_atoms_outside_the_group(orc):
     """FixNVEIntel with igroup != all (fix_nve_intel.cpp:88-97, 173-190): dtfm is 0 outside the group and those
     atoms keep x and v; inside, v += dtf/m f and x += dt v with rmass overriding the per-type mass"""
