@@ -134,7 +134,11 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p);
  * nspecial[n][3] holds LAMMPS's cumulative counts (partners [0,n0) are 1-2, [n0,n1) 1-3, [n1,n2) 1-4), special[n][maxspecial]
  * the partners as 0-based upload indices; both in upload order.  Call after b200md_atoms_upload; NULL clears.  Flagged
  * pairs stay in the list whatever their factor (stock drops factor-0 pairs when no k-space style is defined: forces are
- * identical, the pair set is not).  One GPU only (the arrays are indexed by upload position); maxspecial <= 32. */
+ * identical, the pair set is not).  maxspecial <= 32.
+ * Several GPUs: collective (every rank calls it with the rows of its own upload and the same maxspecial); the partners
+ * are GLOBAL ids - rank r's k-th uploaded atom has id (atoms uploaded by ranks < r) + k, what b200md_atoms_download_ids
+ * reports.  The rows are gathered into one table indexed by global id on every rank (12 + 4 maxspecial bytes per atom
+ * of the whole system), so they follow atoms that migrate between the ranks; halo atoms carry their ids. */
 int b200md_atoms_set_special(b200md_ctx *ctx, int maxspecial, const int *nspecial, const int *special);
 
 /* ------------------------------------------------------------------------------------------------
@@ -225,7 +229,8 @@ int b200md_nve_setup(b200md_ctx *ctx, double dt);
  * FixNVEIntel::reset_dt (fix_nve_intel.cpp:147-190: _dtfm = 0 outside the group) and the `_dtfm[i] != 0.0` branch of
  * initial_integrate (:88-97: atoms outside the group keep x and v).  ingroup[n] (0 / non-zero) and rmass[n] are in
  * upload order; either may be NULL (group all / per-type mass).  Call after b200md_atoms_upload and before
- * b200md_nve_setup.  One GPU only (the arrays are indexed by upload position). */
+ * b200md_nve_setup.  Several GPUs: collective, every rank passes the rows of its own upload (the same arrays NULL /
+ * non-NULL on every rank); they are gathered into tables indexed by global id. */
 int b200md_nve_set_group(b200md_ctx *ctx, const int *ingroup, const double *rmass);
 int b200md_nve_initial_integrate(b200md_ctx *ctx);
 int b200md_nve_final_integrate(b200md_ctx *ctx);

@@ -93,6 +93,20 @@ int b2_comm_allgather_int(b200md_ctx *ctx, int value, int *host_out) {
   return 0;
 }
 
+// every rank contributes `bytes[rank]` bytes at displacement disp[rank] of recv (device memory, may be the buffer the
+// contribution already sits in): one broadcast per contributing rank inside a group
+int b2_comm_allgatherv(b200md_ctx *ctx, const void *send, void *recv, const size_t *bytes, const size_t *disp) {
+  CommState *cs = ctx->comm;
+  if (!cs) return 0;
+  NCCL_OK(ctx, ncclGroupStart());
+  for (int r = 0; r < cs->nranks; r++)
+    if (bytes[r])
+      NCCL_OK(ctx, ncclBroadcast(r == cs->rank ? send : (const char *)recv + disp[r], (char *)recv + disp[r], bytes[r],
+                                 ncclChar, r, cs->comm, ctx->stream));
+  NCCL_OK(ctx, ncclGroupEnd());
+  return 0;
+}
+
 // all-to-all with per-peer element counts (bytes) and displacements: the FFT transposes
 int b2_comm_alltoallv(b200md_ctx *ctx, const void *sbuf, const size_t *scount, const size_t *sdisp, void *rbuf,
                       const size_t *rcount, const size_t *rdisp) {

@@ -207,7 +207,7 @@ void b200md_ctx_destroy(b200md_ctx *ctx) {
   ns.gbin.free_(); ns.gperm.free_(); ns.bin_count.free_(); ns.bin_start.free_(); ns.bin_end.free_(); ns.bin_cursor.free_();
   ns.perm.free_(); ns.ghost_src.free_(); ns.ghost_shift.free_(); ns.ghost_cnt.free_();
   ns.numneigh.free_(); ns.offsets.free_(); ns.entries.free_(); ns.mask_words.free_(); ns.mask_off.free_(); ns.maskbuf.free_();
-  ns.halo_idx.free_(); ns.halo_sbuf.free_(); ns.halo_rbuf.free_(); ns.halo_stype.free_(); ns.halo_rtype.free_();
+  ns.halo_idx.free_(); ns.halo_sbuf.free_(); ns.halo_rbuf.free_(); ns.halo_stype.free_(); ns.halo_rtype.free_(); ns.halo_stag.free_(); ns.halo_rtag.free_();
   ns.mig_flag.free_(); ns.mig_off.free_(); ns.mig_send.free_(); ns.mig_recv.free_(); ns.xhold.free_(); ns.flags.free_();
   ns.scan_ws.free_(); ns.tmp4a.free_(); ns.tmp4b.free_(); ns.tmpi_a.free_(); ns.tmpi_b.free_();
   harvest_timers(ctx);

@@ -105,6 +105,7 @@ struct NeighState {
   int ns_lo = 0, ns_hi = 0, nr_lo = 0, nr_hi = 0;   // sent to lower/upper, received from lower/upper
   DevBuf<double4> halo_sbuf, halo_rbuf;             // rbuf = [from lower | from upper]
   DevBuf<int> halo_stype, halo_rtype;
+  DevBuf<int> halo_stag, halo_rtag;   // global ids of the halo atoms (exchanged at a rebuild when special bonds are set)
   DevBuf<int> mig_flag, mig_off;                    // migration scratch: 3 flag / 3 offset arrays
   DevBuf<unsigned char> mig_send, mig_recv;
   double slab_lo = 0, slab_hi = 0;                  // this rank's z slab
@@ -130,10 +131,11 @@ struct b200md_ctx {
   int device = 0;
   int prec = B200MD_PREC_DOUBLE;
   cudaStream_t stream = nullptr;
-  DevBuf<int> sp_count, sp_list;   // special bonds, upload order: [n][3] cumulative counts, [n][sp_max] partner ids
+  // special bonds, indexed by global id (= upload index on one GPU): [N][3] cumulative counts, [N][sp_max] partner ids
+  DevBuf<int> sp_count, sp_list;
   int sp_max = 0;                  // 0: atomic system, lists carry no special bits
-  DevBuf<int> nve_group;       // fix nve on a sub-group: 0 / 1 per atom, upload order (b200md_nve_set_group)
-  DevBuf<double> nve_rmass;    // per-atom masses, upload order
+  DevBuf<int> nve_group;       // fix nve on a sub-group: 0 / 1 per atom, by global id (b200md_nve_set_group)
+  DevBuf<double> nve_rmass;    // per-atom masses, by global id
   bool nve_grouped = false, nve_has_rmass = false;
   cudaStream_t copy_stream = nullptr;   // device->host copies that overlap the force kernels (b200md_step_host)
   cudaEvent_t ev_copy = nullptr;
@@ -284,6 +286,8 @@ int b2_comm_exchange_counts(b200md_ctx *ctx, int n_lo, int n_hi, int *n_from_hi,
 int b2_comm_allreduce_sum(b200md_ctx *ctx, double *dev, int n);
 int b2_comm_allreduce_max_int(b200md_ctx *ctx, int *dev, int n);
 int b2_comm_allgather_int(b200md_ctx *ctx, int value, int *host_out /*[nranks]*/);
+int b2_comm_allgatherv(b200md_ctx *ctx, const void *send, void *recv, const size_t *bytes, const size_t *disp);
+
 // grouped point-to-point calls (one NCCL group): several messages per peer are matched in issue order
 struct CommGroup {
   b200md_ctx *ctx;
@@ -309,3 +313,27 @@ int b2_comm_peer_alloc(b200md_ctx *ctx, PeerBuf &pb, size_t bytes, int *ok);
 void b2_comm_peer_free(b200md_ctx *ctx, PeerBuf &pb);
 // stream-ordered barrier over the ranks: returns (on the stream) once every rank has reached it
 int b2_comm_barrier(b200md_ctx *ctx);
+
+// Per-atom host array of this rank's upload (`per` elements per atom, upload order) -> device table of ALL atoms
+// indexed by global id (= upload index on one GPU).  Tables indexed this way stay valid when atoms migrate between the
+// ranks.  Collective on several GPUs (every rank calls it, also with no atoms); *nglobal receives the atom count.
+template <class T>
+inline int b2_atoms_global_table(b200md_ctx *ctx, const T *host_rows, size_t per, DevBuf<T> &table, long *nglobal) {
+  const int P = b2_comm_nranks(ctx), me = b2_comm_rank(ctx);
+  std::vector<int> counts(P, ctx->nlocal);
+  if (P > 1) TRY(b2_comm_allgather_int(ctx, ctx->nlocal, counts.data()));
+  std::vector<size_t> bytes(P), disp(P);
+  size_t tot = 0;
+  for (int r = 0; r < P; r++) {
+    disp[r] = tot * per * sizeof(T);
+    bytes[r] = (size_t)counts[r] * per * sizeof(T);
+    tot += (size_t)counts[r];
+  }
+  RESERVE(ctx, table, tot * per + 1);
+  if (ctx->nlocal > 0)
+    CUDA_OK(ctx, cudaMemcpyAsync((char *)table.p + disp[me], host_rows, bytes[me], cudaMemcpyHostToDevice, ctx->stream));
+  if (P > 1) TRY(b2_comm_allgatherv(ctx, (char *)table.p + disp[me], table.p, bytes.data(), disp.data()));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nglobal) *nglobal = (long)tot;
+  return 0;
+}

@@ -269,6 +269,11 @@ __global__ void k_compact_idx(int n, const int *__restrict__ flag, const int *__
   if (i < n && flag[i]) out[off[i]] = i;
 }
 
+__global__ void k_gather_int(int n, const int *__restrict__ idx, const int *__restrict__ src, int *__restrict__ dst) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[idx[k]];
+}
+
 __global__ void k_halo_pack(int ns, const int *__restrict__ idx, const double4 *__restrict__ xq, double zshift,
                             double4 *__restrict__ sbuf, const int *__restrict__ type, int *__restrict__ stype) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -620,12 +625,14 @@ k_nb_fill(int nlocal, const int *__restrict__ type, const int *__restrict__ lsta
 
 // Special bonds (molecular systems): a warp takes an atom that has special partners, keeps their ids one per lane and
 // scans its row; an entry whose partner's id matches gets the partner's class (1-2, 1-3, 1-4) in bits 30-31 — what stock
-// Neighbor writes from atom->special / nspecial (consumed at pair_buck_coul_long_intel.cpp:283).  Ids are upload
-// indices: tag[] of an owned atom, tag[ghost_src[]] of a periodic image.
+// Neighbor writes from atom->special / nspecial (consumed at pair_buck_coul_long_intel.cpp:283).  Ids are global ids
+// (upload indices on one GPU): tag[] of an owned atom, tag[ghost_src[]] of a periodic image, halo_tag[] of an atom (or
+// image of an atom) received from a neighbour rank; the tables are indexed by global id.
 __global__ void __launch_bounds__(128)
 k_nb_mark_special(int nlocal, const int *__restrict__ tag, const int *__restrict__ ghost_src,
-                  const int *__restrict__ numneigh, const long long *__restrict__ offsets, int *__restrict__ entries,
-                  int idxmask, const int *__restrict__ sp_count, const int *__restrict__ sp_list, int sp_max) {
+                  const int *__restrict__ halo_tag, const int *__restrict__ numneigh,
+                  const long long *__restrict__ offsets, int *__restrict__ entries, int idxmask,
+                  const int *__restrict__ sp_count, const int *__restrict__ sp_list, int sp_max) {
   const int lane = threadIdx.x & 31;
   const int i = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (i >= nlocal) return;
@@ -642,7 +649,7 @@ k_nb_mark_special(int nlocal, const int *__restrict__ tag, const int *__restrict
       e = row[k];
       const int j = e & idxmask;
       const int o = j < nlocal ? j : ghost_src[j - nlocal];
-      tj = o >= 0 ? tag[o] : -2;
+      tj = o >= 0 ? tag[o] : (halo_tag ? halo_tag[-1 - o] : -2);   // halo atom of a neighbour rank: its global id
     }
     int which = 0;
     for (int s = 0; s < ns; s++) {
@@ -892,6 +899,18 @@ int halo_exchange(b200md_ctx *ctx, int with_type) {
     TRY(b2_comm_exchange(ctx, ns.halo_stype.p, (size_t)ns.ns_lo * sizeof(int), ns.halo_stype.p + ns.ns_lo,
                          (size_t)ns.ns_hi * sizeof(int), ns.halo_rtype.p + ns.nr_lo, (size_t)ns.nr_hi * sizeof(int),
                          ns.halo_rtype.p, (size_t)ns.nr_lo * sizeof(int)));
+  if (with_type && ctx->sp_max > 0) {   // molecular systems: the halo atoms' global ids, for the special-bond marks
+    const int nsend = ns.ns_lo + ns.ns_hi;
+    RESERVE(ctx, ns.halo_stag, (size_t)nsend + 64);
+    RESERVE(ctx, ns.halo_rtag, (size_t)ns.nr_lo + ns.nr_hi + 64);
+    if (nsend > 0) {
+      k_gather_int<<<cdiv(nsend, 256), 256, 0, ctx->stream>>>(nsend, ns.halo_idx.p, ctx->tag.p, ns.halo_stag.p);
+      KERNEL_OK(ctx, "k_gather_int");
+    }
+    TRY(b2_comm_exchange(ctx, ns.halo_stag.p, (size_t)ns.ns_lo * sizeof(int), ns.halo_stag.p + ns.ns_lo,
+                         (size_t)ns.ns_hi * sizeof(int), ns.halo_rtag.p + ns.nr_lo, (size_t)ns.nr_hi * sizeof(int),
+                         ns.halo_rtag.p, (size_t)ns.nr_lo * sizeof(int)));
+  }
   return 0;
 }
 
@@ -1140,9 +1159,8 @@ int b2_neigh_build(b200md_ctx *ctx) {
     clk.mark("fill");
   }
   if (ctx->sp_max > 0 && n > 0) {
-    if (b2_comm_nranks(ctx) > 1) return b2_fail(ctx, B200MD_EINVAL, "special bonds are single-GPU only in this build");
     k_nb_mark_special<<<cdiv((long)n * 32, 128), 128, 0, ctx->stream>>>(
-        n, ctx->tag.p, ns.ghost_src.p, ns.numneigh.p, ns.offsets.p, ns.entries.p,
+        n, ctx->tag.p, ns.ghost_src.p, multi ? ns.halo_rtag.p : nullptr, ns.numneigh.p, ns.offsets.p, ns.entries.p,
         ns.packed_type ? B2_IDXMASK26 : B2_NEIGHMASK, ctx->sp_count.p, ctx->sp_list.p, ctx->sp_max);
     KERNEL_OK(ctx, "k_nb_mark_special");
   }

@@ -143,7 +143,7 @@ int b2_kinetic_energy(b200md_ctx *ctx, double *ke) {
   RESERVE(ctx, ctx->ev_partial, (size_t)nb + 1);
   if (nb > 0) {
     k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->nlocal, ctx->v.p, ctx->type.p, dmass, ctx->ev_partial.p, ctx->tag.p,
-                                              ctx->first_id, ctx->nve_has_rmass ? ctx->nve_rmass.p : nullptr);
+                                              0 /* global ids */, ctx->nve_has_rmass ? ctx->nve_rmass.p : nullptr);
     KERNEL_OK(ctx, "k_ke_partial");
   }
   k_sum1<<<1, 256, 0, ctx->stream>>>(nb, ctx->ev_partial.p, ctx->ev_out.p + 8);
@@ -180,7 +180,7 @@ int b200md_nve_setup(b200md_ctx *ctx, double dt) {
     double *dmass;
     TRY(upload_mass(ctx, &dmass));
     k_nve_set_dtfm<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(
-        ctx->nlocal, ctx->type.p, dmass, ctx->dtf, ctx->v.p, ctx->tag.p, ctx->first_id,
+        ctx->nlocal, ctx->type.p, dmass, ctx->dtf, ctx->v.p, ctx->tag.p, 0 /* tables are indexed by global id */,
         ctx->nve_grouped ? ctx->nve_group.p : nullptr, ctx->nve_has_rmass ? ctx->nve_rmass.p : nullptr);
     KERNEL_OK(ctx, "k_nve_set_dtfm");
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -192,23 +192,29 @@ int b200md_nve_setup(b200md_ctx *ctx, double dt) {
 int b200md_nve_set_group(b200md_ctx *ctx, const int *ingroup, const double *rmass) {
   if (!ctx) return B200MD_EINVAL;
   cudaSetDevice(ctx->device);
-  if ((ingroup || rmass) && b2_comm_nranks(ctx) > 1)
-    return b2_fail(ctx, B200MD_EINVAL, "fix nve on a sub-group / with per-atom masses is single-GPU only in this build");
   const size_t n = (size_t)ctx->nlocal;
-  ctx->nve_grouped = ingroup != nullptr && n > 0;
-  ctx->nve_has_rmass = rmass != nullptr && n > 0;
+  const bool multi = b2_comm_nranks(ctx) > 1;
+  // several GPUs: collective, every rank passes the same kind of arrays (a rank without atoms may pass any non-NULL
+  // pointer); the tables are gathered over the ranks and indexed by global id, so they follow migrating atoms
+  ctx->nve_grouped = ingroup != nullptr && (n > 0 || multi);
+  ctx->nve_has_rmass = rmass != nullptr && (n > 0 || multi);
   ctx->nve_ready = false;   // _dtfm has to be rebuilt (reset_dt)
   if (ctx->nve_grouped) {
-    std::vector<int> g(n);
+    std::vector<int> g(n + 1);
     for (size_t i = 0; i < n; i++) g[i] = ingroup[i] ? 1 : 0;
-    RESERVE(ctx, ctx->nve_group, n);
-    CUDA_OK(ctx, cudaMemcpy(ctx->nve_group.p, g.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    TRY(b2_atoms_global_table<int>(ctx, g.data(), 1, ctx->nve_group, nullptr));
   }
   if (ctx->nve_has_rmass) {
+    int bad = 0;
     for (size_t i = 0; i < n; i++)
-      if (!(rmass[i] > 0.0)) return b2_fail(ctx, B200MD_EINVAL, "per-atom mass must be positive");
-    RESERVE(ctx, ctx->nve_rmass, n);
-    CUDA_OK(ctx, cudaMemcpy(ctx->nve_rmass.p, rmass, n * sizeof(double), cudaMemcpyHostToDevice));
+      if (!(rmass[i] > 0.0)) bad = 1;
+    if (multi) {   // agree on the verdict before the collective gather
+      std::vector<int> all(b2_comm_nranks(ctx));
+      TRY(b2_comm_allgather_int(ctx, bad, all.data()));
+      for (int v : all) bad |= v;
+    }
+    if (bad) return b2_fail(ctx, B200MD_EINVAL, "per-atom mass must be positive");
+    TRY(b2_atoms_global_table<double>(ctx, rmass, 1, ctx->nve_rmass, nullptr));
   }
   return 0;
 }
@@ -221,21 +227,43 @@ int b200md_atoms_set_special(b200md_ctx *ctx, int maxspecial, const int *nspecia
     ctx->sp_max = 0;
     return 0;
   }
-  if (b2_comm_nranks(ctx) > 1) return b2_fail(ctx, B200MD_EINVAL, "special bonds are single-GPU only in this build");
-  if (maxspecial > 32) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: maxspecial %d > 32", maxspecial);
+  const bool multi = b2_comm_nranks(ctx) > 1;
   const size_t n = (size_t)ctx->nlocal;
-  for (size_t i = 0; i < n; i++) {
-    const int a = nspecial[3 * i], b = nspecial[3 * i + 1], c = nspecial[3 * i + 2];
-    if (a < 0 || b < a || c < b || c > maxspecial)
-      return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: bad cumulative counts for atom %zu", i);
-    for (int k = 0; k < c; k++)
-      if (special[i * maxspecial + k] < 0 || (size_t)special[i * maxspecial + k] >= n)
-        return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: partner %d of atom %zu is not an atom", k, i);
+  // several GPUs: collective; partner ids are GLOBAL ids (b200md_atoms_download_ids), every rank passes the rows of its
+  // own upload and the same maxspecial
+  long nglobal = (long)n;
+  int bad = maxspecial > 32 ? 1 : 0;
+  if (multi) {
+    std::vector<int> all(b2_comm_nranks(ctx));
+    TRY(b2_comm_allgather_int(ctx, ctx->nlocal, all.data()));
+    nglobal = 0;
+    for (int v : all) nglobal += v;
+    TRY(b2_comm_allgather_int(ctx, maxspecial, all.data()));
+    for (int v : all)
+      if (v != maxspecial) bad = 2;
   }
-  RESERVE(ctx, ctx->sp_count, 3 * n + 1);
-  RESERVE(ctx, ctx->sp_list, n * (size_t)maxspecial + 1);
-  CUDA_OK(ctx, cudaMemcpy(ctx->sp_count.p, nspecial, 3 * n * sizeof(int), cudaMemcpyHostToDevice));
-  CUDA_OK(ctx, cudaMemcpy(ctx->sp_list.p, special, n * (size_t)maxspecial * sizeof(int), cudaMemcpyHostToDevice));
+  size_t bad_atom = 0;
+  if (!bad)
+    for (size_t i = 0; i < n && !bad; i++) {
+      const int a = nspecial[3 * i], b = nspecial[3 * i + 1], c = nspecial[3 * i + 2];
+      if (a < 0 || b < a || c < b || c > maxspecial) { bad = 3; bad_atom = i; break; }
+      for (int k = 0; k < c; k++)
+        if (special[i * maxspecial + k] < 0 || (long)special[i * maxspecial + k] >= nglobal) { bad = 4; bad_atom = i; break; }
+    }
+  if (multi) {
+    std::vector<int> all(b2_comm_nranks(ctx));
+    const int mine = bad;
+    TRY(b2_comm_allgather_int(ctx, mine, all.data()));
+    for (int v : all)
+      if (v && !bad) bad = 5;
+  }
+  if (bad == 1) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: maxspecial %d > 32", maxspecial);
+  if (bad == 2) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: maxspecial differs between the ranks");
+  if (bad == 3) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: bad cumulative counts for atom %zu", bad_atom);
+  if (bad == 4) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: a partner of atom %zu is not an atom", bad_atom);
+  if (bad) return b2_fail(ctx, B200MD_EINVAL, "b200md_atoms_set_special: rejected on another rank");
+  TRY(b2_atoms_global_table<int>(ctx, nspecial, 3, ctx->sp_count, nullptr));
+  TRY(b2_atoms_global_table<int>(ctx, special, (size_t)maxspecial, ctx->sp_list, nullptr));
   ctx->sp_max = maxspecial;
   return 0;
 }
