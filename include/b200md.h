@@ -84,6 +84,14 @@ int b200md_set_units(b200md_ctx *ctx, double qqrd2e, double ftm2v);
 int b200md_set_box(b200md_ctx *ctx, const double boxlo[3], const double boxhi[3],
                    const int periodic[3]);
 
+/* triclinic box: domain->triclinic with the tilt factors xy, xz, yz (Domain::h), fully periodic.  Only the k-space
+ * solver works on it - b200md_pppm_setup / b200md_pppm_compute / b200md_pppm_compute_host, i.e. PPPMIntel::compute
+ * with its x2lamda / lamda2x bracket (pppm_intel.cpp:151-156, 307-309) and the poisson_ik_triclinic branch (:878-883),
+ * ik differentiation, Coulomb grid, one GPU; neighbour lists and pair styles need an orthogonal box.  Positions stay
+ * in box coordinates at the boundary.  b200md_set_box returns to an orthogonal box. */
+int b200md_set_box_triclinic(b200md_ctx *ctx, const double boxlo[3], const double boxhi[3], double xy, double xz,
+                             double yz);
+
 /* ------------------------------------------------------------------------------------------------
  * atoms — replaces IntelBuffers::thr_pack (intel_buffers.h:185-203): one upload, then resident.
  * q may be NULL (atom_style atomic), v may be NULL (zeros).  mass is per type [ntypes+1]. */

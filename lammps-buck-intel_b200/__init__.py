@@ -455,6 +455,11 @@ class Context:
     def set_box(self, boxlo, boxhi, periodic=(1, 1, 1)):
         self._ck(self.lib.b200md_set_box(self.h, _d(f64(boxlo)), _d(f64(boxhi)), _i(i32(periodic))))
 
+    def set_box_triclinic(self, boxlo, boxhi, tilt):
+        """triclinic box, tilt = (xy, xz, yz): k-space solver only (pppm_setup / pppm_compute / pppm_compute_host)"""
+        self._ck(self.lib.b200md_set_box_triclinic(self.h, _d(f64(boxlo)), _d(f64(boxhi)), C.c_double(tilt[0]),
+                                                   C.c_double(tilt[1]), C.c_double(tilt[2])))
+
     def atoms_upload(self, x, type_, mass, v=None, q=None):
         x = f64(x); v = f64(v); q = f64(q); type_ = i32(type_); mass = f64(mass)
         self.nlocal = len(x)

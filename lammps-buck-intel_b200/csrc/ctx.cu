@@ -244,6 +244,23 @@ int b200md_set_box(b200md_ctx *ctx, const double boxlo[3], const double boxhi[3]
   }
   ctx->box_set = true;
   ctx->neigh.ready = false;
+  ctx->triclinic = false;
+  ctx->tilt[0] = ctx->tilt[1] = ctx->tilt[2] = 0.0;
+  return 0;
+}
+
+int b200md_set_box_triclinic(b200md_ctx *ctx, const double boxlo[3], const double boxhi[3], double xy, double xz,
+                             double yz) {
+  if (!ctx) return B200MD_EINVAL;
+  if (!std::isfinite(xy) || !std::isfinite(xz) || !std::isfinite(yz))
+    return b2_fail(ctx, B200MD_ENONFINITE, "Non-numeric box dimensions - simulation unstable");
+  const int periodic[3] = {1, 1, 1};
+  TRY(b200md_set_box(ctx, boxlo, boxhi, periodic));
+  // Domain::set_initial_box [UPSTREAM]: a tilt beyond half a box length is refused
+  if (std::fabs(xy / ctx->prd[0]) > 0.5 || std::fabs(xz / ctx->prd[0]) > 0.5 || std::fabs(yz / ctx->prd[1]) > 0.5)
+    return b2_fail(ctx, B200MD_EINVAL, "Triclinic box skew is too large");
+  ctx->triclinic = xy != 0.0 || xz != 0.0 || yz != 0.0;
+  ctx->tilt[0] = xy; ctx->tilt[1] = xz; ctx->tilt[2] = yz;
   return 0;
 }
 

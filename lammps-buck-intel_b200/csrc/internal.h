@@ -151,6 +151,9 @@ struct b200md_ctx {
   double qqrd2e = 1.0, ftm2v = 1.0;
   double boxlo[3] = {0, 0, 0}, boxhi[3] = {1, 1, 1}, prd[3] = {1, 1, 1};
   int periodic[3] = {1, 1, 1};
+  // triclinic box (b200md_set_box_triclinic): tilt factors xy, xz, yz.  Only the k-space solver works on it.
+  bool triclinic = false;
+  double tilt[3] = {0, 0, 0};
   bool box_set = false;
 
   int nlocal = 0, nghost = 0, ntypes = 0;

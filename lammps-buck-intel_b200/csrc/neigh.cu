@@ -954,6 +954,9 @@ int b2_neigh_build(b200md_ctx *ctx) {
   ctx->ev_pre_valid = false;
   if (!ctx->box_set) return b2_fail(ctx, B200MD_EINVAL, "neighbour build before b200md_set_box");
   if (!ctx->pair.ready) return b2_fail(ctx, B200MD_EINVAL, "neighbour build before b200md_pair_setup");
+  if (ctx->triclinic)
+    return b2_fail(ctx, B200MD_EINVAL, "triclinic boxes: only the k-space solver (b200md_pppm_setup / compute) is "
+                                       "provided; neighbour lists and pair styles need an orthogonal box");
   ScopedTimer tm(ctx, T_NEIGH);
   BinGeom g;
   TRY(make_geom(ctx, g));

@@ -95,6 +95,53 @@ __global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, int yoff, int ny
   greensfn[n] = g;
 }
 
+// PPPM::compute_gf_ik_triclinic [UPSTREAM] (what PPPM::setup_triclinic calls for the box of pppm_intel.cpp:878-883): the
+// wave vectors and their aliases go through Domain::x2lamdaT, the assignment-function factors stay per lamda axis
+__device__ __forceinline__ void d_x2lamdaT(const PppmConst &c, double a, double b, double cc, double &ox, double &oy,
+                                           double &oz) {
+  ox = c.hinv[0] * a;
+  oy = c.hinv[5] * a + c.hinv[1] * b;
+  oz = c.hinv[4] * a + c.hinv[3] * b + c.hinv[2] * cc;
+}
+__global__ void k_gf_ik_tri(PppmConst c, int nbx, int nby, int nbz, double *__restrict__ greensfn) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nfft = (long)c.nx * c.ny * c.nz;
+  if (n >= nfft) return;
+  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
+  const double snx = d_square(sin(kPI * kper / c.nx)), sny = d_square(sin(kPI * lper / c.ny)),
+               snz = d_square(sin(kPI * mper / c.nz));
+  double ux, uy, uz;
+  d_x2lamdaT(c, k2PI * kper, k2PI * lper, k2PI * mper, ux, uy, uz);
+  const double sqk = ux * ux + uy * uy + uz * uz;
+  double g = 0.0;
+  if (sqk != 0.0) {
+    const double numerator = 12.5663706 / sqk;
+    const double denominator = d_gf_denom(c, snx, sny, snz);
+    const int twoorder = 2 * c.order;
+    double sum1 = 0.0;
+    for (int ax = -nbx; ax <= nbx; ax++) {
+      const double wx = d_powsinxx(kPI * kper / c.nx + kPI * ax, twoorder);
+      for (int ay = -nby; ay <= nby; ay++) {
+        const double wy = d_powsinxx(kPI * lper / c.ny + kPI * ay, twoorder);
+        for (int az = -nbz; az <= nbz; az++) {
+          const double wz = d_powsinxx(kPI * mper / c.nz + kPI * az, twoorder);
+          double bx, by, bz;
+          d_x2lamdaT(c, k2PI * c.nx * ax, k2PI * c.ny * ay, k2PI * c.nz * az, bx, by, bz);
+          const double qx = ux + bx, qy = uy + by, qz = uz + bz;
+          const double sx = exp(-0.25 * d_square(qx / c.g_ewald)), sy = exp(-0.25 * d_square(qy / c.g_ewald)),
+                       sz = exp(-0.25 * d_square(qz / c.g_ewald));
+          const double dot1 = ux * qx + uy * qy + uz * qz;
+          const double dot2 = qx * qx + qy * qy + qz * qz;
+          sum1 += (dot1 / dot2) * sx * sy * sz * wx * wy * wz;
+        }
+      }
+    }
+    g = numerator * sum1 / denominator;
+  }
+  greensfn[n] = g;
+}
+
 // PPPM::compute_sf_precoeff + the per-point part of compute_gf_ad
 // (yoff, nyl: the y rows held by this rank, [z][row][x]; the whole grid on one GPU)
 // have_g: greensfn already holds the influence function (dispersion grid: k_gf_6) and only the sums are formed
@@ -269,13 +316,24 @@ __device__ __forceinline__ double frac1(int n, float so, float x, float lo, floa
   return (double)__fsub_rn(__fadd_rn((float)n, so), __fmul_rn(__fsub_rn(x, lo), xi));
 }
 
+// Domain::x2lamda (pppm_intel.cpp:156): box -> lamda coordinates of a triclinic cell, in double; q rides along
+__device__ __forceinline__ double4 to_lamda(const PppmConst &c, const double4 p) {
+  const double dx = p.x - c.boxlo_box[0], dy = p.y - c.boxlo_box[1], dz = p.z - c.boxlo_box[2];
+  return make_double4(c.hinv[0] * dx + c.hinv[5] * dy + c.hinv[4] * dz, c.hinv[1] * dy + c.hinv[3] * dz, c.hinv[2] * dz,
+                      p.w);
+}
+
 template <class flt_t>
 __global__ void k_map_key(int n, const double4 *__restrict__ xq, const float4 *__restrict__ xqf, PppmConst c,
                           int *__restrict__ key, int *__restrict__ cell_count, int *__restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int nx, ny, nz;
-  if (sizeof(flt_t) == 4) {
+  if (c.tri) {   // lamda coordinates, rounded to flt_t like the packed positions of the orthogonal path
+    const double4 p = to_lamda(c, xq[i]);
+    if (sizeof(flt_t) == 4) map_atom<float>(c, (float)p.x, (float)p.y, (float)p.z, nx, ny, nz);
+    else map_atom<double>(c, p.x, p.y, p.z, nx, ny, nz);
+  } else if (sizeof(flt_t) == 4) {
     const float4 p = xqf[i];
     map_atom<float>(c, p.x, p.y, p.z, nx, ny, nz);
   } else {
@@ -328,7 +386,11 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
   int nx, ny, nz;
   double dx, dy, dz, w;
   if (sizeof(flt_t) == 4) {
-    const float4 p = xqf[i];
+    float4 p;
+    if (c.tri) {
+      const double4 pl = to_lamda(c, xq[i]);
+      p = make_float4((float)pl.x, (float)pl.y, (float)pl.z, (float)pl.w);
+    } else p = xqf[i];
     map_atom<float>(c, p.x, p.y, p.z, nx, ny, nz);
     const float so = (float)c.shiftone;
     dx = frac1(nx, so, p.x, (float)c.boxlo[0], (float)c.delinv[0]);
@@ -337,7 +399,7 @@ __global__ void k_fill_sorted(int n, const int *__restrict__ perm, const double4
     const float qw = Btype ? (float)Btype[type[i]] : p.w;
     w = (double)__fmul_rn((float)c.delvolinv, qw);
   } else {
-    const double4 p = xq[i];
+    const double4 p = c.tri ? to_lamda(c, xq[i]) : xq[i];
     map_atom<double>(c, p.x, p.y, p.z, nx, ny, nz);
     dx = frac1(nx, c.shiftone, p.x, c.boxlo[0], c.delinv[0]);
     dy = frac1(ny, c.shiftone, p.y, c.boxlo[1], c.delinv[1]);
@@ -699,13 +761,17 @@ k_fft_pass(FftPlan1d pl, PassGeom pg, int lgTB, int LP, const double *in_real, c
 // forward z pass + Poisson (pppm_intel.cpp:843-872) + (-i k) multiplies (:890-953) + NCOMP inverse z passes.
 // lines are along z at (y,x) = L; TB consecutive L share y (mostly) and have consecutive x.
 // NCOMP = 3: ik (E-field components), NCOMP = 1: ad (potential only).  EV: energy/virial partial sums.
+// Cross terms of the wave vector on a triclinic box (PPPM::setup_triclinic: k = x2lamdaT(2 pi per)):
+// ky += yx[ix], kz += zx[ix] + zy[iy]; yxg is yx with the Nyquist entry zeroed (gradient of the packed Ex + i Ey
+// transform, see below).  All NULL on an orthogonal box.  zy is already offset to this rank's first y row.
+struct TriWave { const double *yx, *zx, *zy, *yxg; };
 template <int NCOMP, int EV>
 __global__ void __launch_bounds__(512)
 k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
                 const double *__restrict__ fky, const double *__restrict__ fkz, const double *__restrict__ fkxg,
                 const double *__restrict__ fkyg, double scaleinv, double g_ewald, double *__restrict__ ev_partial,
-                int disp) {
+                int disp, TriWave tw) {
   extern __shared__ double2 smem[];
   const int TB = 1 << lgTB;
   const int lgtpl = 31 - __clz(blockDim.x) - lgTB;
@@ -730,15 +796,17 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
   double2 *other = (res == bufA) ? bufB : bufA;
   // Green's function multiply; energy / virial tallies
   double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const bool tri = tw.yx != nullptr;
+  const double kzb = (live && tri) ? tw.zx[ix] + tw.zy[iy] : 0.0;   // part of kz that does not depend on iz
   if (live) {
-    const double kx = fkx[ix], ky = fky[iy];
+    const double kx = fkx[ix], ky = fky[iy] + (tri ? tw.yx[ix] : 0.0);
     for (int k = k0; k < n; k += kstep) {
       const long g = L + (long)k * plane;
       const double2 w = res[t * LP + k];
       const double gf = greensfn[g];
       if (EV) {
         const double eng = scaleinv * scaleinv * gf * (w.x * w.x + w.y * w.y);
-        const double kz = fkz[k];
+        const double kz = fkz[k] + kzb;
         const double sqk = kx * kx + ky * ky + kz * kz;
         acc[0] += eng;
         if (sqk != 0.0) {  // PPPM::setup vg[][] evaluated on the fly instead of stored (6 doubles / point)
@@ -789,13 +857,15 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
   for (int comp = 0; comp < NPACK; comp++) {
     double2 *a = res, *b = other;  // V lives in bufV; a/b are free ping-pong buffers
     if (live) {
-      const double kx = NCOMP == 3 ? fkxg[ix] : 0.0, ky = NCOMP == 3 ? fkyg[iy] : 0.0;
+      // triclinic: the Hermitian part of ky = yx[ix] + fky[iy] drops BOTH Nyquist entries; Ez has its own transform
+      // whose real part is kept, exactly what stock poisson_ik_triclinic does with the raw wave vector
+      const double kx = NCOMP == 3 ? fkxg[ix] : 0.0, ky = NCOMP == 3 ? fkyg[iy] + (tri ? tw.yxg[ix] : 0.0) : 0.0;
       for (int k = k0; k < n; k += kstep) {
         const double2 v = bufV[t * LP + k];
         if (NCOMP == 1) a[t * LP + k] = v;
         else if (comp == 0) a[t * LP + k] = make_double2(kx * v.y + ky * v.x, ky * v.y - kx * v.x);
         else {
-          const double fk = fkz[k];
+          const double fk = fkz[k] + kzb;
           a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);
         }
       }
@@ -1162,7 +1232,7 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
     kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, workT, ps.workT2.p, ps.greensfn.p, \
                                              ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, ps.fkx_g.p,            \
                                              ps.fky_g.p + ps.ylos[me], scaleinv, c.g_ewald, ps.partial.p,       \
-                                             ps.p.dispersion);                                                  \
+                                             ps.p.dispersion, TriWave{nullptr, nullptr, nullptr, nullptr});     \
   } while (0)
       {
         ScopedTimer tk(ctx, K_FFT_Z_POISSON);
@@ -1458,13 +1528,15 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
     nblk_z = cdiv(plane, TB);
     const double scaleinv = 1.0 / ((double)c.nx * c.ny * c.nz);
     if (ev) RESERVE(ctx, ps.partial, (size_t)nblk_z * 8);
+    const TriWave tw = c.tri ? TriWave{ps.fkyx.p, ps.fkzx.p, ps.fkzy.p, ps.fkyx_g.p}
+                             : TriWave{nullptr, nullptr, nullptr, nullptr};
 #define ZK(NC, E)                                                                                             \
   do {                                                                                                        \
     auto kern = k_fft_z_poisson<NC, E>;                                                                       \
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, ilog2(TB), LP, ps.work1.p, ps.work2.p,          \
                                              ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, ps.fkx_g.p, ps.fky_g.p,   \
-                                             scaleinv, c.g_ewald, ps.partial.p, ps.p.dispersion);            \
+                                             scaleinv, c.g_ewald, ps.partial.p, ps.p.dispersion, tw);        \
   } while (0)
     {
       ScopedTimer tk(ctx, K_FFT_Z_POISSON);
@@ -1667,7 +1739,7 @@ static void free_state(b200md_ctx *ctx, PppmState *&slot) {
   b2_comm_peer_free(ctx, ps->symT);
   b2_comm_peer_free(ctx, ps->symW);
   for (int d = 0; d < 3; d++) ps->tw[d].free_();
-  ps->fkx_g.free_(); ps->fky_g.free_();
+  ps->fkx_g.free_(); ps->fky_g.free_(); ps->fkyx.free_(); ps->fkzx.free_(); ps->fkzy.free_(); ps->fkyx_g.free_();
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
   ps->work1.free_(); ps->work2.free_(); ps->sf_pre.free_(); ps->Btype.free_();
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
@@ -1801,6 +1873,15 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     for (int d = 0; d < 3; d++)
       if (!ctx->periodic[d]) return b2_fail(ctx, B200MD_EINVAL, "Cannot use nonperiodic boundaries with PPPM");
   }
+  // triclinic boxes (pppm_intel.cpp:151-156, 878-883): stock PPPM::init refuses what it cannot do on them
+  const bool tri = ctx->triclinic;
+  if (tri) {
+    if (p->differentiation == 1)
+      return b2_fail(ctx, B200MD_EINVAL, "Cannot (yet) use PPPM with triclinic box and kspace_modify diff ad");
+    if (slab) return b2_fail(ctx, B200MD_EINVAL, "Cannot (yet) use PPPM with triclinic box and slab correction");
+    if (p->dispersion) return b2_fail(ctx, B200MD_EINVAL, "Cannot (yet) use PPPMDisp with triclinic box");
+    if (b2_comm_nranks(ctx) > 1) return b2_fail(ctx, B200MD_EINVAL, "triclinic PPPM is single-GPU only in this build");
+  }
   PppmState *&slot = p->dispersion ? ctx->pppm6 : ctx->pppm;
   free_state(ctx, slot);
   PppmState *ps = new PppmState();
@@ -1829,6 +1910,31 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     c.hi_out[d] = nhi + c.nupper;
   }
   c.delvolinv = c.delinv[0] * c.delinv[1] * c.delinv[2];
+  c.tri = tri ? 1 : 0;
+  for (int d = 0; d < 6; d++) c.hinv[d] = 0.0;
+  for (int d = 0; d < 3; d++) c.boxlo_box[d] = ctx->boxlo[d];
+  double hmat[6] = {ctx->prd[0], ctx->prd[1], ctx->prd[2], ctx->tilt[2], ctx->tilt[1], ctx->tilt[0]};   // Domain::h
+  if (tri) {
+    // Domain::set_global_box: h_inv; PPPM::setup_triclinic: the mesh spans the unit cube of lamda coordinates;
+    // PPPM::set_grid_local: the skin enters in lamda units (KSpace::kspacebbox)
+    c.hinv[0] = 1.0 / hmat[0]; c.hinv[1] = 1.0 / hmat[1]; c.hinv[2] = 1.0 / hmat[2];
+    c.hinv[3] = -hmat[3] / (hmat[1] * hmat[2]);
+    c.hinv[4] = (hmat[3] * hmat[5] - hmat[1] * hmat[4]) / (hmat[0] * hmat[1] * hmat[2]);
+    c.hinv[5] = -hmat[5] / (hmat[0] * hmat[1]);
+    const double lx = hmat[0], ly = hmat[1], lz = hmat[2], yz = hmat[3], xz = hmat[4], xy = hmat[5];
+    const double dl[3] = {dist * std::sqrt(ly * ly * lz * lz + ly * ly * xz * xz - 2.0 * ly * xy * xz * yz +
+                                           xy * xy * yz * yz + xy * xy * lz * lz) / (lx * ly * lz),
+                          dist * std::sqrt(lz * lz + yz * yz) / (ly * lz), dist / lz};
+    for (int d = 0; d < 3; d++) {
+      c.boxlo[d] = 0.0;
+      c.delinv[d] = ng[d];
+      const int nlo = static_cast<int>((0.0 - dl[d]) * ng[d] + c.shift) - PPPM_OFFSET;
+      const int nhi = static_cast<int>((1.0 + dl[d]) * ng[d] + c.shift) - PPPM_OFFSET;
+      c.lo_out[d] = nlo + c.nlower;
+      c.hi_out[d] = nhi + c.nupper;
+    }
+    c.delvolinv = c.delinv[0] * c.delinv[1] * c.delinv[2] / (c.prd[0] * c.prd[1] * c.prd[2]);
+  }
   c.zoff = 0;
   ps->volume = c.prd[0] * c.prd[1] * c.prd[2];   // xprd * yprd * zprd_slab
   ps->zprd = ctx->prd[2];
@@ -1920,6 +2026,24 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
         CUDA_OK(ctx, cudaMemcpy(gdst.p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));
       }
     }
+    if (tri) {
+      // PPPM::setup_triclinic: k = x2lamdaT(2 pi per_i, 2 pi per_j, 2 pi per_k).  The diagonal of h_inv is 1 / prd, so
+      // fkx / fky / fkz above are its diagonal part; the off-diagonal part is three more one-dimensional arrays
+      auto per = [](int i, int n) { return (double)(i - n * (2 * i / n)); };
+      std::vector<double> yx(p->nx), zx(p->nx), zy(p->ny), yxg(p->nx);
+      for (int i = 0; i < p->nx; i++) {
+        yx[i] = c.hinv[5] * k2PI * per(i, p->nx);
+        zx[i] = c.hinv[4] * k2PI * per(i, p->nx);
+        yxg[i] = (p->nx % 2 == 0 && i == p->nx / 2) ? 0.0 : yx[i];
+      }
+      for (int j = 0; j < p->ny; j++) zy[j] = c.hinv[3] * k2PI * per(j, p->ny);
+      RESERVE(ctx, ps->fkyx, yx.size()); RESERVE(ctx, ps->fkzx, zx.size());
+      RESERVE(ctx, ps->fkzy, zy.size()); RESERVE(ctx, ps->fkyx_g, yxg.size());
+      CUDA_OK(ctx, cudaMemcpy(ps->fkyx.p, yx.data(), yx.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(ctx, cudaMemcpy(ps->fkzx.p, zx.data(), zx.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(ctx, cudaMemcpy(ps->fkzy.p, zy.data(), zy.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(ctx, cudaMemcpy(ps->fkyx_g.p, yxg.data(), yxg.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
   }
   if (p->dispersion) {
     std::vector<double> W, sg;
@@ -1932,6 +2056,16 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
     CUDA_OK(ctx, cudaMemcpy(ps->Btype.p, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (ngf == 0) {
+  } else if (tri) {
+    // compute_gf_ik_triclinic: alias counts from lamda2xT(g_ewald / (pi n) * EPS_HOC-factor)
+    const double fac = std::pow(-std::log(1.0e-7), 0.25);
+    const double t0 = (cg.g_ewald / (kPI * cg.nx)) * fac, t1 = (cg.g_ewald / (kPI * cg.ny)) * fac,
+                 t2 = (cg.g_ewald / (kPI * cg.nz)) * fac;
+    const int nbx = static_cast<int>(hmat[0] * t0);
+    const int nby = static_cast<int>(hmat[5] * t0 + hmat[1] * t1);
+    const int nbz = static_cast<int>(hmat[4] * t0 + hmat[3] * t1 + hmat[2] * t2);
+    k_gf_ik_tri<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, nbx, nby, nbz, ps->greensfn.p);
+    KERNEL_OK(ctx, "k_gf_ik_tri");
   } else if (p->dispersion && !ad) {
     k_gf_6<<<cdiv(ngf, 128), 128, 0, ctx->stream>>>(cg, gf_yoff, gf_nyl, ps->greensfn.p);
     KERNEL_OK(ctx, "k_gf_6");

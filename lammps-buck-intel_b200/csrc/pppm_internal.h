@@ -21,6 +21,10 @@ struct PppmConst {  // everything the kernels need by value
   double drho_coeff[B2_MAXORDER * B2_MAXORDER];
   double gf_b[B2_MAXORDER];
   double g_ewald;
+  // triclinic box: the mesh works in lamda (0..1) coordinates, lamda = hinv (x - boxlo_box) (Domain::x2lamda,
+  // pppm_intel.cpp:151-156); boxlo = 0 and delinv = grid size then.  hinv = Domain::h_inv (xx, yy, zz, yz, xz, xy)
+  int tri;
+  double hinv[6], boxlo_box[3];
 };
 
 struct PppmState {
@@ -31,6 +35,9 @@ struct PppmState {
   FftPlan1d plan[3];
   DevBuf<double2> tw[3];
   DevBuf<double> fkx_g, fky_g;   // gradient wave numbers: fkx/fky with the Nyquist entry zeroed (packed inverse FFT)
+  // wave vector of point (ix, iy, iz): kx = fkx[ix], ky = fky[iy] + fkyx[ix], kz = fkz[iz] + fkzx[ix] + fkzy[iy]; the
+  // cross terms are those of Domain::x2lamdaT on a triclinic box (setup_triclinic) and zero on an orthogonal one
+  DevBuf<double> fkyx, fkzx, fkzy, fkyx_g;
   DevBuf<double> greensfn, fkx, fky, fkz, density, vd;  // vd: 3*nfft (ik) or nfft (ad: u)
   DevBuf<double2> work1, work2;                         // work2: 3*nfft (ik) / nfft (ad)
   DevBuf<double> sf_pre;                                // ad: 6*nfft

@@ -151,6 +151,13 @@ void orc_pppm_compute_arith(orc_pppm *p, int nlocal, const double *x, const doub
                             double *energy, double *virial, int nthreads);
 void orc_pppm_compute_none(orc_pppm *p, int nlocal, const double *x, int nsplit, const double *wn, const double *lam,
                            int eflag, int vflag, double *f, double *energy, double *virial, int nthreads);
+/* triclinic box: PPPMIntel::compute with domain->triclinic (pppm_intel.cpp:151-156, 307-309, 878-883 + stock
+ * setup_triclinic / compute_gf_ik_triclinic / poisson_ik_triclinic); x in box coordinates, ik differentiation */
+orc_pppm *orc_pppm_create_tri(int nx, int ny, int nz, int order, double g_ewald, const double *boxlo, const double *boxhi,
+                              double xy, double xz, double yz, double qqrd2e, int prec);
+void orc_ewald_recip_tri(int n, const double *x, const double *q, const double *boxlo, const double *boxhi, double xy,
+                         double xz, double yz, double g_ewald, int kmax, double qqrd2e, double *f, double *energy,
+                         double *virial);
 /* kspace_modify slab: mesh over zprd * slab_volfactor, PPPM::slabcorr applied (pppm_intel.cpp:305); z non-periodic */
 orc_pppm *orc_pppm_create_slab(int nx, int ny, int nz, int order, double g_ewald, int diff_ad, const double *boxlo,
                                const double *boxhi, double qqrd2e, int prec, double slab_volfactor);

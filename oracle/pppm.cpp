@@ -85,6 +85,11 @@ struct orc_pppm {
   double boxlo[3], prd[3], volume;   // prd[2] = zprd * slab_volfactor (zprd_slab of PPPM::setup)
   double slab_volfactor = 1.0, zprd = 0.0;   // kspace_modify slab; zprd = the box's own z extent
   double cuthalf;
+  // triclinic boxes (pppm_intel.cpp:151-156, 307-309, 878-883 + stock PPPM::setup_triclinic / compute_gf_ik_triclinic /
+  // poisson_ik_triclinic [UPSTREAM, restated]): everything on the mesh side works in lamda (0..1) coordinates
+  int triclinic = 0;
+  double h[6], h_inv[6], boxlo_box[3];   // Domain::h = {xprd, yprd, zprd, yz, xz, xy}
+  std::vector<double> fkx_t, fky_t, fkz_t;   // per FFT point (setup_triclinic)
   int nlower, nupper;
   double shift, shiftone;
   double delxinv, delyinv, delzinv, delvolinv;
@@ -129,6 +134,133 @@ struct orc_pppm {
     setup();
   }
 
+  // Domain::x2lamdaT / lamda2xT [UPSTREAM]
+  void x2lamdaT(const double *v, double *out) const {
+    const double a = v[0], b = v[1], c = v[2];
+    out[0] = h_inv[0] * a;
+    out[1] = h_inv[5] * a + h_inv[1] * b;
+    out[2] = h_inv[4] * a + h_inv[3] * b + h_inv[2] * c;
+  }
+  void lamda2xT(const double *v, double *out) const {
+    const double a = v[0], b = v[1], c = v[2];
+    out[0] = h[0] * a;
+    out[1] = h[5] * a + h[1] * b;
+    out[2] = h[4] * a + h[3] * b + h[2] * c;
+  }
+
+  void init_tri(int nx, int ny, int nz, int order_, double g, const double *lo, const double *hi, double xy, double xz,
+                double yz, double qq, int prec_) {
+    dispersion = 0;
+    slab_volfactor = 1.0;
+    triclinic = 1;
+    nx_pppm = nx; ny_pppm = ny; nz_pppm = nz; order = order_; g_ewald = g; diff_ad = 0;
+    qqrd2e = qq; scale = 1.0; prec = prec_;
+    for (int d = 0; d < 3; d++) { boxlo_box[d] = lo[d]; boxlo[d] = 0.0; prd[d] = hi[d] - lo[d]; }
+    zprd = prd[2];
+    h[0] = prd[0]; h[1] = prd[1]; h[2] = prd[2]; h[3] = yz; h[4] = xz; h[5] = xy;
+    // Domain::set_global_box
+    h_inv[0] = 1.0 / h[0]; h_inv[1] = 1.0 / h[1]; h_inv[2] = 1.0 / h[2];
+    h_inv[3] = -h[3] / (h[1] * h[2]);
+    h_inv[4] = (h[3] * h[5] - h[1] * h[4]) / (h[0] * h[1] * h[2]);
+    h_inv[5] = -h[5] / (h[0] * h[1]);
+    volume = prd[0] * prd[1] * prd[2];
+    cuthalf = 1.0;
+    setup_grid();
+    compute_gf_denom();
+    compute_rho_coeffs();
+    setup_triclinic();
+  }
+
+  // stock PPPM::setup_triclinic [UPSTREAM]
+  void setup_triclinic() {
+    delxinv = nx_pppm; delyinv = ny_pppm; delzinv = nz_pppm;     // lamda coordinates
+    delvolinv = delxinv * delyinv * delzinv / volume;
+    fkx_t.assign(nfft, 0.0); fky_t.assign(nfft, 0.0); fkz_t.assign(nfft, 0.0);
+    for (int k = 0; k < nz_pppm; k++) {
+      const double per_k = k - nz_pppm * (2 * k / nz_pppm);
+      for (int j = 0; j < ny_pppm; j++) {
+        const double per_j = j - ny_pppm * (2 * j / ny_pppm);
+        for (int i = 0; i < nx_pppm; i++) {
+          const double per_i = i - nx_pppm * (2 * i / nx_pppm);
+          double u[3] = {MY_2PI * per_i, MY_2PI * per_j, MY_2PI * per_k};
+          x2lamdaT(u, u);
+          const long n = ((long)k * ny_pppm + j) * nx_pppm + i;
+          fkx_t[n] = u[0]; fky_t[n] = u[1]; fkz_t[n] = u[2];
+          const double sqk = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+          double *v = &vg[6 * n];
+          if (sqk == 0.0) {
+            for (int t = 0; t < 6; t++) v[t] = 0.0;
+          } else {
+            const double vterm = -2.0 * (1.0 / sqk + 0.25 / (g_ewald * g_ewald));
+            v[0] = 1.0 + vterm * u[0] * u[0];
+            v[1] = 1.0 + vterm * u[1] * u[1];
+            v[2] = 1.0 + vterm * u[2] * u[2];
+            v[3] = vterm * u[0] * u[1];
+            v[4] = vterm * u[0] * u[2];
+            v[5] = vterm * u[1] * u[2];
+          }
+        }
+      }
+    }
+    compute_gf_ik_triclinic();
+  }
+
+  // stock PPPM::compute_gf_ik_triclinic [UPSTREAM]
+  void compute_gf_ik_triclinic() {
+    double tmp[3];
+    tmp[0] = (g_ewald / (MY_PI * nx_pppm)) * std::pow(-std::log(EPS_HOC), 0.25);
+    tmp[1] = (g_ewald / (MY_PI * ny_pppm)) * std::pow(-std::log(EPS_HOC), 0.25);
+    tmp[2] = (g_ewald / (MY_PI * nz_pppm)) * std::pow(-std::log(EPS_HOC), 0.25);
+    lamda2xT(tmp, tmp);
+    const int nbx = (int)tmp[0], nby = (int)tmp[1], nbz = (int)tmp[2];
+    const int twoorder = 2 * order;
+#pragma omp parallel for schedule(static)
+    for (int m = 0; m < nz_pppm; m++) {
+      const int mper = m - nz_pppm * (2 * m / nz_pppm);
+      const double snz = square(std::sin(MY_PI * mper / nz_pppm));
+      for (int l = 0; l < ny_pppm; l++) {
+        const int lper = l - ny_pppm * (2 * l / ny_pppm);
+        const double sny = square(std::sin(MY_PI * lper / ny_pppm));
+        for (int k = 0; k < nx_pppm; k++) {
+          const int kper = k - nx_pppm * (2 * k / nx_pppm);
+          const double snx = square(std::sin(MY_PI * kper / nx_pppm));
+          double uk[3] = {MY_2PI * kper, MY_2PI * lper, MY_2PI * mper};
+          x2lamdaT(uk, uk);
+          const double sqk = square(uk[0]) + square(uk[1]) + square(uk[2]);
+          const long n = ((long)m * ny_pppm + l) * nx_pppm + k;
+          if (sqk != 0.0) {
+            const double numerator = 12.5663706 / sqk;
+            const double denominator = gf_denom(snx, sny, snz);
+            double sum1 = 0.0;
+            for (int nx = -nbx; nx <= nbx; nx++) {
+              const double argx = MY_PI * kper / nx_pppm + MY_PI * nx;
+              const double wx = powsinxx(argx, twoorder);
+              for (int ny = -nby; ny <= nby; ny++) {
+                const double argy = MY_PI * lper / ny_pppm + MY_PI * ny;
+                const double wy = powsinxx(argy, twoorder);
+                for (int nz = -nbz; nz <= nbz; nz++) {
+                  const double argz = MY_PI * mper / nz_pppm + MY_PI * nz;
+                  const double wz = powsinxx(argz, twoorder);
+                  double b[3] = {MY_2PI * nx_pppm * nx, MY_2PI * ny_pppm * ny, MY_2PI * nz_pppm * nz};
+                  x2lamdaT(b, b);
+                  const double qx = uk[0] + b[0], qy = uk[1] + b[1], qz = uk[2] + b[2];
+                  const double sx = std::exp(-0.25 * square(qx / g_ewald));
+                  const double sy = std::exp(-0.25 * square(qy / g_ewald));
+                  const double sz = std::exp(-0.25 * square(qz / g_ewald));
+                  const double dot1 = uk[0] * qx + uk[1] * qy + uk[2] * qz;
+                  const double dot2 = qx * qx + qy * qy + qz * qz;
+                  sum1 += (dot1 / dot2) * sx * sy * sz * wx * wy * wz;
+                }
+              }
+            }
+            greensfn[n] = numerator * sum1 / denominator;
+          } else
+            greensfn[n] = 0.0;
+        }
+      }
+    }
+  }
+
   void setup_grid() {
     // PPPM::set_grid_local on one rank
     nlower = -(order - 1) / 2;
@@ -137,10 +269,19 @@ struct orc_pppm {
     else { shift = OFFSET; shiftone = 0.5; }
     const int n[3] = {nx_pppm, ny_pppm, nz_pppm};
     int lo_out[3], hi_out[3];
+    double distv[3] = {cuthalf, cuthalf, cuthalf}, span[3] = {prd[0], prd[1], prd[2]};
+    if (triclinic) {   // KSpace::kspacebbox [UPSTREAM]: the skin in lamda units; the box spans 0..1
+      const double lx = h[0], ly = h[1], lz = h[2], yz = h[3], xz = h[4], xy = h[5];
+      distv[0] = cuthalf * std::sqrt(ly * ly * lz * lz + ly * ly * xz * xz - 2.0 * ly * xy * xz * yz + xy * xy * yz * yz +
+                                     xy * xy * lz * lz) / (lx * ly * lz);
+      distv[1] = cuthalf * std::sqrt(lz * lz + yz * yz) / (ly * lz);
+      distv[2] = cuthalf / lz;
+      span[0] = span[1] = span[2] = 1.0;
+    }
     for (int d = 0; d < 3; d++) {
-      const double dist = cuthalf;
-      const int nlo = (int)((0.0 - dist) * n[d] / prd[d] + shift) - OFFSET;
-      const int nhi = (int)((prd[d] + dist) * n[d] / prd[d] + shift) - OFFSET;
+      const double dist = distv[d];
+      const int nlo = (int)((0.0 - dist) * n[d] / span[d] + shift) - OFFSET;
+      const int nhi = (int)((span[d] + dist) * n[d] / span[d] + shift) - OFFSET;
       lo_out[d] = nlo + nlower;
       hi_out[d] = nhi + nupper;
     }
@@ -633,7 +774,11 @@ struct orc_pppm {
       for (int k = 0; k < nz_pppm; k++)
         for (int j = 0; j < ny_pppm; j++)
           for (int i = 0; i < nx_pppm; i++) {
-            const double fk = d == 0 ? fkx[i] : (d == 1 ? fky[j] : fkz[k]);
+            double fk = d == 0 ? fkx[i] : (d == 1 ? fky[j] : fkz[k]);
+            if (triclinic) {   // poisson_ik_triclinic (called at pppm_intel.cpp:880-883): per-point wave vectors
+              const long p = n / 2;
+              fk = d == 0 ? fkx_t[p] : (d == 1 ? fky_t[p] : fkz_t[p]);
+            }
             work2[n] = fk * work1[n + 1];
             work2[n + 1] = -fk * work1[n];
             n += 2;
@@ -883,7 +1028,17 @@ struct orc_pppm {
     for (int i = 0; i < nlocal; i++) { qsum += qd[i]; qsqsum += qd[i] * qd[i]; }
     if (qsqsum == 0.0) return 0;
     std::vector<flt_t> x(3 * (size_t)nlocal), q(nlocal);
-    for (size_t i = 0; i < 3 * (size_t)nlocal; i++) x[i] = (flt_t)xd[i];
+    if (triclinic) {
+      // Domain::x2lamda (pppm_intel.cpp:156): the mesh works in lamda coordinates, boxlo = boxlo_lamda = 0
+      for (int i = 0; i < nlocal; i++) {
+        const double dx = xd[3 * (size_t)i] - boxlo_box[0], dy = xd[3 * (size_t)i + 1] - boxlo_box[1],
+                     dz = xd[3 * (size_t)i + 2] - boxlo_box[2];
+        x[3 * (size_t)i] = (flt_t)(h_inv[0] * dx + h_inv[5] * dy + h_inv[4] * dz);
+        x[3 * (size_t)i + 1] = (flt_t)(h_inv[1] * dy + h_inv[3] * dz);
+        x[3 * (size_t)i + 2] = (flt_t)(h_inv[2] * dz);
+      }
+    } else
+      for (size_t i = 0; i < 3 * (size_t)nlocal; i++) x[i] = (flt_t)xd[i];
     for (int i = 0; i < nlocal; i++) q[i] = (flt_t)qd[i];
     if (particle_map<flt_t>(nlocal, x, nthr)) return 1;  // "Out of range atoms - cannot compute PPPM"
     make_rho<flt_t>(nlocal, x, q, nthr);
@@ -1264,6 +1419,14 @@ orc_pppm *orc_pppm_create_slab(int nx, int ny, int nz, int order, double g_ewald
   p->init(nx, ny, nz, order, g_ewald, diff_ad, boxlo, boxhi, qqrd2e, prec, 0, slab_volfactor);
   return p;
 }
+/* triclinic box (tilt factors xy, xz, yz): ik differentiation, Coulomb grid */
+orc_pppm *orc_pppm_create_tri(int nx, int ny, int nz, int order, double g_ewald, const double *boxlo, const double *boxhi,
+                              double xy, double xz, double yz, double qqrd2e, int prec) {
+  if (order < 1 || order > MAXORDER) return nullptr;
+  orc_pppm *p = new orc_pppm();
+  p->init_tri(nx, ny, nz, order, g_ewald, boxlo, boxhi, xy, xz, yz, qqrd2e, prec);
+  return p;
+}
 void orc_pppm_destroy(orc_pppm *p) { delete p; }
 
 void orc_pppm_compute(orc_pppm *p, int nlocal, const double *x, const double *q, int eflag, int vflag,
@@ -1324,15 +1487,27 @@ void orc_pppm_rho_coeff(const orc_pppm *p, double *rho_coeff, double *drho_coeff
   }
 }
 
+void orc_ewald_recip_tri(int n, const double *x, const double *q, const double *boxlo, const double *boxhi, double xy,
+                         double xz, double yz, double g_ewald, int kmax, double qqrd2e, double *f, double *energy,
+                         double *virial);
 void orc_ewald_recip(int n, const double *x, const double *q, const double *boxlo, const double *boxhi,
                      double g_ewald, int kmax, double qqrd2e, double *f, double *energy,
                      double *virial) {
+  orc_ewald_recip_tri(n, x, q, boxlo, boxhi, 0.0, 0.0, 0.0, g_ewald, kmax, qqrd2e, f, energy, virial);
+}
+/* the same sum over the reciprocal lattice of a triclinic cell (edge vectors (xprd,0,0), (xy,yprd,0), (xz,yz,zprd)):
+ * k = 2 pi h^-T m */
+void orc_ewald_recip_tri(int n, const double *x, const double *q, const double *boxlo, const double *boxhi, double xy,
+                         double xz, double yz, double g_ewald, int kmax, double qqrd2e, double *f, double *energy,
+                         double *virial) {
   // plain reciprocal-space Ewald sum (what kspace_style ewald evaluates, in.buck_coul_long:12):
   //   E = (2 pi / V) sum_{k != 0} exp(-k^2/4g^2)/k^2 |S(k)|^2  - g/sqrt(pi) sum q^2 - pi/(2 g^2 V) (sum q)^2
   //   f_i = (4 pi q_i / V) sum_k (k/k^2) exp(-k^2/4g^2) Im( exp(i k.r_i) conj(S(k)) )
   (void)boxlo;
   const double prd[3] = {boxhi[0] - boxlo[0], boxhi[1] - boxlo[1], boxhi[2] - boxlo[2]};
   const double V = prd[0] * prd[1] * prd[2];
+  const double hi0 = 1.0 / prd[0], hi1 = 1.0 / prd[1], hi2 = 1.0 / prd[2], hi3 = -yz / (prd[1] * prd[2]),
+               hi4 = (yz * xy - prd[1] * xz) / (prd[0] * prd[1] * prd[2]), hi5 = -xy / (prd[0] * prd[1]);
   double e = 0.0, vir[6] = {0, 0, 0, 0, 0, 0};
   std::vector<double> fx(n, 0.0), fy(n, 0.0), fz(n, 0.0);
   const double g2inv4 = 0.25 / (g_ewald * g_ewald);
@@ -1345,7 +1520,7 @@ void orc_ewald_recip(int n, const double *x, const double *q, const double *boxl
       for (int ky = -kmax; ky <= kmax; ky++)
         for (int kz = -kmax; kz <= kmax; kz++) {
           if (!kx && !ky && !kz) continue;
-          const double k[3] = {MY_2PI * kx / prd[0], MY_2PI * ky / prd[1], MY_2PI * kz / prd[2]};
+          const double k[3] = {MY_2PI * (hi0 * kx), MY_2PI * (hi5 * kx + hi1 * ky), MY_2PI * (hi4 * kx + hi3 * ky + hi2 * kz)};
           const double sqk = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
           const double ug = std::exp(-sqk * g2inv4) / sqk;
           if (ug < 1e-300) continue;

@@ -321,6 +321,22 @@ class PPPM:
         self.nfft = nx * ny * nz
         return self
 
+    @classmethod
+    def triclinic(cls, nx, ny, nz, order, g_ewald, boxlo, boxhi, tilt, qqrd2e, prec=DOUBLE):
+        """PPPMIntel::compute on a triclinic box, tilt = (xy, xz, yz); compute(x, q) takes box coordinates"""
+        self = cls.__new__(cls)
+        lib().orc_pppm_create_tri.restype = C.c_void_p
+        h = lib().orc_pppm_create_tri(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(order), C.c_double(g_ewald),
+                                      _d(f64(boxlo)), _d(f64(boxhi)), C.c_double(tilt[0]), C.c_double(tilt[1]),
+                                      C.c_double(tilt[2]), C.c_double(qqrd2e), C.c_int(prec))
+        if not h:
+            raise ValueError("PPPM order not supported")
+        self.h = C.c_void_p(h)
+        self.grid = (nx, ny, nz)
+        self.order = order
+        self.nfft = nx * ny * nz
+        return self
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_pppm_destroy(self.h)
@@ -442,6 +458,17 @@ def ewald_recip(x, q, boxlo, boxhi, g_ewald, kmax, qqrd2e):
     v = np.zeros(6)
     lib().orc_ewald_recip(C.c_int(n), _d(f64(x)), _d(f64(q)), _d(f64(boxlo)), _d(f64(boxhi)),
                           C.c_double(g_ewald), C.c_int(kmax), C.c_double(qqrd2e), _d(f), C.byref(e), _d(v))
+    return f, e.value, v
+
+
+def ewald_recip_tri(x, q, boxlo, boxhi, tilt, g_ewald, kmax, qqrd2e):
+    n = len(x)
+    f = np.zeros((n, 3))
+    e = C.c_double(0.0)
+    v = np.zeros(6)
+    lib().orc_ewald_recip_tri(C.c_int(n), _d(f64(x)), _d(f64(q)), _d(f64(boxlo)), _d(f64(boxhi)), C.c_double(tilt[0]),
+                              C.c_double(tilt[1]), C.c_double(tilt[2]), C.c_double(g_ewald), C.c_int(kmax),
+                              C.c_double(qqrd2e), _d(f), C.byref(e), _d(v))
     return f, e.value, v
 
 

@@ -90,6 +90,68 @@ def test_pppm_matches_oracle(pkg, W, orc, name, order, ad, prec):
     ctx.close()
 
 
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("grid,order,tilt", [((24, 24, 27), 5, (3.0, -2.0, 4.0)), ((30, 32, 36), 7, (-6.0, 5.0, 1.5)),
+                                             ((24, 25, 27), 4, (0.0, 0.0, 7.0)), ((24, 24, 27), 5, (0.0, 0.0, 0.0))])
+def test_pppm_triclinic_matches_oracle(pkg, W, orc, grid, order, tilt, prec):
+    """PPPMIntel::compute on a triclinic box (pppm_intel.cpp:151-156 x2lamda, :878-883 poisson_ik_triclinic, stock
+    setup_triclinic / compute_gf_ik_triclinic): Green's function, density, field bricks, forces, energy and virial
+    against the oracle (pinned by the Ewald sum over the tilted cell's reciprocal lattice); even and odd grid sizes
+    exercise the Nyquist handling of the packed Ex + i Ey transform with the cross terms of the wave vector"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    g = 0.28
+    lo, hi = s["boxlo"], s["boxhi"]
+    prd = hi - lo
+    lam = (s["x"] - lo) / prd
+    x = np.column_stack([lo[0] + prd[0] * lam[:, 0] + tilt[0] * lam[:, 1] + tilt[1] * lam[:, 2],
+                         lo[1] + prd[1] * lam[:, 1] + tilt[2] * lam[:, 2], lo[2] + prd[2] * lam[:, 2]])
+    ctx = pkg.Context(0, prec)
+    ctx.set_units(u["qqrd2e"], u["ftm2v"])
+    ctx.set_box_triclinic(lo, hi, tilt)
+    ctx.atoms_upload(x, s["type"], s["mass"], q=s["q"])
+    ctx.neigh_setup(2.0)
+    ctx.pppm_setup(*grid, order, g)
+    # zero tilt through the triclinic entry point is the orthogonal path (float positions, not float lamda coordinates)
+    pp = (orc.PPPM.triclinic(*grid, order, g, lo, hi, tilt, u["qqrd2e"], prec=prec) if any(tilt) else
+          orc.PPPM(*grid, order, g, lo, hi, u["qqrd2e"], prec=prec))
+    fo, eo, vo = pp.compute(x, s["q"])
+    f, e, v = ctx.pppm_compute_host(x, s["q"], 1, 1)
+    d = ctx.pppm_download()
+    assert np.abs(d["greensfn"] - pp.greensfn()).max() <= 1e-12 * np.abs(pp.greensfn()).max()
+    tol_grid = 1e-11 if prec == 0 else 2e-5
+    assert np.abs(d["density"] - pp.density()).max() <= tol_grid * np.abs(pp.density()).max()
+    for k, cc in enumerate(("fx", "fy", "fz")):
+        ref = pp.field(k)
+        assert np.abs(d[cc] - ref).max() <= tol_grid * np.abs(ref).max(), cc
+    tol_f, tol_e = (1e-9, 1e-10) if prec == 0 else (1e-5, 1e-5)
+    assert util.rel_force_err(f, fo) <= tol_f
+    assert abs(e - eo) <= tol_e * abs(eo)
+    assert np.abs(v - vo).max() <= tol_e * np.abs(vo).max()
+    # resident form on the uploaded atoms: same numbers
+    e2, v2 = ctx.pppm_compute(1, 1)
+    assert util.rel_force_err(ctx.atoms_download(("f",))["f"], fo) <= tol_f and abs(e2 - eo) <= tol_e * abs(eo)
+    if any(tilt):
+        # what stock PPPM::init refuses on a triclinic box, and the parts of the path that need an orthogonal one
+        for kw, msg in ((dict(differentiation=1), "kspace_modify diff ad"), (dict(dispersion=1, B=np.array([0.0, 1.0, 2.0])), "PPPMDisp")):
+            with pytest.raises(pkg.B200MDError, match=msg):
+                ctx.pppm_setup(*grid, order, g, **kw)
+        co = W.coeffs_aC(6.0, 6.0)
+        cf = pkg.pair_coeffs(pkg.PAIR_BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+        ctx.pair_setup(pkg.PAIR_BUCK_COUL_LONG, 2, cf, g_ewald=g)
+        with pytest.raises(pkg.B200MDError, match="triclinic"):
+            ctx.neigh_build()
+    else:
+        # zero tilt through the triclinic entry point is the orthogonal path
+        c2 = pkg.make_context(s, precision=prec)
+        c2.neigh_setup(2.0)
+        c2.pppm_setup(*grid, order, g)
+        f0, e0, v0 = c2.pppm_compute_host(x, s["q"], 1, 1)
+        assert util.rel_force_err(f, f0) <= (1e-13 if prec == 0 else 1e-6) and abs(e - e0) <= 1e-10 * abs(e0)
+        c2.close()
+    ctx.close()
+
+
 @pytest.mark.parametrize("name,order,ad,prec", [("aC1", 5, 0, 0), ("aC2_1e-4", 5, 1, 0), ("water", 7, 0, 0),
                                                 ("aC1", 4, 0, 1)])
 def test_pppm_peratom_matches_oracle(pkg, W, orc, name, order, ad, prec):

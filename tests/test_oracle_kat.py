@@ -172,6 +172,60 @@ def test_pppm_plus_real_space_equals_ewald(orc, W):
     assert ea == pytest.approx(ee, rel=1e-6)
 
 
+def _sheared(s, tilt):
+    """the atoms of an orthogonal system carried along with a shear of its box (same lamda coordinates)"""
+    xy, xz, yz = tilt
+    prd = s["boxhi"] - s["boxlo"]
+    lam = (s["x"] - s["boxlo"]) / prd
+    x = np.empty_like(s["x"])
+    x[:, 0] = s["boxlo"][0] + prd[0] * lam[:, 0] + xy * lam[:, 1] + xz * lam[:, 2]
+    x[:, 1] = s["boxlo"][1] + prd[1] * lam[:, 1] + yz * lam[:, 2]
+    x[:, 2] = s["boxlo"][2] + prd[2] * lam[:, 2]
+    return x
+
+
+def test_triclinic_pppm_known_answers(orc, W):
+    """PPPMIntel::compute on a triclinic box (pppm_intel.cpp:151-156, 878-883 -> stock setup_triclinic,
+    compute_gf_ik_triclinic, poisson_ik_triclinic, restated): (1) zero tilt is the orthogonal path; (2) a tight mesh
+    reproduces the direct Ewald sum over the reciprocal lattice of the tilted cell; (3) tilting the box by one whole
+    lattice vector (xy = xprd) describes the same crystal: same energy and forces"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    g = 0.30
+    lo, hi = s["boxlo"], s["boxhi"]
+    f0, e0, v0 = orc.PPPM(24, 24, 27, 5, g, lo, hi, u["qqrd2e"]).compute(s["x"], s["q"])
+    ft, et, vt = orc.PPPM.triclinic(24, 24, 27, 5, g, lo, hi, (0.0, 0.0, 0.0), u["qqrd2e"]).compute(s["x"], s["q"])
+    assert et == pytest.approx(e0, rel=1e-12) and np.abs(ft - f0).max() <= 1e-11 * np.abs(f0).max()
+    assert np.allclose(vt, v0, rtol=0, atol=1e-11 * np.abs(v0).max())
+    # (2) a genuinely tilted cell
+    tilt = (3.0, -2.0, 4.0)
+    x = _sheared(s, tilt)
+    fe, ee, ve = orc.ewald_recip_tri(x, s["q"], lo, hi, tilt, g, 14, u["qqrd2e"])
+    fp, ep, vp = orc.PPPM.triclinic(60, 60, 64, 7, g, lo, hi, tilt, u["qqrd2e"]).compute(x, s["q"])
+    scale = np.abs(fe).max()
+    assert np.abs(fp - fe).max() / scale < 2e-5
+    assert ep == pytest.approx(ee, rel=1e-6)
+    assert np.allclose(vp, ve, rtol=1e-4, atol=1e-4 * np.abs(ve).max())
+    assert np.abs(fe - orc.ewald_recip(s["x"], s["q"], lo, hi, g, 14, u["qqrd2e"])[0]).max() > 0.05 * scale   # not the cube again
+    # (3) xy = xprd: the same lattice; atoms wrapped into the tilted cell
+    prd = hi - lo
+    tilt1 = (prd[0], 0.0, 0.0)
+    lam = np.empty_like(s["x"])
+    d = s["x"] - lo
+    lam[:, 2] = d[:, 2] / prd[2]
+    lam[:, 1] = d[:, 1] / prd[1]
+    lam[:, 0] = (d[:, 0] - tilt1[0] * lam[:, 1]) / prd[0]
+    lam -= np.floor(lam)
+    xw = np.column_stack([lo[0] + prd[0] * lam[:, 0] + tilt1[0] * lam[:, 1], lo[1] + prd[1] * lam[:, 1],
+                          lo[2] + prd[2] * lam[:, 2]])
+    fo, eo, _ = orc.ewald_recip(s["x"], s["q"], lo, hi, g, 14, u["qqrd2e"])
+    f1, e1, _ = orc.ewald_recip_tri(xw, s["q"], lo, hi, tilt1, g, 16, u["qqrd2e"])
+    assert e1 == pytest.approx(eo, rel=1e-10) and np.abs(f1 - fo).max() <= 1e-9 * np.abs(fo).max()
+    # the 45-degree cell is a different (coarser) discretisation of the same crystal: a tight mesh converges to it
+    fq, eq, _ = orc.PPPM.triclinic(60, 60, 64, 7, g, lo, hi, tilt1, u["qqrd2e"]).compute(xw, s["q"])
+    assert eq == pytest.approx(eo, rel=1e-8) and np.abs(fq - fo).max() <= 2e-6 * np.abs(fo).max()
+
+
 def test_madelung_constant_rocksalt(orc, pkg):
     """NaCl rock salt: E per ion pair = -M q^2 / r0 with M = 1.747565, from PPPM + real-space erfc"""
     nc, a = 4, 5.64
