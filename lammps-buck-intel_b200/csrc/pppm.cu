@@ -56,9 +56,9 @@ __device__ __forceinline__ double d_gf_denom(const PppmConst &c, double x, doubl
 // (yoff, nyl): the y rows this rank holds in the z-pencil layout [z][y local][x]; (0, ny) on one GPU
 __global__ void k_gf_ik(PppmConst c, int nbx, int nby, int nbz, int yoff, int nyl, double *__restrict__ greensfn) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * nyl * c.nz;
+  const long nfft = (long)c.sx * nyl * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % nyl) + yoff, m = (int)(n / ((long)c.nx * nyl));
+  const int k = (int)(n % c.sx), l = (int)((n / c.sx) % nyl) + yoff, m = (int)(n / ((long)c.sx * nyl));
   const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
   const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
@@ -105,9 +105,9 @@ __device__ __forceinline__ void d_x2lamdaT(const PppmConst &c, double a, double 
 }
 __global__ void k_gf_ik_tri(PppmConst c, int nbx, int nby, int nbz, double *__restrict__ greensfn) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
+  const long nfft = (long)c.sx * c.ny * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % c.ny), m = (int)(n / ((long)c.nx * c.ny));
+  const int k = (int)(n % c.sx), l = (int)((n / c.sx) % c.ny), m = (int)(n / ((long)c.sx * c.ny));
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
   const double snx = d_square(sin(kPI * kper / c.nx)), sny = d_square(sin(kPI * lper / c.ny)),
                snz = d_square(sin(kPI * mper / c.nz));
@@ -145,12 +145,40 @@ __global__ void k_gf_ik_tri(PppmConst c, int nbx, int nby, int nbz, double *__re
 // PPPM::compute_sf_precoeff + the per-point part of compute_gf_ad
 // (yoff, nyl: the y rows held by this rank, [z][row][x]; the whole grid on one GPU)
 // have_g: greensfn already holds the influence function (dispersion grid: k_gf_6) and only the sums are formed
+// the six alias sums of PPPM::compute_sf_precoeff at the grid point with the periodic indices (kper, lper, mper)
+__device__ __forceinline__ void sf_sums(const PppmConst &c, int kper, int lper, int mper, double sum[6]) {
+  double wx0[5], wy0[5], wz0[5], wx1[5], wy1[5], wz1[5], wx2[5], wy2[5], wz2[5];
+  for (int i = 0; i < 5; i++) {
+    wx0[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 2))) / c.nx, c.order);
+    wx1[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 1))) / c.nx, c.order);
+    wx2[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i))) / c.nx, c.order);
+    wy0[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i - 2))) / c.ny, c.order);
+    wy1[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i - 1))) / c.ny, c.order);
+    wy2[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i))) / c.ny, c.order);
+    wz0[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i - 2))) / c.nz, c.order);
+    wz1[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i - 1))) / c.nz, c.order);
+    wz2[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i))) / c.nz, c.order);
+  }
+  for (int t = 0; t < 6; t++) sum[t] = 0.0;
+  for (int ax = 0; ax < 5; ax++)
+    for (int ay = 0; ay < 5; ay++)
+      for (int az = 0; az < 5; az++) {
+        const double u0 = wx0[ax] * wy0[ay] * wz0[az];
+        sum[0] += u0 * (wx1[ax] * wy0[ay] * wz0[az]);
+        sum[1] += u0 * (wx2[ax] * wy0[ay] * wz0[az]);
+        sum[2] += u0 * (wx0[ax] * wy1[ay] * wz0[az]);
+        sum[3] += u0 * (wx0[ax] * wy2[ay] * wz0[az]);
+        sum[4] += u0 * (wx0[ax] * wy0[ay] * wz1[az]);
+        sum[5] += u0 * (wx0[ax] * wy0[ay] * wz2[az]);
+      }
+}
+
 __global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ greensfn, double *__restrict__ sfpre,
                         int have_g) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * nyl * c.nz;
+  const long nfft = (long)c.sx * nyl * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % nyl) + yoff, m = (int)(n / ((long)c.nx * nyl));
+  const int k = (int)(n % c.sx), l = (int)((n / c.sx) % nyl) + yoff, m = (int)(n / ((long)c.sx * nyl));
   const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
   const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
@@ -169,30 +197,16 @@ __global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ gre
     if (sqk != 0.0) g = (k4PI / sqk) * sx * sy * sz * wx * wy * wz / d_gf_denom(c, snx, sny, snz);
     greensfn[n] = g;
   }
-  double wx0[5], wy0[5], wz0[5], wx1[5], wy1[5], wz1[5], wx2[5], wy2[5], wz2[5];
-  for (int i = 0; i < 5; i++) {
-    wx0[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 2))) / c.nx, c.order);
-    wx1[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i - 1))) / c.nx, c.order);
-    wx2[i] = d_powsinxx(0.5 * (k2PI * (kper + c.nx * (i))) / c.nx, c.order);
-    wy0[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i - 2))) / c.ny, c.order);
-    wy1[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i - 1))) / c.ny, c.order);
-    wy2[i] = d_powsinxx(0.5 * (k2PI * (lper + c.ny * (i))) / c.ny, c.order);
-    wz0[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i - 2))) / c.nz, c.order);
-    wz1[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i - 1))) / c.nz, c.order);
-    wz2[i] = d_powsinxx(0.5 * (k2PI * (mper + c.nz * (i))) / c.nz, c.order);
+  double sum[6];
+  sf_sums(c, kper, lper, mper, sum);
+  // half spectrum: a stored point with 0 < kx < nx / 2 also stands for its mirror image (-kx, -ky, -kz) in the sums
+  // over the grid; G is even, the truncated alias sums are not exactly, so the mirror image is evaluated itself
+  if (c.sx != c.nx && k != 0 && 2 * k != c.nx) {
+    const int k2 = c.nx - k, l2 = (c.ny - l) % c.ny, m2 = (c.nz - m) % c.nz;
+    double sum2[6];
+    sf_sums(c, k2 - c.nx * (2 * k2 / c.nx), l2 - c.ny * (2 * l2 / c.ny), m2 - c.nz * (2 * m2 / c.nz), sum2);
+    for (int t = 0; t < 6; t++) sum[t] += sum2[t];
   }
-  double sum[6] = {0, 0, 0, 0, 0, 0};
-  for (int ax = 0; ax < 5; ax++)
-    for (int ay = 0; ay < 5; ay++)
-      for (int az = 0; az < 5; az++) {
-        const double u0 = wx0[ax] * wy0[ay] * wz0[az];
-        sum[0] += u0 * (wx1[ax] * wy0[ay] * wz0[az]);
-        sum[1] += u0 * (wx2[ax] * wy0[ay] * wz0[az]);
-        sum[2] += u0 * (wx0[ax] * wy1[ay] * wz0[az]);
-        sum[3] += u0 * (wx0[ax] * wy2[ay] * wz0[az]);
-        sum[4] += u0 * (wx0[ax] * wy0[ay] * wz1[az]);
-        sum[5] += u0 * (wx0[ax] * wy0[ay] * wz2[az]);
-      }
   for (int t = 0; t < 6; t++) sfpre[(size_t)t * nfft + n] = sum[t] * g;
 }
 
@@ -200,9 +214,9 @@ __global__ void k_gf_ad(PppmConst c, int yoff, int nyl, double *__restrict__ gre
 // the geometric-mixing grid of PPPMDispIntel::compute (pppm_disp_intel.cpp:245-313).
 __global__ void k_gf_6(PppmConst c, int yoff, int nyl, double *__restrict__ greensfn) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * nyl * c.nz;
+  const long nfft = (long)c.sx * nyl * c.nz;
   if (n >= nfft) return;
-  const int k = (int)(n % c.nx), l = (int)((n / c.nx) % nyl) + yoff, m = (int)(n / ((long)c.nx * nyl));
+  const int k = (int)(n % c.sx), l = (int)((n / c.sx) % nyl) + yoff, m = (int)(n / ((long)c.sx * nyl));
   const double xprd = c.prd[0], yprd = c.prd[1], zprd = c.prd[2];
   const double unitkx = k2PI / xprd, unitky = k2PI / yprd, unitkz = k2PI / zprd;
   const int kper = k - c.nx * (2 * k / c.nx), lper = l - c.ny * (2 * l / c.ny), mper = m - c.nz * (2 * m / c.nz);
@@ -758,20 +772,102 @@ k_fft_pass(FftPlan1d pl, PassGeom pg, int lgTB, int LP, const double *in_real, c
   }
 }
 
+// Real-to-complex x pass.  The density is real, so rho(-k) = conj rho(k): only kx = 0 .. nx/2 is kept (hx = nx/2 + 1
+// points per line) and every later pass works on half as many lines.  Two real lines a, b ride in ONE complex transform
+// z = a + i b and are separated by A(k) = (Z(k) + conj Z(n-k)) / 2, B(k) = (Z(k) - conj Z(n-k)) / (2i).
+// Real line L starts at in_real + L n, its half spectrum at out + L hx.
+__global__ void __launch_bounds__(512)
+k_fft_x_r2c(FftPlan1d pl, long nlines, int lgTB, int LP, const double *__restrict__ in_real, double2 *__restrict__ out,
+            double s) {
+  extern __shared__ double2 smem[];
+  const int TB = 1 << lgTB;
+  const int lgtpl = 31 - __clz(blockDim.x) - lgTB, tpl = 1 << lgtpl;
+  double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *tw_s = smem + 2 * (size_t)TB * LP;
+  const int n = pl.n, hx = n / 2 + 1;
+  const long npairs = (nlines + 1) >> 1;
+  const long P0 = (long)blockIdx.x * TB;
+  const int nl = (int)min((long)TB, npairs - P0);
+  stage_twiddles(pl, tw_s);
+  const int t = threadIdx.x >> lgtpl, k0 = threadIdx.x & (tpl - 1);
+  const long La = 2 * (P0 + t), Lb = La + 1;
+  const bool two = Lb < nlines;
+  if (t < nl) {
+    const double *a = in_real + La * n, *b = in_real + Lb * n;
+    for (int k = k0; k < n; k += tpl) bufA[t * LP + k] = make_double2(a[k], two ? b[k] : 0.0);
+  }
+  __syncthreads();
+  double2 *res = block_fft(bufA, bufB, pl, LP, nl, lgtpl, s, tw_s);
+  if (t < nl) {
+    double2 *oa = out + La * hx, *ob = out + Lb * hx;
+    for (int k = k0; k < hx; k += tpl) {
+      const double2 zk = res[t * LP + k], zm = res[t * LP + (k ? n - k : 0)];
+      oa[k] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+      if (two) ob[k] = make_double2(0.5 * (zk.y + zm.y), 0.5 * (zm.x - zk.x));
+    }
+  }
+}
+
+// Complex-to-real x pass, the inverse of the above: the half spectra A, B of two real lines are joined,
+// Z(k) = A(k) + i B(k), Z(n-k) = conj A(k) + i conj B(k), and one complex transform returns a = Re z, b = Im z.
+// The self-conjugate entries (k = 0 and, on an even grid, k = n/2) of a real line are real: their imaginary parts
+// (round-off, or the Nyquist plane of a gradient field: the reference keeps Re(IFFT), see k_fft_z_poisson) are dropped.
+__global__ void __launch_bounds__(512)
+k_fft_x_c2r(FftPlan1d pl, long nlines, int lgTB, int LP, const double2 *__restrict__ in, double *__restrict__ out_real,
+            double s) {
+  extern __shared__ double2 smem[];
+  const int TB = 1 << lgTB;
+  const int lgtpl = 31 - __clz(blockDim.x) - lgTB, tpl = 1 << lgtpl;
+  double2 *bufA = smem, *bufB = smem + (size_t)TB * LP, *tw_s = smem + 2 * (size_t)TB * LP;
+  const int n = pl.n, hx = n / 2 + 1;
+  const long npairs = (nlines + 1) >> 1;
+  const long P0 = (long)blockIdx.x * TB;
+  const int nl = (int)min((long)TB, npairs - P0);
+  stage_twiddles(pl, tw_s);
+  const int t = threadIdx.x >> lgtpl, k0 = threadIdx.x & (tpl - 1);
+  const long La = 2 * (P0 + t), Lb = La + 1;
+  const bool two = Lb < nlines;
+  if (t < nl) {
+    const double2 *ia = in + La * hx, *ib = in + Lb * hx;
+    for (int k = k0; k < hx; k += tpl) {
+      double2 A = ia[k], B = two ? ib[k] : make_double2(0.0, 0.0);
+      const bool self = k == 0 || 2 * k == n;
+      if (self) { A.y = 0.0; B.y = 0.0; }
+      bufA[t * LP + k] = make_double2(A.x - B.y, A.y + B.x);
+      if (!self) bufA[t * LP + n - k] = make_double2(A.x + B.y, B.x - A.y);
+    }
+  }
+  __syncthreads();
+  double2 *res = block_fft(bufA, bufB, pl, LP, nl, lgtpl, s, tw_s);
+  if (t < nl) {
+    double *oa = out_real + La * n, *ob = out_real + Lb * n;
+    for (int k = k0; k < n; k += tpl) {
+      const double2 v = res[t * LP + k];
+      oa[k] = v.x;
+      if (two) ob[k] = v.y;
+    }
+  }
+}
+
 // forward z pass + Poisson (pppm_intel.cpp:843-872) + (-i k) multiplies (:890-953) + NCOMP inverse z passes.
 // lines are along z at (y,x) = L; TB consecutive L share y (mostly) and have consecutive x.
 // NCOMP = 3: ik (E-field components), NCOMP = 1: ad (potential only).  EV: energy/virial partial sums.
 // Cross terms of the wave vector on a triclinic box (PPPM::setup_triclinic: k = x2lamdaT(2 pi per)):
 // ky += yx[ix], kz += zx[ix] + zy[iy]; yxg is yx with the Nyquist entry zeroed (gradient of the packed Ex + i Ey
 // transform, see below).  All NULL on an orthogonal box.  zy is already offset to this rank's first y row.
+// HALF = 1 (orthogonal boxes): half-spectrum layout (real-to-complex x pass): nx is the stored x extent
+// nxfull / 2 + 1; a point with 0 < kx < nxfull / 2 also stands for its mirror image (-kx, -ky, -kz) in the energy /
+// virial sums (on a Nyquist plane the mirror image keeps the sign of that wave number: its cross terms are summed
+// with their own signs); the three gradient fields are transformed one by one
+// (each is Hermitian: fkxg / fkyg / fkzg have their Nyquist entries zeroed, which is what keeping Re(IFFT) of the
+// reference's unsymmetric Nyquist planes amounts to) instead of Ex + i Ey sharing a transform.
 struct TriWave { const double *yx, *zx, *zy, *yxg; };
-template <int NCOMP, int EV>
+template <int NCOMP, int EV, int HALF>
 __global__ void __launch_bounds__(512)
 k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
                 const double *__restrict__ fky, const double *__restrict__ fkz, const double *__restrict__ fkxg,
-                const double *__restrict__ fkyg, double scaleinv, double g_ewald, double *__restrict__ ev_partial,
-                int disp, TriWave tw) {
+                const double *__restrict__ fkyg, const double *__restrict__ fkzg, int nxfull, double scaleinv,
+                double g_ewald, double *__restrict__ ev_partial, int disp, TriWave tw) {
   extern __shared__ double2 smem[];
   const int TB = 1 << lgTB;
   const int lgtpl = 31 - __clz(blockDim.x) - lgTB;
@@ -805,7 +901,8 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
       const double2 w = res[t * LP + k];
       const double gf = greensfn[g];
       if (EV) {
-        const double eng = scaleinv * scaleinv * gf * (w.x * w.x + w.y * w.y);
+        const double wgt = (HALF && ix != 0 && 2 * ix != nxfull) ? 2.0 : 1.0;
+        const double eng = wgt * scaleinv * scaleinv * gf * (w.x * w.x + w.y * w.y);
         const double kz = fkz[k] + kzb;
         const double sqk = kx * kx + ky * ky + kz * kz;
         acc[0] += eng;
@@ -820,9 +917,17 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
           acc[1] += eng * (1.0 + vterm * kx * kx);
           acc[2] += eng * (1.0 + vterm * ky * ky);
           acc[3] += eng * (1.0 + vterm * kz * kz);
-          acc[4] += eng * (vterm * kx * ky);
-          acc[5] += eng * (vterm * kx * kz);
-          acc[6] += eng * (vterm * ky * kz);
+          if (HALF && wgt == 2.0) {
+            // the point and its mirror image: (-kx, +-ky, +-kz), a wave number on its Nyquist plane keeps its sign
+            const double e1 = 0.5 * eng, sy = 2 * iy == ny ? 1.0 : -1.0, sz = 2 * k == n ? 1.0 : -1.0;
+            acc[4] += e1 * (vterm * kx * ky) * (1.0 - sy);
+            acc[5] += e1 * (vterm * kx * kz) * (1.0 - sz);
+            acc[6] += e1 * (vterm * ky * kz) * (1.0 + sy * sz);
+          } else {
+            acc[4] += eng * (vterm * kx * ky);
+            acc[5] += eng * (vterm * kx * kz);
+            acc[6] += eng * (vterm * ky * kz);
+          }
         }
       }
       const double sg = scaleinv * gf;
@@ -853,7 +958,7 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
   // -n/2 * unitk, not 0) and that plane contributes exactly nothing to the real part — so dropping it (fkxg/fkyg
   // have the Nyquist entry zeroed) leaves Re(IFFT(Wx)) unchanged and makes Wx, Wy exactly Hermitian, which is what
   // the packing needs for the two fields not to leak into each other.
-  constexpr int NPACK = NCOMP == 3 ? 2 : 1;
+  constexpr int NPACK = NCOMP == 3 ? (HALF ? 3 : 2) : 1;
   for (int comp = 0; comp < NPACK; comp++) {
     double2 *a = res, *b = other;  // V lives in bufV; a/b are free ping-pong buffers
     if (live) {
@@ -863,7 +968,10 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
       for (int k = k0; k < n; k += kstep) {
         const double2 v = bufV[t * LP + k];
         if (NCOMP == 1) a[t * LP + k] = v;
-        else if (comp == 0) a[t * LP + k] = make_double2(kx * v.y + ky * v.x, ky * v.y - kx * v.x);
+        else if (HALF) {
+          const double fk = comp == 0 ? kx : (comp == 1 ? ky : fkzg[k]);
+          a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);
+        } else if (comp == 0) a[t * LP + k] = make_double2(kx * v.y + ky * v.x, ky * v.y - kx * v.x);
         else {
           const double fk = fkz[k] + kzb;
           a[t * LP + k] = make_double2(fk * v.y, -fk * v.x);
@@ -959,9 +1067,9 @@ __global__ void k_peratom_mul(PppmConst c, int comp, double scaleinv, const doub
                               const double *__restrict__ greensfn, const double *__restrict__ fkx,
                               const double *__restrict__ fky, const double *__restrict__ fkz, double2 *__restrict__ out) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nfft = (long)c.nx * c.ny * c.nz;
+  const long nfft = (long)c.sx * c.ny * c.nz;
   if (n >= nfft) return;
-  const int i = (int)(n % c.nx), j = (int)((n / c.nx) % c.ny), k = (int)(n / ((long)c.nx * c.ny));
+  const int i = (int)(n % c.sx), j = (int)((n / c.sx) % c.ny), k = (int)(n / ((long)c.sx * c.ny));
   double w = scaleinv * greensfn[n];
   if (comp > 0) {
     const double kx = fkx[i], ky = fky[j], kz = fkz[k];
@@ -969,13 +1077,17 @@ __global__ void k_peratom_mul(PppmConst c, int comp, double scaleinv, const doub
     double vg = 0.0;
     if (sqk != 0.0) {
       const double vterm = -2.0 * (1.0 / sqk + 0.25 / (c.g_ewald * c.g_ewald));
+      // half spectrum: the reference keeps Re(IFFT) of products that are not Hermitian where exactly one of the two
+      // wave numbers sits on its Nyquist plane (it does not change sign under k -> -k there); their Hermitian part is 0
+      const bool half = c.sx != c.nx;
+      const bool nqx = 2 * i == c.nx, nqy = 2 * j == c.ny, nqz = 2 * k == c.nz;
       switch (comp) {
         case 1: vg = 1.0 + vterm * kx * kx; break;
         case 2: vg = 1.0 + vterm * ky * ky; break;
         case 3: vg = 1.0 + vterm * kz * kz; break;
-        case 4: vg = vterm * kx * ky; break;
-        case 5: vg = vterm * kx * kz; break;
-        default: vg = vterm * ky * kz; break;
+        case 4: vg = (half && nqx != nqy) ? 0.0 : vterm * kx * ky; break;
+        case 5: vg = (half && nqx != nqz) ? 0.0 : vterm * kx * kz; break;
+        default: vg = (half && nqy != nqz) ? 0.0 : vterm * ky * kz; break;
       }
     }
     w *= vg;
@@ -1052,6 +1164,79 @@ int launch_pass(b200md_ctx *ctx, const FftPlan1d &pl, const PassGeom &pg, const 
   return 0;
 }
 
+// x passes of the half-spectrum path: nlines real lines of pl.n points <-> nlines half lines of pl.n / 2 + 1 points
+int launch_x_r2c(b200md_ctx *ctx, const FftPlan1d &pl, long nlines, const double *in_real, double2 *out, int timer_id) {
+  const int TB = pick_tb(pl.n, 2);
+  const int LP = pl.n | 1;
+  const size_t smem = (2 * (size_t)TB * LP + pl.n) * sizeof(double2);
+  if (smem > 220 * 1024) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d too long for one shared-memory line", pl.n);
+  CUDA_OK(ctx, cudaFuncSetAttribute(k_fft_x_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long npairs = (nlines + 1) / 2;
+  if (npairs <= 0) return 0;
+  {
+    ScopedTimer tk(ctx, timer_id);
+    k_fft_x_r2c<<<cdiv(npairs, TB), fft_threads(), smem, ctx->stream>>>(pl, nlines, ilog2(TB), LP, in_real, out, S_FWD);
+  }
+  KERNEL_OK(ctx, "k_fft_x_r2c");
+  return 0;
+}
+int launch_x_c2r(b200md_ctx *ctx, const FftPlan1d &pl, long nlines, const double2 *in, double *out_real, int timer_id) {
+  const int TB = pick_tb(pl.n, 2);
+  const int LP = pl.n | 1;
+  const size_t smem = (2 * (size_t)TB * LP + pl.n) * sizeof(double2);
+  if (smem > 220 * 1024) return b2_fail(ctx, B200MD_EINVAL, "FFT length %d too long for one shared-memory line", pl.n);
+  CUDA_OK(ctx, cudaFuncSetAttribute(k_fft_x_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long npairs = (nlines + 1) / 2;
+  if (npairs <= 0) return 0;
+  {
+    ScopedTimer tk(ctx, timer_id >= 0 ? timer_id : T_OTHER, timer_id >= 0);
+    k_fft_x_c2r<<<cdiv(npairs, TB), fft_threads(), smem, ctx->stream>>>(pl, nlines, ilog2(TB), LP, in, out_real, S_BWD);
+  }
+  KERNEL_OK(ctx, "k_fft_x_c2r");
+  return 0;
+}
+
+// The fused z pass / Poisson / gradient kernel on this rank's z pencils: nyl rows starting at global row yoff, lines of
+// gnz points, spectral x extent ps.c.sx.  in = x,y-transformed density [gnz][nyl][sx]; out = [npack][gnz][nyl][sx]
+// (npack: 1 ad, 2 ik full spectrum (Ex + i Ey, Ez), 3 ik half spectrum).  Returns the block count (rows of ps.partial).
+int launch_z_poisson(b200md_ctx *ctx, PppmState &ps, int nyl, int yoff, int gnz, const double2 *in, double2 *out,
+                     int ev, int *nblk_out) {
+  const PppmConst &c = ps.c;
+  const bool ad = ps.p.differentiation == 1, half = c.sx != c.nx;
+  const int TB = pick_tb(gnz, 3);
+  const int LP = gnz | 1;
+  const size_t smem = (3 * (size_t)TB * LP + gnz) * sizeof(double2);
+  const int nblk = cdiv((long)c.sx * nyl, TB);
+  *nblk_out = nblk;
+  const double scaleinv = 1.0 / ((double)c.nx * c.ny * gnz);
+  if (ev) RESERVE(ctx, ps.partial, (size_t)std::max(nblk, 1) * 8);
+  if (nblk <= 0) return 0;
+  const TriWave tw = c.tri ? TriWave{ps.fkyx.p, ps.fkzx.p, ps.fkzy.p + yoff, ps.fkyx_g.p}
+                           : TriWave{nullptr, nullptr, nullptr, nullptr};
+#define ZK(NC, E, H)                                                                                              \
+  do {                                                                                                            \
+    auto kern = k_fft_z_poisson<NC, E, H>;                                                                        \
+    CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    kern<<<nblk, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.sx, nyl, ilog2(TB), LP, in, out, ps.greensfn.p, \
+                                                     ps.fkx.p, ps.fky.p + yoff, ps.fkz.p, ps.fkx_g.p,            \
+                                                     ps.fky_g.p + yoff, ps.fkz_g.p, c.nx, scaleinv, c.g_ewald,  \
+                                                     ps.partial.p, ps.p.dispersion, tw);                          \
+  } while (0)
+  {
+    ScopedTimer tk(ctx, K_FFT_Z_POISSON);
+    if (half) {
+      if (ad) { if (ev) ZK(1, 1, 1); else ZK(1, 0, 1); }
+      else { if (ev) ZK(3, 1, 1); else ZK(3, 0, 1); }
+    } else {
+      if (ad) { if (ev) ZK(1, 1, 0); else ZK(1, 0, 0); }
+      else { if (ev) ZK(3, 1, 0); else ZK(3, 0, 0); }
+    }
+  }
+#undef ZK
+  KERNEL_OK(ctx, "k_fft_z_poisson");
+  return 0;
+}
+
 int reduce_cols(b200md_ctx *ctx, PppmState &ps, long n, int ncol, const double *cols, double *host_out) {
   const int nb = cdiv(n, 256);
   RESERVE(ctx, ps.partial, (size_t)nb * ncol);
@@ -1106,12 +1291,41 @@ void compute_gf_denom(PppmConst &c) {
   for (int l = 0; l < order; l++) c.gf_b[l] *= gaminv;
 }
 
+// density [nplanes][ny][nx] (real) -> work [nplanes][ny][sx]: x and y transformed
 int fft3d_forward_xy(b200md_ctx *ctx, PppmState &ps, const double *density, double2 *work, int nplanes) {
   const PppmConst &c = ps.c;
-  PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1, 0};
-  TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD, K_FFT_X_FWD)));
-  PassGeom gy{(long)c.nx * nplanes, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
+  if (c.sx != c.nx) TRY(launch_x_r2c(ctx, ps.plan[0], (long)c.ny * nplanes, density, work, K_FFT_X_FWD));
+  else {
+    PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1, 0};
+    TRY((launch_pass<1, 1, 0>(ctx, ps.plan[0], gx, density, nullptr, work, nullptr, S_FWD, K_FFT_X_FWD)));
+  }
+  PassGeom gy{(long)c.sx * nplanes, c.sx, (long)c.sx * c.ny, (long)c.sx, 0};
   TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work, work, nullptr, S_FWD, K_FFT_Y_FWD)));
+  return 0;
+}
+
+// fields [npack][nplanes][ny][sx] (z already inverted) -> real bricks vd [ncomp][nplanes][ny][nx]: inverse y, inverse x
+int fft3d_inverse_yx(b200md_ctx *ctx, PppmState &ps, double2 *work2, double *vd, int nplanes) {
+  const PppmConst &c = ps.c;
+  const bool ad = ps.p.differentiation == 1, half = c.sx != c.nx;
+  const int npack = ad ? 1 : (half ? 3 : 2);
+  const long nreal = (long)c.nx * c.ny * nplanes, nspec = (long)c.sx * c.ny * nplanes;
+  PassGeom gy{(long)c.sx * nplanes * npack, c.sx, (long)c.sx * c.ny, (long)c.sx, 0};
+  TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work2, work2, nullptr, S_BWD, K_FFT_Y_INV)));
+  if (half) {
+    for (int comp = 0; comp < npack; comp++)
+      TRY(launch_x_c2r(ctx, ps.plan[0], (long)c.ny * nplanes, work2 + (size_t)comp * nspec, vd + (size_t)comp * nreal,
+                       K_FFT_X_INV));
+  } else if (ad) {
+    PassGeom gx{(long)c.ny * nplanes, 1, (long)c.nx, 1, 0};
+    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, work2, nullptr, vd, S_BWD, K_FFT_X_INV)));
+  } else {
+    // the x pass stores Re (and, for the first pack, Im as the second field)
+    PassGeom gxy{(long)c.ny * nplanes, 1, (long)c.nx, 1, nreal};
+    TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, work2, nullptr, vd, S_BWD, K_FFT_X_INV)));
+    PassGeom gz{(long)c.ny * nplanes, 1, (long)c.nx, 1, 0};
+    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, work2 + nreal, nullptr, vd + 2 * nreal, S_BWD, K_FFT_X_INV)));
+  }
   return 0;
 }
 
@@ -1218,30 +1432,7 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
       TRY(b2_comm_alltoallv(ctx, ps.tsend.p, scount, sdisp, ps.workT.p, rcount, rdisp));
     }
     // ---- z pass + Green's function + gradients + inverse z on my pencils ------------------------------------------
-    const int TB = pick_tb(gnz, 3);
-    const int LP = gnz | 1;
-    const size_t smem = (3 * (size_t)TB * LP + gnz) * sizeof(double2);
-    nblk_z = cdiv((long)nx * nyl, TB);
-    const double scaleinv = 1.0 / ((double)nx * ny * gnz);
-    if (ev) RESERVE(ctx, ps.partial, (size_t)std::max(nblk_z, 1) * 8);
-    if (nblk_z > 0) {
-#define ZK(NC, E)                                                                                               \
-  do {                                                                                                          \
-    auto kern = k_fft_z_poisson<NC, E>;                                                                         \
-    CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], nx, nyl, ilog2(TB), LP, workT, ps.workT2.p, ps.greensfn.p, \
-                                             ps.fkx.p, ps.fky.p + ps.ylos[me], ps.fkz.p, ps.fkx_g.p,            \
-                                             ps.fky_g.p + ps.ylos[me], scaleinv, c.g_ewald, ps.partial.p,       \
-                                             ps.p.dispersion, TriWave{nullptr, nullptr, nullptr, nullptr});     \
-  } while (0)
-      {
-        ScopedTimer tk(ctx, K_FFT_Z_POISSON);
-        if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
-        else { if (ev) ZK(3, 1); else ZK(3, 0); }
-      }
-#undef ZK
-      KERNEL_OK(ctx, "k_fft_z_poisson");
-    }
+    TRY(launch_z_poisson(ctx, ps, nyl, ps.ylos[me], gnz, workT, ps.workT2.p, ev, &nblk_z));
     // ---- transpose back, both packed transforms (Ex + i Ey, Ez) in one exchange: to rank q its planes (contiguous
     //      in [z][row][x]) ----------------------------------------------------------------------------------------
     const int npack = ad ? 1 : 2;
@@ -1359,22 +1550,26 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
 // vg_c) and run one inverse 3-D FFT whose last pass stores the real part.  7 bricks: u, v0..v5.
 static int peratom_fields(b200md_ctx *ctx, PppmState &ps, int do_e, int do_v) {
   const PppmConst &c = ps.c;
-  const long nfft = ps.nfft;
+  const long nfft = ps.nfft, nspec = (long)c.sx * c.ny * c.nz;
+  const bool half = c.sx != c.nx;
   RESERVE(ctx, ps.pa_fields, 7 * (size_t)nfft);
-  RESERVE(ctx, ps.pa_work, (size_t)nfft);
+  RESERVE(ctx, ps.pa_work, (size_t)nspec);
   PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
-  PassGeom gy{(long)c.nx * c.nz, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
-  PassGeom gz{(long)c.nx * c.ny, c.nx * c.ny, 0, (long)c.nx * c.ny, 0};
+  PassGeom gy{(long)c.sx * c.nz, c.sx, (long)c.sx * c.ny, (long)c.sx, 0};
+  PassGeom gz{(long)c.sx * c.ny, c.sx * c.ny, 0, (long)c.sx * c.ny, 0};
   TRY((launch_pass<0, 0, 0>(ctx, ps.plan[2], gz, nullptr, ps.work1.p, ps.work1.p, nullptr, S_FWD)));
   const double scaleinv = 1.0 / ((double)c.nx * c.ny * c.nz);
   for (int comp = do_e ? 0 : 1; comp < (do_v ? 7 : 1); comp++) {
-    k_peratom_mul<<<cdiv(nfft, 256), 256, 0, ctx->stream>>>(c, comp, scaleinv, ps.work1.p, ps.greensfn.p, ps.fkx.p,
-                                                            ps.fky.p, ps.fkz.p, ps.pa_work.p);
+    k_peratom_mul<<<cdiv(nspec, 256), 256, 0, ctx->stream>>>(c, comp, scaleinv, ps.work1.p, ps.greensfn.p, ps.fkx.p,
+                                                             ps.fky.p, ps.fkz.p, ps.pa_work.p);
     KERNEL_OK(ctx, "k_peratom_mul");
     TRY((launch_pass<0, 0, 0>(ctx, ps.plan[2], gz, nullptr, ps.pa_work.p, ps.pa_work.p, nullptr, S_BWD)));
     TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.pa_work.p, ps.pa_work.p, nullptr, S_BWD)));
-    TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.pa_work.p, nullptr, ps.pa_fields.p + (size_t)comp * nfft,
-                              S_BWD)));
+    if (half)
+      TRY(launch_x_c2r(ctx, ps.plan[0], (long)c.ny * c.nz, ps.pa_work.p, ps.pa_fields.p + (size_t)comp * nfft, -1));
+    else
+      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.pa_work.p, nullptr,
+                                ps.pa_fields.p + (size_t)comp * nfft, S_BWD)));
   }
   return 0;
 }
@@ -1521,45 +1716,9 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   {
     ScopedTimer tm(ctx, T_FFT);
     TRY(fft3d_forward_xy(ctx, ps, ps.density.p, ps.work1.p, c.nz));
-    const int TB = pick_tb(c.nz, 3);
-    const int LP = c.nz | 1;
-    const size_t smem = (3 * (size_t)TB * LP + c.nz) * sizeof(double2);
-    const long plane = (long)c.nx * c.ny;
-    nblk_z = cdiv(plane, TB);
-    const double scaleinv = 1.0 / ((double)c.nx * c.ny * c.nz);
-    if (ev) RESERVE(ctx, ps.partial, (size_t)nblk_z * 8);
-    const TriWave tw = c.tri ? TriWave{ps.fkyx.p, ps.fkzx.p, ps.fkzy.p, ps.fkyx_g.p}
-                             : TriWave{nullptr, nullptr, nullptr, nullptr};
-#define ZK(NC, E)                                                                                             \
-  do {                                                                                                        \
-    auto kern = k_fft_z_poisson<NC, E>;                                                                       \
-    CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    kern<<<nblk_z, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.nx, c.ny, ilog2(TB), LP, ps.work1.p, ps.work2.p,          \
-                                             ps.greensfn.p, ps.fkx.p, ps.fky.p, ps.fkz.p, ps.fkx_g.p, ps.fky_g.p,   \
-                                             scaleinv, c.g_ewald, ps.partial.p, ps.p.dispersion, tw);        \
-  } while (0)
-    {
-      ScopedTimer tk(ctx, K_FFT_Z_POISSON);
-      if (ad) { if (ev) ZK(1, 1); else ZK(1, 0); }
-      else { if (ev) ZK(3, 1); else ZK(3, 0); }
-    }
-#undef ZK
-    KERNEL_OK(ctx, "k_fft_z_poisson");
-    // inverse y over the packed transforms (2 for ik: Ex + i Ey and Ez; 1 for ad), inverse x storing the real part
-    // (and, for the first pack, the imaginary part as the second field)
-    const int npack = ad ? 1 : 2;
-    PassGeom gy{(long)c.nx * c.nz * npack, c.nx, (long)c.nx * c.ny, (long)c.nx, 0};
-    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, ps.work2.p, ps.work2.p, nullptr, S_BWD, K_FFT_Y_INV)));
-    if (ad) {
-      PassGeom gx{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gx, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD, K_FFT_X_INV)));
-    } else {
-      PassGeom gxy{(long)c.ny * c.nz, 1, (long)c.nx, 1, nfft};
-      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, ps.work2.p, nullptr, ps.vd.p, S_BWD, K_FFT_X_INV)));
-      PassGeom gz{(long)c.ny * c.nz, 1, (long)c.nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, ps.work2.p + nfft, nullptr, ps.vd.p + 2 * nfft, S_BWD,
-                                K_FFT_X_INV)));
-    }
+    TRY(launch_z_poisson(ctx, ps, c.ny, 0, c.nz, ps.work1.p, ps.work2.p, ev, &nblk_z));
+    // inverse y over the transformed fields, inverse x storing the real bricks
+    TRY(fft3d_inverse_yx(ctx, ps, ps.work2.p, ps.vd.p, c.nz));
   }
   if (ev) {
     ScopedTimer tm(ctx, T_POISSON);
@@ -1740,6 +1899,7 @@ static void free_state(b200md_ctx *ctx, PppmState *&slot) {
   b2_comm_peer_free(ctx, ps->symW);
   for (int d = 0; d < 3; d++) ps->tw[d].free_();
   ps->fkx_g.free_(); ps->fky_g.free_(); ps->fkyx.free_(); ps->fkzx.free_(); ps->fkzy.free_(); ps->fkyx_g.free_();
+  ps->fkz_g.free_();
   ps->greensfn.free_(); ps->fkx.free_(); ps->fky.free_(); ps->fkz.free_(); ps->density.free_(); ps->vd.free_();
   ps->work1.free_(); ps->work2.free_(); ps->sf_pre.free_(); ps->Btype.free_();
   ps->key.free_(); ps->cell_count.free_(); ps->cell_start.free_(); ps->cursor.free_(); ps->perm.free_();
@@ -1790,6 +1950,8 @@ int b2_pppm_compute(b200md_ctx *ctx, int eflag, int vflag, double *energy, doubl
       return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial is not provided for the dispersion grid");
     if (b2_comm_nranks(ctx) > 1)
       return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial from PPPM is single-GPU only in this build");
+    if (ctx->pppm->c.tri)
+      return b2_fail(ctx, B200MD_EINVAL, "per-atom energy/virial from PPPM is not provided on a triclinic box");
   }
   PppmView v;
   v.n = ctx->nlocal;
@@ -1983,6 +2145,16 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
       }
     }
   }
+  // half-spectrum transforms: the default (B200MD_R2C=0 keeps the complex-to-complex passes, for comparison runs)
+  {
+    const char *re = getenv("B200MD_R2C");
+    ps->r2c = !(re && re[0] == '0');
+    if (ps->nranks > 1) ps->r2c = false;   // slab-decomposed solve: complex-to-complex passes
+    // triclinic: the influence function of a Nyquist-plane point and of its mirror image differ (x2lamdaT of wave
+    // numbers that do not change sign), which half a spectrum cannot hold: complex-to-complex passes
+    if (tri) ps->r2c = false;
+  }
+  c.sx = ps->r2c ? p->nx / 2 + 1 : p->nx;
   ps->nfft = (long)p->nx * p->ny * c.nz;   // points of the local brick (= the whole grid on one GPU)
   if ((long)p->nx * p->ny * p->nz > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");
   compute_rho_coeffs(c);
@@ -2001,7 +2173,7 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   const bool ad = p->differentiation == 1;
   PppmConst cg = c;             // global-grid view for the Green's function kernels
   cg.nz = p->nz;
-  const long ngf = (long)p->nx * gf_nyl * p->nz;   // Green's function points held here ([z][y rows of this rank][x])
+  const long ngf = (long)c.sx * gf_nyl * p->nz;   // Green's function points held here ([z][y rows of this rank][sx])
   RESERVE(ctx, ps->greensfn, (size_t)std::max(ngf, 1L));
   RESERVE(ctx, ps->density, (size_t)nfft);
   RESERVE(ctx, ps->work1, (size_t)nfft);
@@ -2019,8 +2191,8 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
       fk.assign(ng[d], 0.0);
       for (int i = 0; i < ng[d]; i++) fk[i] = unitk * (i - ng[d] * (2 * i / ng[d]));
       CUDA_OK(ctx, cudaMemcpy(dst[d]->p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));
-      if (d < 2) {   // gradient copies with the Nyquist entry dropped (see k_fft_z_poisson)
-        DevBuf<double> &gdst = d == 0 ? ps->fkx_g : ps->fky_g;
+      {   // gradient copies with the Nyquist entry dropped (see k_fft_z_poisson; z: half-spectrum path only)
+        DevBuf<double> &gdst = d == 0 ? ps->fkx_g : (d == 1 ? ps->fky_g : ps->fkz_g);
         RESERVE(ctx, gdst, (size_t)ng[d]);
         if (ng[d] % 2 == 0) fk[ng[d] / 2] = 0.0;
         CUDA_OK(ctx, cudaMemcpy(gdst.p, fk.data(), ng[d] * sizeof(double), cudaMemcpyHostToDevice));
@@ -2039,6 +2211,7 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
       for (int j = 0; j < p->ny; j++) zy[j] = c.hinv[3] * k2PI * per(j, p->ny);
       RESERVE(ctx, ps->fkyx, yx.size()); RESERVE(ctx, ps->fkzx, zx.size());
       RESERVE(ctx, ps->fkzy, zy.size()); RESERVE(ctx, ps->fkyx_g, yxg.size());
+
       CUDA_OK(ctx, cudaMemcpy(ps->fkyx.p, yx.data(), yx.size() * sizeof(double), cudaMemcpyHostToDevice));
       CUDA_OK(ctx, cudaMemcpy(ps->fkzx.p, zx.data(), zx.size() * sizeof(double), cudaMemcpyHostToDevice));
       CUDA_OK(ctx, cudaMemcpy(ps->fkzy.p, zy.data(), zy.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -2226,7 +2399,21 @@ int b200md_pppm_download(b200md_ctx *ctx, double *density_fft, double *greensfn,
   const bool ad = ps.p.differentiation == 1;
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   if (density_fft) CUDA_OK(ctx, cudaMemcpy(density_fft, ps.density.p, nb, cudaMemcpyDeviceToHost));
-  if (greensfn) CUDA_OK(ctx, cudaMemcpy(greensfn, ps.greensfn.p, nb, cudaMemcpyDeviceToHost));
+  if (greensfn) {
+    const PppmConst &c = ps.c;
+    if (c.sx == c.nx) CUDA_OK(ctx, cudaMemcpy(greensfn, ps.greensfn.p, nb, cudaMemcpyDeviceToHost));
+    else {   // half spectrum [nz][ny][sx] -> the full array: G(-k) = G(k)
+      std::vector<double> h((size_t)c.sx * c.ny * c.nz);
+      CUDA_OK(ctx, cudaMemcpy(h.data(), ps.greensfn.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < c.nz; k++)
+        for (int j = 0; j < c.ny; j++)
+          for (int i = 0; i < c.nx; i++) {
+            const bool mir = i >= c.sx;
+            const int ii = mir ? c.nx - i : i, jj = mir ? (c.ny - j) % c.ny : j, kk = mir ? (c.nz - k) % c.nz : k;
+            greensfn[((size_t)k * c.ny + j) * c.nx + i] = h[((size_t)kk * c.ny + jj) * c.sx + ii];
+          }
+    }
+  }
   if (field_x) CUDA_OK(ctx, cudaMemcpy(field_x, ps.vd.p, nb, cudaMemcpyDeviceToHost));
   if (field_y) CUDA_OK(ctx, cudaMemcpy(field_y, ps.vd.p + (ad ? 0 : ps.nfft), nb, cudaMemcpyDeviceToHost));
   if (field_z) CUDA_OK(ctx, cudaMemcpy(field_z, ps.vd.p + (ad ? 0 : 2 * ps.nfft), nb, cudaMemcpyDeviceToHost));

@@ -25,6 +25,9 @@ struct PppmConst {  // everything the kernels need by value
   // pppm_intel.cpp:151-156); boxlo = 0 and delinv = grid size then.  hinv = Domain::h_inv (xx, yy, zz, yz, xz, xy)
   int tri;
   double hinv[6], boxlo_box[3];
+  // x extent of the spectral arrays: nx (complex-to-complex passes) or nx / 2 + 1 (real-to-complex: only kx >= 0 is
+  // stored, the rest follows from rho(-k) = conj rho(k))
+  int sx;
 };
 
 struct PppmState {
@@ -38,6 +41,7 @@ struct PppmState {
   // wave vector of point (ix, iy, iz): kx = fkx[ix], ky = fky[iy] + fkyx[ix], kz = fkz[iz] + fkzx[ix] + fkzy[iy]; the
   // cross terms are those of Domain::x2lamdaT on a triclinic box (setup_triclinic) and zero on an orthogonal one
   DevBuf<double> fkyx, fkzx, fkzy, fkyx_g;
+  DevBuf<double> fkz_g;   // half-spectrum path: the z gradient has its Nyquist entry zeroed too
   DevBuf<double> greensfn, fkx, fky, fkz, density, vd;  // vd: 3*nfft (ik) or nfft (ad: u)
   DevBuf<double2> work1, work2;                         // work2: 3*nfft (ik) / nfft (ad)
   DevBuf<double> sf_pre;                                // ad: 6*nfft
@@ -88,6 +92,7 @@ struct PppmState {
   // the other ranks store straight into them
   PeerBuf symT, symW;
   bool p2p = false, p2p_dma = true;
+  bool r2c = true;    // half-spectrum transforms (B200MD_R2C=0 selects the complex-to-complex passes)
 };
 
 struct PppmView {
