@@ -332,9 +332,16 @@ class Config:
 # ---------------------------------------------------------------------------------------------------------------------
 # per-kernel roofline (SURVEY §8d work models; launch times from CUDA events recorded on the launching stream)
 
+def pppm_half_spectrum(world):
+    """mirrors b200md_pppm_setup: real-to-complex transforms unless B200MD_R2C=0 (orthogonal boxes)"""
+    return os.environ.get("B200MD_R2C", "1")[:1] != "0"
+
+
 def kernel_rooflines(cfg, timers, steps, N, nall, entries, F, G_tiles, fp_peak, hbm_peak, prec, ncomp_packs=2,
-                     fp32_peak=None):
-    """timers: name -> (ms, calls) accumulated over `steps` timed steps on this rank.  Returns (list, ideal ms/step)."""
+                     fp32_peak=None, half_nx=0):
+    """timers: name -> (ms, calls) accumulated over `steps` timed steps on this rank.  Returns (list, ideal ms/step).
+    half_nx > 0: the half-spectrum (real-to-complex) PPPM transforms are on; the spectral arrays hold
+    Fs = F (nx/2 + 1) / nx points and the three gradient fields are transformed one by one."""
     flt = 8 if prec == "double" else 4
     fl = PAIR_FLOPS.get(cfg["flops_key"]) if cfg.get("flops_key") else None
     rows = []
@@ -376,16 +383,26 @@ def kernel_rooflines(cfg, timers, steps, N, nall, entries, F, G_tiles, fp_peak, 
         "writes 4 B x entries + 8 B x N, reads the hit masks")
     add("k_rho_tiles", "k_rho_tiles", "hbm", 40.0 * N + 8.0 * G_tiles, "40 B x N + 8 B x tile-block points")
     add("k_rho_fold", "k_rho_fold", "hbm", 8.0 * G_tiles + 8.0 * F, "reads every tile-block point once, writes 8 B x F")
-    add("k_fft_pass x fwd (real in)", "k_fft_x_fwd", "hbm", 24.0 * F, "8 B x F in, 16 B x F out")
-    add("k_fft_pass y fwd", "k_fft_y_fwd", "hbm", 32.0 * F, "16 B x F in and out")
-    add("k_fft_z_poisson", "k_fft_z_poisson", "hbm", (16.0 + 8.0 + 16.0 * ncomp_packs) * F,
-        "16 B x F in, 8 B x F Green's function, 16 B x F out per packed field")
-    add("k_fft_pass y inv", "k_fft_y_inv", "hbm", 32.0 * ncomp_packs * F, "16 B x F in and out per packed field")
-    xinv_ms, xinv_calls = timers.get("k_fft_x_inv", (0.0, 0))
-    if xinv_calls:
-        per = 56.0 * F / 2.0 if ncomp_packs == 2 else 24.0 * F
-        add("k_fft_pass x inv (real out)", "k_fft_x_inv", "hbm", per,
-            "16 B x F in per packed field, 8 B x F out per field component (average of the two launches)")
+    if half_nx:
+        Fs = F * (half_nx // 2 + 1) / half_nx
+        nf = 3 if ncomp_packs == 2 else 1          # fields transformed back: Ex, Ey, Ez (ik) or u (ad)
+        add("k_fft_x_r2c (x fwd, real in)", "k_fft_x_fwd", "hbm", 8.0 * F + 16.0 * Fs, "8 B x F in, 16 B x Fs out (half spectrum)")
+        add("k_fft_pass y fwd", "k_fft_y_fwd", "hbm", 32.0 * Fs, "16 B x Fs in and out")
+        add("k_fft_z_poisson", "k_fft_z_poisson", "hbm", (16.0 + 8.0 + 16.0 * nf) * Fs,
+            "16 B x Fs in, 8 B x Fs Green's function, 16 B x Fs out per field")
+        add("k_fft_pass y inv", "k_fft_y_inv", "hbm", 32.0 * nf * Fs, "16 B x Fs in and out per field")
+        add("k_fft_x_c2r (x inv, real out)", "k_fft_x_inv", "hbm", 16.0 * Fs + 8.0 * F, "16 B x Fs in, 8 B x F out per field")
+    else:
+        add("k_fft_pass x fwd (real in)", "k_fft_x_fwd", "hbm", 24.0 * F, "8 B x F in, 16 B x F out")
+        add("k_fft_pass y fwd", "k_fft_y_fwd", "hbm", 32.0 * F, "16 B x F in and out")
+        add("k_fft_z_poisson", "k_fft_z_poisson", "hbm", (16.0 + 8.0 + 16.0 * ncomp_packs) * F,
+            "16 B x F in, 8 B x F Green's function, 16 B x F out per packed field")
+        add("k_fft_pass y inv", "k_fft_y_inv", "hbm", 32.0 * ncomp_packs * F, "16 B x F in and out per packed field")
+        xinv_ms, xinv_calls = timers.get("k_fft_x_inv", (0.0, 0))
+        if xinv_calls:
+            per = 56.0 * F / 2.0 if ncomp_packs == 2 else 24.0 * F
+            add("k_fft_pass x inv (real out)", "k_fft_x_inv", "hbm", per,
+                "16 B x F in per packed field, 8 B x F out per field component (average of the two launches)")
     add("k_fieldforce", "fieldforce", "hbm", 104.0 * N + 24.0 * F,
         "40 B x N sorted atoms + 64 B x N force read-modify-write + 24 B x F field bricks (the L1 data pipe binds, "
         "see profiles/r02_ncu_k_fieldforce.txt)")
@@ -635,7 +652,8 @@ def run_b200(args):
         G_tiles = int(np.prod([-(-g // 8) for g in (grid[0], grid[1], max(grid[2] // world, 8))])) * E ** 3
     fp32_peak = ctx.microbench(1)
     rows, ideal_ms, nbar = kernel_rooflines(desc, timers, args.steps, nlocal0, nlocal0 + int(st1["nghost"]), entries_local,
-                                            F, G_tiles, fp_peak, hbm_peak, args.prec, fp32_peak=fp32_peak)
+                                            F, G_tiles, fp_peak, hbm_peak, args.prec, fp32_peak=fp32_peak,
+                                            half_nx=(grid[0] if grid and pppm_half_spectrum(world) else 0))
     for r in rows:
         r["share_of_step"] = round(r["ms_per_step"] / ms_per_step, 4)
     rows = [r for r in rows if r["share_of_step"] >= 0.01 or r["kernel"] == "k_pair"]

@@ -866,8 +866,8 @@ __global__ void __launch_bounds__(512)
 k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *__restrict__ in,
                 double2 *__restrict__ out, const double *__restrict__ greensfn, const double *__restrict__ fkx,
                 const double *__restrict__ fky, const double *__restrict__ fkz, const double *__restrict__ fkxg,
-                const double *__restrict__ fkyg, const double *__restrict__ fkzg, int nxfull, double scaleinv,
-                double g_ewald, double *__restrict__ ev_partial, int disp, TriWave tw) {
+                const double *__restrict__ fkyg, const double *__restrict__ fkzg, int nxfull, int iy_nyq,
+                double scaleinv, double g_ewald, double *__restrict__ ev_partial, int disp, TriWave tw) {
   extern __shared__ double2 smem[];
   const int TB = 1 << lgTB;
   const int lgtpl = 31 - __clz(blockDim.x) - lgTB;
@@ -919,7 +919,8 @@ k_fft_z_poisson(FftPlan1d pl, int nx, int ny, int lgTB, int LP, const double2 *_
           acc[3] += eng * (1.0 + vterm * kz * kz);
           if (HALF && wgt == 2.0) {
             // the point and its mirror image: (-kx, +-ky, +-kz), a wave number on its Nyquist plane keeps its sign
-            const double e1 = 0.5 * eng, sy = 2 * iy == ny ? 1.0 : -1.0, sz = 2 * k == n ? 1.0 : -1.0;
+            // (iy_nyq: the LOCAL row that holds the y Nyquist plane, -1 if none: ny is this rank's row count)
+            const double e1 = 0.5 * eng, sy = iy == iy_nyq ? 1.0 : -1.0, sz = 2 * k == n ? 1.0 : -1.0;
             acc[4] += e1 * (vterm * kx * ky) * (1.0 - sy);
             acc[5] += e1 * (vterm * kx * kz) * (1.0 - sz);
             acc[6] += e1 * (vterm * ky * kz) * (1.0 + sy * sz);
@@ -1211,6 +1212,7 @@ int launch_z_poisson(b200md_ctx *ctx, PppmState &ps, int nyl, int yoff, int gnz,
   const double scaleinv = 1.0 / ((double)c.nx * c.ny * gnz);
   if (ev) RESERVE(ctx, ps.partial, (size_t)std::max(nblk, 1) * 8);
   if (nblk <= 0) return 0;
+  const int iy_nyq = (c.ny % 2 == 0) ? c.ny / 2 - yoff : -1;   // local row of the y Nyquist plane (may be outside)
   const TriWave tw = c.tri ? TriWave{ps.fkyx.p, ps.fkzx.p, ps.fkzy.p + yoff, ps.fkyx_g.p}
                            : TriWave{nullptr, nullptr, nullptr, nullptr};
 #define ZK(NC, E, H)                                                                                              \
@@ -1219,7 +1221,8 @@ int launch_z_poisson(b200md_ctx *ctx, PppmState &ps, int nyl, int yoff, int gnz,
     CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     kern<<<nblk, fft_threads(), smem, ctx->stream>>>(ps.plan[2], c.sx, nyl, ilog2(TB), LP, in, out, ps.greensfn.p, \
                                                      ps.fkx.p, ps.fky.p + yoff, ps.fkz.p, ps.fkx_g.p,            \
-                                                     ps.fky_g.p + yoff, ps.fkz_g.p, c.nx, scaleinv, c.g_ewald,  \
+                                                     ps.fky_g.p + yoff, ps.fkz_g.p, c.nx, iy_nyq, scaleinv,     \
+                                                     c.g_ewald,                                                   \
                                                      ps.partial.p, ps.p.dispersion, tw);                          \
   } while (0)
   {
@@ -1337,6 +1340,8 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   const int P = ps.nranks, me = ps.rank, lower = (me + P - 1) % P, upper = (me + 1) % P;
   const int nx = c.nx, ny = c.ny, gnz = ps.gnz;
   const long plane = (long)nx * ny;
+  const int sx = c.sx;                        // x extent of the spectral arrays (nx / 2 + 1 with half-spectrum transforms)
+  const long splane = (long)sx * ny;
   const int nzo = ps.pzhi[me] - ps.pzlo[me];
   const bool ad = ps.p.differentiation == 1;
   const int ncomp = ad ? 1 : 3;   // field bricks: Ex, Ey, Ez (ik) or the potential u (ad)
@@ -1372,25 +1377,26 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
   RankRows rr;
   rr.n = P;
   const int nyl = ps.yhis[me] - ps.ylos[me];
-  const long nT = (long)nx * nyl * gnz;   // points of my z-pencil block
+  const long nT = (long)sx * nyl * gnz;   // points of my z-pencil block
+  const int npack = ad ? 1 : (sx != nx ? 3 : 2);   // transforms coming back: u | Ex, Ey, Ez | Ex + i Ey, Ez
   {
     ScopedTimer tm(ctx, T_FFT);
     // ---- forward x, y on the owned planes -------------------------------------------------------------------------
-    RESERVE(ctx, ps.work1, (size_t)plane * nzo);
+    RESERVE(ctx, ps.work1, (size_t)splane * nzo);
     TRY(fft3d_forward_xy(ctx, ps, ps.dens_own.p, ps.work1.p, nzo));
     // ---- transpose to z pencils: block for rank q = my planes x q's rows; lands at q in [z][row][x] order ---------
-    RESERVE(ctx, ps.tsend, (size_t)plane * nzo);
+    RESERVE(ctx, ps.tsend, (size_t)splane * nzo);
     RESERVE(ctx, ps.workT, (size_t)nT);
-    RESERVE(ctx, ps.workT2, (size_t)nT * ncomp);
+    RESERVE(ctx, ps.workT2, (size_t)nT * npack);
     size_t scount[8], sdisp[8], rcount[8], rdisp[8];
     long off = 0;
     for (int q = 0; q < P; q++) {
       rr.ylo[q] = ps.ylos[q]; rr.yhi[q] = ps.yhis[q]; rr.boff[q] = off;
-      const long cnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * nx;
+      const long cnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * sx;
       scount[q] = cnt * sizeof(double2); sdisp[q] = off * sizeof(double2);
       off += cnt;
-      rcount[q] = (size_t)(ps.pzhi[q] - ps.pzlo[q]) * nyl * nx * sizeof(double2);
-      rdisp[q] = (size_t)ps.pzlo[q] * nyl * nx * sizeof(double2);
+      rcount[q] = (size_t)(ps.pzhi[q] - ps.pzlo[q]) * nyl * sx * sizeof(double2);
+      rdisp[q] = (size_t)ps.pzlo[q] * nyl * sx * sizeof(double2);
     }
     double2 *workT = ps.p2p ? (double2 *)ps.symT.local : ps.workT.p;
     PeerPtrs peersT, peersW;
@@ -1412,30 +1418,28 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
         const int q = (me + k) % P;   // start with myself, then round the ring: spreads the traffic over the peers
         const int nylq = ps.yhis[q] - ps.ylos[q];
         if (nylq == 0) continue;
-        CUDA_OK(ctx, cudaMemcpy2DAsync(peersT.p[q] + (size_t)ps.pzlo[me] * nylq * nx, (size_t)nylq * nx * sizeof(double2),
-                                       ps.work1.p + (size_t)ps.ylos[q] * nx, (size_t)plane * sizeof(double2),
-                                       (size_t)nylq * nx * sizeof(double2), (size_t)nzo, cudaMemcpyDeviceToDevice,
+        CUDA_OK(ctx, cudaMemcpy2DAsync(peersT.p[q] + (size_t)ps.pzlo[me] * nylq * sx, (size_t)nylq * sx * sizeof(double2),
+                                       ps.work1.p + (size_t)ps.ylos[q] * sx, (size_t)splane * sizeof(double2),
+                                       (size_t)nylq * sx * sizeof(double2), (size_t)nzo, cudaMemcpyDeviceToDevice,
                                        ctx->stream));
       }
       TRY(b2_comm_barrier(ctx));
     } else if (ps.p2p) {
       // every rank stores its planes straight into the pencil blocks of their owners (NVLink stores from the kernel);
       // the barrier orders those stores before the z pass of every rank.
-      if (plane * nzo > 0) {
-        k_tr_scatter_fwd<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, ps.pzlo[me], rr, peersT, ps.work1.p);
+      if (splane * nzo > 0) {
+        k_tr_scatter_fwd<<<cdiv(splane * nzo, 256), 256, 0, ctx->stream>>>(sx, ny, nzo, ps.pzlo[me], rr, peersT, ps.work1.p);
         KERNEL_OK(ctx, "k_tr_scatter_fwd");
       }
       TRY(b2_comm_barrier(ctx));
     } else {
-      k_tr_pack<<<cdiv(plane * nzo, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, rr, ps.work1.p, ps.tsend.p);
+      k_tr_pack<<<cdiv(splane * nzo, 256), 256, 0, ctx->stream>>>(sx, ny, nzo, rr, ps.work1.p, ps.tsend.p);
       KERNEL_OK(ctx, "k_tr_pack");
       TRY(b2_comm_alltoallv(ctx, ps.tsend.p, scount, sdisp, ps.workT.p, rcount, rdisp));
     }
     // ---- z pass + Green's function + gradients + inverse z on my pencils ------------------------------------------
     TRY(launch_z_poisson(ctx, ps, nyl, ps.ylos[me], gnz, workT, ps.workT2.p, ev, &nblk_z));
-    // ---- transpose back, both packed transforms (Ex + i Ey, Ez) in one exchange: to rank q its planes (contiguous
-    //      in [z][row][x]) ----------------------------------------------------------------------------------------
-    const int npack = ad ? 1 : 2;
+    // ---- transpose back, all transformed fields in one exchange: to rank q its planes (contiguous in [z][row][x]) --
     double2 *work2 = ps.p2p ? (double2 *)ps.symW.local : nullptr;
     if (ps.p2p && ps.p2p_dma) {
       // the same the other way: per destination and packed field one 2-D copy puts my rows of its planes where its
@@ -1446,57 +1450,46 @@ int poisson_multi(b200md_ctx *ctx, PppmState &ps, int ev, double *evsum) {
         const int nzq = ps.pzhi[q] - ps.pzlo[q];
         if (nzq == 0) continue;
         for (int comp = 0; comp < npack; comp++)
-          CUDA_OK(ctx, cudaMemcpy2DAsync(peersW.p[q] + ((size_t)comp * nzq * ny + ps.ylos[me]) * nx, (size_t)plane * sizeof(double2),
-                                         ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * nx,
-                                         (size_t)nyl * nx * sizeof(double2), (size_t)nyl * nx * sizeof(double2), (size_t)nzq,
+          CUDA_OK(ctx, cudaMemcpy2DAsync(peersW.p[q] + ((size_t)comp * nzq * ny + ps.ylos[me]) * sx, (size_t)splane * sizeof(double2),
+                                         ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * sx,
+                                         (size_t)nyl * sx * sizeof(double2), (size_t)nyl * sx * sizeof(double2), (size_t)nzq,
                                          cudaMemcpyDeviceToDevice, ctx->stream));
       }
       TRY(b2_comm_barrier(ctx));
     } else if (ps.p2p) {
       // kernel flavour of the same: every rank stores its pencils into the plane blocks of their owners
       if (nT > 0) {
-        k_tr_scatter_bwd<<<cdiv(nT * npack, 256), 256, 0, ctx->stream>>>(nx, ny, nyl, gnz, ps.ylos[me], npack, rp, peersW,
+        k_tr_scatter_bwd<<<cdiv(nT * npack, 256), 256, 0, ctx->stream>>>(sx, ny, nyl, gnz, ps.ylos[me], npack, rp, peersW,
                                                                         ps.workT2.p);
         KERNEL_OK(ctx, "k_tr_scatter_bwd");
       }
       TRY(b2_comm_barrier(ctx));
     } else {
-    RESERVE(ctx, ps.trecv, (size_t)plane * nzo * npack);
+    RESERVE(ctx, ps.trecv, (size_t)splane * nzo * npack);
     {
       CommGroup grp(ctx);
       long roff = 0;
       for (int q = 0; q < P; q++) {
-        const long scnt = (long)(ps.pzhi[q] - ps.pzlo[q]) * nyl * nx;
-        const long rcnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * nx;
+        const long scnt = (long)(ps.pzhi[q] - ps.pzlo[q]) * nyl * sx;
+        const long rcnt = (long)nzo * (ps.yhis[q] - ps.ylos[q]) * sx;
         rr.boff[q] = roff;
         for (int comp = 0; comp < npack; comp++) {
-          TRY(grp.send(ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * nx, scnt * sizeof(double2), q));
+          TRY(grp.send(ps.workT2.p + (size_t)comp * nT + (size_t)ps.pzlo[q] * nyl * sx, scnt * sizeof(double2), q));
           TRY(grp.recv(ps.trecv.p + roff + (size_t)comp * rcnt, rcnt * sizeof(double2), q));
         }
         roff += rcnt * npack;
       }
       TRY(grp.end());
     }
-    RESERVE(ctx, ps.work2, (size_t)plane * nzo * npack);
-    k_tr_unpack<<<cdiv(plane * nzo * npack, 256), 256, 0, ctx->stream>>>(nx, ny, nzo, npack, rr, ps.trecv.p, ps.work2.p);
+    RESERVE(ctx, ps.work2, (size_t)splane * nzo * npack);
+    k_tr_unpack<<<cdiv(splane * nzo * npack, 256), 256, 0, ctx->stream>>>(sx, ny, nzo, npack, rr, ps.trecv.p, ps.work2.p);
     KERNEL_OK(ctx, "k_tr_unpack");
     work2 = ps.work2.p;
     }
-    // ---- inverse y, x on the owned planes; the x pass stores Re (and Im of the first pack) as the three fields ------
+    // ---- inverse y, x on the owned planes -> the real field bricks of my planes -----------------------------------
     const long nown = plane * nzo;
     RESERVE(ctx, ps.vd_own, (size_t)nown * ncomp);
-    PassGeom gy{(long)nx * nzo * npack, nx, plane, (long)nx, 0};
-    TRY((launch_pass<0, 0, 0>(ctx, ps.plan[1], gy, nullptr, work2, work2, nullptr, S_BWD, K_FFT_Y_INV)));
-    if (ad) {
-      PassGeom gu{(long)ny * nzo, 1, (long)nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gu, nullptr, work2, nullptr, ps.vd_own.p, S_BWD, K_FFT_X_INV)));
-    } else {
-      PassGeom gxy{(long)ny * nzo, 1, (long)nx, 1, nown};
-      TRY((launch_pass<1, 0, 2>(ctx, ps.plan[0], gxy, nullptr, work2, nullptr, ps.vd_own.p, S_BWD, K_FFT_X_INV)));
-      PassGeom gz{(long)ny * nzo, 1, (long)nx, 1, 0};
-      TRY((launch_pass<1, 0, 1>(ctx, ps.plan[0], gz, nullptr, work2 + nown, nullptr, ps.vd_own.p + 2 * nown, S_BWD,
-                                K_FFT_X_INV)));
-    }
+    TRY(fft3d_inverse_yx(ctx, ps, work2, ps.vd_own.p, nzo));
   }
   {
     ScopedTimer tm(ctx, T_COMM);
@@ -2104,6 +2097,15 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
   ps->nranks = b2_comm_nranks(ctx);
   ps->rank = b2_comm_rank(ctx);
   ps->skin_setup = ctx->neigh.skin;
+  // half-spectrum transforms: the default (B200MD_R2C=0 keeps the complex-to-complex passes, for comparison runs)
+  {
+    const char *re = getenv("B200MD_R2C");
+    ps->r2c = !(re && re[0] == '0');
+    // triclinic: the influence function of a Nyquist-plane point and of its mirror image differ (x2lamdaT of wave
+    // numbers that do not change sign), which half a spectrum cannot hold: complex-to-complex passes
+    if (tri) ps->r2c = false;
+  }
+  c.sx = ps->r2c ? p->nx / 2 + 1 : p->nx;
   int gf_yoff = 0, gf_nyl = p->ny;
   if (ps->nranks > 1) {
     // z-slab decomposition: owned planes, local brick (owned + stencil/skin halo) and z-pencil rows of every rank
@@ -2131,9 +2133,9 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
         maxrows = std::max(maxrows, ps->yhis[q] - ps->ylos[q]);
         maxplanes = std::max(maxplanes, ps->pzhi[q] - ps->pzlo[q]);
       }
-      const int npack = p->differentiation == 1 ? 1 : 2;
-      const size_t bytesT = ((size_t)p->nx * maxrows * p->nz + 16) * sizeof(double2);
-      const size_t bytesW = ((size_t)p->nx * p->ny * maxplanes * npack + 16) * sizeof(double2);
+      const int npack = p->differentiation == 1 ? 1 : (ps->r2c ? 3 : 2);
+      const size_t bytesT = ((size_t)c.sx * maxrows * p->nz + 16) * sizeof(double2);
+      const size_t bytesW = ((size_t)c.sx * p->ny * maxplanes * npack + 16) * sizeof(double2);
       int okT = 0, okW = 0;
       TRY(b2_comm_peer_alloc(ctx, ps->symT, bytesT, &okT));
       TRY(b2_comm_peer_alloc(ctx, ps->symW, bytesW, &okW));
@@ -2145,16 +2147,6 @@ int b200md_pppm_setup(b200md_ctx *ctx, const b200md_pppm_params *p) {
       }
     }
   }
-  // half-spectrum transforms: the default (B200MD_R2C=0 keeps the complex-to-complex passes, for comparison runs)
-  {
-    const char *re = getenv("B200MD_R2C");
-    ps->r2c = !(re && re[0] == '0');
-    if (ps->nranks > 1) ps->r2c = false;   // slab-decomposed solve: complex-to-complex passes
-    // triclinic: the influence function of a Nyquist-plane point and of its mirror image differ (x2lamdaT of wave
-    // numbers that do not change sign), which half a spectrum cannot hold: complex-to-complex passes
-    if (tri) ps->r2c = false;
-  }
-  c.sx = ps->r2c ? p->nx / 2 + 1 : p->nx;
   ps->nfft = (long)p->nx * p->ny * c.nz;   // points of the local brick (= the whole grid on one GPU)
   if ((long)p->nx * p->ny * p->nz > 2000000000L) return b2_fail(ctx, B200MD_EINVAL, "PPPM grid has too many points");
   compute_rho_coeffs(c);

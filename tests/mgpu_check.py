@@ -160,7 +160,9 @@ if rank == 0:
     print("step %d: x err %.3e  force err %.3e  etot err %.3e  ke err %.3e" %
           (nsteps, np.abs(dx).max(), np.abs(g1["f"] - dr["f"]).max() / fs,
            abs(th1[0] + th1[1] + th1[8] - r1[0] - r1[1] - r1[8]) / abs(r1[0] + r1[1] + r1[8]), abs(th1[15] - r1[15]) / r1[15]))
-    ok = np.abs(g0["f"] - f0).max() / fs < 1e-9 and np.abs(dx).max() < 1e-8
+    ev_err = max(abs(th0[0] + th0[1] - r0[0] - r0[1]) / abs(r0[0] + r0[1]), abs(th0[8] - r0[8]) / abs(r0[8]),
+                 e(th0[2:8] + th0[9:15], r0[2:8] + r0[9:15]))
+    ok = np.abs(g0["f"] - f0).max() / fs < 1e-9 and np.abs(dx).max() < 1e-8 and ev_err < 1e-10
     print("MGPU CHECK", "OK" if ok else "FAILED")
     ref.close()
 ctx.close()
