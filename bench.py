@@ -665,11 +665,26 @@ def run_b200(args):
                                                          "compute roof)" if dominant["bound"] != "hbm" else ""),
                     "achieved": dominant["achieved"], "peak": dominant["peak"], "unit": dominant["unit"],
                     "frac": dominant["frac"], "traffic": None,
-                    "traffic_note": "dram bytes per launch are in profiles/ (ncu --set full captures), not re-measured here",
+                    "traffic_note": "dram bytes per launch come from ncu --set full captures (profiles/); none exists for "
+                                    "this configuration",
                     "peak_source": ("FMA microbenchmark in this run (b200md_microbench); MEASURED_PEAKS.json holds no "
                                     "FP64/FP32 figure") if dominant["bound"] != "hbm" else hbm_src,
                     "work_model": dominant["work_model"], "avg_launch_ms": dominant["avg_launch_ms"],
                     "share_of_step": dominant["share_of_step"]}
+
+    if roofline:
+        # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture - only for the
+        # very configuration the capture was taken on (same kernel, atoms, list size, precision, one GPU)
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as fh:
+                cap = json.load(fh).get(roofline["kernel"])
+            a = cap["applies_to"] if cap else None
+            if (a and a["config"] == args.config and a["n_gpus"] == world and a["precision"] == args.prec and
+                    not args.table and abs(entries_local - a["neighbor_entries"]) <= 1e-3 * a["neighbor_entries"]):
+                roofline["traffic"] = cap["dram_bytes_per_launch"]
+                roofline["traffic_note"] = cap["source"]
+        except (OSError, ValueError, KeyError):
+            pass
 
     # ---- e2e: the same step through host buffers (pinned), H2D x and D2H x,f every step ------------------
     e2e = None
