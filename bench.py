@@ -674,13 +674,14 @@ def run_b200(args):
 
     if roofline:
         # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture - only for the
-        # very configuration the capture was taken on (same kernel, atoms, list size, precision, one GPU)
+        # very configuration the capture was taken on (same kernel, atoms, precision, one GPU; the list size drifts by
+        # about 1 % with the step count at which the last rebuild falls, hence the 2 % window)
         try:
             with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as fh:
                 cap = json.load(fh).get(roofline["kernel"])
             a = cap["applies_to"] if cap else None
             if (a and a["config"] == args.config and a["n_gpus"] == world and a["precision"] == args.prec and
-                    not args.table and abs(entries_local - a["neighbor_entries"]) <= 1e-3 * a["neighbor_entries"]):
+                    not args.table and abs(entries_local - a["neighbor_entries"]) <= 2e-2 * a["neighbor_entries"]):
                 roofline["traffic"] = cap["dram_bytes_per_launch"]
                 roofline["traffic_note"] = cap["source"]
         except (OSError, ValueError, KeyError):
