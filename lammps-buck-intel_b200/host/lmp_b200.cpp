@@ -461,6 +461,12 @@ struct Script {
                   "\"g_ewald_6\": %.10g, \"grid_6\": [%d, %d, %d]",
                   kspace_style_name.c_str(), kspace->g_ewald, kspace->nx_pppm, kspace->ny_pppm, kspace->nz_pppm,
                   kspace->order, kspace->g_ewald_6, kspace->nx_pppm_6, kspace->ny_pppm_6, kspace->nz_pppm_6);
+    if (auto *pd = dynamic_cast<PPPMDispIntel *>(kspace.get())) {
+      // which functions of PPPMDisp::compute the styles select (Coulomb, geometric, arithmetic, no mixing)
+      static const char *rule[4] = {"none", "geometric", "arithmetic", "no mixing rule"};
+      std::printf(", \"disp_functions\": [%d, %d, %d, %d], \"dispersion_grid\": \"%s\"", pd->function[0], pd->function[1],
+                  pd->function[2], pd->function[3], rule[pd->disp_rule()]);
+    }
     std::printf("}\n");
   }
 

@@ -95,6 +95,32 @@ def test_dry_run_slab_sizing_and_boundary_checks(pkg, W, tmp_path):
     assert out.returncode != 0 and "Cannot use nonperiodic boundaries with PPPM" in out.stdout + out.stderr
 
 
+def test_pppm_disp_function_selection(pkg, W, tmp_path):
+    """PPPMDisp::init [UPSTREAM] as restated in PPPMDispIntel::init: order-6 dispersion is served by function[1]
+    (geometric), function[2] (arithmetic: the pair style's ewald_mix) or function[3] (`kspace_modify mix/disp none`);
+    `mix/disp geom` forces the geometric grid; the Buckingham style has no mixing rule to offer: geometric"""
+    import json
+    cases = [("", [1, 0, 1, 0], "arithmetic"), ("mix/disp none", [1, 0, 0, 1], "no mixing rule"),
+             ("mix/disp geom", [1, 1, 0, 0], "geometric"), ("mix/disp pair", [1, 0, 1, 0], "arithmetic")]
+    for mixdisp, fn, name in cases:
+        txt = scripts.IN_LJ_DISP_MIX.format(mixdisp=mixdisp, steps=1, thermo=1)
+        r = _run(pkg, ["-in", scripts.write(tmp_path, "in.ljmix", txt, W), "-sf", "intel", "-dry-run"])
+        assert r.returncode == 0, r.stdout + r.stderr
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["disp_functions"] == fn and d["dispersion_grid"] == name and d["grid_6"] == [30, 30, 32], d
+    # pair_modify mix geometric on the LJ style, and the Buckingham style of config 5
+    txt = scripts.IN_LJ_DISP_MIX.format(mixdisp="", steps=1, thermo=1).replace("mix arithmetic", "mix geometric")
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.ljmix", txt, W), "-sf", "intel", "-dry-run"])
+    assert json.loads(r.stdout.strip().splitlines()[-1])["disp_functions"] == [1, 1, 0, 0]
+    txt = scripts.IN_BUCK_DISP.format(n=4, g6=0.9, m=30, steps=1, thermo=1, A=3000.0)
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.disp", txt), "-sf", "intel", "-dry-run"])
+    assert json.loads(r.stdout.strip().splitlines()[-1])["disp_functions"] == [0, 1, 0, 0]
+    # an unknown mix/disp keyword is an illegal kspace_modify
+    txt = scripts.IN_LJ_DISP_MIX.format(mixdisp="mix/disp harmonic", steps=1, thermo=1)
+    r = _run(pkg, ["-in", scripts.write(tmp_path, "in.ljmix", txt, W), "-sf", "intel", "-dry-run"])
+    assert r.returncode != 0 and "Illegal kspace_modify command" in r.stdout + r.stderr
+
+
 def test_dispersion_grid_components(pkg, orc):
     """csrc/pppm.cu disp_components (host side of b200md_pppm_setup): the signed self-coupled components a dispersion
     grid is run as reproduce the r^-6 coefficient of every type pair, sum_m sign_m W_m[i] W_m[j] = C_ij -
