@@ -1574,7 +1574,6 @@ int pppm_compute_view(b200md_ctx *ctx, PppmState &ps, const PppmView &v, int efl
   const int n = v.n;
   const long nfft = ps.nfft;
   const int eflag_global = eflag & 1, vflag_global = vflag & 3;
-  const bool ad = ps.p.differentiation == 1;
   if (energy) *energy = 0.0;
   if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
 
