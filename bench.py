@@ -778,6 +778,8 @@ def run_b200(args):
                        "grid": desc.get("grid"), "g_ewald": desc.get("g_ewald", desc.get("g_ewald_6")),
                        "neighbor_entries": int(entries), "nbar": round(nbar, 1), "nghost": int(st1["nghost"]),
                        "rebuilds_in_timed_region": rebuilds,
+                       "pppm_transforms": (("half spectrum (real-to-complex)" if pppm_half_spectrum(world) else
+                                            "complex-to-complex (B200MD_R2C=0)") if desc.get("grid") else None),
                        "l2": "inputs larger than L2 (neighbour list %.1f GB, grids %.2f GB per GPU)" %
                              (4.0 * entries_local / 1e9, 56.0 * F / 1e9),
                        "parallelism": ("z-slab x%d (%s geometry)" % (world, args.geometry)) if world > 1 else "single GPU"},

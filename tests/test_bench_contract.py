@@ -91,3 +91,28 @@ def test_own_arm_json_line_on_a_small_workload():
     p = d["parity"]
     assert p["ok"] is True and p["pair_set_equal"] is True
     assert p["max_rel_force_err"] <= 1e-9 and p["epair_rel"] <= 1e-10 and p["ekspace_rel"] <= 1e-9
+
+
+def test_kernel_roofline_models_of_the_half_spectrum_passes():
+    """bench.kernel_rooflines is pure arithmetic: with the half-spectrum transforms on, the spectral passes are charged
+    Fs = F (nx/2 + 1) / nx points and three fields come back; the ideal step time is the sum of the rows"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, entries, grid = 4050000, 2087561650, (250, 250, 270)
+    F = grid[0] * grid[1] * grid[2]
+    timers = {"pair": (200.0, 20), "k_fft_x_fwd": (2.0, 20), "k_fft_y_fwd": (2.4, 20), "k_fft_z_poisson": (9.2, 20),
+              "k_fft_y_inv": (6.4, 20), "k_fft_x_inv": (6.0, 60), "fieldforce": (18.0, 20)}
+    cfg = {"flops_key": "buck_coul_long"}
+    rows, ideal, nbar = bench.kernel_rooflines(cfg, timers, 20, N, N + 800000, entries, F, 0, 34.7, 6551.4, "double",
+                                               fp32_peak=65.0, half_nx=grid[0])
+    by = {r["kernel"]: r for r in rows}
+    Fs = F * (grid[0] // 2 + 1) / grid[0]
+    assert by["k_fft_x_r2c (x fwd, real in)"]["work_per_launch"] == 8.0 * F + 16.0 * Fs
+    assert by["k_fft_z_poisson"]["work_per_launch"] == (16.0 + 8.0 + 48.0) * Fs
+    assert by["k_fft_x_c2r (x inv, real out)"]["launches"] == 60
+    assert abs(ideal - sum(r["ideal_ms_per_step"] for r in rows)) < 1e-12 and nbar == entries / N
+    full, _, _ = bench.kernel_rooflines(cfg, timers, 20, N, N + 800000, entries, F, 0, 34.7, 6551.4, "double", fp32_peak=65.0)
+    assert {r["kernel"] for r in full} >= {"k_fft_pass x fwd (real in)", "k_fft_pass x inv (real out)"}
+    assert bench.pppm_half_spectrum(1) is (os.environ.get("B200MD_R2C", "1")[:1] != "0")
