@@ -143,7 +143,8 @@ int b200md_pair_setup(b200md_ctx *ctx, const b200md_pair_params *p);
  * the partners as 0-based upload indices; both in upload order.  Call after b200md_atoms_upload; NULL clears.  Flagged
  * pairs stay in the list whatever their factor (stock drops factor-0 pairs when no k-space style is defined: forces are
  * identical, the pair set is not).  maxspecial <= 32.
- * Several GPUs: collective (every rank calls it with the rows of its own upload and the same maxspecial); the partners
+ * Several GPUs: collective (every rank calls it with the rows of its own upload and the same maxspecial - a rank that
+ * owns no atoms still passes non-NULL arrays, NULL means "clear" on every rank); the partners
  * are GLOBAL ids - rank r's k-th uploaded atom has id (atoms uploaded by ranks < r) + k, what b200md_atoms_download_ids
  * reports.  The rows are gathered into one table indexed by global id on every rank (12 + 4 maxspecial bytes per atom
  * of the whole system), so they follow atoms that migrate between the ranks; halo atoms carry their ids. */
