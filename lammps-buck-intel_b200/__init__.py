@@ -86,7 +86,7 @@ def build_host(force=False, verbose=False):
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [HEADER, LIBPATH]
     if not force and os.path.exists(LMP) and os.path.getmtime(LMP) >= max(os.path.getmtime(d) for d in deps):
         return LMP
-    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", LMP] + srcs + \
+    cmd = ["g++", "-O2", "-fopenmp", "-std=c++17", "-Wall", "-o", LMP] + srcs + \
           ["-L", HERE, "-l:libb200md.so", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN"]
     if verbose:
         print(" ".join(cmd), flush=True)

@@ -54,6 +54,7 @@ class Atom {
   std::vector<double> x, v, f;
   std::vector<double> q;
   std::vector<int> type;
+  std::vector<int> molecule; // molecule id per atom (atom_style full); only `delete_atoms ... mol yes` reads it
   std::vector<double> mass;  // [ntypes+1]
   std::vector<int> mask;     // group bits per atom (bit 0 = all); empty = every atom in `all` only
   std::vector<double> rmass; // per-atom masses when rmass_flag (fix_nve_intel.cpp:148-156)
@@ -194,6 +195,7 @@ class KSpace : protected Pointers {
   int gridflag_6 = 0, gewaldflag_6 = 0;
   int mixflag = 0;                // kspace_modify mix/disp pair (0) | geom (1) | none (2)
   double accuracy = 0.0, accuracy_relative = 0.0, accuracy_absolute = -1.0, two_charge_force = 0.0;
+  double accuracy_real_6 = -1.0, accuracy_kspace_6 = -1.0;   // kspace_modify force/disp/real, force/disp/kspace
   double scale = 1.0;
   int slabflag = 0;                 // kspace_modify slab
   double slab_volfactor = 1.0;

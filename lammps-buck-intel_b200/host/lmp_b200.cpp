@@ -77,7 +77,10 @@ struct Script {
   // lattice
   double lattice_a = 1.0;
   std::vector<std::array<double, 3>> basis;
-  double reg_lo[3] = {0, 0, 0}, reg_hi[3] = {0, 0, 0};
+  struct Block { double lo[3], hi[3]; };
+  std::map<std::string, Block> regions;             // region ID block ... (lattice units; scale 1 without a lattice)
+  std::vector<std::string> skipped_fixes;           // -dry-run only: fix styles outside the pair / k-space / nve path
+  bool warned_dump = false;
   bool dt_set = false;
   double last_thermo[6] = {0, 0, 0, 0, 0, 0};
   long nbuilds_reported = 0;
@@ -185,7 +188,8 @@ struct Script {
     long natoms = 0;
     double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
     std::string section;
-    std::vector<std::pair<long, std::array<double, 5>>> rows;
+    std::vector<std::pair<long, std::array<double, 6>>> rows;   // id -> type, q, x, y, z, molecule
+    std::map<long, std::array<double, 3>> vel;                  // Velocities section: id -> vx, vy, vz
     while (std::getline(in, line)) {
       const size_t hash = line.find('#');
       if (hash != std::string::npos) line = line.substr(0, hash);
@@ -220,12 +224,15 @@ struct Script {
         const size_t mol = a->molecule_flag ? 1 : 0;
         const size_t need = (a->q_flag ? 6 : 5) + mol;
         if (w.size() < need) fail("Incorrect atom format in data file");
-        std::array<double, 5> r;
+        std::array<double, 6> r;
+        r[5] = mol ? std::atof(w[1].c_str()) : 0.0;
         r[0] = std::atof(w[1 + mol].c_str());
         size_t c = 2 + mol;
         r[1] = a->q_flag ? std::atof(w[c++].c_str()) : 0.0;
         r[2] = std::atof(w[c].c_str()); r[3] = std::atof(w[c + 1].c_str()); r[4] = std::atof(w[c + 2].c_str());
         rows.push_back({std::atol(w[0].c_str()), r});
+      } else if (section == "Velocities" && w.size() >= 4) {
+        vel[std::atol(w[0].c_str())] = {std::atof(w[1].c_str()), std::atof(w[2].c_str()), std::atof(w[3].c_str())};
       }
     }
     if ((long)rows.size() != natoms) fail("Did not assign all atoms correctly");
@@ -242,19 +249,33 @@ struct Script {
       a->x.insert(a->x.end(), x, x + 3);
       a->type.push_back((int)r.second[0]);
       if (a->q_flag) a->q.push_back(r.second[1]);
+      if (a->molecule_flag) a->molecule.push_back((int)r.second[5]);
     }
     a->nlocal = (int)a->type.size();
     a->natoms = a->nlocal;
     a->v.assign((size_t)3 * a->nlocal, 0.0);
     a->f.assign((size_t)3 * a->nlocal, 0.0);
+    if (!vel.empty()) {
+      if (vel.size() != rows.size()) fail("Did not assign all velocities correctly");
+      for (size_t i = 0; i < rows.size(); i++) {
+        const auto it = vel.find(rows[i].first);
+        if (it == vel.end()) fail("Invalid atom ID in Velocities section of data file");
+        for (int d = 0; d < 3; d++) a->v[3 * i + d] = it->second[d];
+      }
+    }
+    // bonds name atoms by id; ids of a data file need not be 1..N in file order, but they are dense here
+    for (size_t i = 0; i < rows.size(); i++)
+      if (rows[i].first != (long)i + 1) { if (!a->bonds.empty()) fail("Atom IDs of a molecular data file must run 1..N"); break; }
   }
 
   void replicate(int nx, int ny, int nz) {
     Atom *a = lmp.atom;
     Domain *d = lmp.domain;
     const int n = a->nlocal;
-    std::vector<double> x, q;
-    std::vector<int> type;
+    std::vector<double> x, q, v;
+    std::vector<int> type, molecule;
+    int maxmol = 0;
+    for (int m : a->molecule) maxmol = std::max(maxmol, m);
     // new tags run z outer, y, x inner, old atoms inner-most (atom_offset = (iz*ny*nx + iy*nx + ix)*maxtag)
     for (int iz = 0; iz < nz; iz++)
       for (int iy = 0; iy < ny; iy++)
@@ -265,11 +286,14 @@ struct Script {
             x.push_back(a->x[3 * i + 2] + iz * d->prd[2]);
             type.push_back(a->type[i]);
             if (a->q_flag) q.push_back(a->q[i]);
+            for (int d2 = 0; d2 < 3; d2++) v.push_back(a->v[3 * i + d2]);
+            // mol_offset = (iz*ny*nx + iy*nx + ix) * maxmol for molecule ids > 0 (Replicate [UPSTREAM])
+            if (a->molecule_flag) molecule.push_back(a->molecule[i] > 0 ? a->molecule[i] + ((iz * ny + iy) * nx + ix) * maxmol : 0);
           }
     double hi[3] = {d->boxlo[0] + nx * d->prd[0], d->boxlo[1] + ny * d->prd[1], d->boxlo[2] + nz * d->prd[2]};
     double lo[3] = {d->boxlo[0], d->boxlo[1], d->boxlo[2]};
     d->set_box(lo, hi);
-    a->x.swap(x); a->q.swap(q); a->type.swap(type);
+    a->x.swap(x); a->q.swap(q); a->type.swap(type); a->molecule.swap(molecule);
     if (!a->bonds.empty()) {   // every image carries the molecule's bonds (the data file keeps molecules whole)
       std::vector<int> b;
       for (int r = 0; r < nx * ny * nz; r++)
@@ -278,8 +302,59 @@ struct Script {
     }
     a->nlocal = (int)a->type.size();
     a->natoms = a->nlocal;
-    a->v.assign((size_t)3 * a->nlocal, 0.0);
+    a->v.swap(v);
     a->f.assign((size_t)3 * a->nlocal, 0.0);
+  }
+
+  // delete_atoms region ID [mol yes] (examples/in.spce_if, in.hexane_if): atoms inside the block go, with `mol yes`
+  // every atom of a molecule that has an atom inside; bonds of deleted atoms go with them.  The survivors keep their
+  // order (a molecular system keeps its ids in stock LAMMPS; here the arrays are positional)
+  long delete_atoms_region(const Block &b, bool mol) {
+    Atom *a = lmp.atom;
+    const int n = a->nlocal;
+    std::vector<char> dead(n, 0);
+    for (int i = 0; i < n; i++) {
+      bool in = true;
+      for (int d = 0; d < 3; d++)
+        if (a->x[3 * (size_t)i + d] < b.lo[d] || a->x[3 * (size_t)i + d] > b.hi[d]) in = false;
+      dead[i] = in;
+    }
+    if (mol) {
+      if (!a->molecule_flag) fail("Cannot delete_atoms mol yes for non-molecular systems");
+      int maxmol = 0;
+      for (int m : a->molecule) maxmol = std::max(maxmol, m);
+      std::vector<char> moldead(maxmol + 1, 0);
+      for (int i = 0; i < n; i++)
+        if (dead[i] && a->molecule[i] > 0) moldead[a->molecule[i]] = 1;
+      for (int i = 0; i < n; i++)
+        if (a->molecule[i] > 0 && moldead[a->molecule[i]]) dead[i] = 1;
+    }
+    std::vector<int> newidx(n, -1);
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      if (dead[i]) continue;
+      newidx[i] = m;
+      for (int d = 0; d < 3; d++) { a->x[3 * (size_t)m + d] = a->x[3 * (size_t)i + d]; a->v[3 * (size_t)m + d] = a->v[3 * (size_t)i + d]; }
+      a->type[m] = a->type[i];
+      if (a->q_flag) a->q[m] = a->q[i];
+      if (a->molecule_flag) a->molecule[m] = a->molecule[i];
+      if (!a->mask.empty()) a->mask[m] = a->mask[i];
+      m++;
+    }
+    a->x.resize((size_t)3 * m); a->v.resize((size_t)3 * m); a->type.resize(m);
+    if (a->q_flag) a->q.resize(m);
+    if (a->molecule_flag) a->molecule.resize(m);
+    if (!a->mask.empty()) a->mask.resize(m);
+    std::vector<int> bonds;
+    for (size_t k = 0; k + 1 < a->bonds.size(); k += 2) {
+      const int i = newidx[a->bonds[k]], j = newidx[a->bonds[k + 1]];
+      if (i >= 0 && j >= 0) { bonds.push_back(i); bonds.push_back(j); }
+    }
+    a->bonds.swap(bonds);
+    a->nlocal = m;
+    a->natoms = m;
+    a->f.assign((size_t)3 * m, 0.0);
+    return n - m;
   }
 
   // Special::build [UPSTREAM]: 1-2 partners are the bonded atoms, 1-3 their partners, 1-4 one hop further; an atom is
@@ -461,11 +536,22 @@ struct Script {
                   "\"g_ewald_6\": %.10g, \"grid_6\": [%d, %d, %d]",
                   kspace_style_name.c_str(), kspace->g_ewald, kspace->nx_pppm, kspace->ny_pppm, kspace->nz_pppm,
                   kspace->order, kspace->g_ewald_6, kspace->nx_pppm_6, kspace->ny_pppm_6, kspace->nz_pppm_6);
+    if (auto *pp = dynamic_cast<PPPMIntel *>(kspace.get()))
+      std::printf(", \"acc\": [%.10g, %.10g, %.10g]", pp->acc_est[0], pp->acc_est[1], pp->acc_est[2]);
     if (auto *pd = dynamic_cast<PPPMDispIntel *>(kspace.get())) {
       // which functions of PPPMDisp::compute the styles select (Coulomb, geometric, arithmetic, no mixing)
       static const char *rule[4] = {"none", "geometric", "arithmetic", "no mixing rule"};
       std::printf(", \"disp_functions\": [%d, %d, %d, %d], \"dispersion_grid\": \"%s\"", pd->function[0], pd->function[1],
                   pd->function[2], pd->function[3], rule[pd->disp_rule()]);
+      // estimated absolute RMS force accuracies (PPPMDisp::final_accuracy / final_accuracy_6): Coulomb sum; dispersion
+      // sum total, real space, k-space
+      std::printf(", \"acc_coul\": [%.10g, %.10g, %.10g], \"acc_6\": [%.10g, %.10g, %.10g], \"order_6\": %d", pd->acc_coul[0],
+                  pd->acc_coul[1], pd->acc_coul[2], pd->acc_6[0], pd->acc_6[1], pd->acc_6[2], pd->order_6);
+    }
+    if (!skipped_fixes.empty()) {
+      std::printf(", \"skipped_fixes\": [");
+      for (size_t i = 0; i < skipped_fixes.size(); i++) std::printf("%s\"%s\"", i ? ", " : "", skipped_fixes[i].c_str());
+      std::printf("]");
     }
     std::printf("}\n");
   }
@@ -568,18 +654,36 @@ struct Script {
     } else if (c == "region") {
       need(9);
       if (w[2] != "block") fail("Illegal region command (only block is provided)");
+      Block b;
       for (int d = 0; d < 3; d++) {
-        reg_lo[d] = std::atof(w[3 + 2 * d].c_str()) * lattice_a;
-        reg_hi[d] = std::atof(w[4 + 2 * d].c_str()) * lattice_a;
+        b.lo[d] = std::atof(w[3 + 2 * d].c_str()) * lattice_a;
+        b.hi[d] = std::atof(w[4 + 2 * d].c_str()) * lattice_a;
       }
+      regions[w[1]] = b;
     } else if (c == "create_box") {
       need(3);
+      const auto ri = regions.find(w[2]);
+      if (ri == regions.end()) fail("Create_box region ID does not exist");
+      const Block &b = ri->second;
       a->ntypes = std::atoi(w[1].c_str());
       a->mass.assign(a->ntypes + 1, 0.0);
       a->mass_setflag.assign(a->ntypes + 1, 0);
-      lmp.domain->set_box(reg_lo, reg_hi);
-      std::printf("Created orthogonal box = (%g %g %g) to (%.6g %.6g %.6g)\n", reg_lo[0], reg_lo[1], reg_lo[2], reg_hi[0],
-                  reg_hi[1], reg_hi[2]);
+      lmp.domain->set_box(b.lo, b.hi);
+      std::printf("Created orthogonal box = (%g %g %g) to (%.6g %.6g %.6g)\n", b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1],
+                  b.hi[2]);
+    } else if (c == "delete_atoms") {
+      // delete_atoms region ID [mol yes|no] [compress ...]
+      need(3);
+      if (w[1] != "region") fail("Illegal delete_atoms command (only `region` is provided)");
+      const auto ri = regions.find(w[2]);
+      if (ri == regions.end()) fail("Could not find delete_atoms region ID");
+      bool mol = false;
+      for (size_t i = 3; i + 1 < w.size(); i += 2) {
+        if (w[i] == "mol") mol = w[i + 1] == "yes";
+        else if (w[i] != "compress") fail("Illegal delete_atoms command");
+      }
+      const long gone = delete_atoms_region(ri->second, mol);
+      std::printf("Deleted %ld atoms, new total = %d\n", gone, a->nlocal);
     } else if (c == "create_atoms") {
       need(3);
       create_atoms(std::atoi(w[1].c_str()));
@@ -662,7 +766,13 @@ struct Script {
       need(4);
       std::string s = w[3];
       if (s.size() > 6 && s.substr(s.size() - 6) == "/intel") s = s.substr(0, s.size() - 6);
-      if (s != "nve") fail("Unknown fix style " + w[3] + " (only nve is provided)");
+      if (s != "nve") {
+        // shake, nvt, npt, rigid/small ...: integrators and constraints outside the pair / k-space / nve path.  A dry
+        // run still sizes the styles of the script and lists what it skipped; a real run refuses
+        if (!dry_run) fail("Unknown fix style " + w[3] + " (only nve is provided)");
+        skipped_fixes.push_back(w[3]);
+        return;
+      }
       const auto gi = groups.find(w[2]);
       if (gi == groups.end()) fail("Could not find fix group ID " + w[2]);
       nve.reset(new FixNVEIntel(&lmp));
@@ -718,6 +828,10 @@ struct Script {
       for (int i = 0; i < a->nlocal; i++)
         std::fprintf(fp, "%d %.17g %.17g %.17g\n", a->type[i], a->x[3 * i], a->x[3 * i + 1], a->x[3 * i + 2]);
       std::fclose(fp);
+    }
+    else if (c == "dump" || c == "dump_modify" || c == "undump") {
+      if (!warned_dump) std::fprintf(stderr, "WARNING: dump output is not provided by this driver (%s ignored)\n", c.c_str());
+      warned_dump = true;
     }
     else if (c == "thermo_style" || c == "thermo_modify" || c == "processors" || c == "newton" || c == "echo" ||
              c == "log" || c == "dimension" || c == "boundary") {

@@ -172,6 +172,7 @@ void *PairBuckLongCoulLong::extract(const char *str, int &dim) {
   dim = 0;
   if (std::strcmp(str, "cut_coul") == 0) return &cut_coul;
   if (std::strcmp(str, "ewald_order") == 0) return &ewald_order;
+  if (std::strcmp(str, "cut_LJ") == 0) return &cut_global;   // the r^-6 real-space cut-off PPPMDisp sizes g_ewald_6 on
   if (std::strcmp(str, "B") == 0) { dim = 2; return k.c.data(); }   // dispersion coefficients read by pppm/disp
   return nullptr;
 }

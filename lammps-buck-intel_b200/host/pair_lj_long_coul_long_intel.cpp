@@ -105,6 +105,7 @@ void *PairLJLongCoulLong::extract(const char *str, int &dim) {
   if (std::strcmp(str, "cut_coul") == 0) return &cut_coul;
   if (std::strcmp(str, "ewald_order") == 0) return &ewald_order;
   if (std::strcmp(str, "ewald_mix") == 0) return &mix_flag;
+  if (std::strcmp(str, "cut_LJ") == 0) return &cut_global;
   dim = 2;   // [(ntypes+1)^2] matrices read by PPPMDisp::init_coeffs
   if (std::strcmp(str, "B") == 0) return k.c.data();          // lj4 = 4 eps sigma^6
   if (std::strcmp(str, "epsilon") == 0) return epsilon.data();

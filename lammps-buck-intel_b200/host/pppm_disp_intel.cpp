@@ -7,6 +7,7 @@
 // init_coeffs / the real-space accuracy estimate restate the stock base class PPPMDisp.
 #include "pppm_disp_intel.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -15,12 +16,157 @@ using namespace LAMMPS_NS;
 static const double MY_PI = 3.14159265358979323846;
 
 double PPPMDispIntel::lj_rspace_error(double g6) const {
-  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2];
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2] * slab_volfactor;   // zprd_slab
   double rgs = cutoff_lj * g6;
   rgs *= rgs;
   const double rgs_inv = 1.0 / rgs;
   return csum / std::sqrt((double)atom->natoms * xprd * yprd * zprd * cutoff_lj) * std::sqrt(MY_PI) * std::pow(g6, 5.0) *
          std::exp(-rgs) * (1.0 + rgs_inv * (3.0 + rgs_inv * (6.0 + rgs_inv * 6.0)));
+}
+
+// ---- mesh sizing of the stock base class PPPMDisp [UPSTREAM], restated: both meshes are sized on the
+// error functional of the optimal influence function (PPPM::compute_qopt), not on PPPM's closed-form ik estimate ------
+
+double PPPMDispIntel::df_kspace_coul() const {   // sqrt(qopt / natoms) q2 / volume on the Coulomb mesh
+  return compute_df_kspace();
+}
+
+double PPPMDispIntel::df_kspace_6() const {      // the same with csum = sum_i C_ii on the dispersion mesh
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd_slab = domain->prd[2] * slab_volfactor;
+  const int n[3] = {nx_pppm_6, ny_pppm_6, nz_pppm_6};
+  const double prd[3] = {xprd, yprd, zprd_slab};
+  const double qopt = compute_qopt(n, prd, order_6, g_ewald_6, differentiation_flag, 1);
+  return std::sqrt(qopt / atom->natoms) * csum / (xprd * yprd * zprd_slab);
+}
+
+// PPPMDisp::set_grid: g_ewald from the real-space error, then a uniform spacing shrunk by 5 % a time from 4/g_ewald
+void PPPMDispIntel::set_grid() {
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2];
+  const long natoms = atom->natoms;
+  if (!gewaldflag) {
+    if (accuracy <= 0.0) error->all(FLERR, "KSpace accuracy must be > 0");
+    g_ewald = accuracy * std::sqrt(natoms * cutoff * xprd * yprd * zprd) / (2.0 * q2);
+    if (g_ewald >= 1.0) error->all(FLERR, "KSpace accuracy too large to estimate G vector");
+    g_ewald = std::sqrt(-std::log(g_ewald)) / cutoff;
+  }
+  if (!gridflag) {
+    double h = 4.0 / g_ewald;
+    for (int count = 1;; count++) {
+      nx_pppm = std::max(static_cast<int>(xprd / h), 2);
+      ny_pppm = std::max(static_cast<int>(yprd / h), 2);
+      nz_pppm = std::max(static_cast<int>(zprd * slab_volfactor / h), 2);
+      if (df_kspace_coul() <= accuracy || count > 500) break;
+      h *= 0.95;
+    }
+  }
+  while (!factorable(nx_pppm)) nx_pppm++;
+  while (!factorable(ny_pppm)) ny_pppm++;
+  while (!factorable(nz_pppm)) nz_pppm++;
+}
+
+double PPPMDispIntel::f_coul() const {   // PPPMDisp::f: real-space minus k-space error of the Coulomb sum
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2];
+  const double df_rspace = 2.0 * q2 * std::exp(-g_ewald * g_ewald * cutoff * cutoff) /
+                           std::sqrt(atom->natoms * cutoff * xprd * yprd * zprd);
+  return df_rspace - df_kspace_coul();
+}
+
+void PPPMDispIntel::adjust_gewald() {    // Newton-Raphson on f, one-sided difference of 1e-6 (PPPMDisp::derivf)
+  for (int i = 0; i < 10000; i++) {
+    const double f1 = f_coul();
+    g_ewald += 1.0e-6;
+    const double f2 = f_coul();
+    g_ewald -= 1.0e-6;
+    g_ewald -= f1 / ((f2 - f1) / 1.0e-6);
+    if (std::fabs(f_coul()) < 1.0e-5) return;
+  }
+  error->all(FLERR, "Could not compute g_ewald");
+}
+
+void PPPMDispIntel::final_accuracy() {
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd = domain->prd[2];
+  acc_coul[2] = df_kspace_coul();
+  acc_coul[1] = 2.0 * q2 * std::exp(-g_ewald * g_ewald * cutoff * cutoff) / std::sqrt(atom->natoms * cutoff * xprd * yprd * zprd);
+  acc_coul[0] = std::sqrt(acc_coul[1] * acc_coul[1] + acc_coul[2] * acc_coul[2]);
+}
+
+// PPPMDisp::set_init_g6: the real-space error falls monotonically with g_ewald_6; bracket the root from 1/cutoff by
+// doubling / halving, then bisect to 1e-5
+void PPPMDispIntel::set_init_g6() {
+  const double acc_rspace = accuracy_real_6 > 0.0 ? accuracy_real_6 : accuracy;
+  const int LARGE = 10000;
+  const double SMALL = 0.00001;
+  int counter = 0;
+  double g_old = g_ewald_6 = 1.0 / cutoff_lj;
+  double df_real = lj_rspace_error(g_ewald_6) - acc_rspace;
+  if (df_real > 0.0)
+    while (df_real > 0.0 && counter < LARGE) {
+      counter++;
+      g_old = g_ewald_6;
+      g_ewald_6 *= 2.0;
+      df_real = lj_rspace_error(g_ewald_6) - acc_rspace;
+    }
+  if (df_real < 0.0)
+    while (df_real < 0.0 && counter < LARGE) {
+      counter++;
+      g_old = g_ewald_6;
+      g_ewald_6 *= 0.5;
+      df_real = lj_rspace_error(g_ewald_6) - acc_rspace;
+    }
+  if (counter >= LARGE - 1) error->all(FLERR, "Cannot compute initial g_ewald_disp");
+  double gmin = std::min(g_old, g_ewald_6), gmax = std::max(g_old, g_ewald_6);
+  g_ewald_6 = gmin + 0.5 * (gmax - gmin);
+  counter = 0;
+  while (gmax - gmin > SMALL && counter < LARGE) {
+    counter++;
+    df_real = lj_rspace_error(g_ewald_6) - acc_rspace;
+    if (df_real < 0.0) gmax = g_ewald_6;
+    else gmin = g_ewald_6;
+    g_ewald_6 = gmin + 0.5 * (gmax - gmin);
+  }
+  if (counter >= LARGE - 1) error->all(FLERR, "Cannot compute initial g_ewald_disp");
+}
+
+// PPPMDisp::set_n_pppm_6: uniform spacing from 4/g_ewald_6, shrunk by 5 % a time until the k-space error of the
+// dispersion mesh meets `kspace_modify force/disp/kspace` (else the overall accuracy)
+void PPPMDispIntel::set_n_pppm_6() {
+  const double xprd = domain->prd[0], yprd = domain->prd[1], zprd_slab = domain->prd[2] * slab_volfactor;
+  const double acc_kspace = accuracy_kspace_6 > 0.0 ? accuracy_kspace_6 : accuracy;
+  double h = 4.0 / g_ewald_6;
+  for (int count = 1;; count++) {
+    nx_pppm_6 = std::max(static_cast<int>(xprd / h), 2);
+    ny_pppm_6 = std::max(static_cast<int>(yprd / h), 2);
+    nz_pppm_6 = std::max(static_cast<int>(zprd_slab / h), 2);
+    if (df_kspace_6() <= acc_kspace || count > 500) break;
+    h *= 0.95;
+  }
+}
+
+void PPPMDispIntel::set_grid_6() {
+  if (!gewaldflag_6) set_init_g6();
+  if (!gridflag_6) set_n_pppm_6();
+  while (!factorable(nx_pppm_6)) nx_pppm_6++;
+  while (!factorable(ny_pppm_6)) ny_pppm_6++;
+  while (!factorable(nz_pppm_6)) nz_pppm_6++;
+}
+
+void PPPMDispIntel::adjust_gewald_6() {   // Newton-Raphson on f_6 = real-space minus k-space error of the r^-6 sum
+  auto f_6 = [&]() { return lj_rspace_error(g_ewald_6) - df_kspace_6(); };
+  for (int i = 0; i < 10000; i++) {
+    const double f1 = f_6();
+    g_ewald_6 += 1.0e-6;
+    const double f2 = f_6();
+    g_ewald_6 -= 1.0e-6;
+    g_ewald_6 -= f1 / ((f2 - f1) / 1.0e-6);
+    if (std::fabs(f_6()) < 1.0e-5) return;
+  }
+  error->all(FLERR, "Could not adjust g_ewald_6");
+}
+
+void PPPMDispIntel::final_accuracy_6() {
+  acc_6[1] = lj_rspace_error(g_ewald_6);
+  acc_6[2] = df_kspace_6();
+  acc_6[0] = std::sqrt(acc_6[1] * acc_6[1] + acc_6[2] * acc_6[2]);
 }
 
 void PPPMDispIntel::init() {
@@ -50,7 +196,12 @@ void PPPMDispIntel::init() {
   if (!function[0] && !rule) error->all(FLERR, "PPPMDisp used but no parameters set, for full pppm use pppm");
   if (order_6 > 7 || order > 7) error->all(FLERR, "PPPM order greater than supported by USER-INTEL");
 
-  if (function[0]) PPPM::init();   // Coulomb grid: qsum_qsq, set_grid_global, adjust_gewald
+  if (function[0]) {   // Coulomb mesh: qsum_qsq, PPPMDisp::set_grid, adjust_gewald, final_accuracy
+    init_charges();
+    set_grid();
+    if (!gewaldflag) adjust_gewald();
+    final_accuracy();
+  }
 
   if (rule) {
     if (!b) error->all(FLERR, "KSpace style is incompatible with Pair style");
@@ -88,28 +239,17 @@ void PPPMDispIntel::init() {
       for (int j = 1; j < n; j++)
         csumij += cnt[i] * cnt[j] * (rule == 1 ? std::sqrt(std::fabs(b[i * n + i] * b[j * n + j])) : b[i * n + j]);
     }
-    cutoff_lj = force->pair->cutforce;
+    double *p_cutoff_lj = (double *)force->pair->extract("cut_LJ", itmp);
+    if (!p_cutoff_lj) error->all(FLERR, "KSpace style is incompatible with Pair style");
+    cutoff_lj = *p_cutoff_lj;
     if (!function[0]) {
       two_charge_force = force->qqr2e * (force->qelectron * force->qelectron) / (force->angstrom * force->angstrom);
       accuracy = accuracy_absolute >= 0.0 ? accuracy_absolute : accuracy_relative * two_charge_force;
     }
-    if (!gewaldflag_6) {
-      // real-space error of the r^-6 sum = requested accuracy, on the decaying branch of the estimate
-      double lo = std::sqrt(2.5) / cutoff_lj, hi = 12.0 / cutoff_lj;
-      if (lj_rspace_error(lo) < accuracy) g_ewald_6 = lo;
-      else {
-        for (int it = 0; it < 200; it++) {
-          const double mid = 0.5 * (lo + hi);
-          if (lj_rspace_error(mid) > accuracy) lo = mid; else hi = mid;
-        }
-        g_ewald_6 = 0.5 * (lo + hi);
-      }
-    }
-    if (!gridflag_6)
-      error->all(FLERR, "pppm/disp/intel needs `kspace_modify mesh/disp nx ny nz` in this build (the qopt-based "
-                        "sizing of the dispersion grid is not restated)");
-    auto smooth = [](int v) { while (true) { int m = v; for (int f : {2, 3, 5}) while (m % f == 0) m /= f; if (m == 1) return v; v++; } };
-    nx_pppm_6 = smooth(nx_pppm_6); ny_pppm_6 = smooth(ny_pppm_6); nz_pppm_6 = smooth(nz_pppm_6);
+    set_grid_6();
+    // PPPMDisp::init [UPSTREAM]: with one accuracy for both halves of the sum, g_ewald_6 is re-balanced on the mesh
+    if (!gewaldflag_6 && accuracy_kspace_6 == accuracy_real_6) adjust_gewald_6();
+    final_accuracy_6();
   }
   if (!lmp->fix_intel && lmp->dry_run) return;
   if (!lmp->fix_intel) error->all(FLERR, "The 'package intel' command is required for /intel styles");

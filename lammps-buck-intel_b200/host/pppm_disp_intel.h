@@ -20,6 +20,18 @@ class PPPMDispIntel : public PPPM {
   std::vector<double> B;
   double csum = 0.0, csumij = 0.0, cutoff_lj = 0.0;
   double lj_rspace_error(double g6) const;
+  // mesh sizing of stock PPPMDisp (restated): Coulomb mesh and dispersion mesh, both on PPPM::compute_qopt
+  void set_grid();
+  void adjust_gewald();
+  void final_accuracy();
+  void set_grid_6();
+  void set_init_g6();
+  void set_n_pppm_6();
+  void adjust_gewald_6();
+  void final_accuracy_6();
+  double df_kspace_coul() const, df_kspace_6() const, f_coul() const;
+  // estimated absolute RMS force accuracy of the Coulomb sum and of the dispersion sum: total, real space, k-space
+  double acc_coul[3] = {0.0, 0.0, 0.0}, acc_6[3] = {0.0, 0.0, 0.0};
 
  private:
   FixIntel *fix = nullptr;

@@ -131,6 +131,28 @@ def coeffs_spce(cut_lj=6.8, cut_coul=8.8):
     return dict(A=eps, rho=sig, C=np.zeros((3, 3)), cut_lj=np.full((3, 3), float(cut_lj)), cut_coul=np.full((3, 3), float(cut_coul)))
 
 
+def hexane_system():
+    """examples/equilibrated_data.hexane (6 000 united-atom sites, 1 000 molecules, no charges; tests/golden/
+    data_hexane.npz, made by tests/golden/make_data_hexane.py from the reference's file) wrapped into the box, with the
+    file's own velocities — the input of in.hexane (`lj/long/coul/long long off 9.8` + `pppm/disp 1.0e-4`)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "data_hexane.npz")
+    d = np.load(path)
+    lo, hi = d["boxlo"].copy(), d["boxhi"].copy()
+    return dict(x=wrap(d["x"], lo, hi), v=d["v"].copy(), type=d["type"].copy(), q=np.zeros(len(d["x"])), boxlo=lo, boxhi=hi,
+                mass=d["mass"].copy(), ntypes=2, units="real", mol=d["mol"].copy())
+
+
+def coeffs_hexane(cut=9.8):
+    """examples/in.hexane:9,19-20: lj/long/coul/long long off 9.8; pair_coeff 1 1 0.1744742 3.97, 2 2 0.1147228 3.97, the 1-2
+    pair by the style's default geometric mixing (epsilon as A, sigma as rho)"""
+    eps = np.zeros((3, 3)); sig = np.ones((3, 3))
+    eps[1, 1], eps[2, 2] = 0.1744742, 0.1147228
+    eps[1, 2] = eps[2, 1] = np.sqrt(eps[1, 1] * eps[2, 2])
+    sig[1:, 1:] = 3.97
+    return dict(A=eps, rho=sig, C=np.zeros((3, 3)), cut_lj=np.full((3, 3), float(cut)), cut_coul=np.zeros((3, 3)))
+
+
 def water_like_system(nmol_side, seed=4711, box=35.5):
     """S4 stand-in for data.spce (positions+charges only, PPPM-only workload): rigid SPC/E-geometry
     molecules (O -0.8472, H +0.4236, r_OH = 1, angle 109.47) on a jittered simple-cubic lattice with random

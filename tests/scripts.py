@@ -167,3 +167,70 @@ timestep 2.0
 thermo {thermo}
 run {steps}
 """
+
+
+# examples/in.hexane with the parts that are on the pair / k-space path: the real equilibrated_data.hexane (atom_style
+# full, no charges, no bonds), lj/long/coul/long long off 9.8, pppm/disp 1.0e-4 with the script's own accuracy split
+# (`kspace_modify force/disp/real 0.0001`, `force/disp/kspace 0.002`: g_ewald_6 and the dispersion mesh are sized from
+# them), the script's pair_coeff lines (1-2 by geometric mixing), neighbour settings and 2 fs step.  `fix rigid/small
+# molecule` and the image dump of the original are outside that path: fix nve.
+IN_HEXANE_NVE = """units real
+atom_style full
+read_data {data}
+pair_style lj/long/coul/long long off 9.8
+kspace_style pppm/disp 1.0e-4
+kspace_modify force/disp/real 0.0001
+kspace_modify force/disp/kspace 0.002
+{kspace_modify}
+pair_coeff 1 1 0.1744742 3.97
+pair_coeff 2 2 0.1147228 3.97
+{pair_modify}
+neighbor 2.0 bin
+neigh_modify every 1 delay 10 check yes
+fix 1 all nve
+timestep 2.0
+thermo_style one
+thermo {thermo}
+run {steps}
+"""
+
+
+def write_data_hexane(path):
+    """equilibrated_data.hexane for the driver, regenerated from the committed fixture with the file's own layout
+    (`Atoms # full`: id mol type q x y z, then Velocities) and full precision"""
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_hexane.npz"))
+    n = len(d["x"])
+    with open(path, "w") as fh:
+        fh.write("LAMMPS data file regenerated from tests/golden/data_hexane.npz\n\n%d atoms\n2 atom types\n\n" % n)
+        for k, c in enumerate("xyz"):
+            fh.write("%.16e %.16e %slo %shi\n" % (d["boxlo"][k], d["boxhi"][k], c, c))
+        fh.write("\nMasses\n\n1 %.16g\n2 %.16g\n\nAtoms # full\n\n" % (d["mass"][1], d["mass"][2]))
+        for i in range(n):
+            fh.write("%d %d %d 0.0 %.16e %.16e %.16e 0 0 0\n" % (i + 1, d["mol"][i], d["type"][i], *d["x"][i]))
+        fh.write("\nVelocities\n\n")
+        for i in range(n):
+            fh.write("%d %.16e %.16e %.16e\n" % (i + 1, *d["v"][i]))
+    return path
+
+
+def write_data_spce(path):
+    """data.spce for the driver, regenerated from the committed fixture (atom_style full: id mol type q x y z) with the
+    O-H bonds of every molecule; the reference file itself is not available on the GPU box"""
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_spce.npz"))
+    n = len(d["x"])
+    with open(path, "w") as fh:
+        fh.write("LAMMPS Atom File\n\n%d atoms\n%d bonds\n\n2 atom types\n1 bond types\n\n" % (n, 2 * (n // 3)))
+        for k, c in enumerate("xyz"):
+            fh.write("%.5f %.5f %slo %shi\n" % (d["boxlo"][k], d["boxhi"][k], c, c))
+        fh.write("\nMasses\n\n1 %.4f\n2 %.5f\n\nAtoms\n\n" % (d["mass"][1], d["mass"][2]))
+        for i in range(n):
+            fh.write("%d %d %d %.4f %.5f %.5f %.5f 0 0 0\n" % (i + 1, d["mol"][i], d["type"][i], d["q"][i], *d["x"][i]))
+        fh.write("\nBonds\n\n")
+        b = 1
+        for o in range(0, n, 3):
+            for h in (1, 2):
+                fh.write("%d 1 %d %d\n" % (b, o + 1, o + 1 + h))
+                b += 1
+    return path

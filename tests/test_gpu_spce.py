@@ -80,3 +80,53 @@ def test_in_spce_nonbonded_and_kspace_forces(pkg, W, orc, table, prec):
         assert util.rel_force_err(fh[:, :3] + fk, ftot) <= 1e-9
     ctx.run(3)    # a few steps with the bits re-made at rebuilds
     ctx.close()
+
+
+@pytest.mark.parametrize("prec", [0, 1], ids=["double", "mixed"])
+@pytest.mark.parametrize("table", [False, True], ids=["analytic", "table"])
+def test_in_hexane_pair_and_dispersion_kspace_forces(pkg, W, orc, table, prec):
+    """examples/in.hexane on the device: `lj/long/coul/long long off 9.8` (ORDER1 = 0, ORDER6 = 1: the instantiation the
+    oracle equals the reference on bit for bit, test_lj_long_off_on_hexane_bitwise) + the geometric dispersion grid of
+    `pppm/disp`, g_ewald_6 and mesh as the host class sizes them from the script's accuracies (test_host_sizing.py), on
+    the real equilibrated_data.hexane — forces, energies, virial against the oracle"""
+    s = W.hexane_system()
+    n = len(s["x"])
+    co = W.coeffs_hexane()
+    skin, g6, grid6 = 2.0, 0.3044751226, (50, 24, 20)
+    P = orc.Params(orc.LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], g_ewald_6=g6,
+                   order1=0, order6=1)
+    cf = pkg.pair_coeffs(pkg.PAIR_LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"])
+    dt = None
+    if table:
+        dt = pkg.init_disp_tables(9.8, g6)
+        P.set_disp_tables(dt[0], 12, dt[1], dt[2], dt[3])
+    B = np.sqrt(4.0 * np.array([0.0, co["A"][1, 1], co["A"][2, 2]]) * 3.97 ** 6)
+    ctx = pkg.make_context(s, precision=prec)
+    ctx.neigh_setup(skin, every=1, delay=10, check=1)
+    ctx.pair_setup(pkg.PAIR_LJ_LONG_COUL_LONG, 2, cf, g_ewald_6=g6, ewald_order=1 << 6, disp_tables=dt)
+    ctx.pppm_setup(*grid6, 5, g6, dispersion=1, B=B)
+    ctx.nve_setup(2.0)
+    th = ctx.setup_forces(1, 1)
+    f = ctx.atoms_download(("f",))["f"]
+    cutneighmax = P.cutmax() + skin
+    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cutneighmax)
+    hn, hoff, hent = orc.neigh_half_bin(n, xa, ta, 2, P.cutneighsq(skin), s["boxlo"], s["boxhi"], cutneighmax, prec)
+    fo, evo = orc.pair_eval(P, prec, 1, 1, n, xa, ta, qa, hn, hoff, hent, newton=1)
+    fo = orc.reverse_comm(n, src, fo)[:n]
+    fk, ek, vk = orc.PPPM.dispersion(*grid6, 5, g6, s["boxlo"], s["boxhi"], prec=prec).compute(s["x"], B[s["type"]])
+    ftot = fo[:, :3] + fk
+    tol_f, tol_e = (1e-9, 1e-10) if prec == 0 else (5e-5, 1e-5)   # mixed: newton-on arm, see test_gpu_pair.py
+    assert util.rel_force_err(f, ftot) <= tol_f
+    assert abs(th[0] - evo[0]) <= tol_e * abs(evo[0]) and th[1] == 0.0 == evo[1]
+    assert np.abs(th[2:8] - evo[2:8]).max() <= tol_e * np.abs(evo[2:8]).max()
+    assert abs(th[8] - ek) <= max(tol_e, 1e-9) * abs(ek)
+    assert np.abs(th[9:15] - vk).max() <= max(tol_e, 1e-9) * np.abs(vk).max()
+    ctx.run(3)
+    # the k-space forces alone (the overlapping united atoms of a molecule dominate the total: 4e5 against 0.3): a fresh
+    # upload zeroes the force array, the dispersion grid accumulates onto it
+    ctx.atoms_upload(s["x"], s["type"], s["mass"], v=s["v"], q=s["q"])
+    e2, v2 = ctx.pppm_compute(1, 1)
+    f2 = ctx.atoms_download(("f",))["f"]
+    assert np.abs(f2 - fk).max() <= (1e-9 if prec == 0 else 2e-5) * np.abs(fk).max()
+    assert abs(e2 - ek) <= max(tol_e, 1e-9) * abs(ek)
+    ctx.close()

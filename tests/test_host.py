@@ -414,25 +414,7 @@ def test_read_data_atom_style_full_data_spce(pkg, W, tmp_path):
 
 
 def _write_data_spce(W, tmp_path):
-    """data.spce for the driver, regenerated from the committed fixture (atom_style full: id mol type q x y z) with the
-    O-H bonds of every molecule; the reference file itself is not available on the GPU box"""
-    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_spce.npz"))
-    n = len(d["x"])
-    path = os.path.join(str(tmp_path), "data.spce")
-    with open(path, "w") as fh:
-        fh.write("LAMMPS Atom File\n\n%d atoms\n%d bonds\n\n2 atom types\n1 bond types\n\n" % (n, 2 * (n // 3)))
-        for k, c in enumerate("xyz"):
-            fh.write("%.5f %.5f %slo %shi\n" % (d["boxlo"][k], d["boxhi"][k], c, c))
-        fh.write("\nMasses\n\n1 %.4f\n2 %.5f\n\nAtoms\n\n" % (d["mass"][1], d["mass"][2]))
-        for i in range(n):
-            fh.write("%d %d %d %.4f %.5f %.5f %.5f 0 0 0\n" % (i + 1, d["mol"][i], d["type"][i], d["q"][i], *d["x"][i]))
-        fh.write("\nBonds\n\n")
-        b = 1
-        for o in range(0, n, 3):
-            for h in (1, 2):
-                fh.write("%d 1 %d %d\n" % (b, o + 1, o + 1 + h))
-                b += 1
-    return path
+    return scripts.write_data_spce(os.path.join(str(tmp_path), "data.spce"))
 
 
 def test_dry_run_in_spce_nve(pkg, W, tmp_path):
@@ -486,3 +468,33 @@ def test_in_spce_nve_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
     fk, ek, vk = orc.PPPM(*grid, 5, ge, s["boxlo"], s["boxhi"], u["qqrd2e"]).compute(s["x"], s["q"])
     assert th[0, 2] == pytest.approx(evo[0] + evo[1] + ek, rel=1e-8)
     assert th[0, 1] == pytest.approx(300.0, rel=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("table", [0, 12])
+def test_in_hexane_nve_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
+    """in.hexane's non-bonded + k-space force through the driver and the host classes (PairLJLongCoulLongIntel with
+    `long off`, PPPMDispIntel sizing g_ewald_6 and the dispersion mesh from `force/disp/real`, `force/disp/kspace`):
+    step-0 E_pair against the oracle at the g_ewald_6 / mesh the dry run reports; `table/disp 12` is the stock default"""
+    data = scripts.write_data_hexane(os.path.join(str(tmp_path), "data.hexane"))
+    txt = scripts.IN_HEXANE_NVE.format(data=data, kspace_modify="", pair_modify="pair_modify table/disp %d" % table,
+                                       thermo=1, steps=2)
+    p = scripts.write(tmp_path, "in.hexane_nve", txt)
+    d = _summary(_run(pkg, ["-in", p, "-sf", "intel", "-dry-run"]).stdout)
+    g6, grid6 = d["g_ewald_6"], tuple(d["grid_6"])
+    assert grid6 == (50, 24, 20) and g6 == pytest.approx(0.3044751226, rel=1e-9)
+    r = _run(pkg, ["-in", p, "-sf", "intel"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    th = _thermo(r.stdout)
+    s = W.hexane_system()
+    co = W.coeffs_hexane()
+    P = orc.Params(orc.LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], g_ewald_6=g6,
+                   order1=0, order6=1)
+    if table:
+        dt = pkg.init_disp_tables(9.8, g6)
+        P.set_disp_tables(dt[0], 12, dt[1], dt[2], dt[3])
+    f, ev, _ = orc.pair_forces_periodic(P, 0, s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], 2.0)
+    B = np.sqrt(4.0 * np.array([0.0, co["A"][1, 1], co["A"][2, 2]]) * 3.97 ** 6)
+    fk, ek, vk = orc.PPPM.dispersion(*grid6, 5, g6, s["boxlo"], s["boxhi"]).compute(s["x"], B[s["type"]])
+    assert th[0, 2] == pytest.approx(ev[0] + ek, rel=1e-9)
+    assert th[0, 1] == pytest.approx(d["temperature"], rel=1e-9)      # the velocities of the data file

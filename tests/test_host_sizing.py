@@ -1,0 +1,296 @@
+"""Mesh sizing of the host classes (lammps-buck-intel_b200/host/pppm_intel.cpp, pppm_disp_intel.cpp): the stock base
+classes' accuracy-driven choice of g_ewald / g_ewald_6 and of the two meshes, which the reference inherits
+(`kspace_style pppm/disp 1.0e-4` + `kspace_modify force/disp/real`, `force/disp/kspace` in examples/in.hexane:11-17;
+`PPPM::init` reached from pppm_intel.cpp:69, `PPPMDisp::init` from pppm_disp_intel.cpp:88).  Stock LAMMPS is not in the
+reference, so the restatement is pinned two ways, both on the CPU through `lmp_b200 -dry-run`:
+  * the error functional Q of the optimal influence function against the literal quintuple loops of stock
+    compute_qopt_ik / _ad / _6_ik / _6_ad written out in numpy (no symmetry, no tables);
+  * the predicted RMS k-space force error against the error the oracle's PPPM really makes on that mesh (measured
+    against a much finer mesh at the same Ewald parameter) — the estimate is a physical statement, so this is a
+    known-answer test of the formula AND its normalisation."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from scipy.special import erfc
+
+import scripts
+
+REF_EXAMPLES = "/root/reference/examples"
+
+
+def _dry(pkg, path, cwd=None):
+    r = subprocess.run([pkg.build_host(), "-in", path, "-sf", "intel", "-dry-run"], capture_output=True, text=True, cwd=cwd,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]), r.stdout
+
+
+def _smooth(k):
+    """next size with no prime factor above 5 (PPPM::factorable)"""
+    while True:
+        m = k
+        for f in (2, 3, 5):
+            while m % f == 0:
+                m //= f
+        if m == 1:
+            return k
+        k += 1
+
+
+def qopt_literal(n, prd, order, g, ad, dispersion):
+    """stock PPPM(Disp)::compute_qopt_* as written: every mesh point, aliases -2..2 per dimension"""
+    unitk = 2.0 * np.pi / np.asarray(prd, float)
+    idx = [np.arange(n[d]) for d in range(3)]
+    kper = [i - n[d] * (2 * i // n[d]) for d, i in enumerate(idx)]
+    al = np.arange(-2, 3)
+    q = [unitk[d] * (kper[d][:, None] + n[d] * al[None, :]) for d in range(3)]             # [n_d, 5]
+    s = [np.exp(-0.25 * (q[d] / g) ** 2) for d in range(3)]
+    w = []
+    for d in range(3):
+        arg = 0.5 * q[d] * prd[d] / n[d]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            w.append(np.where(arg != 0.0, (np.sin(arg) / arg) ** order, 1.0))
+    kx = (unitk[0] * kper[0])[None, None, :, None, None, None]
+    ky = (unitk[1] * kper[1])[None, :, None, None, None, None]
+    kz = (unitk[2] * kper[2])[:, None, None, None, None, None]
+    qopt = 0.0
+    for m in range(n[2]):                      # one z plane at a time to bound memory
+        kzm = unitk[2] * kper[2][m]
+        qx = q[0][None, :, :, None, None]; qy = q[1][:, None, None, :, None]; qz = q[2][m][None, None, None, None, :]
+        sx = s[0][None, :, :, None, None]; sy = s[1][:, None, None, :, None]; sz = s[2][m][None, None, None, None, :]
+        wx = w[0][None, :, :, None, None]; wy = w[1][:, None, None, :, None]; wz = w[2][m][None, None, None, None, :]
+        kxx = (unitk[0] * kper[0])[None, :, None, None, None]; kyy = (unitk[1] * kper[1])[:, None, None, None, None]
+        sqk = (kxx ** 2 + kyy ** 2 + kzm ** 2)[:, :, 0, 0, 0]
+        dot1 = kxx * qx + kyy * qy + kzm * qz
+        dot2 = qx * qx + qy * qy + qz * qz
+        u2 = (wx * wy * wz) ** 2
+        s3 = sx * sy * sz
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if not dispersion:
+                t1 = s3 * s3 / dot2 * 16.0 * np.pi ** 2
+                t2 = s3 * u2 * 4.0 * np.pi if ad else u2 * s3 * 4.0 * np.pi / dot2 * dot1
+            else:
+                i2 = 0.5 / g
+                rt = np.sqrt(dot2)
+                term = g ** 3 * ((1.0 - 2.0 * dot2 * i2 * i2) * s3 + 2.0 * dot2 * rt * i2 ** 3 * np.sqrt(np.pi) * erfc(rt * i2))
+                t1 = term * term * np.pi ** 3 / 9.0 * dot2
+                t2 = -u2 * term * np.pi * np.sqrt(np.pi) / 3.0 * (dot2 if ad else dot1)
+            sum1 = t1.sum(axis=(2, 3, 4)); sum2 = t2.sum(axis=(2, 3, 4)); sum3 = u2.sum(axis=(2, 3, 4))
+            sum4 = (dot2 * u2).sum(axis=(2, 3, 4))
+            lost = sum2 ** 2 / (sum3 * sum4) if ad else sum2 ** 2 / (sum3 ** 2 * sqk)
+        val = sum1 - lost
+        qopt += val[sqk != 0.0].sum()
+    return qopt
+
+
+IN_QOPT = """units metal
+atom_style charge
+read_data data.aC
+pair_style lj/long/coul/long long long 9.0
+pair_coeff 1 1 0.008 2.9
+pair_coeff 2 2 0.021 3.3
+kspace_style pppm/disp 1e-4
+kspace_modify mesh {m[0]} {m[1]} {m[2]} gewald 0.28 mesh/disp {m6[0]} {m6[1]} {m6[2]} gewald/disp 0.31 order {o} order/disp {o6} diff {diff}
+fix 1 all nve
+run 0
+"""
+
+
+@pytest.mark.parametrize("diff", ["ik", "ad"])
+def test_error_functional_equals_the_literal_loops(pkg, W, tmp_path, diff):
+    """PPPM::compute_qopt (one octant with multiplicities, per-dimension tables) == the stock loops over every mesh
+    point, for the Coulomb and the dispersion kernel, ik and ad, on meshes with even and odd sizes (the Nyquist index of
+    an even mesh has no mirror image)"""
+    m, m6, o, o6 = (15, 16, 18), (12, 9, 10), 5, 4
+    s, _ = _dry(pkg, scripts.write(tmp_path, "in.q", IN_QOPT.format(m=m, m6=m6, o=o, o6=o6, diff=diff), W))
+    assert tuple(s["grid"]) == m and tuple(s["grid_6"]) == m6
+    x, t, q, lo, hi = W.data_aC()
+    prd = hi - lo
+    n, vol = len(x), float(np.prod(prd))
+    u = W.UNITS["metal"]
+    ad = diff == "ad"
+    want = np.sqrt(qopt_literal(m, prd, o, 0.28, ad, 0) / n) * (q ** 2).sum() * u["qqrd2e"] / vol
+    assert s["acc_coul"][2] == pytest.approx(want, rel=1e-8)
+    eps, sig = np.array([0.0, 0.008, 0.021]), np.array([0.0, 2.9, 3.3])
+    csum = (4.0 * eps * sig ** 6)[t].sum()
+    want6 = np.sqrt(qopt_literal(m6, prd, o6, 0.31, ad, 1) / n) * csum / vol
+    assert s["acc_6"][2] == pytest.approx(want6, rel=1e-8)
+
+
+def _hexane_B():
+    eps, sig = np.array([0.0, 0.1744742, 0.1147228]), 3.97
+    return np.sqrt(4.0 * eps * sig ** 6)
+
+
+def _lj_rspace_error(g6, csum, n, vol, rc):
+    rgs = (rc * g6) ** 2
+    ri = 1.0 / rgs
+    return csum / np.sqrt(n * vol * rc) * np.sqrt(np.pi) * g6 ** 5 * np.exp(-rgs) * (1.0 + ri * (3.0 + ri * (6.0 + ri * 6.0)))
+
+
+@pytest.mark.parametrize("diff", ["ik", "ad"])
+def test_in_hexane_sizes_its_dispersion_mesh_from_the_accuracies(pkg, W, orc, tmp_path, diff):
+    """examples/in.hexane:9-17 as shipped: no charges -> only the geometric dispersion function; g_ewald_6 puts the
+    real-space error at force/disp/real = 1e-4, the mesh is the first of the 5 % sequence whose predicted k-space error
+    is below force/disp/kspace = 0.002 — and the error PPPM really makes on that mesh is what was predicted"""
+    data = scripts.write_data_hexane(os.path.join(str(tmp_path), "data.hexane"))
+    txt = scripts.IN_HEXANE_NVE.format(data=data, kspace_modify="kspace_modify diff " + diff, pair_modify="", thermo=0, steps=0)
+    s, _ = _dry(pkg, scripts.write(tmp_path, "in.hexane_nve", txt))
+    h = W.hexane_system()
+    n, prd = len(h["x"]), h["boxhi"] - h["boxlo"]
+    B = _hexane_B()
+    csum = (B ** 2)[h["type"]].sum()
+    assert s["natoms"] == 6000 and s["disp_functions"] == [0, 1, 0, 0] and s["grid"] == [0, 0, 0]
+    assert s["temperature"] == pytest.approx(98.2095103, rel=1e-6)        # the data file's own velocities are read
+    # real-space half: the root of the (monotonic) error estimate, bisected to 1e-5 in g
+    g6 = s["g_ewald_6"]
+    assert _lj_rspace_error(g6 - 2e-5, csum, n, np.prod(prd), 9.8) > 1e-4 > _lj_rspace_error(g6 + 2e-5, csum, n, np.prod(prd), 9.8)
+    assert s["acc_6"][1] == pytest.approx(1e-4, rel=1e-3)
+    # k-space half: predicted error below the target, and the previous mesh of the sequence was above it
+    grid = tuple(s["grid_6"])
+    assert s["acc_6"][2] <= 0.002
+    assert s["acc_6"][2] == pytest.approx(np.sqrt(qopt_literal(grid, prd, 5, g6, diff == "ad", 1) / n) * csum / np.prod(prd), rel=1e-8)
+    # replay of PPPMDisp::set_n_pppm_6 with the literal loops: spacing 4/g_ewald_6 shrunk by 5 % a time
+    est = lambda gr: np.sqrt(qopt_literal(gr, prd, 5, g6, diff == "ad", 1) / n) * csum / np.prod(prd)
+    hh, raw = 4.0 / g6, None
+    for _ in range(80):
+        raw = tuple(max(int(p / hh), 2) for p in prd)
+        if est(raw) <= 0.002:
+            break
+        hh *= 0.95
+
+    assert tuple(_smooth(k) for k in raw) == grid
+    # measured: the same mesh against a far finer one, same g_ewald_6
+    w = B[h["type"]]
+    ad = int(diff == "ad")
+    f, _, _ = orc.PPPM.dispersion(*grid, 5, g6, h["boxlo"], h["boxhi"], diff_ad=ad).compute(h["x"], w)
+    fr, _, _ = orc.PPPM.dispersion(108, 54, 45, 7, g6, h["boxlo"], h["boxhi"]).compute(h["x"], w)
+    rms = np.sqrt(np.mean(np.sum((f - fr) ** 2, axis=1)))
+    assert 0.7 * s["acc_6"][2] < rms < 1.4 * s["acc_6"][2], (rms, s["acc_6"])
+
+
+IN_COUL_AUTO = """units metal
+atom_style charge
+read_data data.aC
+pair_style {pair}
+{coeffs}
+kspace_style {kspace} 1e-4
+kspace_modify diff {diff} {extra}
+fix 1 all nve
+run 0
+"""
+_LJ = "pair_coeff 1 1 0.008 2.9\npair_coeff 2 2 0.021 3.3"
+
+# a gas of random +-1 charges: the estimates model uncorrelated charges, which neither a perfect crystal (data.aC: the
+# real error is 4 x smaller than predicted) nor neutral molecules (data.spce: 2.3 x smaller) are
+IN_GAS_AUTO = """units real
+atom_style charge
+read_data {data}
+pair_style {pair}
+pair_coeff * * 0.1 3.0
+kspace_style {kspace} 1.0e-4
+kspace_modify diff {diff}
+fix 1 all nve
+run 0
+"""
+
+
+def _random_gas(path, n=2000, box=(30.0, 32.0, 36.0), seed=11):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0.0, 1.0, (n, 3)) * np.array(box)
+    q = np.where(np.arange(n) % 2 == 0, 1.0, -1.0)
+    with open(path, "w") as fh:
+        fh.write("random charges\n\n%d atoms\n1 atom types\n\n" % n)
+        for k, c in enumerate("xyz"):
+            fh.write("0.0 %.17g %slo %shi\n" % (box[k], c, c))
+        fh.write("\nMasses\n\n1 1.0\n\nAtoms\n\n")
+        for i in range(n):
+            fh.write("%d 1 %.1f %.17g %.17g %.17g\n" % (i + 1, q[i], *x[i]))
+    return x, q, np.zeros(3), np.array(box)
+
+
+@pytest.mark.parametrize("kspace,diff", [("pppm", "ad"), ("pppm/disp", "ik"), ("pppm/disp", "ad")])
+def test_coulomb_mesh_sized_on_the_error_functional(pkg, W, orc, tmp_path, kspace, diff):
+    """`kspace_modify diff ad` of plain pppm and the Coulomb mesh of pppm/disp are sized on the error functional of the
+    mesh (no closed form exists for ad; PPPMDisp uses it for ik too): the predicted k-space error of the chosen mesh
+    is what the oracle's PPPM really makes on it for uncorrelated charges"""
+    data = os.path.join(str(tmp_path), "data.gas")
+    x, q, lo, hi = _random_gas(data)
+    pair = "lj/cut/coul/long 8.0" if kspace == "pppm" else "lj/long/coul/long cut long 8.0"
+    s, _ = _dry(pkg, scripts.write(tmp_path, "in.c", IN_GAS_AUTO.format(data=data, pair=pair, kspace=kspace, diff=diff)))
+    u = W.UNITS["real"]
+    acc = s["acc"] if kspace == "pppm" else s["acc_coul"]
+    target = 1e-4 * u["qqrd2e"]
+    grid, g = tuple(s["grid"]), s["g_ewald"]
+    assert all(_smooth(k) == k for k in grid)
+    # g_ewald is re-balanced after the mesh was chosen, so the prediction sits near, not under, the target
+    assert 0.5 * target < acc[2] < 1.5 * target and acc[1] < 1.5 * target
+    n, vol = len(x), float(np.prod(hi - lo))
+    assert acc[2] == pytest.approx(np.sqrt(qopt_literal(grid, hi - lo, 5, g, diff == "ad", 0) / n) * (q ** 2).sum() * u["qqrd2e"] / vol,
+                                   rel=1e-8)
+    f, _, _ = orc.PPPM(*grid, 5, g, lo, hi, u["qqrd2e"], diff_ad=int(diff == "ad")).compute(x, q)
+    fr, _, _ = orc.PPPM(72, 75, 80, 7, g, lo, hi, u["qqrd2e"]).compute(x, q)
+    rms = np.sqrt(np.mean(np.sum((f - fr) ** 2, axis=1)))
+    assert 0.9 * acc[2] < rms < 1.1 * acc[2], (rms, acc)   # measured: within 1 %
+    if kspace == "pppm/disp":
+        assert s["disp_functions"] == [1, 0, 0, 0]
+
+
+def test_equal_accuracies_rebalance_g_ewald_6(pkg, W, tmp_path):
+    """without force/disp/real|kspace both halves of the dispersion sum share `accuracy`: PPPMDisp::init then moves
+    g_ewald_6 until the real-space and the k-space estimate of the chosen mesh are equal (adjust_gewald_6)"""
+    txt = IN_COUL_AUTO.format(pair="lj/long/coul/long long off 9.0", coeffs=_LJ, kspace="pppm/disp", diff="ik", extra="")
+    s, _ = _dry(pkg, scripts.write(tmp_path, "in.c", txt.replace("1e-4", "1e-3"), W))
+    assert s["disp_functions"] == [0, 1, 0, 0]
+    assert abs(s["acc_6"][1] - s["acc_6"][2]) < 1.1e-5          # |f_6| < SMALL
+    # an explicit g_ewald_6 is left alone
+    s2, _ = _dry(pkg, scripts.write(tmp_path, "in.c2", IN_COUL_AUTO.format(
+        pair="lj/long/coul/long long off 9.0", coeffs=_LJ, kspace="pppm/disp", diff="ik", extra="gewald/disp 0.3"), W))
+    assert s2["g_ewald_6"] == 0.3
+
+
+def test_delete_atoms_region_mol_yes(pkg, W, tmp_path):
+    """`region bigZ block ...` + `delete_atoms region bigZ mol yes` (examples/in.hexane_if:27-28, in.spce_if:40-41) on the
+    hexane fixture replicated 1 x 3 x 1: every molecule with a site inside the block goes, whole"""
+    data = scripts.write_data_hexane(os.path.join(str(tmp_path), "data.hexane"))
+    txt = ("units real\natom_style full\nread_data %s\nreplicate 1 3 1\npair_style lj/long/coul/long long off 9.8\n"
+           "kspace_style pppm/disp 1.0e-4\nkspace_modify gewald/disp 0.3 mesh/disp 48 72 18\npair_coeff 1 1 0.1744742 3.97\n"
+           "pair_coeff 2 2 0.1147228 3.97\nregion bigZ block 0. 105. 75. 153. 0. 42.\ndelete_atoms region bigZ mol yes\n"
+           "fix 1 all rigid/small molecule\ndump hexane all image 50 hexane*.ppm type mass\ndump_modify hexane pad 5\nrun 0\n" % data)
+    s, out = _dry(pkg, scripts.write(tmp_path, "in.if", txt))
+    h = W.hexane_system()
+    prd = h["boxhi"] - h["boxlo"]
+    x = np.concatenate([h["x"] + np.array([0.0, iy * prd[1], 0.0]) for iy in range(3)])
+    mol = np.concatenate([h["mol"] + iy * h["mol"].max() for iy in range(3)])
+    inside = np.all((x >= [0.0, 75.0, 0.0]) & (x <= [105.0, 153.0, 42.0]), axis=1)
+    dead = np.isin(mol, np.unique(mol[inside]))
+    assert s["natoms"] == int((~dead).sum()) == 8574
+    assert "Deleted %d atoms, new total = %d" % (dead.sum(), (~dead).sum()) in out
+    assert s["skipped_fixes"] == ["rigid/small"]
+    assert s["box"][1] == pytest.approx(3 * prd[1])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("script,natoms,style,skipped", [
+    ("in.hexane", 6000, "lj/long/coul/long", ["rigid/small"]), ("in.hexane_if", 8574, "lj/long/coul/long", ["rigid/small"]),
+    ("in.spce", 288000, "lj/cut/coul/long", ["shake", "nvt"]), ("in.spce_if", 18048, "lj/cut/coul/long", ["shake", "nvt"])])
+def test_shipped_molecular_scripts_size_their_styles(pkg, script, natoms, style, skipped):
+    """the reference's molecular examples as shipped: everything on the pair / k-space path is parsed and sized in a dry
+    run (read_data of atom_style full with Velocities, replicate, region + delete_atoms mol yes, the accuracy-driven
+    meshes); the integrators / constraints outside that path are listed, and a real run refuses them"""
+    r = subprocess.run([pkg.build_host(), "-in", script, "-sf", "intel", "-dry-run"], cwd=REF_EXAMPLES, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    s = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert (s["natoms"], s["pair_style"], s["skipped_fixes"]) == (natoms, style, skipped)
+    if "hexane" in script:
+        assert s["acc_6"][1] == pytest.approx(1e-4, rel=1e-3) and s["acc_6"][2] <= 0.002 and min(s["grid_6"]) > 2
+    else:
+        assert min(s["grid"]) > 2 and s["acc"][0] < 2e-4 * 332.06371
+    r = subprocess.run([pkg.build_host(), "-in", script, "-sf", "intel"], cwd=REF_EXAMPLES, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 1 and "Unknown fix style " + skipped[0] in r.stdout

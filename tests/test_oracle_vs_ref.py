@@ -205,3 +205,38 @@ def test_lj_long_coul_long_bitwise(pkg, W, orc, variant, prec):
         assert np.array_equal(fo, fr), (variant, prec, eflag, vflag, np.abs(fo - fr).max())
         assert np.array_equal(evo, evr), (variant, prec, evo, evr)
     assert np.abs(fo[:n, :3]).max() > 1.0
+
+
+@pytest.mark.parametrize("prec", [0, 1], ids=["double", "mixed"])
+@pytest.mark.parametrize("table", [0, 12], ids=["analytic", "table"])
+def test_lj_long_off_on_hexane_bitwise(pkg, W, orc, table, prec):
+    """the instantiation examples/in.hexane selects — `lj/long/coul/long long off 9.8`: eval<..., ORDER1 = 0, ORDER6 = 1>
+    (pair_lj_long_coul_long_intel.cpp:426-747), analytic and with the dispersion table of the stock default
+    `table/disp 12` — on the real equilibrated_data.hexane (no charges, no special bonds), g_ewald_6 as PPPMDisp sizes it
+    for the script's `force/disp/real 0.0001`"""
+    s = W.hexane_system()
+    co = W.coeffs_hexane()
+    g6 = 0.3044751226
+    P = orc.Params(orc.LJ_LONG_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], g_ewald_6=g6,
+                   order1=0, order6=1)
+    if table:
+        # pack_force_const copies every table — the dispersion ones too — only `if (ncoultablebits)` (:839-860), from the
+        # Coulomb arrays' length: as shipped (both defaults 12, Coulomb off, so stock init_style never builds rtable)
+        # the reference reads a null rtable.  The harness hands it Coulomb tables as well; ORDER1 = 0 never reads them
+        ct = pkg.init_coul_tables(9.8, 0.3, 1.0)
+        P.set_coul_tables(ct[0], 12, ct[1], ct[2], ct[3])
+        dt = pkg.init_disp_tables(9.8, g6)
+        P.set_disp_tables(dt[0], 12, dt[1], dt[2], dt[3])
+    n = len(s["x"])
+    skin = 2.0
+    cutneighmax = P.cutmax() + skin
+    assert abs(cutneighmax - 11.8) < 1e-12
+    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cutneighmax)
+    nn, off, ent = orc.neigh_half_bin(n, xa, ta, 2, P.cutneighsq(skin), s["boxlo"], s["boxhi"], cutneighmax, prec)
+    for eflag, vflag, eatom in ((0, 0, 0), (1, 1, 1), (1, 2, 0)):
+        fo, evo = orc.pair_eval(P, prec, eflag, vflag, n, xa, ta, qa, nn, off, ent, newton=1, eatom=eatom, nthreads=1)
+        fr, evr = refc.pair_eval(P, prec, eflag, vflag, n, xa, ta, qa, nn, off, ent, newton=1, eatom=eatom, nthreads=1,
+                                 skin=skin)
+        assert np.array_equal(fo, fr), (table, prec, eflag, vflag, np.abs(fo - fr).max())
+        assert np.array_equal(evo, evr), (table, prec, evo, evr)
+    assert np.abs(fo[:n, :3]).max() > 1.0 and evo[1] == 0.0
