@@ -172,8 +172,9 @@ run {steps}
 # examples/in.hexane with the parts that are on the pair / k-space path: the real equilibrated_data.hexane (atom_style
 # full, no charges, no bonds), lj/long/coul/long long off 9.8, pppm/disp 1.0e-4 with the script's own accuracy split
 # (`kspace_modify force/disp/real 0.0001`, `force/disp/kspace 0.002`: g_ewald_6 and the dispersion mesh are sized from
-# them), the script's pair_coeff lines (1-2 by geometric mixing), neighbour settings and 2 fs step.  `fix rigid/small
-# molecule` and the image dump of the original are outside that path: fix nve.
+# them), the script's pair_coeff lines (1-2 by geometric mixing) and neighbour settings.  `fix rigid/small molecule` and
+# the image dump of the original are outside that path: fix nve — and, with nothing holding the overlapping united
+# atoms of a molecule apart from each other's r^-12 wall (4e5 kcal/mol/A), a time step far below the script's 2 fs.
 IN_HEXANE_NVE = """units real
 atom_style full
 read_data {data}
@@ -188,7 +189,7 @@ pair_coeff 2 2 0.1147228 3.97
 neighbor 2.0 bin
 neigh_modify every 1 delay 10 check yes
 fix 1 all nve
-timestep 2.0
+timestep {dt}
 thermo_style one
 thermo {thermo}
 run {steps}

@@ -105,7 +105,7 @@ def test_in_hexane_pair_and_dispersion_kspace_forces(pkg, W, orc, table, prec):
     ctx.neigh_setup(skin, every=1, delay=10, check=1)
     ctx.pair_setup(pkg.PAIR_LJ_LONG_COUL_LONG, 2, cf, g_ewald_6=g6, ewald_order=1 << 6, disp_tables=dt)
     ctx.pppm_setup(*grid6, 5, g6, dispersion=1, B=B)
-    ctx.nve_setup(2.0)
+    ctx.nve_setup(1.0e-4)   # fix nve instead of the script's rigid bodies: see scripts.IN_HEXANE_NVE
     th = ctx.setup_forces(1, 1)
     f = ctx.atoms_download(("f",))["f"]
     cutneighmax = P.cutmax() + skin

@@ -478,7 +478,7 @@ def test_in_hexane_nve_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
     step-0 E_pair against the oracle at the g_ewald_6 / mesh the dry run reports; `table/disp 12` is the stock default"""
     data = scripts.write_data_hexane(os.path.join(str(tmp_path), "data.hexane"))
     txt = scripts.IN_HEXANE_NVE.format(data=data, kspace_modify="", pair_modify="pair_modify table/disp %d" % table,
-                                       thermo=1, steps=2)
+                                       thermo=1, steps=2, dt=1.0e-4)
     p = scripts.write(tmp_path, "in.hexane_nve", txt)
     d = _summary(_run(pkg, ["-in", p, "-sf", "intel", "-dry-run"]).stdout)
     g6, grid6 = d["g_ewald_6"], tuple(d["grid_6"])
@@ -497,4 +497,4 @@ def test_in_hexane_nve_runs_like_the_oracle(pkg, W, orc, tmp_path, table):
     B = np.sqrt(4.0 * np.array([0.0, co["A"][1, 1], co["A"][2, 2]]) * 3.97 ** 6)
     fk, ek, vk = orc.PPPM.dispersion(*grid6, 5, g6, s["boxlo"], s["boxhi"]).compute(s["x"], B[s["type"]])
     assert th[0, 2] == pytest.approx(ev[0] + ek, rel=1e-9)
-    assert th[0, 1] == pytest.approx(d["temperature"], rel=1e-9)      # the velocities of the data file
+    assert th[0, 1] == pytest.approx(d["temperature"], rel=1e-7)      # the velocities of the data file (8 printed digits)

@@ -138,7 +138,7 @@ def test_in_hexane_sizes_its_dispersion_mesh_from_the_accuracies(pkg, W, orc, tm
     real-space error at force/disp/real = 1e-4, the mesh is the first of the 5 % sequence whose predicted k-space error
     is below force/disp/kspace = 0.002 — and the error PPPM really makes on that mesh is what was predicted"""
     data = scripts.write_data_hexane(os.path.join(str(tmp_path), "data.hexane"))
-    txt = scripts.IN_HEXANE_NVE.format(data=data, kspace_modify="kspace_modify diff " + diff, pair_modify="", thermo=0, steps=0)
+    txt = scripts.IN_HEXANE_NVE.format(data=data, kspace_modify="kspace_modify diff " + diff, pair_modify="", thermo=0, steps=0, dt=2.0)
     s, _ = _dry(pkg, scripts.write(tmp_path, "in.hexane_nve", txt))
     h = W.hexane_system()
     n, prd = len(h["x"]), h["boxhi"] - h["boxlo"]
