@@ -229,7 +229,7 @@ def pair_coeffs(style, ntypes, A, rho, Cc, cut_lj, cut_coul=None, offset_flag=0)
 
 def init_coul_tables(cut_coul, g_ewald, qqrd2e, nbits=12, tabinner=np.sqrt(2.0)):
     """Pair::init_bitmap + Pair::init_tables (no rRESPA, no MSM) -> (tables dict, mask, shift, tabinnersq)."""
-    from math import erfc as _erfc
+    from math import erfc as _erfc, exp as _exp   # libm, as the C++ host classes: the two builders are bit-identical
     EWALD_F = 1.12837917
     inner, outer = float(tabinner), float(cut_coul)
     nlowermin = 1
@@ -259,7 +259,7 @@ def init_coul_tables(cut_coul, g_ewald, qqrd2e, nbits=12, tabinner=np.sqrt(2.0))
         rsq = i2f(bits)
         r = float(np.sqrt(np.float32(rsq)))
         grij = g_ewald * r
-        expm2 = np.exp(-grij * grij)
+        expm2 = _exp(-grij * grij)
         derfc = _erfc(grij)
         t["r"][i] = rsq
         t["c"][i] = qqrd2e / r
@@ -278,7 +278,7 @@ def init_coul_tables(cut_coul, g_ewald, qqrd2e, nbits=12, tabinner=np.sqrt(2.0))
         rsq = float(np.float32(cut_coulsq))
         r = float(np.sqrt(np.float32(rsq)))
         grij = g_ewald * r
-        expm2 = np.exp(-grij * grij)
+        expm2 = _exp(-grij * grij)
         derfc = _erfc(grij)
         t["dr"][itablemax] = 1.0 / (rsq - t["r"][itablemax])
         t["df"][itablemax] = qqrd2e / r * (derfc + EWALD_F * grij * expm2) - t["f"][itablemax]
@@ -318,9 +318,10 @@ def init_disp_tables(cut_lj, g_ewald_6, nbits=12, tabinner=np.sqrt(2.0)):
     tabinnersq = float(tabinner) ** 2
 
     def ev(rsq):
+        from math import exp as _exp
         x2 = g2 * rsq
         a2 = 1.0 / x2
-        x2 = a2 * np.exp(-x2)
+        x2 = a2 * _exp(-x2)
         return g8 * (((6.0 * a2 + 6.0) * a2 + 3.0) * a2 + 1.0) * x2 * rsq, g6 * ((a2 + 1.0) * a2 + 0.5) * x2
 
     t = {k: np.zeros(ntable) for k in ("r", "dr", "f", "df", "e", "de")}

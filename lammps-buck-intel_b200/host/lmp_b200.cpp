@@ -523,6 +523,29 @@ struct Script {
     return kinetic_energy();
   }
 
+  // CRC-32 (IEEE, as zlib.crc32) of a table set: every array as raw doubles, then mask, shift, tabinnersq
+  static unsigned int crc32(unsigned int crc, const void *data, size_t n) {
+    static unsigned int tab[256];
+    if (!tab[1])
+      for (unsigned int i = 0; i < 256; i++) {
+        unsigned int c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        tab[i] = c;
+      }
+    const unsigned char *p = (const unsigned char *)data;
+    crc = ~crc;
+    for (size_t i = 0; i < n; i++) crc = tab[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+    return ~crc;
+  }
+  static unsigned int table_crc(const PairTables &t) {
+    unsigned int c = 0;
+    for (const std::vector<double> *v : {&t.r, &t.dr, &t.f, &t.df, &t.e, &t.de, &t.c, &t.dc})
+      c = crc32(c, v->data(), v->size() * sizeof(double));
+    const int ms[2] = {t.mask, t.shiftbits};
+    c = crc32(c, ms, sizeof(ms));
+    return crc32(c, &t.tabinnersq, sizeof(double));
+  }
+
   void dry_summary() {
     Atom *a = lmp.atom;
     std::printf("{\"dry_run\": true, \"natoms\": %ld, \"ntypes\": %d, \"units\": \"%s\", \"box\": [%.10g, %.10g, %.10g], "
@@ -532,8 +555,8 @@ struct Script {
                 lmp.domain->prd[2], pair_style_name.c_str(), pair->cutforce, lmp.neighbor->skin, lmp.neighbor->every,
                 lmp.neighbor->delay, lmp.neighbor->dist_check, lmp.update->dt, temperature());
     if (kspace)
-      std::printf(", \"kspace_style\": \"%s\", \"g_ewald\": %.10g, \"grid\": [%d, %d, %d], \"order\": %d, "
-                  "\"g_ewald_6\": %.10g, \"grid_6\": [%d, %d, %d]",
+      std::printf(", \"kspace_style\": \"%s\", \"g_ewald\": %.17g, \"grid\": [%d, %d, %d], \"order\": %d, "
+                  "\"g_ewald_6\": %.17g, \"grid_6\": [%d, %d, %d]",
                   kspace_style_name.c_str(), kspace->g_ewald, kspace->nx_pppm, kspace->ny_pppm, kspace->nz_pppm,
                   kspace->order, kspace->g_ewald_6, kspace->nx_pppm_6, kspace->ny_pppm_6, kspace->nz_pppm_6);
     if (auto *pp = dynamic_cast<PPPMIntel *>(kspace.get()))
@@ -547,6 +570,10 @@ struct Script {
       // sum total, real space, k-space
       std::printf(", \"acc_coul\": [%.10g, %.10g, %.10g], \"acc_6\": [%.10g, %.10g, %.10g], \"order_6\": %d", pd->acc_coul[0],
                   pd->acc_coul[1], pd->acc_coul[2], pd->acc_6[0], pd->acc_6[1], pd->acc_6[2], pd->order_6);
+    }
+    if (auto *pb = dynamic_cast<PairBuck *>(pair.get())) {
+      if (const PairTables *t = pb->coul_tables()) std::printf(", \"coul_table\": [%d, %u]", t->nbits, table_crc(*t));
+      if (const PairTables *t = pb->disp_tables()) std::printf(", \"disp_table\": [%d, %u]", t->nbits, table_crc(*t));
     }
     if (!skipped_fixes.empty()) {
       std::printf(", \"skipped_fixes\": [");

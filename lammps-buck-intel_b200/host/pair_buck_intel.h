@@ -33,6 +33,10 @@ class PairBuck : public Pair {
   void coeff(int narg, char **arg) override;
   void init_style() override {}
   double init_one(int i, int j) override;
+  // the lookup tables init_style built (nullptr: none) — read by `lmp_b200 -dry-run`, which prints their CRC-32 so that
+  // the harness-side builders (lammps-buck-intel_b200/__init__.py) can be held bit-identical to these on the CPU
+  virtual const PairTables *coul_tables() const { return nullptr; }
+  virtual const PairTables *disp_tables() const { return nullptr; }
 
  protected:
   double cut_global = 0.0;

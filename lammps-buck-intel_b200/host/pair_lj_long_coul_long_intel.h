@@ -15,6 +15,8 @@ class PairLJLongCoulLong : public PairBuck {
   void init_style() override;
   double init_one(int i, int j) override;
   void *extract(const char *str, int &dim) override;
+  const PairTables *coul_tables() const override { return ctab.nbits ? &ctab : nullptr; }
+  const PairTables *disp_tables() const override { return dtab.nbits ? &dtab : nullptr; }
 
  protected:
   int ewald_order = 0, ewald_off = 0;   // bit1 = long Coulomb, bit6 = long dispersion (pair_lj_long_coul_long_intel.cpp:111-112)

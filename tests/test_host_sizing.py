@@ -11,6 +11,7 @@ reference, so the restatement is pinned two ways, both on the CPU through `lmp_b
 import json
 import os
 import subprocess
+import zlib
 
 import numpy as np
 import pytest
@@ -294,3 +295,31 @@ def test_shipped_molecular_scripts_size_their_styles(pkg, script, natoms, style,
     r = subprocess.run([pkg.build_host(), "-in", script, "-sf", "intel"], cwd=REF_EXAMPLES, capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 1 and "Unknown fix style " + skipped[0] in r.stdout
+
+
+def _table_crc(tables):
+    t, mask, shift, inner = tables
+    c = 0
+    for k in ("r", "dr", "f", "df", "e", "de", "c", "dc"):
+        c = zlib.crc32(np.ascontiguousarray(t.get(k, np.zeros(0)), np.float64).tobytes(), c)
+    c = zlib.crc32(np.array([mask, shift], np.int32).tobytes(), c)
+    return zlib.crc32(np.array([inner], np.float64).tobytes(), c)
+
+
+@pytest.mark.parametrize("bits", [12, 10, 14])
+def test_lookup_tables_of_the_host_classes_equal_the_harness_builders(pkg, W, tmp_path, bits):
+    """Pair::init_tables / init_tables_disp exist twice in the product: host/pair_buck_intel.cpp (what a LAMMPS build
+    uses) and lammps-buck-intel_b200/__init__.py (what the tests and bench.py hand to the C ABI).  `lmp_b200 -dry-run`
+    prints the CRC-32 of the tables the host classes built: bit-identical to the Python builders, for the Coulomb tables
+    of buck/coul/long and for both tables of lj/long/coul/long long long (examples' default `pair_modify table 12`)"""
+    u = W.UNITS["metal"]
+    txt = ("units metal\natom_style charge\nread_data data.aC\npair_style buck/coul/long 12.0\npair_coeff 2 2 1388.77 .3623188 175.0\n"
+           "pair_coeff 1 2 18003 .2052124 133.5381\npair_coeff 1 1 0 .1 0\npair_modify table %d\nkspace_style pppm 1e-4\n"
+           "fix 1 all nve\nrun 0\n" % bits)
+    s, _ = _dry(pkg, scripts.write(tmp_path, "in.t", txt, W))
+    want = _table_crc(pkg.init_coul_tables(12.0, s["g_ewald"], u["qqrd2e"], nbits=bits))
+    assert s["coul_table"] == [bits, want] and "disp_table" not in s
+    s, _ = _dry(pkg, scripts.write(tmp_path, "in.t2", IN_QOPT.format(m=(24, 24, 27), m6=(30, 30, 32), o=5, o6=5, diff="ik")
+                                   .replace("kspace_style", "pair_modify table %d table/disp %d\nkspace_style" % (bits, bits)), W))
+    assert s["coul_table"] == [bits, _table_crc(pkg.init_coul_tables(9.0, 0.28, u["qqrd2e"], nbits=bits))]
+    assert s["disp_table"] == [bits, _table_crc(pkg.init_disp_tables(9.0, 0.31, nbits=bits))]
