@@ -810,96 +810,107 @@ def cpu_setup(W, rep, acc):
     P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
                    g_ewald=g_ewald)
     pp = orc.PPPM(*grid, ORDER, g_ewald, s["boxlo"], s["boxhi"], u["qqrd2e"])
-    md = orc.MD(s, P, prec=orc.DOUBLE, skin=skin, every=1, delay=0, check=1, dt=u["dt"], ftm2v=u["ftm2v"], pppm=pp)
-    return orc, s, md, natoms, grid
+    kw = dict(prec=orc.DOUBLE, skin=skin, every=1, delay=0, check=1, dt=u["dt"], ftm2v=u["ftm2v"], pppm=pp)
+    return orc, s, P, kw, natoms, grid
 
 
-def cpu_baseline(args, W):
-    """oracle/ whole-step loop (half list, newton on, thread-private force arrays and grids, OpenMP over all host
-    cores) on a bounded sample: data.aC x cpu_rep^3, same styles/accuracy; the metric is intensive in N."""
-    cores = os.cpu_count() or 1
-    orc, s, md, natoms, grid = cpu_setup(W, args.cpu_rep, args.acc)
-    md.run(1, cores)                      # builds the list, first forces
-    t0 = time.perf_counter()
-    tm = md.run(args.cpu_steps, cores)
-    dt = time.perf_counter() - t0
-    try:
-        ref_loops = reference_loops(args, W)
-    except Exception as ex:   # noqa: BLE001
-        ref_loops = {"error": str(ex)}
-    return {"value": natoms * args.cpu_steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "reference_loops": ref_loops,
-            "sample": "data.aC x %d^3 = %d atoms, grid %dx%dx%d, %d steps, %.1f s; restatement of the reference loops "
-                      "(g++ -O3 -march=native -fopenmp; bit-identical to the reference's own compiled loops, oracle/_ref), "
-                      "not the ICC USER-INTEL build" % (args.cpu_rep, natoms, *grid, args.cpu_steps, dt),
-            "phase_s": {k: round(v, 3) for k, v in tm.items() if k != "nbuilds"}}
-
-
-def reference_loops(args, W):
-    """the reference's OWN compiled loops (oracle/_ref/libref.so: pair_buck_coul_long_intel.cpp eval<> and
-    PPPMIntel::compute, built unchanged by oracle/Makefile.ref, g++ -O3 -fopenmp, all host cores) timed on the sample —
-    the two hot loops only: the neighbour list, ghosts and the integrator around them are not in the reference"""
+def reference_step_loop(args, W, steps, warm):
+    """the whole Verlet step with every function the reference ships — PairBuckCoulLongIntel::compute, PPPMIntel::compute,
+    FixNVEIntel::initial_integrate / final_integrate — running from the reference's OWN translation units, compiled
+    unchanged into oracle/_ref/libref.so (oracle/Makefile.ref), all host cores; only what the reference inherits from
+    upstream LAMMPS (neighbour list, ghosts, forward / reverse communication, the re-neighbouring decision) comes from the
+    oracle (tests/refmd.py).  Returns None where oracle/_ref is not available."""
     graft.load_oracle()
     import refc
     if not refc.available():
         return None
-    orc = graft.load_oracle()
-    pkg = graft.load_package()
+    import refmd
     cores = os.cpu_count() or 1
-    u = W.UNITS["metal"]
-    s = W.aC_system(args.cpu_rep)
-    n = len(s["x"])
-    cut, skin = 12.0, 0.3
-    grid, g = pkg.pppm_init(args.acc, u["qqrd2e"], s["q"], n, cut, s["boxhi"] - s["boxlo"], order=ORDER)
-    co = W.coeffs_aC(cut, cut)
-    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
-                   g_ewald=g)
-    cm = P.cutmax() + skin
-    xa, ta, qa, src, shift = orc.make_ghosts(s["x"], s["type"], s["q"], s["boxlo"], s["boxhi"], cm)
-    nn, off, ent = orc.neigh_half_bin(n, xa, ta, 2, P.cutneighsq(skin), s["boxlo"], s["boxhi"], cm, orc.DOUBLE)
-    tp, tk = [], []
-    for _ in range(3):
-        refc.pair_eval(P, orc.DOUBLE, 0, 0, n, xa, ta, qa, nn, off, ent, newton=1, nthreads=cores, skin=skin)
-        tp.append(refc.last_seconds())
-    pp = orc.PPPM(*grid, ORDER, g, s["boxlo"], s["boxhi"], u["qqrd2e"])
-    for _ in range(3):
-        refc.pppm_compute(pp, s["x"], s["q"], eflag=0, vflag=0, nthreads=cores, want_grids=False)
-        tk.append(refc.last_seconds())
-    return {"kind": "reference", "cores": cores, "atoms": n, "half_list_entries": int(len(ent)),
-            "pair_seconds_per_call": round(min(tp), 4), "pppm_seconds_per_call": round(min(tk), 4),
-            "pair_plus_pppm_atoms_per_s": n / (min(tp) + min(tk)),
-            "what": "PairBuckCoulLongIntel::compute (eval<0,0,1>) and PPPMIntel::compute of /root/reference compiled unchanged "
-                    "(oracle/_ref), best of 3, %d OpenMP threads" % cores}
+    orc, s, P, kw, natoms, grid = cpu_setup(W, args.cpu_rep, args.acc)
+    rm = refmd.RefMD(s, P, nthreads=cores, **kw)
+    rm.run(max(warm, 1))                   # builds the list, first forces, warm-up steps
+    t0, w0, nb0 = dict(rm.t), time.perf_counter(), rm.nbuilds
+    rm.run(steps)
+    wall = time.perf_counter() - w0
+    ph = {k: rm.t[k] - t0[k] for k in rm.t}
+    secs = sum(v for k, v in ph.items() if k != "harness")
+    return {"value": natoms * steps / secs, "unit": UNIT, "cores": cores, "kind": "reference", "seconds": secs,
+            "steps": steps, "atoms": natoms, "grid": list(grid), "rebuilds": rm.nbuilds - nb0,
+            "wall_seconds_with_marshalling": round(wall, 3),
+            "phase_s": {k: round(v, 3) for k, v in ph.items()},
+            "sample": "data.aC x %d^3 = %d atoms, grid %dx%dx%d, %d steps, %.1f s: PairBuckCoulLongIntel::compute, "
+                      "PPPMIntel::compute and FixNVEIntel::initial/final_integrate of /root/reference compiled UNCHANGED "
+                      "(oracle/_ref: g++ -O3 -fopenmp, %d threads; not the ICC build), the upstream neighbour list / ghosts / "
+                      "communication around them from the oracle; timed = the reference's members + that glue, without the "
+                      "marshalling between the two libraries (%.1f s of wall time in all)"
+                      % (args.cpu_rep, natoms, *grid, steps, secs, cores, wall)}
+
+
+def port_step_loop(args, W, steps, warm):
+    """oracle/ whole-step loop (restatement of the same loops; bit-identical to oracle/_ref) — the fallback where
+    oracle/_ref is not available, and a second opinion beside it"""
+    cores = os.cpu_count() or 1
+    orc, s, P, kw, natoms, grid = cpu_setup(W, args.cpu_rep, args.acc)
+    md = orc.MD(s, P, **kw)
+    md.run(max(warm, 1), cores)
+    t0 = time.perf_counter()
+    tm = md.run(steps, cores)
+    dt = time.perf_counter() - t0
+    return {"value": natoms * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt, "steps": steps,
+            "atoms": natoms, "grid": list(grid), "rebuilds": tm["nbuilds"],
+            "phase_s": {k: round(v, 3) for k, v in tm.items() if k != "nbuilds"},
+            "sample": "data.aC x %d^3 = %d atoms, grid %dx%dx%d, %d steps, %.1f s; oracle/ restatement of the reference "
+                      "loops (g++ -O3 -march=native -fopenmp, %d threads; bit-identical to the reference's own compiled "
+                      "loops, oracle/_ref), not the ICC USER-INTEL build" % (args.cpu_rep, natoms, *grid, steps, dt, cores)}
+
+
+def cpu_baseline(args, W):
+    """the CPU arm on a bounded sample (data.aC x cpu_rep^3, same styles / accuracy; the metric is intensive in N): the
+    reference's own compiled units where oracle/_ref exists (kind "reference"), else the oracle port (kind "port")"""
+    try:
+        ref = reference_step_loop(args, W, args.cpu_steps, 1)
+    except Exception as ex:   # noqa: BLE001
+        ref = None
+        err = str(ex)
+    else:
+        err = None
+    port = port_step_loop(args, W, args.cpu_steps, 1)
+    out = dict(ref or port)
+    out["port"] = {k: port[k] for k in ("value", "seconds", "phase_s", "rebuilds")} if ref else None
+    if err:
+        out["reference_error"] = err
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port: the whole-step loop needs the
-    stock neighbour list / FFT / integrator glue that the reference does not ship), all host threads, same
-    metric/config, each step a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads, same metric / config, each step
+    a bounded sample of the workload.  The reference's own compiled translation units (oracle/_ref) run every function
+    it ships; where they are not available the oracle port of the same loops stands in (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     W = importlib.import_module("lammps_buck_intel_b200.workloads") if graft.load_package() else None
-    cores = os.cpu_count() or 1
-    orc, s, md, natoms, grid = cpu_setup(W, args.cpu_rep, args.acc)
-    md.run(max(args.warmup, 1), cores)
-    t0 = time.perf_counter()
-    md.run(args.steps, cores)
-    dt = time.perf_counter() - t0
-    value = natoms * args.steps / dt
+    warm = max(args.warmup, 1)
+    try:
+        r = reference_step_loop(args, W, args.steps, warm)
+    except Exception as ex:   # noqa: BLE001
+        print("bench.py: oracle/_ref failed (%s); timing the oracle port" % ex, file=sys.stderr)
+        r = None
+    if r is None:
+        r = port_step_loop(args, W, args.steps, warm)
+    value, natoms, grid = r["value"], r["atoms"], r["grid"]
     out = {"impl": "reference", "metric": "atom-timesteps/s buck/coul/long+PPPM", "value": value, "unit": UNIT,
            "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "warmup": warm, "ms_per_step": r["seconds"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "data.aC x %d^3 (%d atoms per step sample) buck/coul/long 12.0 + pppm %g order %d grid "
                                   "%dx%dx%d, skin 0.3 check yes, nve; bounded sample of the 4.05 M-atom workload "
                                   "(metric is intensive in N)" % (args.cpu_rep, natoms, args.acc, ORDER, *grid)},
            "same_config": False, "sample_atoms": natoms,
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "oracle/ restatement (half list, newton on, OpenMP %d threads), bit-identical to the "
-                                      "reference's own compiled loops (oracle/_ref); the whole step cannot run from "
-                                      "/root/reference alone (it needs LAMMPS core + MPI)" % cores},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "phase_s", "rebuilds") if k in r},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if "wall_seconds_with_marshalling" in r:
+        out["wall_seconds_with_marshalling"] = r["wall_seconds_with_marshalling"]
     print(json.dumps(out))
 
 

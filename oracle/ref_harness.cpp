@@ -308,8 +308,11 @@ int ref_nve(int which, int nlocal, int ntypes, double *x, double *v, const doubl
     nve.setup(0);
     if (ingroup || rmass) nve.reset_dt();   // setup() only calls it for ntypes > 1 (fix_nve_intel.cpp:52)
     w.neighbor.ago = 1;
-    if (which == 0) nve.initial_integrate(0);
-    else nve.final_integrate();
+    {
+      Stopwatch sw;
+      if (which == 0) nve.initial_integrate(0);
+      else nve.final_integrate();
+    }
     memcpy(x, w.xbuf.data(), sizeof(double) * 3 * (size_t)nlocal);
     memcpy(v, w.vbuf.data(), sizeof(double) * 3 * (size_t)nlocal);
     return 0;
@@ -479,7 +482,8 @@ int ref_pppm_compute(const orc_pppm_state *st, int prec, int nlocal, const doubl
   return rc;
 }
 
-/* seconds the reference's own compute() took in the last ref_pair_eval / ref_pppm_compute call (set-up excluded) */
+/* seconds the reference's own compute() / initial_integrate() / final_integrate() took in the last ref_pair_eval /
+ * ref_pppm_compute / ref_nve call (set-up excluded) */
 double ref_last_seconds(void) { return g_last_seconds; }
 
 int ref_has_openmp(void) {

@@ -1,4 +1,5 @@
-"""bench.py contract (CPU part): the reference arm — the oracle's whole-step loop on the host cores — prints ONE JSON line
+"""bench.py contract (CPU part): the reference arm — the reference's own compiled units (oracle/_ref) stepping a bounded
+sample on the host cores, or the oracle port of the same loops where they are not available — prints ONE JSON line
 with the keys the driver reads, for N = 1 and, under torchrun with two ranks, from rank 0 only."""
 import json
 import os
@@ -19,7 +20,16 @@ def _check(line, n_gpus):
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert "workload" in d["config"] and "buck/coul/long" in d["config"]["workload"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # the reference's own compiled units where oracle/_ref exists (this container, and prebuilt on the GPU box)
+    assert cb["kind"] == ("reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref.so")) else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    if cb["kind"] == "reference":
+        ph = cb["phase_s"]
+        assert ph["ref_pair"] > 0 and ph["ref_kspace"] > 0 and ph["ref_nve"] >= 0
+        # the reported time is the reference's members + the upstream glue; marshalling is left out and stated
+        timed = sum(v for k, v in ph.items() if k != "harness")
+        assert abs(d["ms_per_step"] * d["steps"] / 1e3 - timed) < 5e-3 * max(d["steps"], 1) + 1e-2 * timed
+        assert d["wall_seconds_with_marshalling"] >= timed
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"]
     assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
@@ -76,10 +86,11 @@ def test_own_arm_json_line_on_a_small_workload():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 76800 * 24 and e["d2h_bytes_per_step"] == 76800 * 48
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
-    # the reference's own compiled loops (oracle/_ref travels to the GPU box prebuilt) timed beside the port
-    rl = cb["reference_loops"]
-    assert rl["kind"] == "reference" and rl["pair_seconds_per_call"] > 0 and rl["pppm_seconds_per_call"] > 0
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1
+    if cb["kind"] == "reference":
+        # the reference's own compiled units (oracle/_ref travels to the GPU box prebuilt) run the step; the oracle port
+        # of the same loops is timed beside them
+        assert cb["phase_s"]["ref_pair"] > 0 and cb["phase_s"]["ref_kspace"] > 0 and cb["port"]["value"] > 0
     assert d["clocks"]["sm_max_mhz"] > 0
     # one roofline entry per kernel with >= 1 % of the step, measured in this run
     names = [r["kernel"] for r in d["roofline_kernels"]]

@@ -240,3 +240,29 @@ def test_lj_long_off_on_hexane_bitwise(pkg, W, orc, table, prec):
         assert np.array_equal(fo, fr), (table, prec, eflag, vflag, np.abs(fo - fr).max())
         assert np.array_equal(evo, evr), (table, prec, evo, evr)
     assert np.abs(fo[:n, :3]).max() > 1.0 and evo[1] == 0.0
+
+
+@pytest.mark.parametrize("prec", [0, 1], ids=["double", "mixed"])
+def test_whole_step_from_the_reference_units_equals_the_oracle_loop(pkg, W, orc, prec):
+    """tests/refmd.py (what `bench.py --impl reference` times): the Verlet step with PairBuckCoulLongIntel::compute,
+    PPPMIntel::compute and FixNVEIntel::initial/final_integrate running from the reference's own compiled units and the
+    upstream pieces from the oracle — the same trajectory, bit for bit at one thread, as oracle/md.cpp over steps that
+    include list rebuilds and ghost refreshes"""
+    import refmd
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    co = W.coeffs_aC(8.0, 8.0)
+    g = 0.30
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=g)
+    kw = dict(prec=prec, skin=0.3, every=1, delay=0, check=1, dt=0.001, ftm2v=u["ftm2v"])   # 4 builds in 20 steps
+    pp = orc.PPPM(24, 24, 27, 5, g, s["boxlo"], s["boxhi"], u["qqrd2e"], prec=prec)
+    md = orc.MD(s, P, pppm=pp, **kw)
+    tm = md.run(20, 1)
+    pp2 = orc.PPPM(24, 24, 27, 5, g, s["boxlo"], s["boxhi"], u["qqrd2e"], prec=prec)
+    rm = refmd.RefMD(s, P, pppm=pp2, nthreads=1, **kw)
+    tr = rm.run(20)
+    xo, vo, fo = md.get()
+    assert tr["nbuilds"] == tm["nbuilds"] and 3 <= tr["nbuilds"] < 10
+    assert np.array_equal(rm.x, xo) and np.array_equal(rm.v, vo) and np.array_equal(rm.f, fo)
+    assert tr["ref_pair"] > 0.0 and tr["ref_kspace"] > 0.0 and tr["ref_nve"] > 0.0 and rm.seconds() > 0.0
