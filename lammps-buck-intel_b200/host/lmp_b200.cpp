@@ -8,6 +8,7 @@
 // (initial_integrate -> neighbor decide -> pair -> kspace -> final_integrate) and Thermo one-style output.
 // All forces, neighbour lists and integration run through the classes of this directory, i.e. through the C ABI.
 //   -dry-run     parse + host-side init only (no device): prints a JSON summary of what would run
+//   -styles      list the registered pair / kspace / fix styles (the PairStyle(key,Class) lines of the headers)
 //   -host-step   plug-in deployment: positions/forces cross PCIe every step (FixIntel::resident = 0)
 #include <algorithm>
 #include <array>
@@ -60,8 +61,42 @@ class RanPark {
   int seed;
 };
 
+// ---- style registries, filled the way Force::Force / Modify::Modify of stock LAMMPS fill theirs: the style headers are
+// included once more with PAIR_CLASS / KSPACE_CLASS / FIX_CLASS defined, so that only their PairStyle(key,Class) ...
+// lines are seen (pair_buck_intel.h:18-22 of the reference) ------------------------------------------------------
+typedef Pair *(*PairCreator)(LAMMPS *);
+typedef KSpace *(*KSpaceCreator)(LAMMPS *, int, char **);
+typedef Fix *(*FixCreator)(LAMMPS *, int, char **);
+template <class T> Pair *pair_creator(LAMMPS *l) { return new T(l); }
+template <class T> KSpace *kspace_creator(LAMMPS *l, int narg, char **arg) { return new T(l, narg, arg); }
+template <class T> Fix *fix_creator(LAMMPS *l, int narg, char **arg) { return new T(l, narg, arg); }
+
+struct Styles {
+  std::map<std::string, PairCreator> pair;
+  std::map<std::string, KSpaceCreator> kspace;
+  std::map<std::string, FixCreator> fix;
+  Styles() {
+#define PAIR_CLASS
+#define PairStyle(key, Class) pair[#key] = &pair_creator<Class>;
+#include "style_pair.h"
+#undef PairStyle
+#undef PAIR_CLASS
+#define KSPACE_CLASS
+#define KSpaceStyle(key, Class) kspace[#key] = &kspace_creator<Class>;
+#include "style_kspace.h"
+#undef KSpaceStyle
+#undef KSPACE_CLASS
+#define FIX_CLASS
+#define FixStyle(key, Class) fix[#key] = &fix_creator<Class>;
+#include "style_fix.h"
+#undef FixStyle
+#undef FIX_CLASS
+  }
+};
+
 struct Script {
   LAMMPS lmp;
+  Styles styles;
   std::map<std::string, std::string> vars;
   std::unique_ptr<Pair> pair;
   std::unique_ptr<KSpace> kspace;
@@ -439,29 +474,31 @@ struct Script {
     for (double &v : a->v) v *= fac;
   }
 
-  template <class Plain, class Intel>
-  Pair *make_pair() {
-    // `-sf intel` appends the suffix when the style exists; only the /intel classes compute on the device
-    if (!suffix_intel) fail("Pair style " + pair_style_name + " without -sf intel: only the /intel styles are provided");
-    return new Intel(&lmp);
+  // Force::new_pair / new_kspace, Modify::add_fix [UPSTREAM]: with a suffix enabled (`-sf intel`, `suffix intel`) the
+  // style name + "/intel" is looked up first.  Only the /intel classes compute (on the device): the un-suffixed
+  // styles exist as their base classes, so asking for one without the suffix is an error here
+  template <class Map>
+  typename Map::mapped_type lookup(const Map &m, std::string &name, const char *what) {
+    if (name.size() > 6 && name.substr(name.size() - 6) == "/intel") { name = name.substr(0, name.size() - 6); suffix_intel = true; }
+    const auto it = m.find(name + "/intel");
+    if (it == m.end()) fail(std::string("Unknown ") + what + " style " + name);
+    if (!suffix_intel)
+      fail(std::string(what) + " style " + name + " without -sf intel: only the /intel styles are provided");
+    return it->second;
   }
 
   void pair_style(const std::vector<std::string> &w) {
     std::string s = w[1];
-    if (s.size() > 6 && s.substr(s.size() - 6) == "/intel") { s = s.substr(0, s.size() - 6); suffix_intel = true; }
-    pair_style_name = s;
-    if (s == "buck") pair.reset(make_pair<PairBuck, PairBuckIntel>());
-    else if (s == "buck/coul/cut") pair.reset(make_pair<PairBuckCoulCut, PairBuckCoulCutIntel>());
-    else if (s == "buck/coul/long") pair.reset(make_pair<PairBuckCoulLong, PairBuckCoulLongIntel>());
-    else if (s == "buck/long/coul/long") pair.reset(make_pair<PairBuckLongCoulLong, PairBuckLongCoulLongIntel>());
-    else if (s == "lj/long/coul/long" || s == "lj/cut/coul/long")
-      pair.reset(make_pair<PairLJLongCoulLong, PairLJLongCoulLongIntel>());
-    else fail("Unknown pair style " + s);
+    // `lj/cut/coul/long cut_lj [cut_coul]` (examples/in.spce:7) is `lj/long/coul/long cut long cut_lj [cut_coul]`
+    const bool lj_cut = s == "lj/cut/coul/long" || s == "lj/cut/coul/long/intel";
+    std::string key = lj_cut ? "lj/long/coul/long" : s;
+    const PairCreator make = lookup(styles.pair, key, "pair");
+    pair_style_name = lj_cut ? "lj/cut/coul/long" : key;
+    pair.reset(make(&lmp));
     lmp.force->pair = pair.get();
     std::vector<char *> args;
-    // `lj/cut/coul/long cut_lj [cut_coul]` (examples/in.spce:7) is `lj/long/coul/long cut long cut_lj [cut_coul]`
     static char a_cut[] = "cut", a_long[] = "long";
-    if (s == "lj/cut/coul/long") { args.push_back(a_cut); args.push_back(a_long); }
+    if (lj_cut) { args.push_back(a_cut); args.push_back(a_long); }
     for (size_t i = 2; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
     pair->settings((int)args.size(), args.data());
   }
@@ -477,10 +514,11 @@ struct Script {
       std::fprintf(stderr, "WARNING: kspace_style ewald is not provided on the device; using pppm at the same accuracy\n");
       s = "pppm";
     }
+    // only the /intel k-space classes exist here; they are created whatever the suffix setting (the pair style decides)
+    const auto it = styles.kspace.find(s + "/intel");
+    if (it == styles.kspace.end()) fail("Unknown kspace style " + s);
     kspace_style_name = s;
-    if (s == "pppm") kspace.reset(new PPPMIntel(&lmp, (int)args.size(), args.data()));
-    else if (s == "pppm/disp") kspace.reset(new PPPMDispIntel(&lmp, (int)args.size(), args.data()));
-    else fail("Unknown kspace style " + s);
+    kspace.reset(it->second(&lmp, (int)args.size(), args.data()));
     lmp.force->kspace = kspace.get();
   }
 
@@ -802,7 +840,9 @@ struct Script {
       }
       const auto gi = groups.find(w[2]);
       if (gi == groups.end()) fail("Could not find fix group ID " + w[2]);
-      nve.reset(new FixNVEIntel(&lmp));
+      std::vector<char *> args;
+      for (size_t i = 1; i < w.size(); i++) args.push_back(const_cast<char *>(w[i].c_str()));
+      nve.reset(static_cast<FixNVEIntel *>(styles.fix.at(s + "/intel")(&lmp, (int)args.size(), args.data())));
       nve->igroup = gi->second;
       nve->groupbit = 1 << gi->second;
     } else if (c == "group") {
@@ -884,6 +924,12 @@ int main(int argc, char **argv) {
         std::string line = "package";
         while (i + 1 < argc && argv[i + 1][0] != '-') line += std::string(" ") + argv[++i];
         s.command(line);
+      } else if (a == "-styles") {
+        // the registered style names, one per line: what the PairStyle / KSpaceStyle / FixStyle lines of the headers add
+        for (const auto &kv : s.styles.pair) std::printf("pair %s\n", kv.first.c_str());
+        for (const auto &kv : s.styles.kspace) std::printf("kspace %s\n", kv.first.c_str());
+        for (const auto &kv : s.styles.fix) std::printf("fix %s\n", kv.first.c_str());
+        return 0;
       } else if (a == "-dry-run") s.dry_run = true;
       else if (a == "-host-step") s.host_step = true;
       else if (a == "-echo") s.echo = true;

@@ -3,7 +3,16 @@
 //   PairStyle(buck/coul/long/intel,PairBuckCoulLongIntel)          pair_buck_coul_long_intel.h:18-40
 //   PairStyle(buck/long/coul/long/intel,PairBuckLongCoulLongIntel) pair_buck_long_coul_long_intel.h:18-46
 // each over its stock base class (settings / coeff / init_one), restated here.
-#pragma once
+#ifdef PAIR_CLASS
+
+PairStyle(buck/coul/cut/intel,PairBuckCoulCutIntel)
+PairStyle(buck/coul/long/intel,PairBuckCoulLongIntel)
+PairStyle(buck/long/coul/long/intel,PairBuckLongCoulLongIntel)
+
+#else
+
+#ifndef B200MD_PAIR_BUCK_COUL_INTEL_H
+#define B200MD_PAIR_BUCK_COUL_INTEL_H
 #include "pair_buck_intel.h"
 
 namespace LAMMPS_NS {
@@ -85,3 +94,6 @@ class PairBuckLongCoulLongIntel : public PairBuckLongCoulLong {
 };
 
 }  // namespace LAMMPS_NS
+
+#endif
+#endif

@@ -2,7 +2,14 @@
 // Mirrors pair_buck_intel.h:32-38 of the reference: same class name, same public surface
 // (`compute(int,int)`, `init_style()`), `settings/coeff/init_one` from the stock base class PairBuck
 // (restated here because the reference does not ship it).
-#pragma once
+#ifdef PAIR_CLASS
+
+PairStyle(buck/intel,PairBuckIntel)
+
+#else
+
+#ifndef B200MD_PAIR_BUCK_INTEL_H
+#define B200MD_PAIR_BUCK_INTEL_H
 #include "fix_intel.h"
 #include "lammps_shim.h"
 
@@ -67,3 +74,6 @@ class PairBuckIntel : public PairBuck {
 };
 
 }  // namespace LAMMPS_NS
+
+#endif
+#endif

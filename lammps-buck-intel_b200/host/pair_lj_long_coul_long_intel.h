@@ -1,7 +1,14 @@
 // pair_lj_long_coul_long_intel.h — PairStyle(lj/long/coul/long/intel,PairLJLongCoulLongIntel) on the device
 // (pair_lj_long_coul_long_intel.h:18-46 of the reference).  With `cut long` it is the lj/cut/coul/long of
 // examples/in.spce:7, which the driver maps onto it.  The stock base class (settings / coeff / init_one) is restated.
-#pragma once
+#ifdef PAIR_CLASS
+
+PairStyle(lj/long/coul/long/intel,PairLJLongCoulLongIntel)
+
+#else
+
+#ifndef B200MD_PAIR_LJ_LONG_COUL_LONG_INTEL_H
+#define B200MD_PAIR_LJ_LONG_COUL_LONG_INTEL_H
 #include "pair_buck_intel.h"
 
 namespace LAMMPS_NS {
@@ -36,3 +43,6 @@ class PairLJLongCoulLongIntel : public PairLJLongCoulLong {
 };
 
 }  // namespace LAMMPS_NS
+
+#endif
+#endif

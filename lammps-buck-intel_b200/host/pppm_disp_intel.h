@@ -2,7 +2,14 @@
 // reference).  All four "functions" of PPPMDisp::compute run on the device: the Coulomb grid ('c') and the
 // geometric-mixing dispersion grid ('g') the reference accelerates itself (pppm_disp_intel.cpp:183-313), and the
 // arithmetic-mixing (seven grids, :315-407) and no-mixing (:409-467) branches it leaves to the stock members.
-#pragma once
+#ifdef KSPACE_CLASS
+
+KSpaceStyle(pppm/disp/intel,PPPMDispIntel)
+
+#else
+
+#ifndef B200MD_PPPM_DISP_INTEL_H
+#define B200MD_PPPM_DISP_INTEL_H
 #include "pppm_intel.h"
 
 namespace LAMMPS_NS {
@@ -38,3 +45,6 @@ class PPPMDispIntel : public PPPM {
 };
 
 }  // namespace LAMMPS_NS
+
+#endif
+#endif

@@ -2,7 +2,14 @@
 // Mirrors pppm_intel.h:33-39 / pppm_disp_intel.h of the reference: `PPPMIntel(LAMMPS*, int narg, char **arg)`
 // (arg0 = relative accuracy), `init()`, `compute(int,int)`; `setup()` and the grid-sizing logic come from the stock
 // base class PPPM, restated here because the reference does not ship it.
-#pragma once
+#ifdef KSPACE_CLASS
+
+KSpaceStyle(pppm/intel,PPPMIntel)
+
+#else
+
+#ifndef B200MD_PPPM_INTEL_H
+#define B200MD_PPPM_INTEL_H
 #include "fix_intel.h"
 #include "lammps_shim.h"
 
@@ -49,3 +56,6 @@ class PPPMIntel : public PPPM {
 };
 
 }  // namespace LAMMPS_NS
+
+#endif
+#endif

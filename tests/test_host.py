@@ -222,6 +222,28 @@ def test_shipped_example_scripts_parse_verbatim(pkg, script, natoms, style, cut)
     assert (s["natoms"], s["pair_style"], s["cutforce"]) == (natoms, style, cut)
 
 
+def test_styles_are_registered_like_the_reference_registers_them(pkg):
+    """the headers of host/ carry the `#ifdef PAIR_CLASS  PairStyle(key,Class)  #else ... #endif` blocks of the reference's
+    headers (pair_buck_intel.h:18-22 and siblings, pppm_intel.h:18-22, pppm_disp_intel.h:18-22) and the driver fills its
+    style maps by including them with PAIR_CLASS / KSPACE_CLASS / FIX_CLASS defined, as stock Force / Modify do: the
+    registered names (and, where the reference is mounted, the key -> class pairs) are the reference's"""
+    import re
+    r = _run(pkg, ["-styles"])
+    assert r.returncode == 0
+    got = sorted(tuple(l.split()) for l in r.stdout.splitlines())
+    assert got == sorted([("pair", "buck/intel"), ("pair", "buck/coul/cut/intel"), ("pair", "buck/coul/long/intel"),
+                          ("pair", "buck/long/coul/long/intel"), ("pair", "lj/long/coul/long/intel"),
+                          ("kspace", "pppm/intel"), ("kspace", "pppm/disp/intel"), ("fix", "nve/intel")])
+    pat = re.compile(r"^(Pair|KSpace|Fix)Style\(([^,]+),(\w+)\)", re.M)
+    host = os.path.join(pkg.HERE, "host")
+    mine = {m.groups() for f in os.listdir(host) if f.endswith(".h") for m in pat.finditer(open(os.path.join(host, f)).read())}
+    assert {("%s" % k.lower(), key) for k, key, _ in mine} == set(got)
+    if os.path.isdir("/root/reference"):
+        ref = {m.groups() for f in os.listdir("/root/reference") if f.endswith(".h")
+               for m in pat.finditer(open(os.path.join("/root/reference", f)).read())}
+        assert len(ref) == 7 and ref <= mine          # the reference ships no header for fix nve/intel
+
+
 def test_driver_errors(pkg, W, tmp_path):
     bad = scripts.IN_BUCK.format(n=4, steps=1, thermo=0).replace("pair_coeff 1 1 1.0 0.2 -0.8", "")
     r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bad", bad), "-sf", "intel", "-dry-run"])
