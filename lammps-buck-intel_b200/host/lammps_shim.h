@@ -3,8 +3,10 @@
 // The reference is a plug-in: its classes derive from upstream LAMMPS base classes (Pair, KSpace, Fix) and read
 // upstream singletons (atom, force, domain, neighbor, update, error).  None of those ship with the reference
 // (SURVEY.md §2.2, App. A), so this header restates the members the hot path uses — same names, same meaning — for
-// the stand-alone host layer of this repo.  Inside a real LAMMPS tree these declarations are replaced by the real
-// headers and the classes in this directory compile against them unchanged.
+// the stand-alone host layer of this repo.  Inside a real LAMMPS tree the real headers take their place; what carries
+// over is the body of each class's C-ABI marshalling, with two mechanical differences:
+// per-atom arrays here are flat std::vector<double> ([n][3] contiguous, what atom->x[0] points at in LAMMPS) and
+// per-type-pair tables flat [(ntypes+1)^2] vectors instead of double**.
 //
 //   reference use                                         member here
 //   atom->x/v/f/q/type/mass/nlocal/ntypes                 Atom        (fix_nve_intel.cpp:64-72, pair_buck_intel.cpp:86)

@@ -578,6 +578,7 @@ class KSpace : public Pointers {
   double g_ewald = 0, g_ewald_6 = 0, scale = 1.0, qqrd2e = 1.0;
   int order = 5, order_6 = 5;
   int differentiation_flag = 0, slabflag = 0, triclinic = 0, tip4pflag = 0;
+  double slab_volfactor = 1.0;   /* kspace_modify slab (the reference reads slabflag only; the B200 binding passes this on) */
   int suffix_flag = 0;
   int evflag = 0, evflag_atom = 0, eflag_either = 0, eflag_global = 0, eflag_atom = 0;
   int vflag_either = 0, vflag_global = 0, vflag_atom = 0;

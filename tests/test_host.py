@@ -244,6 +244,36 @@ def test_styles_are_registered_like_the_reference_registers_them(pkg):
         assert len(ref) == 7 and ref <= mine          # the reference ships no header for fix nve/intel
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("unit,symbols", [
+    ("pair_buck_coul_long_intel.cpp", ["PairBuckCoulLongIntel::init_style()", "PairBuckCoulLongIntel::compute(int, int)",
+                                       "b200md_pair_setup", "b200md_pair_compute"]),
+    ("pppm_intel.cpp", ["PPPMIntel::init()", "PPPMIntel::compute(int, int)", "PPPMIntel::brick2fft()", "b200md_pppm_setup",
+                        "b200md_pppm_compute"])])
+def test_integration_binding_compiles_against_the_reference_header(pkg, tmp_path, unit, symbols):
+    """lammps-buck-intel_b200/integration/: the translation units a maintainer puts in place of the reference's
+    pair_buck_coul_long_intel.cpp / pppm_intel.cpp.  They implement the classes that the reference's OWN headers declare
+    (pair_buck_coul_long_intel.h, pppm_intel.h, included unchanged from /root/reference) through the C ABI, against the
+    stand-ins of the stock LAMMPS headers that the reference's own sources compile against (oracle/ref_shim): g++ -Wall
+    accepts them, every member the header declares is defined, and the only undefined b200md symbols are C-ABI entries
+    of include/b200md.h"""
+    root = os.path.dirname(pkg.HERE)
+    obj = os.path.join(str(tmp_path), unit + ".o")
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-Wall", "-Werror", "-Wno-unknown-pragmas", "-DINTEL_VMASK", "-DINTEL_ALLOW_TABLE",
+           "-I", os.path.join(root, "oracle", "ref_shim"), "-I", "/root/reference", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(pkg.HERE, "integration"), "-c", os.path.join(pkg.HERE, "integration", unit), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    nm = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    defined = [l for l in nm.splitlines() if " T " in l]
+    undefined = [l.split()[-1] for l in nm.splitlines() if " U " in l and "b200" in l]
+    for sym in symbols:
+        assert any(sym in l for l in (defined if "::" in sym else nm.splitlines())), sym
+    header = open(os.path.join(root, "include", "b200md.h")).read()
+    for u in undefined:
+        assert u.startswith("b200md_") and (u + "(") in header or u.startswith("LAMMPS_NS::b200_"), u
+
+
 def test_driver_errors(pkg, W, tmp_path):
     bad = scripts.IN_BUCK.format(n=4, steps=1, thermo=0).replace("pair_coeff 1 1 1.0 0.2 -0.8", "")
     r = _run(pkg, ["-in", scripts.write(tmp_path, "in.bad", bad), "-sf", "intel", "-dry-run"])
