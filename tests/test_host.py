@@ -246,14 +246,24 @@ def test_styles_are_registered_like_the_reference_registers_them(pkg):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree is only mounted in the build container")
 @pytest.mark.parametrize("unit,symbols", [
+    ("pair_buck_intel.cpp", ["PairBuckIntel::init_style()", "PairBuckIntel::compute(int, int)", "b200md_pair_setup",
+                             "b200md_pair_compute"]),
+    ("pair_buck_coul_cut_intel.cpp", ["PairBuckCoulCutIntel::init_style()", "PairBuckCoulCutIntel::compute(int, int)",
+                                      "b200md_pair_setup", "b200md_pair_compute"]),
     ("pair_buck_coul_long_intel.cpp", ["PairBuckCoulLongIntel::init_style()", "PairBuckCoulLongIntel::compute(int, int)",
                                        "b200md_pair_setup", "b200md_pair_compute"]),
+    ("pair_buck_long_coul_long_intel.cpp", ["PairBuckLongCoulLongIntel::init_style()",
+                                            "PairBuckLongCoulLongIntel::compute(int, int)", "b200md_pair_setup",
+                                            "b200md_pair_compute"]),
+    ("pair_lj_long_coul_long_intel.cpp", ["PairLJLongCoulLongIntel::init_style()",
+                                          "PairLJLongCoulLongIntel::compute(int, int)", "b200md_pair_setup",
+                                          "b200md_pair_compute"]),
     ("pppm_intel.cpp", ["PPPMIntel::init()", "PPPMIntel::compute(int, int)", "PPPMIntel::brick2fft()", "b200md_pppm_setup",
                         "b200md_pppm_compute"])])
 def test_integration_binding_compiles_against_the_reference_header(pkg, tmp_path, unit, symbols):
-    """lammps-buck-intel_b200/integration/: the translation units a maintainer puts in place of the reference's
-    pair_buck_coul_long_intel.cpp / pppm_intel.cpp.  They implement the classes that the reference's OWN headers declare
-    (pair_buck_coul_long_intel.h, pppm_intel.h, included unchanged from /root/reference) through the C ABI, against the
+    """lammps-buck-intel_b200/integration/: the translation units a maintainer puts in place of the reference's five
+    pair_*_intel.cpp and pppm_intel.cpp.  They implement the classes that the reference's OWN headers declare (included
+    unchanged from /root/reference) through the C ABI, against the
     stand-ins of the stock LAMMPS headers that the reference's own sources compile against (oracle/ref_shim): g++ -Wall
     accepts them, every member the header declares is defined, and the only undefined b200md symbols are C-ABI entries
     of include/b200md.h"""
