@@ -53,3 +53,35 @@ def test_spce_system_replicates_the_fixture(W):
     assert len(s["x"]) == 36000 and s["units"] == "real"
     assert np.all(s["x"] >= s["boxlo"]) and np.all(s["x"] < s["boxhi"])
     assert abs(s["q"].sum()) < 1e-8
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/examples/equilibrated_data.hexane"), reason="reference tree not mounted")
+def test_data_hexane_fixture_is_the_reference_file():
+    """tests/golden/data_hexane.npz is examples/equilibrated_data.hexane (positions, velocities, types, molecule ids, box,
+    masses), re-parsed here"""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_data_hexane", os.path.join(here, "golden", "make_data_hexane.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    src = "/root/reference/examples/equilibrated_data.hexane"
+    d = m.parse(src)
+    d["v"] = m.velocities(src, len(d["x"]))
+    g = np.load(os.path.join(here, "golden", "data_hexane.npz"))
+    for k in ("x", "v", "type", "mol", "boxlo", "boxhi", "mass"):
+        assert np.array_equal(d[k], g[k]), k
+    assert len(g["x"]) == 6000 and not d["q"].any()
+
+
+def test_hexane_system(W):
+    """1 000 hexane molecules of six united atoms: CH3 (type 1) at both ends, four CH2 (type 2) between; wrapped into the box"""
+    s = W.hexane_system()
+    assert len(s["x"]) == 6000 and s["units"] == "real" and s["ntypes"] == 2
+    assert np.all(s["x"] >= s["boxlo"]) and np.all(s["x"] < s["boxhi"])
+    assert np.bincount(s["type"])[1:].tolist() == [2000, 4000]
+    mol, cnt = np.unique(s["mol"], return_counts=True)
+    assert len(mol) == 1000 and np.all(cnt == 6)
+    for m in mol[:50]:
+        assert np.bincount(s["type"][s["mol"] == m], minlength=3)[1:].tolist() == [2, 4]
+    co = W.coeffs_hexane()
+    assert co["A"][1, 2] == pytest.approx(np.sqrt(0.1744742 * 0.1147228)) and np.all(co["rho"][1:, 1:] == 3.97)
