@@ -33,6 +33,7 @@ struct orc_md {
   int nghost;
   double cutmax;
   bool built;
+  bool lost = false;   // an atom left the box by more than one period (the model blew up): stepping stops
 };
 
 namespace {
@@ -56,6 +57,12 @@ void pbc(orc_md *m) {
 void build(orc_md *m) {
   pbc(m);
   const int n = m->nlocal;
+  for (int i = 0; i < n && !m->lost; i++)
+    for (int d = 0; d < 3; d++) {
+      const double c = m->x[3 * (size_t)i + d];
+      if (!(c >= m->boxlo[d] && c < m->boxhi[d])) m->lost = true;   // also catches NaN
+    }
+  if (m->lost) return;
   const double cutneighmax = m->cutmax + m->skin;
   const int periodic[3] = {1, 1, 1};
   size_t cap = (size_t)n * 2 + 4096;
@@ -192,14 +199,14 @@ void orc_md_run(orc_md *m, int nsteps, int nthreads, double *timers, int *nbuild
   if (nthreads <= 0) nthreads = omp_get_max_threads();
   double tn = 0, tp = 0, tk = 0, tv = 0, tc = 0;
   int nb = 0;
-  if (!m->built) {
+  if (!m->built && !m->lost) {
     double t0 = now();
     build(m);
     nb++;
     tn += now() - t0;
-    forces(m, 0, 0, nthreads, nullptr, nullptr, nullptr, &tp, &tk);
+    if (!m->lost) forces(m, 0, 0, nthreads, nullptr, nullptr, nullptr, &tp, &tk);
   }
-  for (int s = 0; s < nsteps; s++) {
+  for (int s = 0; s < nsteps && !m->lost; s++) {
     double t0 = now();
     orc_nve_initial(m->nlocal, m->x.data(), m->v.data(), m->f.data(), m->dtfm.data(), m->dt);
     double t1 = now();
@@ -211,6 +218,7 @@ void orc_md_run(orc_md *m, int nsteps, int nthreads, double *timers, int *nbuild
       build(m);
       nb++;
       tn += now() - t1;
+      if (m->lost) break;
     } else {
       forward_comm(m);
       tc += now() - t1;
@@ -225,6 +233,8 @@ void orc_md_run(orc_md *m, int nsteps, int nthreads, double *timers, int *nbuild
   }
   if (nbuilds) *nbuilds += nb;
 }
+
+int orc_md_lost(const orc_md *m) { return m->lost ? 1 : 0; }
 
 void orc_md_get(orc_md *m, double *x, double *v, double *f) {
   if (x) std::copy(m->x.begin(), m->x.end(), x);

@@ -209,6 +209,8 @@ orc_md *orc_md_create(int nlocal, const double *x, const double *v, const double
 void orc_md_destroy(orc_md *m);
 /* runs nsteps velocity-Verlet steps; timers[8] accumulate seconds {neigh,pair,kspace,nve,comm,..} */
 void orc_md_run(orc_md *m, int nsteps, int nthreads, double *timers, int *nbuilds);
+/* 1 once an atom has left the box by more than one period (or is NaN): orc_md_run stops stepping instead of binning it */
+int orc_md_lost(const orc_md *m);
 void orc_md_get(orc_md *m, double *x, double *v, double *f);
 void orc_md_energy(orc_md *m, int nthreads, double *ev /*8*/, double *ekspace, double *ke);
 

@@ -533,6 +533,8 @@ class MD:
         timers = np.zeros(8)
         nb = C.c_int(0)
         lib().orc_md_run(self.h, C.c_int(nsteps), C.c_int(nthreads), _d(timers), C.byref(nb))
+        if lib().orc_md_lost(self.h):
+            raise RuntimeError("oracle MD: an atom left the box by more than one period (the model blew up)")
         return dict(neigh=timers[0], pair=timers[1], kspace=timers[2], nve=timers[3], comm=timers[4], nbuilds=nb.value)
 
     def get(self):

@@ -548,3 +548,18 @@ def test_slab_correction_known_answers(orc):
     xm[i, 2] -= d
     num = -(pp.compute(xp, q)[1] - pp.compute(xm, q)[1]) / (2 * d)
     assert abs(num - f3[i, 2]) < 5e-4 * np.abs(f3).max()
+
+
+def test_md_loop_stops_when_the_model_blows_up(orc, W):
+    """Buckingham's -C/r^6 wins over A exp(-r/rho) at short range: a system that is hot enough collapses, atoms fly out of
+    the box, and the oracle's MD loop reports it instead of binning coordinates that are out of range"""
+    s = W.aC_system(1)
+    u = W.UNITS["metal"]
+    co = W.coeffs_aC(8.0, 8.0)
+    P = orc.Params(orc.BUCK_COUL_LONG, 2, co["A"], co["rho"], co["C"], co["cut_lj"], co["cut_coul"], qqrd2e=u["qqrd2e"],
+                   g_ewald=0.3)
+    s["v"] = s["v"] * 6.0
+    pp = orc.PPPM(24, 24, 27, 5, 0.3, s["boxlo"], s["boxhi"], u["qqrd2e"])
+    md = orc.MD(s, P, pppm=pp, skin=0.3, every=1, delay=0, check=1, dt=0.002, ftm2v=u["ftm2v"])
+    with pytest.raises(RuntimeError, match="left the box"):
+        md.run(40, 1)
