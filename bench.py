@@ -26,8 +26,11 @@ kernel with >= 1 % of the step: live CUDA-event launch time, algorithmic bytes|f
 sample data.aC x 8^3, GPU path against the CPU oracle: forces, energies, pair set; at N > 1 the sample is decomposed over
 the N ranks, so the line proves the multi-GPU path too).
 
-`--impl reference` times the CPU restatement of the reference (oracle/; pinned bit for bit against the reference's own
-compiled loops, oracle/_ref) on the host cores, on a bounded sample of the same workload.
+`--impl reference` (and the `cpu_baseline` leg of the own arm) steps a bounded sample of the same workload on the host
+cores with every function the reference ships running from the reference's OWN translation units, compiled unchanged
+(oracle/_ref: PairBuckCoulLongIntel::compute, PPPMIntel::compute, FixNVEIntel), and the upstream pieces around them
+(neighbour list, ghosts, communication) from the oracle — tests/refmd.py; where oracle/_ref is missing, the oracle's
+restatement of the same loops (bit-identical to it) is timed instead.
 """
 import argparse
 import importlib
