@@ -19,6 +19,8 @@ void b200_positions_to_device(FixIntel *fix);
 // after a force contribution: atom->f += what the device added since the last call (b200md_atoms_download) — the
 // add_result_array of the reference
 void b200_forces_to_host(FixIntel *fix);
+// ~FixIntel: destroys the context of this fix
+void b200_release(FixIntel *fix);
 }  // namespace LAMMPS_NS
 
 #endif

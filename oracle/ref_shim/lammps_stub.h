@@ -205,6 +205,7 @@ class NeighList {
 class Neighbor {
  public:
   int ago = 0, oneatom = 2000, maxhead = 0;
+  int every = 1, delay = 10, dist_check = 1;   /* neigh_modify (stock defaults); read by the B200 binding only */
   double skin = 0.0;
   int nrequest = 0;
   NeighRequest **requests = nullptr;
@@ -226,6 +227,7 @@ class Domain {
   int triclinic = 0;
   double boxlo[3] = {0, 0, 0}, boxhi[3] = {1, 1, 1};
   double boxlo_lamda[3] = {0, 0, 0};
+  int periodicity[3] = {1, 1, 1};              /* read by the B200 binding only */
   double xprd = 1, yprd = 1, zprd = 1;
   double prd[3] = {1, 1, 1};
   void x2lamda(int) {}
