@@ -32,7 +32,7 @@ def main():
     rng = np.random.default_rng(5)
     dx = rng.uniform(-0.01, 0.01, (n, 3))
     nsteps = 3
-    xfin = s["x"] + (nsteps - 1) * dx
+    xfin = W.wrap(s["x"] + (nsteps - 1) * dx, s["boxlo"], s["boxhi"])   # the oracle bins wrapped positions; forces do not care
     worst = 0.0
     for table in (False, True):
         for use_grid in (True, False):
