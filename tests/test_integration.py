@@ -53,6 +53,6 @@ def test_integration_units_on_the_gpu():
     if not _have_lib():
         pytest.skip("oracle/_ref/libinteg.so: neither prebuilt nor buildable here")
     r = subprocess.run([sys.executable, os.path.join(HERE, "integration_check.py")], capture_output=True, text=True,
-                       timeout=300, cwd=ROOT)
+                       timeout=120, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "INTEGRATION OK" in r.stdout
