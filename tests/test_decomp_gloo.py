@@ -171,7 +171,8 @@ def _memcpy2d(dst, doff, dpitch, src, soff, spitch, width, height):
         dst[doff + r * dpitch: doff + r * dpitch + width] = src[soff + r * spitch: soff + r * spitch + width]
 
 
-@pytest.mark.parametrize("P,nx,ny,nz,npack", [(2, 6, 10, 24, 2), (3, 5, 10, 37, 2), (4, 4, 9, 48, 1), (8, 3, 13, 96, 2)])
+@pytest.mark.parametrize("P,nx,ny,nz,npack", [(2, 6, 10, 24, 2), (3, 5, 10, 37, 2), (4, 4, 9, 48, 1), (8, 3, 13, 96, 2),
+                                                (8, 7, 13, 96, 3), (4, 4, 10, 50, 3)])   # npack 3: the half-spectrum path (nx = sx)
 def test_peer_copy_plan_tiles_the_transposes(pkg, P, nx, ny, nz, npack):
     """the copy-engine transposes of csrc/pppm.cu (poisson_multi): the strided copies every rank issues into its peers'
     pencil / plane blocks — destination offset and pitch, source offset and pitch, width, height exactly as in the
