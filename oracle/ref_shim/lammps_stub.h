@@ -312,6 +312,7 @@ class Pair : public Pointers {
   int no_virial_fdotr = 0;
   int offset_flag = 0, mix_flag = 0;
   NeighList *list = nullptr;
+  virtual void *extract(const char *, int &dim) { dim = 0; return nullptr; }   /* stock Pair::extract (KSpace styles read cut-offs and coefficients through it) */
   /* Coulomb / dispersion tables (Pair::init_tables products; filled by the harness from host-built tables) */
   int ncoultablebits = 0, ncoulmask = 0, ncoulshiftbits = 0;
   double tabinner = 0, tabinnersq = 0;

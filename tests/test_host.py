@@ -259,10 +259,12 @@ def test_styles_are_registered_like_the_reference_registers_them(pkg):
                                           "PairLJLongCoulLongIntel::compute(int, int)", "b200md_pair_setup",
                                           "b200md_pair_compute"]),
     ("pppm_intel.cpp", ["PPPMIntel::init()", "PPPMIntel::compute(int, int)", "PPPMIntel::brick2fft()", "b200md_pppm_setup",
-                        "b200md_pppm_compute"])])
+                        "b200md_pppm_compute"]),
+    ("pppm_disp_intel.cpp", ["PPPMDispIntel::init()", "PPPMDispIntel::compute(int, int)", "b200md_pppm_setup",
+                             "b200md_pppm_compute"])])
 def test_integration_binding_compiles_against_the_reference_header(pkg, tmp_path, unit, symbols):
     """lammps-buck-intel_b200/integration/: the translation units a maintainer puts in place of the reference's five
-    pair_*_intel.cpp and pppm_intel.cpp.  They implement the classes that the reference's OWN headers declare (included
+    pair_*_intel.cpp, pppm_intel.cpp and pppm_disp_intel.cpp.  They implement the classes that the reference's OWN headers declare (included
     unchanged from /root/reference) through the C ABI, against the
     stand-ins of the stock LAMMPS headers that the reference's own sources compile against (oracle/ref_shim): g++ -Wall
     accepts them, every member the header declares is defined, and the only undefined b200md symbols are C-ABI entries

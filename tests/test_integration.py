@@ -35,6 +35,7 @@ def test_binding_chain_links_loads_and_fails_loudly_without_a_gpu(pkg, W, orc):
                 "PairLJLongCoulLongIntel"):
         assert " T LAMMPS_NS::%s::compute(int, int)" % cls in nm and " T LAMMPS_NS::%s::init_style()" % cls in nm, cls
     assert " T LAMMPS_NS::PPPMIntel::compute(int, int)" in nm and " T LAMMPS_NS::b200_positions_to_device" in nm
+    assert " T LAMMPS_NS::PPPMDispIntel::compute(int, int)" in nm and " T LAMMPS_NS::PPPMDispIntel::init()" in nm
     und = subprocess.run(["ldd", "-r", integ.LIB], capture_output=True, text=True)
     assert "undefined symbol" not in und.stdout + und.stderr
     s = W.aC_system(1)
